@@ -1,0 +1,1343 @@
+// ht2_core.h -- per-read HISAT2 alignment state machine (host+device).
+//
+// This is the B200 re-implementation of the reference's per-read hot path
+// HI_Aligner::go (hi_aligner.h:4048) and everything below it, written as a
+// self-contained, allocation-free state machine over a fixed-size per-read
+// workspace so that one GPU thread can run one read (pair) to completion.
+// Every function cites the reference lines whose behaviour it reproduces;
+// results (the ordered list of reported alignments and the RNG state) must be
+// identical to the reference's.
+//
+// The same source compiles for the device (the product) and for the host
+// (tests/hostsim only: used to debug parity against oracle/_ref on machines
+// without a GPU; the shipped library never runs it).
+#ifndef HT2_CORE_H_
+#define HT2_CORE_H_
+
+#include "ht2_image.h"
+#include "ht2_fm.h"
+#include "ht2_params.h"
+
+#ifndef HT2_MAX_RDLEN
+#define HT2_MAX_RDLEN 256
+#endif
+#define HT2_MAX_EDITS 32
+#define HT2_MAX_PHITS 28
+#define HT2_MAX_GHITS 24
+#define HT2_POOL 80
+#define HT2_MAX_SEARCHED 256
+#define HT2_MAX_RES 24
+#define HT2_MAX_PAIRS 48
+#define HT2_MAX_COORDS 24
+#define HT2_MAX_DEPTH 128
+#define HT2_REFBUF (HT2_MAX_RDLEN + 64)
+
+#define HT2_MIN_I64 ((int64_t)0x8000000000000000ll)
+#define HT2_MIN_SCORE (HT2_MIN_I64 / 2)   /* getMinScore(), aln_sink.h:34 */
+
+// error bits (per read); any bit set => results for the read are unreliable
+#define HT2_ERR_EDITS     1u
+#define HT2_ERR_PHITS     2u
+#define HT2_ERR_GHITS     4u
+#define HT2_ERR_POOL      8u
+#define HT2_ERR_SEARCHED 16u
+#define HT2_ERR_RES      32u
+#define HT2_ERR_PAIRS    64u
+#define HT2_ERR_COORDS  128u
+#define HT2_ERR_RDLEN   256u
+#define HT2_ERR_GRAPH   512u
+
+enum { HT2_EDIT_READ_GAP = 1, HT2_EDIT_REF_GAP, HT2_EDIT_MM, HT2_EDIT_SNP, HT2_EDIT_SPL };
+enum { HT2_CANDIDATE_HIT = 1, HT2_PSEUDOGENE_HIT, HT2_ANCHOR_HIT }; // hi_aligner.h:96-100
+
+struct Ht2Edit {          // edit.h:41-330
+    uint32_t pos;
+    uint8_t  chr;         // reference char ('A','C','G','T','N','-')
+    uint8_t  qchr;        // read char
+    uint8_t  type;
+    uint8_t  pad;
+    uint32_t snpID;
+};
+
+struct Ht2Hit {           // GenomeHit, hi_aligner.h:431-1369
+    uint32_t fw;
+    uint32_t rdoff, len, trim5, trim3;
+    uint32_t tidx, toff, joinedOff;
+    int64_t  score;
+    uint32_t hitcount;
+    uint32_t nedits;
+    Ht2Edit  edits[HT2_MAX_EDITS];
+};
+
+struct Ht2BwtHit {        // BWTHit, hi_aligner.h:108-208
+    uint32_t top, bot, node_top, node_bot;
+    uint32_t bwoff, len;
+    uint8_t  hit_type, hasCoords, pad0, pad1;
+};
+
+struct Ht2ReadHits {      // ReadBWTHit, hi_aligner.h:216-389
+    uint32_t len, cur, done;
+    uint32_t numPartialSearch, numUniqueSearch;
+    uint32_t nhits;
+    Ht2BwtHit hits[HT2_MAX_PHITS];
+};
+
+struct Ht2Coord {         // Coord, ref_coord.h:35
+    uint32_t ref;
+    uint32_t off;
+    uint32_t fw;
+    uint32_t joinedOff;
+};
+
+// One reported alignment == the fields reportHit hands to AlnRes::init
+// (hi_aligner.h:6129-6166; AlnRes::setShape aligner_result.cpp:77-132).
+struct Ht2Res {
+    uint32_t tidx, toff;
+    uint32_t fw;
+    uint32_t rdlen;
+    int64_t  score;
+    uint32_t trim5p, trim3p;  // 5'/3' soft trimming in read orientation
+    uint32_t rfextent;        // # reference chars covered
+    uint32_t nedits;
+    Ht2Edit  edits[HT2_MAX_EDITS]; // AlnRes::ned(): 5'->3', relative to trim5p
+};
+
+struct Ht2Read {
+    uint32_t len;
+    uint8_t  seq[2][HT2_MAX_RDLEN];   // [0]=fw, [1]=revcomp; codes 0..4
+    uint8_t  qual[2][HT2_MAX_RDLEN];  // [0]=fw, [1]=reversed; raw ASCII
+};
+
+struct Ht2Rng {           // RandomSource, random_source.h:30-110
+    uint32_t last;
+    HT2_HD void init(uint32_t seed) { last = seed; }
+    HT2_HD uint32_t nextU32() {
+        uint32_t ret;
+        last = 1664525u * last + 1013904223u;
+        ret = last >> 16;
+        last = 1664525u * last + 1013904223u;
+        ret ^= last;
+        return ret;
+    }
+};
+
+// Per-read (pair) workspace.  One per in-flight GPU thread.
+struct Ht2Work {
+    Ht2Read     rd[2];
+    Ht2ReadHits hits[2][2];                 // [mate][fw=0/rc=1]
+    Ht2Hit      genomeHits[HT2_MAX_GHITS];  // _genomeHits
+    uint8_t     genomeHitsDone[HT2_MAX_GHITS];
+    uint32_t    nGenomeHits;
+    Ht2Hit      pool[HT2_POOL];             // GenomeHit temporaries (stack)
+    uint32_t    poolTop;
+    Ht2Hit      searched[2][HT2_MAX_SEARCHED]; // _hits_searched
+    uint32_t    nSearched[2];
+    Ht2Res      res[2][HT2_MAX_RES];        // rs1u_/rs2u_ of AlnSinkWrap
+    uint32_t    nRes[2];
+    uint16_t    pairs[HT2_MAX_PAIRS][2];    // rs1_/rs2_ as indexes into res
+    uint32_t    nPairs;
+    // AlnSinkWrap best-score tracking (aln_sink.h:2600-2655)
+    int64_t     bestPair, best2Pair, bestUnp[2], best2Unp[2];
+    // ReportingState (aln_sink.cpp:33-340), reduced to what the path reads back
+    uint32_t    nconcord, nunpair[2];
+    uint32_t    doneConcord, doneUnpair[2], stDone;
+    int64_t     concordBest;
+    uint32_t    concordInspected[2];        // _concordantIdxInspected
+    Ht2Coord    coords[HT2_MAX_COORDS];     // BWTHit::_coords scratch
+    uint32_t    nCoords;
+    uint8_t     refbuf[HT2_REFBUF + 16];
+    uint8_t     refbuf2[HT2_REFBUF + 16];
+    int64_t     tscores[HT2_MAX_RDLEN];
+    int64_t     tscores2[HT2_MAX_RDLEN];
+    Ht2Rng      rnd;
+    uint32_t    err;
+    // work counters (HIMetrics hi_aligner.h:3897 + roofline accounting)
+    uint32_t    localindexatts;
+    uint32_t    maxLocalindexatts;
+    uint32_t    nLF;      // LF steps (boundary ranks) executed
+    uint32_t    nSides;   // sides touched
+};
+
+// ------------------------------------------------------------------------
+// Scoring helpers (scoring.h:259-318, 96-130)
+// ------------------------------------------------------------------------
+HT2_HD int ht2_mmpen(const Ht2Params& P, int q) {
+    if (P.mmcostConstant) return P.mmpMax;
+    if (q < 0) q = 0;
+    int ii = q < 40 ? q : 40;
+    float frac = (float)ii / 40.0f;
+    return P.mmpMin + (int)(frac * (float)(P.mmpMax - P.mmpMin));
+}
+// Scoring::score(rdc, refm, q)
+HT2_HD int ht2_score(const Ht2Params& P, int rdc, int refm, int q) {
+    if (rdc > 3 || refm > 15) return -P.npen;
+    if ((refm & (1 << rdc)) != 0) return 0;
+    return -ht2_mmpen(P, q);
+}
+// Scoring::sc(q) soft-clip penalty (scoring.h:312-318)
+HT2_HD int ht2_scpen(const Ht2Params& P, int q) {
+    if (q <= 33) return P.scpMin;
+    q -= 33;
+    if (q > 40) q = 40;
+    return (int)(((float)q / 40.0f) * (float)(P.scpMax - P.scpMin) + (float)P.scpMin);
+}
+HT2_HD int ht2_asc2code(uint8_t ch) { // dna2col[ch]-'0'
+    switch (ch) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 4; }
+}
+HT2_HD int ht2_asc2mask(uint8_t ch) { // asc2dnamask[ch]
+    switch (ch) { case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8; case 'N': return 15; default: return 0; }
+}
+HT2_HD uint8_t ht2_code2asc(int c) { return (uint8_t)("ACGTN"[c]); }
+// Scoring::maxReadGaps / maxRefGaps (scoring.cpp:42-98); match bonus is 0.
+HT2_HD int ht2_max_gaps(int64_t minsc, int open, int ext) {
+    int64_t sc = 0;
+    bool first = true;
+    int num = 0;
+    while (sc >= minsc) {
+        if (first) { first = false; sc -= open; }
+        else sc -= ext;
+        num++;
+    }
+    return num - 1;
+}
+
+// ------------------------------------------------------------------------
+// The aligner
+// ------------------------------------------------------------------------
+struct Ht2Aligner {
+    const uint8_t*        blob;
+    const Ht2ImageHeader* H;
+    Ht2Fm<uint32_t>       gfm;
+    const Ht2Params*      P;
+    Ht2Work*              W;
+    bool     paired;
+    bool     rightendonly;
+    bool     nofw[2], norc[2];
+    int64_t  minsc[2];
+
+    HT2_HD void bind(const uint8_t* blob_, const Ht2Params* P_, Ht2Work* W_) {
+        blob = blob_;
+        H = (const Ht2ImageHeader*)blob_;
+        gfm.init(blob_, &H->global);
+        P = P_;
+        W = W_;
+    }
+
+    // ---- edits / hits ---------------------------------------------------
+    HT2_HD static void copyHit(Ht2Hit& d, const Ht2Hit& s) {
+        d.fw = s.fw; d.rdoff = s.rdoff; d.len = s.len; d.trim5 = s.trim5; d.trim3 = s.trim3;
+        d.tidx = s.tidx; d.toff = s.toff; d.joinedOff = s.joinedOff; d.score = s.score;
+        d.hitcount = 1; // GenomeHit::init resets _hitcount (hi_aligner.h:569)
+        d.nedits = s.nedits;
+        for (uint32_t i = 0; i < s.nedits; i++) d.edits[i] = s.edits[i];
+    }
+    HT2_HD static void initHit(Ht2Hit& h, bool fw, uint32_t rdoff, uint32_t len, uint32_t trim5, uint32_t trim3,
+                               uint32_t tidx, uint32_t toff, uint32_t joinedOff) {
+        h.fw = fw ? 1 : 0; h.rdoff = rdoff; h.len = len; h.trim5 = trim5; h.trim3 = trim3;
+        h.tidx = tidx; h.toff = toff; h.joinedOff = joinedOff; h.score = 0; h.hitcount = 1; h.nedits = 0;
+    }
+    HT2_HD static Ht2Edit mkEdit(uint32_t pos, uint8_t chr, uint8_t qchr, uint8_t type) {
+        Ht2Edit e; e.pos = pos; e.chr = chr; e.qchr = qchr; e.type = type; e.pad = 0; e.snpID = HT2_IDX_MAX32; return e;
+    }
+    HT2_HD bool pushEdit(Ht2Hit& h, const Ht2Edit& e) {
+        if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
+        h.edits[h.nedits++] = e; return true;
+    }
+    HT2_HD bool insertEditFront(Ht2Hit& h, const Ht2Edit& e) {
+        if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
+        for (uint32_t i = h.nedits; i > 0; i--) h.edits[i] = h.edits[i - 1];
+        h.edits[0] = e; h.nedits++; return true;
+    }
+    HT2_HD static bool editEq(const Ht2Edit& a, const Ht2Edit& b) { // Edit::operator== (edit.h)
+        if (a.type != b.type) return false;
+        if (a.pos != b.pos) return false;
+        return a.chr == b.chr && a.qchr == b.qchr;
+    }
+    HT2_HD static bool isGapOrSnp(const Ht2Edit& e) {
+        return e.type == HT2_EDIT_SPL || e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_REF_GAP ||
+               (e.type == HT2_EDIT_MM && e.snpID != HT2_IDX_MAX32);
+    }
+    // GenomeHit::operator== (hi_aligner.h:1156-1183)
+    HT2_HD static bool hitEq(const Ht2Hit& a, const Ht2Hit& b) {
+        if (a.fw != b.fw || a.rdoff != b.rdoff || a.len != b.len || a.tidx != b.tidx || a.toff != b.toff ||
+            a.trim5 != b.trim5 || a.trim3 != b.trim3) return false;
+        if (a.nedits != b.nedits) return false;
+        for (uint32_t i = 0; i < a.nedits; i++) {
+            const Ht2Edit& e = a.edits[i]; const Ht2Edit& oe = b.edits[i];
+            if (e.type == HT2_EDIT_READ_GAP) { if (oe.type != HT2_EDIT_READ_GAP) return false; }
+            else if (e.type == HT2_EDIT_REF_GAP) { if (oe.type != HT2_EDIT_REF_GAP) return false; }
+            else if (!editEq(e, oe)) return false;
+        }
+        return true;
+    }
+    // Edit::invertPoss (edit.cpp:70-111), sort=false
+    HT2_HD static void invertPoss(Ht2Edit* ed, uint32_t n, uint32_t sz) {
+        for (uint32_t i = 0; i < n / 2; i++) { Ht2Edit t = ed[i]; ed[i] = ed[n - i - 1]; ed[n - i - 1] = t; }
+        for (uint32_t i = 0; i < n; i++) {
+            if (ed[i].type == HT2_EDIT_READ_GAP || ed[i].type == HT2_EDIT_SPL) ed[i].pos = (uint32_t)(sz - ed[i].pos);
+            else ed[i].pos = (uint32_t)(sz - ed[i].pos - 1);
+        }
+    }
+    HT2_HD Ht2Hit* poolAlloc() {
+        if (W->poolTop >= HT2_POOL) { W->err |= HT2_ERR_POOL; return &W->pool[HT2_POOL - 1]; }
+        return &W->pool[W->poolTop++];
+    }
+
+    // GenomeHit::getLeft (hi_aligner.h:919-957)
+    HT2_HD void getLeft(const Ht2Hit& h, uint32_t& rdoff, uint32_t& len, uint32_t& toff, int64_t* score, uint32_t rdi) const {
+        toff = h.toff; rdoff = h.rdoff; len = h.len;
+        if (score) *score = 0;
+        const uint8_t* qual = W->rd[rdi].qual[h.fw ? 0 : 1];
+        for (uint32_t i = 0; i < h.nedits; i++) {
+            const Ht2Edit& e = h.edits[i];
+            if (isGapOrSnp(e)) { len = e.pos; break; }
+            if (score && e.type == HT2_EDIT_MM && e.snpID == HT2_IDX_MAX32)
+                *score += ht2_score(*P, ht2_asc2code(e.qchr), ht2_asc2mask(e.chr), (int)qual[h.rdoff + e.pos] - 33);
+        }
+    }
+    // GenomeHit::getRightOff (hi_aligner.h:1020-1035)
+    HT2_HD static uint32_t getRightOff(const Ht2Hit& h) {
+        uint32_t toff = h.toff + h.len;
+        for (uint32_t i = 0; i < h.nedits; i++) {
+            if (h.edits[i].type == HT2_EDIT_READ_GAP) toff++;
+            else if (h.edits[i].type == HT2_EDIT_REF_GAP) toff--;
+        }
+        return toff;
+    }
+    // GenomeHit::getRight (hi_aligner.h:962-1015)
+    HT2_HD void getRight(const Ht2Hit& h, uint32_t& rdoff, uint32_t& len, uint32_t& toff, int64_t* score, uint32_t rdi) const {
+        toff = h.toff; rdoff = h.rdoff; len = h.len;
+        if (score) *score = 0;
+        if (h.nedits == 0) return;
+        const uint8_t* qual = W->rd[rdi].qual[h.fw ? 0 : 1];
+        for (int i = (int)h.nedits - 1; i >= 0; i--) {
+            const Ht2Edit& e = h.edits[i];
+            if (isGapOrSnp(e)) {
+                rdoff = h.rdoff + e.pos;
+                len = h.len - e.pos;
+                if (e.type == HT2_EDIT_REF_GAP) { rdoff++; len--; }
+                else if (e.type == HT2_EDIT_MM) { rdoff++; len--; }
+                toff = getRightOff(h) - len;
+                break;
+            }
+            if (score && e.type == HT2_EDIT_MM && e.snpID == HT2_IDX_MAX32)
+                *score += ht2_score(*P, ht2_asc2code(e.qchr), ht2_asc2mask(e.chr), (int)qual[h.rdoff + e.pos] - 33);
+        }
+    }
+
+    // GenomeHit::calculateScore (hi_aligner.h:3711-3891), no splice edits.
+    HT2_HD int64_t calculateScore(Ht2Hit& h, uint32_t rdi) const {
+        int64_t score = 0;
+        const uint8_t* qual = W->rd[rdi].qual[h.fw ? 0 : 1];
+        for (uint32_t i = 0; i < h.nedits; i++) {
+            const Ht2Edit& e = h.edits[i];
+            if (e.type == HT2_EDIT_MM) {
+                if (e.snpID == HT2_IDX_MAX32)
+                    score += ht2_score(*P, ht2_asc2code(e.qchr), ht2_asc2mask(e.chr), (int)qual[h.rdoff + e.pos] - 33);
+            } else if (e.type == HT2_EDIT_READ_GAP) {
+                bool open = true;
+                if (i > 0 && h.edits[i - 1].type == HT2_EDIT_READ_GAP && h.edits[i - 1].pos == e.pos) open = false;
+                if (e.snpID == HT2_IDX_MAX32) score -= open ? (P->rdGapConst + P->rdGapLinear) : P->rdGapLinear;
+            } else if (e.type == HT2_EDIT_REF_GAP) {
+                bool open = true;
+                if (i > 0 && h.edits[i - 1].type == HT2_EDIT_REF_GAP && h.edits[i - 1].pos + 1 == e.pos) open = false;
+                if (e.snpID == HT2_IDX_MAX32) score -= open ? (P->rfGapConst + P->rfGapLinear) : P->rfGapLinear;
+            }
+        }
+        // soft-clip penalty indexes qual[i], not the clipped position (hi_aligner.h:3872-3878)
+        for (uint32_t i = 0; i < h.trim5; i++) score -= ht2_scpen(*P, qual[i]);
+        for (uint32_t i = 0; i < h.trim3; i++) score -= ht2_scpen(*P, qual[i]);
+        h.score = score;
+        return score;
+    }
+
+    // ---- 2-bit reference (reference.cpp:396-430, 486-640) ------------------
+    HT2_HD uint32_t refLen(uint32_t tidx) const { return ((const uint32_t*)(blob + H->o_refLens))[tidx]; }
+    // dest[i] = base at toff+i for i<count; 4 inside N gaps / past the end.
+    HT2_HD void getStretch(uint8_t* dest, uint32_t tidx, uint32_t toff, uint32_t count) const {
+        const Ht2RefRecord* recs = (const Ht2RefRecord*)(blob + H->o_recs);
+        const uint32_t* recOffs = (const uint32_t*)(blob + H->o_refRecOffs);
+        const uint64_t* refOffs = (const uint64_t*)(blob + H->o_refOffs);
+        const uint8_t* buf = blob + H->o_refBuf;
+        uint32_t reci = recOffs[tidx], recf = recOffs[tidx + 1];
+        uint64_t bufOff = refOffs[tidx];
+        uint64_t off = 0, t = toff;
+        uint32_t cur = 0;
+        for (uint32_t i = reci; i < recf && count > 0; i++) {
+            off += recs[i].off;
+            while (t < off && count > 0) { dest[cur++] = 4; t++; count--; }
+            if (count == 0) break;
+            if (t < off + recs[i].len) bufOff += (t - off);
+            else bufOff += recs[i].len;
+            off += recs[i].len;
+            while (t < off && count > 0) {
+                dest[cur++] = (buf[bufOff >> 2] >> ((bufOff & 3) << 1)) & 3;
+                bufOff++; t++; count--;
+            }
+        }
+        while (count > 0) { dest[cur++] = 4; count--; }
+    }
+    HT2_HD int getBase(uint32_t tidx, uint32_t toff) const {
+        uint8_t b; getStretch(&b, tidx, toff, 1); return b;
+    }
+
+    // ---- joined <-> text coordinates (gfm.h:5527-5600) ---------------------
+    template <typename IT>
+    HT2_HD bool joinedToTextOff(const Ht2Fm<IT>& fm, uint32_t qlen, uint32_t off, uint32_t& tidx, uint32_t& textoff,
+                                bool rejectStraddle, bool& straddled) const {
+        const uint32_t nFrag = fm.g->nFrag;
+        uint32_t top = 0, bot = nFrag;
+        uint32_t elt = (uint32_t)Ht2Fm<IT>::imax();
+        while (true) {
+            uint32_t oldelt = elt;
+            elt = top + ((bot - top) >> 1);
+            if (oldelt == elt) { tidx = HT2_IDX_MAX32; return false; }
+            uint32_t lower = fm.rstarts[elt * 3];
+            uint32_t upper = (elt == nFrag - 1) ? fm.g->len : fm.rstarts[(elt + 1) * 3];
+            if (lower <= off) {
+                if (upper > off) {
+                    if (off + qlen > upper) {
+                        straddled = true;
+                        if (rejectStraddle) { tidx = HT2_IDX_MAX32; return false; }
+                    }
+                    tidx = fm.rstarts[elt * 3 + 1];
+                    uint32_t fragoff = off - fm.rstarts[elt * 3];
+                    textoff = (uint32_t)(IT)(fragoff + fm.rstarts[elt * 3 + 2]);
+                    break;
+                } else top = elt;
+            } else bot = elt;
+        }
+        return true;
+    }
+
+    // ---- one backward-search step --------------------------------------
+    // Returns new [top,bot) and node range for extending with base c
+    // (partialSearch inner step, hi_aligner.h:6466-6484; mapLF gfm.h:3739,
+    // mapGLF1 gfm.h:3957, mapLF1 gfm.h:3889).  Linear indexes only here;
+    // graph indexes are dispatched in lfStepGraph.
+    template <typename IT>
+    HT2_HD void lfStep(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c,
+                       uint32_t& ntop, uint32_t& nbot, uint32_t& nntop, uint32_t& nnbot) {
+        if (bot - top != 1) {
+            W->nLF += 2;
+            ntop = ht2_lf(fm, top, c);
+            nbot = ht2_lf(fm, bot, c);
+            nntop = ntop; nnbot = nbot;
+        } else {
+            W->nLF += 1;
+            if (ht2_rowL(fm, top) != c || ht2_is_zoff(fm, top)) { ntop = nbot = nntop = nnbot = 0; return; }
+            ntop = ht2_lf(fm, top, c);
+            nbot = (uint32_t)(IT)(ntop + 1);
+            nntop = ntop; nnbot = nbot;
+        }
+    }
+
+    // HI_Aligner::partialSearch (hi_aligner.h:6361-6600).  Returns stop
+    // flags through pseudogeneStop/anchorStop like the reference.
+    HT2_HD void partialSearch(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
+        bool pseudogeneStop_ = pseudogeneStop, anchorStop_ = anchorStop;
+        pseudogeneStop = anchorStop = false;
+        Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
+        const uint32_t ftabLen = gfm.g->ftabChars;
+        const uint32_t len = W->rd[rdi].len;
+        const uint8_t* seq = W->rd[rdi].seq[fw ? 0 : 1];
+        const uint32_t minK = P->minK;
+        hit.numPartialSearch++;
+        uint32_t offset = hit.cur;
+        uint32_t dep = offset;
+        uint32_t left = len - dep;
+        if (hit.nhits >= HT2_MAX_PHITS) { W->err |= HT2_ERR_PHITS; hit.cur = len; hit.done = 1; return; }
+        Ht2BwtHit& ph = hit.hits[hit.nhits];
+        ph.top = ph.bot = ph.node_top = ph.node_bot = HT2_IDX_MAX32;
+        ph.bwoff = offset; ph.hit_type = HT2_CANDIDATE_HIT; ph.hasCoords = 0;
+        if (left < ftabLen + 1) {
+            hit.cur = len;
+            ph.len = hit.cur - offset; hit.nhits++;
+            hit.done = 1;
+            return;
+        }
+        for (uint32_t i = 0; i < ftabLen; i++) {
+            int c = seq[len - dep - 1 - i];
+            if (c > 3) {
+                hit.cur += (i + 1);
+                ph.len = hit.cur - offset; hit.nhits++;
+                if (hit.cur >= len) hit.done = 1;
+                return;
+            }
+        }
+        uint32_t top = 0, bot = 0, ntop = 0, nbot = 0;
+        ht2_ftab_lohi(gfm, seq, len - dep - ftabLen, top, bot);
+        dep += ftabLen;
+        if (top >= bot) {
+            hit.cur = dep;
+            ph.len = hit.cur - offset; hit.nhits++;
+            if (hit.cur >= len) hit.done = 1;
+            return;
+        }
+        uint32_t same_range = 0, similar_range = 0;
+        uint32_t khits5 = P->khits < 5 ? P->khits : 5;
+        // node_range starts as (0,0) in the reference (hi_aligner.h:6396)
+        while (dep < len) {
+            int c = seq[len - dep - 1];
+            uint32_t ttop = 0, tbot = 0, tntop = 0, tnbot = 0;
+            if (c <= 3) lfStep(gfm, top, bot, c, ttop, tbot, tntop, tnbot);
+            if (ttop >= tbot) break;
+            uint32_t nw = tnbot - tntop, ow = nbot - ntop;
+            if (pseudogeneStop_) {
+                if (nw < ow && ow <= khits5) {
+                    if (dep - offset >= minK + 6 && similar_range >= 5) {
+                        hit.numUniqueSearch++;
+                        pseudogeneStop = true;
+                        break;
+                    }
+                }
+                if (nw != 1) {
+                    if (nw + 2 >= ow) similar_range++;
+                    else if (nw + 4 < ow) similar_range = 0;
+                } else pseudogeneStop_ = false;
+            }
+            if (anchorStop_) {
+                if (nw != 1 && ow == nw) {
+                    same_range++;
+                    if (same_range >= 5) anchorStop_ = false;
+                } else same_range = 0;
+                if (dep - offset >= minK + 8 && nw >= 4) anchorStop_ = false;
+            }
+            top = ttop; bot = tbot; ntop = tntop; nbot = tnbot;
+            dep++;
+            if (anchorStop_) {
+                if (dep - offset >= minK + 12 && bot - top == 1) {
+                    hit.numUniqueSearch++;
+                    anchorStop = true;
+                    break;
+                }
+            }
+        }
+        if (top < bot) {
+            uint8_t hit_type = HT2_CANDIDATE_HIT;
+            if (anchorStop) hit_type = HT2_ANCHOR_HIT;
+            else if (pseudogeneStop) hit_type = HT2_PSEUDOGENE_HIT;
+            bool report = ntop < nbot;
+            if (nbot - ntop < bot - top) report = false; // no in-edge list on linear indexes
+            if (report) { ph.top = top; ph.bot = bot; ph.node_top = ntop; ph.node_bot = nbot; }
+            ph.len = dep - offset;
+            ph.hit_type = hit_type;
+            hit.nhits++;
+            hit.cur = dep;
+            if (hit.cur >= len) {
+                if (hit_type == HT2_CANDIDATE_HIT) hit.numUniqueSearch++;
+                hit.done = 1;
+            }
+        }
+    }
+
+    // HI_Aligner::globalGFMSearch / localGFMSearch (hi_aligner.h:6606-6744,
+    // 6751-6892) share one body; 'local' picks minUniqueLen/maxHitLen/maxHits.
+    template <typename IT>
+    HT2_HD uint32_t gfmSearch(const Ht2Fm<IT>& fm, uint32_t rdi, bool fw, uint32_t rdoff, uint32_t& hitlen,
+                              uint32_t& top, uint32_t& bot, uint32_t& node_top, uint32_t& node_bot,
+                              bool& uniqueStop, uint32_t minUniqueLen, uint32_t maxHitLen, uint32_t maxHits, bool local) {
+        bool uniqueStop_ = uniqueStop;
+        uniqueStop = false;
+        const uint32_t ftabLen = fm.g->ftabChars;
+        const uint32_t len = W->rd[rdi].len;
+        const uint8_t* seq = W->rd[rdi].seq[fw ? 0 : 1];
+        uint32_t offset = len - rdoff - 1;
+        uint32_t dep = offset;
+        if (local) top = bot = node_top = node_bot = 0;
+        uint32_t left = len - dep;
+        if (left < ftabLen + 1) { hitlen = left; return 0; }
+        for (uint32_t i = 0; i < ftabLen; i++) {
+            int c = seq[len - dep - 1 - i];
+            if (c > 3) { hitlen = i + 1; return 0; }
+        }
+        uint32_t rtop = 0, rbot = 0, ntop = 0, nbot = 0;
+        ht2_ftab_lohi(fm, seq, len - dep - ftabLen, rtop, rbot);
+        dep += ftabLen;
+        if (rtop >= rbot) { hitlen = ftabLen; return 0; }
+        while (dep < len) {
+            int c = seq[len - dep - 1];
+            uint32_t ttop = 0, tbot = 0, tntop = 0, tnbot = 0;
+            if (c <= 3) lfStep(fm, rtop, rbot, c, ttop, tbot, tntop, tnbot);
+            if (ttop >= tbot) break;
+            rtop = ttop; rbot = tbot; ntop = tntop; nbot = tnbot;
+            dep++;
+            if (uniqueStop_) {
+                if (rbot - rtop == 1 && dep - offset >= minUniqueLen) { uniqueStop = true; break; }
+            }
+            if (local && dep - offset >= maxHitLen) break;
+        }
+        uint32_t nelt = 0;
+        if (ntop < nbot && nbot - ntop <= maxHits) {
+            top = rtop; bot = rbot; node_top = ntop; node_bot = nbot;
+            nelt = nbot - ntop;
+            hitlen = dep - offset;
+        }
+        return nelt;
+    }
+
+    // ---- SA-offset resolution (group_walk.h GWState::init/advance,
+    // GroupWalk2S::advanceElement :1491; gfm.h tryOffset :2719) -------------
+    // Walk row left until a sampled row (or '$') is met; joined offset =
+    // sample + #steps.  Linear indexes: node == row.
+    template <typename IT>
+    HT2_HD uint32_t resolveRow(const Ht2Fm<IT>& fm, uint32_t row) {
+        uint32_t steps = 0;
+        while (true) {
+            if (ht2_is_zoff(fm, row)) return (uint32_t)(IT)(0 + steps);
+            if ((row & fm.g->offMask) == row) {
+                return (uint32_t)(IT)(fm.offs[row >> fm.g->offRate] + steps);
+            }
+            int c = ht2_rowL(fm, row);
+            row = ht2_lf(fm, row, c);
+            W->nLF++;
+            steps++;
+        }
+    }
+
+    // HI_Aligner::getGenomeCoords (hi_aligner.h:5774-5855); appends to W->coords.
+    HT2_HD bool getGenomeCoords(uint32_t top, uint32_t bot, uint32_t node_top, uint32_t node_bot, bool fw,
+                                uint32_t maxelt, uint32_t rdlen, bool rejectStraddle, bool& straddled) {
+        straddled = false;
+        uint32_t nelt = node_bot - node_top;
+        if (nelt > maxelt) nelt = maxelt;
+        for (uint32_t i = 0; i < nelt; i++) {
+            uint32_t joff = resolveRow(gfm, top + i);
+            uint32_t tidx = 0, toff = 0;
+            bool straddled2 = false;
+            joinedToTextOff(gfm, rdlen, joff, tidx, toff, rejectStraddle, straddled2);
+            straddled |= straddled2;
+            if (tidx == HT2_IDX_MAX32) return false;
+            if (W->nCoords >= HT2_MAX_COORDS) { W->err |= HT2_ERR_COORDS; return false; }
+            Ht2Coord& c = W->coords[W->nCoords++];
+            c.ref = straddled2 ? HT2_IDX_MAX32 : tidx;
+            c.off = toff; c.fw = fw ? 1 : 0; c.joinedOff = joff;
+        }
+        return true;
+    }
+
+    // HI_Aligner::getGenomeCoords_local (hi_aligner.h:5861-5941); fills out[].
+    HT2_HD bool getGenomeCoordsLocal(const Ht2Fm<uint16_t>& lfm, uint32_t top, uint32_t bot, uint32_t node_top,
+                                     uint32_t node_bot, bool fw, uint32_t rdoff, uint32_t rdlen,
+                                     Ht2Coord* out, uint32_t& nout, uint32_t cap) {
+        uint32_t nelt = node_bot - node_top;
+        for (uint32_t i = 0; i < nelt; i++) {
+            uint32_t joff = resolveRow(lfm, top + i);
+            uint32_t tidx = 0, toff = 0;
+            bool straddled2 = false;
+            bool ok = joinedToTextOff(lfm, rdlen, joff, tidx, toff, true, straddled2);
+            if (!ok) continue;
+            uint32_t global_toff = toff + lfm.g->localOffset;
+            uint32_t joinedOff = joff + lfm.g->joinedOffset;
+            if (global_toff < rdoff) continue;
+            if (nout >= cap) { W->err |= HT2_ERR_COORDS; return false; }
+            Ht2Coord& c = out[nout++];
+            c.ref = lfm.g->tidx; c.off = global_toff; c.fw = fw ? 1 : 0; c.joinedOff = joinedOff;
+        }
+        return true;
+    }
+    HT2_HD static bool coordLess(const Ht2Coord& a, const Ht2Coord& b) { // ref_coord.h:79-87
+        if (a.ref != b.ref) return a.ref < b.ref;
+        if (a.fw != b.fw) return a.fw < b.fw;
+        return a.off < b.off;
+    }
+    HT2_HD static void sortCoords(Ht2Coord* c, uint32_t n) {
+        for (uint32_t i = 1; i < n; i++) {
+            Ht2Coord t = c[i]; uint32_t j = i;
+            while (j > 0 && coordLess(t, c[j - 1])) { c[j] = c[j - 1]; j--; }
+            c[j] = t;
+        }
+    }
+
+    // ---- local index dispatch (hgfm.h:1713-1740) ------------------------------
+    HT2_HD int localIndexId(uint32_t tidx, uint32_t offset) const {
+        const uint32_t* first = (const uint32_t*)(blob + H->o_localFirst);
+        uint32_t idx = offset / HT2_LOCAL_INDEX_INTERVAL;
+        uint32_t n = first[tidx + 1] - first[tidx];
+        if (idx >= n) return -1;
+        return (int)(first[tidx] + idx);
+    }
+    HT2_HD const Ht2Gfm* localGeom(int id) const { return ((const Ht2Gfm*)(blob + H->o_localGfm)) + id; }
+    HT2_HD int prevLocal(int id) const {
+        const Ht2Gfm* g = localGeom(id);
+        if (g->localOffset < HT2_LOCAL_INDEX_INTERVAL) return -1;
+        return localIndexId(g->tidx, g->localOffset - HT2_LOCAL_INDEX_INTERVAL);
+    }
+    HT2_HD int nextLocal(int id) const {
+        const Ht2Gfm* g = localGeom(id);
+        return localIndexId(g->tidx, g->localOffset + HT2_LOCAL_INDEX_INTERVAL);
+    }
+
+    // ---- extension against the reference -------------------------------------
+    // GenomeHit::alignWithALTs + alignWithALTs_recur restricted to an empty ALT
+    // list (hi_aligner.h:683-783, 2763-2860, 3168-3223): mismatch-bounded scan.
+    // Left: scans read positions rdoff, rdoff-1, ... against rfseq[rflen-1], ...
+    // Returns the extension length; new edits are inserted at the front of h.
+    HT2_HD uint32_t alignLeft(Ht2Hit& h, const uint8_t* seq, uint32_t base_rdoff, uint32_t rdoff, uint32_t rdlen,
+                              uint32_t tidx, int rfoff, uint32_t rflen, uint32_t mm, uint32_t* numNs) {
+        if (numNs) *numNs = 0;
+        const uint32_t nedits0 = h.nedits;
+        int best_rdoff = (int)rdoff;
+        if (rfoff < -16) return 0;
+        uint32_t contig_len = refLen(tidx);
+        if (rfoff >= 0 && (uint32_t)rfoff >= contig_len) return 0;
+        if (rfoff >= 0 && (uint32_t)rfoff + rflen > contig_len) rflen = contig_len - (uint32_t)rfoff;
+        else if (rfoff < 0 && rflen > contig_len) rflen = contig_len;
+        if (rflen == 0) return 0;
+        if (rflen > HT2_REFBUF) { W->err |= HT2_ERR_RDLEN; return 0; }
+        uint8_t* rfseq = W->refbuf;
+        {
+            uint32_t lead = rfoff < 0 ? (uint32_t)(-rfoff) : 0;
+            for (uint32_t i = 0; i < lead && i < rflen; i++) rfseq[i] = 4;
+            if (rflen > lead) getStretch(rfseq + lead, tidx, rfoff > 0 ? (uint32_t)rfoff : 0, rflen - lead);
+        }
+        uint32_t tmp_mm = 0;
+        int mm_min_rd_i = (int)rdoff;
+        uint32_t mm_tmp_numNs = 0;
+        for (int rf_i = (int)rflen - 1; rf_i >= 0 && mm_min_rd_i >= 0; rf_i--, mm_min_rd_i--) {
+            int rf_bp = rfseq[rf_i];
+            int rd_bp = seq[mm_min_rd_i];
+            if (rf_bp != rd_bp || rd_bp == 4) {
+                if (tmp_mm >= mm) break;
+                tmp_mm++;
+                insertEditFront(h, mkEdit((uint32_t)mm_min_rd_i, ht2_code2asc(rf_bp), ht2_code2asc(rd_bp), HT2_EDIT_MM));
+            }
+            if (rf_bp == 4) mm_tmp_numNs++;
+        }
+        if (mm_min_rd_i < best_rdoff) {
+            best_rdoff = mm_min_rd_i;
+            if (numNs) *numNs = mm_tmp_numNs;
+        } else {
+            // edits are only committed when the scan improved on best_rdoff
+            if (h.nedits > nedits0) {
+                uint32_t added = h.nedits - nedits0;
+                for (uint32_t i = 0; i + added < h.nedits; i++) h.edits[i] = h.edits[i + added];
+                h.nedits = nedits0;
+            }
+        }
+        uint32_t extlen = rdoff - (uint32_t)best_rdoff;
+        return fixupExt(h, extlen, nedits0, base_rdoff, rdoff, true);
+    }
+    // Right: scans read positions rdoff.. against rfseq[0..).
+    HT2_HD uint32_t alignRight(Ht2Hit& h, const uint8_t* seq, uint32_t base_rdoff, uint32_t rdoff, uint32_t rdlen,
+                               uint32_t tidx, int rfoff, uint32_t rflen, uint32_t mm) {
+        const uint32_t nedits0 = h.nedits;
+        if (rfoff < -16) return 0;
+        uint32_t contig_len = refLen(tidx);
+        if (rfoff >= 0 && (uint32_t)rfoff >= contig_len) return 0;
+        if (rfoff >= 0 && (uint32_t)rfoff + rflen > contig_len) rflen = contig_len - (uint32_t)rfoff;
+        else if (rfoff < 0 && rflen > contig_len) rflen = contig_len;
+        if (rflen == 0) return 0;
+        if (rflen > HT2_REFBUF) { W->err |= HT2_ERR_RDLEN; return 0; }
+        uint8_t* rfseq = W->refbuf;
+        {
+            uint32_t lead = rfoff < 0 ? (uint32_t)(-rfoff) : 0;
+            for (uint32_t i = 0; i < lead && i < rflen; i++) rfseq[i] = 4;
+            if (rflen > lead) getStretch(rfseq + lead, tidx, rfoff > 0 ? (uint32_t)rfoff : 0, rflen - lead);
+        }
+        const uint32_t rdoff_add = rdoff - base_rdoff;
+        uint32_t tmp_mm = 0;
+        uint32_t mm_max_rd_i = 0;
+        for (uint32_t rf_i = 0; rf_i < rflen && mm_max_rd_i < rdlen; rf_i++, mm_max_rd_i++) {
+            int rf_bp = rfseq[rf_i];
+            int rd_bp = seq[rdoff + mm_max_rd_i];
+            if (rf_bp != rd_bp || rd_bp == 4) {
+                if (tmp_mm >= mm) break;
+                tmp_mm++;
+                pushEdit(h, mkEdit(mm_max_rd_i + rdoff_add, ht2_code2asc(rf_bp), ht2_code2asc(rd_bp), HT2_EDIT_MM));
+            }
+        }
+        int best_rdoff = (int)rdoff;
+        if ((int)(mm_max_rd_i + rdoff) > best_rdoff) best_rdoff = (int)(mm_max_rd_i + rdoff);
+        else h.nedits = nedits0;
+        uint32_t extlen = (uint32_t)best_rdoff - rdoff;
+        return fixupExt(h, extlen, nedits0, base_rdoff, rdoff, false);
+    }
+    // tail of alignWithALTs (hi_aligner.h:756-783)
+    HT2_HD uint32_t fixupExt(Ht2Hit& h, uint32_t extlen, uint32_t nedits0, uint32_t base_rdoff, uint32_t rdoff, bool left) {
+        if (extlen > 0 && h.nedits > 0) {
+            const Ht2Edit& f = h.edits[0];
+            if (f.pos + extlen == base_rdoff + 1) {
+                if (f.type == HT2_EDIT_READ_GAP || f.type == HT2_EDIT_REF_GAP || f.type == HT2_EDIT_SPL) extlen = 0;
+                if (f.type == HT2_EDIT_MM && f.chr == 'N') extlen = 0;
+            }
+            const Ht2Edit& b = h.edits[h.nedits - 1];
+            if (extlen > 0 && b.pos == rdoff - base_rdoff + extlen - 1) {
+                if (b.type == HT2_EDIT_READ_GAP || b.type == HT2_EDIT_REF_GAP) extlen = 0;
+            }
+            if (extlen == 0 && h.nedits > nedits0) {
+                if (left) {
+                    uint32_t added = h.nedits - nedits0;
+                    for (uint32_t i = 0; i + added < h.nedits; i++) h.edits[i] = h.edits[i + added];
+                    h.nedits = nedits0;
+                } else h.nedits = nedits0;
+            }
+        }
+        return extlen;
+    }
+
+    // GenomeHit::extend (hi_aligner.h:2031-2232)
+    HT2_HD bool extend(Ht2Hit& h, uint32_t rdi, uint32_t& leftext, uint32_t& rightext, uint32_t mm) {
+        uint32_t max_leftext = leftext, max_rightext = rightext;
+        leftext = 0; rightext = 0;
+        const uint32_t rdlen = W->rd[rdi].len;
+        const uint8_t* seq = W->rd[rdi].seq[h.fw ? 0 : 1];
+        if (max_leftext > 0 && h.rdoff > 0) {
+            if (h.toff <= 0) return false;
+            int rl = (int)h.toff - (int)h.rdoff;
+            uint32_t reflen = h.rdoff + 10;
+            rl -= (int)(reflen - h.rdoff);
+            if (rl < 0) { reflen += rl; rl = 0; }
+            uint32_t numNs = 0;
+            uint32_t num_prev_edits = h.nedits;
+            uint32_t best_ext = alignLeft(h, seq, h.rdoff - 1, h.rdoff - 1, h.rdoff, h.tidx, rl, reflen, mm, &numNs);
+            if (h.len == 0 && mm == 0 && h.nedits > 0) { h.nedits = 0; return false; }
+            if (best_ext > 0) {
+                leftext = best_ext;
+                uint32_t added_edits = h.nedits - num_prev_edits;
+                int ref_ext = (int)best_ext;
+                for (uint32_t i = 0; i < added_edits; i++) {
+                    if (h.edits[i].type == HT2_EDIT_REF_GAP) ref_ext--;
+                    else if (h.edits[i].type == HT2_EDIT_READ_GAP) ref_ext++;
+                }
+                h.rdoff -= best_ext;
+                h.toff -= (uint32_t)ref_ext;
+                h.len += best_ext;
+                h.joinedOff -= (uint32_t)(ref_ext - (int)numNs);
+                for (uint32_t i = 0; i < h.nedits; i++) {
+                    if (i < added_edits) h.edits[i].pos -= h.rdoff;
+                    else h.edits[i].pos += best_ext;
+                }
+            }
+        }
+        if (max_rightext > 0 && h.rdoff + h.len < rdlen) {
+            uint32_t right_rdoff, right_len, right_toff;
+            getRight(h, right_rdoff, right_len, right_toff, NULL, rdi);
+            uint32_t rl = right_toff + right_len;
+            uint32_t rr = rdlen - (right_rdoff + right_len);
+            uint32_t tlen = refLen(h.tidx);
+            if (rl < tlen) {
+                uint32_t reflen = rr + 10;
+                if (rl + reflen > tlen) reflen = tlen - rl;
+                uint32_t best_ext = alignRight(h, seq, h.rdoff, h.rdoff + h.len, rdlen - (h.rdoff + h.len),
+                                               h.tidx, (int)rl, reflen, mm);
+                if (h.len == 0 && mm == 0 && h.nedits > 0) { h.nedits = 0; return false; }
+                if (best_ext > 0) { rightext = best_ext; h.len += best_ext; }
+            }
+        }
+        calculateScore(h, rdi);
+        return leftext > 0 || rightext > 0;
+    }
+
+    // GenomeHit::compatibleWith (hi_aligner.h:1375-1413)
+    HT2_HD bool compatibleWith(const Ht2Hit& a, const Ht2Hit& o, uint32_t rdi) const {
+        if (&a == &o) return false;
+        if (a.fw != o.fw || a.tidx != o.tidx) return false;
+        if (a.rdoff > o.rdoff) return false;
+        if (a.rdoff + a.len > o.rdoff + o.len) return false;
+        if (a.toff > o.toff) return false;
+        uint32_t this_rdoff, this_len, this_toff, other_rdoff, other_len, other_toff;
+        getRight(a, this_rdoff, this_len, this_toff, NULL, rdi);
+        getLeft(o, other_rdoff, other_len, other_toff, NULL, rdi);
+        if (this_rdoff > other_rdoff) return false;
+        if (this_rdoff + this_len > other_rdoff + other_len) return false;
+        if (this_toff > other_toff) return false;
+        uint32_t refdif = other_toff - this_toff;
+        uint32_t rddif = other_rdoff - this_rdoff;
+        if (!P->noSplicedAlignment) {
+            if (refdif > rddif + P->maxIntronLen) return false;
+        }
+        return true;
+    }
+
+    // GenomeHit::leftAlign (hi_aligner.h:3554-3610)
+    HT2_HD void leftAlign(Ht2Hit& h, uint32_t rdi) const {
+        const uint8_t* seq = W->rd[rdi].seq[h.fw ? 0 : 1];
+        for (uint32_t ei = 0; ei < h.nedits; ei++) {
+            Ht2Edit& edit = h.edits[ei];
+            if (edit.type != HT2_EDIT_READ_GAP && edit.type != HT2_EDIT_REF_GAP) continue;
+            if (edit.snpID != HT2_IDX_MAX32) continue;
+            uint32_t ei2 = ei + 1;
+            for (; ei2 < h.nedits; ei2++) {
+                const Ht2Edit& edit2 = h.edits[ei2];
+                if (edit2.type != edit.type) break;
+                if (edit.type == HT2_EDIT_READ_GAP) { if (edit.pos != edit2.pos) break; }
+                else { if (edit.pos + ei2 - ei != edit2.pos) break; }
+            }
+            ei2 -= 1;
+            Ht2Edit& edit2 = h.edits[ei2];
+            int b = 0;
+            if (ei > 0) b = (int)h.edits[ei - 1].pos;
+            int l = (int)edit.pos - 1;
+            while (l > b) {
+                int rdc = seq[h.rdoff + l];
+                uint8_t rfc = (edit.type == HT2_EDIT_READ_GAP ? edit2.chr : edit2.qchr);
+                if (rfc != ht2_code2asc(rdc)) break;
+                for (int ei3 = (int)ei2; ei3 > (int)ei; ei3--) {
+                    if (edit.type == HT2_EDIT_READ_GAP) h.edits[ei3].chr = h.edits[ei3 - 1].chr;
+                    else h.edits[ei3].qchr = h.edits[ei3 - 1].qchr;
+                    h.edits[ei3].pos -= 1;
+                }
+                if (edit.type == HT2_EDIT_READ_GAP) edit.chr = ht2_code2asc(rdc);
+                else edit.qchr = ht2_code2asc(rdc);
+                edit.pos -= 1;
+                l--;
+            }
+            ei = ei2;
+        }
+    }
+
+    // GenomeHit::combineWith (hi_aligner.h:1420-2025), non-spliced paths
+    // (splicing is rejected under --no-spliced-alignment, :1500-1502).
+    HT2_HD bool combineWith(Ht2Hit& a, const Ht2Hit& o, uint32_t rdi, int64_t minsc_) {
+        if (&a == &o) return false;
+        uint32_t this_rdoff, this_len, this_toff, other_rdoff, other_len, other_toff;
+        int64_t this_score, other_score;
+        getRight(a, this_rdoff, this_len, this_toff, &this_score, rdi);
+        getLeft(o, other_rdoff, other_len, other_toff, &other_score, rdi);
+        if (this_len != 0 && other_len != 0 && this_rdoff + this_len > other_rdoff + other_len) return false;
+        uint32_t len = other_rdoff - this_rdoff + other_len;
+        const uint32_t reflen = refLen(a.tidx);
+        if (this_toff + len > reflen) return false;
+        uint32_t refdif = other_toff - this_toff;
+        uint32_t rddif = other_rdoff - this_rdoff;
+        bool spliced = false, ins = false, del = false;
+        if (refdif != rddif) {
+            if (refdif > rddif) {
+                if (!P->noSplicedAlignment && refdif - rddif >= P->minIntronLen) spliced = true;
+                else del = true;
+            } else ins = true;
+        }
+        if (spliced) return false; // spliced joins are outside this build's scope
+        if (!ins && !del && this_rdoff + this_len == other_rdoff) {
+            uint32_t addoff = o.rdoff - a.rdoff;
+            for (uint32_t i = 0; i < o.nedits; i++) {
+                if (!pushEdit(a, o.edits[i])) return false;
+                a.edits[a.nedits - 1].pos += addoff;
+            }
+            a.len += o.len;
+            calculateScore(a, rdi);
+            return true;
+        }
+        const uint8_t* seq = W->rd[rdi].seq[a.fw ? 0 : 1];
+        const uint8_t* qual = W->rd[rdi].qual[a.fw ? 0 : 1];
+        const uint32_t rdlen = W->rd[rdi].len;
+        int64_t remainsc = minsc_ - (a.score - this_score) - (o.score - other_score);
+        if (remainsc > 0) remainsc = 0;
+        int read_gaps = ht2_max_gaps(remainsc + P->canSplPen, P->rdGapConst + P->rdGapLinear, P->rdGapLinear);
+        int ref_gaps = ht2_max_gaps(remainsc + P->canSplPen, P->rfGapConst + P->rfGapLinear, P->rfGapLinear);
+        (void)rdlen;
+        if (ins) { if (refdif + (uint32_t)ref_gaps < rddif) return false; }
+        else if (del) { if (rddif + (uint32_t)read_gaps < refdif) return false; }
+        int this_ref_ext = read_gaps;
+        if (this_toff + len > reflen) return false;
+        if (this_toff + len + (uint32_t)this_ref_ext > reflen) this_ref_ext = (int)(reflen - (this_toff + len));
+        if (len + (uint32_t)this_ref_ext > HT2_REFBUF || len > HT2_MAX_RDLEN) { W->err |= HT2_ERR_RDLEN; return false; }
+        uint8_t* refbuf = W->refbuf;
+        getStretch(refbuf, a.tidx, this_toff, len + (uint32_t)this_ref_ext);
+        uint8_t* refbuf2 = NULL;
+        uint32_t maxscorei = HT2_IDX_MAX32;
+        int64_t maxscore = HT2_MIN_I64;
+        if (ins || del) {
+            int other_ref_ext = read_gaps;
+            int lim = (int)(other_toff + other_len - len);
+            if (lim < other_ref_ext) other_ref_ext = lim;
+            if ((int)len + other_ref_ext > (int)HT2_REFBUF || other_ref_ext < 0) { W->err |= HT2_ERR_RDLEN; return false; }
+            getStretch(W->refbuf2, o.tidx, other_toff + other_len - len - (uint32_t)other_ref_ext, len + (uint32_t)other_ref_ext);
+            refbuf2 = W->refbuf2 + other_ref_ext;
+            int64_t* ts = W->tscores; int64_t* ts2 = W->tscores2;
+            int inslen = (ins ? (int)(rddif - refdif) : 0);
+            int dellen = (del ? (int)(refdif - rddif) : 0);
+            int64_t gap_penalty;
+            if (ins) gap_penalty = -((int64_t)(P->rfGapConst + P->rfGapLinear) + (int64_t)P->rfGapLinear * (inslen - 1));
+            else gap_penalty = -((int64_t)(P->rdGapConst + P->rdGapLinear) + (int64_t)P->rdGapLinear * (dellen - 1));
+            if (gap_penalty < remainsc) return false;
+            int i;
+            for (i = 0; i < (int)len; i++) {
+                int rdc = seq[this_rdoff + i], rfc = refbuf[i];
+                ts[i] = i > 0 ? ts[i - 1] : 0;
+                if (rdc != rfc) ts[i] += ht2_score(*P, rdc, 1 << rfc, (int)qual[this_rdoff + i] - 33);
+                if (ts[i] + gap_penalty < remainsc) break;
+            }
+            int i_limit = i < (int)len ? i : (int)len;
+            int i2;
+            for (i2 = (int)len - 1; i2 >= 0; i2--) {
+                int rdc = seq[this_rdoff + i2], rfc = refbuf2[i2];
+                ts2[i2] = ((uint32_t)(i2 + 1) < len) ? ts2[i2 + 1] : 0;
+                if (rdc != rfc) ts2[i2] += ht2_score(*P, rdc, 1 << rfc, (int)qual[this_rdoff + i2] - 33);
+                if (ts2[i2] + gap_penalty < remainsc) break;
+            }
+            int i2_limit = (i2 < inslen ? 0 : i2 - inslen);
+            for (i = i2_limit, i2 = i2_limit + 1 + inslen; i < i_limit && i2 < (int)len; i++, i2++) {
+                int64_t tempscore = ts[i] + ts2[i2] + gap_penalty;
+                if (maxscore < tempscore) { maxscore = tempscore; maxscorei = (uint32_t)i; }
+            }
+            if (maxscore == HT2_MIN_I64) return false;
+            if (maxscore < remainsc) return false;
+        }
+        // drop this hit's trailing plain mismatches (hi_aligner.h:1818-1830)
+        {
+            bool clear = true;
+            for (int i = (int)a.nedits - 1; i >= 0; i--) {
+                if (isGapOrSnp(a.edits[i])) { a.nedits = (uint32_t)i + 1; clear = false; break; }
+            }
+            if (clear) a.nedits = 0;
+        }
+        {
+            uint32_t ins_len = 0;
+            for (uint32_t i = 0; i < len; i++) {
+                int rdc = seq[this_rdoff + i];
+                int rfc = (i <= maxscorei ? refbuf[i] : refbuf2[i]);
+                uint32_t addoff = this_rdoff - a.rdoff;
+                if (rdc != rfc) {
+                    // (graph indexes: look the mismatch up in the ALT table here, :1917-1930)
+                    if (!pushEdit(a, mkEdit(i + addoff, ht2_code2asc(rfc), ht2_code2asc(rdc), HT2_EDIT_MM))) return false;
+                }
+                if (i == maxscorei) {
+                    uint32_t left = this_toff + i + 1;
+                    if (other_toff + other_len < len - i - 1) return false;
+                    uint32_t right = other_toff + other_len - (len - i - 1);
+                    if (del) {
+                        uint32_t skipLen = right - left;
+                        for (uint32_t j = 0; j < skipLen; j++) {
+                            int temp_rfc;
+                            if (i + 1 + j < len) temp_rfc = refbuf[i + 1 + j];
+                            else temp_rfc = getBase(a.tidx, this_toff + i + 1 + j);
+                            if (!pushEdit(a, mkEdit(i + 1 + addoff, ht2_code2asc(temp_rfc), '-', HT2_EDIT_READ_GAP))) return false;
+                        }
+                    } else {
+                        uint32_t skipLen = left - right;
+                        for (uint32_t j = 0; j < skipLen; j++) {
+                            int temp_rdc = seq[this_rdoff + i + 1 + j];
+                            if (!pushEdit(a, mkEdit(i + 1 + j + addoff, '-', ht2_code2asc(temp_rdc), HT2_EDIT_REF_GAP))) return false;
+                        }
+                        i += skipLen;
+                        ins_len += skipLen;
+                    }
+                }
+            }
+            (void)ins_len;
+        }
+        uint32_t fsi = o.nedits;
+        for (uint32_t i = 0; i < o.nedits; i++) {
+            if (isGapOrSnp(o.edits[i])) { fsi = i; break; }
+        }
+        uint32_t addoff = o.rdoff - a.rdoff;
+        for (uint32_t i = fsi; i < o.nedits; i++) {
+            if (!pushEdit(a, o.edits[i])) return false;
+            a.edits[a.nedits - 1].pos += addoff;
+        }
+        if (ins || del) leftAlign(a, rdi);
+        a.len = o.rdoff + o.len - a.rdoff;
+        a.trim3 += o.trim3;
+        calculateScore(a, rdi);
+        return true;
+    }
+
+    // ---- sink: AlnSinkWrap::report (aln_sink.h:2565-2655) + ReportingState ----
+    HT2_HD void sinkReset(bool paired_) {
+        W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0;
+        W->bestPair = W->best2Pair = HT2_MIN_SCORE;
+        W->bestUnp[0] = W->best2Unp[0] = W->bestUnp[1] = W->best2Unp[1] = HT2_MIN_SCORE;
+        W->nconcord = 0; W->nunpair[0] = W->nunpair[1] = 0;
+        // ReportingState::nextRead (aln_sink.cpp:33-66)
+        if (paired_) {
+            W->doneConcord = 0;
+            W->doneUnpair[0] = P->mixed ? 0 : 1;
+            W->doneUnpair[1] = P->mixed ? 0 : 1;
+        } else {
+            W->doneConcord = 1; W->doneUnpair[0] = 0; W->doneUnpair[1] = 1;
+        }
+        W->stDone = 0;
+        W->concordBest = HT2_MIN_SCORE;
+    }
+    HT2_HD void reportUnpaired(uint32_t mate /*0 or 1 == rs1/rs2*/, int64_t score) {
+        // ReportingState::foundUnpaired (aln_sink.cpp:96-132), -k mode (mhits unset)
+        W->nunpair[mate]++;
+        if (!W->doneUnpair[mate]) {
+            if (W->nunpair[mate] >= P->khits) {
+                W->doneUnpair[mate] = 1;
+                if (W->doneUnpair[0] && W->doneUnpair[1]) { /* updateDone */ }
+            }
+        }
+        if (score > W->bestUnp[mate]) { W->best2Unp[mate] = W->bestUnp[mate]; W->bestUnp[mate] = score; }
+        else if (score > W->best2Unp[mate]) W->best2Unp[mate] = score;
+    }
+
+    // HI_Aligner::reportHit (hi_aligner.h:6064-6198), unpaired form.
+    HT2_HD bool reportHit(uint32_t rdi, const Ht2Hit& hit) {
+        const uint32_t rdlen = W->rd[rdi].len;
+        if (hit.rdoff - hit.trim5 > 0 || hit.len + hit.trim5 + hit.trim3 < rdlen) return false;
+        if (hit.score < minsc[rdi]) return false;
+        uint32_t slot = (rdi == 0 && !rightendonly) ? 0 : 1;
+        if (W->nRes[slot] >= HT2_MAX_RES) { W->err |= HT2_ERR_RES; return false; }
+        Ht2Res& r = W->res[slot][W->nRes[slot]++];
+        r.tidx = hit.tidx; r.toff = hit.toff; r.fw = hit.fw; r.rdlen = rdlen; r.score = hit.score;
+        r.trim5p = hit.fw ? hit.trim5 : hit.trim3;
+        r.trim3p = hit.fw ? hit.trim3 : hit.trim5;
+        r.nedits = hit.nedits;
+        for (uint32_t i = 0; i < hit.nedits; i++) { r.edits[i] = hit.edits[i]; r.edits[i].pos += hit.trim5; }
+        if (!hit.fw) invertPoss(r.edits, r.nedits, rdlen);
+        // AlnRes::setShape (aligner_result.cpp:111-129)
+        for (uint32_t i = 0; i < r.nedits; i++) r.edits[i].pos -= r.trim5p;
+        uint32_t rfextent = rdlen - r.trim5p - r.trim3p;
+        for (uint32_t i = 0; i < r.nedits; i++) {
+            if (r.edits[i].type == HT2_EDIT_REF_GAP) rfextent--;
+            else if (r.edits[i].type == HT2_EDIT_READ_GAP) rfextent++;
+        }
+        r.rfextent = rfextent;
+        reportUnpaired(slot, hit.score);
+        return true;
+    }
+
+    // HI_Aligner::redundant(sink, rdi, hit) (hi_aligner.h:6311-6351)
+    HT2_HD bool redundant(uint32_t rdi, const Ht2Hit& hit) {
+        const uint32_t rdlen = W->rd[rdi].len;
+        for (uint32_t i = 0; i < W->nRes[rdi]; i++) {
+            const Ht2Res& rsi = W->res[rdi][i];
+            if (rsi.tidx == hit.tidx && rsi.toff == hit.toff && rsi.fw == hit.fw) {
+                if (rsi.nedits == hit.nedits) {
+                    uint32_t eidx = 0;
+                    for (; eidx < rsi.nedits; eidx++) {
+                        // compare against hit.edits as Edit::invertPoss(edits, rdlen) would lay them out
+                        Ht2Edit e = hit.fw ? hit.edits[eidx] : hit.edits[hit.nedits - eidx - 1];
+                        if (!hit.fw) {
+                            if (e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_SPL) e.pos = (uint32_t)(rdlen - e.pos);
+                            else e.pos = (uint32_t)(rdlen - e.pos - 1);
+                        }
+                        if (!editEq(rsi.edits[eidx], e)) break;
+                    }
+                    if (eidx >= rsi.nedits) return true;
+                }
+            }
+        }
+        return false;
+    }
+    // isSearched / addSearched (hi_aligner.h:6898-6922)
+    HT2_HD bool isSearched(const Ht2Hit& hit, uint32_t rdi) const {
+        for (uint32_t i = 0; i < W->nSearched[rdi]; i++) if (hitEq(W->searched[rdi][i], hit)) return true;
+        return false;
+    }
+    HT2_HD void addSearched(const Ht2Hit& hit, uint32_t rdi) {
+        if (W->nSearched[rdi] >= HT2_MAX_SEARCHED) { W->err |= HT2_ERR_SEARCHED; return; }
+        copyHit(W->searched[rdi][W->nSearched[rdi]++], hit);
+    }
+
+    // ---- policy --------------------------------------------------------------
+    // ReadBWTHit::searchScore (hi_aligner.h:321-334)
+    HT2_HD int64_t searchScore(const Ht2ReadHits& h) const {
+        int64_t score = 0;
+        const int64_t penaltyPerOffset = (int64_t)P->minK * P->minK;
+        for (uint32_t i = 0; i < h.nhits; i++) { uint32_t len = h.hits[i].len; score += (int64_t)(uint32_t)(len * len); }
+        uint32_t aps = h.numPartialSearch - h.numUniqueSearch;
+        score -= (int64_t)aps * penaltyPerOffset;
+        score -= (int64_t)(1 << (aps << 1));
+        return score;
+    }
+    // HI_Aligner::pickNextReadToSearch (hi_aligner.h:4868-4894)
+    HT2_HD bool pickNextReadToSearch(uint32_t& rdi, bool& fw) {
+        rdi = 0; fw = true;
+        bool picked = false;
+        int64_t maxScore = HT2_MIN_I64;
+        for (uint32_t rdi2 = 0; rdi2 < (paired ? 2u : 1u); rdi2++) {
+            for (uint32_t fwi = 0; fwi < 2; fwi++) {
+                if (fwi == 0 && nofw[rdi2]) continue;
+                else if (fwi == 1 && norc[rdi2]) continue;
+                Ht2ReadHits& h = W->hits[rdi2][fwi];
+                if (h.done) continue;
+                int64_t curScore = searchScore(h);
+                if (h.cur == 0) curScore = 0x7fffffffffffffffll;
+                if (curScore > maxScore) { maxScore = curScore; rdi = rdi2; fw = (fwi == 0); picked = true; }
+            }
+        }
+        return picked;
+    }
+    // HI_Aligner::nextBWT (hi_aligner.h:4644-4752)
+    HT2_HD bool nextBWT(uint32_t& rdi, bool& fw) {
+        while (pickNextReadToSearch(rdi, fw)) {
+            uint32_t fwi = fw ? 0 : 1;
+            Ht2ReadHits& hit = W->hits[rdi][fwi];
+            bool pseudogeneStop = gfm.g->linearFM && !P->noSplicedAlignment;
+            bool anchorStop = P->anchorStop != 0;
+            if (!P->secondary) {
+                uint32_t numSearched = hit.numPartialSearch - hit.numUniqueSearch;
+                int64_t bestScore = W->bestUnp[rdi];
+                if (bestScore >= minsc[rdi]) {
+                    uint32_t maxmm = (uint32_t)((-bestScore + P->mmpMax - 1) / P->mmpMax);
+                    if (numSearched > maxmm + 0 /*bestSplicedUnp*/ + 1) {
+                        hit.done = 1;
+                        if (paired) {
+                            if (W->bestUnp[1 - rdi] >= minsc[1 - rdi] && W->nPairs > 0) return false;
+                            else continue;
+                        } else return false;
+                    }
+                }
+                Ht2ReadHits& rchit = W->hits[rdi][1 - fwi];
+                if (rchit.done && bestScore < minsc[rdi]) {
+                    if (numSearched > (rchit.numPartialSearch - rchit.numUniqueSearch) + (anchorStop ? 1u : 0u)) {
+                        hit.done = 1;
+                        return false;
+                    }
+                }
+            }
+            partialSearch(rdi, fw, pseudogeneStop, anchorStop);
+            if (hit.done) return true;
+            if (!pseudogeneStop) { if (hit.cur + 1 < hit.len) hit.cur++; }
+            if (anchorStop) { hit.done = 1; return true; }
+        }
+        return false;
+    }
+
+    // HI_Aligner::getAnchorHits (hi_aligner.h:5007-5193), linear-index form of
+    // adjustWithALT (hi_aligner.h:2251-2264).
+    HT2_HD uint32_t getAnchorHits(uint32_t rdi, bool fw, uint32_t maxGenomeHitSize) {
+        Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
+        const uint32_t offsetSize = hit.nhits;
+        const uint32_t minK = P->minK;
+        for (uint32_t hi = 0; hi < offsetSize; hi++) {
+            uint32_t hj = 0;
+            for (; hj < offsetSize; hj++) {
+                Ht2BwtHit& pj = hit.hits[hj];
+                if (pj.bot <= pj.top || pj.hasCoords || pj.len <= minK + 2) continue;
+                else break;
+            }
+            if (hj >= offsetSize) break;
+            for (uint32_t hk = hj + 1; hk < offsetSize; hk++) {
+                Ht2BwtHit& pj = hit.hits[hj];
+                Ht2BwtHit& pk = hit.hits[hk];
+                if (pk.bot <= pk.top || pk.hasCoords || pk.len <= minK + 2) continue;
+                if (pj.hit_type == pk.hit_type) {
+                    uint32_t sj = pj.bot - pj.top, sk = pk.bot - pk.top;
+                    if (sj > sk || (sj == sk && pj.len < pk.len)) hj = hk;
+                } else if (pk.hit_type > pj.hit_type) hj = hk;
+            }
+            Ht2BwtHit& ph = hit.hits[hj];
+            uint32_t remained = maxGenomeHitSize - W->nGenomeHits;
+            if (remained <= 0) break;
+            uint32_t expectedNumCoords = ph.node_bot - ph.node_top;
+            bool straddled = false;
+            W->nCoords = 0;
+            if (expectedNumCoords <= remained) {
+                getGenomeCoords(ph.top, ph.bot, ph.node_top, ph.node_bot, fw, ph.bot - ph.top, ph.len, false, straddled);
+            } else {
+                uint32_t top = ph.top;
+                uint32_t added = 0;
+                for (uint32_t node = ph.node_top; node < ph.node_bot; node++, expectedNumCoords--) {
+                    uint32_t bot = top + 1;
+                    uint32_t rndi = W->rnd.nextU32() % expectedNumCoords;
+                    if (rndi < remained - added) {
+                        getGenomeCoords(top, bot, node, node + 1, fw, ph.bot - ph.top, ph.len, false, straddled);
+                        added++;
+                        if (added >= remained) break;
+                    }
+                    top = bot;
+                }
+            }
+            ph.hasCoords = W->nCoords > 0 ? 1 : 0;
+            if (!ph.hasCoords) continue;
+            const uint32_t genomeHit_size = W->nGenomeHits;
+            if (genomeHit_size + W->nCoords > maxGenomeHitSize) {
+                // EList::shufflePortion (ds.h:836-847)
+                uint32_t left = W->nCoords;
+                for (uint32_t i = 0; i + 1 < W->nCoords; i++) {
+                    uint32_t rndi = W->rnd.nextU32() % left;
+                    if (rndi > 0) { Ht2Coord t = W->coords[i]; W->coords[i] = W->coords[i + rndi]; W->coords[i + rndi] = t; }
+                    left--;
+                }
+            }
+            for (uint32_t k = 0; k < W->nCoords; k++) {
+                const Ht2Coord& coord = W->coords[k];
+                if (coord.ref == HT2_IDX_MAX32) continue;
+                uint32_t len = ph.len;
+                uint32_t rdoff = hit.len - ph.bwoff - len;
+                bool overlapped = false;
+                for (uint32_t l = 0; l < genomeHit_size; l++) {
+                    Ht2Hit& gh = W->genomeHits[l];
+                    if (gh.tidx != coord.ref || gh.fw != coord.fw) continue;
+                    uint32_t hitoff = gh.toff + hit.len - gh.rdoff;
+                    uint32_t hitoff2 = coord.off + hit.len - rdoff;
+                    int64_t hitoff_diff = (P->noSplicedAlignment ? 0 : (int64_t)P->maxIntronLen);
+                    int64_t d = (int64_t)hitoff - (int64_t)hitoff2;
+                    if (d < 0) d = -d;
+                    if (d <= hitoff_diff) { overlapped = true; gh.hitcount++; break; }
+                }
+                if (!overlapped) {
+                    if (W->nGenomeHits >= HT2_MAX_GHITS) { W->err |= HT2_ERR_GHITS; break; }
+                    initHit(W->genomeHits[W->nGenomeHits++], coord.fw != 0, rdoff, len, 0, 0, coord.ref, coord.off, coord.joinedOff);
+                }
+                if (ph.hit_type == HT2_CANDIDATE_HIT && W->nGenomeHits >= maxGenomeHitSize) break;
+            }
+            if (ph.hit_type == HT2_CANDIDATE_HIT && W->nGenomeHits >= maxGenomeHitSize) break;
+        }
+        return W->nGenomeHits;
+    }
+
+    // HI_Aligner::align (hi_aligner.h:5484-5571)
+    HT2_HD bool align(uint32_t rdi, bool fw) {
+        Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
+        {   // ReadBWTHit::minWidth (hi_aligner.h:302-318)
+            bool any = false;
+            for (uint32_t i = 0; i < hit.nhits; i++) if (hit.hits[i].bot > hit.hits[i].top) { any = true; break; }
+            if (!any) return false;
+        }
+        int64_t bestScore = W->bestUnp[rdi];
+        if (bestScore < minsc[rdi]) bestScore = minsc[rdi];
+        uint32_t maxmm = (uint32_t)((-bestScore + P->mmpMax - 1) / P->mmpMax);
+        uint32_t numActualPartialSearch = hit.numPartialSearch - hit.numUniqueSearch;
+        if (!P->secondary && numActualPartialSearch > maxmm + 0 + 1) return true;
+        const uint32_t maxsize = P->khits > P->kseeds ? P->khits : P->kseeds;
+        W->nGenomeHits = 0;
+        uint32_t numHits = getAnchorHits(rdi, fw, maxsize);
+        if (numHits <= 0) return false;
+        uint64_t add = (uint64_t)(-minsc[rdi] / P->mmpMax) * numHits * (P->secondary ? 2 : 1);
+        W->maxLocalindexatts = W->localindexatts + (uint32_t)(add > 10 ? add : 10);
+        hybridSearch(rdi, fw);
+        return true;
+    }
+
+    // SplicedAligner::hybridSearch (spliced_aligner.h:112-322), bowtie2_dp == 0
+    HT2_HD void hybridSearch(uint32_t rdi, bool fw) {
+        (void)fw;
+        for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
+            uint32_t leftext = HT2_IDX_MAX32, rightext = HT2_IDX_MAX32;
+            extend(W->genomeHits[hi], rdi, leftext, rightext, 0);
+        }
+        for (uint32_t i = 0; i < W->nGenomeHits; i++) W->genomeHitsDone[i] = 0;
+        for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
+            uint32_t hj = 0;
+            for (; hj < W->nGenomeHits; hj++) if (!W->genomeHitsDone[hj]) break;
+            if (hj >= W->nGenomeHits) break;
+            for (uint32_t hk = hj + 1; hk < W->nGenomeHits; hk++) {
+                if (W->genomeHitsDone[hk]) continue;
+                Ht2Hit& gj = W->genomeHits[hj]; Ht2Hit& gk = W->genomeHits[hk];
+                if (gk.hitcount > gj.hitcount || (gk.hitcount == gj.hitcount && gk.len > gj.len)) hj = hk;
+            }
+            Ht2Hit& gh = W->genomeHits[hj];
+            hybridSearchRecur(rdi, gh, gh.rdoff, gh.len, false, 0);
+            W->genomeHitsDone[hj] = 1;
+        }
+    }
+
+    HT2_HD int64_t sinkFloor(uint32_t rdi, int64_t cushion) const {
+        int64_t m = minsc[rdi];
+        if (!P->secondary) {
+            int64_t b = W->bestUnp[rdi] - cushion;
+            if (b > m) m = b;
+        }
+        return m;
+    }
+
+    // SplicedAligner::hybridSearch_recur (spliced_aligner.h:331-2052) for an
+    // empty splice-site DB (--no-spliced-alignment / no known sites).
+    HT2_HDN int64_t hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, uint32_t hitoff, uint32_t hitlen,
+                                      bool alignMate, uint32_t dep);
+
+    // HI_Aligner::go (hi_aligner.h:4048-4638), unpaired + paired without repeats
+    HT2_HDN void go();
+    HT2_HDN void pairReads();
+    HT2_HDN bool alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff);
+};
+
+#include "ht2_core_impl.h"
+
+#endif // HT2_CORE_H_

@@ -1,0 +1,57 @@
+// ht2_host.h -- host-side front end (read preparation, per-read parameters)
+// and back end (AlnSinkWrap::finishRead-equivalent selection, MAPQ, SAM text)
+// that sit either side of the device hot path.  These reproduce, outside the
+// kernels, the reference steps SURVEY.md §9 lists as deciding byte equality:
+//   hisat2.cpp:3360-3470 (minsc, filters, RNG seed), pat.h:55-91 (genRandSeed)
+//   aln_sink.h:1939-2560 (finishRead), :2680-2755 (selectByScore)
+//   unique.h:170-420 (BowtieMapq2), aln_sink.h:3024-3250 (appendMate)
+//   sam.h:525-1010 (optional flags), aligner_result.cpp:660-1000 (StackedAln)
+#ifndef HT2_HOST_H_
+#define HT2_HOST_H_
+
+#include <string>
+#include <vector>
+
+#include "ht2_core.h"
+#include "ht2_index.h"
+
+struct Ht2HostRead {
+    std::string name;
+    std::vector<uint8_t> seq;   // codes 0..4
+    std::vector<uint8_t> qual;  // raw ASCII
+    uint32_t seed;
+    int mate;                   // 0 unpaired, 1, 2
+};
+
+struct Ht2ReadFilters {
+    bool nfilt, scfilt, lenfilt, qcfilt; // true = passes
+    bool pass() const { return nfilt && scfilt && lenfilt && qcfilt; }
+};
+
+// Everything the device returns for one read (pair).
+struct Ht2ReadOut {
+    std::vector<Ht2Res> res[2];
+    std::vector<std::pair<uint16_t, uint16_t> > pairs;
+    uint32_t rngLast;
+    uint32_t err;
+};
+
+void ht2_default_params(Ht2Params& P, const Ht2Image& img, bool noSplicedAlignment);
+
+// Per-read preprocessing (hisat2.cpp:3387-3467)
+int64_t ht2_minsc(uint32_t rdlen);
+Ht2ReadFilters ht2_filters(const Ht2HostRead& rd, int64_t minsc);
+uint32_t ht2_gen_rand_seed(const Ht2HostRead& rd, uint32_t seed);
+void ht2_fill_read(Ht2Read& dst, const Ht2HostRead& src);
+
+// FASTA reader following FastaPatternSource::read (pat.cpp:725-849)
+bool ht2_read_fasta(const char* path, std::vector<Ht2HostRead>& out, int mate, std::string& err);
+
+// SAM
+void ht2_sam_header(std::string& o, const Ht2Image& img);
+// finishRead for an unpaired read (aln_sink.h:2213-2557, unpaired branches)
+void ht2_finish_unpaired(std::string& o, const Ht2Image& img, const Ht2Params& P,
+                         const Ht2HostRead& rd, const Ht2ReadFilters& f,
+                         Ht2ReadOut& out);
+
+#endif

@@ -1,0 +1,295 @@
+// ht2_index.cpp -- host parser: HISAT2 .ht2 files -> packed index image.
+//
+// Reads <base>.1.ht2 .. <base>.8.ht2 exactly as laid out by the reference's
+// loaders and re-packs the arrays into the single position-independent blob
+// described in ht2_image.h.  Formats follow (not copied from):
+//   gfm.h:5917-6458  GFM::readIntoMemory     (.1 header/body, .2 SA sample)
+//   hgfm.h:2453-2651 HGFM::readIntoMemory    (.5 header)
+//   hgfm.h:1106-1530 LocalGFM::readIntoMemory (.5 body, .6 SA sample)
+//   reference.cpp:30-390 BitPairReference    (.3 records, .4 packed bases)
+//   gfm.h:714-778, alt.h:197-204             (.7 ALTs)
+// Little-endian files only (the reference refuses byte-swapped mmap too).
+#include "ht2_index.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct FileBuf {
+    std::vector<uint8_t> d;
+    size_t pos = 0;
+    explicit FileBuf(const std::string& path, bool optional = false) {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) {
+            if (optional) return;
+            throw std::runtime_error("ht2: could not open index file " + path);
+        }
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        d.resize((size_t)sz);
+        if (sz > 0 && fread(d.data(), 1, (size_t)sz, f) != (size_t)sz) {
+            fclose(f);
+            throw std::runtime_error("ht2: short read on " + path);
+        }
+        fclose(f);
+    }
+    void need(size_t n) const {
+        if (pos + n > d.size()) throw std::runtime_error("ht2: truncated index file");
+    }
+    uint32_t u32() { need(4); uint32_t v; memcpy(&v, &d[pos], 4); pos += 4; return v; }
+    int32_t  i32() { return (int32_t)u32(); }
+    uint16_t u16() { need(2); uint16_t v; memcpy(&v, &d[pos], 2); pos += 2; return v; }
+    uint64_t u64() { need(8); uint64_t v; memcpy(&v, &d[pos], 8); pos += 8; return v; }
+    const uint8_t* take(size_t n) { need(n); const uint8_t* p = &d[pos]; pos += n; return p; }
+    bool eof() const { return pos >= d.size(); }
+};
+
+struct Blob {
+    std::vector<uint8_t> d;
+    uint64_t alloc(size_t n, size_t align) {
+        size_t off = (d.size() + align - 1) / align * align;
+        d.resize(off + n, 0);
+        return off;
+    }
+    uint64_t put(const void* src, size_t n, size_t align) {
+        uint64_t off = alloc(n, align);
+        if (n) memcpy(&d[off], src, n);
+        return off;
+    }
+};
+
+// GFMParams::init (gfm.h:134-176), for entry width 'eb' bytes.
+void initGeom(Ht2Gfm& g, uint32_t len, uint32_t gbwtLen, uint32_t numNodes,
+              int32_t lineRate, int32_t offRate, int32_t ftabChars,
+              uint32_t eftabLen, uint32_t eb)
+{
+    memset(&g, 0, sizeof(g));
+    g.entryBytes = eb;
+    const uint32_t entryMax = (eb == 4) ? 0xffffffffu : 0xffffu;
+    // all arithmetic in the reference happens in index_t (wraps for uint16)
+    auto wrap = [&](uint32_t v) { return v & entryMax; };
+    g.linearFM = (wrap(len + 1) == gbwtLen || gbwtLen == 0) ? 1 : 0;
+    g.len = len;
+    g.gbwtLen = (gbwtLen == 0 ? wrap(len + 1) : gbwtLen);
+    g.numNodes = (numNodes == 0 ? wrap(len + 1) : numNodes);
+    uint32_t gbwtSz = g.linearFM ? wrap(g.gbwtLen / 4 + 1) : wrap(g.gbwtLen / 2 + 1);
+    g.offRate = (uint32_t)offRate;
+    g.offMask = wrap(entryMax << offRate);
+    g.ftabChars = (uint32_t)ftabChars;
+    g.eftabLen = eftabLen;
+    g.ftabLen = wrap((1u << (ftabChars * 2)) + 1);
+    g.offsLen = wrap((g.numNodes + (1u << offRate) - 1) >> offRate);
+    g.sideSz = 1u << lineRate;
+    if (g.linearFM) {
+        g.sideGbwtSz = g.sideSz - eb * 4;
+        g.sideGbwtLen = g.sideGbwtSz << 2;
+    } else {
+        g.sideGbwtSz = g.sideSz - eb * 6;
+        g.sideGbwtLen = g.sideGbwtSz << 1;
+    }
+    g.numSides = (gbwtSz + g.sideGbwtSz - 1) / g.sideGbwtSz;
+    g.ftabCmp = g.linearFM ? g.len : g.gbwtLen;
+}
+
+// Body shared by the global (.1) and local (.5) formats, after the header
+// ints: nPat plen[] nFrag rstarts[] gfm[] nzOffs zOffs[] fchr[5] ftab[] eftab[]
+void readBody(FileBuf& f, Blob& b, Ht2Gfm& g)
+{
+    const uint32_t eb = g.entryBytes;
+    auto rdIdx = [&]() -> uint32_t { return eb == 4 ? f.u32() : f.u16(); };
+    g.nPat = rdIdx();
+    g.o_plen = b.put(f.take((size_t)g.nPat * eb), (size_t)g.nPat * eb, 16);
+    g.nFrag = rdIdx();
+    g.o_rstarts = b.put(f.take((size_t)g.nFrag * 3 * eb), (size_t)g.nFrag * 3 * eb, 16);
+    size_t tot = (size_t)g.numSides * g.sideSz;
+    g.o_gfm = b.put(f.take(tot), tot, 128);
+    // keep one zeroed side of slack after the BWT so 128-bit side loads of the
+    // last side and select scans that run off the end stay inside the blob
+    b.alloc(g.sideSz, 128);
+    g.nzOffs = rdIdx();
+    g.o_zoffs = b.put(f.take((size_t)g.nzOffs * eb), (size_t)g.nzOffs * eb, 16);
+    for (int i = 0; i < 5; i++) g.fchr[i] = rdIdx();
+    g.o_ftab = b.put(f.take((size_t)g.ftabLen * eb), (size_t)g.ftabLen * eb, 16);
+    g.o_eftab = b.put(f.take((size_t)g.eftabLen * eb), (size_t)g.eftabLen * eb, 16);
+}
+
+} // namespace
+
+Ht2Image* ht2_image_load(const char* base_c, std::string& err)
+{
+    try {
+        const std::string base(base_c);
+        Blob b;
+        b.alloc(sizeof(Ht2ImageHeader), 128);
+        Ht2ImageHeader h;
+        memset(&h, 0, sizeof(h));
+        h.magic = HT2_MAGIC;
+        h.version = HT2_IMAGE_VERSION;
+
+        // ---- .1.ht2 : global index ------------------------------------
+        FileBuf f1(base + ".1.ht2");
+        if (f1.u32() != 1) throw std::runtime_error("ht2: index has opposite endianness");
+        f1.u32(); // version word
+        uint32_t len = f1.u32(), gbwtLen = f1.u32(), numNodes = f1.u32();
+        int32_t lineRate = f1.i32();
+        f1.i32(); // linesPerSide
+        int32_t offRate = f1.i32();
+        int32_t ftabChars = f1.i32();
+        uint32_t eftabLen = f1.u32();
+        f1.i32(); // flags
+        initGeom(h.global, len, gbwtLen, numNodes, lineRate, offRate, ftabChars, eftabLen, 4);
+        readBody(f1, b, h.global);
+        // reference names: '\n'-separated, '\0'-terminated (gfm.h:6270-6300)
+        std::vector<std::string> names;
+        {
+            std::string cur;
+            while (!f1.eof()) {
+                char c = (char)*f1.take(1);
+                if (c == '\0') break;
+                if (c == '\n') { names.push_back(cur); cur.clear(); }
+                else cur.push_back(c);
+            }
+            if (!cur.empty()) names.push_back(cur);
+        }
+        h.nRefs = h.global.nPat;
+        while (names.size() < h.nRefs) names.push_back(std::to_string(names.size()));
+        {
+            std::string packed;
+            for (uint32_t i = 0; i < h.nRefs; i++) { packed += names[i]; packed.push_back('\0'); }
+            h.o_names = b.put(packed.data(), packed.size(), 16);
+            h.namesBytes = packed.size();
+        }
+
+        // ---- .2.ht2 : SA sample ---------------------------------------
+        {
+            FileBuf f2(base + ".2.ht2");
+            f2.u32(); // endian hint
+            size_t n = (size_t)h.global.offsLen * 4;
+            h.global.o_offs = b.put(f2.take(n), n, 128);
+        }
+
+        // ---- .5/.6.ht2 : local indexes --------------------------------
+        std::vector<Ht2Gfm> locals;
+        std::vector<uint32_t> localFirst(h.nRefs + 1, 0);
+        {
+            FileBuf f5(base + ".5.ht2", true), f6(base + ".6.ht2", true);
+            if (!f5.d.empty()) {
+                if (f5.u32() != 1) throw std::runtime_error("ht2: local index has opposite endianness");
+                if (!f6.d.empty()) f6.u32();
+                uint32_t nlocal = f5.u32();
+                int32_t llineRate = f5.i32();
+                f5.i32();
+                int32_t loffRate = f5.i32();
+                int32_t lftabChars = f5.i32();
+                f5.i32(); // flags
+                locals.resize(nlocal);
+                std::vector<uint32_t> counts(h.nRefs, 0);
+                for (uint32_t i = 0; i < nlocal; i++) {
+                    Ht2Gfm& g = locals[i];
+                    uint32_t tidx = f5.u32(), localOffset = f5.u32(), joinedOffset = f5.u32();
+                    uint32_t llen = f5.u16(), lgbwtLen = f5.u16(), lnumNodes = f5.u16(), leftabLen = f5.u16();
+                    initGeom(g, llen, lgbwtLen, lnumNodes, llineRate, loffRate, lftabChars, leftabLen, 2);
+                    g.tidx = tidx; g.localOffset = localOffset; g.joinedOffset = joinedOffset;
+                    if (tidx >= h.nRefs) throw std::runtime_error("ht2: local index tidx out of range");
+                    counts[tidx]++;
+                    if (llen == 0) continue; // empty local index (hgfm.h:1147-1150)
+                    readBody(f5, b, g);
+                    size_t n = (size_t)g.offsLen * 2;
+                    g.o_offs = b.put(f6.take(n), n, 16);
+                }
+                // the reference appends local indexes to the list of their
+                // reference in file order (hgfm.h:2637-2641)
+                for (uint32_t t = 0; t < h.nRefs; t++) localFirst[t + 1] = localFirst[t] + counts[t];
+                uint32_t prev = 0;
+                for (uint32_t i = 0; i < nlocal; i++) {
+                    if (locals[i].tidx < prev) throw std::runtime_error("ht2: local indexes not grouped by reference");
+                    prev = locals[i].tidx;
+                }
+            }
+        }
+        h.nLocal = (uint32_t)locals.size();
+        h.o_localGfm = b.put(locals.data(), locals.size() * sizeof(Ht2Gfm), 128);
+        h.o_localFirst = b.put(localFirst.data(), localFirst.size() * 4, 16);
+
+        // ---- .3/.4.ht2 : 2-bit reference ------------------------------
+        {
+            FileBuf f3(base + ".3.ht2");
+            if (f3.i32() != 1) throw std::runtime_error("ht2: reference has opposite endianness");
+            uint32_t nrec = f3.u32();
+            std::vector<Ht2RefRecord> recs(nrec);
+            std::vector<uint32_t> refRecOffs;
+            std::vector<uint64_t> refOffs;
+            std::vector<uint32_t> refLens;
+            uint64_t cumsz = 0;
+            uint32_t cumlen = 0;
+            for (uint32_t i = 0; i < nrec; i++) {
+                recs[i].off = f3.u32();
+                recs[i].len = f3.u32();
+                recs[i].first = *f3.take(1) ? 1 : 0;
+                recs[i].pad = 0;
+                if (recs[i].first) {
+                    refRecOffs.push_back(i);
+                    refOffs.push_back(cumsz);
+                    if (refRecOffs.size() > 1) refLens.push_back(cumlen);
+                    cumlen = 0;
+                } else if (i == 0) {
+                    throw std::runtime_error("ht2: first reference record is not marked 'first'");
+                }
+                cumsz += recs[i].len;
+                cumlen += recs[i].off + recs[i].len;
+            }
+            refRecOffs.push_back(nrec);
+            refOffs.push_back(cumsz);
+            refLens.push_back(cumlen);
+            if (refLens.size() != h.nRefs)
+                throw std::runtime_error("ht2: .3.ht2 reference count differs from .1.ht2");
+            h.nRecs = nrec;
+            h.o_recs = b.put(recs.data(), recs.size() * sizeof(Ht2RefRecord), 16);
+            h.o_refRecOffs = b.put(refRecOffs.data(), refRecOffs.size() * 4, 16);
+            h.o_refOffs = b.put(refOffs.data(), refOffs.size() * 8, 16);
+            h.o_refLens = b.put(refLens.data(), refLens.size() * 4, 16);
+            FileBuf f4(base + ".4.ht2");
+            size_t need = (size_t)((cumsz + 3) >> 2);
+            if (f4.d.size() < need) throw std::runtime_error("ht2: .4.ht2 shorter than .3.ht2 implies");
+            h.refBufBytes = need;
+            h.o_refBuf = b.put(f4.d.data(), need, 128);
+            b.alloc(16, 16);
+        }
+
+        // ---- .7.ht2 : ALTs (graph indexes) -----------------------------
+        {
+            FileBuf f7(base + ".7.ht2", true);
+            std::vector<Ht2Alt> alts;
+            if (f7.d.size() >= 8) {
+                f7.u32(); // endian hint
+                uint32_t nalt = f7.u32();
+                for (uint32_t i = 0; i < nalt && !f7.eof(); i++) {
+                    Ht2Alt a;
+                    a.pos = f7.u32(); a.type = f7.u32(); a.len = f7.u32(); a.reversed = 0;
+                    a.seq = f7.u64();
+                    alts.push_back(a);
+                }
+            }
+            h.nAlts = (uint32_t)alts.size();
+            h.o_alts = b.put(alts.data(), alts.size() * sizeof(Ht2Alt), 16);
+        }
+
+        b.alloc(0, 128);
+        h.totalBytes = b.d.size();
+        memcpy(b.d.data(), &h, sizeof(h));
+
+        Ht2Image* img = new Ht2Image();
+        img->blob.swap(b.d);
+        return img;
+    } catch (const std::exception& e) {
+        err = e.what();
+        return nullptr;
+    }
+}

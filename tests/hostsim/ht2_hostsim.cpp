@@ -1,0 +1,60 @@
+// ht2_hostsim.cpp -- TEST-ONLY host build of the per-read state machine.
+//
+// Compiles ht2_core.h for the CPU so parity against oracle/_ref can be
+// debugged on machines without a GPU.  Not part of the product: the shipped
+// library (libht2gpu.so) has no CPU path and fails loudly without CUDA.
+// usage: ht2_hostsim <index_base> <reads.fa> <out.sam> [--spliced]
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../hisat2_b200/csrc/ht2_host.h"
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: %s index reads.fa out.sam\n", argv[0]); return 2; }
+    std::string err;
+    Ht2Image* img = ht2_image_load(argv[1], err);
+    if (!img) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    std::vector<Ht2HostRead> reads;
+    if (!ht2_read_fasta(argv[2], reads, 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    Ht2Params P;
+    ht2_default_params(P, *img, true);
+    std::string sam;
+    ht2_sam_header(sam, *img);
+    Ht2Work* W = new Ht2Work();
+    Ht2Aligner A;
+    size_t nerr = 0;
+    uint64_t nLF = 0;
+    for (size_t i = 0; i < reads.size(); i++) {
+        Ht2HostRead& rd = reads[i];
+        rd.seed = ht2_gen_rand_seed(rd, 0);
+        int64_t minsc = ht2_minsc((uint32_t)rd.seq.size());
+        Ht2ReadFilters f = ht2_filters(rd, minsc);
+        Ht2ReadOut out;
+        out.err = 0;
+        A.bind(img->blob.data(), &P, W);
+        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0;
+        W->rnd.init(rd.seed);
+        A.paired = false; A.rightendonly = false;
+        A.nofw[0] = P.nofw; A.norc[0] = P.norc; A.nofw[1] = true; A.norc[1] = true;
+        A.minsc[0] = minsc; A.minsc[1] = HT2_IDX_MAX32;
+        A.sinkReset(false);
+        if (rd.seq.size() > HT2_MAX_RDLEN) W->err |= HT2_ERR_RDLEN;
+        if (f.pass() && !W->err) {
+            ht2_fill_read(W->rd[0], rd);
+            A.go();
+        }
+        out.rngLast = W->rnd.last;
+        out.err = W->err;
+        nLF += W->nLF;
+        if (W->err) { nerr++; fprintf(stderr, "read %zu (%s): err=0x%x\n", i, rd.name.c_str(), W->err); }
+        out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
+        out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
+        ht2_finish_unpaired(sam, *img, P, rd, f, out);
+    }
+    FILE* fo = fopen(argv[3], "wb");
+    fwrite(sam.data(), 1, sam.size(), fo);
+    fclose(fo);
+    fprintf(stderr, "reads=%zu errors=%zu LF=%llu\n", reads.size(), nerr, (unsigned long long)nLF);
+    return 0;
+}
