@@ -1,0 +1,306 @@
+"""ctypes bindings for include/ht2gpu.h plus small batching helpers.
+
+This is the reference-side binding a maintainer would add:
+plain pointers and sizes cross the boundary, no torch types.  The product path
+is the CUDA library; if it is missing or no CUDA device is usable the calls
+raise -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libht2gpu.so")
+_lib = None
+
+
+class Ht2GpuError(RuntimeError):
+    pass
+
+
+class Options(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "device", "no_spliced_alignment", "khits", "max_seeds", "secondary", "mp_max", "mp_min",
+        "sp_max", "sp_min", "np", "rdg_const", "rdg_linear", "rfg_const", "rfg_linear",
+        "ignore_quals", "nofw", "norc", "min_frag", "max_frag", "no_mixed", "no_discordant")] + [
+        ("seed", C.c_uint32), ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32)]
+
+
+class CReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("paired", C.c_int32), ("seq", C.c_void_p), ("qual", C.c_void_p),
+                ("offs", C.c_void_p), ("seeds", C.c_void_p)]
+
+
+EDIT_DTYPE = np.dtype([("pos", "<u4"), ("chr", "u1"), ("qchr", "u1"), ("type", "u1"), ("pad", "u1"), ("snp_id", "<u4")])
+ALN_DTYPE = np.dtype([("tidx", "<u4"), ("toff", "<u4"), ("score", "<i4"), ("fw", "u1"), ("mate", "u1"),
+                      ("n_edits", "<u2"), ("trim5", "<u2"), ("trim3", "<u2"), ("ref_extent", "<u4"), ("edit_off", "<u4")])
+READ_DTYPE = np.dtype([("aln_off", "<u4"), ("n_aln", "<u2", (2,)), ("pair_off", "<u4"), ("n_pairs", "<u4"),
+                       ("rng_state", "<u4"), ("err", "<u4"), ("n_lf", "<u4"), ("filt", "<u4")])
+
+
+class CResultBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("reads", C.c_void_p), ("n_alns", C.c_uint32), ("alns", C.c_void_p),
+                ("n_edits", C.c_uint32), ("edits", C.c_void_p), ("n_pairs", C.c_uint32), ("pairs", C.c_void_p),
+                ("ms_h2d", C.c_float), ("ms_kernel", C.c_float), ("ms_d2h", C.c_float),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32), ("pad", C.c_uint32),
+                ("priv", C.c_void_p)]
+
+
+EXPORTS = [
+    "ht2gpu_default_options", "ht2gpu_open", "ht2gpu_open_image", "ht2gpu_open_device_image", "ht2gpu_build_image",
+    "ht2gpu_free_image", "ht2gpu_image_data", "ht2gpu_image_bytes", "ht2gpu_device_image", "ht2gpu_align_batch",
+    "ht2gpu_align_resident", "ht2gpu_free_results", "ht2gpu_format_sam", "ht2gpu_sam_header", "ht2gpu_free_text",
+    "ht2gpu_num_refs", "ht2gpu_ref_name", "ht2gpu_ref_len", "ht2gpu_read_seed", "ht2gpu_last_error", "ht2gpu_close",
+]
+
+
+def load_library(path=None):
+    """dlopen the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIBPATH
+    if not os.path.exists(p):
+        raise Ht2GpuError("%s not found: run `python -m hisat2_b200.build` (no CPU fallback exists)" % p)
+    lib = C.CDLL(p)
+    lib.ht2gpu_default_options.argtypes = [C.POINTER(Options)]
+    lib.ht2gpu_open.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(C.c_void_p)]
+    lib.ht2gpu_open_image.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(Options), C.POINTER(C.c_void_p)]
+    lib.ht2gpu_open_device_image.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Options), C.POINTER(C.c_void_p)]
+    lib.ht2gpu_build_image.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+    lib.ht2gpu_free_image.argtypes = [C.c_void_p]
+    lib.ht2gpu_image_data.argtypes = [C.c_void_p]; lib.ht2gpu_image_data.restype = C.c_void_p
+    lib.ht2gpu_image_bytes.argtypes = [C.c_void_p]; lib.ht2gpu_image_bytes.restype = C.c_size_t
+    lib.ht2gpu_device_image.argtypes = [C.c_void_p]; lib.ht2gpu_device_image.restype = C.c_void_p
+    lib.ht2gpu_align_batch.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.POINTER(CResultBatch)]
+    lib.ht2gpu_align_resident.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_int, C.POINTER(CResultBatch)]
+    lib.ht2gpu_free_results.argtypes = [C.POINTER(CResultBatch)]
+    lib.ht2gpu_format_sam.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_char_p, C.POINTER(CResultBatch),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.ht2gpu_sam_header.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.ht2gpu_free_text.argtypes = [C.c_void_p]
+    lib.ht2gpu_num_refs.argtypes = [C.c_void_p]; lib.ht2gpu_num_refs.restype = C.c_uint32
+    lib.ht2gpu_ref_name.argtypes = [C.c_void_p, C.c_uint32]; lib.ht2gpu_ref_name.restype = C.c_char_p
+    lib.ht2gpu_ref_len.argtypes = [C.c_void_p, C.c_uint32]; lib.ht2gpu_ref_len.restype = C.c_uint32
+    lib.ht2gpu_read_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]
+    lib.ht2gpu_read_seed.restype = C.c_uint32
+    lib.ht2gpu_last_error.argtypes = [C.c_void_p]; lib.ht2gpu_last_error.restype = C.c_char_p
+    lib.ht2gpu_close.argtypes = [C.c_void_p]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+_ASC2DNA = np.zeros(256, dtype=np.uint8)
+_DNACAT = np.zeros(256, dtype=np.uint8)
+for _ch in b"ACGTacgt":
+    _DNACAT[_ch] = 1
+for _ch in b"BDHKMNRSVWXYbdhkmnrsvwxy":
+    _DNACAT[_ch] = 2
+_DNACAT[ord("-")] = 3
+for _ch, _v in ((b"Cc", 1), (b"Gg", 2), (b"Tt", 3), (b"Nn", 4)):
+    for _c in _ch:
+        _ASC2DNA[_c] = _v
+
+
+class ReadBatch(object):
+    """Structure-of-arrays read batch in host memory (see ht2gpu_read_batch_t).
+
+    seq: uint8 codes 0..4 concatenated; offs: uint64 (n+1); seeds: uint32 (n);
+    qual: uint8 ASCII or None (FASTA: all 'I'); names: list of bytes.
+    """
+
+    def __init__(self, seq, offs, seeds, names, qual=None, paired=False):
+        self.seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        self.offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        self.seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        self.qual = None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)
+        self.names = names
+        self.paired = bool(paired)
+        self.n = len(self.offs) - 1
+
+    def c_struct(self):
+        b = CReadBatch()
+        b.n_reads = self.n
+        b.paired = 1 if self.paired else 0
+        b.seq = self.seq.ctypes.data
+        b.qual = None if self.qual is None else self.qual.ctypes.data
+        b.offs = self.offs.ctypes.data
+        b.seeds = self.seeds.ctypes.data
+        return b
+
+    def names_blob(self):
+        return b"\0".join(self.names) + b"\0"
+
+    @staticmethod
+    def from_fasta(path, lib=None, global_seed=0, path2=None):
+        """Parse FASTA like FastaPatternSource::read (pat.cpp:725-849)."""
+        lib = lib or load_library()
+
+        def parse(p):
+            names, seqs = [], []
+            name, chunks, cnt = None, [], 0
+            with open(p, "rb") as f:
+                for line in f:
+                    if line.startswith(b">"):
+                        if name is not None:
+                            seqs.append(b"".join(chunks)); names.append(name)
+                        name = line[1:].rstrip(b"\r\n") or str(cnt).encode()
+                        cnt += 1
+                        chunks = []
+                    elif line[:1] in (b"#", b";"):
+                        continue
+                    else:
+                        chunks.append(line.rstrip(b"\r\n"))
+                if name is not None:
+                    seqs.append(b"".join(chunks)); names.append(name)
+            keep = [i for i, s in enumerate(seqs) if len(s) > 0]
+            return [names[i] for i in keep], [seqs[i] for i in keep]
+
+        names, seqs = parse(path)
+        if path2 is not None:
+            n2, s2 = parse(path2)
+            if len(n2) != len(names):
+                raise Ht2GpuError("mate files differ in read count")
+            # the reference appends /1 and /2 to mate names (pat.cpp fixName)
+            inames, iseqs = [], []
+            for a, b, c, d in zip(names, seqs, n2, s2):
+                inames += [a if a.endswith(b"/1") else a + b"/1", c if c.endswith(b"/2") else c + b"/2"]
+                iseqs += [b, d]
+            names, seqs = inames, iseqs
+        codes, offs = [], [0]
+        for s in seqs:
+            a = np.frombuffer(s, dtype=np.uint8)
+            a = a[_DNACAT[a] > 0]
+            codes.append(_ASC2DNA[a])
+            offs.append(offs[-1] + len(a))
+        seq = np.concatenate(codes) if codes else np.zeros(0, np.uint8)
+        seeds = np.zeros(len(names), dtype=np.uint32)
+        for i, nm in enumerate(names):
+            c = np.ascontiguousarray(codes[i])
+            seeds[i] = lib.ht2gpu_read_seed(c.ctypes.data, None, len(c), nm, global_seed)
+        return ReadBatch(seq, offs, seeds, names, None, paired=path2 is not None)
+
+
+class AlignResult(object):
+    """Owns one ht2gpu_result_batch_t; exposes zero-copy numpy views."""
+
+    def __init__(self, lib, cres):
+        self._lib = lib
+        self._c = cres
+        self.reads = self._view(cres.reads, cres.n_reads, READ_DTYPE)
+        self.alns = self._view(cres.alns, cres.n_alns, ALN_DTYPE)
+        self.edits = self._view(cres.edits, cres.n_edits, EDIT_DTYPE)
+        self.pairs = self._view(cres.pairs, cres.n_pairs * 2, np.dtype("<u2")).reshape(-1, 2)
+        self.ms_h2d, self.ms_kernel, self.ms_d2h = cres.ms_h2d, cres.ms_kernel, cres.ms_d2h
+        self.h2d_bytes, self.d2h_bytes, self.n_launches = cres.h2d_bytes, cres.d2h_bytes, cres.n_launches
+
+    @staticmethod
+    def _view(ptr, n, dt):
+        if not ptr or n == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_uint8 * (n * dt.itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    def close(self):
+        if self._c is not None:
+            self._lib.ht2gpu_free_results(C.byref(self._c))
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Index(object):
+    """Device-resident HISAT2 index + alignment entry points."""
+
+    def __init__(self, base=None, image=None, device_image=None, device=0, **opts):
+        self._lib = load_library()
+        o = Options()
+        self._lib.ht2gpu_default_options(C.byref(o))
+        o.device = device
+        for k, v in opts.items():
+            setattr(o, k, v)
+        self._h = C.c_void_p()
+        if base is not None:
+            rc = self._lib.ht2gpu_open(os.fsencode(base), C.byref(o), C.byref(self._h))
+        elif image is not None:
+            img = np.ascontiguousarray(image, dtype=np.uint8)
+            rc = self._lib.ht2gpu_open_image(img.ctypes.data, img.nbytes, C.byref(o), C.byref(self._h))
+        else:
+            ptr, nbytes, prefix = device_image
+            prefix = np.ascontiguousarray(prefix, dtype=np.uint8)
+            self._keep = prefix
+            rc = self._lib.ht2gpu_open_device_image(ptr, nbytes, prefix.ctypes.data, prefix.nbytes, C.byref(o), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.ht2gpu_last_error(self._h).decode() if self._h else "open failed"
+            self.close()
+            raise Ht2GpuError("ht2gpu_open rc=%d: %s" % (rc, msg))
+
+    @staticmethod
+    def build_image(base):
+        """Parse the .ht2 files into the packed image (host only; no GPU needed)."""
+        lib = load_library()
+        p, n = C.c_void_p(), C.c_size_t()
+        err = C.create_string_buffer(512)
+        rc = lib.ht2gpu_build_image(os.fsencode(base), C.byref(p), C.byref(n), err, 512)
+        if rc != 0:
+            raise Ht2GpuError("ht2gpu_build_image rc=%d: %s" % (rc, err.value.decode()))
+        arr = np.frombuffer((C.c_uint8 * n.value).from_address(p.value), dtype=np.uint8).copy()
+        lib.ht2gpu_free_image(p)
+        return arr
+
+    def image(self):
+        n = self._lib.ht2gpu_image_bytes(self._h)
+        p = self._lib.ht2gpu_image_data(self._h)
+        return np.frombuffer((C.c_uint8 * n).from_address(p), dtype=np.uint8)
+
+    def _check(self, rc, what, allow_capacity=False):
+        if rc != 0 and not (allow_capacity and rc == -4):
+            raise Ht2GpuError("%s rc=%d: %s" % (what, rc, self._lib.ht2gpu_last_error(self._h).decode()))
+
+    def align(self, batch, resident_iters=0, allow_capacity=False):
+        cb = batch.c_struct()
+        cr = CResultBatch()
+        if resident_iters > 0:
+            rc = self._lib.ht2gpu_align_resident(self._h, C.byref(cb), resident_iters, C.byref(cr))
+        else:
+            rc = self._lib.ht2gpu_align_batch(self._h, C.byref(cb), C.byref(cr))
+        res = AlignResult(self._lib, cr)
+        self._check(rc, "ht2gpu_align", allow_capacity)
+        return res
+
+    def sam_header(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.ht2gpu_sam_header(self._h, C.byref(p), C.byref(n)), "ht2gpu_sam_header")
+        s = C.string_at(p.value, n.value)
+        self._lib.ht2gpu_free_text(p)
+        return s
+
+    def format_sam(self, batch, res):
+        cb = batch.c_struct()
+        p, n = C.c_void_p(), C.c_size_t()
+        names = batch.names_blob()
+        self._check(self._lib.ht2gpu_format_sam(self._h, C.byref(cb), names, C.byref(res._c), C.byref(p), C.byref(n)),
+                    "ht2gpu_format_sam")
+        s = C.string_at(p.value, n.value)
+        self._lib.ht2gpu_free_text(p)
+        return s
+
+    def ref_names(self):
+        return [self._lib.ht2gpu_ref_name(self._h, i).decode() for i in range(self._lib.ht2gpu_num_refs(self._h))]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ht2gpu_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -21,15 +21,16 @@
 #ifndef HT2_MAX_RDLEN
 #define HT2_MAX_RDLEN 256
 #endif
-#define HT2_MAX_EDITS 32
+#define HT2_MAX_EDITS 24
 #define HT2_MAX_PHITS 28
 #define HT2_MAX_GHITS 24
-#define HT2_POOL 80
-#define HT2_MAX_SEARCHED 256
-#define HT2_MAX_RES 24
+#define HT2_POOL 40
+#define HT2_MAX_SEARCHED 128
+#define HT2_MAX_RES 32
 #define HT2_MAX_PAIRS 48
 #define HT2_MAX_COORDS 24
 #define HT2_MAX_DEPTH 128
+#define HT2_DEPTH_CAP 24   /* recursion depth the workspace/stack is sized for */
 #define HT2_REFBUF (HT2_MAX_RDLEN + 64)
 
 #define HT2_MIN_I64 ((int64_t)0x8000000000000000ll)
@@ -46,6 +47,8 @@
 #define HT2_ERR_COORDS  128u
 #define HT2_ERR_RDLEN   256u
 #define HT2_ERR_GRAPH   512u
+#define HT2_ERR_DEPTH  1024u
+#define HT2_ERR_OUTPUT 2048u
 
 enum { HT2_EDIT_READ_GAP = 1, HT2_EDIT_REF_GAP, HT2_EDIT_MM, HT2_EDIT_SNP, HT2_EDIT_SPL };
 enum { HT2_CANDIDATE_HIT = 1, HT2_PSEUDOGENE_HIT, HT2_ANCHOR_HIT }; // hi_aligner.h:96-100
@@ -155,6 +158,7 @@ struct Ht2Work {
     uint32_t    localindexatts;
     uint32_t    maxLocalindexatts;
     uint32_t    nLF;      // LF steps (boundary ranks) executed
+    uint32_t    maxPool, maxDepth, maxEdits; // high-water marks (sizing evidence)
     uint32_t    nSides;   // sides touched
 };
 
@@ -241,12 +245,12 @@ struct Ht2Aligner {
     }
     HT2_HD bool pushEdit(Ht2Hit& h, const Ht2Edit& e) {
         if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
-        h.edits[h.nedits++] = e; return true;
+        h.edits[h.nedits++] = e; if (h.nedits > W->maxEdits) W->maxEdits = h.nedits; return true;
     }
     HT2_HD bool insertEditFront(Ht2Hit& h, const Ht2Edit& e) {
         if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
         for (uint32_t i = h.nedits; i > 0; i--) h.edits[i] = h.edits[i - 1];
-        h.edits[0] = e; h.nedits++; return true;
+        h.edits[0] = e; h.nedits++; if (h.nedits > W->maxEdits) W->maxEdits = h.nedits; return true;
     }
     HT2_HD static bool editEq(const Ht2Edit& a, const Ht2Edit& b) { // Edit::operator== (edit.h)
         if (a.type != b.type) return false;
@@ -280,6 +284,7 @@ struct Ht2Aligner {
     }
     HT2_HD Ht2Hit* poolAlloc() {
         if (W->poolTop >= HT2_POOL) { W->err |= HT2_ERR_POOL; return &W->pool[HT2_POOL - 1]; }
+        if (W->poolTop + 1 > W->maxPool) W->maxPool = W->poolTop + 1;
         return &W->pool[W->poolTop++];
     }
 

@@ -20,6 +20,8 @@ HT2_HDN int64_t Ht2Aligner::hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, u
     }
     if (hit.score + cushion < minsc[rdi]) return maxsc;
     if (dep >= HT2_MAX_DEPTH) return maxsc;
+    if (dep > W->maxDepth) W->maxDepth = dep;
+    if (dep >= HT2_DEPTH_CAP) { W->err |= HT2_ERR_DEPTH; return maxsc; }
     if (hitoff == hit.rdoff - hit.trim5 && hitlen == hit.len + hit.trim5 + hit.trim3) {
         if (isSearched(hit, rdi)) return maxsc;
         addSearched(hit, rdi);

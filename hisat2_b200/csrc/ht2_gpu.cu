@@ -1,0 +1,579 @@
+// ht2_gpu.cu -- CUDA kernels + C ABI (include/ht2gpu.h) of the alignment path.
+//
+// Kernel inventory
+//   ht2_align_kernel : one thread runs one read (pair) through the complete
+//                      HI_Aligner::go state machine (ht2_core.h) against the
+//                      HBM-resident index image and appends its alignments to
+//                      the batch result pools.
+// Host code here only moves bytes and launches; it never aligns anything.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ht2gpu.h"
+#include "ht2_core.h"
+#include "ht2_host.h"
+#include "ht2_index.h"
+
+// ---------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------
+struct DevBatch {
+    const uint8_t*  seq;
+    const uint8_t*  qual;   // may be NULL
+    const uint64_t* offs;
+    const uint32_t* seeds;
+    const uint8_t*  filt;   // per read: 1 = passes all filters
+    const int32_t*  minsc;  // per read
+    uint32_t        n_units;
+    int32_t         paired;
+};
+
+struct DevOut {
+    ht2gpu_read_result_t* reads;
+    ht2gpu_aln_t*         alns;
+    ht2gpu_edit_t*        edits;
+    uint16_t*             pairs;
+    uint32_t              capAlns, capEdits, capPairs;
+    unsigned int*         counters; // [0] alns, [1] edits, [2] pairs
+};
+
+__device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, uint32_t ri, uint32_t& err)
+{
+    uint64_t o0 = b.offs[ri], o1 = b.offs[ri + 1];
+    uint32_t n = (uint32_t)(o1 - o0);
+    if (n > HT2_MAX_RDLEN) { err |= HT2_ERR_RDLEN; n = HT2_MAX_RDLEN; }
+    dst.len = n;
+    const uint8_t* s = b.seq + o0;
+    const uint8_t* q = b.qual ? b.qual + o0 : NULL;
+    for (uint32_t i = 0; i < n; i++) {
+        uint8_t c = s[i];
+        dst.seq[0][i] = c;
+        dst.seq[1][n - i - 1] = c < 4 ? (uint8_t)(c ^ 3) : (uint8_t)4;
+        uint8_t qq = q ? q[i] : (uint8_t)'I';
+        dst.qual[0][i] = qq;
+        dst.qual[1][n - i - 1] = qq;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    Ht2Work* W = work + tid;
+    Ht2Aligner A;
+    A.bind(blob, &P, W);
+    for (uint32_t u = tid; u < b.n_units; u += nthreads) {
+        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0;
+        W->maxPool = W->maxDepth = W->maxEdits = 0;
+        uint32_t filtBits = 0;
+        if (!b.paired) {
+            const uint32_t ri = u;
+            A.paired = false; A.rightendonly = false;
+            A.nofw[0] = P.nofw != 0; A.norc[0] = P.norc != 0; A.nofw[1] = true; A.norc[1] = true;
+            A.minsc[0] = b.minsc[ri]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
+            W->rnd.init(b.seeds[ri]);
+            A.sinkReset(false);
+            if (b.filt[ri]) {
+                filtBits = 1;
+                ht2_load_read(W->rd[0], b, ri, W->err);
+                if (!W->err) A.go();
+            }
+        } else {
+            const uint32_t r1 = 2 * u, r2 = 2 * u + 1;
+            bool f1 = b.filt[r1] != 0, f2 = b.filt[r2] != 0;
+            filtBits = (f1 ? 1u : 0u) | (f2 ? 2u : 0u);
+            // nofw/norc per mate (hisat2.cpp:3444-3447) for --fr
+            A.nofw[0] = P.gMate1fw ? (P.nofw != 0) : (P.norc != 0);
+            A.norc[0] = P.gMate1fw ? (P.norc != 0) : (P.nofw != 0);
+            A.nofw[1] = P.gMate2fw ? (P.nofw != 0) : (P.norc != 0);
+            A.norc[1] = P.gMate2fw ? (P.norc != 0) : (P.nofw != 0);
+            W->rnd.init((f1 && f2) ? (b.seeds[r1] ^ b.seeds[r2]) : b.seeds[r1]);
+            A.sinkReset(true);
+            if (f1 && f2) {
+                A.paired = true; A.rightendonly = false;
+                A.minsc[0] = b.minsc[r1]; A.minsc[1] = b.minsc[r2];
+                ht2_load_read(W->rd[0], b, r1, W->err);
+                ht2_load_read(W->rd[1], b, r2, W->err);
+                if (!W->err) A.go();
+            } else if (f1 || f2) {
+                A.paired = false; A.rightendonly = !f1;
+                uint32_t rr = f1 ? r1 : r2;
+                uint32_t m = f1 ? 0 : 1;
+                bool nf = A.nofw[m], nr = A.norc[m];
+                A.nofw[0] = nf; A.norc[0] = nr; A.nofw[1] = true; A.norc[1] = true;
+                A.minsc[0] = b.minsc[rr]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
+                ht2_load_read(W->rd[0], b, rr, W->err);
+                if (!W->err) A.go();
+            }
+        }
+        // ---- append results --------------------------------------------
+        ht2gpu_read_result_t rr;
+        rr.n_aln[0] = (uint16_t)W->nRes[0];
+        rr.n_aln[1] = (uint16_t)W->nRes[1];
+        rr.n_pairs = W->nPairs;
+        rr.rng_state = W->rnd.last;
+        rr.n_lf = W->nLF;
+        rr.filt = filtBits;
+        uint32_t nal = W->nRes[0] + W->nRes[1];
+        uint32_t ned = 0;
+        for (uint32_t m = 0; m < 2; m++)
+            for (uint32_t i = 0; i < W->nRes[m]; i++) ned += W->res[m][i].nedits;
+        uint32_t aoff = nal ? atomicAdd(&o.counters[0], nal) : 0;
+        uint32_t eoff = ned ? atomicAdd(&o.counters[1], ned) : 0;
+        uint32_t poff = W->nPairs ? atomicAdd(&o.counters[2], W->nPairs) : 0;
+        if (aoff + nal > o.capAlns || eoff + ned > o.capEdits || poff + W->nPairs > o.capPairs) {
+            W->err |= HT2_ERR_OUTPUT;
+            rr.n_aln[0] = rr.n_aln[1] = 0; rr.n_pairs = 0;
+        } else {
+            uint32_t a = aoff, e = eoff;
+            for (uint32_t m = 0; m < 2; m++) {
+                for (uint32_t i = 0; i < W->nRes[m]; i++) {
+                    const Ht2Res& r = W->res[m][i];
+                    ht2gpu_aln_t& d = o.alns[a++];
+                    d.tidx = r.tidx; d.toff = r.toff; d.score = (int32_t)r.score;
+                    d.fw = (uint8_t)r.fw; d.mate = (uint8_t)m; d.n_edits = (uint16_t)r.nedits;
+                    d.trim5 = (uint16_t)r.trim5p; d.trim3 = (uint16_t)r.trim3p;
+                    d.ref_extent = r.rfextent; d.edit_off = e;
+                    for (uint32_t k = 0; k < r.nedits; k++) {
+                        ht2gpu_edit_t& de = o.edits[e++];
+                        de.pos = r.edits[k].pos; de.chr = r.edits[k].chr; de.qchr = r.edits[k].qchr;
+                        de.type = r.edits[k].type; de.pad = 0; de.snp_id = r.edits[k].snpID;
+                    }
+                }
+            }
+            for (uint32_t i = 0; i < W->nPairs; i++) {
+                o.pairs[2 * (poff + i)] = W->pairs[i][0];
+                o.pairs[2 * (poff + i) + 1] = W->pairs[i][1];
+            }
+        }
+        rr.aln_off = aoff;
+        rr.pair_off = poff;
+        rr.err = W->err;
+        o.reads[u] = rr;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct ht2gpu_handle {
+    Ht2Image*      img;        // host copy (may hold only the header prefix when adopting a device image)
+    uint8_t*       dBlob;
+    bool           ownBlob;
+    size_t         blobBytes;
+    Ht2Params      P;
+    ht2gpu_options_t opt;
+    int            device;
+    int            nSM;
+    int            tpb, bpsm;
+    Ht2Work*       dWork;
+    size_t         nWork;
+    cudaStream_t   stream;
+    cudaEvent_t    ev[4];
+    std::string    err;
+    // device batch buffers (grown on demand)
+    uint8_t *dSeq, *dQual, *dFilt; uint64_t* dOffs; uint32_t* dSeeds; int32_t* dMinsc;
+    size_t capBases, capReads;
+    // device output buffers
+    ht2gpu_read_result_t* dReads; ht2gpu_aln_t* dAlns; ht2gpu_edit_t* dEdits; uint16_t* dPairs; unsigned int* dCounters;
+    size_t capUnits, capAlns, capEdits, capPairs;
+    // host staging for filters
+    std::vector<uint8_t> hFilt; std::vector<int32_t> hMinsc;
+};
+
+struct ResPriv {
+    std::vector<ht2gpu_read_result_t> reads;
+    std::vector<ht2gpu_aln_t> alns;
+    std::vector<ht2gpu_edit_t> edits;
+    std::vector<uint16_t> pairs;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return HT2GPU_ERR_CUDA; } } while (0)
+
+extern "C" void ht2gpu_default_options(ht2gpu_options_t* o)
+{
+    memset(o, 0, sizeof(*o));
+    o->device = 0;
+    o->no_spliced_alignment = 1;
+    o->mp_max = 6; o->mp_min = 2; o->sp_max = 2; o->sp_min = 1; o->np = 1;
+    o->rdg_const = 5; o->rdg_linear = 3; o->rfg_const = 5; o->rfg_linear = 3;
+    o->min_frag = 0; o->max_frag = 1000;
+}
+
+static void applyOptions(Ht2Params& P, const Ht2Image& img, const ht2gpu_options_t& o)
+{
+    ht2_default_params(P, img, o.no_spliced_alignment != 0);
+    if (o.khits > 0) P.khits = (uint32_t)o.khits;
+    P.kseeds = o.max_seeds > 0 ? (uint32_t)o.max_seeds : (P.khits * 2 > 5 ? P.khits * 2 : 5);
+    P.secondary = o.secondary ? 1 : 0;
+    P.mmpMax = o.mp_max; P.mmpMin = o.mp_min; P.scpMax = o.sp_max; P.scpMin = o.sp_min; P.npen = o.np;
+    P.rdGapConst = o.rdg_const; P.rdGapLinear = o.rdg_linear; P.rfGapConst = o.rfg_const; P.rfGapLinear = o.rfg_linear;
+    P.mmcostConstant = o.ignore_quals ? 1 : 0;
+    P.nofw = o.nofw ? 1 : 0; P.norc = o.norc ? 1 : 0;
+    P.minFrag = (uint32_t)o.min_frag; P.maxFrag = (uint32_t)o.max_frag;
+    P.mixed = o.no_mixed ? 0 : 1; P.discord = o.no_discordant ? 0 : 1;
+}
+
+static int finishOpen(ht2gpu_handle* h)
+{
+    const Ht2ImageHeader* H = h->img->header();
+    if (H->magic != HT2_MAGIC || H->version != HT2_IMAGE_VERSION) { h->err = "bad index image"; return HT2GPU_ERR_INDEX; }
+    if (!h->opt.no_spliced_alignment) { h->err = "spliced alignment is not implemented in this build; pass --no-spliced-alignment"; return HT2GPU_ERR_UNSUPPORTED; }
+    if (!H->global.linearFM) { h->err = "graph (SNP) indexes are not implemented in this build"; return HT2GPU_ERR_UNSUPPORTED; }
+    applyOptions(h->P, *h->img, h->opt);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->nSM = prop.multiProcessorCount;
+    h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 128;
+    if (h->tpb > 128) h->tpb = 128;
+    h->bpsm = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 4;
+    h->nWork = (size_t)h->nSM * h->bpsm * h->tpb;
+    CK(cudaMalloc(&h->dWork, h->nWork * sizeof(Ht2Work)));
+    CK(cudaMemset(h->dWork, 0, h->nWork * sizeof(Ht2Work)));
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, 40 * 1024));
+    CK(cudaStreamCreate(&h->stream));
+    for (int i = 0; i < 4; i++) CK(cudaEventCreate(&h->ev[i]));
+    return HT2GPU_OK;
+}
+
+static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
+{
+    ht2gpu_handle* h = new ht2gpu_handle();
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0;
+    h->stream = 0;
+    h->dSeq = h->dQual = h->dFilt = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->dMinsc = NULL; h->capBases = h->capReads = 0;
+    h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL;
+    h->capUnits = h->capAlns = h->capEdits = h->capPairs = 0;
+    if (opt) h->opt = *opt; else ht2gpu_default_options(&h->opt);
+    h->device = h->opt.device;
+    return h;
+}
+
+static int selectDevice(ht2gpu_handle* h)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        h->err = std::string("no usable CUDA device (this library has no CPU path): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return HT2GPU_ERR_CUDA;
+    }
+    CK(cudaSetDevice(h->device));
+    return HT2GPU_OK;
+}
+
+extern "C" int ht2gpu_build_image(const char* index_base, void** image, size_t* bytes, char* errbuf, size_t errbuf_len)
+{
+    std::string err;
+    Ht2Image* img = ht2_image_load(index_base, err);
+    if (!img) {
+        if (errbuf && errbuf_len) { strncpy(errbuf, err.c_str(), errbuf_len - 1); errbuf[errbuf_len - 1] = 0; }
+        return HT2GPU_ERR_INDEX;
+    }
+    void* p = malloc(img->blob.size());
+    memcpy(p, img->blob.data(), img->blob.size());
+    *image = p; *bytes = img->blob.size();
+    delete img;
+    return HT2GPU_OK;
+}
+extern "C" void ht2gpu_free_image(void* image) { free(image); }
+
+extern "C" int ht2gpu_open_image(const void* image, size_t bytes, const ht2gpu_options_t* opt, ht2gpu_handle_t** out)
+{
+    if (!image || !out || bytes < sizeof(Ht2ImageHeader)) return HT2GPU_ERR_ARG;
+    ht2gpu_handle* h = newHandle(opt);
+    *out = h;
+    int rc = selectDevice(h);
+    if (rc) return rc;
+    h->img = new Ht2Image();
+    h->img->blob.assign((const uint8_t*)image, (const uint8_t*)image + bytes);
+    h->blobBytes = bytes;
+    CK(cudaMalloc(&h->dBlob, bytes));
+    h->ownBlob = true;
+    CK(cudaMemcpy(h->dBlob, image, bytes, cudaMemcpyHostToDevice));
+    return finishOpen(h);
+}
+
+extern "C" int ht2gpu_open_device_image(const void* dev_image, size_t bytes, const void* host_prefix, size_t prefix_bytes,
+                                        const ht2gpu_options_t* opt, ht2gpu_handle_t** out)
+{
+    if (!dev_image || !out || !host_prefix || prefix_bytes < sizeof(Ht2ImageHeader)) return HT2GPU_ERR_ARG;
+    ht2gpu_handle* h = newHandle(opt);
+    *out = h;
+    int rc = selectDevice(h);
+    if (rc) return rc;
+    h->img = new Ht2Image();
+    // host copy is needed for reference names / lengths (SAM) -- fetch it from the device
+    h->img->blob.resize(bytes);
+    CK(cudaMemcpy(h->img->blob.data(), dev_image, bytes, cudaMemcpyDeviceToHost));
+    h->blobBytes = bytes;
+    h->dBlob = (uint8_t*)dev_image;
+    h->ownBlob = false;
+    return finishOpen(h);
+}
+
+extern "C" int ht2gpu_open(const char* index_base, const ht2gpu_options_t* opt, ht2gpu_handle_t** out)
+{
+    if (!index_base || !out) return HT2GPU_ERR_ARG;
+    ht2gpu_handle* h = newHandle(opt);
+    *out = h;
+    int rc = selectDevice(h);
+    if (rc) return rc;
+    h->img = ht2_image_load(index_base, h->err);
+    if (!h->img) return HT2GPU_ERR_INDEX;
+    h->blobBytes = h->img->blob.size();
+    CK(cudaMalloc(&h->dBlob, h->blobBytes));
+    h->ownBlob = true;
+    CK(cudaMemcpy(h->dBlob, h->img->blob.data(), h->blobBytes, cudaMemcpyHostToDevice));
+    return finishOpen(h);
+}
+
+extern "C" const void* ht2gpu_image_data(const ht2gpu_handle_t* h) { return h && h->img ? h->img->blob.data() : NULL; }
+extern "C" size_t ht2gpu_image_bytes(const ht2gpu_handle_t* h) { return h ? h->blobBytes : 0; }
+extern "C" const void* ht2gpu_device_image(const ht2gpu_handle_t* h) { return h ? h->dBlob : NULL; }
+extern "C" const char* ht2gpu_last_error(const ht2gpu_handle_t* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" uint32_t ht2gpu_num_refs(const ht2gpu_handle_t* h) { return h && h->img ? h->img->header()->nRefs : 0; }
+extern "C" const char* ht2gpu_ref_name(const ht2gpu_handle_t* h, uint32_t i) { return h->img->refName(i); }
+extern "C" uint32_t ht2gpu_ref_len(const ht2gpu_handle_t* h, uint32_t i) { return h->img->refPlen(i); }
+
+extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
+{
+    if (!h) return HT2GPU_OK;
+    if (h->dBlob && h->ownBlob) cudaFree(h->dBlob);
+    if (h->dWork) cudaFree(h->dWork);
+    cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dFilt); cudaFree(h->dOffs); cudaFree(h->dSeeds); cudaFree(h->dMinsc);
+    cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters);
+    if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
+    delete h->img;
+    delete h;
+    return HT2GPU_OK;
+}
+
+extern "C" uint32_t ht2gpu_read_seed(const uint8_t* seq, const uint8_t* qual, uint32_t len, const char* name, uint32_t global_seed)
+{
+    Ht2HostRead r;
+    r.seq.assign(seq, seq + len);
+    if (qual) r.qual.assign(qual, qual + len); else r.qual.assign(len, (uint8_t)'I');
+    r.name = name ? name : "";
+    return ht2_gen_rand_seed(r, global_seed);
+}
+
+template <typename T>
+static cudaError_t growBuf(T*& p, size_t& cap, size_t need, size_t slackNum = 5, size_t slackDen = 4)
+{
+    if (need <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = NULL;
+    size_t ncap = need * slackNum / slackDen + 16;
+    cudaError_t e = cudaMalloc(&p, ncap * sizeof(T));
+    cap = (e == cudaSuccess) ? ncap : 0;
+    return e;
+}
+
+// Stage a batch: per-read filters (host arithmetic, hisat2.cpp:3387-3440) + H2D copies.
+static int uploadBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint64_t& h2dBytes)
+{
+    const uint32_t n = b->n_reads;
+    const uint64_t nb = b->offs[n];
+    h->hFilt.resize(n); h->hMinsc.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t len = (uint32_t)(b->offs[i + 1] - b->offs[i]);
+        int64_t minsc = ht2_minsc(len);
+        Ht2HostRead tmp; // only seq is inspected by the N filter
+        const uint8_t* s = b->seq + b->offs[i];
+        size_t maxns = (size_t)((double)2.0f + (double)0.1f * (double)len);
+        size_t ns = 0; bool nf = true;
+        for (uint32_t k = 0; k < len; k++) if (s[k] == 4) { if (++ns > maxns) { nf = false; break; } }
+        bool lenf = !(len <= 0 || len < 2);
+        bool scf = (0 >= minsc);
+        h->hFilt[i] = (nf && lenf && scf) ? 1 : 0;
+        h->hMinsc[i] = (int32_t)minsc;
+    }
+    // sequence / quality / offsets / seeds share capBases / capReads growth
+    {
+        size_t c1 = h->capBases, c2 = h->capBases;
+        CK(growBuf(h->dSeq, c1, nb));
+        if (b->qual) { CK(growBuf(h->dQual, c2, nb)); }
+        h->capBases = c1;
+        size_t r1 = h->capReads, r2 = h->capReads, r3 = h->capReads, r4 = h->capReads;
+        CK(growBuf(h->dOffs, r1, (size_t)n + 1));
+        CK(growBuf(h->dSeeds, r2, (size_t)n + 1));
+        CK(growBuf(h->dFilt, r3, (size_t)n + 1));
+        CK(growBuf(h->dMinsc, r4, (size_t)n + 1));
+        h->capReads = r1;
+    }
+    CK(cudaMemcpyAsync(h->dSeq, b->seq, nb, cudaMemcpyHostToDevice, h->stream));
+    if (b->qual) CK(cudaMemcpyAsync(h->dQual, b->qual, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dOffs, b->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dSeeds, b->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dFilt, h->hFilt.data(), n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dMinsc, h->hMinsc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    h2dBytes = nb * (b->qual ? 2 : 1) + ((size_t)n + 1) * 8 + (size_t)n * 9;
+    return HT2GPU_OK;
+}
+
+static int ensureOut(ht2gpu_handle* h, uint32_t units, size_t alns, size_t edits, size_t pairs)
+{
+    CK(growBuf(h->dReads, h->capUnits, units));
+    CK(growBuf(h->dAlns, h->capAlns, alns));
+    CK(growBuf(h->dEdits, h->capEdits, edits));
+    size_t pc = h->capPairs * 2, need = pairs * 2;
+    if (need > pc || !h->dPairs) { CK(growBuf(h->dPairs, pc, need)); h->capPairs = pc / 2; }
+    if (!h->dCounters) CK(cudaMalloc(&h->dCounters, 4 * sizeof(unsigned int)));
+    return HT2GPU_OK;
+}
+
+static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units)
+{
+    DevBatch db;
+    db.seq = h->dSeq; db.qual = b->qual ? h->dQual : NULL; db.offs = h->dOffs; db.seeds = h->dSeeds;
+    db.filt = h->dFilt; db.minsc = h->dMinsc; db.n_units = units; db.paired = b->paired;
+    DevOut o;
+    o.reads = h->dReads; o.alns = h->dAlns; o.edits = h->dEdits; o.pairs = h->dPairs;
+    o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
+    o.counters = h->dCounters;
+    CK(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned int), h->stream));
+    uint32_t grid = (uint32_t)(h->nWork / h->tpb);
+    uint32_t needBlocks = (units + h->tpb - 1) / h->tpb;
+    if (needBlocks < grid) grid = needBlocks ? needBlocks : 1;
+    ht2_align_kernel<<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
+    CK(cudaGetLastError());
+    return HT2GPU_OK;
+}
+
+static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, ht2gpu_result_batch_t* res, bool timeCopies)
+{
+    if (!h || !b || !res) return HT2GPU_ERR_ARG;
+    if (b->paired && (b->n_reads & 1)) { h->err = "paired batch needs an even number of reads"; return HT2GPU_ERR_ARG; }
+    memset(res, 0, sizeof(*res));
+    if (b->n_reads == 0) return HT2GPU_OK;
+    CK(cudaSetDevice(h->device));
+    const uint32_t units = b->paired ? b->n_reads / 2 : b->n_reads;
+    uint64_t h2d = 0;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    int rc = uploadBatch(h, b, h2d);
+    if (rc) return rc;
+    size_t capA = (size_t)b->n_reads * 2 + 1024, capE = (size_t)b->n_reads * 4 + 4096, capP = (size_t)units * 2 + 1024;
+    unsigned int counters[4] = {0, 0, 0, 0};
+    float msKernel = 0;
+    uint32_t nLaunch = 0;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        rc = ensureOut(h, units, capA, capE, capP);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        for (int it = 0; it < iters; it++) { rc = launch(h, b, units); if (rc) return rc; nLaunch++; }
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        CK(cudaMemcpyAsync(counters, h->dCounters, sizeof(counters), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaEventElapsedTime(&msKernel, h->ev[1], h->ev[2]));
+        if (counters[0] <= h->capAlns && counters[1] <= h->capEdits && counters[2] <= h->capPairs) break;
+        // result pools were too small: grow and re-run (results are deterministic)
+        capA = counters[0] + 1024; capE = counters[1] + 4096; capP = counters[2] + 1024;
+    }
+    ResPriv* pv = new ResPriv();
+    pv->reads.resize(units); pv->alns.resize(counters[0]); pv->edits.resize(counters[1]); pv->pairs.resize((size_t)counters[2] * 2);
+    CK(cudaMemcpyAsync(pv->reads.data(), h->dReads, (size_t)units * sizeof(ht2gpu_read_result_t), cudaMemcpyDeviceToHost, h->stream));
+    if (counters[0]) CK(cudaMemcpyAsync(pv->alns.data(), h->dAlns, (size_t)counters[0] * sizeof(ht2gpu_aln_t), cudaMemcpyDeviceToHost, h->stream));
+    if (counters[1]) CK(cudaMemcpyAsync(pv->edits.data(), h->dEdits, (size_t)counters[1] * sizeof(ht2gpu_edit_t), cudaMemcpyDeviceToHost, h->stream));
+    if (counters[2]) CK(cudaMemcpyAsync(pv->pairs.data(), h->dPairs, (size_t)counters[2] * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float msH2d = 0, msD2h = 0;
+    CK(cudaEventElapsedTime(&msH2d, h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&msD2h, h->ev[2], h->ev[3]));
+    res->n_reads = units; res->reads = pv->reads.data();
+    res->n_alns = counters[0]; res->alns = pv->alns.data();
+    res->n_edits = counters[1]; res->edits = pv->edits.data();
+    res->n_pairs = counters[2]; res->pairs = pv->pairs.data();
+    res->ms_h2d = msH2d; res->ms_kernel = msKernel; res->ms_d2h = msD2h;
+    res->h2d_bytes = h2d;
+    res->d2h_bytes = (uint64_t)units * sizeof(ht2gpu_read_result_t) + (uint64_t)counters[0] * sizeof(ht2gpu_aln_t) +
+                     (uint64_t)counters[1] * sizeof(ht2gpu_edit_t) + (uint64_t)counters[2] * 4 + sizeof(counters);
+    res->n_launches = nLaunch;
+    res->priv = pv;
+    (void)timeCopies;
+    uint32_t anyErr = 0;
+    for (uint32_t i = 0; i < units; i++) anyErr |= pv->reads[i].err;
+    if (anyErr) {
+        char buf[128]; snprintf(buf, sizeof(buf), "device capacity exceeded for some reads (err bits 0x%x)", anyErr);
+        h->err = buf;
+        return HT2GPU_ERR_CAPACITY;
+    }
+    return HT2GPU_OK;
+}
+
+extern "C" int ht2gpu_align_batch(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, ht2gpu_result_batch_t* res)
+{
+    return runBatch(h, b, 1, res, true);
+}
+extern "C" int ht2gpu_align_resident(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, int iters, ht2gpu_result_batch_t* res)
+{
+    return runBatch(h, b, iters < 1 ? 1 : iters, res, false);
+}
+extern "C" void ht2gpu_free_results(ht2gpu_result_batch_t* res)
+{
+    if (res && res->priv) { delete (ResPriv*)res->priv; res->priv = NULL; }
+}
+
+// ---------------------------------------------------------------------------
+// host back end (SAM)
+// ---------------------------------------------------------------------------
+extern "C" int ht2gpu_sam_header(ht2gpu_handle_t* h, char** out, size_t* out_len)
+{
+    std::string s;
+    ht2_sam_header(s, *h->img);
+    char* p = (char*)malloc(s.size() + 1);
+    memcpy(p, s.data(), s.size()); p[s.size()] = 0;
+    *out = p; if (out_len) *out_len = s.size();
+    return HT2GPU_OK;
+}
+extern "C" void ht2gpu_free_text(char* p) { free(p); }
+
+extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, const char* names,
+                                 const ht2gpu_result_batch_t* res, char** out, size_t* out_len)
+{
+    if (!h || !b || !res || !names || !out) return HT2GPU_ERR_ARG;
+    if (b->paired) { h->err = "paired-end SAM formatting is not implemented yet"; return HT2GPU_ERR_UNSUPPORTED; }
+    std::string sam;
+    sam.reserve((size_t)b->n_reads * 400);
+    const char* nm = names;
+    for (uint32_t i = 0; i < b->n_reads; i++) {
+        Ht2HostRead rd;
+        rd.name = nm; nm += rd.name.size() + 1;
+        rd.mate = 0;
+        const uint8_t* s = b->seq + b->offs[i];
+        uint32_t len = (uint32_t)(b->offs[i + 1] - b->offs[i]);
+        rd.seq.assign(s, s + len);
+        if (b->qual) rd.qual.assign(b->qual + b->offs[i], b->qual + b->offs[i] + len); else rd.qual.assign(len, (uint8_t)'I');
+        int64_t minsc = ht2_minsc(len);
+        Ht2ReadFilters f = ht2_filters(rd, minsc);
+        const ht2gpu_read_result_t& rr = res->reads[i];
+        Ht2ReadOut o;
+        o.rngLast = rr.rng_state; o.err = rr.err;
+        uint32_t a = rr.aln_off;
+        for (uint32_t m = 0; m < 2; m++) {
+            for (uint32_t k = 0; k < rr.n_aln[m]; k++, a++) {
+                const ht2gpu_aln_t& al = res->alns[a];
+                Ht2Res r;
+                r.tidx = al.tidx; r.toff = al.toff; r.fw = al.fw; r.rdlen = len; r.score = al.score;
+                r.trim5p = al.trim5; r.trim3p = al.trim3; r.rfextent = al.ref_extent; r.nedits = al.n_edits;
+                for (uint32_t e = 0; e < al.n_edits && e < HT2_MAX_EDITS; e++) {
+                    const ht2gpu_edit_t& se = res->edits[al.edit_off + e];
+                    r.edits[e].pos = se.pos; r.edits[e].chr = se.chr; r.edits[e].qchr = se.qchr; r.edits[e].type = se.type;
+                    r.edits[e].pad = 0; r.edits[e].snpID = se.snp_id;
+                }
+                o.res[m].push_back(r);
+            }
+        }
+        ht2_finish_unpaired(sam, *h->img, h->P, rd, f, o);
+    }
+    char* p = (char*)malloc(sam.size() + 1);
+    memcpy(p, sam.data(), sam.size()); p[sam.size()] = 0;
+    *out = p; if (out_len) *out_len = sam.size();
+    return HT2GPU_OK;
+}

@@ -1,0 +1,186 @@
+/* ht2gpu.h -- C ABI of the B200 HISAT2 alignment hot path.
+ *
+ * The reference has no FFI for alignment ("Alignment APIs: TODO",
+ * hisat2lib/ht2.h:133-138); its seam is the per-thread C++ call
+ *     HI_Aligner::initRead(s) + HI_Aligner::go(...)   hi_aligner.h:3992-4067
+ * invoked once per read (pair) from multiseedSearchWorker_hisat2
+ * (hisat2.cpp:3532-3559), whose outputs are the AlnRes objects handed to
+ * AlnSinkWrap::report (aln_sink.h:2565) and finally printed by
+ * AlnSinkWrap::finishRead (aln_sink.h:1939).  This library replaces that seam
+ * with a batched call in the style of ht2.h (opaque handle, int error codes,
+ * plain pointers and sizes, caller-visible result buffers):
+ *
+ *   ht2gpu_open          <-> HGFM ctor + loadIntoMemory      hisat2.cpp:3779-3825
+ *                            BitPairReference ctor           hisat2.cpp:4040-4060
+ *   ht2gpu_align_batch   <-> nextReadPair .. go() per read   hisat2.cpp:3278-3559
+ *   ht2gpu_format_sam    <-> AlnSinkWrap::finishRead         aln_sink.h:1939-2560
+ *   ht2gpu_close         <-> destructors
+ *
+ * No CPU fallback exists: every entry point that needs the device fails with
+ * HT2GPU_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef HT2GPU_H_
+#define HT2GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HT2GPU_OK            0
+#define HT2GPU_ERR_ARG      -1
+#define HT2GPU_ERR_INDEX    -2   /* index files missing / malformed */
+#define HT2GPU_ERR_CUDA     -3   /* no usable CUDA device or a CUDA call failed */
+#define HT2GPU_ERR_CAPACITY -4   /* a read exceeded a fixed device-side capacity */
+#define HT2GPU_ERR_UNSUPPORTED -5
+
+typedef struct ht2gpu_handle ht2gpu_handle_t;
+
+/* Options mirror the hisat2 command line (hisat2.cpp:541-764).  Zero-initialise
+ * and call ht2gpu_default_options, then override. */
+typedef struct {
+    int32_t  device;                 /* CUDA device ordinal */
+    int32_t  no_spliced_alignment;   /* --no-spliced-alignment (must be 1 in this build) */
+    int32_t  khits;                  /* -k; 0 = index default (5 linear / 10 graph) */
+    int32_t  max_seeds;              /* --max-seeds; 0 = max(5, 2k) */
+    int32_t  secondary;              /* --secondary */
+    int32_t  mp_max, mp_min;         /* --mp 6,2 */
+    int32_t  sp_max, sp_min;         /* --sp 2,1 */
+    int32_t  np;                     /* --np 1 */
+    int32_t  rdg_const, rdg_linear;  /* --rdg 5,3 */
+    int32_t  rfg_const, rfg_linear;  /* --rfg 5,3 */
+    int32_t  ignore_quals;           /* --ignore-quals */
+    int32_t  nofw, norc;             /* --nofw / --norc */
+    int32_t  min_frag, max_frag;     /* -I / -X */
+    int32_t  no_mixed, no_discordant;
+    uint32_t seed;                   /* --seed */
+    int32_t  threads_per_block;      /* 0 = default */
+    int32_t  blocks_per_sm;          /* 0 = default */
+} ht2gpu_options_t;
+
+/* A batch of reads, structure-of-arrays, host memory.  Read i occupies
+ * seq[offs[i] .. offs[i+1]).  Bases are codes 0..4 (A,C,G,T,N) exactly as
+ * Read::patFw holds them (read.h:47); qual is raw ASCII (NULL = all 'I', what
+ * the FASTA parser assigns, pat.cpp:828).  seeds[i] is Read::seed
+ * (pat.h:55-91).  When paired != 0 reads 2j and 2j+1 are mate 1 / mate 2. */
+typedef struct {
+    uint32_t        n_reads;
+    int32_t         paired;
+    const uint8_t*  seq;
+    const uint8_t*  qual;
+    const uint64_t* offs;     /* n_reads + 1 entries */
+    const uint32_t* seeds;    /* n_reads entries (mate seeds are combined by the library) */
+} ht2gpu_read_batch_t;
+
+/* One nucleotide edit of an alignment: Edit (edit.h:41), positions in the
+ * 5'->3' orientation of the read, relative to the soft-trimmed 5' end
+ * (AlnRes::ned, aligner_result.cpp:111-118). */
+typedef struct {
+    uint32_t pos;
+    uint8_t  chr;      /* reference char, '-' for a reference gap */
+    uint8_t  qchr;     /* read char, '-' for a read gap */
+    uint8_t  type;     /* 1 read gap, 2 ref gap, 3 mismatch */
+    uint8_t  pad;
+    uint32_t snp_id;   /* ALT index or 0xffffffff */
+} ht2gpu_edit_t;
+
+/* One reported alignment == the arguments reportHit gives AlnRes::init
+ * (hi_aligner.h:6129-6166). */
+typedef struct {
+    uint32_t tidx;       /* reference id */
+    uint32_t toff;       /* 0-based leftmost reference offset */
+    int32_t  score;      /* AS:i */
+    uint8_t  fw;         /* aligned to forward strand */
+    uint8_t  mate;       /* 0 = mate 1 / unpaired, 1 = mate 2 */
+    uint16_t n_edits;
+    uint16_t trim5;      /* soft-trimmed bases at the read's 5' end */
+    uint16_t trim3;
+    uint32_t ref_extent; /* # reference chars covered */
+    uint32_t edit_off;   /* first edit in ht2gpu_result_batch_t.edits */
+} ht2gpu_aln_t;
+
+/* Per-read (pair) summary.  alns[aln_off .. aln_off+n_aln[0]) are mate-1 /
+ * unpaired alignments in the order the reference's sink received them
+ * (rs1u_), followed by n_aln[1] mate-2 alignments (rs2u_).  Concordant pairs
+ * (rs1_/rs2_) are index pairs into those two lists. */
+typedef struct {
+    uint32_t aln_off;
+    uint16_t n_aln[2];
+    uint32_t pair_off;
+    uint32_t n_pairs;
+    uint32_t rng_state;  /* RandomSource::last after go(); finishRead continues from it */
+    uint32_t err;        /* 0, or HT2_ERR_* capacity bits: results unreliable */
+    uint32_t n_lf;       /* LF-mapping steps executed (roofline accounting) */
+    uint32_t filt;       /* bit0 mate1 passed filters, bit1 mate2 passed filters; bits 4.. = YF reasons */
+} ht2gpu_read_result_t;
+
+typedef struct {
+    uint32_t              n_reads;   /* reads (SE) or pairs (PE) */
+    ht2gpu_read_result_t* reads;
+    uint32_t              n_alns;
+    ht2gpu_aln_t*         alns;
+    uint32_t              n_edits;
+    ht2gpu_edit_t*        edits;
+    uint32_t              n_pairs;
+    uint16_t*             pairs;     /* 2 entries per pair */
+    /* timings of the last call, milliseconds (CUDA events on the launch stream) */
+    float                 ms_h2d, ms_kernel, ms_d2h;
+    uint64_t              h2d_bytes, d2h_bytes;
+    uint32_t              n_launches;
+    uint32_t              pad;
+    void*                 priv;      /* owned by the library */
+} ht2gpu_result_batch_t;
+
+void ht2gpu_default_options(ht2gpu_options_t* opt);
+
+/* Parse <index_base>.[1-8].ht2, build the packed image, upload it to HBM. */
+int ht2gpu_open(const char* index_base, const ht2gpu_options_t* opt, ht2gpu_handle_t** out);
+/* Same, from an image produced by another rank (see ht2gpu_image_*): host copy. */
+int ht2gpu_open_image(const void* image, size_t bytes, const ht2gpu_options_t* opt, ht2gpu_handle_t** out);
+/* Same, adopting an image that already sits in device memory (e.g. the
+ * destination buffer of an NCCL broadcast).  The caller keeps ownership of
+ * dev_image and must keep it alive until ht2gpu_close. host_header is the first
+ * ht2gpu_image_header_bytes() bytes of the image in host memory. */
+int ht2gpu_open_device_image(const void* dev_image, size_t bytes, const void* host_image_prefix, size_t prefix_bytes,
+                             const ht2gpu_options_t* opt, ht2gpu_handle_t** out);
+/* Parse only (no device needed): returns a malloc'ed image the caller frees with ht2gpu_free_image. */
+int ht2gpu_build_image(const char* index_base, void** image, size_t* bytes, char* errbuf, size_t errbuf_len);
+void ht2gpu_free_image(void* image);
+const void* ht2gpu_image_data(const ht2gpu_handle_t* h);   /* host copy of the image */
+size_t ht2gpu_image_bytes(const ht2gpu_handle_t* h);
+const void* ht2gpu_device_image(const ht2gpu_handle_t* h); /* device pointer */
+
+/* Align a batch held in host memory: H2D copy, kernels, D2H copy. */
+int ht2gpu_align_batch(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, ht2gpu_result_batch_t* res);
+/* Upload a batch once and run the alignment kernels 'iters' times on the
+ * resident copy (device-timed throughput; results of the last iteration). */
+int ht2gpu_align_resident(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, int iters,
+                          ht2gpu_result_batch_t* res);
+void ht2gpu_free_results(ht2gpu_result_batch_t* res);
+
+/* Host back end: selection, MAPQ and SAM text for a batch (finishRead).
+ * names: n_reads '\0'-terminated read names, concatenated.  The returned
+ * buffer is malloc'ed; free with ht2gpu_free_text. */
+int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, const char* names,
+                      const ht2gpu_result_batch_t* res, char** out, size_t* out_len);
+int ht2gpu_sam_header(ht2gpu_handle_t* h, char** out, size_t* out_len);
+void ht2gpu_free_text(char* p);
+
+/* Reference-sequence names and lengths (ht2_index_getrefnames, ht2.h:108). */
+uint32_t ht2gpu_num_refs(const ht2gpu_handle_t* h);
+const char* ht2gpu_ref_name(const ht2gpu_handle_t* h, uint32_t i);
+uint32_t ht2gpu_ref_len(const ht2gpu_handle_t* h, uint32_t i);
+
+/* Per-read seed exactly as the reference derives it (pat.h:55-91). */
+uint32_t ht2gpu_read_seed(const uint8_t* seq, const uint8_t* qual, uint32_t len,
+                          const char* name, uint32_t global_seed);
+
+const char* ht2gpu_last_error(const ht2gpu_handle_t* h);
+int ht2gpu_close(ht2gpu_handle_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HT2GPU_H_ */

@@ -25,6 +25,7 @@ int main(int argc, char** argv) {
     Ht2Aligner A;
     size_t nerr = 0;
     uint64_t nLF = 0;
+    uint32_t mx[8] = {0,0,0,0,0,0,0,0};
     for (size_t i = 0; i < reads.size(); i++) {
         Ht2HostRead& rd = reads[i];
         rd.seed = ht2_gen_rand_seed(rd, 0);
@@ -33,7 +34,7 @@ int main(int argc, char** argv) {
         Ht2ReadOut out;
         out.err = 0;
         A.bind(img->blob.data(), &P, W);
-        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0;
+        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         W->rnd.init(rd.seed);
         A.paired = false; A.rightendonly = false;
         A.nofw[0] = P.nofw; A.norc[0] = P.norc; A.nofw[1] = true; A.norc[1] = true;
@@ -47,6 +48,8 @@ int main(int argc, char** argv) {
         out.rngLast = W->rnd.last;
         out.err = W->err;
         nLF += W->nLF;
+        { uint32_t v[8] = {W->maxPool, W->maxDepth, W->maxEdits, W->nSearched[0], W->nRes[0], W->nGenomeHits, W->hits[0][0].nhits, W->hits[0][1].nhits};
+          for (int k = 0; k < 8; k++) if (v[k] > mx[k]) mx[k] = v[k]; }
         if (W->err) { nerr++; fprintf(stderr, "read %zu (%s): err=0x%x\n", i, rd.name.c_str(), W->err); }
         out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
         out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
@@ -55,6 +58,6 @@ int main(int argc, char** argv) {
     FILE* fo = fopen(argv[3], "wb");
     fwrite(sam.data(), 1, sam.size(), fo);
     fclose(fo);
-    fprintf(stderr, "reads=%zu errors=%zu LF=%llu\n", reads.size(), nerr, (unsigned long long)nLF);
+    fprintf(stderr, "reads=%zu errors=%zu LF=%llu maxPool=%u maxDepth=%u maxEdits=%u maxSearched=%u maxRes=%u maxGH=%u maxPH=%u/%u sizeof(Work)=%zu\n", reads.size(), nerr, (unsigned long long)nLF, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[6], mx[7], sizeof(Ht2Work));
     return 0;
 }

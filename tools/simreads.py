@@ -71,6 +71,37 @@ def simulate(seq, n, seed=1, rdlen=101, fmin=200, fmax=400, sub=0.005):
     return m1, m2
 
 
+def add_noise(reads, seed, indel=0.0, nrate=0.0, ragged=False):
+    """Return a list of byte strings: reads with random short indels, Ns and
+    (optionally) ragged lengths -- edge cases for the parity tests."""
+    rng = np.random.default_rng(seed + 7919)
+    out = []
+    for r in reads:
+        b = bytearray(r.tobytes())
+        if indel > 0 and rng.random() < indel * len(b):
+            pos = int(rng.integers(5, len(b) - 5))
+            ln = int(rng.integers(1, 4))
+            if rng.random() < 0.5:
+                del b[pos:pos + ln]
+            else:
+                b[pos:pos] = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), ln))
+        if nrate > 0:
+            for i in np.nonzero(rng.random(len(b)) < nrate)[0]:
+                b[int(i)] = ord("N")
+        if ragged:
+            cut = int(rng.integers(0, 70))
+            if cut and rng.random() < 0.5:
+                b = b[:len(b) - cut]
+        out.append(bytes(b))
+    return out
+
+
+def write_fasta_list(path, reads, prefix="r"):
+    with open(path, "wb") as f:
+        for i, r in enumerate(reads):
+            f.write(b">%s%d\n%s\n" % (prefix.encode(), i, r))
+
+
 def write_fasta(path, reads, prefix="r"):
     n, rdlen = reads.shape
     with open(path, "wb") as f:
@@ -93,9 +124,18 @@ def main():
     ap.add_argument("out_prefix")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--paired", action="store_true")
+    ap.add_argument("--indel", type=float, default=0.0, help="per-base chance of one short indel per read")
+    ap.add_argument("--nrate", type=float, default=0.0, help="per-base N rate")
+    ap.add_argument("--sub", type=float, default=0.005)
+    ap.add_argument("--ragged", action="store_true", help="randomly truncate half of the reads")
     a = ap.parse_args()
     _, seq = load_fasta_codes(a.reference)
-    m1, m2 = simulate(seq, a.n, a.seed)
+    m1, m2 = simulate(seq, a.n, a.seed, sub=a.sub)
+    if a.indel > 0 or a.nrate > 0 or a.ragged:
+        write_fasta_list(a.out_prefix + "_1.fa", add_noise(m1, a.seed, a.indel, a.nrate, a.ragged))
+        if a.paired:
+            write_fasta_list(a.out_prefix + "_2.fa", add_noise(m2, a.seed + 1, a.indel, a.nrate, a.ragged))
+        return
     write_fasta(a.out_prefix + "_1.fa", m1)
     if a.paired:
         write_fasta(a.out_prefix + "_2.fa", m2)
