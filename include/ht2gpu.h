@@ -141,8 +141,8 @@ int ht2gpu_open(const char* index_base, const ht2gpu_options_t* opt, ht2gpu_hand
 int ht2gpu_open_image(const void* image, size_t bytes, const ht2gpu_options_t* opt, ht2gpu_handle_t** out);
 /* Same, adopting an image that already sits in device memory (e.g. the
  * destination buffer of an NCCL broadcast).  The caller keeps ownership of
- * dev_image and must keep it alive until ht2gpu_close. host_header is the first
- * ht2gpu_image_header_bytes() bytes of the image in host memory. */
+ * dev_image and must keep it alive until ht2gpu_close. host_image_prefix is the
+ * leading part (at least the header) of the same image in host memory. */
 int ht2gpu_open_device_image(const void* dev_image, size_t bytes, const void* host_image_prefix, size_t prefix_bytes,
                              const ht2gpu_options_t* opt, ht2gpu_handle_t** out);
 /* Parse only (no device needed): returns a malloc'ed image the caller frees with ht2gpu_free_image. */

@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""Regenerate the committed golden fixtures with the UNMODIFIED reference
+(oracle/_ref, built by oracle/Makefile from /root/reference).
+
+  tiny.fa            two small references cut from the example region
+                     (chrA with a mutated duplicate -> multi-mappers, chrB with
+                     an N gap -> several rstarts fragments)
+  tiny.{1..8}.ht2    hisat2-build-s --ftabchars 7 tiny.fa tiny   (linear index)
+  tiny_se.fa         700 single-end reads: clean, 2% substitutions, indels, Ns,
+                     ragged lengths, a few unalignable
+  tiny_se.sam        hisat2-align-s --no-spliced-alignment -f -x tiny -U tiny_se.fa
+  tiny_pe_{1,2}.fa / tiny_pe.sam   300 pairs, same flags with -1/-2
+  tiny_dump.txt      oracle/_ref/ref_dump tiny tiny_se.fa 1   (kernel-level vectors)
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os, subprocess, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import simreads
+G = os.path.join(ROOT, "tests", "golden")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+def main():
+    _, seq = simreads.load_fasta_codes(os.path.join(REF, "data", "22_20-21M.fa"))
+    rng = np.random.default_rng(11)
+    def mutate(a, rate):
+        a = a.copy()
+        m = rng.random(len(a)) < rate
+        a[m] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, m.sum())]
+        return a
+    s1 = seq[100000:125000]; s2 = seq[300000:315000]
+    chrA = np.concatenate([s1, s2, mutate(s1[5000:15000], 0.01)])
+    s3 = seq[700000:712000]; s4 = seq[820000:838000]
+    chrB = np.concatenate([s3, np.full(137, ord("N"), np.uint8), s4])
+    with open(os.path.join(G, "tiny.fa"), "wb") as f:
+        for name, s in (("chrA test contig", chrA), ("chrB", chrB)):
+            f.write(b">" + name.encode() + b"\n")
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60].tobytes() + b"\n")
+    subprocess.run([os.path.join(REF, "hisat2-build-s"), "-q", "--ftabchars", "7", "tiny.fa", "tiny"], check=True, cwd=G,
+                   stdout=subprocess.DEVNULL)
+    # reads: sample from the concatenation of both contigs (N-containing fragments are skipped by simulate)
+    cat = np.concatenate([chrA, np.full(500, ord("N"), np.uint8), chrB])
+    a1, _ = simreads.simulate(cat, 250, seed=21, fmin=120, fmax=300, sub=0.0)
+    b1, _ = simreads.simulate(cat, 250, seed=22, fmin=120, fmax=300, sub=0.02)
+    c1, _ = simreads.simulate(cat, 180, seed=23, fmin=120, fmax=300, sub=0.01)
+    rnd = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), (20, 101))
+    se = [r.tobytes() for r in a1] + [r.tobytes() for r in b1] + \
+        simreads.add_noise(c1, 5, indel=0.006, nrate=0.004, ragged=True) + [r.tobytes() for r in rnd]
+    simreads.write_fasta_list(os.path.join(G, "tiny_se.fa"), se, prefix="s")
+    p1, p2 = simreads.simulate(cat, 300, seed=31, fmin=150, fmax=400, sub=0.01)
+    q1 = simreads.add_noise(p1, 6, indel=0.002, nrate=0.001)
+    q2 = simreads.add_noise(p2, 7, indel=0.002, nrate=0.001)
+    simreads.write_fasta_list(os.path.join(G, "tiny_pe_1.fa"), q1, prefix="p")
+    simreads.write_fasta_list(os.path.join(G, "tiny_pe_2.fa"), q2, prefix="p")
+    al = os.path.join(REF, "hisat2-align-s")
+    def sam(args, out):
+        subprocess.run([al, "--no-spliced-alignment", "-f", "-x", "tiny"] + args + ["-S", out + ".tmp"], check=True, cwd=G,
+                       stderr=subprocess.DEVNULL)
+        with open(os.path.join(G, out + ".tmp")) as fi, open(os.path.join(G, out), "w") as fo:
+            fo.writelines(l for l in fi if not l.startswith("@PG"))
+        os.remove(os.path.join(G, out + ".tmp"))
+    sam(["-U", "tiny_se.fa"], "tiny_se.sam")
+    sam(["-1", "tiny_pe_1.fa", "-2", "tiny_pe_2.fa"], "tiny_pe.sam")
+    # kernel-level vectors: reads 0..99 (clean), 250..349 (2% subs), 500..599 (indels/Ns/ragged)
+    keep = set(list(range(0, 100)) + list(range(250, 350)) + list(range(500, 600)))
+    for mode, name in (("1", "tiny_dump.txt"), ("0", "tiny_dump_spliced.txt")):
+        out = subprocess.run([os.path.join(REF, "ref_dump"), "tiny", "tiny_se.fa", mode], check=True, cwd=G,
+                             stdout=subprocess.PIPE).stdout.decode().splitlines(True)
+        with open(os.path.join(G, name), "w") as fo:
+            fo.writelines(l for l in out if int(l.split()[1]) in keep)
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""CPU-side tests (no GPU): oracle vs golden vectors, host logic, C ABI."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, sam_lines
+
+KEEP = set(list(range(0, 100)) + list(range(250, 350)) + list(range(500, 600)))
+
+
+def test_oracle_matches_reference_dump(oracle_bin):
+    """oracle/ht2_oracle.c == golden vectors dumped from the unmodified
+    reference's partialSearch/getOffset/joinedToTextOff (tests/golden/make_golden.py)."""
+    for mode, name in (("1", "tiny_dump.txt"), ("0", "tiny_dump_spliced.txt")):
+        out = subprocess.run([oracle_bin, "dump", "tiny", "tiny_se.fa", mode], cwd=GOLDEN, check=True,
+                             stdout=subprocess.PIPE).stdout.decode().splitlines(True)
+        got = [l for l in out if int(l.split()[1]) in KEEP]
+        want = open(os.path.join(GOLDEN, name)).readlines()
+        assert len(want) > 1000
+        assert got == want
+
+
+def test_host_state_machine_matches_golden_sam(hostsim_bin, tmp_path):
+    """Host build of ht2_core.h + the host SAM back end reproduce the reference's
+    SAM byte for byte on the tiny fixture (two references, N gap, indels, Ns,
+    ragged lengths, unalignable reads)."""
+    out = str(tmp_path / "se.sam")
+    subprocess.run([hostsim_bin, "tiny", "tiny_se.fa", out], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL)
+    assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_se.sam"), "rb").read())
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    from hisat2_b200 import api
+    assert sorted(api.EXPORTS) == declared
+
+
+def test_image_build_is_host_only_and_consistent(lib):
+    from hisat2_b200 import api
+    img = api.Index.build_image(os.path.join(GOLDEN, "tiny"))
+    assert img[:4].tobytes() == b"HT2B"
+    hdr = np.frombuffer(img[:16].tobytes(), dtype="<u4")
+    assert hdr[1] == 2  # image version
+    total = int(np.frombuffer(img[8:16].tobytes(), dtype="<u8")[0])
+    assert total == img.nbytes and total % 128 == 0
+    # global geometry (Ht2Gfm at offset 16): len, gbwtLen, numNodes, eftabLen, linearFM, sideSz, sideGbwtSz, sideGbwtLen
+    g = np.frombuffer(img[16:16 + 32].tobytes(), dtype="<u4")
+    raw = np.fromfile(os.path.join(GOLDEN, "tiny.1.ht2"), dtype="<u4", count=11)
+    assert g[0] == raw[2] and g[1] == raw[3]
+    assert g[4] == 1 and g[5] == 64 and g[6] == 48 and g[7] == 192
+    with pytest.raises(api.Ht2GpuError):
+        api.Index.build_image(os.path.join(GOLDEN, "does_not_exist"))
+
+
+def test_open_fails_loudly_without_cuda(lib):
+    """No CPU fallback: without a usable device open() must fail."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from hisat2_b200 import api
+    with pytest.raises(api.Ht2GpuError) as e:
+        api.Index(os.path.join(GOLDEN, "tiny"))
+    assert "CUDA" in str(e.value)
+
+
+def test_read_seed_matches_reference_formula(lib):
+    """genRandSeed (pat.h:55-91) known answer computed by hand from the formula."""
+    seq = np.array([0, 1, 2, 3, 4, 0], dtype=np.uint8)
+    name = b"r7/1"
+    want = ((0 + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83) & 0xffffffff
+    for i, p in enumerate(seq):
+        want ^= (int(p) << ((i & 15) << 1)) & 0xffffffff
+    for i in range(len(seq)):
+        want ^= (ord("I") << ((i & 3) << 3)) & 0xffffffff
+    for i, ch in enumerate(name):
+        if ch == ord("/"):
+            break
+        want ^= (ch << ((i & 3) << 3)) & 0xffffffff
+    got = lib.ht2gpu_read_seed(seq.ctypes.data, None, len(seq), name, 0)
+    assert got == want
+
+
+def test_fasta_parser_and_simulator_are_deterministic(lib):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import simreads
+    from hisat2_b200 import api
+    _, seq = simreads.load_fasta_codes(os.path.join(GOLDEN, "tiny.fa"))
+    a1, a2 = simreads.simulate(seq, 50, seed=3)
+    b1, b2 = simreads.simulate(seq, 50, seed=3)
+    assert (a1 == b1).all() and (a2 == b2).all() and a1.shape == (50, 101)
+    batch = api.ReadBatch.from_fasta(os.path.join(GOLDEN, "tiny_se.fa"))
+    assert batch.n == 700 and batch.offs[-1] == len(batch.seq) and batch.seq.max() <= 4
+    assert batch.names[0] == b"s0"
+
+
+def test_shard_ranges_cover_input_in_order():
+    from hisat2_b200.parallel import shard_range
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            pos = 0
+            for r in range(w):
+                lo, hi = shard_range(n, r, w)
+                assert lo == pos and hi >= lo
+                pos = hi
+            assert pos == n
+
+
+def _gloo_worker(rank, world, port, tmpdir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hisat2_b200 import api
+    from hisat2_b200.parallel import broadcast_image, gather_bytes, shard_range
+    img = api.Index.build_image(os.path.join(GOLDEN, "tiny")) if rank == 0 else None
+    t = broadcast_image(img, rank)
+    ref = api.Index.build_image(os.path.join(GOLDEN, "tiny"))
+    assert t.numpy().tobytes() == ref.tobytes()
+    lines = open(os.path.join(GOLDEN, "tiny_se.sam"), "rb").read().splitlines(True)
+    recs = [l for l in lines if not l.startswith(b"@")]
+    lo, hi = shard_range(len(recs), rank, world)
+    chunks = gather_bytes(b"".join(recs[lo:hi]), rank, world)
+    if rank == 0:
+        assert b"".join(chunks) == b"".join(recs)
+        open(os.path.join(tmpdir, "ok"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_broadcast_and_ordered_gather(lib, tmp_path):
+    """world_size-2 CPU run of the multi-GPU plumbing: image broadcast + rank-ordered gather."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok"))
