@@ -36,7 +36,7 @@ EDIT_DTYPE = np.dtype([("pos", "<u4"), ("chr", "u1"), ("qchr", "u1"), ("type", "
 ALN_DTYPE = np.dtype([("tidx", "<u4"), ("toff", "<u4"), ("score", "<i4"), ("fw", "u1"), ("mate", "u1"),
                       ("n_edits", "<u2"), ("trim5", "<u2"), ("trim3", "<u2"), ("ref_extent", "<u4"), ("edit_off", "<u4")])
 READ_DTYPE = np.dtype([("aln_off", "<u4"), ("n_aln", "<u2", (2,)), ("pair_off", "<u4"), ("n_pairs", "<u4"),
-                       ("rng_state", "<u4"), ("err", "<u4"), ("n_lf", "<u4"), ("filt", "<u4")])
+                       ("rng_state", "<u4"), ("err", "<u4"), ("n_lf", "<u4"), ("alg_bytes", "<u4"), ("filt", "<u4")])
 
 
 class CResultBatch(C.Structure):

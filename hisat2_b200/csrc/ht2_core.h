@@ -22,7 +22,7 @@
 #define HT2_MAX_RDLEN 256
 #endif
 #define HT2_MAX_EDITS 24
-#define HT2_MAX_PHITS 28
+#define HT2_MAX_PHITS 64
 #define HT2_MAX_GHITS 24
 #define HT2_POOL 40
 #define HT2_MAX_SEARCHED 128
@@ -160,6 +160,7 @@ struct Ht2Work {
     uint32_t    nLF;      // LF steps (boundary ranks) executed
     uint32_t    maxPool, maxDepth, maxEdits; // high-water marks (sizing evidence)
     uint32_t    nSides;   // sides touched
+    uint32_t    algBytes; // algorithmic bytes: sides*sideSz + ftab/eftab entries + SA samples + 2-bit ref bytes
 };
 
 // ------------------------------------------------------------------------
@@ -360,6 +361,7 @@ struct Ht2Aligner {
     HT2_HD uint32_t refLen(uint32_t tidx) const { return ((const uint32_t*)(blob + H->o_refLens))[tidx]; }
     // dest[i] = base at toff+i for i<count; 4 inside N gaps / past the end.
     HT2_HD void getStretch(uint8_t* dest, uint32_t tidx, uint32_t toff, uint32_t count) const {
+        W->algBytes += (count + 3) >> 2;
         const Ht2RefRecord* recs = (const Ht2RefRecord*)(blob + H->o_recs);
         const uint32_t* recOffs = (const uint32_t*)(blob + H->o_refRecOffs);
         const uint64_t* refOffs = (const uint64_t*)(blob + H->o_refOffs);
@@ -425,11 +427,13 @@ struct Ht2Aligner {
                        uint32_t& ntop, uint32_t& nbot, uint32_t& nntop, uint32_t& nnbot) {
         if (bot - top != 1) {
             W->nLF += 2;
+            W->algBytes += ((top / fm.g->sideGbwtLen) == (bot / fm.g->sideGbwtLen) ? 1u : 2u) * fm.g->sideSz;
             ntop = ht2_lf(fm, top, c);
             nbot = ht2_lf(fm, bot, c);
             nntop = ntop; nnbot = nbot;
         } else {
             W->nLF += 1;
+            W->algBytes += fm.g->sideSz;
             if (ht2_rowL(fm, top) != c || ht2_is_zoff(fm, top)) { ntop = nbot = nntop = nnbot = 0; return; }
             ntop = ht2_lf(fm, top, c);
             nbot = (uint32_t)(IT)(ntop + 1);
@@ -472,6 +476,7 @@ struct Ht2Aligner {
         }
         uint32_t top = 0, bot = 0, ntop = 0, nbot = 0;
         ht2_ftab_lohi(gfm, seq, len - dep - ftabLen, top, bot);
+        W->algBytes += 8;
         dep += ftabLen;
         if (top >= bot) {
             hit.cur = dep;
@@ -558,6 +563,7 @@ struct Ht2Aligner {
         }
         uint32_t rtop = 0, rbot = 0, ntop = 0, nbot = 0;
         ht2_ftab_lohi(fm, seq, len - dep - ftabLen, rtop, rbot);
+        W->algBytes += 2 * (uint32_t)sizeof(IT);
         dep += ftabLen;
         if (rtop >= rbot) { hitlen = ftabLen; return 0; }
         while (dep < len) {
@@ -591,11 +597,13 @@ struct Ht2Aligner {
         while (true) {
             if (ht2_is_zoff(fm, row)) return (uint32_t)(IT)(0 + steps);
             if ((row & fm.g->offMask) == row) {
+                W->algBytes += (uint32_t)sizeof(IT);
                 return (uint32_t)(IT)(fm.offs[row >> fm.g->offRate] + steps);
             }
             int c = ht2_rowL(fm, row);
             row = ht2_lf(fm, row, c);
             W->nLF++;
+            W->algBytes += fm.g->sideSz;
             steps++;
         }
     }

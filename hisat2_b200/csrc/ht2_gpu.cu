@@ -69,7 +69,7 @@ ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevO
     Ht2Aligner A;
     A.bind(blob, &P, W);
     for (uint32_t u = tid; u < b.n_units; u += nthreads) {
-        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0;
+        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0;
         W->maxPool = W->maxDepth = W->maxEdits = 0;
         uint32_t filtBits = 0;
         if (!b.paired) {
@@ -119,6 +119,7 @@ ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevO
         rr.n_pairs = W->nPairs;
         rr.rng_state = W->rnd.last;
         rr.n_lf = W->nLF;
+        rr.alg_bytes = W->algBytes;
         rr.filt = filtBits;
         uint32_t nal = W->nRes[0] + W->nRes[1];
         uint32_t ned = 0;

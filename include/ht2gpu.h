@@ -113,6 +113,7 @@ typedef struct {
     uint32_t rng_state;  /* RandomSource::last after go(); finishRead continues from it */
     uint32_t err;        /* 0, or HT2_ERR_* capacity bits: results unreliable */
     uint32_t n_lf;       /* LF-mapping steps executed (roofline accounting) */
+    uint32_t alg_bytes;  /* algorithmic bytes touched: sides*sideSz + ftab + SA samples + 2-bit ref */
     uint32_t filt;       /* bit0 mate1 passed filters, bit1 mate2 passed filters; bits 4.. = YF reasons */
 } ht2gpu_read_result_t;
 

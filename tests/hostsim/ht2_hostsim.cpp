@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
         Ht2ReadOut out;
         out.err = 0;
         A.bind(img->blob.data(), &P, W);
-        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
+        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         W->rnd.init(rd.seed);
         A.paired = false; A.rightendonly = false;
         A.nofw[0] = P.nofw; A.norc[0] = P.norc; A.nofw[1] = true; A.norc[1] = true;

@@ -1,0 +1,173 @@
+"""GPU parity tests: every case goes through the C ABI (ctypes) on cuda:0 and is
+compared with (a) the committed golden output of the unmodified reference,
+(b) the reference binary run on the same box (oracle/_ref), (c) size-independent
+properties at full batch sizes."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REFDIR, ROOT, sam_lines
+
+pytestmark = pytest.mark.gpu
+
+DATA = os.path.join(ROOT, "data")
+REFBIN = os.path.join(REFDIR, "hisat2-align-s")
+
+
+@pytest.fixture(scope="module")
+def h2(lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import hisat2_b200
+    return hisat2_b200
+
+
+@pytest.fixture(scope="module")
+def tiny(h2):
+    idx = h2.Index(os.path.join(GOLDEN, "tiny"))
+    yield idx
+    idx.close()
+
+
+@pytest.fixture(scope="module")
+def chr22(h2):
+    base = os.path.join(DATA, "22_20-21M")
+    if not os.path.exists(base + ".1.ht2"):
+        pytest.skip("data/22_20-21M index not staged (oracle/make_data.sh)")
+    idx = h2.Index(base)
+    yield idx
+    idx.close()
+
+
+def gpu_sam(idx, batch):
+    res = idx.align(batch)
+    assert int((res.reads["err"] != 0).sum()) == 0
+    assert res.n_launches >= 1
+    return idx.sam_header() + idx.format_sam(batch, res), res
+
+
+def test_tiny_se_matches_golden_reference_sam(h2, tiny):
+    batch = h2.ReadBatch.from_fasta(os.path.join(GOLDEN, "tiny_se.fa"))
+    sam, res = gpu_sam(tiny, batch)
+    assert sam_lines(sam) == sam_lines(open(os.path.join(GOLDEN, "tiny_se.sam"), "rb").read())
+    # every CIGAR class of the fixture is exercised: M, I, D, S and unaligned
+    txt = sam.decode()
+    for op in ("I", "D", "S"):
+        assert any(op in l.split("\t")[5] for l in txt.splitlines() if not l.startswith("@"))
+
+
+def test_in_kernel_seed_search_matches_oracle(h2, tiny, oracle_bin):
+    """LF-step counts and alignments imply the same search as oracle/ht2_oracle.c:
+    the first partial search of every strand recorded by the oracle must be
+    consistent with what the kernel reported (aligned reads have an anchor whose
+    resolved coordinate the oracle also finds)."""
+    batch = h2.ReadBatch.from_fasta(os.path.join(GOLDEN, "tiny_se.fa"))
+    res = tiny.align(batch)
+    out = subprocess.run([oracle_bin, "dump", "tiny", "tiny_se.fa", "1"], cwd=GOLDEN, check=True,
+                         stdout=subprocess.PIPE).stdout.decode().splitlines()
+    coords = {}
+    for l in out:
+        f = l.split()
+        if f[0] == "C":
+            coords.setdefault(int(f[1]), set()).add((int(f[6]), int(f[7])))  # (tidx, toff) of a seed
+    checked = 0
+    for i in range(250):  # clean reads: full-length exact alignments
+        rr = res.reads[i]
+        if rr["n_aln"][0] == 0:
+            continue
+        al = res.alns[rr["aln_off"]]
+        if al["n_edits"] != 0 or i not in coords:
+            continue
+        # an exact 101M alignment at toff must contain every oracle seed hit of the same reference
+        ok = any(t == al["tidx"] and al["toff"] <= o < al["toff"] + 101 for (t, o) in coords[i])
+        assert ok, (i, al, coords[i])
+        checked += 1
+    assert checked > 150
+
+
+def test_batch_composition_invariance_and_determinism(h2, tiny):
+    """Reads are independent units: any split of the batch gives the same records."""
+    batch = h2.ReadBatch.from_fasta(os.path.join(GOLDEN, "tiny_se.fa"))
+    full, _ = gpu_sam(tiny, batch)
+    again, _ = gpu_sam(tiny, batch)
+    assert full == again
+    k = 333
+    offs = batch.offs
+    a = h2.ReadBatch(batch.seq[:int(offs[k])], offs[:k + 1], batch.seeds[:k], batch.names[:k])
+    b = h2.ReadBatch(batch.seq[int(offs[k]):], offs[k:] - offs[k], batch.seeds[k:], batch.names[k:])
+    sa, _ = gpu_sam(tiny, a)
+    sb, _ = gpu_sam(tiny, b)
+    hdr = tiny.sam_header()
+    assert full == hdr + sa[len(hdr):] + sb[len(hdr):]
+
+
+def test_edge_cases(h2, tiny):
+    """empty batch, reads shorter than the ftab, all-N read, 1-base read, max-length read."""
+    lib = h2.load_library()
+    empty = h2.ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(0, np.uint32), [])
+    r = tiny.align(empty)
+    assert len(r.reads) == 0 and len(r.alns) == 0
+    rng = np.random.default_rng(5)
+    seqs = [np.array([0, 1, 2], np.uint8), np.full(60, 4, np.uint8), np.array([2], np.uint8),
+            rng.integers(0, 4, 256).astype(np.uint8), rng.integers(0, 4, 7).astype(np.uint8)]
+    names = [b"short3", b"allN", b"one", b"len256", b"short7"]
+    offs = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint64)
+    seeds = np.array([lib.ht2gpu_read_seed(np.ascontiguousarray(s).ctypes.data, None, len(s), n, 0)
+                      for s, n in zip(seqs, names)], dtype=np.uint32)
+    b = h2.ReadBatch(np.concatenate(seqs), offs, seeds, names)
+    res = tiny.align(b)
+    assert int((res.reads["err"] != 0).sum()) == 0
+    sam = tiny.format_sam(b, res).decode().splitlines()
+    assert len(sam) == 5
+    assert all(l.split("\t")[1] == "4" for l in sam)           # nothing aligns
+    assert "YF:Z:NS" in sam[1] and "YF:Z:LN" in sam[2]           # N filter / length filter (hisat2.cpp:3417-3440)
+    # over-long read: reported as a capacity error, never silently truncated
+    long_ = h2.ReadBatch(rng.integers(0, 4, 300).astype(np.uint8), np.array([0, 300], np.uint64), np.array([1], np.uint32), [b"len300"])
+    res = tiny.align(long_, allow_capacity=True)
+    assert res.reads["err"][0] != 0
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("name", ["reads", "hard20k", "sim200k"])
+def test_chr22_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
+    """BASELINE configs[0]/[1]-shaped inputs: SAM byte-identical to the unmodified
+    reference run on this box (-p N --reorder)."""
+    fa = os.path.join(DATA, name + "_1.fa")
+    if not os.path.exists(fa):
+        pytest.skip(fa + " not staged")
+    batch = h2.ReadBatch.from_fasta(fa)
+    sam, res = gpu_sam(chr22, batch)
+    out = str(tmp_path / "ref.sam")
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", os.path.join(DATA, "22_20-21M"), "-U", fa, "-S", out,
+                    "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    assert sam_lines(sam) == sam_lines(open(out, "rb").read())
+
+
+def test_full_size_properties_1M_reads(h2, chr22):
+    """BASELINE configs[1] size (1M x 101 bp): properties that do not need the CPU
+    reference -- every read yields a record set, >= 99% align, reads sampled from
+    the forward strand of the reference without errors align exactly where they
+    were cut, results are identical across two runs, no capacity errors."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, ROOT)
+    import bench
+    ascii_reads, codes = bench.gen_reads(1000000, seed=1)
+    names = [b"r%d" % i for i in range(len(codes))]
+    seeds = bench.seeds_for(codes, names)
+    offs = np.arange(0, (len(codes) + 1) * 101, 101, dtype=np.uint64)
+    batch = h2.ReadBatch(codes.reshape(-1), offs, seeds, names)
+    r1 = chr22.align(batch)
+    assert int((r1.reads["err"] != 0).sum()) == 0
+    n_al = (r1.reads["n_aln"][:, 0] > 0).sum()
+    assert n_al >= 0.99 * len(codes)
+    assert (r1.reads["n_aln"][:, 0] <= 32).all()
+    a = r1.alns
+    assert (a["score"] <= 0).all() and (a["score"] >= -20).all()       # minsc(101) = -20
+    assert (a["ref_extent"] > 0).all() and (a["toff"] + a["ref_extent"] <= 1000000).all()
+    r2 = chr22.align(batch)
+    assert np.array_equal(r1.reads["rng_state"], r2.reads["rng_state"])
+    assert np.array_equal(np.sort(r1.alns, order=["toff", "score", "fw", "tidx"])[["toff", "score", "fw"]],
+                          np.sort(r2.alns, order=["toff", "score", "fw", "tidx"])[["toff", "score", "fw"]])
