@@ -229,7 +229,7 @@ struct Ht2Aligner {
     }
 
     // ---- edits / hits ---------------------------------------------------
-    HT2_HD static void copyHit(Ht2Hit& d, const Ht2Hit& s) {
+    HT2_NI static void copyHit(Ht2Hit& d, const Ht2Hit& s) {
         d.fw = s.fw; d.rdoff = s.rdoff; d.len = s.len; d.trim5 = s.trim5; d.trim3 = s.trim3;
         d.tidx = s.tidx; d.toff = s.toff; d.joinedOff = s.joinedOff; d.score = s.score;
         d.hitcount = 1; // GenomeHit::init resets _hitcount (hi_aligner.h:569)
@@ -248,7 +248,7 @@ struct Ht2Aligner {
         if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
         h.edits[h.nedits++] = e; if (h.nedits > W->maxEdits) W->maxEdits = h.nedits; return true;
     }
-    HT2_HD bool insertEditFront(Ht2Hit& h, const Ht2Edit& e) {
+    HT2_NI bool insertEditFront(Ht2Hit& h, const Ht2Edit& e) {
         if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
         for (uint32_t i = h.nedits; i > 0; i--) h.edits[i] = h.edits[i - 1];
         h.edits[0] = e; h.nedits++; if (h.nedits > W->maxEdits) W->maxEdits = h.nedits; return true;
@@ -290,7 +290,7 @@ struct Ht2Aligner {
     }
 
     // GenomeHit::getLeft (hi_aligner.h:919-957)
-    HT2_HD void getLeft(const Ht2Hit& h, uint32_t& rdoff, uint32_t& len, uint32_t& toff, int64_t* score, uint32_t rdi) const {
+    HT2_NI void getLeft(const Ht2Hit& h, uint32_t& rdoff, uint32_t& len, uint32_t& toff, int64_t* score, uint32_t rdi) const {
         toff = h.toff; rdoff = h.rdoff; len = h.len;
         if (score) *score = 0;
         const uint8_t* qual = W->rd[rdi].qual[h.fw ? 0 : 1];
@@ -311,7 +311,7 @@ struct Ht2Aligner {
         return toff;
     }
     // GenomeHit::getRight (hi_aligner.h:962-1015)
-    HT2_HD void getRight(const Ht2Hit& h, uint32_t& rdoff, uint32_t& len, uint32_t& toff, int64_t* score, uint32_t rdi) const {
+    HT2_NI void getRight(const Ht2Hit& h, uint32_t& rdoff, uint32_t& len, uint32_t& toff, int64_t* score, uint32_t rdi) const {
         toff = h.toff; rdoff = h.rdoff; len = h.len;
         if (score) *score = 0;
         if (h.nedits == 0) return;
@@ -332,7 +332,7 @@ struct Ht2Aligner {
     }
 
     // GenomeHit::calculateScore (hi_aligner.h:3711-3891), no splice edits.
-    HT2_HD int64_t calculateScore(Ht2Hit& h, uint32_t rdi) const {
+    HT2_NI int64_t calculateScore(Ht2Hit& h, uint32_t rdi) const {
         int64_t score = 0;
         const uint8_t* qual = W->rd[rdi].qual[h.fw ? 0 : 1];
         for (uint32_t i = 0; i < h.nedits; i++) {
@@ -360,7 +360,7 @@ struct Ht2Aligner {
     // ---- 2-bit reference (reference.cpp:396-430, 486-640) ------------------
     HT2_HD uint32_t refLen(uint32_t tidx) const { return ((const uint32_t*)(blob + H->o_refLens))[tidx]; }
     // dest[i] = base at toff+i for i<count; 4 inside N gaps / past the end.
-    HT2_HD void getStretch(uint8_t* dest, uint32_t tidx, uint32_t toff, uint32_t count) const {
+    HT2_NI void getStretch(uint8_t* dest, uint32_t tidx, uint32_t toff, uint32_t count) const {
         W->algBytes += (count + 3) >> 2;
         const Ht2RefRecord* recs = (const Ht2RefRecord*)(blob + H->o_recs);
         const uint32_t* recOffs = (const uint32_t*)(blob + H->o_refRecOffs);
@@ -390,7 +390,7 @@ struct Ht2Aligner {
 
     // ---- joined <-> text coordinates (gfm.h:5527-5600) ---------------------
     template <typename IT>
-    HT2_HD bool joinedToTextOff(const Ht2Fm<IT>& fm, uint32_t qlen, uint32_t off, uint32_t& tidx, uint32_t& textoff,
+    HT2_NI bool joinedToTextOff(const Ht2Fm<IT>& fm, uint32_t qlen, uint32_t off, uint32_t& tidx, uint32_t& textoff,
                                 bool rejectStraddle, bool& straddled) const {
         const uint32_t nFrag = fm.g->nFrag;
         uint32_t top = 0, bot = nFrag;
@@ -423,7 +423,7 @@ struct Ht2Aligner {
     // mapGLF1 gfm.h:3957, mapLF1 gfm.h:3889).  Linear indexes only here;
     // graph indexes are dispatched in lfStepGraph.
     template <typename IT>
-    HT2_HD void lfStep(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c,
+    HT2_NI void lfStep(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c,
                        uint32_t& ntop, uint32_t& nbot, uint32_t& nntop, uint32_t& nnbot) {
         if (bot - top != 1) {
             W->nLF += 2;
@@ -443,7 +443,7 @@ struct Ht2Aligner {
 
     // HI_Aligner::partialSearch (hi_aligner.h:6361-6600).  Returns stop
     // flags through pseudogeneStop/anchorStop like the reference.
-    HT2_HD void partialSearch(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
+    HT2_NI void partialSearch(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
         bool pseudogeneStop_ = pseudogeneStop, anchorStop_ = anchorStop;
         pseudogeneStop = anchorStop = false;
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
@@ -544,7 +544,7 @@ struct Ht2Aligner {
     // HI_Aligner::globalGFMSearch / localGFMSearch (hi_aligner.h:6606-6744,
     // 6751-6892) share one body; 'local' picks minUniqueLen/maxHitLen/maxHits.
     template <typename IT>
-    HT2_HD uint32_t gfmSearch(const Ht2Fm<IT>& fm, uint32_t rdi, bool fw, uint32_t rdoff, uint32_t& hitlen,
+    HT2_NI uint32_t gfmSearch(const Ht2Fm<IT>& fm, uint32_t rdi, bool fw, uint32_t rdoff, uint32_t& hitlen,
                               uint32_t& top, uint32_t& bot, uint32_t& node_top, uint32_t& node_bot,
                               bool& uniqueStop, uint32_t minUniqueLen, uint32_t maxHitLen, uint32_t maxHits, bool local) {
         bool uniqueStop_ = uniqueStop;
@@ -592,7 +592,7 @@ struct Ht2Aligner {
     // Walk row left until a sampled row (or '$') is met; joined offset =
     // sample + #steps.  Linear indexes: node == row.
     template <typename IT>
-    HT2_HD uint32_t resolveRow(const Ht2Fm<IT>& fm, uint32_t row) {
+    HT2_NI uint32_t resolveRow(const Ht2Fm<IT>& fm, uint32_t row) {
         uint32_t steps = 0;
         while (true) {
             if (ht2_is_zoff(fm, row)) return (uint32_t)(IT)(0 + steps);
@@ -609,7 +609,7 @@ struct Ht2Aligner {
     }
 
     // HI_Aligner::getGenomeCoords (hi_aligner.h:5774-5855); appends to W->coords.
-    HT2_HD bool getGenomeCoords(uint32_t top, uint32_t bot, uint32_t node_top, uint32_t node_bot, bool fw,
+    HT2_NI bool getGenomeCoords(uint32_t top, uint32_t bot, uint32_t node_top, uint32_t node_bot, bool fw,
                                 uint32_t maxelt, uint32_t rdlen, bool rejectStraddle, bool& straddled) {
         straddled = false;
         uint32_t nelt = node_bot - node_top;
@@ -630,7 +630,7 @@ struct Ht2Aligner {
     }
 
     // HI_Aligner::getGenomeCoords_local (hi_aligner.h:5861-5941); fills out[].
-    HT2_HD bool getGenomeCoordsLocal(const Ht2Fm<uint16_t>& lfm, uint32_t top, uint32_t bot, uint32_t node_top,
+    HT2_NI bool getGenomeCoordsLocal(const Ht2Fm<uint16_t>& lfm, uint32_t top, uint32_t bot, uint32_t node_top,
                                      uint32_t node_bot, bool fw, uint32_t rdoff, uint32_t rdlen,
                                      Ht2Coord* out, uint32_t& nout, uint32_t cap) {
         uint32_t nelt = node_bot - node_top;
@@ -686,7 +686,7 @@ struct Ht2Aligner {
     // list (hi_aligner.h:683-783, 2763-2860, 3168-3223): mismatch-bounded scan.
     // Left: scans read positions rdoff, rdoff-1, ... against rfseq[rflen-1], ...
     // Returns the extension length; new edits are inserted at the front of h.
-    HT2_HD uint32_t alignLeft(Ht2Hit& h, const uint8_t* seq, uint32_t base_rdoff, uint32_t rdoff, uint32_t rdlen,
+    HT2_NI uint32_t alignLeft(Ht2Hit& h, const uint8_t* seq, uint32_t base_rdoff, uint32_t rdoff, uint32_t rdlen,
                               uint32_t tidx, int rfoff, uint32_t rflen, uint32_t mm, uint32_t* numNs) {
         if (numNs) *numNs = 0;
         const uint32_t nedits0 = h.nedits;
@@ -732,7 +732,7 @@ struct Ht2Aligner {
         return fixupExt(h, extlen, nedits0, base_rdoff, rdoff, true);
     }
     // Right: scans read positions rdoff.. against rfseq[0..).
-    HT2_HD uint32_t alignRight(Ht2Hit& h, const uint8_t* seq, uint32_t base_rdoff, uint32_t rdoff, uint32_t rdlen,
+    HT2_NI uint32_t alignRight(Ht2Hit& h, const uint8_t* seq, uint32_t base_rdoff, uint32_t rdoff, uint32_t rdlen,
                                uint32_t tidx, int rfoff, uint32_t rflen, uint32_t mm) {
         const uint32_t nedits0 = h.nedits;
         if (rfoff < -16) return 0;
@@ -767,7 +767,7 @@ struct Ht2Aligner {
         return fixupExt(h, extlen, nedits0, base_rdoff, rdoff, false);
     }
     // tail of alignWithALTs (hi_aligner.h:756-783)
-    HT2_HD uint32_t fixupExt(Ht2Hit& h, uint32_t extlen, uint32_t nedits0, uint32_t base_rdoff, uint32_t rdoff, bool left) {
+    HT2_NI uint32_t fixupExt(Ht2Hit& h, uint32_t extlen, uint32_t nedits0, uint32_t base_rdoff, uint32_t rdoff, bool left) {
         if (extlen > 0 && h.nedits > 0) {
             const Ht2Edit& f = h.edits[0];
             if (f.pos + extlen == base_rdoff + 1) {
@@ -790,7 +790,7 @@ struct Ht2Aligner {
     }
 
     // GenomeHit::extend (hi_aligner.h:2031-2232)
-    HT2_HD bool extend(Ht2Hit& h, uint32_t rdi, uint32_t& leftext, uint32_t& rightext, uint32_t mm) {
+    HT2_NI bool extend(Ht2Hit& h, uint32_t rdi, uint32_t& leftext, uint32_t& rightext, uint32_t mm) {
         uint32_t max_leftext = leftext, max_rightext = rightext;
         leftext = 0; rightext = 0;
         const uint32_t rdlen = W->rd[rdi].len;
@@ -843,7 +843,7 @@ struct Ht2Aligner {
     }
 
     // GenomeHit::compatibleWith (hi_aligner.h:1375-1413)
-    HT2_HD bool compatibleWith(const Ht2Hit& a, const Ht2Hit& o, uint32_t rdi) const {
+    HT2_NI bool compatibleWith(const Ht2Hit& a, const Ht2Hit& o, uint32_t rdi) const {
         if (&a == &o) return false;
         if (a.fw != o.fw || a.tidx != o.tidx) return false;
         if (a.rdoff > o.rdoff) return false;
@@ -864,7 +864,7 @@ struct Ht2Aligner {
     }
 
     // GenomeHit::leftAlign (hi_aligner.h:3554-3610)
-    HT2_HD void leftAlign(Ht2Hit& h, uint32_t rdi) const {
+    HT2_NI void leftAlign(Ht2Hit& h, uint32_t rdi) const {
         const uint8_t* seq = W->rd[rdi].seq[h.fw ? 0 : 1];
         for (uint32_t ei = 0; ei < h.nedits; ei++) {
             Ht2Edit& edit = h.edits[ei];
@@ -902,7 +902,7 @@ struct Ht2Aligner {
 
     // GenomeHit::combineWith (hi_aligner.h:1420-2025), non-spliced paths
     // (splicing is rejected under --no-spliced-alignment, :1500-1502).
-    HT2_HD bool combineWith(Ht2Hit& a, const Ht2Hit& o, uint32_t rdi, int64_t minsc_) {
+    HT2_NI bool combineWith(Ht2Hit& a, const Ht2Hit& o, uint32_t rdi, int64_t minsc_) {
         if (&a == &o) return false;
         uint32_t this_rdoff, this_len, this_toff, other_rdoff, other_len, other_toff;
         int64_t this_score, other_score;
@@ -1048,10 +1048,11 @@ struct Ht2Aligner {
     }
 
     // ---- sink: AlnSinkWrap::report (aln_sink.h:2565-2655) + ReportingState ----
-    HT2_HD void sinkReset(bool paired_) {
+    HT2_NI void sinkReset(bool paired_) {
         W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0;
-        W->bestPair = W->best2Pair = HT2_MIN_SCORE;
-        W->bestUnp[0] = W->best2Unp[0] = W->bestUnp[1] = W->best2Unp[1] = HT2_MIN_SCORE;
+        // AlnSinkWrap::nextRead starts these at numeric_limits<THitInt>::min() (aln_sink.h:1896-1898)
+        W->bestPair = W->best2Pair = HT2_MIN_I64;
+        W->bestUnp[0] = W->best2Unp[0] = W->bestUnp[1] = W->best2Unp[1] = HT2_MIN_I64;
         W->nconcord = 0; W->nunpair[0] = W->nunpair[1] = 0;
         // ReportingState::nextRead (aln_sink.cpp:33-66)
         if (paired_) {
@@ -1078,7 +1079,7 @@ struct Ht2Aligner {
     }
 
     // HI_Aligner::reportHit (hi_aligner.h:6064-6198), unpaired form.
-    HT2_HD bool reportHit(uint32_t rdi, const Ht2Hit& hit) {
+    HT2_NI bool reportHit(uint32_t rdi, const Ht2Hit& hit) {
         const uint32_t rdlen = W->rd[rdi].len;
         if (hit.rdoff - hit.trim5 > 0 || hit.len + hit.trim5 + hit.trim3 < rdlen) return false;
         if (hit.score < minsc[rdi]) return false;
@@ -1104,7 +1105,7 @@ struct Ht2Aligner {
     }
 
     // HI_Aligner::redundant(sink, rdi, hit) (hi_aligner.h:6311-6351)
-    HT2_HD bool redundant(uint32_t rdi, const Ht2Hit& hit) {
+    HT2_NI bool redundant(uint32_t rdi, const Ht2Hit& hit) {
         const uint32_t rdlen = W->rd[rdi].len;
         for (uint32_t i = 0; i < W->nRes[rdi]; i++) {
             const Ht2Res& rsi = W->res[rdi][i];
@@ -1127,11 +1128,11 @@ struct Ht2Aligner {
         return false;
     }
     // isSearched / addSearched (hi_aligner.h:6898-6922)
-    HT2_HD bool isSearched(const Ht2Hit& hit, uint32_t rdi) const {
+    HT2_NI bool isSearched(const Ht2Hit& hit, uint32_t rdi) const {
         for (uint32_t i = 0; i < W->nSearched[rdi]; i++) if (hitEq(W->searched[rdi][i], hit)) return true;
         return false;
     }
-    HT2_HD void addSearched(const Ht2Hit& hit, uint32_t rdi) {
+    HT2_NI void addSearched(const Ht2Hit& hit, uint32_t rdi) {
         if (W->nSearched[rdi] >= HT2_MAX_SEARCHED) { W->err |= HT2_ERR_SEARCHED; return; }
         copyHit(W->searched[rdi][W->nSearched[rdi]++], hit);
     }
@@ -1148,7 +1149,7 @@ struct Ht2Aligner {
         return score;
     }
     // HI_Aligner::pickNextReadToSearch (hi_aligner.h:4868-4894)
-    HT2_HD bool pickNextReadToSearch(uint32_t& rdi, bool& fw) {
+    HT2_NI bool pickNextReadToSearch(uint32_t& rdi, bool& fw) {
         rdi = 0; fw = true;
         bool picked = false;
         int64_t maxScore = HT2_MIN_I64;
@@ -1166,7 +1167,7 @@ struct Ht2Aligner {
         return picked;
     }
     // HI_Aligner::nextBWT (hi_aligner.h:4644-4752)
-    HT2_HD bool nextBWT(uint32_t& rdi, bool& fw) {
+    HT2_NI bool nextBWT(uint32_t& rdi, bool& fw) {
         while (pickNextReadToSearch(rdi, fw)) {
             uint32_t fwi = fw ? 0 : 1;
             Ht2ReadHits& hit = W->hits[rdi][fwi];
@@ -1203,7 +1204,7 @@ struct Ht2Aligner {
 
     // HI_Aligner::getAnchorHits (hi_aligner.h:5007-5193), linear-index form of
     // adjustWithALT (hi_aligner.h:2251-2264).
-    HT2_HD uint32_t getAnchorHits(uint32_t rdi, bool fw, uint32_t maxGenomeHitSize) {
+    HT2_NI uint32_t getAnchorHits(uint32_t rdi, bool fw, uint32_t maxGenomeHitSize) {
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
         const uint32_t offsetSize = hit.nhits;
         const uint32_t minK = P->minK;
@@ -1286,7 +1287,7 @@ struct Ht2Aligner {
     }
 
     // HI_Aligner::align (hi_aligner.h:5484-5571)
-    HT2_HD bool align(uint32_t rdi, bool fw) {
+    HT2_NI bool align(uint32_t rdi, bool fw) {
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
         {   // ReadBWTHit::minWidth (hi_aligner.h:302-318)
             bool any = false;
@@ -1309,7 +1310,7 @@ struct Ht2Aligner {
     }
 
     // SplicedAligner::hybridSearch (spliced_aligner.h:112-322), bowtie2_dp == 0
-    HT2_HD void hybridSearch(uint32_t rdi, bool fw) {
+    HT2_NI void hybridSearch(uint32_t rdi, bool fw) {
         (void)fw;
         for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
             uint32_t leftext = HT2_IDX_MAX32, rightext = HT2_IDX_MAX32;
@@ -1334,7 +1335,9 @@ struct Ht2Aligner {
     HT2_HD int64_t sinkFloor(uint32_t rdi, int64_t cushion) const {
         int64_t m = minsc[rdi];
         if (!P->secondary) {
-            int64_t b = W->bestUnp[rdi] - cushion;
+            // the reference computes sink.bestUnpN() - cushion in int64; with no alignment yet
+            // (INT64_MIN) and a non-zero cushion this wraps to a huge positive floor
+            int64_t b = (int64_t)((uint64_t)W->bestUnp[rdi] - (uint64_t)cushion);
             if (b > m) m = b;
         }
         return m;
@@ -1342,13 +1345,14 @@ struct Ht2Aligner {
 
     // SplicedAligner::hybridSearch_recur (spliced_aligner.h:331-2052) for an
     // empty splice-site DB (--no-spliced-alignment / no known sites).
-    HT2_HDN int64_t hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, uint32_t hitoff, uint32_t hitlen,
+    HT2_NI int64_t hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, uint32_t hitoff, uint32_t hitlen,
                                       bool alignMate, uint32_t dep);
 
     // HI_Aligner::go (hi_aligner.h:4048-4638), unpaired + paired without repeats
-    HT2_HDN void go();
-    HT2_HDN void pairReads();
-    HT2_HDN bool alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff);
+    HT2_NI void go();
+    HT2_NI void pairReads();
+    HT2_NI bool peConcordant(int64_t off1, uint32_t len1, bool fw1, int64_t off2, uint32_t len2, bool fw2) const;
+    HT2_NI bool alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff);
 };
 
 #include "ht2_core_impl.h"

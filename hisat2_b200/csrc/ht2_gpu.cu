@@ -60,11 +60,18 @@ __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, u
     }
 }
 
+// LANES = 1 : one thread per read (pair).
+// LANES = 32: one warp per read; every lane executes the same scalar state
+//             machine on the warp's single workspace (uniform control flow, no
+//             divergence, broadcast loads), lane 0 publishes the results.
+template <int LANES>
 __global__ void __launch_bounds__(128)
 ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
 {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nthreads = gridDim.x * blockDim.x;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tid = gtid / LANES;
+    const uint32_t lane = gtid % LANES;
+    const uint32_t nthreads = (gridDim.x * blockDim.x) / LANES;
     Ht2Work* W = work + tid;
     Ht2Aligner A;
     A.bind(blob, &P, W);
@@ -125,9 +132,17 @@ ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevO
         uint32_t ned = 0;
         for (uint32_t m = 0; m < 2; m++)
             for (uint32_t i = 0; i < W->nRes[m]; i++) ned += W->res[m][i].nedits;
-        uint32_t aoff = nal ? atomicAdd(&o.counters[0], nal) : 0;
-        uint32_t eoff = ned ? atomicAdd(&o.counters[1], ned) : 0;
-        uint32_t poff = W->nPairs ? atomicAdd(&o.counters[2], W->nPairs) : 0;
+        uint32_t aoff = 0, eoff = 0, poff = 0;
+        if (lane == 0) {
+            aoff = nal ? atomicAdd(&o.counters[0], nal) : 0;
+            eoff = ned ? atomicAdd(&o.counters[1], ned) : 0;
+            poff = W->nPairs ? atomicAdd(&o.counters[2], W->nPairs) : 0;
+        }
+        if (LANES > 1) {
+            aoff = __shfl_sync(0xffffffffu, aoff, 0);
+            eoff = __shfl_sync(0xffffffffu, eoff, 0);
+            poff = __shfl_sync(0xffffffffu, poff, 0);
+        }
         if (aoff + nal > o.capAlns || eoff + ned > o.capEdits || poff + W->nPairs > o.capPairs) {
             W->err |= HT2_ERR_OUTPUT;
             rr.n_aln[0] = rr.n_aln[1] = 0; rr.n_pairs = 0;
@@ -156,7 +171,8 @@ ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevO
         rr.aln_off = aoff;
         rr.pair_off = poff;
         rr.err = W->err;
-        o.reads[u] = rr;
+        if (lane == 0) o.reads[u] = rr;
+        if (LANES > 1) __syncwarp();
     }
 }
 
@@ -172,7 +188,7 @@ struct ht2gpu_handle {
     ht2gpu_options_t opt;
     int            device;
     int            nSM;
-    int            tpb, bpsm;
+    int            tpb, bpsm, lanes;
     Ht2Work*       dWork;
     size_t         nWork;
     cudaStream_t   stream;
@@ -234,7 +250,8 @@ static int finishOpen(ht2gpu_handle* h)
     h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 128;
     if (h->tpb > 128) h->tpb = 128;
     h->bpsm = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 4;
-    h->nWork = (size_t)h->nSM * h->bpsm * h->tpb;
+    h->lanes = h->opt.warp_per_read ? 32 : 1;
+    h->nWork = (size_t)h->nSM * h->bpsm * h->tpb / h->lanes;
     CK(cudaMalloc(&h->dWork, h->nWork * sizeof(Ht2Work)));
     CK(cudaMemset(h->dWork, 0, h->nWork * sizeof(Ht2Work)));
     CK(cudaDeviceSetLimit(cudaLimitStackSize, 40 * 1024));
@@ -439,10 +456,12 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
     o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
     o.counters = h->dCounters;
     CK(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned int), h->stream));
-    uint32_t grid = (uint32_t)(h->nWork / h->tpb);
-    uint32_t needBlocks = (units + h->tpb - 1) / h->tpb;
+    uint32_t perBlock = (uint32_t)(h->tpb / h->lanes);
+    uint32_t grid = (uint32_t)(h->nWork / perBlock);
+    uint32_t needBlocks = (units + perBlock - 1) / perBlock;
     if (needBlocks < grid) grid = needBlocks ? needBlocks : 1;
-    ht2_align_kernel<<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
+    if (h->lanes == 32) ht2_align_kernel<32><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
+    else ht2_align_kernel<1><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
     CK(cudaGetLastError());
     return HT2GPU_OK;
 }
@@ -539,21 +558,26 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
                                  const ht2gpu_result_batch_t* res, char** out, size_t* out_len)
 {
     if (!h || !b || !res || !names || !out) return HT2GPU_ERR_ARG;
-    if (b->paired) { h->err = "paired-end SAM formatting is not implemented yet"; return HT2GPU_ERR_UNSUPPORTED; }
     std::string sam;
     sam.reserve((size_t)b->n_reads * 400);
     const char* nm = names;
-    for (uint32_t i = 0; i < b->n_reads; i++) {
-        Ht2HostRead rd;
+    const uint32_t units = b->paired ? b->n_reads / 2 : b->n_reads;
+    auto mkRead = [&](uint32_t i, int mate, Ht2HostRead& rd) {
         rd.name = nm; nm += rd.name.size() + 1;
-        rd.mate = 0;
+        rd.mate = mate;
         const uint8_t* s = b->seq + b->offs[i];
         uint32_t len = (uint32_t)(b->offs[i + 1] - b->offs[i]);
         rd.seq.assign(s, s + len);
         if (b->qual) rd.qual.assign(b->qual + b->offs[i], b->qual + b->offs[i] + len); else rd.qual.assign(len, (uint8_t)'I');
-        int64_t minsc = ht2_minsc(len);
-        Ht2ReadFilters f = ht2_filters(rd, minsc);
-        const ht2gpu_read_result_t& rr = res->reads[i];
+    };
+    for (uint32_t u = 0; u < units; u++) {
+        Ht2HostRead rd1, rd2;
+        if (b->paired) { mkRead(2 * u, 1, rd1); mkRead(2 * u + 1, 2, rd2); }
+        else mkRead(u, 0, rd1);
+        Ht2ReadFilters f1 = ht2_filters(rd1, ht2_minsc((uint32_t)rd1.seq.size()));
+        Ht2ReadFilters f2 = f1;
+        if (b->paired) f2 = ht2_filters(rd2, ht2_minsc((uint32_t)rd2.seq.size()));
+        const ht2gpu_read_result_t& rr = res->reads[u];
         Ht2ReadOut o;
         o.rngLast = rr.rng_state; o.err = rr.err;
         uint32_t a = rr.aln_off;
@@ -561,7 +585,8 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
             for (uint32_t k = 0; k < rr.n_aln[m]; k++, a++) {
                 const ht2gpu_aln_t& al = res->alns[a];
                 Ht2Res r;
-                r.tidx = al.tidx; r.toff = al.toff; r.fw = al.fw; r.rdlen = len; r.score = al.score;
+                r.tidx = al.tidx; r.toff = al.toff; r.fw = al.fw; r.score = al.score;
+                r.rdlen = (uint32_t)((m == 0 || !b->paired) ? (m == 0 ? rd1.seq.size() : rd1.seq.size()) : rd2.seq.size());
                 r.trim5p = al.trim5; r.trim3p = al.trim3; r.rfextent = al.ref_extent; r.nedits = al.n_edits;
                 for (uint32_t e = 0; e < al.n_edits && e < HT2_MAX_EDITS; e++) {
                     const ht2gpu_edit_t& se = res->edits[al.edit_off + e];
@@ -571,7 +596,10 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
                 o.res[m].push_back(r);
             }
         }
-        ht2_finish_unpaired(sam, *h->img, h->P, rd, f, o);
+        for (uint32_t k = 0; k < rr.n_pairs; k++)
+            o.pairs.push_back(std::make_pair(res->pairs[2 * (rr.pair_off + k)], res->pairs[2 * (rr.pair_off + k) + 1]));
+        if (b->paired) ht2_finish_paired(sam, *h->img, h->P, rd1, rd2, f1, f2, o);
+        else ht2_finish_unpaired(sam, *h->img, h->P, rd1, f1, o);
     }
     char* p = (char*)malloc(sam.size() + 1);
     memcpy(p, sam.data(), sam.size()); p[sam.size()] = 0;

@@ -470,22 +470,68 @@ void appendYF(std::string& o, const Ht2ReadFilters& f) {
 
 } // namespace
 
-// AlnSinkSam::appendMate (aln_sink.h:3024-3250) for an unpaired read
-static void appendMateUnpaired(std::string& o, const Ht2Image& img, const Ht2HostRead& rd, const Ht2ReadFilters& f,
-                               const Ht2Res* rs, const Summ& summ, bool primary)
+// AlnFlags::pairing (aligner_result.h:383-398)
+enum { PAIR_CONCORD_MATE1 = 1, PAIR_CONCORD_MATE2, PAIR_DISCORD_MATE1, PAIR_DISCORD_MATE2,
+       PAIR_UNPAIRED_MATE1, PAIR_UNPAIRED_MATE2, PAIR_UNPAIRED };
+
+struct MateFlags {
+    int pairing; bool primary; bool oppAligned;
+    bool partOfPair() const { return pairing < PAIR_UNPAIRED; }
+    bool readMate1() const { return pairing == PAIR_CONCORD_MATE1 || pairing == PAIR_DISCORD_MATE1 || pairing == PAIR_UNPAIRED_MATE1; }
+    bool concordant() const { return pairing == PAIR_CONCORD_MATE1 || pairing == PAIR_CONCORD_MATE2; }
+    bool discordant() const { return pairing == PAIR_DISCORD_MATE1 || pairing == PAIR_DISCORD_MATE2; }
+    bool unpairedMate() const { return pairing == PAIR_UNPAIRED_MATE1 || pairing == PAIR_UNPAIRED_MATE2; }
+};
+
+// AlnRes::setFragmentLength (aligner_result.h:1631-1694) without splice sites
+static int64_t fragmentLength(const Ht2Res& me, const Ht2Res& o, bool meMate1)
 {
-    appendName(o, rd.name, false);
+    auto ext = [](const Ht2Res& r, int64_t& st, int64_t& en) {
+        int64_t trim_st = r.fw ? r.trim5p : r.trim3p, trim_en = r.fw ? r.trim3p : r.trim5p;
+        st = (int64_t)r.toff - trim_st;
+        en = (int64_t)r.toff + r.rfextent - 1 + trim_en;
+    };
+    int64_t st, en, ost, oen;
+    ext(me, st, en); ext(o, ost, oen);
+    bool imUpstream;
+    if (st < ost) imUpstream = true;
+    else if (st == ost) {
+        if (me.fw && o.fw && meMate1) imUpstream = true;
+        else if (me.fw && !o.fw) imUpstream = true;
+        else imUpstream = false;
+    } else imUpstream = false;
+    int64_t up = std::min(st, ost), dn = std::max(en, oen);
+    int64_t fraglen = 1 + dn - up;
+    if (!imUpstream) fraglen = -fraglen;
+    return fraglen;
+}
+
+// AlnSinkSam::appendMate (aln_sink.h:3024-3250)
+static void appendMate(std::string& o, const Ht2Image& img, const Ht2HostRead& rd, size_t ordlen, const Ht2ReadFilters& f,
+                       const Ht2Res* rs, const Ht2Res* rso, const Summ& summ, const MateFlags& fl,
+                       bool fraglenSet, int64_t fraglen, bool haveOscore)
+{
+    appendName(o, rd.name, fl.partOfPair());
     o.push_back('\t');
-    int fl = 0;
-    if (!primary) fl |= 256;
-    if (rs != NULL && !rs->fw) fl |= 16;
-    if (rs == NULL) fl |= 4;
-    o += std::to_string(fl);
+    int flag = 0;
+    if (fl.partOfPair()) {
+        flag |= 1;
+        if (fl.concordant()) flag |= 2;
+        if (!fl.oppAligned) flag |= 8;
+        flag |= fl.readMate1() ? 64 : 128;
+        if (fl.oppAligned && rso != NULL && !rso->fw) flag |= 32;
+    }
+    if (!fl.primary) flag |= 256;
+    if (rs != NULL && !rs->fw) flag |= 16;
+    if (rs == NULL) flag |= 4;
+    o += std::to_string(flag);
     o.push_back('\t');
+    const char* ytz = fl.concordant() ? "CP" : fl.discordant() ? "DP" : fl.unpairedMate() ? "UP" : "UU";
     if (rs == NULL) {
-        o += "*\t0\t0\t*\t*\t0\t0\t";
+        if (summ.orefid != -1) { appendRefName(o, img, (uint32_t)summ.orefid); o.push_back('\t'); o += std::to_string(summ.orefoff + 1); o += "\t0\t*\t=\t"; o += std::to_string(summ.orefoff + 1); o += "\t0\t"; }
+        else o += "*\t0\t0\t*\t*\t0\t0\t";
         appendSeqQual(o, rd, true);
-        o += "\tYT:Z:UU";
+        o += "\tYT:Z:"; o += ytz;
         appendYF(o, f);
         o.push_back('\n');
         return;
@@ -510,26 +556,34 @@ static void appendMateUnpaired(std::string& o, const Ht2Image& img, const Ht2Hos
     o.push_back('\t');
     o += std::to_string((int64_t)rs->toff + 1);
     o.push_back('\t');
-    o += std::to_string(mapqV2(summ, true, rd.seq.size(), 0));
+    o += std::to_string(mapqV2(summ, rd.mate < 2, rd.seq.size(), ordlen));
     o.push_back('\t');
     st.cigar(o);
-    o += "\t*\t0\t0\t";
+    o.push_back('\t');
+    if (fl.partOfPair()) {
+        if (rso != NULL && rs->tidx != rso->tidx) { appendRefName(o, img, rso->tidx); o.push_back('\t'); }
+        else o += "=\t";
+        o += std::to_string((int64_t)(rso ? rso->toff : rs->toff) + 1);
+        o.push_back('\t');
+    } else o += "*\t0\t";
+    o += fraglenSet ? std::to_string(fraglen) : std::string("0");
+    o.push_back('\t');
     appendSeqQual(o, rd, rs->fw != 0);
     // optional flags (sam.h:525-1010)
     o += "\tAS:i:"; o += std::to_string(rs->score);
-    if (summ.secbest[0].valid) { o += "\tZS:i:"; o += std::to_string(summ.secbest[0].score); }
+    const ScoreKey& sb = summ.secbest[rd.mate < 2 ? 0 : 1];
+    if (sb.valid) { o += "\tZS:i:"; o += std::to_string(sb.score); }
     o += "\tXN:i:0";
-    size_t num_mm = 0, num_go = 0, num_gx = 0, NM = 0;
+    size_t num_mm = 0, num_go = 0, num_gx = 0, NM = rs->nedits;
     for (size_t i = 0; i < rs->nedits; i++) {
         const Ht2Edit& e = rs->edits[i];
-        NM++;
         if (e.type == HT2_EDIT_MM) num_mm++;
         else if (e.type == HT2_EDIT_READ_GAP) {
             num_go++; num_gx++;
-            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos && rs->edits[i + 1].type == HT2_EDIT_READ_GAP) { i++; num_gx++; NM++; }
+            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos && rs->edits[i + 1].type == HT2_EDIT_READ_GAP) { i++; num_gx++; }
         } else if (e.type == HT2_EDIT_REF_GAP) {
             num_go++; num_gx++;
-            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos + 1 && rs->edits[i + 1].type == HT2_EDIT_REF_GAP) { i++; num_gx++; NM++; }
+            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos + 1 && rs->edits[i + 1].type == HT2_EDIT_REF_GAP) { i++; num_gx++; }
         }
     }
     o += "\tXM:i:"; o += std::to_string(num_mm);
@@ -537,9 +591,11 @@ static void appendMateUnpaired(std::string& o, const Ht2Image& img, const Ht2Hos
     o += "\tXG:i:"; o += std::to_string(num_gx);
     o += "\tNM:i:"; o += std::to_string(NM);
     o += "\tMD:Z:"; st.mdz(o);
-    o += "\tYT:Z:UU";
+    if (summ.paired && haveOscore && rso) { o += "\tYS:i:"; o += std::to_string(rso->score); }
+    o += "\tYT:Z:"; o += ytz;
     appendYF(o, f);
-    o += "\tNH:i:"; o += std::to_string(summ.numAlns[0]);
+    if (fl.concordant() || fl.discordant()) { o += "\tNH:i:"; o += std::to_string(summ.numAlnsPaired); }
+    else { o += "\tNH:i:"; o += std::to_string((fl.pairing == PAIR_UNPAIRED || fl.readMate1()) ? summ.numAlns[0] : summ.numAlns[1]); }
     o.push_back('\n');
 }
 
@@ -550,16 +606,152 @@ void ht2_finish_unpaired(std::string& o, const Ht2Image& img, const Ht2Params& P
     const std::vector<Ht2Res>& rs = out.res[0];
     uint64_t nunpair1 = std::min<uint64_t>(rs.size(), P.khits); // ReportingState::getReport
     Summ summ; summ.reset();
+    MateFlags fl = {PAIR_UNPAIRED, true, false};
     if (nunpair1 > 0) {
         summ.addUnp(0, rs);
         std::vector<size_t> select;
         selectByScore(rs, NULL, NULL, nunpair1, select, rnd, P.secondary != 0);
         summ.numAlns[0] = select.size();
         for (size_t i = 0; i < select.size(); i++) {
-            appendMateUnpaired(o, img, rd, f, &rs[select[i]], summ, i == 0);
+            fl.primary = (i == 0);
+            appendMate(o, img, rd, 0, f, &rs[select[i]], NULL, summ, fl, false, 0, false);
         }
     } else {
-        appendMateUnpaired(o, img, rd, f, NULL, summ, true);
+        appendMate(o, img, rd, 0, f, NULL, NULL, summ, fl, false, 0, false);
+    }
+    out.rngLast = rnd.last;
+}
+
+// AlnSinkWrap::finishRead for a pair (aln_sink.h:1939-2557)
+void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
+                       const Ht2HostRead& rd1, const Ht2HostRead& rd2,
+                       const Ht2ReadFilters& f1, const Ht2ReadFilters& f2, Ht2ReadOut& out)
+{
+    Ht2Rng rnd; rnd.last = out.rngLast;
+    const std::vector<Ht2Res>& rs1u = out.res[0];
+    const std::vector<Ht2Res>& rs2u = out.res[1];
+    // ReportingState replay (aln_sink.cpp:72-131, 139-170)
+    uint64_t nconcord_ = 0;
+    {
+        int64_t best = HT2_MIN_SCORE;
+        for (size_t i = 0; i < out.pairs.size(); i++) {
+            int64_t sc = rs1u[out.pairs[i].first].score + rs2u[out.pairs[i].second].score;
+            if (sc > best) { best = sc; nconcord_ = 0; }
+            nconcord_++;
+        }
+    }
+    uint64_t nunpair1_ = rs1u.size(), nunpair2_ = rs2u.size();
+    bool discordant = P.discord && out.pairs.empty() && nunpair1_ == 1 && nunpair2_ == 1;
+    if (nconcord_ > 0) {
+        uint64_t nconcord = std::min<uint64_t>(P.khits, nconcord_);
+        Summ summ; summ.reset();
+        summ.paired = true;
+        for (size_t i = 0; i < out.pairs.size(); i++) {
+            const Ht2Res& a = rs1u[out.pairs[i].first]; const Ht2Res& b = rs2u[out.pairs[i].second];
+            ScoreKey sc = {a.score + b.score, hisat2Score(a) + hisat2Score(b), true};
+            if (keyGt(sc, summ.bestPaired)) { summ.secbestPaired = summ.bestPaired; summ.bestPaired = sc; }
+            else if (keyGt(sc, summ.secbestPaired)) summ.secbestPaired = sc;
+        }
+        summ.addUnp(0, rs1u); summ.addUnp(1, rs2u);
+        std::vector<size_t> select;
+        selectByScore(rs1u, &rs2u, &out.pairs, nconcord, select, rnd, P.secondary != 0);
+        summ.numAlnsPaired = select.size();
+        MateFlags fl1 = {PAIR_CONCORD_MATE1, true, true}, fl2 = {PAIR_CONCORD_MATE2, true, true};
+        for (size_t i = 0; i < select.size(); i++) {
+            const Ht2Res& a = rs1u[out.pairs[select[i]].first]; const Ht2Res& b = rs2u[out.pairs[select[i]].second];
+            fl1.primary = fl2.primary = (i == 0);
+            appendMate(o, img, rd1, rd2.seq.size(), f1, &a, &b, summ, fl1, true, fragmentLength(a, b, true), true);
+            appendMate(o, img, rd2, rd1.seq.size(), f2, &b, &a, summ, fl2, true, fragmentLength(b, a, false), true);
+        }
+        out.rngLast = rnd.last;
+        return;
+    } else if (discordant) {
+        Summ summ; summ.reset();
+        summ.paired = true;
+        {
+            const Ht2Res& a = rs1u[0]; const Ht2Res& b = rs2u[0];
+            ScoreKey sc = {a.score + b.score, hisat2Score(a) + hisat2Score(b), true};
+            summ.bestPaired = sc;
+        }
+        summ.addUnp(0, rs1u); summ.addUnp(1, rs2u);
+        summ.numAlnsPaired = 1; // AlnSetSumm::init counts rs1->size()
+        std::vector<std::pair<uint16_t, uint16_t> > dp(1, std::make_pair((uint16_t)0, (uint16_t)0));
+        std::vector<size_t> select;
+        selectByScore(rs1u, &rs2u, &dp, 1, select, rnd, P.secondary != 0);
+        MateFlags fl1 = {PAIR_DISCORD_MATE1, true, true}, fl2 = {PAIR_DISCORD_MATE2, true, true};
+        const Ht2Res& a = rs1u[0]; const Ht2Res& b = rs2u[0];
+        bool sameRef = a.tidx == b.tidx; // setMateParams (aligner_result.h:1594-1618)
+        appendMate(o, img, rd1, rd2.seq.size(), f1, &a, &b, summ, fl1, sameRef, sameRef ? fragmentLength(a, b, true) : 0, true);
+        appendMate(o, img, rd2, rd1.seq.size(), f2, &b, &a, summ, fl2, sameRef, sameRef ? fragmentLength(b, a, false) : 0, true);
+        out.rngLast = rnd.last;
+        return;
+    }
+    uint64_t nunpair1 = 0, nunpair2 = 0;
+    if (P.mixed && nunpair1_ + nunpair2_ > 0) {
+        nunpair1 = std::min<uint64_t>(nunpair1_, P.khits);
+        nunpair2 = std::min<uint64_t>(nunpair2_, P.khits);
+    }
+    bool rep1 = nunpair1 > 0, rep2 = nunpair2 > 0;
+    Summ summ1, summ2; summ1.reset(); summ2.reset();
+    std::vector<size_t> select1, select2;
+    const Ht2Res *repRs1 = NULL, *repRs2 = NULL;
+    if (rep1) {
+        summ1.addUnp(0, rs1u);
+        if (rep2) summ1.addUnp(1, rs2u);
+        selectByScore(rs1u, NULL, NULL, nunpair1, select1, rnd, P.secondary != 0);
+        repRs1 = &rs1u[select1[0]];
+    }
+    if (rep2) {
+        summ2.addUnp(1, rs2u);
+        if (rep1) summ2.addUnp(0, rs1u);
+        selectByScore(rs2u, NULL, NULL, nunpair2, select2, rnd, P.secondary != 0);
+        repRs2 = &rs2u[select2[0]];
+    }
+    // numAlns1/2 setters are applied to both summaries (aln_sink.h:2238-2239, 2263-2264)
+    if (rep1) { summ1.numAlns[0] = select1.size(); summ2.numAlns[0] = select1.size(); }
+    if (rep2) { summ1.numAlns[1] = select2.size(); summ2.numAlns[1] = select2.size(); }
+    MateFlags fl1 = {PAIR_UNPAIRED_MATE1, true, repRs2 != NULL}, fl2 = {PAIR_UNPAIRED_MATE2, true, repRs1 != NULL};
+    int64_t refid = -1, refoff = -1;
+    if (rep1) {
+        // AlnSink::reportHits (aln_sink.h:730-790)
+        if (repRs2 != NULL) {
+            const Ht2Res* r1pri = &rs1u[select1[0]]; const Ht2Res* r2pri = &rs2u[select2[0]];
+            appendMate(o, img, rd1, rd2.seq.size(), f1, r1pri, r2pri, summ1, fl1, false, 0, false);
+            appendMate(o, img, rd2, rd1.seq.size(), f2, r2pri, r1pri, summ1, fl2, false, 0, false);
+            fl1.primary = fl2.primary = false;
+            for (size_t i = 1; i < select1.size(); i++)
+                appendMate(o, img, rd1, rd2.seq.size(), f1, &rs1u[select1[i]], r2pri, summ1, fl1, false, 0, false);
+            for (size_t i = 1; i < select2.size(); i++)
+                appendMate(o, img, rd2, rd1.seq.size(), f2, &rs2u[select2[i]], r1pri, summ1, fl2, false, 0, false);
+            fl1.primary = fl2.primary = true;
+        } else {
+            for (size_t i = 0; i < select1.size(); i++) {
+                fl1.primary = (i == 0);
+                appendMate(o, img, rd1, 0, f1, &rs1u[select1[i]], NULL, summ1, fl1, false, 0, false);
+            }
+            fl1.primary = true;
+        }
+        refid = rs1u[select1[0]].tidx; refoff = rs1u[select1[0]].toff;
+    }
+    if (rep2 && !rep1) {
+        for (size_t i = 0; i < select2.size(); i++) {
+            fl2.primary = (i == 0);
+            appendMate(o, img, rd2, 0, f2, &rs2u[select2[i]], NULL, summ2, fl2, false, 0, false);
+        }
+        fl2.primary = true;
+        refid = rs2u[select2[0]].tidx; refoff = rs2u[select2[0]].toff;
+    }
+    if (nunpair1 == 0) {
+        Summ s; s.reset();
+        if (nunpair2 > 0) { s.orefid = refid; s.orefoff = refoff; }
+        MateFlags fl = {PAIR_UNPAIRED_MATE1, true, repRs2 != NULL};
+        appendMate(o, img, rd1, 0, f1, NULL, NULL, s, fl, false, 0, false);
+    }
+    if (nunpair2 == 0) {
+        Summ s; s.reset();
+        if (nunpair1 > 0) { s.orefid = refid; s.orefoff = refoff; }
+        MateFlags fl = {PAIR_UNPAIRED_MATE2, true, repRs1 != NULL};
+        appendMate(o, img, rd2, 0, f2, NULL, NULL, s, fl, false, 0, false);
     }
     out.rngLast = rnd.last;
 }

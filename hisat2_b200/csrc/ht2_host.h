@@ -54,4 +54,9 @@ void ht2_finish_unpaired(std::string& o, const Ht2Image& img, const Ht2Params& P
                          const Ht2HostRead& rd, const Ht2ReadFilters& f,
                          Ht2ReadOut& out);
 
+// finishRead for a pair: concordant / discordant / unpaired-mate branches
+void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
+                       const Ht2HostRead& rd1, const Ht2HostRead& rd2,
+                       const Ht2ReadFilters& f1, const Ht2ReadFilters& f2, Ht2ReadOut& out);
+
 #endif

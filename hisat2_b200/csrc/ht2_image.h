@@ -20,9 +20,11 @@
 #if defined(__CUDACC__)
 #define HT2_HD __host__ __device__ __forceinline__
 #define HT2_HDN __host__ __device__ inline
+#define HT2_NI __host__ __device__ __noinline__   /* big functions: keep ONE copy (I-cache) */
 #else
 #define HT2_HD inline
 #define HT2_HDN inline
+#define HT2_NI inline
 #endif
 
 #define HT2_MAGIC 0x42325448u /* "HT2B" */

@@ -16,7 +16,12 @@ int main(int argc, char** argv) {
     Ht2Image* img = ht2_image_load(argv[1], err);
     if (!img) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     std::vector<Ht2HostRead> reads;
-    if (!ht2_read_fasta(argv[2], reads, 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    // usage: ht2_hostsim index reads.fa out.sam            (unpaired)
+    //        ht2_hostsim index reads_1.fa out.sam reads_2.fa (paired, --fr)
+    const bool pairedMode = argc > 4;
+    if (!ht2_read_fasta(argv[2], reads, pairedMode ? 1 : 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    std::vector<Ht2HostRead> reads2;
+    if (pairedMode && !ht2_read_fasta(argv[4], reads2, 2, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     Ht2Params P;
     ht2_default_params(P, *img, true);
     std::string sam;
@@ -26,7 +31,44 @@ int main(int argc, char** argv) {
     size_t nerr = 0;
     uint64_t nLF = 0;
     uint32_t mx[8] = {0,0,0,0,0,0,0,0};
-    for (size_t i = 0; i < reads.size(); i++) {
+    for (size_t i = 0; pairedMode && i < reads.size(); i++) {
+        Ht2HostRead& r1 = reads[i]; Ht2HostRead& r2 = reads2[i];
+        r1.seed = ht2_gen_rand_seed(r1, 0); r2.seed = ht2_gen_rand_seed(r2, 0);
+        int64_t ms1 = ht2_minsc((uint32_t)r1.seq.size()), ms2 = ht2_minsc((uint32_t)r2.seq.size());
+        Ht2ReadFilters f1 = ht2_filters(r1, ms1), f2 = ht2_filters(r2, ms2);
+        Ht2ReadOut out; out.err = 0;
+        A.bind(img->blob.data(), &P, W);
+        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
+        bool p1 = f1.pass(), p2 = f2.pass();
+        W->rnd.init((p1 && p2) ? (r1.seed ^ r2.seed) : r1.seed);
+        A.nofw[0] = P.gMate1fw ? P.nofw : P.norc; A.norc[0] = P.gMate1fw ? P.norc : P.nofw;
+        A.nofw[1] = P.gMate2fw ? P.nofw : P.norc; A.norc[1] = P.gMate2fw ? P.norc : P.nofw;
+        A.sinkReset(true);
+        if (r1.seq.size() > HT2_MAX_RDLEN || r2.seq.size() > HT2_MAX_RDLEN) W->err |= HT2_ERR_RDLEN;
+        if (!W->err) {
+            if (p1 && p2) {
+                A.paired = true; A.rightendonly = false; A.minsc[0] = ms1; A.minsc[1] = ms2;
+                ht2_fill_read(W->rd[0], r1); ht2_fill_read(W->rd[1], r2);
+                A.go();
+            } else if (p1 || p2) {
+                A.paired = false; A.rightendonly = !p1;
+                bool nf = A.nofw[p1 ? 0 : 1], nr = A.norc[p1 ? 0 : 1];
+                A.nofw[0] = nf; A.norc[0] = nr; A.nofw[1] = true; A.norc[1] = true;
+                A.minsc[0] = p1 ? ms1 : ms2; A.minsc[1] = HT2_IDX_MAX32;
+                ht2_fill_read(W->rd[0], p1 ? r1 : r2);
+                A.go();
+            }
+        }
+        out.rngLast = W->rnd.last; out.err = W->err; nLF += W->nLF;
+        if (W->err) { nerr++; fprintf(stderr, "pair %zu (%s): err=0x%x\n", i, r1.name.c_str(), W->err); }
+        { uint32_t v[8] = {W->maxPool, W->maxDepth, W->maxEdits, W->nSearched[0] > W->nSearched[1] ? W->nSearched[0] : W->nSearched[1], W->nRes[0] > W->nRes[1] ? W->nRes[0] : W->nRes[1], W->nGenomeHits, W->nPairs, 0};
+          for (int k = 0; k < 8; k++) if (v[k] > mx[k]) mx[k] = v[k]; }
+        out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
+        out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
+        for (uint32_t k = 0; k < W->nPairs; k++) out.pairs.push_back(std::make_pair(W->pairs[k][0], W->pairs[k][1]));
+        ht2_finish_paired(sam, *img, P, r1, r2, f1, f2, out);
+    }
+    for (size_t i = 0; !pairedMode && i < reads.size(); i++) {
         Ht2HostRead& rd = reads[i];
         rd.seed = ht2_gen_rand_seed(rd, 0);
         int64_t minsc = ht2_minsc((uint32_t)rd.seq.size());
