@@ -33,6 +33,13 @@ def test_host_state_machine_matches_golden_sam(hostsim_bin, tmp_path):
     assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_se.sam"), "rb").read())
 
 
+def test_host_state_machine_matches_golden_sam_paired(hostsim_bin, tmp_path):
+    """Paired-end: concordant pairs, mate rescue (alignMate), unpaired mates, unaligned mates."""
+    out = str(tmp_path / "pe.sam")
+    subprocess.run([hostsim_bin, "tiny", "tiny_pe_1.fa", out, "tiny_pe_2.fa"], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL)
+    assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe.sam"), "rb").read())
+
+
 def test_abi_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))

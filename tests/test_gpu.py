@@ -59,6 +59,31 @@ def test_tiny_se_matches_golden_reference_sam(h2, tiny):
         assert any(op in l.split("\t")[5] for l in txt.splitlines() if not l.startswith("@"))
 
 
+def test_tiny_pe_matches_golden_reference_sam(h2, tiny):
+    """Paired-end (--fr, -I 0 -X 1000): concordant, rescued, unpaired and unaligned mates."""
+    batch = h2.ReadBatch.from_fasta(os.path.join(GOLDEN, "tiny_pe_1.fa"), path2=os.path.join(GOLDEN, "tiny_pe_2.fa"))
+    assert batch.paired and batch.n == 600
+    sam, res = gpu_sam(tiny, batch)
+    assert sam_lines(sam) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe.sam"), "rb").read())
+    flags = set(int(l.split(b"\t")[1]) for l in sam_lines(sam) if not l.startswith(b"@"))
+    assert {99, 147, 83, 163}.issubset(flags) and (73 in flags or 89 in flags) and 77 in flags
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("name", ["sim10k", "hard20k"])
+def test_chr22_paired_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
+    """BASELINE configs[2]-shaped input (2x101 bp pairs): SAM identical to the reference."""
+    f1, f2 = os.path.join(DATA, name + "_1.fa"), os.path.join(DATA, name + "_2.fa")
+    if not os.path.exists(f1):
+        pytest.skip(f1 + " not staged")
+    batch = h2.ReadBatch.from_fasta(f1, path2=f2)
+    sam, res = gpu_sam(chr22, batch)
+    out = str(tmp_path / "ref.sam")
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", os.path.join(DATA, "22_20-21M"), "-1", f1, "-2", f2, "-S", out,
+                    "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    assert sam_lines(sam) == sam_lines(open(out, "rb").read())
+
+
 def test_in_kernel_seed_search_matches_oracle(h2, tiny, oracle_bin):
     """LF-step counts and alignments imply the same search as oracle/ht2_oracle.c:
     the first partial search of every strand recorded by the oracle must be
