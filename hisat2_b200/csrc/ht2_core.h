@@ -124,6 +124,20 @@ struct Ht2Rng {           // RandomSource, random_source.h:30-110
     }
 };
 
+// One activation of hybridSearch_recur in the explicit-stack formulation
+// (ht2_machine.h): the locals that must survive a "recursive call".
+struct Ht2Frame {
+    uint16_t pc;
+    uint8_t  rdi, alignMate, use_localindex, success, first, uniqueStop;
+    const Ht2Hit* hit;
+    Ht2Hit*  tempHit;
+    uint32_t hitoff, hitlen, dep, count, extoff, extlen, ncoords, nLocalHits, ti, poolMark;
+    int32_t  lid, ri;
+    int64_t  maxsc, prev_score, cushion;
+    Ht2Coord coords[8];
+    uint16_t localHits[16];
+};
+
 // Per-read (pair) workspace.  One per in-flight GPU thread.
 struct Ht2Work {
     Ht2Read     rd[2];
@@ -159,6 +173,13 @@ struct Ht2Work {
     uint32_t    maxLocalindexatts;
     uint32_t    nLF;      // LF steps (boundary ranks) executed
     uint32_t    maxPool, maxDepth, maxEdits; // high-water marks (sizing evidence)
+    // explicit-stack state machine (ht2_machine.h)
+    uint32_t    st, nFrames;
+    int64_t     childRet;
+    uint8_t     curRdi, curFw, alignRet, pad8;
+    uint8_t     found[2][2];
+    uint32_t    hybIter, hybHj, mateI, mateJ, mateSize[2];
+    Ht2Frame    frames[HT2_DEPTH_CAP];
     uint32_t    nSides;   // sides touched
     uint32_t    algBytes; // algorithmic bytes: sides*sideSz + ftab/eftab entries + SA samples + 2-bit ref bytes
 };
@@ -1353,8 +1374,17 @@ struct Ht2Aligner {
     HT2_NI void pairReads();
     HT2_NI bool peConcordant(int64_t off1, uint32_t len1, bool fw1, int64_t off2, uint32_t len2, bool fw2) const;
     HT2_NI bool alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff);
+    HT2_NI void alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff);
+    // explicit-stack formulation (ht2_machine.h)
+    HT2_HD void pushFrame(uint32_t rdi, const Ht2Hit* hit, uint32_t hitoff, uint32_t hitlen, bool alignMate, uint32_t dep);
+    HT2_NI void runFrame();
+    HT2_NI void runTop();
+    HT2_HD void machineStart();
+    HT2_HD bool machineDone() const;
+    HT2_HD void machineStep();
 };
 
 #include "ht2_core_impl.h"
+#include "ht2_machine.h"
 
 #endif // HT2_CORE_H_

@@ -498,6 +498,20 @@ HT2_NI void Ht2Aligner::pairReads()
 HT2_NI bool Ht2Aligner::alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
 {
     const uint32_t ordi = 1 - rdi;
+    alignMateAnchors(rdi, fw, tidx, toff);
+    for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
+        Ht2Hit& gh = W->genomeHits[hi];
+        uint32_t leftext = HT2_IDX_MAX32, rightext = HT2_IDX_MAX32;
+        extend(gh, ordi, leftext, rightext, 0);
+        hybridSearchRecur(ordi, gh, gh.rdoff, gh.len, true, 0);
+    }
+    return true;
+}
+
+// anchor search part of alignMate (hi_aligner.h:5600-5717): fills W->genomeHits
+HT2_NI void Ht2Aligner::alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
+{
+    const uint32_t ordi = 1 - rdi;
     const bool ofw = (fw == (P->gMate2fw != 0)) ? (P->gMate1fw != 0) : (P->gMate2fw != 0);
     const uint32_t rdlen = W->rd[ordi].len;
     const uint32_t minKL = P->minKLocal;
@@ -557,13 +571,6 @@ HT2_NI bool Ht2Aligner::alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32
         }
         W->nGenomeHits = maxsize;
     }
-    for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
-        Ht2Hit& gh = W->genomeHits[hi];
-        uint32_t leftext = HT2_IDX_MAX32, rightext = HT2_IDX_MAX32;
-        extend(gh, ordi, leftext, rightext, 0);
-        hybridSearchRecur(ordi, gh, gh.rdoff, gh.len, true, 0);
-    }
-    return true;
 }
 
 // HI_Aligner::go (hi_aligner.h:4048-4149); the repeat-index block

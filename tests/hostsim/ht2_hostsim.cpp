@@ -6,9 +6,19 @@
 // usage: ht2_hostsim <index_base> <reads.fa> <out.sam> [--spliced]
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../hisat2_b200/csrc/ht2_host.h"
+
+// HT2_RECURSIVE=1 runs the recursive formulation (ht2_core_impl.h) instead of the
+// explicit-stack state machine the kernels use (ht2_machine.h); both must agree.
+static void runRead(Ht2Aligner& A) {
+    static const bool recursive = getenv("HT2_RECURSIVE") != NULL;
+    if (recursive) { runRead(A); return; }
+    A.machineStart();
+    while (!A.machineDone()) A.machineStep();
+}
 
 int main(int argc, char** argv) {
     if (argc < 4) { fprintf(stderr, "usage: %s index reads.fa out.sam\n", argv[0]); return 2; }
@@ -49,14 +59,14 @@ int main(int argc, char** argv) {
             if (p1 && p2) {
                 A.paired = true; A.rightendonly = false; A.minsc[0] = ms1; A.minsc[1] = ms2;
                 ht2_fill_read(W->rd[0], r1); ht2_fill_read(W->rd[1], r2);
-                A.go();
+                runRead(A);
             } else if (p1 || p2) {
                 A.paired = false; A.rightendonly = !p1;
                 bool nf = A.nofw[p1 ? 0 : 1], nr = A.norc[p1 ? 0 : 1];
                 A.nofw[0] = nf; A.norc[0] = nr; A.nofw[1] = true; A.norc[1] = true;
                 A.minsc[0] = p1 ? ms1 : ms2; A.minsc[1] = HT2_IDX_MAX32;
                 ht2_fill_read(W->rd[0], p1 ? r1 : r2);
-                A.go();
+                runRead(A);
             }
         }
         out.rngLast = W->rnd.last; out.err = W->err; nLF += W->nLF;
@@ -85,7 +95,7 @@ int main(int argc, char** argv) {
         if (rd.seq.size() > HT2_MAX_RDLEN) W->err |= HT2_ERR_RDLEN;
         if (f.pass() && !W->err) {
             ht2_fill_read(W->rd[0], rd);
-            A.go();
+            runRead(A);
         }
         out.rngLast = W->rnd.last;
         out.err = W->err;
