@@ -25,7 +25,7 @@
 #define HT2_MAX_PHITS 64
 #define HT2_MAX_GHITS 24
 #define HT2_POOL 40
-#define HT2_MAX_SEARCHED 128
+#define HT2_MAX_SEARCHED 96
 #define HT2_MAX_RES 32
 #define HT2_MAX_PAIRS 48
 #define HT2_MAX_COORDS 24
@@ -173,6 +173,10 @@ struct Ht2Work {
     uint32_t    maxLocalindexatts;
     uint32_t    nLF;      // LF steps (boundary ranks) executed
     uint32_t    maxPool, maxDepth, maxEdits; // high-water marks (sizing evidence)
+    // per-read configuration (so a workspace can be resumed by any lane)
+    int64_t     cfgMinsc[2];
+    uint8_t     cfgPaired, cfgRightendonly, cfgNofw[2], cfgNorc[2], cfgPad[2];
+    uint32_t    unit, filtBits;
     // explicit-stack state machine (ht2_machine.h)
     uint32_t    st, nFrames;
     int64_t     childRet;
@@ -241,6 +245,18 @@ struct Ht2Aligner {
     bool     nofw[2], norc[2];
     int64_t  minsc[2];
 
+    // save / restore the per-read configuration in the workspace
+    HT2_HD void saveCfg() {
+        W->cfgPaired = paired; W->cfgRightendonly = rightendonly;
+        W->cfgNofw[0] = nofw[0]; W->cfgNofw[1] = nofw[1]; W->cfgNorc[0] = norc[0]; W->cfgNorc[1] = norc[1];
+        W->cfgMinsc[0] = minsc[0]; W->cfgMinsc[1] = minsc[1];
+    }
+    HT2_HD void attach(Ht2Work* W_) {
+        W = W_;
+        paired = W->cfgPaired != 0; rightendonly = W->cfgRightendonly != 0;
+        nofw[0] = W->cfgNofw[0] != 0; nofw[1] = W->cfgNofw[1] != 0; norc[0] = W->cfgNorc[0] != 0; norc[1] = W->cfgNorc[1] != 0;
+        minsc[0] = W->cfgMinsc[0]; minsc[1] = W->cfgMinsc[1];
+    }
     HT2_HD void bind(const uint8_t* blob_, const Ht2Params* P_, Ht2Work* W_) {
         blob = blob_;
         H = (const Ht2ImageHeader*)blob_;
@@ -1382,6 +1398,8 @@ struct Ht2Aligner {
     HT2_HD void machineStart();
     HT2_HD bool machineDone() const;
     HT2_HD void machineStep();
+    HT2_HD bool machineAtHeavyState() const;
+    HT2_HD void machineRun();
 };
 
 #include "ht2_core_impl.h"

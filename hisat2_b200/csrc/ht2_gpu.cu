@@ -60,10 +60,128 @@ __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, u
     }
 }
 
-// LANES = 1 : one thread per read (pair).
+// Set up workspace W for unit u (one read or one pair): filters, seeds, reads.
+// Returns true when there is something to align (machineStart() was called).
+__device__ __noinline__ bool ht2_setup_unit(Ht2Aligner& A, const Ht2Params& P, const DevBatch& b, uint32_t u, uint32_t& filtBits)
+{
+    Ht2Work* W = A.W;
+    W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0;
+    W->maxPool = W->maxDepth = W->maxEdits = 0;
+    W->nFrames = 0; W->st = TS_DONE;
+    filtBits = 0;
+    bool run = false;
+    if (!b.paired) {
+        const uint32_t ri = u;
+        A.paired = false; A.rightendonly = false;
+        A.nofw[0] = P.nofw != 0; A.norc[0] = P.norc != 0; A.nofw[1] = true; A.norc[1] = true;
+        A.minsc[0] = b.minsc[ri]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
+        W->rnd.init(b.seeds[ri]);
+        A.sinkReset(false);
+        if (b.filt[ri]) {
+            filtBits = 1;
+            ht2_load_read(W->rd[0], b, ri, W->err);
+            run = !W->err;
+        }
+    } else {
+        const uint32_t r1 = 2 * u, r2 = 2 * u + 1;
+        bool f1 = b.filt[r1] != 0, f2 = b.filt[r2] != 0;
+        filtBits = (f1 ? 1u : 0u) | (f2 ? 2u : 0u);
+        // nofw/norc per mate (hisat2.cpp:3444-3447)
+        A.nofw[0] = P.gMate1fw ? (P.nofw != 0) : (P.norc != 0);
+        A.norc[0] = P.gMate1fw ? (P.norc != 0) : (P.nofw != 0);
+        A.nofw[1] = P.gMate2fw ? (P.nofw != 0) : (P.norc != 0);
+        A.norc[1] = P.gMate2fw ? (P.norc != 0) : (P.nofw != 0);
+        W->rnd.init((f1 && f2) ? (b.seeds[r1] ^ b.seeds[r2]) : b.seeds[r1]);
+        A.sinkReset(true);
+        if (f1 && f2) {
+            A.paired = true; A.rightendonly = false;
+            A.minsc[0] = b.minsc[r1]; A.minsc[1] = b.minsc[r2];
+            ht2_load_read(W->rd[0], b, r1, W->err);
+            ht2_load_read(W->rd[1], b, r2, W->err);
+            run = !W->err;
+        } else if (f1 || f2) {
+            A.paired = false; A.rightendonly = !f1;
+            uint32_t rr = f1 ? r1 : r2;
+            uint32_t m = f1 ? 0 : 1;
+            bool nf = A.nofw[m], nr = A.norc[m];
+            A.nofw[0] = nf; A.norc[0] = nr; A.nofw[1] = true; A.norc[1] = true;
+            A.minsc[0] = b.minsc[rr]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
+            ht2_load_read(W->rd[0], b, rr, W->err);
+            run = !W->err;
+        }
+    }
+    W->unit = u; W->filtBits = filtBits;
+    A.saveCfg();
+    if (run) A.machineStart();
+    return run;
+}
+
+// Append unit u's alignments to the batch result pools.
+template <int LANES>
+__device__ __noinline__ void ht2_finish_unit(Ht2Work* W, const DevOut& o, uint32_t u, uint32_t filtBits, uint32_t lane)
+{
+    ht2gpu_read_result_t rr;
+    rr.n_aln[0] = (uint16_t)W->nRes[0];
+    rr.n_aln[1] = (uint16_t)W->nRes[1];
+    rr.n_pairs = W->nPairs;
+    rr.rng_state = W->rnd.last;
+    rr.n_lf = W->nLF;
+    rr.alg_bytes = W->algBytes;
+    rr.filt = filtBits;
+    uint32_t nal = W->nRes[0] + W->nRes[1];
+    uint32_t ned = 0;
+    for (uint32_t m = 0; m < 2; m++)
+        for (uint32_t i = 0; i < W->nRes[m]; i++) ned += W->res[m][i].nedits;
+    uint32_t aoff = 0, eoff = 0, poff = 0;
+    if (lane == 0) {
+        aoff = nal ? atomicAdd(&o.counters[0], nal) : 0;
+        eoff = ned ? atomicAdd(&o.counters[1], ned) : 0;
+        poff = W->nPairs ? atomicAdd(&o.counters[2], W->nPairs) : 0;
+    }
+    if (LANES > 1) {
+        aoff = __shfl_sync(0xffffffffu, aoff, 0);
+        eoff = __shfl_sync(0xffffffffu, eoff, 0);
+        poff = __shfl_sync(0xffffffffu, poff, 0);
+    }
+    if (aoff + nal > o.capAlns || eoff + ned > o.capEdits || poff + W->nPairs > o.capPairs) {
+        W->err |= HT2_ERR_OUTPUT;
+        rr.n_aln[0] = rr.n_aln[1] = 0; rr.n_pairs = 0;
+    } else if (lane == 0) {
+        uint32_t a = aoff, e = eoff;
+        for (uint32_t m = 0; m < 2; m++) {
+            for (uint32_t i = 0; i < W->nRes[m]; i++) {
+                const Ht2Res& r = W->res[m][i];
+                ht2gpu_aln_t& d = o.alns[a++];
+                d.tidx = r.tidx; d.toff = r.toff; d.score = (int32_t)r.score;
+                d.fw = (uint8_t)r.fw; d.mate = (uint8_t)m; d.n_edits = (uint16_t)r.nedits;
+                d.trim5 = (uint16_t)r.trim5p; d.trim3 = (uint16_t)r.trim3p;
+                d.ref_extent = r.rfextent; d.edit_off = e;
+                for (uint32_t k = 0; k < r.nedits; k++) {
+                    ht2gpu_edit_t& de = o.edits[e++];
+                    de.pos = r.edits[k].pos; de.chr = r.edits[k].chr; de.qchr = r.edits[k].qchr;
+                    de.type = r.edits[k].type; de.pad = 0; de.snp_id = r.edits[k].snpID;
+                }
+            }
+        }
+        for (uint32_t i = 0; i < W->nPairs; i++) {
+            o.pairs[2 * (poff + i)] = W->pairs[i][0];
+            o.pairs[2 * (poff + i) + 1] = W->pairs[i][1];
+        }
+    }
+    rr.aln_off = aoff;
+    rr.pair_off = poff;
+    rr.err = W->err;
+    if (lane == 0) o.reads[u] = rr;
+}
+
+// LANES = 1 : one lane per read (pair).  Every lane owns a read and all lanes of
+//             a warp spin in the same dispatcher loop; each iteration runs ONE
+//             segment of the lane's state machine (ht2_machine.h), so lanes that
+//             are in the same state fetch and execute the same instructions
+//             together.  Reads are claimed dynamically (atomic ticket) so a slow
+//             read never holds back the rest of its warp's queue.
 // LANES = 32: one warp per read; every lane executes the same scalar state
-//             machine on the warp's single workspace (uniform control flow, no
-//             divergence, broadcast loads), lane 0 publishes the results.
+//             machine on the warp's single workspace, lane 0 publishes.
 template <int LANES>
 __global__ void __launch_bounds__(128)
 ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
@@ -71,108 +189,221 @@ ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevO
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t tid = gtid / LANES;
     const uint32_t lane = gtid % LANES;
-    const uint32_t nthreads = (gridDim.x * blockDim.x) / LANES;
     Ht2Work* W = work + tid;
     Ht2Aligner A;
     A.bind(blob, &P, W);
-    for (uint32_t u = tid; u < b.n_units; u += nthreads) {
-        W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0;
-        W->maxPool = W->maxDepth = W->maxEdits = 0;
-        uint32_t filtBits = 0;
-        if (!b.paired) {
-            const uint32_t ri = u;
-            A.paired = false; A.rightendonly = false;
-            A.nofw[0] = P.nofw != 0; A.norc[0] = P.norc != 0; A.nofw[1] = true; A.norc[1] = true;
-            A.minsc[0] = b.minsc[ri]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
-            W->rnd.init(b.seeds[ri]);
-            A.sinkReset(false);
-            if (b.filt[ri]) {
-                filtBits = 1;
-                ht2_load_read(W->rd[0], b, ri, W->err);
-                if (!W->err) A.go();
+    // 0 = needs a unit, 1 = running, 2 = no work left.  Every lane stays in the loop
+    // until the whole warp is out of work: the warp vote at the top is the point
+    // where the lanes re-converge before the next segment.
+    int mode = 0;
+    uint32_t u = 0, filtBits = 0;
+    for (;;) {
+        if (!__any_sync(0xffffffffu, mode != 2)) break;
+        if (mode == 0) {
+            if (LANES == 1) u = atomicAdd(&o.counters[3], 1u);
+            else {
+                if (lane == 0) u = atomicAdd(&o.counters[3], 1u);
+                u = __shfl_sync(0xffffffffu, u, 0);
             }
-        } else {
-            const uint32_t r1 = 2 * u, r2 = 2 * u + 1;
-            bool f1 = b.filt[r1] != 0, f2 = b.filt[r2] != 0;
-            filtBits = (f1 ? 1u : 0u) | (f2 ? 2u : 0u);
-            // nofw/norc per mate (hisat2.cpp:3444-3447) for --fr
-            A.nofw[0] = P.gMate1fw ? (P.nofw != 0) : (P.norc != 0);
-            A.norc[0] = P.gMate1fw ? (P.norc != 0) : (P.nofw != 0);
-            A.nofw[1] = P.gMate2fw ? (P.nofw != 0) : (P.norc != 0);
-            A.norc[1] = P.gMate2fw ? (P.norc != 0) : (P.nofw != 0);
-            W->rnd.init((f1 && f2) ? (b.seeds[r1] ^ b.seeds[r2]) : b.seeds[r1]);
-            A.sinkReset(true);
-            if (f1 && f2) {
-                A.paired = true; A.rightendonly = false;
-                A.minsc[0] = b.minsc[r1]; A.minsc[1] = b.minsc[r2];
-                ht2_load_read(W->rd[0], b, r1, W->err);
-                ht2_load_read(W->rd[1], b, r2, W->err);
-                if (!W->err) A.go();
-            } else if (f1 || f2) {
-                A.paired = false; A.rightendonly = !f1;
-                uint32_t rr = f1 ? r1 : r2;
-                uint32_t m = f1 ? 0 : 1;
-                bool nf = A.nofw[m], nr = A.norc[m];
-                A.nofw[0] = nf; A.norc[0] = nr; A.nofw[1] = true; A.norc[1] = true;
-                A.minsc[0] = b.minsc[rr]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
-                ht2_load_read(W->rd[0], b, rr, W->err);
-                if (!W->err) A.go();
+            if (u >= b.n_units) mode = 2;
+            else if (ht2_setup_unit(A, P, b, u, filtBits)) mode = 1;
+            else ht2_finish_unit<LANES>(W, o, u, filtBits, lane);
+        } else if (mode == 1) {
+            A.machineStep();
+            if (A.machineDone()) {
+                ht2_finish_unit<LANES>(W, o, u, filtBits, lane);
+                mode = 0;
             }
         }
-        // ---- append results --------------------------------------------
-        ht2gpu_read_result_t rr;
-        rr.n_aln[0] = (uint16_t)W->nRes[0];
-        rr.n_aln[1] = (uint16_t)W->nRes[1];
-        rr.n_pairs = W->nPairs;
-        rr.rng_state = W->rnd.last;
-        rr.n_lf = W->nLF;
-        rr.alg_bytes = W->algBytes;
-        rr.filt = filtBits;
-        uint32_t nal = W->nRes[0] + W->nRes[1];
-        uint32_t ned = 0;
-        for (uint32_t m = 0; m < 2; m++)
-            for (uint32_t i = 0; i < W->nRes[m]; i++) ned += W->res[m][i].nedits;
-        uint32_t aoff = 0, eoff = 0, poff = 0;
-        if (lane == 0) {
-            aoff = nal ? atomicAdd(&o.counters[0], nal) : 0;
-            eoff = ned ? atomicAdd(&o.counters[1], ned) : 0;
-            poff = W->nPairs ? atomicAdd(&o.counters[2], W->nPairs) : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ht2_align_regroup_kernel: state-regrouping execution.
+//
+// A warp owns 32*K read slots (workspaces).  Each round it histograms the
+// states of its live slots, picks the most populous state, gathers up to 32
+// slots that are in that state and runs ONE segment of each on its 32 lanes.
+// All lanes therefore enter the same segment of the state machine together
+// (converged instruction fetch, one I-cache stream per warp) while the other
+// slots simply wait their turn.  Slot states live in shared memory.
+// ---------------------------------------------------------------------------
+#define RG_MAXK 16
+#define RG_WARPS 4
+#define RG_NEED 0u
+#define RG_FINISH 1u
+#define RG_TOP 2u          /* + TS_* */
+#define RG_FRAME 20u       /* + F_*  */
+#define RG_EXIT 255u
+#define RG_BINS 64
+
+__device__ __forceinline__ uint32_t rg_code(const Ht2Work* W)
+{
+    if (W->nFrames > 0) return RG_FRAME + W->frames[W->nFrames - 1].pc;
+    if (W->st == TS_DONE) return RG_FINISH;
+    return RG_TOP + W->st;
+}
+
+template <int RG_K>
+__global__ void __launch_bounds__(32 * RG_WARPS)
+ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+{
+    constexpr int RG_SLOTS = 32 * RG_K;
+    __shared__ uint8_t  sCode[RG_WARPS][RG_SLOTS];
+    __shared__ uint16_t sHist[RG_WARPS][RG_BINS];
+    __shared__ uint16_t sSel[RG_WARPS][32];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + wib;
+    Ht2Work* base = work + (size_t)gwarp * RG_SLOTS;
+    uint8_t* code = sCode[wib];
+    uint16_t* hist = sHist[wib];
+    uint16_t* sel = sSel[wib];
+    for (int j = 0; j < RG_K; j++) code[lane + 32 * j] = RG_NEED;
+    Ht2Aligner A;
+    A.bind(blob, &P, base);
+    __syncwarp();
+    for (;;) {
+        // ---- histogram of live slot states
+        hist[lane] = 0; hist[lane + 32] = 0;
+        __syncwarp();
+        for (int j = 0; j < RG_K; j++) {
+            uint32_t c = code[lane + 32 * j];
+            if (c != RG_EXIT) atomicAdd((unsigned int*)(hist) + (c >> 1), (c & 1) ? 0x10000u : 1u); // two u16 bins per word
         }
-        if (LANES > 1) {
-            aoff = __shfl_sync(0xffffffffu, aoff, 0);
-            eoff = __shfl_sync(0xffffffffu, eoff, 0);
-            poff = __shfl_sync(0xffffffffu, poff, 0);
+        __syncwarp();
+        uint32_t c0 = hist[lane], c1 = hist[lane + 32];
+        uint32_t best = c0 >= c1 ? ((c0 << 8) | lane) : ((c1 << 8) | (lane + 32));
+        for (int off = 16; off > 0; off >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best, off); best = v > best ? v : best; }
+        if ((best >> 8) == 0) break;                    // no live slot left
+        const uint32_t target = best & 0xff;
+        // ---- gather up to 32 slots in the target state
+        uint32_t taken = 0;
+        for (int j = 0; j < RG_K; j++) {
+            bool m = code[lane + 32 * j] == target;
+            uint32_t mask = __ballot_sync(0xffffffffu, m);
+            uint32_t rank = taken + __popc(mask & ((1u << lane) - 1));
+            if (m && rank < 32) sel[rank] = (uint16_t)(lane + 32 * j);
+            taken += __popc(mask);
         }
-        if (aoff + nal > o.capAlns || eoff + ned > o.capEdits || poff + W->nPairs > o.capPairs) {
-            W->err |= HT2_ERR_OUTPUT;
-            rr.n_aln[0] = rr.n_aln[1] = 0; rr.n_pairs = 0;
-        } else {
-            uint32_t a = aoff, e = eoff;
-            for (uint32_t m = 0; m < 2; m++) {
-                for (uint32_t i = 0; i < W->nRes[m]; i++) {
-                    const Ht2Res& r = W->res[m][i];
-                    ht2gpu_aln_t& d = o.alns[a++];
-                    d.tidx = r.tidx; d.toff = r.toff; d.score = (int32_t)r.score;
-                    d.fw = (uint8_t)r.fw; d.mate = (uint8_t)m; d.n_edits = (uint16_t)r.nedits;
-                    d.trim5 = (uint16_t)r.trim5p; d.trim3 = (uint16_t)r.trim3p;
-                    d.ref_extent = r.rfextent; d.edit_off = e;
-                    for (uint32_t k = 0; k < r.nedits; k++) {
-                        ht2gpu_edit_t& de = o.edits[e++];
-                        de.pos = r.edits[k].pos; de.chr = r.edits[k].chr; de.qchr = r.edits[k].qchr;
-                        de.type = r.edits[k].type; de.pad = 0; de.snp_id = r.edits[k].snpID;
-                    }
+        __syncwarp();
+        const uint32_t nsel = taken < 32 ? taken : 32;
+        // ---- run one segment on each selected slot
+        if (lane < nsel) {
+            const uint32_t slot = sel[lane];
+            Ht2Work* W = base + slot;
+            uint32_t nc;
+            if (target == RG_NEED) {
+                uint32_t u = atomicAdd(&o.counters[3], 1u);
+                if (u >= b.n_units) nc = RG_EXIT;
+                else {
+                    A.W = W;
+                    uint32_t filtBits;
+                    bool run = ht2_setup_unit(A, P, b, u, filtBits);
+                    if (run) { while (!A.machineAtHeavyState()) A.machineStep(); } // TS_START / TS_NEXTBWT glue
+                    nc = run ? rg_code(W) : RG_FINISH;
                 }
+            } else if (target == RG_FINISH) {
+                ht2_finish_unit<1>(W, o, W->unit, W->filtBits, 0);
+                nc = RG_NEED;
+            } else {
+                A.attach(W);
+                A.machineRun();
+                nc = rg_code(W);
             }
-            for (uint32_t i = 0; i < W->nPairs; i++) {
-                o.pairs[2 * (poff + i)] = W->pairs[i][0];
-                o.pairs[2 * (poff + i) + 1] = W->pairs[i][1];
-            }
+            code[slot] = (uint8_t)nc;
         }
-        rr.aln_off = aoff;
-        rr.pair_off = poff;
-        rr.err = W->err;
-        if (lane == 0) o.reads[u] = rr;
-        if (LANES > 1) __syncwarp();
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ht2_align_block_regroup_kernel: like the warp version, but the WHOLE block
+// agrees on one state per round, so every warp of the SM (one block per SM)
+// runs the same segment of code at the same time: one instruction stream in the
+// I-cache, several warps per scheduler to hide memory latency.
+// ---------------------------------------------------------------------------
+#define BRG_WARPS 8
+template <int RG_K>
+__global__ void __launch_bounds__(32 * BRG_WARPS)
+ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+{
+    constexpr int NT = 32 * BRG_WARPS;
+    constexpr int SLOTS = NT * RG_K;
+    __shared__ uint8_t  sCode[SLOTS];
+    __shared__ unsigned int sHist[RG_BINS];
+    __shared__ uint16_t sSel[NT];
+    __shared__ unsigned int sWarpCnt[RG_K][BRG_WARPS];
+    __shared__ unsigned int sTarget, sNsel;
+    const uint32_t t = threadIdx.x, lane = t & 31, wib = t >> 5;
+    Ht2Work* base = work + (size_t)blockIdx.x * SLOTS;
+    for (int j = 0; j < RG_K; j++) sCode[t + NT * j] = RG_NEED;
+    Ht2Aligner A;
+    A.bind(blob, &P, base);
+    __syncthreads();
+    for (;;) {
+        if (t < RG_BINS) sHist[t] = 0;
+        __syncthreads();
+        for (int j = 0; j < RG_K; j++) {
+            uint32_t c = sCode[t + NT * j];
+            if (c != RG_EXIT) atomicAdd(&sHist[c], 1u);
+        }
+        __syncthreads();
+        if (wib == 0) {
+            uint32_t c0 = sHist[lane], c1 = sHist[lane + 32];
+            uint32_t best = c0 >= c1 ? ((c0 << 8) | lane) : ((c1 << 8) | (lane + 32));
+            for (int off = 16; off > 0; off >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best, off); best = v > best ? v : best; }
+            if (lane == 0) { sTarget = (best >> 8) ? (best & 0xff) : 0xffffffffu; sNsel = 0; }
+        }
+        __syncthreads();
+        const uint32_t target = sTarget;
+        if (target == 0xffffffffu) break;
+        // ---- block-wide gather of up to NT slots in the target state
+        bool m[RG_K];
+        for (int j = 0; j < RG_K; j++) {
+            m[j] = sCode[t + NT * j] == target;
+            uint32_t mask = __ballot_sync(0xffffffffu, m[j]);
+            if (lane == 0) sWarpCnt[j][wib] = __popc(mask);
+        }
+        __syncthreads();
+        {
+            uint32_t baseRank = 0;
+            for (int j = 0; j < RG_K; j++) {
+                uint32_t before = 0, total = 0;
+                for (int w = 0; w < BRG_WARPS; w++) { uint32_t c = sWarpCnt[j][w]; if (w < (int)wib) before += c; total += c; }
+                uint32_t mask = __ballot_sync(0xffffffffu, m[j]);
+                uint32_t rank = baseRank + before + __popc(mask & ((1u << lane) - 1));
+                if (m[j] && rank < NT) sSel[rank] = (uint16_t)(t + NT * j);
+                baseRank += total;
+            }
+            if (t == 0) sNsel = baseRank < NT ? baseRank : NT;
+        }
+        __syncthreads();
+        const uint32_t nsel = sNsel;
+        if (t < nsel) {
+            const uint32_t slot = sSel[t];
+            Ht2Work* W = base + slot;
+            uint32_t nc;
+            if (target == RG_NEED) {
+                uint32_t u = atomicAdd(&o.counters[3], 1u);
+                if (u >= b.n_units) nc = RG_EXIT;
+                else {
+                    A.W = W;
+                    uint32_t filtBits;
+                    bool run = ht2_setup_unit(A, P, b, u, filtBits);
+                    if (run) { while (!A.machineAtHeavyState()) A.machineStep(); }
+                    nc = run ? rg_code(W) : RG_FINISH;
+                }
+            } else if (target == RG_FINISH) {
+                ht2_finish_unit<1>(W, o, W->unit, W->filtBits, 0);
+                nc = RG_NEED;
+            } else {
+                A.attach(W);
+                A.machineRun();
+                nc = rg_code(W);
+            }
+            sCode[slot] = (uint8_t)nc;
+        }
+        __syncthreads();
     }
 }
 
@@ -189,6 +420,8 @@ struct ht2gpu_handle {
     int            device;
     int            nSM;
     int            tpb, bpsm, lanes;
+    bool           regroup, blockRegroup;
+    int            rgK;
     Ht2Work*       dWork;
     size_t         nWork;
     cudaStream_t   stream;
@@ -250,7 +483,21 @@ static int finishOpen(ht2gpu_handle* h)
     h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 128;
     if (h->tpb > 128) h->tpb = 128;
     h->bpsm = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 4;
-    h->lanes = h->opt.warp_per_read ? 32 : 1;
+    h->lanes = h->opt.warp_per_read == 1 ? 32 : 1;
+    h->regroup = (h->opt.warp_per_read == 2 || h->opt.warp_per_read == 0);
+    if (h->opt.warp_per_read == 3) h->regroup = false; // 3 = plain one-lane-per-read dispatcher
+    h->blockRegroup = (h->opt.warp_per_read == 4);
+    if (h->blockRegroup) h->regroup = true;
+    if (h->regroup) {
+        h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 32 * RG_WARPS;
+        if (h->tpb > 32 * RG_WARPS) h->tpb = 32 * RG_WARPS;
+        h->tpb = (h->tpb / 32) * 32; if (h->tpb < 32) h->tpb = 32;
+        h->bpsm = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 1;
+        h->rgK = h->opt.slots_per_lane > 0 ? h->opt.slots_per_lane : 4;
+        if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8 && h->rgK != 16) h->rgK = 4;
+        if (h->blockRegroup) h->tpb = 32 * BRG_WARPS;
+        h->nWork = (size_t)h->nSM * h->bpsm * (h->tpb / 32) * 32 * h->rgK;
+    } else
     h->nWork = (size_t)h->nSM * h->bpsm * h->tpb / h->lanes;
     CK(cudaMalloc(&h->dWork, h->nWork * sizeof(Ht2Work)));
     CK(cudaMemset(h->dWork, 0, h->nWork * sizeof(Ht2Work)));
@@ -456,6 +703,26 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
     o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
     o.counters = h->dCounters;
     CK(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned int), h->stream));
+    if (h->regroup) {
+        uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
+        if (h->blockRegroup) {
+            switch (h->rgK) {
+                case 2:  ht2_align_block_regroup_kernel<2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 8:  ht2_align_block_regroup_kernel<8><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                default: ht2_align_block_regroup_kernel<4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            }
+            CK(cudaGetLastError());
+            return HT2GPU_OK;
+        }
+        switch (h->rgK) {
+            case 2:  ht2_align_regroup_kernel<2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 8:  ht2_align_regroup_kernel<8><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 16: ht2_align_regroup_kernel<16><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            default: ht2_align_regroup_kernel<4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+        }
+        CK(cudaGetLastError());
+        return HT2GPU_OK;
+    }
     uint32_t perBlock = (uint32_t)(h->tpb / h->lanes);
     uint32_t grid = (uint32_t)(h->nWork / perBlock);
     uint32_t needBlocks = (units + perBlock - 1) / perBlock;

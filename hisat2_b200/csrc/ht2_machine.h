@@ -733,5 +733,28 @@ HT2_HD void Ht2Aligner::machineStep()
     if (W->nFrames > 0) runFrame();
     else runTop();
 }
+// "Heavy" states are the ones worth regrouping lanes for (index searches,
+// reference extension, combine); everything else is short glue that is chained
+// onto the end of the previous segment.
+HT2_HD bool Ht2Aligner::machineAtHeavyState() const
+{
+    if (W->nFrames > 0) {
+        switch (W->frames[W->nFrames - 1].pc) {
+            case F_ENTER: case F_L_START: case F_L_WHILE: case F_L_COORD: case F_L_AFTER_WHILE: case F_L_GCOORD: case F_L_TRIM: case F_L_EXT:
+            case F_R_START: case F_R_WHILE: case F_R_COORD: case F_R_AFTER_WHILE: case F_R_GCOORD: case F_R_TRIM: case F_R_EXT:
+                return true;
+            default: return false;
+        }
+    }
+    switch (W->st) {
+        case TS_PS: case TS_ALIGN: case TS_HYB_EXTEND: case TS_MATE_SEARCH: case TS_MATE_ANCHOR: case TS_DONE: return true;
+        default: return false;
+    }
+}
+// run one heavy segment plus the glue that follows it
+HT2_HD void Ht2Aligner::machineRun()
+{
+    do { machineStep(); } while (!machineAtHeavyState());
+}
 
 #endif // HT2_MACHINE_H_
