@@ -162,8 +162,8 @@ struct Ht2Work {
     uint32_t    concordInspected[2];        // _concordantIdxInspected
     Ht2Coord    coords[HT2_MAX_COORDS];     // BWTHit::_coords scratch
     uint32_t    nCoords;
-    uint8_t     refbuf[HT2_REFBUF + 16];
-    uint8_t     refbuf2[HT2_REFBUF + 16];
+    alignas(8) uint8_t refbuf[HT2_REFBUF + 16];   // getStretch stores 32-bit words
+    alignas(8) uint8_t refbuf2[HT2_REFBUF + 16];
     int64_t     tscores[HT2_MAX_RDLEN];
     int64_t     tscores2[HT2_MAX_RDLEN];
     Ht2Rng      rnd;
@@ -396,8 +396,14 @@ struct Ht2Aligner {
 
     // ---- 2-bit reference (reference.cpp:396-430, 486-640) ------------------
     HT2_HD uint32_t refLen(uint32_t tidx) const { return ((const uint32_t*)(blob + H->o_refLens))[tidx]; }
-    // dest[i] = base at toff+i for i<count; 4 inside N gaps / past the end.
-    HT2_NI void getStretch(uint8_t* dest, uint32_t tidx, uint32_t toff, uint32_t count) const {
+    // Decodes count bases starting at toff: 0-3, or 4 inside N gaps / past the
+    // end.  Returns the address of the first base, dest + skip with skip < 4:
+    // when the window lies inside one unambiguous stretch and dest is 4-byte
+    // aligned, whole bytes of the 2-bit buffer are expanded with one 32-bit
+    // store each (the reference's getStretch also returns such an offset,
+    // reference.cpp:486-640).  dest needs room for count + 7 bytes.  With
+    // allowSkip == false the bases always start at dest.
+    HT2_NI const uint8_t* getStretch(uint8_t* dest, uint32_t tidx, uint32_t toff, uint32_t count, bool allowSkip = true) const {
         W->algBytes += (count + 3) >> 2;
         const Ht2RefRecord* recs = (const Ht2RefRecord*)(blob + H->o_recs);
         const uint32_t* recOffs = (const uint32_t*)(blob + H->o_refRecOffs);
@@ -409,20 +415,36 @@ struct Ht2Aligner {
         uint32_t cur = 0;
         for (uint32_t i = reci; i < recf && count > 0; i++) {
             off += recs[i].off;
+            const uint32_t rlen = recs[i].len;
+            if (allowSkip && cur == 0 && t >= off && t + count <= off + rlen && (((uintptr_t)dest) & 3) == 0) {
+                bufOff += (t - off);
+                const uint32_t skip = (uint32_t)(bufOff & 3);
+                const uint8_t* src = buf + (bufOff >> 2);
+                uint32_t* d32 = (uint32_t*)dest;
+                const uint32_t nb = (skip + count + 3) >> 2;
+                for (uint32_t k = 0; k < nb; k++) {
+                    uint32_t x = src[k];
+                    x = (x | (x << 12)) & 0x000f000fu;
+                    x = (x | (x << 6)) & 0x03030303u;
+                    d32[k] = x;
+                }
+                return dest + skip;
+            }
             while (t < off && count > 0) { dest[cur++] = 4; t++; count--; }
             if (count == 0) break;
-            if (t < off + recs[i].len) bufOff += (t - off);
-            else bufOff += recs[i].len;
-            off += recs[i].len;
+            if (t < off + rlen) bufOff += (t - off);
+            else bufOff += rlen;
+            off += rlen;
             while (t < off && count > 0) {
                 dest[cur++] = (buf[bufOff >> 2] >> ((bufOff & 3) << 1)) & 3;
                 bufOff++; t++; count--;
             }
         }
         while (count > 0) { dest[cur++] = 4; count--; }
+        return dest;
     }
     HT2_HD int getBase(uint32_t tidx, uint32_t toff) const {
-        uint8_t b; getStretch(&b, tidx, toff, 1); return b;
+        uint8_t b[8]; return *getStretch(b + 1, tidx, toff, 1);
     }
 
     // ---- joined <-> text coordinates (gfm.h:5527-5600) ---------------------
@@ -464,15 +486,17 @@ struct Ht2Aligner {
                        uint32_t& ntop, uint32_t& nbot, uint32_t& nntop, uint32_t& nnbot) {
         if (bot - top != 1) {
             W->nLF += 2;
-            W->algBytes += ((top / fm.g->sideGbwtLen) == (bot / fm.g->sideGbwtLen) ? 1u : 2u) * fm.g->sideSz;
+            W->algBytes += ((top >> HT2_SIDE_SHIFT) == (bot >> HT2_SIDE_SHIFT) ? 1u : 2u) * HT2_SIDE_BYTES;
             ntop = ht2_lf(fm, top, c);
             nbot = ht2_lf(fm, bot, c);
             nntop = ntop; nnbot = nbot;
         } else {
             W->nLF += 1;
-            W->algBytes += fm.g->sideSz;
-            if (ht2_rowL(fm, top) != c || ht2_is_zoff(fm, top)) { ntop = nbot = nntop = nnbot = 0; return; }
-            ntop = ht2_lf(fm, top, c);
+            W->algBytes += HT2_SIDE_BYTES;
+            int own;
+            uint32_t r = ht2_lf_own(fm, top, own);
+            if (own != c || ht2_is_zoff(fm, top)) { ntop = nbot = nntop = nnbot = 0; return; }
+            ntop = r;
             nbot = (uint32_t)(IT)(ntop + 1);
             nntop = ntop; nnbot = nbot;
         }
@@ -631,18 +655,22 @@ struct Ht2Aligner {
     template <typename IT>
     HT2_NI uint32_t resolveRow(const Ht2Fm<IT>& fm, uint32_t row) {
         uint32_t steps = 0;
+        const uint32_t offMask = fm.offMask, z0 = fm.z0;
+        uint32_t res;
         while (true) {
-            if (ht2_is_zoff(fm, row)) return (uint32_t)(IT)(0 + steps);
-            if ((row & fm.g->offMask) == row) {
+            if (row == z0) { res = (uint32_t)(IT)(0 + steps); break; }
+            if ((row & offMask) == row) {
                 W->algBytes += (uint32_t)sizeof(IT);
-                return (uint32_t)(IT)(fm.offs[row >> fm.g->offRate] + steps);
+                res = (uint32_t)(IT)(fm.offs[row >> fm.offRate] + steps);
+                break;
             }
-            int c = ht2_rowL(fm, row);
-            row = ht2_lf(fm, row, c);
-            W->nLF++;
-            W->algBytes += fm.g->sideSz;
+            int c;
+            row = ht2_lf_own(fm, row, c);
             steps++;
         }
+        W->nLF += steps;
+        W->algBytes += steps * HT2_SIDE_BYTES;
+        return res;
     }
 
     // HI_Aligner::getGenomeCoords (hi_aligner.h:5774-5855); appends to W->coords.
@@ -735,11 +763,15 @@ struct Ht2Aligner {
         else if (rfoff < 0 && rflen > contig_len) rflen = contig_len;
         if (rflen == 0) return 0;
         if (rflen > HT2_REFBUF) { W->err |= HT2_ERR_RDLEN; return 0; }
-        uint8_t* rfseq = W->refbuf;
+        const uint8_t* rfseq = W->refbuf;
         {
             uint32_t lead = rfoff < 0 ? (uint32_t)(-rfoff) : 0;
-            for (uint32_t i = 0; i < lead && i < rflen; i++) rfseq[i] = 4;
-            if (rflen > lead) getStretch(rfseq + lead, tidx, rfoff > 0 ? (uint32_t)rfoff : 0, rflen - lead);
+            if (lead == 0) rfseq = getStretch(W->refbuf, tidx, (uint32_t)rfoff, rflen);
+            else {
+                // window starts before the reference: unaligned destination takes the generic path (skip 0)
+                for (uint32_t i = 0; i < lead && i < rflen; i++) W->refbuf[i] = 4;
+                if (rflen > lead) getStretch(W->refbuf + lead, tidx, 0, rflen - lead, false);
+            }
         }
         uint32_t tmp_mm = 0;
         int mm_min_rd_i = (int)rdoff;
@@ -779,11 +811,15 @@ struct Ht2Aligner {
         else if (rfoff < 0 && rflen > contig_len) rflen = contig_len;
         if (rflen == 0) return 0;
         if (rflen > HT2_REFBUF) { W->err |= HT2_ERR_RDLEN; return 0; }
-        uint8_t* rfseq = W->refbuf;
+        const uint8_t* rfseq = W->refbuf;
         {
             uint32_t lead = rfoff < 0 ? (uint32_t)(-rfoff) : 0;
-            for (uint32_t i = 0; i < lead && i < rflen; i++) rfseq[i] = 4;
-            if (rflen > lead) getStretch(rfseq + lead, tidx, rfoff > 0 ? (uint32_t)rfoff : 0, rflen - lead);
+            if (lead == 0) rfseq = getStretch(W->refbuf, tidx, (uint32_t)rfoff, rflen);
+            else {
+                // window starts before the reference: unaligned destination takes the generic path (skip 0)
+                for (uint32_t i = 0; i < lead && i < rflen; i++) W->refbuf[i] = 4;
+                if (rflen > lead) getStretch(W->refbuf + lead, tidx, 0, rflen - lead, false);
+            }
         }
         const uint32_t rdoff_add = rdoff - base_rdoff;
         uint32_t tmp_mm = 0;
@@ -983,9 +1019,8 @@ struct Ht2Aligner {
         if (this_toff + len > reflen) return false;
         if (this_toff + len + (uint32_t)this_ref_ext > reflen) this_ref_ext = (int)(reflen - (this_toff + len));
         if (len + (uint32_t)this_ref_ext > HT2_REFBUF || len > HT2_MAX_RDLEN) { W->err |= HT2_ERR_RDLEN; return false; }
-        uint8_t* refbuf = W->refbuf;
-        getStretch(refbuf, a.tidx, this_toff, len + (uint32_t)this_ref_ext);
-        uint8_t* refbuf2 = NULL;
+        const uint8_t* refbuf = getStretch(W->refbuf, a.tidx, this_toff, len + (uint32_t)this_ref_ext);
+        const uint8_t* refbuf2 = NULL;
         uint32_t maxscorei = HT2_IDX_MAX32;
         int64_t maxscore = HT2_MIN_I64;
         if (ins || del) {
@@ -993,8 +1028,8 @@ struct Ht2Aligner {
             int lim = (int)(other_toff + other_len - len);
             if (lim < other_ref_ext) other_ref_ext = lim;
             if ((int)len + other_ref_ext > (int)HT2_REFBUF || other_ref_ext < 0) { W->err |= HT2_ERR_RDLEN; return false; }
-            getStretch(W->refbuf2, o.tidx, other_toff + other_len - len - (uint32_t)other_ref_ext, len + (uint32_t)other_ref_ext);
-            refbuf2 = W->refbuf2 + other_ref_ext;
+            refbuf2 = getStretch(W->refbuf2, o.tidx, other_toff + other_len - len - (uint32_t)other_ref_ext, len + (uint32_t)other_ref_ext)
+                      + other_ref_ext;
             int64_t* ts = W->tscores; int64_t* ts2 = W->tscores2;
             int inslen = (ins ? (int)(rddif - refdif) : 0);
             int dellen = (del ? (int)(refdif - rddif) : 0);

@@ -19,6 +19,12 @@
 
 #define HT2_IDX_MAX32 0xffffffffu
 
+#if defined(__CUDACC__)
+#define HT2_ALIGN16 __align__(16)
+#else
+#define HT2_ALIGN16 __attribute__((aligned(16)))
+#endif
+
 // View of one FM index inside the blob.
 template <typename IT>
 struct Ht2Fm {
@@ -30,8 +36,13 @@ struct Ht2Fm {
     const IT* zoffs;
     const IT* rstarts;
     const IT* plen;
+    uint32_t z0;          // the '$' row of a linear index
+    uint32_t offMask, offRate;
     HT2_HD void init(const uint8_t* blob, const Ht2Gfm* geom) {
         g = geom;
+        z0 = geom->zOff0;
+        offMask = geom->offMask;
+        offRate = geom->offRate;
         gfm = blob + geom->o_gfm;
         ftab = (const IT*)(blob + geom->o_ftab);
         eftab = (const IT*)(blob + geom->o_eftab);
@@ -68,42 +79,67 @@ HT2_HD uint32_t ht2_count_upto(const uint8_t* side, uint32_t charOff, int c) {
     return cnt;
 }
 
+// ---- linear indexes: 32-byte rank sides (ht2_image.h) ----------------------
+struct HT2_ALIGN16 Ht2SideBwt { uint64_t lo, hi; };   // 64 BW chars
+
+template <typename IT>
+HT2_HD const uint8_t* ht2_side(const Ht2Fm<IT>& fm, uint32_t row) {
+    return fm.gfm + ((uint64_t)(row >> HT2_SIDE_SHIFT) << 5);
+}
+
+// # occurrences of c among the first n (<64) chars of a side.
+HT2_HD uint32_t ht2_count_side(const Ht2SideBwt& w, int c, uint32_t n) {
+    const uint64_t p = ht2_rep2(c);
+    uint64_t x0 = ~(w.lo ^ p), x1 = ~(w.hi ^ p);
+    x0 = x0 & (x0 >> 1) & 0x5555555555555555ull;
+    x1 = x1 & (x1 >> 1) & 0x5555555555555555ull;
+    const uint64_t low = (1ull << ((n & 31) << 1)) - 1;
+    const bool hi = n >= 32;
+    const uint64_t m0 = hi ? ~0ull : low, m1 = hi ? low : 0ull;
+    return (uint32_t)(HT2_POPC64(x0 & m0) + HT2_POPC64(x1 & m1));
+}
+
+HT2_HD int ht2_side_char(const Ht2SideBwt& w, uint32_t charOff) {
+    const uint64_t v = (charOff & 32) ? w.hi : w.lo;
+    return (int)((v >> ((charOff & 31) << 1)) & 3);
+}
+
 // BW character at 'row' (GFM::rowL).
 template <typename IT>
 HT2_HD int ht2_rowL(const Ht2Fm<IT>& fm, uint32_t row) {
-    uint32_t sideNum = row / fm.g->sideGbwtLen;
-    uint32_t charOff = row - sideNum * fm.g->sideGbwtLen;
-    const uint8_t* side = fm.gfm + (uint64_t)sideNum * fm.g->sideSz;
-    return (side[charOff >> 2] >> ((charOff & 3) << 1)) & 3;
+    const uint32_t charOff = row & (HT2_SIDE_CHARS - 1);
+    return (ht2_side(fm, row)[charOff >> 2] >> ((charOff & 3) << 1)) & 3;
 }
 
 // LF(row, c) = fchr[c] + occ(c, row)   (GFM::countBt2Side gfm.h:2958-2999,
 // mapLF(l,c) gfm.h:3712-3732).  The '$' is stored as an 'A' and must not be
-// counted (gfm.h:2967-2979).
+// counted (gfm.h:2967-2979); fchr[c] is folded into the side's occ entries.
+template <typename IT>
+HT2_HD uint32_t ht2_lf_side(const Ht2Fm<IT>& fm, const uint8_t* side, const Ht2SideBwt& w, uint32_t row, int c) {
+    const uint32_t charOff = row & (HT2_SIDE_CHARS - 1);
+    uint32_t cnt = ht2_count_side(w, c, charOff);
+    // '$' inside [sideStart, row): unsigned compare also rejects z < sideStart
+    if (c == 0 && (uint32_t)(fm.z0 - (row - charOff)) < charOff) cnt--;
+    return (uint32_t)(IT)(((const uint32_t*)(side + 16))[c] + cnt);
+}
 template <typename IT>
 HT2_HD uint32_t ht2_lf(const Ht2Fm<IT>& fm, uint32_t row, int c) {
-    const Ht2Gfm* g = fm.g;
-    uint32_t sideNum = row / g->sideGbwtLen;
-    uint32_t charOff = row - sideNum * g->sideGbwtLen;
-    const uint8_t* side = fm.gfm + (uint64_t)sideNum * g->sideSz;
-    uint32_t cnt = ht2_count_upto(side, charOff, c);
-    if (c == 0) {
-        uint32_t sideStart = row - charOff;
-        for (uint32_t i = 0; i < g->nzOffs; i++) {
-            uint32_t z = fm.zoffs[i];
-            if (z >= sideStart && z < row) cnt--;
-        }
-    }
-    const IT* acgt = (const IT*)(side + g->sideGbwtSz + (g->linearFM ? 0 : 2 * sizeof(IT)));
-    return (uint32_t)(IT)(acgt[c] + cnt + g->fchr[c]);
+    const uint8_t* side = ht2_side(fm, row);
+    const Ht2SideBwt w = *(const Ht2SideBwt*)side;
+    return ht2_lf_side(fm, side, w, row, c);
+}
+// c = rowL(row); returns LF(row, c)  (one side load; GFM::mapLF1 gfm.h:3889-3911).
+template <typename IT>
+HT2_HD uint32_t ht2_lf_own(const Ht2Fm<IT>& fm, uint32_t row, int& c) {
+    const uint8_t* side = ht2_side(fm, row);
+    const Ht2SideBwt w = *(const Ht2SideBwt*)side;
+    c = ht2_side_char(w, row & (HT2_SIDE_CHARS - 1));
+    return ht2_lf_side(fm, side, w, row, c);
 }
 
 template <typename IT>
 HT2_HD bool ht2_is_zoff(const Ht2Fm<IT>& fm, uint32_t row) {
-    for (uint32_t i = 0; i < fm.g->nzOffs; i++) {
-        if (row == fm.zoffs[i]) return true;
-    }
-    return false;
+    return row == fm.z0;
 }
 
 // ftab lookup for the ftabChars bases seq[off..off+ftabChars) (GFM::ftabSeqToInt/ftabHi/ftabLo/ftabLoHi, gfm.h:2569-2715).

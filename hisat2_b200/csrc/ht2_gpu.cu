@@ -27,8 +27,6 @@ struct DevBatch {
     const uint8_t*  qual;   // may be NULL
     const uint64_t* offs;
     const uint32_t* seeds;
-    const uint8_t*  filt;   // per read: 1 = passes all filters
-    const int32_t*  minsc;  // per read
     uint32_t        n_units;
     int32_t         paired;
 };
@@ -60,6 +58,25 @@ __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, u
     }
 }
 
+// Per-read filters and minimum score (hisat2.cpp:3387-3440): length filter,
+// N filter (Scoring::nFilter, nCeil = L,2,0.1 -- hisat2.cpp:443), score filter
+// (minsc = L,0,-0.2 clamped to <= 0 -- hisat2.cpp:441, 3395-3402).  All products
+// are exact in double (24-bit constants x lengths < 2^9), so host
+// (ht2_host.cpp:ht2_minsc/ht2_filters) and device agree bit for bit.
+__device__ __forceinline__ bool ht2_dev_filter(const DevBatch& b, uint32_t ri, int64_t& minsc)
+{
+    const uint64_t o0 = b.offs[ri];
+    const uint32_t len = (uint32_t)(b.offs[ri + 1] - o0);
+    int64_t m = (int64_t)((double)-0.2f * (double)len);
+    if (m > 0) m = 0;
+    minsc = m;
+    const uint32_t maxns = (uint32_t)((double)2.0f + (double)0.1f * (double)len);
+    const uint8_t* s = b.seq + o0;
+    uint32_t ns = 0;
+    for (uint32_t k = 0; k < len; k++) ns += (s[k] == 4);
+    return ns <= maxns && len >= 2 && 0 >= m;
+}
+
 // Set up workspace W for unit u (one read or one pair): filters, seeds, reads.
 // Returns true when there is something to align (machineStart() was called).
 __device__ __noinline__ bool ht2_setup_unit(Ht2Aligner& A, const Ht2Params& P, const DevBatch& b, uint32_t u, uint32_t& filtBits)
@@ -74,17 +91,20 @@ __device__ __noinline__ bool ht2_setup_unit(Ht2Aligner& A, const Ht2Params& P, c
         const uint32_t ri = u;
         A.paired = false; A.rightendonly = false;
         A.nofw[0] = P.nofw != 0; A.norc[0] = P.norc != 0; A.nofw[1] = true; A.norc[1] = true;
-        A.minsc[0] = b.minsc[ri]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
+        int64_t ms;
+        const bool f0 = ht2_dev_filter(b, ri, ms);
+        A.minsc[0] = ms; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
         W->rnd.init(b.seeds[ri]);
         A.sinkReset(false);
-        if (b.filt[ri]) {
+        if (f0) {
             filtBits = 1;
             ht2_load_read(W->rd[0], b, ri, W->err);
             run = !W->err;
         }
     } else {
         const uint32_t r1 = 2 * u, r2 = 2 * u + 1;
-        bool f1 = b.filt[r1] != 0, f2 = b.filt[r2] != 0;
+        int64_t ms1, ms2;
+        const bool f1 = ht2_dev_filter(b, r1, ms1), f2 = ht2_dev_filter(b, r2, ms2);
         filtBits = (f1 ? 1u : 0u) | (f2 ? 2u : 0u);
         // nofw/norc per mate (hisat2.cpp:3444-3447)
         A.nofw[0] = P.gMate1fw ? (P.nofw != 0) : (P.norc != 0);
@@ -95,7 +115,7 @@ __device__ __noinline__ bool ht2_setup_unit(Ht2Aligner& A, const Ht2Params& P, c
         A.sinkReset(true);
         if (f1 && f2) {
             A.paired = true; A.rightendonly = false;
-            A.minsc[0] = b.minsc[r1]; A.minsc[1] = b.minsc[r2];
+            A.minsc[0] = ms1; A.minsc[1] = ms2;
             ht2_load_read(W->rd[0], b, r1, W->err);
             ht2_load_read(W->rd[1], b, r2, W->err);
             run = !W->err;
@@ -105,7 +125,7 @@ __device__ __noinline__ bool ht2_setup_unit(Ht2Aligner& A, const Ht2Params& P, c
             uint32_t m = f1 ? 0 : 1;
             bool nf = A.nofw[m], nr = A.norc[m];
             A.nofw[0] = nf; A.norc[0] = nr; A.nofw[1] = true; A.norc[1] = true;
-            A.minsc[0] = b.minsc[rr]; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
+            A.minsc[0] = f1 ? ms1 : ms2; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
             ht2_load_read(W->rd[0], b, rr, W->err);
             run = !W->err;
         }
@@ -428,13 +448,12 @@ struct ht2gpu_handle {
     cudaEvent_t    ev[4];
     std::string    err;
     // device batch buffers (grown on demand)
-    uint8_t *dSeq, *dQual, *dFilt; uint64_t* dOffs; uint32_t* dSeeds; int32_t* dMinsc;
+    uint8_t *dSeq, *dQual; uint64_t* dOffs; uint32_t* dSeeds;
     size_t capBases, capReads;
     // device output buffers
     ht2gpu_read_result_t* dReads; ht2gpu_aln_t* dAlns; ht2gpu_edit_t* dEdits; uint16_t* dPairs; unsigned int* dCounters;
     size_t capUnits, capAlns, capEdits, capPairs;
     // host staging for filters
-    std::vector<uint8_t> hFilt; std::vector<int32_t> hMinsc;
 };
 
 struct ResPriv {
@@ -512,7 +531,7 @@ static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
     ht2gpu_handle* h = new ht2gpu_handle();
     h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0;
     h->stream = 0;
-    h->dSeq = h->dQual = h->dFilt = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->dMinsc = NULL; h->capBases = h->capReads = 0;
+    h->dSeq = h->dQual = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->capBases = h->capReads = 0;
     h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL;
     h->capUnits = h->capAlns = h->capEdits = h->capPairs = 0;
     if (opt) h->opt = *opt; else ht2gpu_default_options(&h->opt);
@@ -611,7 +630,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     if (!h) return HT2GPU_OK;
     if (h->dBlob && h->ownBlob) cudaFree(h->dBlob);
     if (h->dWork) cudaFree(h->dWork);
-    cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dFilt); cudaFree(h->dOffs); cudaFree(h->dSeeds); cudaFree(h->dMinsc);
+    cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dOffs); cudaFree(h->dSeeds);
     cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters);
     if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
     delete h->img;
@@ -640,45 +659,27 @@ static cudaError_t growBuf(T*& p, size_t& cap, size_t need, size_t slackNum = 5,
     return e;
 }
 
-// Stage a batch: per-read filters (host arithmetic, hisat2.cpp:3387-3440) + H2D copies.
+// Stage a batch: H2D copies only (the per-read filters run on the device, ht2_dev_filter).
 static int uploadBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint64_t& h2dBytes)
 {
     const uint32_t n = b->n_reads;
     const uint64_t nb = b->offs[n];
-    h->hFilt.resize(n); h->hMinsc.resize(n);
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t len = (uint32_t)(b->offs[i + 1] - b->offs[i]);
-        int64_t minsc = ht2_minsc(len);
-        Ht2HostRead tmp; // only seq is inspected by the N filter
-        const uint8_t* s = b->seq + b->offs[i];
-        size_t maxns = (size_t)((double)2.0f + (double)0.1f * (double)len);
-        size_t ns = 0; bool nf = true;
-        for (uint32_t k = 0; k < len; k++) if (s[k] == 4) { if (++ns > maxns) { nf = false; break; } }
-        bool lenf = !(len <= 0 || len < 2);
-        bool scf = (0 >= minsc);
-        h->hFilt[i] = (nf && lenf && scf) ? 1 : 0;
-        h->hMinsc[i] = (int32_t)minsc;
-    }
     // sequence / quality / offsets / seeds share capBases / capReads growth
     {
         size_t c1 = h->capBases, c2 = h->capBases;
         CK(growBuf(h->dSeq, c1, nb));
         if (b->qual) { CK(growBuf(h->dQual, c2, nb)); }
         h->capBases = c1;
-        size_t r1 = h->capReads, r2 = h->capReads, r3 = h->capReads, r4 = h->capReads;
+        size_t r1 = h->capReads, r2 = h->capReads;
         CK(growBuf(h->dOffs, r1, (size_t)n + 1));
         CK(growBuf(h->dSeeds, r2, (size_t)n + 1));
-        CK(growBuf(h->dFilt, r3, (size_t)n + 1));
-        CK(growBuf(h->dMinsc, r4, (size_t)n + 1));
         h->capReads = r1;
     }
     CK(cudaMemcpyAsync(h->dSeq, b->seq, nb, cudaMemcpyHostToDevice, h->stream));
     if (b->qual) CK(cudaMemcpyAsync(h->dQual, b->qual, nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dOffs, b->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dSeeds, b->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->dFilt, h->hFilt.data(), n, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->dMinsc, h->hMinsc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    h2dBytes = nb * (b->qual ? 2 : 1) + ((size_t)n + 1) * 8 + (size_t)n * 9;
+    h2dBytes = nb * (b->qual ? 2 : 1) + ((size_t)n + 1) * 8 + (size_t)n * 4;
     return HT2GPU_OK;
 }
 
@@ -697,7 +698,7 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
 {
     DevBatch db;
     db.seq = h->dSeq; db.qual = b->qual ? h->dQual : NULL; db.offs = h->dOffs; db.seeds = h->dSeeds;
-    db.filt = h->dFilt; db.minsc = h->dMinsc; db.n_units = units; db.paired = b->paired;
+    db.n_units = units; db.paired = b->paired;
     DevOut o;
     o.reads = h->dReads; o.alns = h->dAlns; o.edits = h->dEdits; o.pairs = h->dPairs;
     o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;

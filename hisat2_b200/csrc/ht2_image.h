@@ -28,12 +28,23 @@
 #endif
 
 #define HT2_MAGIC 0x42325448u /* "HT2B" */
-#define HT2_IMAGE_VERSION 2u
+#define HT2_IMAGE_VERSION 3u
 
 // Local-index constants (hier_idx_common.h:23-41).
 #define HT2_LOCAL_INDEX_SIZE     57344u
 #define HT2_LOCAL_INDEX_OVERLAP  1024u
 #define HT2_LOCAL_INDEX_INTERVAL 56320u
+
+// Linear FM indexes (global and local) are NOT kept in the .ht2 side format
+// (48/56 B of BWT + 4 occ entries, 192/224 rows per side, a div/mod per LF
+// step).  The image re-lays them as 32-byte "rank sides", one DRAM sector each:
+//     [ 64 BW chars, 2 bit each = 16 B ][ u32 occ[4] ]
+// occ[c] = fchr[c] + #c in rows [0, sideStart), '$' not counted, so that
+// LF(row,c) = occ[c] + popcount(matches among the first row&63 chars) and the
+// side of a row is row>>6.  (ht2_index.cpp:relayLinear, ht2_fm.h:ht2_lf.)
+#define HT2_SIDE_SHIFT 6u
+#define HT2_SIDE_CHARS 64u
+#define HT2_SIDE_BYTES 32u
 
 // Geometry + array locations of one FM index (global: 32-bit entries,
 // local: 16-bit entries).  Mirrors GFMParams (gfm.h:115-299).
@@ -43,9 +54,9 @@ struct Ht2Gfm {
     uint32_t numNodes;     // # graph nodes (== gbwtLen for linear)
     uint32_t eftabLen;
     uint32_t linearFM;     // 1 iff len+1 == gbwtLen
-    uint32_t sideSz;       // bytes per side (64 linear / 128 graph)
-    uint32_t sideGbwtSz;   // BWT bytes per side
-    uint32_t sideGbwtLen;  // BW chars per side
+    uint32_t sideSz;       // bytes per side: 32 for linear indexes (re-laid "rank sides", see below), 128 graph
+    uint32_t sideGbwtSz;   // BWT bytes per side (16 linear)
+    uint32_t sideGbwtLen;  // BW chars per side (64 linear)
     uint32_t numSides;
     uint32_t offRate;
     uint32_t offMask;      // all-ones << offRate, truncated to entry width
@@ -62,7 +73,7 @@ struct Ht2Gfm {
     uint32_t tidx;
     uint32_t localOffset;
     uint32_t joinedOffset;
-    uint32_t pad0;
+    uint32_t zOff0;        // first (linear: only) row whose BW char is '$'
     // byte offsets from blob base
     uint64_t o_gfm;
     uint64_t o_ftab;

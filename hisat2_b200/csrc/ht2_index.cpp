@@ -98,6 +98,44 @@ void initGeom(Ht2Gfm& g, uint32_t len, uint32_t gbwtLen, uint32_t numNodes,
     g.ftabCmp = g.linearFM ? g.len : g.gbwtLen;
 }
 
+// Re-lay a linear BWT (.ht2 sides: sideGbwtSz bytes of 2-bit chars + 4 occ
+// entries, gfm.h:2952-2991) as 32-byte rank sides (ht2_image.h).  The occ
+// entries of the file are cross-checked against the recount on the way.
+void relayLinear(Blob& b, Ht2Gfm& g, const uint8_t* old, uint32_t z)
+{
+    const uint32_t eb = g.entryBytes;
+    const uint32_t oldSz = g.sideSz, oldBwtSz = g.sideGbwtSz, oldLen = g.sideGbwtLen;
+    const uint32_t nSides = (g.gbwtLen >> HT2_SIDE_SHIFT) + 1;   // a range end may equal gbwtLen
+    // one zeroed side of slack so 16-byte side loads of row gbwtLen+small stay inside the blob
+    g.o_gfm = b.alloc((size_t)(nSides + 1) * HT2_SIDE_BYTES, 128);
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    for (uint32_t row = 0; row <= g.gbwtLen; row++) {
+        if (row % oldLen == 0 && row < g.gbwtLen) {
+            const uint8_t* tr = old + (size_t)(row / oldLen) * oldSz + oldBwtSz;
+            for (int c = 0; c < 4; c++) {
+                uint32_t v;
+                if (eb == 4) memcpy(&v, tr + 4 * c, 4); else { uint16_t v16; memcpy(&v16, tr + 2 * c, 2); v = v16; }
+                if (v != cnt[c]) throw std::runtime_error("ht2: occ table of the index disagrees with its BWT");
+            }
+        }
+        if ((row & (HT2_SIDE_CHARS - 1)) == 0) {
+            uint32_t occ[4];
+            for (int c = 0; c < 4; c++) occ[c] = g.fchr[c] + cnt[c];
+            memcpy(&b.d[g.o_gfm + (size_t)(row >> HT2_SIDE_SHIFT) * HT2_SIDE_BYTES + 16], occ, 16);
+        }
+        if (row == g.gbwtLen) break;
+        const uint32_t co = row % oldLen;
+        const int c = (old[(size_t)(row / oldLen) * oldSz + (co >> 2)] >> ((co & 3) << 1)) & 3;
+        const uint32_t nco = row & (HT2_SIDE_CHARS - 1);
+        b.d[g.o_gfm + (size_t)(row >> HT2_SIDE_SHIFT) * HT2_SIDE_BYTES + (nco >> 2)] |= (uint8_t)(c << ((nco & 3) << 1));
+        if (row != z) cnt[c]++;
+    }
+    g.sideSz = HT2_SIDE_BYTES;
+    g.sideGbwtSz = 16;
+    g.sideGbwtLen = HT2_SIDE_CHARS;
+    g.numSides = nSides;
+}
+
 // Body shared by the global (.1) and local (.5) formats, after the header
 // ints: nPat plen[] nFrag rstarts[] gfm[] nzOffs zOffs[] fchr[5] ftab[] eftab[]
 void readBody(FileBuf& f, Blob& b, Ht2Gfm& g)
@@ -109,13 +147,22 @@ void readBody(FileBuf& f, Blob& b, Ht2Gfm& g)
     g.nFrag = rdIdx();
     g.o_rstarts = b.put(f.take((size_t)g.nFrag * 3 * eb), (size_t)g.nFrag * 3 * eb, 16);
     size_t tot = (size_t)g.numSides * g.sideSz;
-    g.o_gfm = b.put(f.take(tot), tot, 128);
-    // keep one zeroed side of slack after the BWT so 128-bit side loads of the
-    // last side and select scans that run off the end stay inside the blob
-    b.alloc(g.sideSz, 128);
+    const uint8_t* sides = f.take(tot);
     g.nzOffs = rdIdx();
-    g.o_zoffs = b.put(f.take((size_t)g.nzOffs * eb), (size_t)g.nzOffs * eb, 16);
+    const uint8_t* zp = f.take((size_t)g.nzOffs * eb);
+    g.o_zoffs = b.put(zp, (size_t)g.nzOffs * eb, 16);
+    g.zOff0 = 0xffffffffu;
+    if (g.nzOffs) { if (eb == 4) memcpy(&g.zOff0, zp, 4); else { uint16_t v; memcpy(&v, zp, 2); g.zOff0 = v; } }
     for (int i = 0; i < 5; i++) g.fchr[i] = rdIdx();
+    if (g.linearFM) {
+        if (g.nzOffs != 1) throw std::runtime_error("ht2: linear index with other than one '$' row");
+        relayLinear(b, g, sides, g.zOff0);
+    } else {
+        g.o_gfm = b.put(sides, tot, 128);
+        // keep one zeroed side of slack after the BWT so 128-bit side loads of the
+        // last side and select scans that run off the end stay inside the blob
+        b.alloc(g.sideSz, 128);
+    }
     g.o_ftab = b.put(f.take((size_t)g.ftabLen * eb), (size_t)g.ftabLen * eb, 16);
     g.o_eftab = b.put(f.take((size_t)g.eftabLen * eb), (size_t)g.eftabLen * eb, 16);
 }

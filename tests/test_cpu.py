@@ -55,14 +55,38 @@ def test_image_build_is_host_only_and_consistent(lib):
     img = api.Index.build_image(os.path.join(GOLDEN, "tiny"))
     assert img[:4].tobytes() == b"HT2B"
     hdr = np.frombuffer(img[:16].tobytes(), dtype="<u4")
-    assert hdr[1] == 2  # image version
+    assert hdr[1] == 3  # image version
     total = int(np.frombuffer(img[8:16].tobytes(), dtype="<u8")[0])
     assert total == img.nbytes and total % 128 == 0
     # global geometry (Ht2Gfm at offset 16): len, gbwtLen, numNodes, eftabLen, linearFM, sideSz, sideGbwtSz, sideGbwtLen
     g = np.frombuffer(img[16:16 + 32].tobytes(), dtype="<u4")
     raw = np.fromfile(os.path.join(GOLDEN, "tiny.1.ht2"), dtype="<u4", count=11)
     assert g[0] == raw[2] and g[1] == raw[3]
-    assert g[4] == 1 and g[5] == 64 and g[6] == 48 and g[7] == 192
+    # linear indexes are re-laid as 32-byte rank sides of 64 rows (ht2_image.h)
+    assert g[4] == 1 and g[5] == 32 and g[6] == 16 and g[7] == 64
+    # the rank sides must restate the .ht2 file: same BW string, occ = fchr + running counts without '$'
+    gbwt_len = int(g[1])
+    geom = np.frombuffer(img[16:16 + 136].tobytes(), dtype="<u4")
+    fchr, z0 = geom[18:23], int(geom[27])
+    o_gfm = int(np.frombuffer(img[16 + 112:16 + 120].tobytes(), dtype="<u8")[0])
+    f = open(os.path.join(GOLDEN, "tiny.1.ht2"), "rb").read()
+    npat = int(np.frombuffer(f[44:48], "<u4")[0])
+    pos = 48 + 4 * npat
+    nfrag = int(np.frombuffer(f[pos:pos + 4], "<u4")[0])
+    pos += 4 + 12 * nfrag
+    nsides_old = (gbwt_len // 4 + 1 + 47) // 48
+    old = np.frombuffer(f[pos:pos + 64 * nsides_old], np.uint8).reshape(-1, 64)
+    bw_old = ((old[:, :48, None] >> np.array([0, 2, 4, 6])) & 3).reshape(-1)[:gbwt_len]
+    nsides = (gbwt_len >> 6) + 1
+    new = np.frombuffer(img[o_gfm:o_gfm + 32 * nsides].tobytes(), np.uint8).reshape(-1, 32)
+    bw_new = ((new[:, :16, None] >> np.array([0, 2, 4, 6])) & 3).reshape(-1)[:gbwt_len]
+    assert (bw_old == bw_new).all()
+    occ = new[:, 16:].copy().view("<u4")
+    onehot = (bw_new[:, None] == np.arange(4)).astype(np.int64)
+    onehot[z0] = 0
+    cum = np.vstack([np.zeros((1, 4), np.int64), np.cumsum(onehot, axis=0)])
+    want = cum[np.minimum(np.arange(nsides) * 64, gbwt_len)] + fchr[:4].astype(np.int64)
+    assert (occ.astype(np.int64) == want).all()
     with pytest.raises(api.Ht2GpuError):
         api.Index.build_image(os.path.join(GOLDEN, "does_not_exist"))
 

@@ -5,7 +5,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hisat2_b200 as h2
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 fa = sys.argv[1]
-batch = h2.ReadBatch.from_fasta(fa)
+if fa.startswith("synth:"):          # bench.py's synthetic workload, e.g. synth:1000000
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    n = int(fa.split(":")[1])
+    _, codes = bench.gen_reads(n, seed=1)
+    names = [b"r%d" % i for i in range(n)]
+    batch = h2.ReadBatch(codes.reshape(-1), np.arange(0, (n + 1) * 101, 101, dtype=np.uint64), bench.seeds_for(codes, names), names)
+else:
+    batch = h2.ReadBatch.from_fasta(fa)
 ref = None
 for cfg in sys.argv[2:]:
     opts = {k: int(v) for k, v in (kv.split("=") for kv in cfg.split(","))}
