@@ -38,6 +38,7 @@ struct DevOut {
     uint16_t*             pairs;
     uint32_t              capAlns, capEdits, capPairs;
     unsigned int*         counters; // [0] alns, [1] edits, [2] pairs
+    unsigned long long*   stats;    // optional (HT2GPU_STATS=1): per state code [rounds, lanes, cycles, max cycles]
 };
 
 __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, uint32_t ri, uint32_t& err)
@@ -307,6 +308,7 @@ ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch
         }
         __syncwarp();
         const uint32_t nsel = taken < 32 ? taken : 32;
+        const long long t0 = o.stats ? clock64() : 0;
         // ---- run one segment on each selected slot
         if (lane < nsel) {
             const uint32_t slot = sel[lane];
@@ -333,6 +335,16 @@ ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch
             code[slot] = (uint8_t)nc;
         }
         __syncwarp();
+        if (o.stats && lane == 0) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t0);
+            atomicAdd(&o.stats[target * 4 + 0], 1ull);
+            atomicAdd(&o.stats[target * 4 + 1], (unsigned long long)nsel);
+            atomicAdd(&o.stats[target * 4 + 2], dt);
+            atomicMax(&o.stats[target * 4 + 3], dt);
+            const uint32_t bk = nsel >= 32 ? 5 : (nsel >= 16 ? 4 : (nsel >= 8 ? 3 : (nsel >= 4 ? 2 : (nsel >= 2 ? 1 : 0))));
+            atomicAdd(&o.stats[1024 + (target * 6 + bk) * 2 + 0], 1ull);
+            atomicAdd(&o.stats[1024 + (target * 6 + bk) * 2 + 1], dt);
+        }
     }
 }
 
@@ -453,6 +465,7 @@ struct ht2gpu_handle {
     // device output buffers
     ht2gpu_read_result_t* dReads; ht2gpu_aln_t* dAlns; ht2gpu_edit_t* dEdits; uint16_t* dPairs; unsigned int* dCounters;
     size_t capUnits, capAlns, capEdits, capPairs;
+    unsigned long long* dStats;   // HT2GPU_STATS=1: per-state round statistics of the regroup kernel
     // host staging for filters
 };
 
@@ -532,7 +545,7 @@ static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
     h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0;
     h->stream = 0;
     h->dSeq = h->dQual = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->capBases = h->capReads = 0;
-    h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL;
+    h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL; h->dStats = NULL;
     h->capUnits = h->capAlns = h->capEdits = h->capPairs = 0;
     if (opt) h->opt = *opt; else ht2gpu_default_options(&h->opt);
     h->device = h->opt.device;
@@ -631,7 +644,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     if (h->dBlob && h->ownBlob) cudaFree(h->dBlob);
     if (h->dWork) cudaFree(h->dWork);
     cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dOffs); cudaFree(h->dSeeds);
-    cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters);
+    cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters); cudaFree(h->dStats);
     if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
     delete h->img;
     delete h;
@@ -691,6 +704,10 @@ static int ensureOut(ht2gpu_handle* h, uint32_t units, size_t alns, size_t edits
     size_t pc = h->capPairs * 2, need = pairs * 2;
     if (need > pc || !h->dPairs) { CK(growBuf(h->dPairs, pc, need)); h->capPairs = pc / 2; }
     if (!h->dCounters) CK(cudaMalloc(&h->dCounters, 4 * sizeof(unsigned int)));
+    if (!h->dStats && getenv("HT2GPU_STATS")) {
+        CK(cudaMalloc(&h->dStats, (1024 + 256 * 12) * sizeof(unsigned long long)));
+        CK(cudaMemset(h->dStats, 0, (1024 + 256 * 12) * sizeof(unsigned long long)));
+    }
     return HT2GPU_OK;
 }
 
@@ -703,6 +720,7 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
     o.reads = h->dReads; o.alns = h->dAlns; o.edits = h->dEdits; o.pairs = h->dPairs;
     o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
     o.counters = h->dCounters;
+    o.stats = h->dStats;
     CK(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned int), h->stream));
     if (h->regroup) {
         uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
@@ -734,6 +752,39 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
     return HT2GPU_OK;
 }
 
+// HT2GPU_STATS=1: per-state statistics of the regroup kernel's rounds (investigation aid).
+static void dumpStats(ht2gpu_handle* h)
+{
+    static const char* topN[] = {"START", "NEXTBWT", "PS", "ALIGN", "HYB_EXTEND", "HYB_PICK", "HYB_RET", "POST_ALIGN", "AFTER_LOOP",
+                                 "MATE_NEXT", "MATE_SEARCH", "MATE_ANCHOR", "MATE_RET", "MATE_DONE", "DONE"};
+    static const char* frN[] = {"ENTER", "L_START", "L_WHILE", "L_COORD", "L_COORD_RET", "L_WHILE_TAIL", "L_STASH", "L_STASH_RET",
+                                "L_AFTER_WHILE", "L_GCOORD", "L_GCOORD_RET", "L_TRIM", "L_TRIM_RET", "L_EXT", "R_START", "R_WHILE",
+                                "R_COORD", "R_COORD_RET", "R_WHILE_TAIL", "R_STASH", "R_STASH_RET", "R_AFTER_WHILE", "R_GCOORD",
+                                "R_GCOORD_RET", "R_TRIM", "R_TRIM_RET", "R_EXT", "FINAL_RET", "RETURN"};
+    std::vector<unsigned long long> st(1024 + 256 * 12);
+    if (cudaMemcpy(st.data(), h->dStats, st.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    cudaMemset(h->dStats, 0, st.size() * 8);
+    unsigned long long totC = 0;
+    for (int c = 0; c < 256; c++) totC += st[c * 4 + 2];
+    fprintf(stderr, "%-16s %10s %7s %10s %9s %6s\n", "state", "rounds", "lanes", "cyc/round", "max cyc", "time%");
+    for (int c = 0; c < 256; c++) {
+        if (!st[c * 4]) continue;
+        char nm[32];
+        if (c == 0) snprintf(nm, sizeof nm, "NEED");
+        else if (c == 1) snprintf(nm, sizeof nm, "FINISH");
+        else if (c < 20) snprintf(nm, sizeof nm, "T_%s", c - 2 < 15 ? topN[c - 2] : "?");
+        else snprintf(nm, sizeof nm, "F_%s", c - 20 < 29 ? frN[c - 20] : "?");
+        fprintf(stderr, "%-16s %10llu %7.2f %10.0f %9llu %6.2f |", nm, st[c * 4], (double)st[c * 4 + 1] / st[c * 4],
+                (double)st[c * 4 + 2] / st[c * 4], st[c * 4 + 3], 100.0 * st[c * 4 + 2] / (totC ? totC : 1));
+        // cycles per round by group size: 1, 2-3, 4-7, 8-15, 16-31, 32 lanes
+        for (int bk = 0; bk < 6; bk++) {
+            unsigned long long n = st[1024 + (c * 6 + bk) * 2], cy = st[1024 + (c * 6 + bk) * 2 + 1];
+            fprintf(stderr, " %6.0f(%llu)", n ? (double)cy / n / 1000.0 : 0.0, n);
+        }
+        fprintf(stderr, "\n");
+    }
+}
+
 static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, ht2gpu_result_batch_t* res, bool timeCopies)
 {
     if (!h || !b || !res) return HT2GPU_ERR_ARG;
@@ -763,6 +814,7 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
         // result pools were too small: grow and re-run (results are deterministic)
         capA = counters[0] + 1024; capE = counters[1] + 4096; capP = counters[2] + 1024;
     }
+    if (h->dStats) dumpStats(h);
     ResPriv* pv = new ResPriv();
     pv->reads.resize(units); pv->alns.resize(counters[0]); pv->edits.resize(counters[1]); pv->pairs.resize((size_t)counters[2] * 2);
     CK(cudaMemcpyAsync(pv->reads.data(), h->dReads, (size_t)units * sizeof(ht2gpu_read_result_t), cudaMemcpyDeviceToHost, h->stream));
