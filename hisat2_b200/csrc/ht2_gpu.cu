@@ -440,6 +440,136 @@ ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, De
 }
 
 // ---------------------------------------------------------------------------
+// ht2_align_pool_kernel: block-shared slot pool, warp-independent rounds.
+//
+// The NW warps of a block share one pool of NW*32*K read slots whose state
+// codes live in shared memory.  Every warp runs its own rounds -- claim up to
+// 32 slots that are in the block's current target state (one
+// warp at a time, under a block lock held for the few hundred cycles of the
+// gather), run one segment of each, publish the new state codes -- and never
+// waits for another warp's segments.  The target state is a block-wide hint: warps stay
+// on it while it has plenty of claimable slots and otherwise re-elect the most
+// populous state from per-state counters, so the warps of an SM execute the
+// same code most of the time (instruction fetch is the scarce resource: the
+// 32 KB L1.5 I-cache and the GPC instruction cache saturate when every warp
+// walks different code) while groups are drawn from a pool large enough to
+// fill all 32 lanes.
+// ---------------------------------------------------------------------------
+#define RG_BUSY 254u
+#define PL_MIN_GROUP 16
+
+template <int NW, int K>
+__global__ void __launch_bounds__(32 * NW)
+ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+{
+    constexpr int S = NW * 32 * K;      // slots of this block
+    constexpr int NJ = S / 32;          // slots a lane may claim: lane + 32*j
+    __shared__ unsigned int sCode[S];
+    __shared__ int sCount[RG_BINS];     // claimable slots per state code
+    __shared__ unsigned int sTarget;
+    __shared__ int sExit, sLock;
+    __shared__ uint16_t sSel[NW][32];
+    const uint32_t t = threadIdx.x, lane = t & 31, wib = t >> 5;
+    Ht2Work* base = work + (size_t)blockIdx.x * S;
+    for (int i = t; i < S; i += 32 * NW) sCode[i] = RG_NEED;
+    if (t < RG_BINS) sCount[t] = (t == RG_NEED) ? S : 0;
+    if (t == 0) { sTarget = RG_NEED; sExit = 0; sLock = 0; }
+    Ht2Aligner A;
+    A.bind(blob, &P, base);
+    __syncthreads();
+    volatile unsigned int* vCode = sCode;
+    volatile int* vCount = sCount;
+    uint16_t* sel = sSel[wib];
+    uint32_t round = wib * 5;
+    for (;;) {
+        // ---- one warp at a time forms a group (whole groups, not fragments shared between warps)
+        if (lane == 0) { while (atomicCAS(&sLock, 0, 1) != 0) __nanosleep(64); }
+        __syncwarp();
+        // every decision below is made warp-uniform (the counters change under our feet)
+        uint32_t T = __shfl_sync(0xffffffffu, *(volatile unsigned int*)&sTarget, 0);
+        const int cT = __shfl_sync(0xffffffffu, vCount[T], 0);
+        if (cT < 32) {
+            // elect the most populous claimable state
+            int c0 = vCount[lane], c1 = vCount[lane + 32];
+            if (c0 < 0) c0 = 0;
+            if (c1 < 0) c1 = 0;
+            uint32_t best = c0 >= c1 ? (((uint32_t)c0 << 8) | lane) : (((uint32_t)c1 << 8) | (lane + 32));
+            for (int off = 16; off > 0; off >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best, off); best = v > best ? v : best; }
+            if ((best >> 8) == 0) {
+                const bool done = __shfl_sync(0xffffffffu, *(volatile int*)&sExit >= S ? 1 : 0, 0) != 0;   // every slot has drained
+                __syncwarp();
+                if (lane == 0) atomicExch(&sLock, 0);
+                if (done) break;
+                __nanosleep(400);                                 // the rest is being run by other warps
+                continue;
+            }
+            T = best & 0xff;
+            if (lane == 0) *(volatile unsigned int*)&sTarget = T;
+        }
+        // ---- gather up to 32 slots in state T
+        uint32_t taken = 0;
+        {
+            uint32_t j = round % NJ;
+            for (int jj = 0; jj < NJ && taken < 32; jj++) {
+                const uint32_t idx = lane + 32 * j;
+                const bool m = vCode[idx] == T;
+                const uint32_t mask = __ballot_sync(0xffffffffu, m);
+                const uint32_t rank = taken + __popc(mask & ((1u << lane) - 1));
+                if (m && rank < 32) { sel[rank] = (uint16_t)idx; vCode[idx] = RG_BUSY; }
+                taken += __popc(mask);
+                j = (j + 1 == NJ) ? 0 : j + 1;
+            }
+        }
+        round++;
+        const uint32_t nsel = taken < 32 ? taken : 32;
+        if (lane == 0 && nsel) atomicSub(&sCount[T], (int)nsel);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicExch(&sLock, 0);
+        if (nsel == 0) continue;
+        const int my = lane < nsel ? (int)sel[lane] : -1;
+        __threadfence_block();   // acquire: the previous owner's workspace writes
+        const long long t0 = o.stats ? clock64() : 0;
+        if (my >= 0) {
+            Ht2Work* W = base + my;
+            uint32_t nc;
+            if (T == RG_NEED) {
+                uint32_t u = atomicAdd(&o.counters[3], 1u);
+                if (u >= b.n_units) nc = RG_EXIT;
+                else {
+                    A.W = W;
+                    uint32_t filtBits;
+                    bool run = ht2_setup_unit(A, P, b, u, filtBits);
+                    if (run) { while (!A.machineAtHeavyState()) A.machineStep(); }
+                    nc = run ? rg_code(W) : RG_FINISH;
+                }
+            } else if (T == RG_FINISH) {
+                ht2_finish_unit<1>(W, o, W->unit, W->filtBits, 0);
+                nc = RG_NEED;
+            } else {
+                A.attach(W);
+                A.machineRun();
+                nc = rg_code(W);
+            }
+            __threadfence_block();   // release
+            if (nc == RG_EXIT) { vCode[my] = RG_EXIT; atomicAdd(&sExit, 1); }
+            else { atomicExch(&sCode[my], nc); atomicAdd(&sCount[nc], 1); }
+        }
+        __syncwarp();
+        if (o.stats && lane == 0) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t0);
+            atomicAdd(&o.stats[T * 4 + 0], 1ull);
+            atomicAdd(&o.stats[T * 4 + 1], (unsigned long long)nsel);
+            atomicAdd(&o.stats[T * 4 + 2], dt);
+            atomicMax(&o.stats[T * 4 + 3], dt);
+            const uint32_t bk = nsel >= 32 ? 5 : (nsel >= 16 ? 4 : (nsel >= 8 ? 3 : (nsel >= 4 ? 2 : (nsel >= 2 ? 1 : 0))));
+            atomicAdd(&o.stats[1024 + (T * 6 + bk) * 2 + 0], 1ull);
+            atomicAdd(&o.stats[1024 + (T * 6 + bk) * 2 + 1], dt);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct ht2gpu_handle {
@@ -452,7 +582,8 @@ struct ht2gpu_handle {
     int            device;
     int            nSM;
     int            tpb, bpsm, lanes;
-    bool           regroup, blockRegroup;
+    bool           regroup, blockRegroup, pool;
+    int            poolWarps;
     int            rgK;
     Ht2Work*       dWork;
     size_t         nWork;
@@ -519,7 +650,8 @@ static int finishOpen(ht2gpu_handle* h)
     h->regroup = (h->opt.warp_per_read == 2 || h->opt.warp_per_read == 0);
     if (h->opt.warp_per_read == 3) h->regroup = false; // 3 = plain one-lane-per-read dispatcher
     h->blockRegroup = (h->opt.warp_per_read == 4);
-    if (h->blockRegroup) h->regroup = true;
+    h->pool = (h->opt.warp_per_read == 5);
+    if (h->blockRegroup || h->pool) h->regroup = true;
     if (h->regroup) {
         h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 32 * RG_WARPS;
         if (h->tpb > 32 * RG_WARPS) h->tpb = 32 * RG_WARPS;
@@ -528,6 +660,12 @@ static int finishOpen(ht2gpu_handle* h)
         h->rgK = h->opt.slots_per_lane > 0 ? h->opt.slots_per_lane : 4;
         if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8 && h->rgK != 16) h->rgK = 4;
         if (h->blockRegroup) h->tpb = 32 * BRG_WARPS;
+        if (h->pool) {
+            h->poolWarps = (h->opt.threads_per_block >= 512) ? 16 : 8;
+            h->tpb = 32 * h->poolWarps;
+            if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8) h->rgK = 4;
+            if (h->opt.blocks_per_sm <= 0) h->bpsm = 2;
+        }
         h->nWork = (size_t)h->nSM * h->bpsm * (h->tpb / 32) * 32 * h->rgK;
     } else
     h->nWork = (size_t)h->nSM * h->bpsm * h->tpb / h->lanes;
@@ -724,6 +862,18 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
     CK(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned int), h->stream));
     if (h->regroup) {
         uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
+        if (h->pool) {
+            const int key = h->poolWarps * 100 + h->rgK;
+            switch (key) {
+                case 802:  ht2_align_pool_kernel<8, 2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 808:  ht2_align_pool_kernel<8, 8><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 1602: ht2_align_pool_kernel<16, 2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 1604: ht2_align_pool_kernel<16, 4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                default:   ht2_align_pool_kernel<8, 4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            }
+            CK(cudaGetLastError());
+            return HT2GPU_OK;
+        }
         if (h->blockRegroup) {
             switch (h->rgK) {
                 case 2:  ht2_align_block_regroup_kernel<2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
