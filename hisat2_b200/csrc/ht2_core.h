@@ -481,25 +481,14 @@ struct Ht2Aligner {
     // (partialSearch inner step, hi_aligner.h:6466-6484; mapLF gfm.h:3739,
     // mapGLF1 gfm.h:3957, mapLF1 gfm.h:3889).  Linear indexes only here;
     // graph indexes are dispatched in lfStepGraph.
+    // nlf / bytes accumulate the work counters in registers (written back once per search).
     template <typename IT>
-    HT2_NI void lfStep(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c,
-                       uint32_t& ntop, uint32_t& nbot, uint32_t& nntop, uint32_t& nnbot) {
-        if (bot - top != 1) {
-            W->nLF += 2;
-            W->algBytes += ((top >> HT2_SIDE_SHIFT) == (bot >> HT2_SIDE_SHIFT) ? 1u : 2u) * HT2_SIDE_BYTES;
-            ntop = ht2_lf(fm, top, c);
-            nbot = ht2_lf(fm, bot, c);
-            nntop = ntop; nnbot = nbot;
-        } else {
-            W->nLF += 1;
-            W->algBytes += HT2_SIDE_BYTES;
-            int own;
-            uint32_t r = ht2_lf_own(fm, top, own);
-            if (own != c || ht2_is_zoff(fm, top)) { ntop = nbot = nntop = nnbot = 0; return; }
-            ntop = r;
-            nbot = (uint32_t)(IT)(ntop + 1);
-            nntop = ntop; nnbot = nbot;
-        }
+    HT2_HD void lfStep(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c,
+                       uint32_t& ntop, uint32_t& nbot, uint32_t& nlf, uint32_t& bytes) {
+        const bool one = (bot - top == 1);
+        nlf += one ? 1u : 2u;
+        bytes += (one || (top >> HT2_SIDE_SHIFT) == (bot >> HT2_SIDE_SHIFT)) ? HT2_SIDE_BYTES : 2u * HT2_SIDE_BYTES;
+        ht2_lf2(fm, top, bot, c, ntop, nbot);
     }
 
     // HI_Aligner::partialSearch (hi_aligner.h:6361-6600).  Returns stop
@@ -547,12 +536,14 @@ struct Ht2Aligner {
         }
         uint32_t same_range = 0, similar_range = 0;
         uint32_t khits5 = P->khits < 5 ? P->khits : 5;
+        uint32_t nlf = 0, lfBytes = 0;
         // node_range starts as (0,0) in the reference (hi_aligner.h:6396)
         while (dep < len) {
             int c = seq[len - dep - 1];
-            uint32_t ttop = 0, tbot = 0, tntop = 0, tnbot = 0;
-            if (c <= 3) lfStep(gfm, top, bot, c, ttop, tbot, tntop, tnbot);
+            uint32_t ttop = 0, tbot = 0;
+            if (c <= 3) lfStep(gfm, top, bot, c, ttop, tbot, nlf, lfBytes);
             if (ttop >= tbot) break;
+            const uint32_t tntop = ttop, tnbot = tbot;   // linear index: node range == row range
             uint32_t nw = tnbot - tntop, ow = nbot - ntop;
             if (pseudogeneStop_) {
                 if (nw < ow && ow <= khits5) {
@@ -584,6 +575,7 @@ struct Ht2Aligner {
                 }
             }
         }
+        W->nLF += nlf; W->algBytes += lfBytes;
         if (top < bot) {
             uint8_t hit_type = HT2_CANDIDATE_HIT;
             if (anchorStop) hit_type = HT2_ANCHOR_HIT;
@@ -627,18 +619,20 @@ struct Ht2Aligner {
         W->algBytes += 2 * (uint32_t)sizeof(IT);
         dep += ftabLen;
         if (rtop >= rbot) { hitlen = ftabLen; return 0; }
+        uint32_t nlf = 0, lfBytes = 0;
         while (dep < len) {
             int c = seq[len - dep - 1];
-            uint32_t ttop = 0, tbot = 0, tntop = 0, tnbot = 0;
-            if (c <= 3) lfStep(fm, rtop, rbot, c, ttop, tbot, tntop, tnbot);
+            uint32_t ttop = 0, tbot = 0;
+            if (c <= 3) lfStep(fm, rtop, rbot, c, ttop, tbot, nlf, lfBytes);
             if (ttop >= tbot) break;
-            rtop = ttop; rbot = tbot; ntop = tntop; nbot = tnbot;
+            rtop = ttop; rbot = tbot; ntop = ttop; nbot = tbot;
             dep++;
             if (uniqueStop_) {
                 if (rbot - rtop == 1 && dep - offset >= minUniqueLen) { uniqueStop = true; break; }
             }
             if (local && dep - offset >= maxHitLen) break;
         }
+        W->nLF += nlf; W->algBytes += lfBytes;
         uint32_t nelt = 0;
         if (ntop < nbot && nbot - ntop <= maxHits) {
             top = rtop; bot = rbot; node_top = ntop; node_bot = nbot;

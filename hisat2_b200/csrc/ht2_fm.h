@@ -128,6 +128,30 @@ HT2_HD uint32_t ht2_lf(const Ht2Fm<IT>& fm, uint32_t row, int c) {
     const Ht2SideBwt w = *(const Ht2SideBwt*)side;
     return ht2_lf_side(fm, side, w, row, c);
 }
+// Both boundaries of a range at once: the two side loads are issued together
+// (one L2 round trip instead of two dependent ones) and the result is the plain
+// two-boundary formula also for one-row ranges -- LF(top+1,c) - LF(top,c) is 1
+// exactly when the row holds c (and is not '$'), which is what mapLF1's
+// rowL test computes (gfm.h:3889-3911) -- so all lanes run the same code.
+template <typename IT>
+HT2_HD void ht2_lf2(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c, uint32_t& ntop, uint32_t& nbot) {
+    const uint8_t* st = ht2_side(fm, top);
+    const uint8_t* sb = ht2_side(fm, bot);
+    const Ht2SideBwt wt = *(const Ht2SideBwt*)st;
+    const Ht2SideBwt wb = *(const Ht2SideBwt*)sb;
+    const uint32_t ot = ((const uint32_t*)(st + 16))[c];
+    const uint32_t ob = ((const uint32_t*)(sb + 16))[c];
+    const uint32_t ct = top & (HT2_SIDE_CHARS - 1), cb = bot & (HT2_SIDE_CHARS - 1);
+    uint32_t nt = ot + ht2_count_side(wt, c, ct);
+    uint32_t nb = ob + ht2_count_side(wb, c, cb);
+    if (c == 0) {
+        nt -= ((uint32_t)(fm.z0 - (top - ct)) < ct) ? 1u : 0u;
+        nb -= ((uint32_t)(fm.z0 - (bot - cb)) < cb) ? 1u : 0u;
+    }
+    ntop = (uint32_t)(IT)nt;
+    nbot = (uint32_t)(IT)nb;
+}
+
 // c = rowL(row); returns LF(row, c)  (one side load; GFM::mapLF1 gfm.h:3889-3911).
 template <typename IT>
 HT2_HD uint32_t ht2_lf_own(const Ht2Fm<IT>& fm, uint32_t row, int& c) {

@@ -647,10 +647,10 @@ static int finishOpen(ht2gpu_handle* h)
     if (h->tpb > 128) h->tpb = 128;
     h->bpsm = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 4;
     h->lanes = h->opt.warp_per_read == 1 ? 32 : 1;
-    h->regroup = (h->opt.warp_per_read == 2 || h->opt.warp_per_read == 0);
+    h->regroup = (h->opt.warp_per_read == 2);
     if (h->opt.warp_per_read == 3) h->regroup = false; // 3 = plain one-lane-per-read dispatcher
     h->blockRegroup = (h->opt.warp_per_read == 4);
-    h->pool = (h->opt.warp_per_read == 5);
+    h->pool = (h->opt.warp_per_read == 5 || h->opt.warp_per_read == 0);   // default
     if (h->blockRegroup || h->pool) h->regroup = true;
     if (h->regroup) {
         h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 32 * RG_WARPS;
@@ -664,7 +664,7 @@ static int finishOpen(ht2gpu_handle* h)
             h->poolWarps = (h->opt.threads_per_block >= 512) ? 16 : 8;
             h->tpb = 32 * h->poolWarps;
             if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8) h->rgK = 4;
-            if (h->opt.blocks_per_sm <= 0) h->bpsm = 2;
+            if (h->opt.blocks_per_sm <= 0) h->bpsm = 1;
         }
         h->nWork = (size_t)h->nSM * h->bpsm * (h->tpb / 32) * 32 * h->rgK;
     } else

@@ -59,7 +59,7 @@ typedef struct {
     int32_t  threads_per_block;      /* 0 = default */
     int32_t  blocks_per_sm;          /* 0 = default */
     int32_t  slots_per_lane;         /* state-regrouping mode: read slots per lane (2,4,8,16); 0 = default */
-    int32_t  warp_per_read;          /* execution mode: 0/2 = state-regrouping (default), 1 = one warp per read, 3 = one lane per read */
+    int32_t  warp_per_read;          /* execution mode: 0/5 = block-shared slot pool (default), 2 = per-warp state regrouping, 4 = block-synchronous regrouping, 1 = one warp per read, 3 = one lane per read */
 } ht2gpu_options_t;
 
 /* A batch of reads, structure-of-arrays, host memory.  Read i occupies
