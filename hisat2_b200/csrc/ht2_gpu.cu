@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -600,12 +601,43 @@ struct ht2gpu_handle {
     // host staging for filters
 };
 
+// Results live in ONE pinned host buffer per batch (D2H at PCIe speed instead of
+// the pageable-copy path); freed buffers are cached process-wide because
+// cudaHostAlloc costs milliseconds per hundred MB.
 struct ResPriv {
-    std::vector<ht2gpu_read_result_t> reads;
-    std::vector<ht2gpu_aln_t> alns;
-    std::vector<ht2gpu_edit_t> edits;
-    std::vector<uint16_t> pairs;
+    void*  buf;
+    size_t cap;
 };
+static std::mutex gPinMu;
+static std::vector<ResPriv> gPinFree;
+
+static bool pinnedGet(size_t need, ResPriv& out)
+{
+    {
+        std::lock_guard<std::mutex> lk(gPinMu);
+        int best = -1;
+        for (size_t i = 0; i < gPinFree.size(); i++)
+            if (gPinFree[i].cap >= need && (best < 0 || gPinFree[i].cap < gPinFree[best].cap)) best = (int)i;
+        if (best >= 0) { out = gPinFree[best]; gPinFree.erase(gPinFree.begin() + best); return true; }
+    }
+    size_t cap = need + need / 4 + 4096;
+    void* p = NULL;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return false;
+    out.buf = p; out.cap = cap;
+    return true;
+}
+static void pinnedPut(const ResPriv& r)
+{
+    std::lock_guard<std::mutex> lk(gPinMu);
+    if (gPinFree.size() >= 4) {     // keep the largest few
+        size_t mi = 0;
+        for (size_t i = 1; i < gPinFree.size(); i++) if (gPinFree[i].cap < gPinFree[mi].cap) mi = i;
+        if (gPinFree[mi].cap < r.cap) { cudaFreeHost(gPinFree[mi].buf); gPinFree[mi] = r; }
+        else cudaFreeHost(r.buf);
+        return;
+    }
+    gPinFree.push_back(r);
+}
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return HT2GPU_ERR_CUDA; } } while (0)
 
@@ -965,21 +997,29 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
         capA = counters[0] + 1024; capE = counters[1] + 4096; capP = counters[2] + 1024;
     }
     if (h->dStats) dumpStats(h);
+    auto up = [](size_t v) { return (v + 63) & ~(size_t)63; };
+    const size_t szR = up((size_t)units * sizeof(ht2gpu_read_result_t)), szA = up((size_t)counters[0] * sizeof(ht2gpu_aln_t)),
+                 szE = up((size_t)counters[1] * sizeof(ht2gpu_edit_t)), szP = up((size_t)counters[2] * 4);
     ResPriv* pv = new ResPriv();
-    pv->reads.resize(units); pv->alns.resize(counters[0]); pv->edits.resize(counters[1]); pv->pairs.resize((size_t)counters[2] * 2);
-    CK(cudaMemcpyAsync(pv->reads.data(), h->dReads, (size_t)units * sizeof(ht2gpu_read_result_t), cudaMemcpyDeviceToHost, h->stream));
-    if (counters[0]) CK(cudaMemcpyAsync(pv->alns.data(), h->dAlns, (size_t)counters[0] * sizeof(ht2gpu_aln_t), cudaMemcpyDeviceToHost, h->stream));
-    if (counters[1]) CK(cudaMemcpyAsync(pv->edits.data(), h->dEdits, (size_t)counters[1] * sizeof(ht2gpu_edit_t), cudaMemcpyDeviceToHost, h->stream));
-    if (counters[2]) CK(cudaMemcpyAsync(pv->pairs.data(), h->dPairs, (size_t)counters[2] * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (!pinnedGet(szR + szA + szE + szP + 64, *pv)) { delete pv; h->err = "cudaHostAlloc failed for the result batch"; return HT2GPU_ERR_CUDA; }
+    uint8_t* hb = (uint8_t*)pv->buf;
+    ht2gpu_read_result_t* hReads = (ht2gpu_read_result_t*)hb;
+    ht2gpu_aln_t* hAlns = (ht2gpu_aln_t*)(hb + szR);
+    ht2gpu_edit_t* hEdits = (ht2gpu_edit_t*)(hb + szR + szA);
+    uint16_t* hPairs = (uint16_t*)(hb + szR + szA + szE);
+    CK(cudaMemcpyAsync(hReads, h->dReads, (size_t)units * sizeof(ht2gpu_read_result_t), cudaMemcpyDeviceToHost, h->stream));
+    if (counters[0]) CK(cudaMemcpyAsync(hAlns, h->dAlns, (size_t)counters[0] * sizeof(ht2gpu_aln_t), cudaMemcpyDeviceToHost, h->stream));
+    if (counters[1]) CK(cudaMemcpyAsync(hEdits, h->dEdits, (size_t)counters[1] * sizeof(ht2gpu_edit_t), cudaMemcpyDeviceToHost, h->stream));
+    if (counters[2]) CK(cudaMemcpyAsync(hPairs, h->dPairs, (size_t)counters[2] * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     float msH2d = 0, msD2h = 0;
     CK(cudaEventElapsedTime(&msH2d, h->ev[0], h->ev[1]));
     CK(cudaEventElapsedTime(&msD2h, h->ev[2], h->ev[3]));
-    res->n_reads = units; res->reads = pv->reads.data();
-    res->n_alns = counters[0]; res->alns = pv->alns.data();
-    res->n_edits = counters[1]; res->edits = pv->edits.data();
-    res->n_pairs = counters[2]; res->pairs = pv->pairs.data();
+    res->n_reads = units; res->reads = hReads;
+    res->n_alns = counters[0]; res->alns = hAlns;
+    res->n_edits = counters[1]; res->edits = hEdits;
+    res->n_pairs = counters[2]; res->pairs = hPairs;
     res->ms_h2d = msH2d; res->ms_kernel = msKernel; res->ms_d2h = msD2h;
     res->h2d_bytes = h2d;
     res->d2h_bytes = (uint64_t)units * sizeof(ht2gpu_read_result_t) + (uint64_t)counters[0] * sizeof(ht2gpu_aln_t) +
@@ -988,7 +1028,7 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
     res->priv = pv;
     (void)timeCopies;
     uint32_t anyErr = 0;
-    for (uint32_t i = 0; i < units; i++) anyErr |= pv->reads[i].err;
+    for (uint32_t i = 0; i < units; i++) anyErr |= hReads[i].err;
     if (anyErr) {
         char buf[128]; snprintf(buf, sizeof(buf), "device capacity exceeded for some reads (err bits 0x%x)", anyErr);
         h->err = buf;
@@ -1007,7 +1047,7 @@ extern "C" int ht2gpu_align_resident(ht2gpu_handle_t* h, const ht2gpu_read_batch
 }
 extern "C" void ht2gpu_free_results(ht2gpu_result_batch_t* res)
 {
-    if (res && res->priv) { delete (ResPriv*)res->priv; res->priv = NULL; }
+    if (res && res->priv) { ResPriv* pv = (ResPriv*)res->priv; pinnedPut(*pv); delete pv; res->priv = NULL; }
 }
 
 // ---------------------------------------------------------------------------
