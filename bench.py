@@ -301,10 +301,10 @@ def main():
                 "device_ms_per_step": e2e_dev_ms / args.steps},
         "gpu_launches": int(tot[3]),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "ht2_align_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "ht2_align_pool_kernel<8,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                      "algorithmic_bytes_per_read": float(tot[0]) / total_reads,
-                     "note": "algorithmic bytes = sides touched x 64 B + ftab/SA-sample entries + 2-bit reference bytes, counted in-kernel"},
+                     "note": "algorithmic bytes = sides touched x 32 B (rank sides) + ftab/SA-sample entries + 2-bit reference bytes, counted in-kernel"},
     }
     if dist is not None:
         dist.destroy_process_group()
