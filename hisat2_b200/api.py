@@ -52,7 +52,22 @@ EXPORTS = [
     "ht2gpu_free_image", "ht2gpu_image_data", "ht2gpu_image_bytes", "ht2gpu_device_image", "ht2gpu_align_batch",
     "ht2gpu_align_resident", "ht2gpu_free_results", "ht2gpu_format_sam", "ht2gpu_sam_header", "ht2gpu_free_text",
     "ht2gpu_num_refs", "ht2gpu_ref_name", "ht2gpu_ref_len", "ht2gpu_read_seed", "ht2gpu_last_error", "ht2gpu_close",
+    "ht2gpu_seed_search", "ht2gpu_free_seed_results", "ht2gpu_index_is_graph",
 ]
+
+
+class CSeedResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("first_hit", C.c_void_p), ("n_hits", C.c_uint32), ("hits", C.c_void_p),
+                ("n_iedges", C.c_uint32), ("iedges", C.c_void_p), ("n_coords", C.c_uint32), ("coords", C.c_void_p),
+                ("n_lf", C.c_uint64), ("alg_bytes", C.c_uint64), ("ms_kernel", C.c_float), ("err", C.c_uint32),
+                ("priv", C.c_void_p)]
+
+
+SEED_HIT_DTYPE = np.dtype([("read", "<u4"), ("fw", "u1"), ("hit_type", "u1"), ("pseudogene_stop", "u1"), ("anchor_stop", "u1"),
+                           ("bwoff", "<u4"), ("len", "<u4"), ("top", "<u4"), ("bot", "<u4"), ("node_top", "<u4"),
+                           ("node_bot", "<u4"), ("n_iedges", "<u4"), ("iedge_off", "<u4"), ("n_coords", "<u4"),
+                           ("coord_off", "<u4")])
+SEED_COORD_DTYPE = np.dtype([("row", "<u4"), ("joined_off", "<u4"), ("tidx", "<u4"), ("toff", "<u4")])
 
 
 def load_library(path=None):
@@ -87,6 +102,9 @@ def load_library(path=None):
     lib.ht2gpu_read_seed.restype = C.c_uint32
     lib.ht2gpu_last_error.argtypes = [C.c_void_p]; lib.ht2gpu_last_error.restype = C.c_char_p
     lib.ht2gpu_close.argtypes = [C.c_void_p]
+    lib.ht2gpu_seed_search.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_uint32, C.POINTER(CSeedResult)]
+    lib.ht2gpu_free_seed_results.argtypes = [C.POINTER(CSeedResult)]
+    lib.ht2gpu_index_is_graph.argtypes = [C.c_void_p]
     if path is None:
         _lib = lib
     return lib
@@ -215,6 +233,54 @@ class AlignResult(object):
             pass
 
 
+class SeedResult(object):
+    """Owns one ht2gpu_seed_result_t (seed search on its own; linear and graph indexes)."""
+
+    def __init__(self, lib, c):
+        self._lib = lib
+        self._c = c
+        v = AlignResult._view
+        self.first_hit = v(c.first_hit, c.n_reads + 1, np.dtype("<u4"))
+        self.hits = v(c.hits, c.n_hits, SEED_HIT_DTYPE)
+        self.iedges = v(c.iedges, c.n_iedges * 2, np.dtype("<u2")).reshape(-1, 2)
+        self.coords = v(c.coords, c.n_coords, SEED_COORD_DTYPE)
+        self.n_lf, self.alg_bytes, self.ms_kernel, self.err = c.n_lf, c.alg_bytes, c.ms_kernel, c.err
+
+    def dump_lines(self, graph):
+        """The record format of oracle/ref_dump.cpp (H / G / C lines), for parity tests."""
+        out = []
+        hits, co, ie = self.hits, self.coords, self.iedges
+        order = np.zeros(len(hits), dtype=np.int64)
+        for r in range(len(self.first_hit) - 1):
+            lo, hi = int(self.first_hit[r]), int(self.first_hit[r + 1])
+            k = {1: 0, 0: 0}
+            for i in range(lo, hi):
+                f = int(hits["fw"][i]); order[i] = k[f]; k[f] += 1
+        for i in range(len(hits)):
+            h = hits[i]
+            out.append("H %d %d %d %d %d %d %d %d %d\n" % (h["read"], h["fw"], h["bwoff"], h["len"], h["top"], h["bot"], h["hit_type"],
+                                                           h["pseudogene_stop"], h["anchor_stop"]))
+            blank = int(h["top"]) == 0xffffffff
+            if graph and not blank:
+                e = ie[int(h["iedge_off"]):int(h["iedge_off"]) + int(h["n_iedges"])]
+                out.append("G %d %d %d %d %d %d%s\n" % (h["read"], h["fw"], order[i], h["node_top"], h["node_bot"], h["n_iedges"],
+                                                         "".join(" %d:%d" % (a, b) for a, b in e)))
+            for c in co[int(h["coord_off"]):int(h["coord_off"]) + int(h["n_coords"])]:
+                out.append("C %d %d %d %d %d %d %d\n" % (h["read"], h["fw"], order[i], c["row"], c["joined_off"], c["tidx"], c["toff"]))
+        return out
+
+    def close(self):
+        if self._c is not None:
+            self._lib.ht2gpu_free_seed_results(C.byref(self._c))
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Index(object):
     """Device-resident HISAT2 index + alignment entry points."""
 
@@ -272,6 +338,18 @@ class Index(object):
             rc = self._lib.ht2gpu_align_batch(self._h, C.byref(cb), C.byref(cr))
         res = AlignResult(self._lib, cr)
         self._check(rc, "ht2gpu_align", allow_capacity)
+        return res
+
+    def is_graph(self):
+        return bool(self._lib.ht2gpu_index_is_graph(self._h))
+
+    def seed_search(self, batch, max_range=4):
+        """ht2gpu_seed_search: partial-search chains + coordinates of small ranges."""
+        cb = batch.c_struct()
+        cr = CSeedResult()
+        rc = self._lib.ht2gpu_seed_search(self._h, C.byref(cb), max_range, C.byref(cr))
+        res = SeedResult(self._lib, cr)
+        self._check(rc, "ht2gpu_seed_search")
         return res
 
     def sam_header(self):

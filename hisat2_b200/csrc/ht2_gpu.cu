@@ -17,6 +17,7 @@
 
 #include "../../include/ht2gpu.h"
 #include "ht2_core.h"
+#include "ht2_seed.h"
 #include "ht2_host.h"
 #include "ht2_index.h"
 
@@ -571,6 +572,96 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b,
 }
 
 // ---------------------------------------------------------------------------
+// ht2_seed_kernel: the seed search on its own (ht2_seed.h), one lane per read,
+// two passes (count, then fill at host-computed offsets) so that the output is
+// laid out per read without a worst-case allocation.
+// ---------------------------------------------------------------------------
+struct SeedOut {
+    uint32_t*            counts;     // [n][3] hits, iedges, coords            (pass 0 out)
+    const uint32_t*      offs;       // [n][3] exclusive prefix of counts       (pass 1 in)
+    ht2gpu_seed_hit_t*   hits;
+    uint16_t*            iedges;
+    ht2gpu_seed_coord_t* coords;
+    unsigned long long*  totals;     // [0] nLF, [1] algBytes, [2] reads with errors
+};
+
+template <bool GRAPH, bool FILL>
+__global__ void __launch_bounds__(128)
+ht2_seed_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, uint32_t nReads, uint32_t maxRange, SeedOut o)
+{
+    const Ht2ImageHeader* H = (const Ht2ImageHeader*)blob;
+    Ht2Fm<uint32_t> fm;
+    fm.init(blob, &H->global);
+    const uint32_t nFrag = H->global.nFrag;
+    for (uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x; ri < nReads; ri += gridDim.x * blockDim.x) {
+        const uint64_t o0 = b.offs[ri];
+        uint32_t len = (uint32_t)(b.offs[ri + 1] - o0);
+        Ht2SeedState st;
+        st.err = 0; st.nLF = 0; st.algBytes = 0;
+        if (len > HT2_MAX_RDLEN) { st.err = 2; len = 0; }
+        uint8_t rc[HT2_MAX_RDLEN];
+        const uint8_t* fwseq = b.seq + o0;
+        for (uint32_t i = 0; i < len; i++) { const uint8_t c = fwseq[len - 1 - i]; rc[i] = c < 4 ? (uint8_t)(c ^ 3) : (uint8_t)4; }
+        uint32_t nh = 0, ne = 0, nc = 0;
+        uint32_t bh = 0, be = 0, bc = 0;
+        if (FILL) { bh = o.offs[3 * ri]; be = o.offs[3 * ri + 1]; bc = o.offs[3 * ri + 2]; }
+        for (int fwi = 0; fwi < 2 && len > 0; fwi++) {
+            const uint8_t* seq = fwi == 0 ? fwseq : rc;
+            st.len = len; st.cur = 0; st.done = 0; st.numPartialSearch = 0; st.numUniqueSearch = 0;
+            while (!st.done) {
+                Ht2SeedHit ph;
+                bool pseudogeneStop = !GRAPH && !P.noSplicedAlignment, anchorStop = true;   // hi_aligner.h:4669-4670
+                ht2_seed_partial<GRAPH>(fm, P, seq, st, ph, pseudogeneStop, anchorStop);
+                const bool blank = ph.top == HT2_IDX_MAX32;
+                const uint32_t nelt = blank ? 0u : ph.node_bot - ph.node_top;
+                const uint32_t ncoord = (!blank && nelt <= maxRange) ? nelt : 0u;
+                if (FILL) {
+                    ht2gpu_seed_hit_t& out = o.hits[bh + nh];
+                    out.read = ri; out.fw = fwi == 0; out.hit_type = ph.hit_type;
+                    out.pseudogene_stop = ph.pseudogeneStop; out.anchor_stop = ph.anchorStop;
+                    out.bwoff = ph.bwoff; out.len = ph.len; out.top = ph.top; out.bot = ph.bot;
+                    out.node_top = ph.node_top; out.node_bot = ph.node_bot;
+                    out.n_iedges = ph.niedges; out.iedge_off = be + ne;
+                    out.n_coords = ncoord; out.coord_off = bc + nc;
+                    for (uint32_t e = 0; e < ph.niedges; e++) {
+                        o.iedges[2 * (size_t)(be + ne + e)] = ph.iedges[e][0];
+                        o.iedges[2 * (size_t)(be + ne + e) + 1] = ph.iedges[e][1];
+                    }
+                    for (uint32_t i = 0; i < ncoord; i++) {
+                        uint32_t row;
+                        const uint32_t joff = ht2_seed_elt_offset<GRAPH>(fm, ph, i, row, st);
+                        ht2gpu_seed_coord_t& cc = o.coords[bc + nc + i];
+                        cc.row = row; cc.joined_off = joff; cc.tidx = HT2_IDX_MAX32; cc.toff = 0;
+                        // GFM::joinedToTextOff, rejectStraddle = false (gfm.h:5527-5600)
+                        uint32_t lo = 0, hi = nFrag, elt = HT2_IDX_MAX32;
+                        while (true) {
+                            const uint32_t old = elt;
+                            elt = lo + ((hi - lo) >> 1);
+                            if (old == elt) break;
+                            const uint32_t lower = fm.rstarts[elt * 3];
+                            const uint32_t upper = (elt == nFrag - 1) ? fm.g->len : fm.rstarts[(elt + 1) * 3];
+                            if (lower <= joff) {
+                                if (upper > joff) { cc.tidx = fm.rstarts[elt * 3 + 1]; cc.toff = joff - lower + fm.rstarts[elt * 3 + 2]; break; }
+                                lo = elt;
+                            } else hi = elt;
+                        }
+                    }
+                }
+                nh++; ne += ph.niedges; nc += ncoord;
+                if (st.done) break;
+                if (!pseudogeneStop) { if (st.cur + 1 < st.len) st.cur++; }
+            }
+        }
+        if (!FILL) { o.counts[3 * ri] = nh; o.counts[3 * ri + 1] = ne; o.counts[3 * ri + 2] = nc; }
+        else {
+            atomicAdd(&o.totals[0], (unsigned long long)st.nLF);
+            atomicAdd(&o.totals[1], (unsigned long long)st.algBytes);
+            if (st.err) atomicAdd(&o.totals[2], 1ull);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct ht2gpu_handle {
@@ -583,6 +674,7 @@ struct ht2gpu_handle {
     int            device;
     int            nSM;
     int            tpb, bpsm, lanes;
+    bool           graph;
     bool           regroup, blockRegroup, pool;
     int            poolWarps;
     int            rgK;
@@ -670,7 +762,7 @@ static int finishOpen(ht2gpu_handle* h)
     const Ht2ImageHeader* H = h->img->header();
     if (H->magic != HT2_MAGIC || H->version != HT2_IMAGE_VERSION) { h->err = "bad index image"; return HT2GPU_ERR_INDEX; }
     if (!h->opt.no_spliced_alignment) { h->err = "spliced alignment is not implemented in this build; pass --no-spliced-alignment"; return HT2GPU_ERR_UNSUPPORTED; }
-    if (!H->global.linearFM) { h->err = "graph (SNP) indexes are not implemented in this build"; return HT2GPU_ERR_UNSUPPORTED; }
+    h->graph = !H->global.linearFM;   // graph indexes: seed search only (ht2gpu_seed_search); alignment refuses them
     applyOptions(h->P, *h->img, h->opt);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -972,6 +1064,11 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
     if (!h || !b || !res) return HT2GPU_ERR_ARG;
     if (b->paired && (b->n_reads & 1)) { h->err = "paired batch needs an even number of reads"; return HT2GPU_ERR_ARG; }
     memset(res, 0, sizeof(*res));
+    if (h->graph) {
+        h->err = "alignment over graph (SNP) indexes is not implemented in this build (ALT-aware extension); "
+                 "ht2gpu_seed_search supports them";
+        return HT2GPU_ERR_UNSUPPORTED;
+    }
     if (b->n_reads == 0) return HT2GPU_OK;
     CK(cudaSetDevice(h->device));
     const uint32_t units = b->paired ? b->n_reads / 2 : b->n_reads;
@@ -1048,6 +1145,99 @@ extern "C" int ht2gpu_align_resident(ht2gpu_handle_t* h, const ht2gpu_read_batch
 extern "C" void ht2gpu_free_results(ht2gpu_result_batch_t* res)
 {
     if (res && res->priv) { ResPriv* pv = (ResPriv*)res->priv; pinnedPut(*pv); delete pv; res->priv = NULL; }
+}
+
+// ---------------------------------------------------------------------------
+// seed search (linear and graph indexes)
+// ---------------------------------------------------------------------------
+struct SeedPriv {
+    std::vector<uint32_t> firstHit;
+    std::vector<ht2gpu_seed_hit_t> hits;
+    std::vector<uint16_t> iedges;
+    std::vector<ht2gpu_seed_coord_t> coords;
+};
+
+extern "C" int ht2gpu_index_is_graph(const ht2gpu_handle_t* h) { return h && h->graph ? 1 : 0; }
+
+extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, uint32_t maxRange, ht2gpu_seed_result_t* res)
+{
+    if (!h || !b || !res) return HT2GPU_ERR_ARG;
+    memset(res, 0, sizeof(*res));
+    SeedPriv* pv = new SeedPriv();
+    res->priv = pv;
+    const uint32_t n = b->n_reads;
+    res->n_reads = n;
+    pv->firstHit.assign((size_t)n + 1, 0);
+    res->first_hit = pv->firstHit.data();
+    if (n == 0) return HT2GPU_OK;
+    CK(cudaSetDevice(h->device));
+    uint64_t h2d = 0;
+    int rc = uploadBatch(h, b, h2d);
+    if (rc) return rc;
+    DevBatch db;
+    db.seq = h->dSeq; db.qual = NULL; db.offs = h->dOffs; db.seeds = h->dSeeds; db.n_units = n; db.paired = 0;
+    uint32_t *dCounts = NULL, *dOffs3 = NULL;
+    unsigned long long* dTot = NULL;
+    SeedOut so; memset(&so, 0, sizeof(so));
+    CK(cudaMalloc(&dCounts, (size_t)n * 12));
+    CK(cudaMalloc(&dOffs3, (size_t)n * 12));
+    CK(cudaMalloc(&dTot, 3 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(dTot, 0, 3 * sizeof(unsigned long long), h->stream));
+    so.counts = dCounts; so.offs = dOffs3; so.totals = dTot;
+    const int tpb = 128;
+    int grid = (int)((n + tpb - 1) / tpb);
+    const int maxGrid = h->nSM * 16;
+    if (grid > maxGrid) grid = maxGrid;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if (h->graph) ht2_seed_kernel<true, false><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    else ht2_seed_kernel<false, false><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    std::vector<uint32_t> counts((size_t)n * 3), offs((size_t)n * 3);
+    CK(cudaMemcpyAsync(counts.data(), dCounts, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms0 = 0, ms1 = 0;
+    CK(cudaEventElapsedTime(&ms0, h->ev[1], h->ev[2]));
+    uint64_t th = 0, te = 0, tc = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        offs[3 * (size_t)i] = (uint32_t)th; offs[3 * (size_t)i + 1] = (uint32_t)te; offs[3 * (size_t)i + 2] = (uint32_t)tc;
+        pv->firstHit[i] = (uint32_t)th;
+        th += counts[3 * (size_t)i]; te += counts[3 * (size_t)i + 1]; tc += counts[3 * (size_t)i + 2];
+    }
+    pv->firstHit[n] = (uint32_t)th;
+    if (th > 0xfffffff0ull || tc > 0xfffffff0ull) { h->err = "seed search result too large for one batch"; return HT2GPU_ERR_CAPACITY; }
+    ht2gpu_seed_hit_t* dHits = NULL; uint16_t* dIe = NULL; ht2gpu_seed_coord_t* dCo = NULL;
+    CK(cudaMalloc(&dHits, (th + 1) * sizeof(ht2gpu_seed_hit_t)));
+    CK(cudaMalloc(&dIe, (te + 1) * 4));
+    CK(cudaMalloc(&dCo, (tc + 1) * sizeof(ht2gpu_seed_coord_t)));
+    CK(cudaMemcpyAsync(dOffs3, offs.data(), (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+    so.hits = dHits; so.iedges = dIe; so.coords = dCo;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if (h->graph) ht2_seed_kernel<true, true><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    else ht2_seed_kernel<false, true><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    pv->hits.resize(th); pv->iedges.resize(te * 2); pv->coords.resize(tc);
+    unsigned long long tot[3] = {0, 0, 0};
+    if (th) CK(cudaMemcpyAsync(pv->hits.data(), dHits, th * sizeof(ht2gpu_seed_hit_t), cudaMemcpyDeviceToHost, h->stream));
+    if (te) CK(cudaMemcpyAsync(pv->iedges.data(), dIe, te * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (tc) CK(cudaMemcpyAsync(pv->coords.data(), dCo, tc * sizeof(ht2gpu_seed_coord_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(tot, dTot, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&ms1, h->ev[1], h->ev[2]));
+    cudaFree(dCounts); cudaFree(dOffs3); cudaFree(dTot); cudaFree(dHits); cudaFree(dIe); cudaFree(dCo);
+    res->n_hits = (uint32_t)th; res->hits = pv->hits.data();
+    res->n_iedges = (uint32_t)te; res->iedges = pv->iedges.data();
+    res->n_coords = (uint32_t)tc; res->coords = pv->coords.data();
+    res->n_lf = tot[0]; res->alg_bytes = tot[1]; res->err = (uint32_t)tot[2];
+    res->ms_kernel = ms0 + ms1;
+    if (tot[2]) { h->err = "seed search: device capacity exceeded for some reads"; return HT2GPU_ERR_CAPACITY; }
+    return HT2GPU_OK;
+}
+
+extern "C" void ht2gpu_free_seed_results(ht2gpu_seed_result_t* res)
+{
+    if (res && res->priv) { delete (SeedPriv*)res->priv; res->priv = NULL; }
 }
 
 // ---------------------------------------------------------------------------

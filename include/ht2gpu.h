@@ -163,6 +163,54 @@ int ht2gpu_align_resident(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, 
                           ht2gpu_result_batch_t* res);
 void ht2gpu_free_results(ht2gpu_result_batch_t* res);
 
+/* ---- seed search on its own (linear AND graph/SNP indexes) -------------------
+ * For every read and strand (fw first): the chain of partial searches
+ * HI_Aligner::partialSearch produces when driven like nextBWT (hi_aligner.h:
+ * 6361-6601, 4720-4751), i.e. the BWTHit list of ReadBWTHit (hi_aligner.h:108-
+ * 391), and for hits whose node range is <= max_range the joined/text
+ * coordinate of every element (GFM::getOffset gfm.h:5682, joinedToTextOff
+ * :5527; element i = first BW row of node i, group_walk.h:545-560).
+ * Uses the batch's seq/offs only (unpaired view). */
+typedef struct {
+    uint32_t read;                   /* index into the batch */
+    uint8_t  fw;                     /* 1 = forward strand of the read */
+    uint8_t  hit_type;               /* 1 candidate, 2 pseudogene, 3 anchor (hi_aligner.h:96-100) */
+    uint8_t  pseudogene_stop, anchor_stop;
+    uint32_t bwoff, len;             /* offset from the read's 3' end, # bases consumed */
+    uint32_t top, bot;               /* BW row range; 0xffffffff = blank hit */
+    uint32_t node_top, node_bot;     /* node range (== row range on linear indexes) */
+    uint32_t n_iedges, iedge_off;    /* in-edge list: pairs (node index in range, # extra incoming edges) */
+    uint32_t n_coords, coord_off;
+} ht2gpu_seed_hit_t;
+
+typedef struct {
+    uint32_t row;                    /* BW row the walk started from */
+    uint32_t joined_off;             /* offset in the joined reference */
+    uint32_t tidx, toff;             /* 0xffffffff tidx: not inside a reference fragment */
+} ht2gpu_seed_coord_t;
+
+typedef struct {
+    uint32_t             n_reads;
+    uint32_t*            first_hit;  /* n_reads + 1 entries: hits of read i are [first_hit[i], first_hit[i+1]) */
+    uint32_t             n_hits;
+    ht2gpu_seed_hit_t*   hits;
+    uint32_t             n_iedges;
+    uint16_t*            iedges;     /* 2 entries per pair */
+    uint32_t             n_coords;
+    ht2gpu_seed_coord_t* coords;
+    uint64_t             n_lf;       /* LF steps (boundary ranks) executed */
+    uint64_t             alg_bytes;  /* algorithmic bytes of those steps */
+    float                ms_kernel;  /* both passes (count, fill) */
+    uint32_t             err;        /* reads with capacity errors */
+    void*                priv;
+} ht2gpu_seed_result_t;
+
+int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, uint32_t max_range,
+                       ht2gpu_seed_result_t* res);
+void ht2gpu_free_seed_results(ht2gpu_seed_result_t* res);
+/* 1 when the opened index is a graph (SNP / splice-site) index. */
+int ht2gpu_index_is_graph(const ht2gpu_handle_t* h);
+
 /* Host back end: selection, MAPQ and SAM text for a batch (finishRead).
  * names: n_reads '\0'-terminated read names, concatenated.  The returned
  * buffer is malloc'ed; free with ht2gpu_free_text. */

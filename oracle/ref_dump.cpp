@@ -76,9 +76,26 @@ struct Dumper : public HI_Aligner<index_t, local_index_t> {
                 BWTHit<index_t>& ph = hit._partialHits.back();
                 cout << "H " << rdid << " " << fw << " " << ph._bwoff << " " << ph._len << " " << ph._top << " "
                      << ph._bot << " " << ph._hit_type << " " << pseudogeneStop << " " << anchorStop << "\n";
-                if(!ph.empty() && ph._bot - ph._top <= 4) {
-                    for(index_t r = ph._top; r < ph._bot; r++) {
-                        index_t joff = gfm.getOffset(r, r);
+                const bool graph = !gfm.gh().linearFM();
+                if(graph && !ph.empty()) {
+                    // graph indexes: node range and in-edge list of the hit (gfm.h:3759-3837)
+                    cout << "G " << rdid << " " << fw << " " << (hit._partialHits.size() - 1) << " " << ph._node_top << " "
+                         << ph._node_bot << " " << ph._node_iedge_count.size();
+                    for(size_t e = 0; e < ph._node_iedge_count.size(); e++)
+                        cout << " " << ph._node_iedge_count[e].first << ":" << ph._node_iedge_count[e].second;
+                    cout << "\n";
+                }
+                if(!ph.empty() && ph._node_bot - ph._node_top <= 4) {
+                    // element i of the node range: first BW row of the node (group_walk.h:545-560) and its offset
+                    index_t num_iedges = 0; size_t e = 0;
+                    for(index_t i = 0; i < ph._node_bot - ph._node_top; i++) {
+                        while(e < ph._node_iedge_count.size()) {
+                            if(i <= ph._node_iedge_count[e].first) break;
+                            num_iedges += ph._node_iedge_count[e].second;
+                            e++;
+                        }
+                        index_t r = ph._top + i + num_iedges;
+                        index_t joff = gfm.getOffset(r, ph._node_top + i);
                         index_t tidx = 0, toff = 0, tlen = 0; bool straddled = false;
                         gfm.joinedToTextOff(ph._len, joff, tidx, toff, tlen, false, straddled);
                         cout << "C " << rdid << " " << fw << " " << (hit._partialHits.size() - 1) << " " << r << " "

@@ -11,6 +11,9 @@
   tiny_se.sam        hisat2-align-s --no-spliced-alignment -f -x tiny -U tiny_se.fa
   tiny_pe_{1,2}.fa / tiny_pe.sam   300 pairs, same flags with -1/-2
   tiny_dump.txt      oracle/_ref/ref_dump tiny tiny_se.fa 1   (kernel-level vectors)
+  tiny.snp           seeded SNP list (single / deletion / insertion) over tiny.fa
+  tiny_snp.{1..8}.ht2  hisat2-build-s --ftabchars 7 --snp tiny.snp tiny.fa tiny_snp  (GRAPH index)
+  tiny_snp_dump.txt  ref_dump on the graph index: H/C lines plus G lines (node range, in-edge list)
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import os, subprocess, sys
@@ -71,5 +74,47 @@ def main():
         with open(os.path.join(G, name), "w") as fo:
             fo.writelines(l for l in out if int(l.split()[1]) in keep)
 
+def graph():
+    """Graph (SNP) fixture: SNPs every ~150 bp; the dump reads carry alt alleles in half of the cases."""
+    names, seqs = [], []
+    cur = None
+    for l in open(os.path.join(G, "tiny.fa")):
+        if l.startswith(">"):
+            names.append(l[1:].split()[0]); seqs.append([])
+        else:
+            seqs[-1].append(l.strip())
+    seqs = ["".join(x) for x in seqs]
+    rng = np.random.default_rng(77)
+    lines = []
+    k = 0
+    for name, sq in zip(names, seqs):
+        pos = 60
+        while pos + 40 < len(sq):
+            window = sq[pos - 5:pos + 12]
+            if "N" not in window:
+                t = rng.random()
+                if t < 0.75:
+                    alt = "ACGT"[(("ACGT".index(sq[pos])) + int(rng.integers(1, 4))) % 4]
+                    lines.append("ts%d\tsingle\t%s\t%d\t%s" % (k, name, pos, alt))
+                elif t < 0.88:
+                    lines.append("ts%d\tdeletion\t%s\t%d\t%d" % (k, name, pos, int(rng.integers(1, 4))))
+                else:
+                    ins = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, int(rng.integers(1, 4))))
+                    lines.append("ts%d\tinsertion\t%s\t%d\t%s" % (k, name, pos, ins))
+                k += 1
+            pos += int(rng.integers(90, 220))
+    open(os.path.join(G, "tiny.snp"), "w").write("\n".join(lines) + "\n")
+    subprocess.run([os.path.join(REF, "hisat2-build-s"), "-q", "--ftabchars", "7", "--snp", "tiny.snp", "tiny.fa", "tiny_snp"],
+                   check=True, cwd=G, stdout=subprocess.DEVNULL)
+    keep = set(list(range(0, 100)) + list(range(250, 350)) + list(range(500, 600)))
+    out = subprocess.run([os.path.join(REF, "ref_dump"), "tiny_snp", "tiny_se.fa", "1"], check=True, cwd=G,
+                         stdout=subprocess.PIPE).stdout.decode().splitlines(True)
+    with open(os.path.join(G, "tiny_snp_dump.txt"), "w") as fo:
+        fo.writelines(l for l in out if int(l.split()[1]) in keep)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "graph":
+        graph()
+        sys.exit(0)
     main()

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "../../hisat2_b200/csrc/ht2_host.h"
+#include "../../hisat2_b200/csrc/ht2_seed.h"
 
 // HT2_RECURSIVE=1 runs the recursive formulation (ht2_core_impl.h) instead of the
 // explicit-stack state machine the kernels use (ht2_machine.h); both must agree.
@@ -20,7 +21,68 @@ static void runRead(Ht2Aligner& A) {
     while (!A.machineDone()) A.machineStep();
 }
 
+// `ht2_hostsim --seed-dump <index> <reads.fa> <no_spliced>`: host build of ht2_seed.h / ht2_graph.h,
+// printing the record format of oracle/ref_dump.cpp (H / G / C lines).
+template <bool GRAPH>
+static void seedDump(const Ht2Image& img, const Ht2Params& P, const std::vector<Ht2HostRead>& reads) {
+    const Ht2ImageHeader* H = (const Ht2ImageHeader*)img.blob.data();
+    Ht2Fm<uint32_t> fm; fm.init(img.blob.data(), &H->global);
+    for (size_t ri = 0; ri < reads.size(); ri++) {
+        const std::vector<uint8_t>& fwv = reads[ri].seq;
+        const uint32_t len = (uint32_t)fwv.size();
+        if (len == 0) continue;
+        std::vector<uint8_t> rc(len);
+        for (uint32_t i = 0; i < len; i++) { uint8_t c = fwv[len - 1 - i]; rc[i] = c < 4 ? (uint8_t)(c ^ 3) : 4; }
+        for (int fwi = 0; fwi < 2; fwi++) {
+            const uint8_t* seq = fwi == 0 ? fwv.data() : rc.data();
+            Ht2SeedState st; memset(&st, 0, sizeof(st)); st.len = len;
+            unsigned nh = 0;
+            while (!st.done) {
+                Ht2SeedHit ph;
+                bool ps = !GRAPH && !P.noSplicedAlignment, as = true;
+                ht2_seed_partial<GRAPH>(fm, P, seq, st, ph, ps, as);
+                printf("H %zu %d %u %u %u %u %u %u %u\n", ri, fwi == 0, ph.bwoff, ph.len, ph.top, ph.bot, ph.hit_type, ps, as);
+                const bool blank = ph.top == HT2_IDX_MAX32;
+                if (GRAPH && !blank) {
+                    printf("G %zu %d %u %u %u %u", ri, fwi == 0, nh, ph.node_top, ph.node_bot, ph.niedges);
+                    for (uint32_t e = 0; e < ph.niedges; e++) printf(" %u:%u", ph.iedges[e][0], ph.iedges[e][1]);
+                    printf("\n");
+                }
+                if (!blank && ph.node_bot - ph.node_top <= 4) {
+                    for (uint32_t i = 0; i < ph.node_bot - ph.node_top; i++) {
+                        uint32_t row; uint32_t joff = ht2_seed_elt_offset<GRAPH>(fm, ph, i, row, st);
+                        uint32_t tidx = HT2_IDX_MAX32, toff = 0, lo = 0, hi = H->global.nFrag, elt = HT2_IDX_MAX32;
+                        while (true) {
+                            uint32_t old = elt; elt = lo + ((hi - lo) >> 1);
+                            if (old == elt) break;
+                            uint32_t lower = fm.rstarts[elt * 3], upper = (elt == H->global.nFrag - 1) ? fm.g->len : fm.rstarts[(elt + 1) * 3];
+                            if (lower <= joff) { if (upper > joff) { tidx = fm.rstarts[elt * 3 + 1]; toff = joff - lower + fm.rstarts[elt * 3 + 2]; break; } lo = elt; }
+                            else hi = elt;
+                        }
+                        printf("C %zu %d %u %u %u %u %u\n", ri, fwi == 0, nh, row, joff, tidx, toff);
+                    }
+                }
+                nh++;
+                if (st.done) break;
+                if (!ps) { if (st.cur + 1 < st.len) st.cur++; }
+            }
+        }
+    }
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 5 && !strcmp(argv[1], "--seed-dump")) {
+        std::string err;
+        Ht2Image* img = ht2_image_load(argv[2], err);
+        if (!img) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        std::vector<Ht2HostRead> reads;
+        if (!ht2_read_fasta(argv[3], reads, 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        Ht2Params P;
+        ht2_default_params(P, *img, atoi(argv[4]) != 0);
+        const Ht2ImageHeader* H = (const Ht2ImageHeader*)img->blob.data();
+        if (H->global.linearFM) seedDump<false>(*img, P, reads); else seedDump<true>(*img, P, reads);
+        return 0;
+    }
     if (argc < 4) { fprintf(stderr, "usage: %s index reads.fa out.sam\n", argv[0]); return 2; }
     std::string err;
     Ht2Image* img = ht2_image_load(argv[1], err);

@@ -15,8 +15,9 @@ KEEP = set(list(range(0, 100)) + list(range(250, 350)) + list(range(500, 600)))
 def test_oracle_matches_reference_dump(oracle_bin):
     """oracle/ht2_oracle.c == golden vectors dumped from the unmodified
     reference's partialSearch/getOffset/joinedToTextOff (tests/golden/make_golden.py)."""
-    for mode, name in (("1", "tiny_dump.txt"), ("0", "tiny_dump_spliced.txt")):
-        out = subprocess.run([oracle_bin, "dump", "tiny", "tiny_se.fa", mode], cwd=GOLDEN, check=True,
+    for idx, mode, name in (("tiny", "1", "tiny_dump.txt"), ("tiny", "0", "tiny_dump_spliced.txt"),
+                            ("tiny_snp", "1", "tiny_snp_dump.txt")):   # tiny_snp = GRAPH index (SNPs, indels)
+        out = subprocess.run([oracle_bin, "dump", idx, "tiny_se.fa", mode], cwd=GOLDEN, check=True,
                              stdout=subprocess.PIPE).stdout.decode().splitlines(True)
         got = [l for l in out if int(l.split()[1]) in KEEP]
         want = open(os.path.join(GOLDEN, name)).readlines()
@@ -38,6 +39,21 @@ def test_host_state_machine_matches_golden_sam_paired(hostsim_bin, tmp_path):
     out = str(tmp_path / "pe.sam")
     subprocess.run([hostsim_bin, "tiny", "tiny_pe_1.fa", out, "tiny_pe_2.fa"], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL)
     assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe.sam"), "rb").read())
+
+
+def test_host_seed_search_matches_reference_dump(hostsim_bin):
+    """Host build of the product's seed-search headers (ht2_seed.h, ht2_graph.h: mapGLF / mapGLF1 /
+    rank_M / select_F / getInEdgeCount / getOffset over the packed image) == the unmodified
+    reference's partialSearch + getOffset dump, on the linear AND the graph (SNP) fixture."""
+    for idx, mode, name in (("tiny", "1", "tiny_dump.txt"), ("tiny", "0", "tiny_dump_spliced.txt"),
+                            ("tiny_snp", "1", "tiny_snp_dump.txt")):
+        out = subprocess.run([hostsim_bin, "--seed-dump", idx, "tiny_se.fa", mode], cwd=GOLDEN, check=True,
+                             stdout=subprocess.PIPE).stdout.decode().splitlines(True)
+        got = [l for l in out if int(l.split()[1]) in KEEP]
+        want = open(os.path.join(GOLDEN, name)).readlines()
+        assert got == want, (idx, mode)
+    graph = open(os.path.join(GOLDEN, "tiny_snp_dump.txt")).read()
+    assert graph.count("\nG ") > 3000 and any(l.split()[6] != "0" for l in graph.splitlines() if l.startswith("G "))
 
 
 def test_abi_exports_every_declared_symbol(lib):

@@ -113,6 +113,43 @@ def test_in_kernel_seed_search_matches_oracle(h2, tiny, oracle_bin):
     assert checked > 150
 
 
+KEEP = set(list(range(0, 100)) + list(range(250, 350)) + list(range(500, 600)))
+
+
+@pytest.mark.parametrize("idx,name", [("tiny", "tiny_dump.txt"), ("tiny_snp", "tiny_snp_dump.txt")])
+def test_seed_search_kernel_matches_reference_dump(h2, idx, name):
+    """ht2gpu_seed_search (ht2_seed_kernel) == the unmodified reference's partialSearch chains, node
+    ranges, in-edge lists and getOffset / joinedToTextOff results, on the linear and the GRAPH fixture."""
+    index = h2.Index(os.path.join(GOLDEN, idx))
+    assert index.is_graph() == (idx == "tiny_snp")
+    batch = h2.ReadBatch.from_fasta(os.path.join(GOLDEN, "tiny_se.fa"))
+    res = index.seed_search(batch, max_range=4)
+    got = [l for l in res.dump_lines(index.is_graph()) if int(l.split()[1]) in KEEP]
+    want = open(os.path.join(GOLDEN, name)).readlines()
+    assert got == want
+    assert res.n_lf > 0 and res.alg_bytes > 0 and res.err == 0
+    if idx == "tiny_snp":   # alignment over graph indexes is refused loudly, never silently wrong
+        with pytest.raises(h2.Ht2GpuError):
+            index.align(batch)
+    index.close()
+
+
+def test_seed_search_bundled_graph_index_matches_oracle(h2, oracle_bin):
+    """The reference's bundled example index (22_20-21M_snp: 3,689 SNPs/indels, 958,359 rows over
+    954,773 nodes): every H/G/C record of 20k hard reads equals the pinned oracle's."""
+    base = os.path.join(DATA, "22_20-21M_snp")
+    fa = os.path.join(DATA, "hard20k_1.fa")
+    if not (os.path.exists(base + ".1.ht2") and os.path.exists(fa)):
+        pytest.skip("data/ not staged")
+    index = h2.Index(base)
+    assert index.is_graph()
+    batch = h2.ReadBatch.from_fasta(fa)
+    res = index.seed_search(batch, max_range=4)
+    want = subprocess.run([oracle_bin, "dump", base, fa, "1"], check=True, stdout=subprocess.PIPE).stdout.decode().splitlines(True)
+    assert res.dump_lines(True) == want
+    index.close()
+
+
 def test_batch_composition_invariance_and_determinism(h2, tiny):
     """Reads are independent units: any split of the batch gives the same records."""
     batch = h2.ReadBatch.from_fasta(os.path.join(GOLDEN, "tiny_se.fa"))
