@@ -152,6 +152,52 @@ class ReadBatch(object):
         return b"\0".join(self.names) + b"\0"
 
     @staticmethod
+    def from_fastq(path, lib=None, global_seed=0, path2=None):
+        """Parse 4-line Phred+33 FASTQ like FastqPatternSource::parse (pat.cpp:1030-1290)."""
+        lib = lib or load_library()
+
+        def parse(p):
+            names, seqs, quals = [], [], []
+            with open(p, "rb") as f:
+                lines = [l.rstrip(b"\r\n") for l in f]
+            lines = [l for l in lines if l != b""]
+            if len(lines) % 4:
+                raise Ht2GpuError("%s: not a 4-line FASTQ file" % p)
+            for i in range(0, len(lines), 4):
+                if not lines[i].startswith(b"@") or not lines[i + 2].startswith(b"+"):
+                    raise Ht2GpuError("%s: malformed FASTQ record %d" % (p, i // 4))
+                sq = lines[i + 1].replace(b".", b"N")
+                if len(lines[i + 3]) != len(sq):
+                    raise Ht2GpuError("%s: quality / base count mismatch in record %d" % (p, i // 4))
+                if len(sq) == 0:
+                    continue
+                names.append(lines[i][1:] or str(i // 4).encode()); seqs.append(sq); quals.append(lines[i + 3])
+            return names, seqs, quals
+
+        names, seqs, quals = parse(path)
+        if path2 is not None:
+            n2, s2, q2 = parse(path2)
+            if len(n2) != len(names):
+                raise Ht2GpuError("mate files differ in read count")
+            inames, iseqs, iquals = [], [], []
+            for a, b, q, c, d, e in zip(names, seqs, quals, n2, s2, q2):
+                inames += [a if a.endswith(b"/1") else a + b"/1", c if c.endswith(b"/2") else c + b"/2"]
+                iseqs += [b, d]; iquals += [q, e]
+            names, seqs, quals = inames, iseqs, iquals
+        codes, offs = [], [0]
+        for s in seqs:
+            codes.append(_ASC2DNA[np.frombuffer(s, dtype=np.uint8)])
+            offs.append(offs[-1] + len(s))
+        seq = np.concatenate(codes) if codes else np.zeros(0, np.uint8)
+        qual = np.frombuffer(b"".join(quals), dtype=np.uint8).copy() if quals else np.zeros(0, np.uint8)
+        seeds = np.zeros(len(names), dtype=np.uint32)
+        for i, nm in enumerate(names):
+            c = np.ascontiguousarray(codes[i])
+            q = np.ascontiguousarray(qual[offs[i]:offs[i + 1]])
+            seeds[i] = lib.ht2gpu_read_seed(c.ctypes.data, q.ctypes.data, len(c), nm, global_seed)
+        return ReadBatch(seq, offs, seeds, names, qual, paired=path2 is not None)
+
+    @staticmethod
     def from_fasta(path, lib=None, global_seed=0, path2=None):
         """Parse FASTA like FastaPatternSource::read (pat.cpp:725-849)."""
         lib = lib or load_library()

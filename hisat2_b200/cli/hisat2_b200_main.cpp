@@ -72,7 +72,7 @@ int main(int argc, char** argv)
         else if (a == "--no-spliced-alignment") o.no_spliced_alignment = 1;
         else if (a == "-k") o.khits = atoi(next()); else if (a == "--max-seeds") o.max_seeds = atoi(next());
         else if (a == "--secondary") o.secondary = 1;
-        else if (a == "--mp") two(next(), o.mp_max, o.mp_min); else if (a == "--sp") two(next(), o.sp_max, o.sp_min);
+        else if (a == "--mp") two(next(), o.mp_max, o.mp_min); else if (a == "--sp") { two(next(), o.sp_max, o.sp_min); o.sp_min = o.sp_max; /* the reference reads BOTH values from the first number, aligner_seed_policy.cpp:438-441 */ }
         else if (a == "--np") o.np = atoi(next()); else if (a == "--rdg") two(next(), o.rdg_const, o.rdg_linear);
         else if (a == "--rfg") two(next(), o.rfg_const, o.rfg_linear); else if (a == "--ignore-quals") o.ignore_quals = 1;
         else if (a == "--nofw") o.nofw = 1; else if (a == "--norc") o.norc = 1;

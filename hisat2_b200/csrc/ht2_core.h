@@ -25,9 +25,10 @@
 #define HT2_MAX_PHITS 64
 #define HT2_MAX_GHITS 24
 #define HT2_POOL 40
-#define HT2_MAX_SEARCHED 96
-#define HT2_MAX_RES 32
-#define HT2_MAX_PAIRS 48
+#define HT2_SEARCHED_BYTES 24576   /* ~600 searched hits (40 B typical) for both mates */
+
+#define HT2_MAX_RES 64
+#define HT2_MAX_PAIRS 96
 #define HT2_MAX_COORDS 24
 #define HT2_MAX_DEPTH 128
 #define HT2_DEPTH_CAP 24   /* recursion depth the workspace/stack is sized for */
@@ -71,6 +72,14 @@ struct Ht2Hit {           // GenomeHit, hi_aligner.h:431-1369
     uint32_t nedits;
     Ht2Edit  edits[HT2_MAX_EDITS];
 };
+
+struct Ht2SearchedRec {   // what GenomeHit::operator== (hi_aligner.h:1156-1183) looks at
+    uint32_t tidx, toff;
+    uint16_t rdoff, len, trim5, trim3;
+    uint8_t  fw, rdi;
+    uint16_t nedits;
+};
+struct Ht2SearchedEdit { uint32_t pos; uint8_t type, chr, qchr, pad; };
 
 struct Ht2BwtHit {        // BWTHit, hi_aligner.h:108-208
     uint32_t top, bot, node_top, node_bot;
@@ -147,7 +156,10 @@ struct Ht2Work {
     uint32_t    nGenomeHits;
     Ht2Hit      pool[HT2_POOL];             // GenomeHit temporaries (stack)
     uint32_t    poolTop;
-    Ht2Hit      searched[2][HT2_MAX_SEARCHED]; // _hits_searched
+    // _hits_searched (hi_aligner.h:6898-6922) as compact records in one arena shared by both
+    // mates: exactly the fields GenomeHit::operator== compares (Ht2SearchedRec + 8 B per edit)
+    alignas(8) uint8_t searched[HT2_SEARCHED_BYTES];
+    uint32_t    searchedTop;                // bytes used
     uint32_t    nSearched[2];
     Ht2Res      res[2][HT2_MAX_RES];        // rs1u_/rs2u_ of AlnSinkWrap
     uint32_t    nRes[2];
@@ -1195,12 +1207,39 @@ struct Ht2Aligner {
     }
     // isSearched / addSearched (hi_aligner.h:6898-6922)
     HT2_NI bool isSearched(const Ht2Hit& hit, uint32_t rdi) const {
-        for (uint32_t i = 0; i < W->nSearched[rdi]; i++) if (hitEq(W->searched[rdi][i], hit)) return true;
+        uint32_t off = 0;
+        const uint32_t top = W->searchedTop;
+        while (off < top) {
+            const Ht2SearchedRec& r = *(const Ht2SearchedRec*)(W->searched + off);
+            const uint32_t ne = r.nedits;
+            const Ht2SearchedEdit* ed = (const Ht2SearchedEdit*)(W->searched + off + sizeof(Ht2SearchedRec));
+            off += (uint32_t)sizeof(Ht2SearchedRec) + ne * (uint32_t)sizeof(Ht2SearchedEdit);
+            if (r.rdi != rdi || r.toff != hit.toff || r.tidx != hit.tidx || (r.fw != 0) != (hit.fw != 0) || r.rdoff != hit.rdoff ||
+                r.len != hit.len || r.trim5 != hit.trim5 || r.trim3 != hit.trim3 || ne != hit.nedits) continue;
+            bool same = true;
+            for (uint32_t i = 0; i < ne && same; i++) {   // GenomeHit::operator== with the stored hit on the left
+                const Ht2SearchedEdit& e = ed[i]; const Ht2Edit& oe = hit.edits[i];
+                if (e.type == HT2_EDIT_READ_GAP) { if (oe.type != HT2_EDIT_READ_GAP) same = false; }
+                else if (e.type == HT2_EDIT_REF_GAP) { if (oe.type != HT2_EDIT_REF_GAP) same = false; }
+                else if (e.type != oe.type || e.pos != oe.pos || e.chr != oe.chr || e.qchr != oe.qchr) same = false;
+            }
+            if (same) return true;
+        }
         return false;
     }
     HT2_NI void addSearched(const Ht2Hit& hit, uint32_t rdi) {
-        if (W->nSearched[rdi] >= HT2_MAX_SEARCHED) { W->err |= HT2_ERR_SEARCHED; return; }
-        copyHit(W->searched[rdi][W->nSearched[rdi]++], hit);
+        const uint32_t need = (uint32_t)sizeof(Ht2SearchedRec) + hit.nedits * (uint32_t)sizeof(Ht2SearchedEdit);
+        if (W->searchedTop + need > HT2_SEARCHED_BYTES) { W->err |= HT2_ERR_SEARCHED; return; }
+        Ht2SearchedRec& r = *(Ht2SearchedRec*)(W->searched + W->searchedTop);
+        r.tidx = hit.tidx; r.toff = hit.toff; r.rdoff = (uint16_t)hit.rdoff; r.len = (uint16_t)hit.len;
+        r.trim5 = (uint16_t)hit.trim5; r.trim3 = (uint16_t)hit.trim3; r.fw = hit.fw ? 1 : 0; r.rdi = (uint8_t)rdi;
+        r.nedits = (uint16_t)hit.nedits;
+        Ht2SearchedEdit* ed = (Ht2SearchedEdit*)(W->searched + W->searchedTop + sizeof(Ht2SearchedRec));
+        for (uint32_t i = 0; i < hit.nedits; i++) {
+            ed[i].pos = hit.edits[i].pos; ed[i].type = hit.edits[i].type; ed[i].chr = hit.edits[i].chr; ed[i].qchr = hit.edits[i].qchr; ed[i].pad = 0;
+        }
+        W->searchedTop += need;
+        W->nSearched[rdi]++;
     }
 
     // ---- policy --------------------------------------------------------------

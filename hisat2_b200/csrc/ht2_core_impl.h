@@ -584,6 +584,7 @@ HT2_NI void Ht2Aligner::go()
         }
         W->nSearched[rdi] = 0;
     }
+    W->searchedTop = 0;
     W->nGenomeHits = 0;
     W->poolTop = 0;
     W->concordInspected[0] = W->concordInspected[1] = 0;

@@ -164,6 +164,65 @@ bool ht2_read_fasta(const char* path, std::vector<Ht2HostRead>& out, int mate, s
     return true;
 }
 
+// FastqPatternSource::parse (pat.cpp:1030-1290) for well-formed 4-line Phred+33 records:
+// '@name', bases ('.' reads as N, letters only), '+...', qualities kept as raw ASCII.
+bool ht2_read_fastq(const char* path, std::vector<Ht2HostRead>& out, int mate, std::string& err)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) { err = std::string("could not open reads file ") + path; return false; }
+    std::vector<char> buf;
+    {
+        fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+        buf.resize((size_t)sz);
+        if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); err = "short read"; return false; }
+        fclose(f);
+    }
+    size_t p = 0, n = buf.size();
+    uint64_t readCnt = 0;
+    auto line = [&](std::string& o) {
+        o.clear();
+        while (p < n && buf[p] != '\n') { if (buf[p] != '\r') o.push_back(buf[p]); p++; }
+        if (p < n) p++;
+    };
+    std::string l1, l2, l3, l4;
+    while (p < n) {
+        while (p < n && (buf[p] == '\n' || buf[p] == '\r')) p++;
+        if (p >= n) break;
+        line(l1); line(l2); line(l3); line(l4);
+        if (l1.empty() || l1[0] != '@' || l3.empty() || l3[0] != '+') { err = "reads file does not look like a FASTQ file"; return false; }
+        Ht2HostRead r;
+        r.mate = mate;
+        r.name = l1.substr(1);
+        for (size_t i = 0; i < l2.size(); i++) {
+            int c = (unsigned char)l2[i];
+            if (c == '.') c = 'N';
+            if (isalpha(c)) r.seq.push_back(asc2dna(c));
+        }
+        if (l4.size() < r.seq.size()) { err = "fewer quality values than bases for read " + r.name; return false; }
+        if (l4.size() > r.seq.size()) { err = "more quality values than bases for read " + r.name; return false; }
+        for (size_t i = 0; i < r.seq.size(); i++) {
+            if ((unsigned char)l4[i] < 33) { err = "quality value below Phred+33 range in read " + r.name; return false; }
+            r.qual.push_back((uint8_t)l4[i]);
+        }
+        if (r.name.empty()) r.name = std::to_string(readCnt);
+        readCnt++;
+        if (r.seq.empty()) continue;
+        out.push_back(r);
+    }
+    return true;
+}
+
+// FASTA or FASTQ by the first record character (the CLI's -f / -q select explicitly).
+bool ht2_read_reads(const char* path, std::vector<Ht2HostRead>& out, int mate, std::string& err)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) { err = std::string("could not open reads file ") + path; return false; }
+    int c;
+    while ((c = fgetc(f)) != EOF && (c == '\n' || c == '\r')) {}
+    fclose(f);
+    return c == '@' ? ht2_read_fastq(path, out, mate, err) : ht2_read_fasta(path, out, mate, err);
+}
+
 // ---------------------------------------------------------------------------
 // SAM back end
 // ---------------------------------------------------------------------------

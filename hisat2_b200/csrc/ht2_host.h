@@ -46,6 +46,8 @@ void ht2_fill_read(Ht2Read& dst, const Ht2HostRead& src);
 
 // FASTA reader following FastaPatternSource::read (pat.cpp:725-849)
 bool ht2_read_fasta(const char* path, std::vector<Ht2HostRead>& out, int mate, std::string& err);
+bool ht2_read_fastq(const char* path, std::vector<Ht2HostRead>& out, int mate, std::string& err);
+bool ht2_read_reads(const char* path, std::vector<Ht2HostRead>& out, int mate, std::string& err);  // by first character
 
 // SAM
 void ht2_sam_header(std::string& o, const Ht2Image& img);

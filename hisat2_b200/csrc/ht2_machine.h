@@ -562,6 +562,7 @@ HT2_NI void Ht2Aligner::runTop()
             }
             W->nSearched[rdi] = 0;
         }
+        W->searchedTop = 0;
         W->nGenomeHits = 0; W->poolTop = 0; W->nFrames = 0;
         W->concordInspected[0] = W->concordInspected[1] = 0;
         W->found[0][0] = W->found[0][1] = 1; W->found[1][0] = W->found[1][1] = paired ? 1 : 0;

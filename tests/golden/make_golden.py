@@ -113,7 +113,84 @@ def graph():
         fo.writelines(l for l in out if int(l.split()[1]) in keep)
 
 
+def fastq():
+    """FASTQ fixture: the first 400 single-end reads and 150 pairs with seeded Phred+33 qualities
+    (bimodal: mostly 30-40, stretches of 2-15) so that quality-aware mismatch / soft-clip penalties matter."""
+    rng = np.random.default_rng(99)
+    def quals(n):
+        q = rng.integers(28, 41, n)
+        for _ in range(int(rng.integers(0, 4))):
+            a = int(rng.integers(0, n)); b = min(n, a + int(rng.integers(1, 25)))
+            q[a:b] = rng.integers(2, 16, b - a)
+        return bytes((q + 33).astype(np.uint8))
+    def conv(fa, fq, limit):
+        recs, name, seq = [], None, []
+        for l in open(os.path.join(G, fa)):
+            if l.startswith(">"):
+                if name is not None: recs.append((name, "".join(seq)))
+                name, seq = l[1:].strip(), []
+            else: seq.append(l.strip())
+        recs.append((name, "".join(seq)))
+        with open(os.path.join(G, fq), "wb") as f:
+            for name, sq in recs[:limit]:
+                f.write(b"@" + name.encode() + b"\n" + sq.encode() + b"\n+\n" + quals(len(sq)) + b"\n")
+    conv("tiny_se.fa", "tiny_se.fq", 400)
+    conv("tiny_pe_1.fa", "tiny_pe_1.fq", 150)
+    conv("tiny_pe_2.fa", "tiny_pe_2.fq", 150)
+    al = os.path.join(REF, "hisat2-align-s")
+    def sam(args, out):
+        subprocess.run([al, "--no-spliced-alignment", "-q", "-x", "tiny"] + args + ["-S", out + ".tmp"], check=True, cwd=G,
+                       stderr=subprocess.DEVNULL)
+        with open(os.path.join(G, out + ".tmp")) as fi, open(os.path.join(G, out), "w") as fo:
+            fo.writelines(l for l in fi if not l.startswith("@PG"))
+        os.remove(os.path.join(G, out + ".tmp"))
+    sam(["-U", "tiny_se.fq"], "tiny_se_fq.sam")
+    sam(["-1", "tiny_pe_1.fq", "-2", "tiny_pe_2.fq"], "tiny_pe_fq.sam")
+
+
+OPTION_CASES = [
+    # (ht2gpu_options_t fields, reference command-line flags, paired)
+    ("khits=1", ["-k", "1"], False),
+    ("khits=12", ["-k", "12"], False),
+    ("mp_max=4,mp_min=2,np=2", ["--mp", "4,2", "--np", "2"], False),
+    ("rdg_const=3,rdg_linear=2,rfg_const=4,rfg_linear=2", ["--rdg", "3,2", "--rfg", "4,2"], False),
+    # the reference reads BOTH soft-clip bounds from the first number (aligner_seed_policy.cpp:438-441)
+    ("sp_max=3,sp_min=3", ["--sp", "3,1"], False),
+    ("ignore_quals=1", ["--ignore-quals"], False),
+    ("nofw=1", ["--nofw"], False),
+    ("norc=1", ["--norc"], False),
+    ("secondary=1", ["--secondary"], False),
+    ("no_mixed=1", ["--no-mixed"], True),
+    ("no_discordant=1", ["--no-discordant"], True),
+    ("min_frag=150,max_frag=320", ["-I", "150", "-X", "320"], True),
+    ("nofw=1", ["--nofw"], True),
+    ("khits=3", ["-k", "3"], True),
+]
+
+
+def options():
+    """md5 of the reference's SAM (minus @PG) for every option case -> option_matrix.json."""
+    import hashlib, json
+    al = os.path.join(REF, "hisat2-align-s")
+    out = []
+    for opts, flags, paired in OPTION_CASES:
+        inp = ["-1", "tiny_pe_1.fq", "-2", "tiny_pe_2.fq"] if paired else ["-U", "tiny_se.fq"]
+        subprocess.run([al, "--no-spliced-alignment", "-q", "-x", "tiny"] + flags + inp + ["-S", "opt.tmp"], check=True, cwd=G,
+                       stderr=subprocess.DEVNULL)
+        data = b"".join(l for l in open(os.path.join(G, "opt.tmp"), "rb") if not l.startswith(b"@PG"))
+        out.append({"options": opts, "flags": flags, "paired": paired, "md5": hashlib.md5(data).hexdigest(),
+                    "records": data.count(b"\n")})
+    os.remove(os.path.join(G, "opt.tmp"))
+    json.dump(out, open(os.path.join(G, "option_matrix.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "options":
+        options()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fastq":
+        fastq()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "graph":
         graph()
         sys.exit(0)

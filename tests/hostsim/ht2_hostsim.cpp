@@ -91,11 +91,32 @@ int main(int argc, char** argv) {
     // usage: ht2_hostsim index reads.fa out.sam            (unpaired)
     //        ht2_hostsim index reads_1.fa out.sam reads_2.fa (paired, --fr)
     const bool pairedMode = argc > 4;
-    if (!ht2_read_fasta(argv[2], reads, pairedMode ? 1 : 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    if (!ht2_read_reads(argv[2], reads, pairedMode ? 1 : 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     std::vector<Ht2HostRead> reads2;
-    if (pairedMode && !ht2_read_fasta(argv[4], reads2, 2, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    if (pairedMode && !ht2_read_reads(argv[4], reads2, 2, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     Ht2Params P;
     ht2_default_params(P, *img, true);
+    // HT2_OPTS="khits=1,mp_max=4,...": the ht2gpu_options_t fields, mapped like applyOptions (ht2_gpu.cu)
+    if (const char* os = getenv("HT2_OPTS")) {
+        std::string o(os); size_t p0 = 0;
+        bool kseedsGiven = false;
+        while (p0 < o.size()) {
+            size_t c = o.find(',', p0); if (c == std::string::npos) c = o.size();
+            std::string kv = o.substr(p0, c - p0); p0 = c + 1;
+            size_t e = kv.find('='); if (e == std::string::npos) continue;
+            std::string k = kv.substr(0, e); int v = atoi(kv.c_str() + e + 1);
+            if (k == "khits") P.khits = (uint32_t)v; else if (k == "max_seeds") { P.kseeds = (uint32_t)v; kseedsGiven = true; }
+            else if (k == "secondary") P.secondary = v; else if (k == "mp_max") P.mmpMax = v; else if (k == "mp_min") P.mmpMin = v;
+            else if (k == "sp_max") P.scpMax = v; else if (k == "sp_min") P.scpMin = v; else if (k == "np") P.npen = v;
+            else if (k == "rdg_const") P.rdGapConst = v; else if (k == "rdg_linear") P.rdGapLinear = v;
+            else if (k == "rfg_const") P.rfGapConst = v; else if (k == "rfg_linear") P.rfGapLinear = v;
+            else if (k == "ignore_quals") P.mmcostConstant = v; else if (k == "nofw") P.nofw = v; else if (k == "norc") P.norc = v;
+            else if (k == "min_frag") P.minFrag = (uint32_t)v; else if (k == "max_frag") P.maxFrag = (uint32_t)v;
+            else if (k == "no_mixed") P.mixed = v ? 0 : 1; else if (k == "no_discordant") P.discord = v ? 0 : 1;
+            else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
+        }
+        if (!kseedsGiven) P.kseeds = P.khits * 2 > 5 ? P.khits * 2 : 5;
+    }
     std::string sam;
     ht2_sam_header(sam, *img);
     Ht2Work* W = new Ht2Work();

@@ -56,6 +56,32 @@ def test_host_seed_search_matches_reference_dump(hostsim_bin):
     assert graph.count("\nG ") > 3000 and any(l.split()[6] != "0" for l in graph.splitlines() if l.startswith("G "))
 
 
+def test_host_state_machine_fastq_qualities(hostsim_bin, tmp_path):
+    """FASTQ input with low-quality stretches: quality-aware mismatch and soft-clip penalties
+    (Scoring::mm / COST_MODEL_QUAL, scoring.h:117-128), SE and PE, byte-identical SAM."""
+    for args, gold in ((["tiny_se.fq"], "tiny_se_fq.sam"), (["tiny_pe_1.fq", "tiny_pe_2.fq"], "tiny_pe_fq.sam")):
+        out = str(tmp_path / gold)
+        cmd = [hostsim_bin, "tiny", args[0], out] + args[1:]
+        subprocess.run(cmd, cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL)
+        assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read())
+
+
+def test_host_state_machine_option_matrix(hostsim_bin, tmp_path):
+    """Every option of the reference's command line that reaches the path (-k, --mp, --np, --rdg, --rfg,
+    --sp, --ignore-quals, --nofw/--norc, --secondary, --no-mixed, --no-discordant, -I/-X) against the md5
+    of the unmodified reference's SAM for the same flags (tests/golden/option_matrix.json)."""
+    import hashlib, json
+    cases = json.load(open(os.path.join(GOLDEN, "option_matrix.json")))
+    assert len(cases) >= 14
+    for c in cases:
+        out = str(tmp_path / "o.sam")
+        args = ["tiny_pe_1.fq", out, "tiny_pe_2.fq"] if c["paired"] else ["tiny_se.fq", out]
+        subprocess.run([hostsim_bin, "tiny"] + args, cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL,
+                       env=dict(os.environ, HT2_OPTS=c["options"]))
+        got = hashlib.md5(b"\n".join(sam_lines(open(out, "rb").read())) + b"\n").hexdigest()
+        assert got == c["md5"], c
+
+
 def test_abi_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))

@@ -113,6 +113,49 @@ def test_in_kernel_seed_search_matches_oracle(h2, tiny, oracle_bin):
     assert checked > 150
 
 
+def test_fastq_qualities_match_golden_reference_sam(h2, tiny):
+    """FASTQ reads with low-quality stretches (quality-aware penalties), SE and PE."""
+    b = h2.ReadBatch.from_fastq(os.path.join(GOLDEN, "tiny_se.fq"))
+    sam, _ = gpu_sam(tiny, b)
+    assert sam_lines(sam) == sam_lines(open(os.path.join(GOLDEN, "tiny_se_fq.sam"), "rb").read())
+    b = h2.ReadBatch.from_fastq(os.path.join(GOLDEN, "tiny_pe_1.fq"), path2=os.path.join(GOLDEN, "tiny_pe_2.fq"))
+    sam, _ = gpu_sam(tiny, b)
+    assert sam_lines(sam) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe_fq.sam"), "rb").read())
+
+
+def _option_cases():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "option_matrix.json")))
+
+
+@pytest.mark.parametrize("case", range(14))
+def test_option_matrix_matches_reference(h2, case, tmp_path):
+    """Same option names and meaning as the reference's command line (-k, --mp, --np, --rdg, --rfg, --sp,
+    --ignore-quals, --nofw/--norc, --secondary, --no-mixed, --no-discordant, -I/-X): md5 of the SAM equals
+    the committed md5 of the unmodified reference's output, and the reference is re-run on this box when
+    oracle/_ref is present."""
+    import hashlib
+    c = _option_cases()[case]
+    opts = {k: int(v) for k, v in (kv.split("=") for kv in c["options"].split(","))}
+    idx = h2.Index(os.path.join(GOLDEN, "tiny"), **opts)
+    if c["paired"]:
+        f1, f2 = os.path.join(GOLDEN, "tiny_pe_1.fq"), os.path.join(GOLDEN, "tiny_pe_2.fq")
+        batch = h2.ReadBatch.from_fastq(f1, path2=f2)
+        inp = ["-1", f1, "-2", f2]
+    else:
+        f1 = os.path.join(GOLDEN, "tiny_se.fq")
+        batch = h2.ReadBatch.from_fastq(f1)
+        inp = ["-U", f1]
+    sam, _ = gpu_sam(idx, batch)
+    assert hashlib.md5(b"\n".join(sam_lines(sam)) + b"\n").hexdigest() == c["md5"]
+    if os.path.exists(REFBIN):
+        out = str(tmp_path / "ref.sam")
+        subprocess.run([REFBIN, "--no-spliced-alignment", "-q", "-x", os.path.join(GOLDEN, "tiny")] + c["flags"] + inp + ["-S", out],
+                       check=True, stderr=subprocess.DEVNULL)
+        assert sam_lines(sam) == sam_lines(open(out, "rb").read())
+    idx.close()
+
+
 KEEP = set(list(range(0, 100)) + list(range(250, 350)) + list(range(500, 600)))
 
 
@@ -225,7 +268,7 @@ def test_full_size_properties_1M_reads(h2, chr22):
     assert int((r1.reads["err"] != 0).sum()) == 0
     n_al = (r1.reads["n_aln"][:, 0] > 0).sum()
     assert n_al >= 0.99 * len(codes)
-    assert (r1.reads["n_aln"][:, 0] <= 32).all()
+    assert (r1.reads["n_aln"][:, 0] <= 64).all()
     a = r1.alns
     assert (a["score"] <= 0).all() and (a["score"] >= -20).all()       # minsc(101) = -20
     assert (a["ref_extent"] > 0).all() and (a["toff"] + a["ref_extent"] <= 1000000).all()
