@@ -168,7 +168,8 @@ def reference_arm(args, rank, world):
                  "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "reference",
                                   "sample": "%d reads per step, hisat2-align-s -p %d --reorder, wall clock incl. index load and SAM to /dev/null" % (n, threads)},
                  "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                 "gpu_launches": 0})
+                 "sam_backend": sam_info,
+        "gpu_launches": 0})
     line["config"]["host_threads"] = threads
     line["config"]["host_cores"] = os.cpu_count()
     print(json.dumps(line))
@@ -259,6 +260,16 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     barrier()
+    # ---- informational: SAM text for one batch on the host back end (outside the timed regions)
+    sam_info = None
+    if rank == 0:
+        r = idx.align(batch)
+        t1 = time.perf_counter()
+        txt = idx.format_sam(batch, r)
+        sam_info = {"ms_per_step": (time.perf_counter() - t1) * 1000.0, "bytes": len(txt), "host_threads": min(64, os.cpu_count() or 1),
+                    "note": "ht2gpu_format_sam (selectByScore, MAPQ, CIGAR/MD:Z, SAM lines) for one batch; not part of value/e2e"}
+        del txt
+        r.close()
     tk = torch.tensor([kernel_ms, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(alg_bytes), float(n_lf), float(aligned), float(launches), float(err_reads)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -299,6 +310,7 @@ def main():
                    "capacity_error_reads": int(tot[4])},
         "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "device_ms_per_step": e2e_dev_ms / args.steps},
+        "sam_backend": sam_info,
         "gpu_launches": int(tot[3]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ht2_align_pool_kernel<8,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -1258,19 +1259,26 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
                                  const ht2gpu_result_batch_t* res, char** out, size_t* out_len)
 {
     if (!h || !b || !res || !names || !out) return HT2GPU_ERR_ARG;
-    std::string sam;
-    sam.reserve((size_t)b->n_reads * 400);
-    const char* nm = names;
     const uint32_t units = b->paired ? b->n_reads / 2 : b->n_reads;
+    // read-name table (names are '\0'-terminated, concatenated)
+    std::vector<const char*> nameOf((size_t)b->n_reads + 1);
+    {
+        const char* nm = names;
+        for (uint32_t i = 0; i < b->n_reads; i++) { nameOf[i] = nm; nm += strlen(nm) + 1; }
+    }
     auto mkRead = [&](uint32_t i, int mate, Ht2HostRead& rd) {
-        rd.name = nm; nm += rd.name.size() + 1;
+        rd.name = nameOf[i];
         rd.mate = mate;
         const uint8_t* s = b->seq + b->offs[i];
         uint32_t len = (uint32_t)(b->offs[i + 1] - b->offs[i]);
         rd.seq.assign(s, s + len);
         if (b->qual) rd.qual.assign(b->qual + b->offs[i], b->qual + b->offs[i] + len); else rd.qual.assign(len, (uint8_t)'I');
     };
-    for (uint32_t u = 0; u < units; u++) {
+    // Reads are independent (each carries its own RNG state), so the back end runs on
+    // host threads over contiguous unit ranges and the chunks are concatenated in order.
+    auto doRange = [&](uint32_t u0, uint32_t u1, std::string& sam) {
+      sam.reserve((size_t)(u1 - u0) * (b->paired ? 800 : 400));
+      for (uint32_t u = u0; u < u1; u++) {
         Ht2HostRead rd1, rd2;
         if (b->paired) { mkRead(2 * u, 1, rd1); mkRead(2 * u + 1, 2, rd2); }
         else mkRead(u, 0, rd1);
@@ -1286,7 +1294,7 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
                 const ht2gpu_aln_t& al = res->alns[a];
                 Ht2Res r;
                 r.tidx = al.tidx; r.toff = al.toff; r.fw = al.fw; r.score = al.score;
-                r.rdlen = (uint32_t)((m == 0 || !b->paired) ? (m == 0 ? rd1.seq.size() : rd1.seq.size()) : rd2.seq.size());
+                r.rdlen = (uint32_t)((m == 0 || !b->paired) ? rd1.seq.size() : rd2.seq.size());
                 r.trim5p = al.trim5; r.trim3p = al.trim3; r.rfextent = al.ref_extent; r.nedits = al.n_edits;
                 for (uint32_t e = 0; e < al.n_edits && e < HT2_MAX_EDITS; e++) {
                     const ht2gpu_edit_t& se = res->edits[al.edit_off + e];
@@ -1300,9 +1308,28 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
             o.pairs.push_back(std::make_pair(res->pairs[2 * (rr.pair_off + k)], res->pairs[2 * (rr.pair_off + k) + 1]));
         if (b->paired) ht2_finish_paired(sam, *h->img, h->P, rd1, rd2, f1, f2, o);
         else ht2_finish_unpaired(sam, *h->img, h->P, rd1, f1, o);
+      }
+    };
+    unsigned nth = std::thread::hardware_concurrency();
+    if (const char* e = getenv("HT2GPU_THREADS")) nth = (unsigned)atoi(e);
+    if (nth > 64) nth = 64;
+    if (nth < 1 || units < 4096) nth = 1;
+    std::vector<std::string> parts(nth);
+    if (nth == 1) doRange(0, units, parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth; t++) {
+            const uint32_t u0 = (uint32_t)((uint64_t)units * t / nth), u1 = (uint32_t)((uint64_t)units * (t + 1) / nth);
+            th.emplace_back([&, t, u0, u1]() { doRange(u0, u1, parts[t]); });
+        }
+        for (auto& x : th) x.join();
     }
-    char* p = (char*)malloc(sam.size() + 1);
-    memcpy(p, sam.data(), sam.size()); p[sam.size()] = 0;
-    *out = p; if (out_len) *out_len = sam.size();
+    size_t total = 0;
+    for (auto& s2 : parts) total += s2.size();
+    char* p = (char*)malloc(total + 1);
+    size_t at = 0;
+    for (auto& s2 : parts) { memcpy(p + at, s2.data(), s2.size()); at += s2.size(); }
+    p[total] = 0;
+    *out = p; if (out_len) *out_len = total;
     return HT2GPU_OK;
 }
