@@ -168,8 +168,7 @@ def reference_arm(args, rank, world):
                  "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "reference",
                                   "sample": "%d reads per step, hisat2-align-s -p %d --reorder, wall clock incl. index load and SAM to /dev/null" % (n, threads)},
                  "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                 "sam_backend": sam_info,
-        "gpu_launches": 0})
+                 "gpu_launches": 0})
     line["config"]["host_threads"] = threads
     line["config"]["host_cores"] = os.cpu_count()
     print(json.dumps(line))
