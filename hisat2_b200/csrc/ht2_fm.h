@@ -59,26 +59,6 @@ HT2_HD uint64_t ht2_rep2(int c) {
     return 0x5555555555555555ull * (uint64_t)c;
 }
 
-// # occurrences of 2-bit code c among the first n (<=32) chars of word w.
-HT2_HD int ht2_count_word(uint64_t w, int c, uint32_t n) {
-    uint64_t x = ~(w ^ ht2_rep2(c));
-    x = x & (x >> 1) & 0x5555555555555555ull;
-    if (n < 32) x &= ((1ull << (2 * n)) - 1);
-    return HT2_POPC64(x);
-}
-
-// Occurrences of c in the first charOff chars of a side
-// (GFM::countUpTo, gfm.h:3166-3226; countInU64 gfm.h:566-578).
-HT2_HD uint32_t ht2_count_upto(const uint8_t* side, uint32_t charOff, int c) {
-    const uint64_t* w = (const uint64_t*)side;
-    uint32_t cnt = 0;
-    uint32_t full = charOff >> 5;
-    for (uint32_t i = 0; i < full; i++) cnt += ht2_count_word(w[i], c, 32);
-    uint32_t rem = charOff & 31;
-    if (rem) cnt += ht2_count_word(w[full], c, rem);
-    return cnt;
-}
-
 // ---- linear indexes: 32-byte rank sides (ht2_image.h) ----------------------
 struct HT2_ALIGN16 Ht2SideBwt { uint64_t lo, hi; };   // 64 BW chars
 
@@ -180,82 +160,6 @@ HT2_HD void ht2_ftab_lohi(const Ht2Fm<IT>& fm, const uint8_t* seq, uint32_t off,
     if (lo > fm.g->ftabCmp) lo = fm.eftab[(uint32_t)((IT)(lo ^ Ht2Fm<IT>::imax())) * 2];
     top = hi;
     bot = lo;
-}
-
-// ---- graph (GBWT) primitives: F and M bit arrays -----------------------
-// Side layout (graph): [BWT sideGbwtSz/2.. wait see ht2_image/SURVEY a3]:
-//   [0, sideGbwtSz/2)            2-bit BW chars
-//   [sideGbwtSz/2, 3/4 sideGbwtSz) F bits
-//   [3/4 sideGbwtSz, sideGbwtSz)   M bits
-//   then F_loc, M_occ, A, C, G, T as IT.
-
-// # set bits among the first n bits of the bit array starting at 'bits'
-// (GFM::countUpTo_bits gfm.h:3384-3447).
-HT2_HD uint32_t ht2_count_bits(const uint8_t* bits, uint32_t n) {
-    uint32_t cnt = 0;
-    uint32_t i = 0;
-    for (; i + 64 <= n; i += 64) {
-        uint64_t w = 0;
-        for (int b = 0; b < 8; b++) w |= (uint64_t)bits[(i >> 3) + b] << (8 * b);
-        cnt += HT2_POPC64(w);
-    }
-    uint32_t rem = n - i;
-    if (rem) {
-        uint64_t w = 0;
-        uint32_t nb = (rem + 7) >> 3;
-        for (uint32_t b = 0; b < nb; b++) w |= (uint64_t)bits[(i >> 3) + b] << (8 * b);
-        w &= (rem == 64) ? ~0ull : ((1ull << rem) - 1);
-        cnt += HT2_POPC64(w);
-    }
-    return cnt;
-}
-
-// rank1(M, row): # set M bits in rows [0,row)  (GFM::rank_M gfm.h:4100,
-// countMSide gfm.h:3146-3160).
-template <typename IT>
-HT2_HD uint32_t ht2_rank_M(const Ht2Fm<IT>& fm, uint32_t row) {
-    const Ht2Gfm* g = fm.g;
-    uint32_t sideNum = row / g->sideGbwtLen;
-    uint32_t charOff = row - sideNum * g->sideGbwtLen;
-    const uint8_t* side = fm.gfm + (uint64_t)sideNum * g->sideSz;
-    uint32_t cnt = ht2_count_bits(side + ((g->sideGbwtSz * 3) >> 2), charOff);
-    const IT* tr = (const IT*)(side + g->sideGbwtSz);
-    return (uint32_t)(IT)(tr[1] + cnt);
-}
-
-// Row of the count-th (>=1) set F bit at or after 'row'
-// (GFM::select_F gfm.h:4113-4168).
-template <typename IT>
-HT2_HD uint32_t ht2_select_F(const Ht2Fm<IT>& fm, uint32_t row, uint32_t count) {
-    const Ht2Gfm* g = fm.g;
-    uint32_t sideNum = row / g->sideGbwtLen;
-    uint32_t charOff = row - sideNum * g->sideGbwtLen;
-    while (true) {
-        const uint8_t* fbits = fm.gfm + (uint64_t)sideNum * g->sideSz + (g->sideGbwtSz >> 1);
-        while (charOff < g->sideGbwtLen) {
-            uint32_t by = charOff >> 3, bp = charOff & 7;
-            uint32_t bitsLeft = g->sideGbwtLen - charOff;
-            uint32_t take = 64 - bp;
-            if (take > bitsLeft) take = bitsLeft;
-            uint64_t w = 0;
-            uint32_t nb = (bp + take + 7) >> 3;
-            for (uint32_t b = 0; b < nb && b < 8; b++) w |= (uint64_t)fbits[by + b] << (8 * b);
-            w >>= bp;
-            if (nb > 8) w |= (uint64_t)fbits[by + 8] << (64 - bp);
-            if (take < 64) w &= ((1ull << take) - 1);
-            uint32_t pc = HT2_POPC64(w);
-            if (pc >= count) {
-                // locate the count-th set bit inside w
-                for (uint32_t k = 1; k < count; k++) w &= (w - 1);
-                uint32_t pos = (uint32_t)HT2_FFS64(w) - 1;
-                return sideNum * g->sideGbwtLen + charOff + pos;
-            }
-            count -= pc;
-            charOff += take;
-        }
-        sideNum++;
-        charOff = 0;
-    }
 }
 
 #endif // HT2_FM_H_

@@ -9,9 +9,12 @@
 //     row  = select1(F, node + 1)                    (node -> its first BW row)
 // and ranges carry both [top,bot) rows and [node_top,node_bot) nodes.
 //
-// Graph indexes stay in the .ht2 side format inside the image (a3):
-//   [sideGbwtSz/2 B 2-bit BW chars][sideGbwtSz/4 B F bits][sideGbwtSz/4 B M bits]
-//   [F_loc][M_occ][A][C][G][T]                        (entries are IT wide)
+// Inside the image graph indexes are re-laid as 64-byte rank sides of 64 rows (ht2_image.h,
+// ht2_index.cpp:relayGraph) -- the .ht2 format keeps 208 rows per 128-byte side (a3), i.e. a
+// div/mod per rank and byte loops over 26-byte bit arrays:
+//   [16 B BW chars][u64 F][u64 M][u32 occ[4] incl. fchr][u32 M_occ][u32 F_loc][pad]
+// M_occ = rank1(M, sideStart); F_loc = select1(F, M_occ).  One search boundary touches the
+// character side of the row, the M side of the LF result and the F side(s) at F_loc.
 // Reference functions restated here: GFM::mapGLF (gfm.h:3759-3837), mapGLF1
 // (:3957-4095), mapLF1 (:3889-3950), countBt2Side (:2958-2999), rank_M (:4100),
 // countMSide (:3146), select_F (:4113-4168), getInEdgeCount (:4172-4210),
@@ -21,104 +24,102 @@
 
 #include "ht2_fm.h"
 
-template <typename IT>
-struct Ht2GLoc {
-    const uint8_t* side;
-    uint32_t sideNum, charOff;
+struct HT2_ALIGN16 Ht2GSide {
+    Ht2SideBwt bwt;        // 64 BW chars
+    uint64_t   F, M;       // one bit per row
+    uint32_t   occ[4];     // fchr[c] + #c in rows [0, sideStart), '$' rows not counted
+    uint32_t   M_occ;      // rank1(M, sideStart)
+    uint32_t   F_loc;      // select1(F, M_occ): row of the M_occ-th set F bit
+    uint32_t   pad[2];
 };
 
 template <typename IT>
-HT2_HD Ht2GLoc<IT> ht2g_locate(const Ht2Fm<IT>& fm, uint32_t row) {
-    Ht2GLoc<IT> l;
-    l.sideNum = row / fm.g->sideGbwtLen;
-    l.charOff = row - l.sideNum * fm.g->sideGbwtLen;
-    l.side = fm.gfm + (uint64_t)l.sideNum * fm.g->sideSz;
-    return l;
+HT2_HD const Ht2GSide* ht2g_side(const Ht2Fm<IT>& fm, uint32_t row) {
+    return (const Ht2GSide*)(fm.gfm + ((uint64_t)(row >> HT2_SIDE_SHIFT) << 6));
 }
 
 template <typename IT>
 HT2_HD int ht2g_rowL(const Ht2Fm<IT>& fm, uint32_t row) {
-    const Ht2GLoc<IT> l = ht2g_locate(fm, row);
-    return (l.side[l.charOff >> 2] >> ((l.charOff & 3) << 1)) & 3;
+    return ht2_side_char(ht2g_side(fm, row)->bwt, row & (HT2_SIDE_CHARS - 1));
 }
 
 template <typename IT>
 HT2_HD bool ht2g_is_zoff(const Ht2Fm<IT>& fm, uint32_t row) {
-    for (uint32_t i = 0; i < fm.g->nzOffs; i++) if (row == fm.zoffs[i]) return true;
+    if (row == fm.z0) return true;
+    for (uint32_t i = 1; i < fm.g->nzOffs; i++) if (row == fm.zoffs[i]) return true;
     return false;
 }
 
 // fchr[c] + occ(c, row): countBt2Side with the '$' rows (several on a graph) not counted as 'A'.
 template <typename IT>
 HT2_HD uint32_t ht2g_lf(const Ht2Fm<IT>& fm, uint32_t row, int c) {
-    const Ht2Gfm* g = fm.g;
-    const Ht2GLoc<IT> l = ht2g_locate(fm, row);
-    uint32_t cnt = ht2_count_upto(l.side, l.charOff, c);
+    const Ht2GSide* sd = ht2g_side(fm, row);
+    const uint32_t charOff = row & (HT2_SIDE_CHARS - 1);
+    const Ht2SideBwt w = sd->bwt;
+    uint32_t cnt = sd->occ[c] + ht2_count_side(w, c, charOff);
     if (c == 0) {
-        const uint32_t sideStart = row - l.charOff;
-        for (uint32_t i = 0; i < g->nzOffs; i++) {
-            const uint32_t z = fm.zoffs[i];
-            if (z >= sideStart && z < row) cnt--;
-        }
+        const uint32_t sideStart = row - charOff;
+        if ((uint32_t)(fm.z0 - sideStart) < charOff) cnt--;
+        for (uint32_t i = 1; i < fm.g->nzOffs; i++) if ((uint32_t)((uint32_t)fm.zoffs[i] - sideStart) < charOff) cnt--;
     }
-    const IT* acgt = (const IT*)(l.side + g->sideGbwtSz + 2 * sizeof(IT));
-    return (uint32_t)(IT)(acgt[c] + cnt + g->fchr[c]);
+    return (uint32_t)(IT)cnt;
 }
 
 // rank1(M, row) = # set M bits in rows [0,row).
 template <typename IT>
 HT2_HD uint32_t ht2g_rank_M(const Ht2Fm<IT>& fm, uint32_t row) {
-    const Ht2Gfm* g = fm.g;
-    const Ht2GLoc<IT> l = ht2g_locate(fm, row);
-    const uint32_t cnt = ht2_count_bits(l.side + (g->sideGbwtSz - (g->sideGbwtSz >> 2)), l.charOff);
-    const IT* tr = (const IT*)(l.side + g->sideGbwtSz);
-    return (uint32_t)(IT)(tr[1] + cnt);
+    const Ht2GSide* sd = ht2g_side(fm, row);
+    const uint32_t k = row & (HT2_SIDE_CHARS - 1);
+    return (uint32_t)(IT)(sd->M_occ + (uint32_t)HT2_POPC64(sd->M & ((1ull << k) - 1)));
 }
 
-HT2_HD int ht2g_bit(const uint8_t* bits, uint32_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
+// position (0-based) of the n-th (1-based, n <= popcount) set bit of x
+HT2_HD uint32_t ht2g_select64(uint64_t x, uint32_t n) {
+    uint32_t pos = 0;
+    uint32_t lo = (uint32_t)x, c = (uint32_t)HT2_POPC64((uint64_t)lo);
+    if (n > c) { n -= c; pos = 32; lo = (uint32_t)(x >> 32); }
+    c = (uint32_t)HT2_POPC64((uint64_t)(lo & 0xffffu)); if (n > c) { n -= c; pos += 16; lo >>= 16; } lo &= 0xffffu;
+    c = (uint32_t)HT2_POPC64((uint64_t)(lo & 0xffu));   if (n > c) { n -= c; pos += 8;  lo >>= 8; }  lo &= 0xffu;
+    c = (uint32_t)HT2_POPC64((uint64_t)(lo & 0xfu));    if (n > c) { n -= c; pos += 4;  lo >>= 4; }  lo &= 0xfu;
+    c = (uint32_t)HT2_POPC64((uint64_t)(lo & 0x3u));    if (n > c) { n -= c; pos += 2;  lo >>= 2; }  lo &= 0x3u;
+    if (n > (lo & 1u)) pos += 1;
+    return pos;
+}
 
 // Row of the count-th (>= 1) set F bit at or after 'row' (select_F walks forward across sides).
 template <typename IT>
 HT2_HD uint32_t ht2g_select_F(const Ht2Fm<IT>& fm, uint32_t row, uint32_t count) {
-    const Ht2Gfm* g = fm.g;
-    Ht2GLoc<IT> l = ht2g_locate(fm, row);
+    uint32_t s = row >> HT2_SIDE_SHIFT;
+    const uint32_t lastSide = fm.g->numSides;    // one zeroed slack side follows the last side
+    uint64_t bits = ((const Ht2GSide*)(fm.gfm + ((uint64_t)s << 6)))->F >> (row & (HT2_SIDE_CHARS - 1));
+    uint32_t base = row;
     while (true) {
-        const uint8_t* fbits = l.side + (g->sideGbwtSz >> 1);
-        // whole bytes first, then bit by bit inside the byte that holds the answer
-        while (l.charOff < g->sideGbwtLen) {
-            if ((l.charOff & 7) == 0 && l.charOff + 8 <= g->sideGbwtLen) {
-                const uint32_t pc = (uint32_t)HT2_POPC64((uint64_t)fbits[l.charOff >> 3]);
-                if (pc < count) { count -= pc; l.charOff += 8; continue; }
-            }
-            if (ht2g_bit(fbits, l.charOff)) {
-                if (--count == 0) return l.sideNum * g->sideGbwtLen + l.charOff;
-            }
-            l.charOff++;
-        }
-        l.sideNum++;
-        l.charOff = 0;
-        l.side += g->sideSz;
+        const uint32_t pc = (uint32_t)HT2_POPC64(bits);
+        if (pc >= count) return base + ht2g_select64(bits, count);
+        count -= pc;
+        s++;
+        if (s > lastSide) return fm.g->gbwtLen;   // ran off the end (cannot happen on a well-formed index)
+        base = s << HT2_SIDE_SHIFT;
+        bits = ((const Ht2GSide*)(fm.gfm + ((uint64_t)s << 6)))->F;
     }
 }
 
-// Edge row r (an LF result) -> (node id, first BW row of that node); the tail
-// shared by mapGLF's top boundary and mapGLF1 (gfm.h:3786-3807, 3978-4000).
-// Also returns where select started and the M_occ it was relative to, so that
-// mapGLF1 can select the NEXT node's first row from the same start.
+// Edge row r (an LF result) -> (node id, first BW row of that node); the tail shared by mapGLF's top
+// boundary and mapGLF1 (gfm.h:3786-3807, 3978-4000).  The reference steps back a side when its
+// trailer's M_occ exceeds the node; with F_loc = select1(F, M_occ) that case is F_loc itself.
+// Also returns where a further select can start and the M_occ it is relative to, so that mapGLF1
+// selects the NEXT node's first row from the same place.
 template <typename IT>
 HT2_HD void ht2g_edge_to_node(const Ht2Fm<IT>& fm, uint32_t r, uint32_t& node, uint32_t& firstRow,
                               uint32_t& F_loc, uint32_t& M_occ) {
-    const Ht2Gfm* g = fm.g;
-    node = (uint32_t)(IT)(ht2g_rank_M(fm, r + 1) - 1);
-    Ht2GLoc<IT> l = ht2g_locate(fm, r + 1);
-    while (true) {
-        const IT* tr = (const IT*)(l.side + g->sideGbwtSz);
-        F_loc = tr[0]; M_occ = tr[1];
-        if (M_occ <= node) break;
-        l.side -= g->sideSz;       // the node's first edge lies before this side's M prefix
-    }
-    if (M_occ > 0) F_loc = (uint32_t)(IT)(F_loc + 1);
-    firstRow = (node + 1 > M_occ) ? ht2g_select_F(fm, F_loc, node + 1 - M_occ) : F_loc;
+    const Ht2GSide* sd = ht2g_side(fm, r + 1);
+    const uint32_t k = (r + 1) & (HT2_SIDE_CHARS - 1);
+    M_occ = sd->M_occ;
+    F_loc = sd->F_loc;
+    node = (uint32_t)(IT)(M_occ + (uint32_t)HT2_POPC64(sd->M & ((1ull << k) - 1)) - 1);
+    if (node + 1 == M_occ) { firstRow = F_loc; return; }                     // the M_occ-th node itself
+    const uint32_t start = M_occ > 0 ? F_loc + 1 : 0;
+    firstRow = ht2g_select_F(fm, start, node + 1 - M_occ);
 }
 
 // GFM::getInEdgeCount: for the rows [top,bot) (top is a node's first row) list
@@ -126,14 +127,11 @@ HT2_HD void ht2g_edge_to_node(const Ht2Fm<IT>& fm, uint32_t r, uint32_t& node, u
 // Returns the number of entries written (cap entries at most; excess sets overflow).
 template <typename IT>
 HT2_HD uint32_t ht2g_in_edge_count(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, uint16_t (*out)[2], uint32_t cap, bool& overflow) {
-    const Ht2Gfm* g = fm.g;
-    Ht2GLoc<IT> l = ht2g_locate(fm, top);
     uint32_t n = 0, curr = 0, num0s = 0;
-    bool first = true, curOk = false;
-    while (top < bot) {
-        const uint8_t* fbits = l.side + (g->sideGbwtSz >> 1);
-        if (first) first = false;
-        else if (ht2g_bit(fbits, l.charOff)) { curr++; num0s = 0; }
+    bool curOk = false;
+    for (uint32_t r = top + 1; r < bot; r++) {
+        const int bit = (int)((ht2g_side(fm, r)->F >> (r & (HT2_SIDE_CHARS - 1))) & 1);
+        if (bit) { curr++; num0s = 0; }
         else {
             num0s++;
             if (num0s == 1) {
@@ -142,9 +140,6 @@ HT2_HD uint32_t ht2g_in_edge_count(const Ht2Fm<IT>& fm, uint32_t top, uint32_t b
             }
             if (curOk) out[n - 1][1] = (uint16_t)num0s;
         }
-        if (l.charOff + 1 == g->sideGbwtLen) { l.sideNum++; l.charOff = 0; l.side += g->sideSz; }
-        else l.charOff++;
-        top++;
     }
     return n;
 }
@@ -156,20 +151,19 @@ template <typename IT>
 HT2_HD void ht2g_mapGLF(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c, uint32_t k,
                         uint32_t& ntop, uint32_t& nbot, uint32_t& node_top, uint32_t& node_bot,
                         uint16_t (*iedges)[2], uint32_t& niedges, bool& overflow) {
-    const Ht2Gfm* g = fm.g;
     niedges = 0;
     uint32_t t = ht2g_lf(fm, top, c);
     uint32_t b = ht2g_lf(fm, bot, c);
-    if (t + 1 >= g->gbwtLen || t >= b) { ntop = nbot = node_top = node_bot = 0; return; }
+    if (t + 1 >= fm.g->gbwtLen || t >= b) { ntop = nbot = node_top = node_bot = 0; return; }
     uint32_t F_loc, M_occ;
     ht2g_edge_to_node(fm, t, node_top, ntop, F_loc, M_occ);
     {
-        node_bot = ht2g_rank_M(fm, b);
-        const Ht2GLoc<IT> l = ht2g_locate(fm, b);
-        const IT* tr = (const IT*)(l.side + g->sideGbwtSz);
-        uint32_t bF = tr[0], bM = tr[1];
-        if (bM > 0) bF = (uint32_t)(IT)(bF + 1);
-        nbot = (node_bot + 1 > bM) ? ht2g_select_F(fm, bF, node_bot + 1 - bM) : bF;
+        const Ht2GSide* sd = ht2g_side(fm, b);
+        const uint32_t kk = b & (HT2_SIDE_CHARS - 1);
+        const uint32_t bM = sd->M_occ;
+        node_bot = (uint32_t)(IT)(bM + (uint32_t)HT2_POPC64(sd->M & ((1ull << kk) - 1)));
+        const uint32_t start = bM > 0 ? sd->F_loc + 1 : 0;
+        nbot = ht2g_select_F(fm, start, node_bot + 1 - bM);     // node_bot + 1 > bM always (gfm.h:3816)
     }
     if (node_bot - node_top <= k && node_bot - node_top < nbot - ntop)
         niedges = ht2g_in_edge_count(fm, ntop, nbot, iedges, HT2G_MAX_IEDGES, overflow);
@@ -184,7 +178,7 @@ HT2_HD void ht2g_mapGLF1c(const Ht2Fm<IT>& fm, uint32_t row, int c,
     uint32_t F_loc, M_occ;
     ht2g_edge_to_node(fm, t, node_top, ntop, F_loc, M_occ);
     node_bot = node_top + 1;
-    nbot = (node_bot + 1 > M_occ) ? ht2g_select_F(fm, F_loc, node_bot + 1 - M_occ) : F_loc;
+    nbot = ht2g_select_F(fm, M_occ > 0 ? F_loc + 1 : 0, node_bot + 1 - M_occ);   // node_bot + 1 > M_occ always
 }
 
 // GFM::mapGLF1(row, l): follow the row's own character.  Returns false on a '$' row.

@@ -28,7 +28,7 @@
 #endif
 
 #define HT2_MAGIC 0x42325448u /* "HT2B" */
-#define HT2_IMAGE_VERSION 3u
+#define HT2_IMAGE_VERSION 4u
 
 // Local-index constants (hier_idx_common.h:23-41).
 #define HT2_LOCAL_INDEX_SIZE     57344u
@@ -42,6 +42,11 @@
 // occ[c] = fchr[c] + #c in rows [0, sideStart), '$' not counted, so that
 // LF(row,c) = occ[c] + popcount(matches among the first row&63 chars) and the
 // side of a row is row>>6.  (ht2_index.cpp:relayLinear, ht2_fm.h:ht2_lf.)
+// Graph (GBWT) indexes use 64-byte rank sides, also 64 rows each (Ht2GSide in ht2_graph.h):
+//     [16 B BW chars][u64 F bits][u64 M bits][u32 occ[4]][u32 M_occ][u32 F_loc][8 B pad]
+// M_occ = rank1(M, sideStart), F_loc = select1(F, M_occ) (row of the M_occ-th set F bit), which is
+// what the .ht2 trailer pair (F_loc, M_occ) of gfm.h:3790-3807 encodes for 208-row sides.
+#define HT2_GSIDE_BYTES 64u
 #define HT2_SIDE_SHIFT 6u
 #define HT2_SIDE_CHARS 64u
 #define HT2_SIDE_BYTES 32u
@@ -54,7 +59,7 @@ struct Ht2Gfm {
     uint32_t numNodes;     // # graph nodes (== gbwtLen for linear)
     uint32_t eftabLen;
     uint32_t linearFM;     // 1 iff len+1 == gbwtLen
-    uint32_t sideSz;       // bytes per side: 32 for linear indexes (re-laid "rank sides", see below), 128 graph
+    uint32_t sideSz;       // bytes per side: 32 for linear indexes, 64 for graph indexes (re-laid "rank sides")
     uint32_t sideGbwtSz;   // BWT bytes per side (16 linear)
     uint32_t sideGbwtLen;  // BW chars per side (64 linear)
     uint32_t numSides;

@@ -136,6 +136,62 @@ void relayLinear(Blob& b, Ht2Gfm& g, const uint8_t* old, uint32_t z)
     g.numSides = nSides;
 }
 
+// Re-lay a graph BWT (.ht2 sides: 2-bit chars, F bits, M bits, F_loc/M_occ/occ trailer,
+// gfm.h:3394-3398, 3146-3154, 3790-3795) as 64-byte graph rank sides (ht2_image.h).
+void relayGraph(Blob& b, Ht2Gfm& g, const uint8_t* old, const std::vector<uint32_t>& zs)
+{
+    const uint32_t eb = g.entryBytes;
+    const uint32_t oldSz = g.sideSz, oldBwtSz = g.sideGbwtSz, oldLen = g.sideGbwtLen;
+    const uint32_t nSides = (g.gbwtLen >> HT2_SIDE_SHIFT) + 2;   // rank queries reach row gbwtLen + 1
+    g.o_gfm = b.alloc((size_t)(nSides + 1) * HT2_GSIDE_BYTES, 128);
+    auto bitAt = [&](uint32_t row, uint32_t byteOff) -> int {
+        const uint8_t* side = old + (size_t)(row / oldLen) * oldSz;
+        const uint32_t k = row % oldLen;
+        return (side[byteOff + (k >> 3)] >> (k & 7)) & 1;
+    };
+    std::vector<uint32_t> fpos;                 // fpos[n-1] = row of the n-th set F bit
+    fpos.reserve(g.numNodes + 1);
+    for (uint32_t row = 0; row < g.gbwtLen; row++) if (bitAt(row, oldBwtSz >> 1)) fpos.push_back(row);
+    uint32_t cnt[4] = {0, 0, 0, 0}, mcnt = 0;
+    for (uint32_t row = 0; row <= g.gbwtLen + HT2_SIDE_CHARS; row++) {
+        uint8_t* side = &b.d[g.o_gfm + (size_t)(row >> HT2_SIDE_SHIFT) * HT2_GSIDE_BYTES];
+        if ((row >> HT2_SIDE_SHIFT) >= nSides) break;
+        if (row < g.gbwtLen && row % oldLen == 0) {
+            // cross-check the file's own trailer: M_occ and the char occ entries
+            const uint8_t* tr = old + (size_t)(row / oldLen) * oldSz + oldBwtSz;
+            for (int k = 0; k < 6; k++) {
+                uint32_t v;
+                if (eb == 4) memcpy(&v, tr + 4 * k, 4); else { uint16_t v16; memcpy(&v16, tr + 2 * k, 2); v = v16; }
+                if (k == 0 && (mcnt == 0 || mcnt > fpos.size())) continue;
+                const uint32_t want = (k == 0) ? fpos[mcnt - 1] : (k == 1) ? mcnt : cnt[k - 2];
+                if (v != (eb == 4 ? want : (want & 0xffffu))) throw std::runtime_error("ht2: rank tables of the graph index disagree with its BWT");
+            }
+        }
+        if ((row & (HT2_SIDE_CHARS - 1)) == 0) {
+            uint32_t tr[6];
+            for (int c = 0; c < 4; c++) tr[c] = g.fchr[c] + cnt[c];
+            tr[4] = mcnt;
+            tr[5] = (mcnt > 0 && mcnt <= fpos.size()) ? fpos[mcnt - 1] : (mcnt == 0 ? 0u : g.gbwtLen);
+            memcpy(side + 32, tr, 24);
+        }
+        if (row >= g.gbwtLen) continue;
+        const uint32_t co = row % oldLen;
+        const uint8_t* os = old + (size_t)(row / oldLen) * oldSz;
+        const int c = (os[co >> 2] >> ((co & 3) << 1)) & 3;
+        const uint32_t nco = row & (HT2_SIDE_CHARS - 1);
+        side[nco >> 2] |= (uint8_t)(c << ((nco & 3) << 1));
+        if (bitAt(row, oldBwtSz >> 1)) side[16 + (nco >> 3)] |= (uint8_t)(1u << (nco & 7));
+        if (bitAt(row, oldBwtSz - (oldBwtSz >> 2))) { side[24 + (nco >> 3)] |= (uint8_t)(1u << (nco & 7)); mcnt++; }
+        bool isZ = false;
+        for (uint32_t z : zs) if (z == row) isZ = true;
+        if (!isZ) cnt[c]++;
+    }
+    g.sideSz = HT2_GSIDE_BYTES;
+    g.sideGbwtSz = 32;
+    g.sideGbwtLen = HT2_SIDE_CHARS;
+    g.numSides = nSides;
+}
+
 // Body shared by the global (.1) and local (.5) formats, after the header
 // ints: nPat plen[] nFrag rstarts[] gfm[] nzOffs zOffs[] fchr[5] ftab[] eftab[]
 void readBody(FileBuf& f, Blob& b, Ht2Gfm& g)
@@ -158,10 +214,9 @@ void readBody(FileBuf& f, Blob& b, Ht2Gfm& g)
         if (g.nzOffs != 1) throw std::runtime_error("ht2: linear index with other than one '$' row");
         relayLinear(b, g, sides, g.zOff0);
     } else {
-        g.o_gfm = b.put(sides, tot, 128);
-        // keep one zeroed side of slack after the BWT so 128-bit side loads of the
-        // last side and select scans that run off the end stay inside the blob
-        b.alloc(g.sideSz, 128);
+        std::vector<uint32_t> zs(g.nzOffs);
+        for (uint32_t i = 0; i < g.nzOffs; i++) { if (eb == 4) memcpy(&zs[i], zp + 4 * i, 4); else { uint16_t v; memcpy(&v, zp + 2 * i, 2); zs[i] = v; } }
+        relayGraph(b, g, sides, zs);
     }
     g.o_ftab = b.put(f.take((size_t)g.ftabLen * eb), (size_t)g.ftabLen * eb, 16);
     g.o_eftab = b.put(f.take((size_t)g.eftabLen * eb), (size_t)g.eftabLen * eb, 16);

@@ -97,7 +97,7 @@ def test_image_build_is_host_only_and_consistent(lib):
     img = api.Index.build_image(os.path.join(GOLDEN, "tiny"))
     assert img[:4].tobytes() == b"HT2B"
     hdr = np.frombuffer(img[:16].tobytes(), dtype="<u4")
-    assert hdr[1] == 3  # image version
+    assert hdr[1] == 4  # image version
     total = int(np.frombuffer(img[8:16].tobytes(), dtype="<u8")[0])
     assert total == img.nbytes and total % 128 == 0
     # global geometry (Ht2Gfm at offset 16): len, gbwtLen, numNodes, eftabLen, linearFM, sideSz, sideGbwtSz, sideGbwtLen
@@ -129,6 +129,22 @@ def test_image_build_is_host_only_and_consistent(lib):
     cum = np.vstack([np.zeros((1, 4), np.int64), np.cumsum(onehot, axis=0)])
     want = cum[np.minimum(np.arange(nsides) * 64, gbwt_len)] + fchr[:4].astype(np.int64)
     assert (occ.astype(np.int64) == want).all()
+    # graph (SNP) fixture: 64-byte graph rank sides; M_occ / F_loc restate rank1(M) / select1(F)
+    gimg = api.Index.build_image(os.path.join(GOLDEN, "tiny_snp"))
+    gg = np.frombuffer(gimg[16:16 + 136].tobytes(), dtype="<u4")
+    assert gg[4] == 0 and gg[5] == 64 and gg[7] == 64 and gg[1] > gg[2] > gg[0]      # rows > nodes > bases
+    o = int(np.frombuffer(gimg[16 + 112:16 + 120].tobytes(), dtype="<u8")[0])
+    ns = (int(gg[1]) >> 6) + 1
+    sides = np.frombuffer(gimg[o:o + 64 * ns].tobytes(), np.uint8).reshape(-1, 64)
+    fbits = np.unpackbits(sides[:, 16:24], axis=1, bitorder="little").reshape(-1)[:int(gg[1])]
+    mbits = np.unpackbits(sides[:, 24:32], axis=1, bitorder="little").reshape(-1)[:int(gg[1])]
+    assert int(fbits.sum()) == int(gg[2])                                              # one F bit per node
+    tr = sides[:, 32:56].copy().view("<u4")
+    mocc = np.concatenate([[0], np.cumsum(mbits, dtype=np.int64)]).astype(np.int64)[np.minimum(np.arange(ns) * 64, int(gg[1]))]
+    assert (tr[:, 4] == mocc).all()
+    fpos = np.flatnonzero(fbits)
+    ok = mocc > 0
+    assert (tr[ok, 5] == fpos[mocc[ok] - 1]).all()
     with pytest.raises(api.Ht2GpuError):
         api.Index.build_image(os.path.join(GOLDEN, "does_not_exist"))
 
