@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--reads", type=int, default=1000000, help="reads per GPU per step")
     ap.add_argument("--ref-sample", type=int, default=500000, help="reads per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--paired", action="store_true", help="BASELINE configs[2] shape: --reads/2 pairs of 2x101 bp per GPU (not the default workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,13 +213,29 @@ def main():
         idx = h2.Index(INDEX, device=local)
     # ---- synthetic reads for this rank (pinned host memory)
     n = args.reads
-    _, codes = gen_reads(n, seed=1 + rank)
-    names = [b"r%d" % i for i in range(n)]
-    seeds = seeds_for(codes, names)
+    if args.paired:
+        import simreads
+        _, gseq = simreads.load_fasta_codes(FASTA)
+        m1, m2 = simreads.simulate(gseq, n // 2, seed=1 + rank)
+        lut = np.zeros(256, dtype=np.uint8)
+        for i, ch in enumerate(b"ACGT"):
+            lut[ch] = i
+        lut[ord("N")] = 4
+        codes = np.empty((2 * (n // 2), RDLEN), dtype=np.uint8)
+        codes[0::2] = lut[m1]; codes[1::2] = lut[m2]
+        n = codes.shape[0]
+        base_names = [b"r%d" % (i // 2) for i in range(n)]           # genRandSeed stops at '/'
+        names = [b"r%d/%d" % (i // 2, 1 + (i & 1)) for i in range(n)]
+        seeds = seeds_for(codes, base_names)
+    else:
+        _, codes = gen_reads(n, seed=1 + rank)
+        names = [b"r%d" % i for i in range(n)]
+        seeds = seeds_for(codes, names)
     seq_pin = torch.from_numpy(codes.reshape(-1).copy()).pin_memory()
     offs_pin = torch.arange(0, (n + 1) * RDLEN, RDLEN, dtype=torch.int64).pin_memory()
     seeds_pin = torch.from_numpy(seeds.astype(np.uint32).view(np.int32).copy()).pin_memory()
-    batch = h2.ReadBatch(seq_pin.numpy(), offs_pin.numpy().view(np.uint64), seeds_pin.numpy().view(np.uint32), names)
+    batch = h2.ReadBatch(seq_pin.numpy(), offs_pin.numpy().view(np.uint64), seeds_pin.numpy().view(np.uint32), names,
+                         paired=args.paired)
     # point the batch at the pinned buffers themselves (ReadBatch may have copied)
     batch.seq = seq_pin.numpy(); batch.offs = offs_pin.numpy().view(np.uint64); batch.seeds = seeds_pin.numpy().view(np.uint32)
 
@@ -239,7 +256,7 @@ def main():
     kernel_ms = res.ms_kernel
     alg_bytes = int(res.reads["alg_bytes"].astype(np.int64).sum())
     n_lf = int(res.reads["n_lf"].astype(np.int64).sum())
-    aligned = int(((res.reads["n_aln"][:, 0] > 0)).sum())
+    aligned = int((res.reads["n_aln"] > 0).sum()) if args.paired else int(((res.reads["n_aln"][:, 0] > 0)).sum())
     launches = res.n_launches
     err_reads = int((res.reads["err"] != 0).sum())
     res.close()
@@ -259,6 +276,20 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     barrier()
+    # ---- informational: the LF-mapping kernel alone (seed search, ht2gpu_seed_search) on 200k reads of the batch
+    lf_map = None
+    if rank == 0 and not args.paired:
+        k = min(200000, n)
+        sub = h2.ReadBatch(batch.seq[:k * RDLEN], batch.offs[:k + 1], batch.seeds[:k], names[:k])
+        best = None
+        for _ in range(3):
+            sr = idx.seed_search(sub, max_range=4)
+            if best is None or sr.ms_kernel < best[0]:
+                best = (sr.ms_kernel, sr.n_lf, sr.alg_bytes)
+            sr.close()
+        lf_map = {"kernel": "ht2_seed_kernel (count pass + fill pass)", "reads": k, "ms": best[0], "lf_steps": int(best[1]),
+                  "lf_per_s": best[1] / best[0] * 1e3, "achieved": best[2] / best[0] / 1e6, "unit": "GB/s",
+                  "note": "algorithmic bytes of ONE pass over the time of BOTH passes; not part of value/e2e"}
     # ---- informational: SAM text for one batch on the host back end (outside the timed regions)
     sam_info = None
     if rank == 0:
@@ -302,7 +333,8 @@ def main():
         "metric": "reads_per_sec_aligned", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 22_20-21M linear index, %d synthetic 101bp SE reads per GPU, --no-spliced-alignment -k 5" % n,
+        "config": {"workload": ("BASELINE configs[2] shape: 22_20-21M linear index, %d synthetic 2x101bp pairs per GPU (--fr, -I 0 -X 1000), --no-spliced-alignment -k 5" % (n // 2)) if args.paired else
+                               ("BASELINE configs[1]: 22_20-21M linear index, %d synthetic 101bp SE reads per GPU, --no-spliced-alignment -k 5" % n),
                    "reads_per_gpu": n, "read_len": RDLEN, "parallelism": "read-sharded x%d, index replicated (NCCL broadcast at load)" % world,
                    "l2": "index image 6.4 MB is L2-resident by construction (SURVEY 0.4); read batch (101 MB) + per-thread workspace exceed L2, no flush between steps",
                    "aligned_fraction": float(tot[2]) / total_reads, "lf_steps_per_read": float(tot[1]) / total_reads,
@@ -310,6 +342,7 @@ def main():
         "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "device_ms_per_step": e2e_dev_ms / args.steps},
         "sam_backend": sam_info,
+        "lf_map": lf_map,
         "gpu_launches": int(tot[3]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ht2_align_pool_kernel<8,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -320,7 +353,7 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     # ---- CPU baseline (rank 0, N=1 only): the unmodified reference on a bounded sample
-    if world == 1 and not args.no_cpu_baseline and os.path.exists(REFBIN):
+    if world == 1 and not args.no_cpu_baseline and not args.paired and os.path.exists(REFBIN):
         ns = min(args.ref_sample, n)
         ascii_reads, _ = gen_reads(ns, seed=1)
         fa = "/tmp/ht2_bench_cpu_%d.fa" % os.getpid()

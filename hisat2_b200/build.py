@@ -66,6 +66,10 @@ def build_oracle(verbose=False):
         if not _newer(so, [csrc]):
             subprocess.run(["gcc", "-O2", "-std=c99", "-shared", "-fPIC", "-o", so, csrc], check=True)
         out["oracle"] = so
+        exe = os.path.join(odir, "ht2_oracle")     # `ht2_oracle dump <index> <reads.fa> <no_spliced>`: the checker smoke() runs
+        if not _newer(exe, [csrc]):
+            subprocess.run(["gcc", "-O2", "-std=gnu99", "-DHT2_ORACLE_MAIN", "-o", exe, csrc], check=True)
+        out["oracle_exe"] = exe
     ref = os.environ.get("HT2_REFERENCE", "/root/reference")
     if os.path.isdir(ref):
         subprocess.run(["make", "-s", "-j8", "REF=" + ref], check=True, cwd=odir,
