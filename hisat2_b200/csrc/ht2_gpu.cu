@@ -485,8 +485,19 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b,
     uint16_t* sel = sSel[wib];
     uint32_t round = wib * 5;
     for (;;) {
+        // ---- nothing claimable at all (every remaining slot is being run by another warp, or the
+        // batch has drained): wait without touching the lock -- spinning warps cost instruction fetch
+        {
+            const int c0 = vCount[lane], c1 = vCount[lane + 32];
+            if (__ballot_sync(0xffffffffu, c0 > 0 || c1 > 0) == 0) {
+                const bool done = __shfl_sync(0xffffffffu, *(volatile int*)&sExit >= S ? 1 : 0, 0) != 0;
+                if (done) break;
+                __nanosleep(2000);
+                continue;
+            }
+        }
         // ---- one warp at a time forms a group (whole groups, not fragments shared between warps)
-        if (lane == 0) { while (atomicCAS(&sLock, 0, 1) != 0) __nanosleep(64); }
+        if (lane == 0) { unsigned ns = 32; while (atomicCAS(&sLock, 0, 1) != 0) { __nanosleep(ns); if (ns < 1024) ns <<= 1; } }
         __syncwarp();
         // every decision below is made warp-uniform (the counters change under our feet)
         uint32_t T = __shfl_sync(0xffffffffu, *(volatile unsigned int*)&sTarget, 0);

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <chrono>
 #include "../../hisat2_b200/csrc/ht2_host.h"
 #include "../../hisat2_b200/csrc/ht2_seed.h"
 
@@ -123,6 +124,7 @@ int main(int argc, char** argv) {
     Ht2Aligner A;
     size_t nerr = 0;
     uint64_t nLF = 0;
+    long long finishNs = 0;
     uint32_t mx[8] = {0,0,0,0,0,0,0,0};
     for (size_t i = 0; pairedMode && i < reads.size(); i++) {
         Ht2HostRead& r1 = reads[i]; Ht2HostRead& r2 = reads2[i];
@@ -159,7 +161,7 @@ int main(int argc, char** argv) {
         out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
         out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
         for (uint32_t k = 0; k < W->nPairs; k++) out.pairs.push_back(std::make_pair(W->pairs[k][0], W->pairs[k][1]));
-        ht2_finish_paired(sam, *img, P, r1, r2, f1, f2, out);
+        { auto t0 = std::chrono::steady_clock::now(); ht2_finish_paired(sam, *img, P, r1, r2, f1, f2, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
     }
     for (size_t i = 0; !pairedMode && i < reads.size(); i++) {
         Ht2HostRead& rd = reads[i];
@@ -188,11 +190,12 @@ int main(int argc, char** argv) {
         if (W->err) { nerr++; fprintf(stderr, "read %zu (%s): err=0x%x\n", i, rd.name.c_str(), W->err); }
         out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
         out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
-        ht2_finish_unpaired(sam, *img, P, rd, f, out);
+        { auto t0 = std::chrono::steady_clock::now(); ht2_finish_unpaired(sam, *img, P, rd, f, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
     }
     FILE* fo = fopen(argv[3], "wb");
     fwrite(sam.data(), 1, sam.size(), fo);
     fclose(fo);
+    fprintf(stderr, "SAM back end: %.1f ms total, %.2f us per read\n", finishNs / 1e6, finishNs / 1e3 / (double)reads.size());
     fprintf(stderr, "reads=%zu errors=%zu LF=%llu maxPool=%u maxDepth=%u maxEdits=%u maxSearched=%u maxRes=%u maxGH=%u maxPH=%u/%u sizeof(Work)=%zu\n", reads.size(), nerr, (unsigned long long)nLF, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[6], mx[7], sizeof(Ht2Work));
     return 0;
 }

@@ -123,6 +123,24 @@ def test_fastq_qualities_match_golden_reference_sam(h2, tiny):
     assert sam_lines(sam) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe_fq.sam"), "rb").read())
 
 
+def test_command_line_front_end_matches_golden(tmp_path):
+    """`hisat2-b200` (host C++ over the C ABI) with the reference's own flags: -x/-U/-1/-2/-S/-q/-f,
+    --no-spliced-alignment; SAM equals the reference's golden output (the @PG line differs by design)."""
+    cli = os.path.join(ROOT, "hisat2_b200", "hisat2-b200")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built (python -m hisat2_b200.build)")
+    for args, gold in ((["-q", "-U", "tiny_se.fq"], "tiny_se_fq.sam"), (["-f", "-U", "tiny_se.fa"], "tiny_se.sam"),
+                       (["-q", "-1", "tiny_pe_1.fq", "-2", "tiny_pe_2.fq"], "tiny_pe_fq.sam")):
+        out = str(tmp_path / "cli.sam")
+        subprocess.run([cli, "--no-spliced-alignment", "-x", "tiny"] + args + ["-S", out, "-p", "4"], cwd=GOLDEN, check=True,
+                       stderr=subprocess.DEVNULL)
+        assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), args
+    # anything the build cannot honour bit-exactly is refused with a non-zero exit code
+    r = subprocess.run([cli, "-x", "tiny", "-q", "-U", "tiny_se.fq", "-S", str(tmp_path / "x.sam")], cwd=GOLDEN,
+                       stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"spliced" in r.stderr
+
+
 def _option_cases():
     import json
     return json.load(open(os.path.join(GOLDEN, "option_matrix.json")))
