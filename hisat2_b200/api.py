@@ -169,8 +169,6 @@ class ReadBatch(object):
                 sq = lines[i + 1].replace(b".", b"N")
                 if len(lines[i + 3]) != len(sq):
                     raise Ht2GpuError("%s: quality / base count mismatch in record %d" % (p, i // 4))
-                if len(sq) == 0:
-                    continue
                 names.append(lines[i][1:] or str(i // 4).encode()); seqs.append(sq); quals.append(lines[i + 3])
             return names, seqs, quals
 
@@ -219,8 +217,7 @@ class ReadBatch(object):
                         chunks.append(line.rstrip(b"\r\n"))
                 if name is not None:
                     seqs.append(b"".join(chunks)); names.append(name)
-            keep = [i for i, s in enumerate(seqs) if len(s) > 0]
-            return [names[i] for i in keep], [seqs[i] for i in keep]
+            return names, seqs      # empty records stay: the reference reports them unaligned with YF:Z:LN
 
         names, seqs = parse(path)
         if path2 is not None:

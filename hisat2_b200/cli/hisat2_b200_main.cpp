@@ -30,12 +30,12 @@ static bool parseFile(const char* path, bool fastq, std::vector<std::string>& na
         while (p < n) {
             line(l);
             if (!l.empty() && l[0] == '>') {
-                if (have && !seq.empty()) { names.push_back(name); seqs.push_back(seq); quals.push_back(std::string(seq.size(), 'I')); }
+                if (have) { names.push_back(name); seqs.push_back(seq); quals.push_back(std::string(seq.size(), 'I')); }
                 name = l.substr(1); if (name.empty()) name = std::to_string(cnt); cnt++; seq.clear(); have = true;
             } else if (!l.empty() && (l[0] == '#' || l[0] == ';')) continue;
             else for (char c : l) if (dnacat((unsigned char)c)) seq.push_back((char)asc2dna(c));
         }
-        if (have && !seq.empty()) { names.push_back(name); seqs.push_back(seq); quals.push_back(std::string(seq.size(), 'I')); }
+        if (have) { names.push_back(name); seqs.push_back(seq); quals.push_back(std::string(seq.size(), 'I')); }
     } else {
         while (p < n) {
             line(l); if (l.empty()) continue;
@@ -44,7 +44,6 @@ static bool parseFile(const char* path, bool fastq, std::vector<std::string>& na
             std::string codes; std::string qq;
             for (size_t i = 0; i < s.size(); i++) if (dnacat((unsigned char)s[i])) { codes.push_back((char)asc2dna(s[i])); qq.push_back(i < q.size() ? q[i] : 'I'); }
             if (name.empty()) name = std::to_string(cnt); cnt++;
-            if (codes.empty()) continue;
             names.push_back(name); seqs.push_back(codes); quals.push_back(qq);
         }
     }

@@ -63,7 +63,7 @@ __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, u
 }
 
 // Per-read filters and minimum score (hisat2.cpp:3387-3440): length filter,
-// N filter (Scoring::nFilter, nCeil = L,2,0.1 -- hisat2.cpp:443), score filter
+// N filter (Scoring::nFilter, nCeil = L,0,0.15 -- the parseString default, aligner_seed_policy.cpp:293-296), score filter
 // (minsc = L,0,-0.2 clamped to <= 0 -- hisat2.cpp:441, 3395-3402).  All products
 // are exact in double (24-bit constants x lengths < 2^9), so host
 // (ht2_host.cpp:ht2_minsc/ht2_filters) and device agree bit for bit.
@@ -74,7 +74,7 @@ __device__ __forceinline__ bool ht2_dev_filter(const DevBatch& b, uint32_t ri, i
     int64_t m = (int64_t)((double)-0.2f * (double)len);
     if (m > 0) m = 0;
     minsc = m;
-    const uint32_t maxns = (uint32_t)((double)2.0f + (double)0.1f * (double)len);
+    const uint32_t maxns = (uint32_t)((double)0.0f + (double)0.15f * (double)len);   // nCeil = L,0,0.15 (aligner_seed_policy.cpp:293-296)
     const uint8_t* s = b.seq + o0;
     uint32_t ns = 0;
     for (uint32_t k = 0; k < len; k++) ns += (s[k] == 4);

@@ -52,9 +52,10 @@ Ht2ReadFilters ht2_filters(const Ht2HostRead& rd, int64_t minsc)
 {
     Ht2ReadFilters f;
     size_t rdlen = rd.seq.size();
-    // Scoring::nFilter (scoring.cpp:104-117); nCeil = L,0,0.15?? no: hisat2.cpp:443
-    // nCeil.init(SIMPLE_FUNC_LINEAR, 0.0f, DMAX, 2.0f, 0.1f)
-    size_t maxns = (size_t)simpleLinear(0.0, 1.7976931348623157e308, (double)2.0f, (double)0.1f, (double)rdlen);
+    // Scoring::nFilter (scoring.cpp:104-117).  The effective default is nCeil = L,0,0.15: hisat2.cpp:443
+    // initialises 2 + 0.1 len, but SeedAlignmentPolicy::parseString -- always called, hisat2.cpp:1849 --
+    // resets it to DEFAULT_N_CEIL_CONST/LINEAR = 0.0 / 0.15 (aligner_seed_policy.cpp:293-296, scoring.h:65-67).
+    size_t maxns = (size_t)simpleLinear(0.0, 1.7976931348623157e308, (double)0.0f, (double)0.15f, (double)rdlen);
     size_t ns = 0;
     f.nfilt = true;
     for (size_t i = 0; i < rdlen; i++) {
@@ -158,7 +159,7 @@ bool ht2_read_fasta(const char* path, std::vector<Ht2HostRead>& out, int mate, s
         }
         if (r.name.empty()) r.name = std::to_string(readCnt);
         readCnt++;
-        if (r.seq.empty()) continue; // "skipping empty FASTA read"
+        // an empty record stays in the stream: the reference reports it as unaligned with YF:Z:LN
         out.push_back(r);
     }
     return true;
@@ -206,7 +207,6 @@ bool ht2_read_fastq(const char* path, std::vector<Ht2HostRead>& out, int mate, s
         }
         if (r.name.empty()) r.name = std::to_string(readCnt);
         readCnt++;
-        if (r.seq.empty()) continue;
         out.push_back(r);
     }
     return true;
@@ -512,6 +512,7 @@ void appendRefName(std::string& o, const Ht2Image& img, uint32_t tidx) {
 }
 void appendSeqQual(std::string& o, const Ht2HostRead& rd, bool fw) {
     size_t n = rd.seq.size();
+    if (n == 0) { o += "*\t*"; return; }   // aln_sink.h:3194, 3210
     if (fw) for (size_t i = 0; i < n; i++) o.push_back("ACGTN"[rd.seq[i]]);
     else for (size_t i = 0; i < n; i++) { uint8_t c = rd.seq[n - i - 1]; o.push_back("ACGTN"[c < 4 ? (c ^ 3) : 4]); }
     o.push_back('\t');

@@ -22,6 +22,12 @@ fi
 if [ ! -f $D/hard20k_1.fa ]; then
   python ../tools/simreads.py $D/22_20-21M.fa 20000 $D/hard20k --seed 3 --paired --indel 0.004 --nrate 0.003 --sub 0.02 --ragged
 fi
+# short (36 bp: ragged down to empty / 1-3 base reads) and long (150, 250 bp) reads, with indels and Ns
+for L in 36 150 250; do
+  if [ ! -f $D/len${L}_1.fa ]; then
+    python ../tools/simreads.py $D/22_20-21M.fa 20000 $D/len${L} --seed $((70 + L)) --paired --indel 0.004 --nrate 0.002 --sub 0.01 --ragged --rdlen $L
+  fi
+done
 if [ ! -f $D/sim200k_1.fa ]; then
   python ../tools/simreads.py $D/22_20-21M.fa 200000 $D/sim200k --seed 5 --paired
 fi

@@ -70,7 +70,7 @@ def test_tiny_pe_matches_golden_reference_sam(h2, tiny):
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
-@pytest.mark.parametrize("name", ["sim10k", "hard20k"])
+@pytest.mark.parametrize("name", ["sim10k", "hard20k", "len36", "len150"])
 def test_chr22_paired_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
     """BASELINE configs[2]-shaped input (2x101 bp pairs): SAM identical to the reference."""
     f1, f2 = os.path.join(DATA, name + "_1.fa"), os.path.join(DATA, name + "_2.fa")
@@ -254,7 +254,7 @@ def test_edge_cases(h2, tiny):
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
-@pytest.mark.parametrize("name", ["reads", "hard20k", "sim200k"])
+@pytest.mark.parametrize("name", ["reads", "hard20k", "sim200k", "len36", "len150", "len250"])
 def test_chr22_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
     """BASELINE configs[0]/[1]-shaped inputs: SAM byte-identical to the unmodified
     reference run on this box (-p N --reorder)."""
@@ -267,6 +267,27 @@ def test_chr22_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
     subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", os.path.join(DATA, "22_20-21M"), "-U", fa, "-S", out,
                     "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
     assert sam_lines(sam) == sam_lines(open(out, "rb").read())
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
+def test_long_pairs_capacity_errors_are_flagged_never_silent(h2, chr22, tmp_path):
+    """2x250 bp pairs with indels and Ns: a handful of pairs need more than HT2_MAX_EDITS (24) edits in one
+    alignment; those are flagged (err != 0, HT2GPU_ERR_CAPACITY) and every OTHER pair is byte-identical."""
+    f1, f2 = os.path.join(DATA, "len250_1.fa"), os.path.join(DATA, "len250_2.fa")
+    if not os.path.exists(f1):
+        pytest.skip(f1 + " not staged")
+    batch = h2.ReadBatch.from_fasta(f1, path2=f2)
+    res = chr22.align(batch, allow_capacity=True)
+    bad = set(np.flatnonzero(res.reads["err"] != 0).tolist())
+    assert len(bad) <= 10
+    sam = chr22.sam_header() + chr22.format_sam(batch, res)
+    out = str(tmp_path / "ref.sam")
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", os.path.join(DATA, "22_20-21M"), "-1", f1, "-2", f2, "-S", out,
+                    "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    badnames = set(batch.names[2 * u].split(b"/")[0] for u in bad)
+    def keep(lines):
+        return [l for l in lines if l.startswith(b"@") or l.split(b"\t")[0] not in badnames]
+    assert keep(sam_lines(sam)) == keep(sam_lines(open(out, "rb").read()))
 
 
 def test_full_size_properties_1M_reads(h2, chr22):

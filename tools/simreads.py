@@ -128,9 +128,13 @@ def main():
     ap.add_argument("--nrate", type=float, default=0.0, help="per-base N rate")
     ap.add_argument("--sub", type=float, default=0.005)
     ap.add_argument("--ragged", action="store_true", help="randomly truncate half of the reads")
+    ap.add_argument("--rdlen", type=int, default=101)
     a = ap.parse_args()
     _, seq = load_fasta_codes(a.reference)
-    m1, m2 = simulate(seq, a.n, a.seed, sub=a.sub)
+    if a.rdlen != 101:
+        m1, m2 = simulate(seq, a.n, a.seed, rdlen=a.rdlen, fmin=max(2 * a.rdlen, 100), fmax=max(3 * a.rdlen, 200), sub=a.sub)
+    else:
+        m1, m2 = simulate(seq, a.n, a.seed, sub=a.sub)
     if a.indel > 0 or a.nrate > 0 or a.ragged:
         write_fasta_list(a.out_prefix + "_1.fa", add_noise(m1, a.seed, a.indel, a.nrate, a.ragged))
         if a.paired:
