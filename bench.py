@@ -146,7 +146,7 @@ def reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": "reads_per_sec_aligned", "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-            "config": {"workload": "22_20-21M linear index, synthetic 101bp SE reads, --no-spliced-alignment"}}
+            "config": {"workload": "BASELINE configs[1]: 22_20-21M linear index, synthetic 101bp SE reads (bounded sample of --ref-sample reads per step, same generator and seed as the GPU arm), --no-spliced-alignment -k 5"}}
     if not (os.path.exists(REFBIN) and os.path.exists(INDEX + ".1.ht2")):
         line = {"impl": "reference", "unavailable": "oracle/_ref/hisat2-align-s or data/22_20-21M index not present"}
         print(json.dumps(line))
