@@ -246,7 +246,8 @@ HT2_HD int ht2_max_gaps(int64_t minsc, int open, int ext) {
 // ------------------------------------------------------------------------
 // The aligner
 // ------------------------------------------------------------------------
-struct Ht2Aligner {
+template <bool GRAPH>
+struct Ht2AlignerT {
     const uint8_t*        blob;
     const Ht2ImageHeader* H;
     Ht2Fm<uint32_t>       gfm;
@@ -1469,6 +1470,8 @@ struct Ht2Aligner {
     HT2_HD bool machineAtHeavyState() const;
     HT2_HD void machineRun();
 };
+typedef Ht2AlignerT<false> Ht2Aligner;        // linear indexes
+typedef Ht2AlignerT<true>  Ht2GraphAligner;   // graph (SNP) indexes
 
 #include "ht2_core_impl.h"
 #include "ht2_machine.h"

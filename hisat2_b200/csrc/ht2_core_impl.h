@@ -6,7 +6,7 @@
 // SplicedAligner::hybridSearch_recur (spliced_aligner.h:331-2052).
 // Branches guarded by !ssdb.empty() are omitted (the splice-site DB is empty
 // when no splice sites are known and --no-spliced-alignment is on).
-HT2_NI int64_t Ht2Aligner::hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, uint32_t hitoff, uint32_t hitlen,
+template <bool GRAPH> HT2_NI int64_t Ht2AlignerT<GRAPH>::hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, uint32_t hitoff, uint32_t hitlen,
                                               bool alignMate, uint32_t dep)
 {
     int64_t maxsc = HT2_MIN_I64;
@@ -407,7 +407,7 @@ HT2_NI int64_t Ht2Aligner::hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, ui
 // PairedEndPolicy::peClassifyPair (pe.cpp:38-132) with the hisat2 defaults
 // olapOk = containOk = expandToFit = true, dovetailOk = false (hisat2.cpp:348-352).
 // Returns true iff the pair is NOT discordant.
-HT2_NI bool Ht2Aligner::peConcordant(int64_t off1, uint32_t len1, bool fw1, int64_t off2, uint32_t len2, bool fw2) const
+template <bool GRAPH> HT2_NI bool Ht2AlignerT<GRAPH>::peConcordant(int64_t off1, uint32_t len1, bool fw1, int64_t off2, uint32_t len2, bool fw2) const
 {
     uint32_t maxfrag = P->maxFrag;
     if (len1 > maxfrag) maxfrag = len1;
@@ -438,7 +438,7 @@ HT2_NI bool Ht2Aligner::peConcordant(int64_t off1, uint32_t len1, bool fw1, int6
 
 // HI_Aligner::pairReads (hi_aligner.h:5948-6057) + AlnSinkWrap::report for a
 // pair (aln_sink.h:2565-2611) + ReportingState::foundConcordant (aln_sink.cpp:72-92).
-HT2_NI void Ht2Aligner::pairReads()
+template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::pairReads()
 {
     const uint32_t n1 = W->nRes[0], n2 = W->nRes[1];
     uint32_t start_i = W->concordInspected[0], start_j = W->concordInspected[1];
@@ -495,7 +495,7 @@ HT2_NI void Ht2Aligner::pairReads()
 // HI_Aligner::alignMate (hi_aligner.h:5579-5767): use the alignment of one mate
 // (rdi, at tidx:toff) as an anchor and search the local index(es) around it for
 // the other mate.
-HT2_NI bool Ht2Aligner::alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
+template <bool GRAPH> HT2_NI bool Ht2AlignerT<GRAPH>::alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
 {
     const uint32_t ordi = 1 - rdi;
     alignMateAnchors(rdi, fw, tidx, toff);
@@ -509,7 +509,7 @@ HT2_NI bool Ht2Aligner::alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32
 }
 
 // anchor search part of alignMate (hi_aligner.h:5600-5717): fills W->genomeHits
-HT2_NI void Ht2Aligner::alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
+template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
 {
     const uint32_t ordi = 1 - rdi;
     const bool ofw = (fw == (P->gMate2fw != 0)) ? (P->gMate1fw != 0) : (P->gMate2fw != 0);
@@ -575,7 +575,7 @@ HT2_NI void Ht2Aligner::alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, u
 
 // HI_Aligner::go (hi_aligner.h:4048-4149); the repeat-index block
 // (:4151-4636) runs only when a .rep index is loaded.
-HT2_NI void Ht2Aligner::go()
+template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::go()
 {
     for (uint32_t rdi = 0; rdi < 2; rdi++) {
         for (uint32_t fwi = 0; fwi < 2; fwi++) {

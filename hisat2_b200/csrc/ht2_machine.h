@@ -31,7 +31,7 @@ enum {
 };
 
 // push a child frame (== a recursive call of hybridSearch_recur)
-HT2_HD void Ht2Aligner::pushFrame(uint32_t rdi, const Ht2Hit* hit, uint32_t hitoff, uint32_t hitlen, bool alignMate, uint32_t dep)
+template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::pushFrame(uint32_t rdi, const Ht2Hit* hit, uint32_t hitoff, uint32_t hitlen, bool alignMate, uint32_t dep)
 {
     if (W->nFrames >= HT2_DEPTH_CAP) { W->err |= HT2_ERR_DEPTH; W->childRet = HT2_MIN_I64; return; }
     Ht2Frame& f = W->frames[W->nFrames++];
@@ -39,7 +39,7 @@ HT2_HD void Ht2Aligner::pushFrame(uint32_t rdi, const Ht2Hit* hit, uint32_t hito
 }
 
 // One segment of one hybridSearch_recur activation.
-HT2_NI void Ht2Aligner::runFrame()
+template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
 {
     Ht2Frame& f = W->frames[W->nFrames - 1];
     const uint32_t rdi = f.rdi;
@@ -551,7 +551,7 @@ HT2_NI void Ht2Aligner::runFrame()
 }
 
 // One segment of the top-level control (go / nextBWT / align / hybridSearch / alignMate).
-HT2_NI void Ht2Aligner::runTop()
+template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
 {
     switch (W->st) {
     case TS_START: {
@@ -727,9 +727,9 @@ HT2_NI void Ht2Aligner::runTop()
 }
 
 // Run one read (pair) to completion (host build and the one-lane-per-read kernel loop).
-HT2_HD void Ht2Aligner::machineStart() { W->st = TS_START; W->nFrames = 0; }
-HT2_HD bool Ht2Aligner::machineDone() const { return W->st == TS_DONE && W->nFrames == 0; }
-HT2_HD void Ht2Aligner::machineStep()
+template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStart() { W->st = TS_START; W->nFrames = 0; }
+template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineDone() const { return W->st == TS_DONE && W->nFrames == 0; }
+template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStep()
 {
     if (W->nFrames > 0) runFrame();
     else runTop();
@@ -737,7 +737,7 @@ HT2_HD void Ht2Aligner::machineStep()
 // "Heavy" states are the ones worth regrouping lanes for (index searches,
 // reference extension, combine); everything else is short glue that is chained
 // onto the end of the previous segment.
-HT2_HD bool Ht2Aligner::machineAtHeavyState() const
+template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineAtHeavyState() const
 {
     if (W->nFrames > 0) {
         switch (W->frames[W->nFrames - 1].pc) {
@@ -753,7 +753,7 @@ HT2_HD bool Ht2Aligner::machineAtHeavyState() const
     }
 }
 // run one heavy segment plus the glue that follows it
-HT2_HD void Ht2Aligner::machineRun()
+template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineRun()
 {
     do { machineStep(); } while (!machineAtHeavyState());
 }
