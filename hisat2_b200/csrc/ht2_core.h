@@ -16,6 +16,8 @@
 
 #include "ht2_image.h"
 #include "ht2_fm.h"
+#include "ht2_seed.h"
+#include "ht2_gwalk.h"
 #include "ht2_params.h"
 
 #ifndef HT2_MAX_RDLEN
@@ -25,6 +27,7 @@
 #define HT2_MAX_PHITS 64
 #define HT2_MAX_GHITS 24
 #define HT2_POOL 40
+#define HT2_IE_POOL 224          /* in-edge entries per strand (graph indexes) */
 #define HT2_SEARCHED_BYTES 24576   /* ~600 searched hits (40 B typical) for both mates */
 
 #define HT2_MAX_RES 64
@@ -84,7 +87,8 @@ struct Ht2SearchedEdit { uint32_t pos; uint8_t type, chr, qchr, pad; };
 struct Ht2BwtHit {        // BWTHit, hi_aligner.h:108-208
     uint32_t top, bot, node_top, node_bot;
     uint32_t bwoff, len;
-    uint8_t  hit_type, hasCoords, pad0, pad1;
+    uint8_t  hit_type, hasCoords;
+    uint8_t  ieOff, ieN;   // graph indexes: in-edge list of the hit inside Ht2ReadHits::ie
 };
 
 struct Ht2ReadHits {      // ReadBWTHit, hi_aligner.h:216-389
@@ -92,6 +96,8 @@ struct Ht2ReadHits {      // ReadBWTHit, hi_aligner.h:216-389
     uint32_t numPartialSearch, numUniqueSearch;
     uint32_t nhits;
     Ht2BwtHit hits[HT2_MAX_PHITS];
+    uint16_t ie[HT2_IE_POOL][2];   // graph indexes: (node index in range, # extra incoming edges) of the hits
+    uint32_t nie;
 };
 
 struct Ht2Coord {         // Coord, ref_coord.h:35
@@ -124,6 +130,9 @@ struct Ht2Rng {           // RandomSource, random_source.h:30-110
     uint32_t last;
     HT2_HD void init(uint32_t seed) { last = seed; }
     HT2_HD uint32_t nextU32() {
+#if !defined(__CUDA_ARCH__) && defined(HT2_TRACE)
+        fprintf(stderr, "RNG draw (state %u)\n", last);
+#endif
         uint32_t ret;
         last = 1664525u * last + 1013904223u;
         ret = last >> 16;
@@ -145,6 +154,21 @@ struct Ht2Frame {
     int64_t  maxsc, prev_score, cushion;
     Ht2Coord coords[8];
     uint16_t localHits[16];
+};
+
+// Scratch of one alignWithALTs call (graph indexes; ht2_alt.h)
+#define HT2_ALT_CANDS 4
+#define HT2_ALT_BUFS 4
+#define HT2_ALT_MAXDEP 24
+struct Ht2AltScratch {
+    Ht2Edit  tmp[HT2_MAX_EDITS];            // tmp_edits
+    uint32_t ntmp;
+    int32_t  best_rdoff;
+    uint32_t numALTsTried;
+    uint32_t nbuf;                          // reference-window buffers in use (stack discipline)
+    uint8_t  wantCands, ncand, candN[HT2_ALT_CANDS], pad[2];
+    Ht2Edit  cand[HT2_ALT_CANDS][HT2_MAX_EDITS];   // candidate_edits: equally long alternatives (adjustWithALT)
+    alignas(8) uint8_t ref[HT2_ALT_BUFS][HT2_REFBUF + 16];
 };
 
 // Per-read (pair) workspace.  One per in-flight GPU thread.
@@ -178,6 +202,12 @@ struct Ht2Work {
     alignas(8) uint8_t refbuf2[HT2_REFBUF + 16];
     int64_t     tscores[HT2_MAX_RDLEN];
     int64_t     tscores2[HT2_MAX_RDLEN];
+    Ht2AltScratch alt;                      // graph indexes only
+    Ht2GWalk    gw;                         // group walk over graph indexes (ht2_gwalk.h)
+    uint16_t    curIe[24][2];               // in-edge list of the most recent global/local GFM search (graph)
+    uint32_t    nCurIe;
+    uint32_t    offDiffs[40][2];            // findOffDiffs scratch: (|diff|, sign as 0/1/2 = -1/0/+1)
+    uint32_t    nOffDiffs;
     Ht2Rng      rnd;
     uint32_t    err;
     // work counters (HIMetrics hi_aligner.h:3897 + roofline accounting)
@@ -507,6 +537,7 @@ struct Ht2AlignerT {
     // HI_Aligner::partialSearch (hi_aligner.h:6361-6600).  Returns stop
     // flags through pseudogeneStop/anchorStop like the reference.
     HT2_NI void partialSearch(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
+        if (GRAPH) { partialSearchGraph(rdi, fw, pseudogeneStop, anchorStop); return; }
         bool pseudogeneStop_ = pseudogeneStop, anchorStop_ = anchorStop;
         pseudogeneStop = anchorStop = false;
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
@@ -613,6 +644,8 @@ struct Ht2AlignerT {
     HT2_NI uint32_t gfmSearch(const Ht2Fm<IT>& fm, uint32_t rdi, bool fw, uint32_t rdoff, uint32_t& hitlen,
                               uint32_t& top, uint32_t& bot, uint32_t& node_top, uint32_t& node_bot,
                               bool& uniqueStop, uint32_t minUniqueLen, uint32_t maxHitLen, uint32_t maxHits, bool local) {
+        // a graph index may hold LINEAR local indexes (windows without ALTs, or whose local graph exploded at build time)
+        if (GRAPH) { W->nCurIe = 0; if (!fm.g->linearFM) return gfmSearchGraph(fm, rdi, fw, rdoff, hitlen, top, bot, node_top, node_bot, uniqueStop, minUniqueLen, maxHitLen, maxHits, local); }
         bool uniqueStop_ = uniqueStop;
         uniqueStop = false;
         const uint32_t ftabLen = fm.g->ftabChars;
@@ -683,6 +716,7 @@ struct Ht2AlignerT {
     // HI_Aligner::getGenomeCoords (hi_aligner.h:5774-5855); appends to W->coords.
     HT2_NI bool getGenomeCoords(uint32_t top, uint32_t bot, uint32_t node_top, uint32_t node_bot, bool fw,
                                 uint32_t maxelt, uint32_t rdlen, bool rejectStraddle, bool& straddled) {
+        if (GRAPH) return getGenomeCoordsGraph(top, bot, node_top, node_bot, W->curIe, W->nCurIe, fw, maxelt, rdlen, rejectStraddle, straddled);
         straddled = false;
         uint32_t nelt = node_bot - node_top;
         if (nelt > maxelt) nelt = maxelt;
@@ -705,6 +739,7 @@ struct Ht2AlignerT {
     HT2_NI bool getGenomeCoordsLocal(const Ht2Fm<uint16_t>& lfm, uint32_t top, uint32_t bot, uint32_t node_top,
                                      uint32_t node_bot, bool fw, uint32_t rdoff, uint32_t rdlen,
                                      Ht2Coord* out, uint32_t& nout, uint32_t cap) {
+        if (GRAPH && !lfm.g->linearFM) return getGenomeCoordsLocalGraph(lfm, top, bot, node_top, node_bot, fw, rdoff, rdlen, out, nout, cap);
         uint32_t nelt = node_bot - node_top;
         for (uint32_t i = 0; i < nelt; i++) {
             uint32_t joff = resolveRow(lfm, top + i);
@@ -883,7 +918,8 @@ struct Ht2AlignerT {
             if (rl < 0) { reflen += rl; rl = 0; }
             uint32_t numNs = 0;
             uint32_t num_prev_edits = h.nedits;
-            uint32_t best_ext = alignLeft(h, seq, h.rdoff - 1, h.rdoff - 1, h.rdoff, h.tidx, rl, reflen, mm, &numNs);
+            uint32_t best_ext = GRAPH ? alignWithALTs(h, seq, h.joinedOff, h.rdoff - 1, h.rdoff - 1, h.rdoff, h.tidx, rl, reflen, true, false, mm, &numNs)
+                                      : alignLeft(h, seq, h.rdoff - 1, h.rdoff - 1, h.rdoff, h.tidx, rl, reflen, mm, &numNs);
             if (h.len == 0 && mm == 0 && h.nedits > 0) { h.nedits = 0; return false; }
             if (best_ext > 0) {
                 leftext = best_ext;
@@ -912,8 +948,19 @@ struct Ht2AlignerT {
             if (rl < tlen) {
                 uint32_t reflen = rr + 10;
                 if (rl + reflen > tlen) reflen = tlen - rl;
-                uint32_t best_ext = alignRight(h, seq, h.rdoff, h.rdoff + h.len, rdlen - (h.rdoff + h.len),
-                                               h.tidx, (int)rl, reflen, mm);
+                uint32_t best_ext;
+                if (GRAPH) {
+                    int ref_ext = (int)h.len;      // joined offset of the base right after the hit (hi_aligner.h:2152-2159)
+                    for (uint32_t ei = 0; ei < h.nedits; ei++) {
+                        const Ht2Edit& e = h.edits[ei];
+                        if (e.type == HT2_EDIT_REF_GAP) ref_ext--;
+                        else if (e.type == HT2_EDIT_READ_GAP) ref_ext++;
+                        else if (e.type == HT2_EDIT_MM && e.chr == 'N') ref_ext--;
+                    }
+                    best_ext = alignWithALTs(h, seq, h.joinedOff + (uint32_t)ref_ext, h.rdoff, h.rdoff + h.len, rdlen - (h.rdoff + h.len),
+                                             h.tidx, (int)rl, reflen, false, false, mm, NULL);
+                } else best_ext = alignRight(h, seq, h.rdoff, h.rdoff + h.len, rdlen - (h.rdoff + h.len),
+                                             h.tidx, (int)rl, reflen, mm);
                 if (h.len == 0 && mm == 0 && h.nedits > 0) { h.nedits = 0; return false; }
                 if (best_ext > 0) { rightext = best_ext; h.len += best_ext; }
             }
@@ -1082,8 +1129,18 @@ struct Ht2AlignerT {
                 int rfc = (i <= maxscorei ? refbuf[i] : refbuf2[i]);
                 uint32_t addoff = this_rdoff - a.rdoff;
                 if (rdc != rfc) {
-                    // (graph indexes: look the mismatch up in the ALT table here, :1917-1930)
-                    if (!pushEdit(a, mkEdit(i + addoff, ht2_code2asc(rfc), ht2_code2asc(rdc), HT2_EDIT_MM))) return false;
+                    Ht2Edit me = mkEdit(i + addoff, ht2_code2asc(rfc), ht2_code2asc(rdc), HT2_EDIT_MM);
+                    if (GRAPH) {
+                        // a mismatch that is a known single-base ALT carries its id (hi_aligner.h:1917-1933)
+                        const uint32_t key = a.joinedOff + i + (this_toff - a.toff) - ins_len;
+                        const Ht2Alt* alts = altTable();
+                        for (uint32_t ai = altLoBound(key); ai < numAlts(); ai++) {
+                            if (alts[ai].pos > key) break;
+                            if (alts[ai].type != HT2_ALT_SNP_SGL) continue;
+                            if (alts[ai].seq == (uint64_t)rdc) { me.snpID = ai; break; }
+                        }
+                    }
+                    if (!pushEdit(a, me)) return false;
                 }
                 if (i == maxscorei) {
                     uint32_t left = this_toff + i + 1;
@@ -1159,6 +1216,9 @@ struct Ht2AlignerT {
 
     // HI_Aligner::reportHit (hi_aligner.h:6064-6198), unpaired form.
     HT2_NI bool reportHit(uint32_t rdi, const Ht2Hit& hit) {
+#if !defined(__CUDA_ARCH__) && defined(HT2_TRACE)
+        fprintf(stderr, "reportHit rdi %u fw %u toff %u score %lld ned %u\n", rdi, hit.fw, hit.toff, (long long)hit.score, hit.nedits);
+#endif
         const uint32_t rdlen = W->rd[rdi].len;
         if (hit.rdoff - hit.trim5 > 0 || hit.len + hit.trim5 + hit.trim3 < rdlen) return false;
         if (hit.score < minsc[rdi]) return false;
@@ -1338,15 +1398,24 @@ struct Ht2AlignerT {
             bool straddled = false;
             W->nCoords = 0;
             if (expectedNumCoords <= remained) {
-                getGenomeCoords(ph.top, ph.bot, ph.node_top, ph.node_bot, fw, ph.bot - ph.top, ph.len, false, straddled);
+                if (GRAPH) getGenomeCoordsGraph(ph.top, ph.bot, ph.node_top, ph.node_bot, hit.ie + ph.ieOff, ph.ieN, fw, ph.bot - ph.top, ph.len, false, straddled);
+                else getGenomeCoords(ph.top, ph.bot, ph.node_top, ph.node_bot, fw, ph.bot - ph.top, ph.len, false, straddled);
             } else {
                 uint32_t top = ph.top;
                 uint32_t added = 0;
+                uint32_t edgeIdx = 0;
                 for (uint32_t node = ph.node_top; node < ph.node_bot; node++, expectedNumCoords--) {
                     uint32_t bot = top + 1;
+                    uint16_t oneIe[1][2]; uint32_t nOneIe = 0;
+                    if (GRAPH && edgeIdx < ph.ieN && node - ph.node_top == hit.ie[ph.ieOff + edgeIdx][0]) {
+                        bot += hit.ie[ph.ieOff + edgeIdx][1];      // this node has extra incoming edges (hi_aligner.h:5097-5107)
+                        oneIe[0][0] = 0; oneIe[0][1] = hit.ie[ph.ieOff + edgeIdx][1]; nOneIe = 1;
+                        edgeIdx++;
+                    }
                     uint32_t rndi = W->rnd.nextU32() % expectedNumCoords;
                     if (rndi < remained - added) {
-                        getGenomeCoords(top, bot, node, node + 1, fw, ph.bot - ph.top, ph.len, false, straddled);
+                        if (GRAPH) getGenomeCoordsGraph(top, bot, node, node + 1, oneIe, nOneIe, fw, ph.bot - ph.top, ph.len, false, straddled);
+                        else getGenomeCoords(top, bot, node, node + 1, fw, ph.bot - ph.top, ph.len, false, straddled);
                         added++;
                         if (added >= remained) break;
                     }
@@ -1365,6 +1434,10 @@ struct Ht2AlignerT {
                     left--;
                 }
             }
+#if !defined(__CUDA_ARCH__) && defined(HT2_TRACE)
+            fprintf(stderr, "partial hj %u bwoff %u len %u top %u bot %u ntop %u nbot %u ncoords %u\n", hj, ph.bwoff, ph.len, ph.top, ph.bot, ph.node_top, ph.node_bot, W->nCoords);
+            for (uint32_t k = 0; k < W->nCoords; k++) fprintf(stderr, "  coord ref %u off %u joined %u\n", W->coords[k].ref, W->coords[k].off, W->coords[k].joinedOff);
+#endif
             for (uint32_t k = 0; k < W->nCoords; k++) {
                 const Ht2Coord& coord = W->coords[k];
                 if (coord.ref == HT2_IDX_MAX32) continue;
@@ -1383,12 +1456,15 @@ struct Ht2AlignerT {
                 }
                 if (!overlapped) {
                     if (W->nGenomeHits >= HT2_MAX_GHITS) { W->err |= HT2_ERR_GHITS; break; }
-                    initHit(W->genomeHits[W->nGenomeHits++], coord.fw != 0, rdoff, len, 0, 0, coord.ref, coord.off, coord.joinedOff);
+                    adjustWithALTCoord(rdoff, len, coord, rdi);     // plain init on linear indexes (hi_aligner.h:2251-2264)
                 }
                 if (ph.hit_type == HT2_CANDIDATE_HIT && W->nGenomeHits >= maxGenomeHitSize) break;
             }
             if (ph.hit_type == HT2_CANDIDATE_HIT && W->nGenomeHits >= maxGenomeHitSize) break;
         }
+#if !defined(__CUDA_ARCH__) && defined(HT2_TRACE)
+        for (uint32_t gi = 0; gi < W->nGenomeHits; gi++) fprintf(stderr, "anchor %u fw %u rdoff %u len %u toff %u ned %u\n", gi, W->genomeHits[gi].fw, W->genomeHits[gi].rdoff, W->genomeHits[gi].len, W->genomeHits[gi].toff, W->genomeHits[gi].nedits);
+#endif
         return W->nGenomeHits;
     }
 
@@ -1469,6 +1545,8 @@ struct Ht2AlignerT {
     HT2_HD void machineStep();
     HT2_HD bool machineAtHeavyState() const;
     HT2_HD void machineRun();
+
+#include "ht2_alt.h"
 };
 typedef Ht2AlignerT<false> Ht2Aligner;        // linear indexes
 typedef Ht2AlignerT<true>  Ht2GraphAligner;   // graph (SNP) indexes

@@ -547,7 +547,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::alignMateAnchors(uint32_t 
                         if (coord.off + P->maxFrag * 2 < toff || toff + P->maxFrag * 2 < coord.off) continue;
                     }
                     if (W->nGenomeHits >= HT2_MAX_GHITS) { W->err |= HT2_ERR_GHITS; break; }
-                    initHit(W->genomeHits[W->nGenomeHits++], coord.fw != 0, hitoff - hitlen + 1, hitlen, 0, 0, coord.ref, coord.off, coord.joinedOff);
+                    adjustWithALTCoord(hitoff - hitlen + 1, hitlen, coord, ordi);   // plain init on linear indexes (hi_aligner.h:5692)
                 }
                 max_hitlen = hitlen;
             }

@@ -634,16 +634,25 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2HostRead& r
     const ScoreKey& sb = summ.secbest[rd.mate < 2 ? 0 : 1];
     if (sb.valid) { o += "\tZS:i:"; o += std::to_string(sb.score); }
     o += "\tXN:i:0";
-    size_t num_mm = 0, num_go = 0, num_gx = 0, NM = rs->nedits;
+    // counts exclude edits that are known ALTs (snpID < #alts, sam.h:574-647)
+    const Ht2ImageHeader* IH = img.header();
+    const uint32_t nAlts = IH->nAlts;
+    const Ht2Alt* altTab = (const Ht2Alt*)(img.blob.data() + IH->o_alts);
+    size_t num_mm = 0, num_go = 0, num_gx = 0, NM = 0;
+    for (size_t i = 0; i < rs->nedits; i++) if (rs->edits[i].type != HT2_EDIT_SPL && rs->edits[i].snpID >= nAlts) NM++;
     for (size_t i = 0; i < rs->nedits; i++) {
         const Ht2Edit& e = rs->edits[i];
-        if (e.type == HT2_EDIT_MM) num_mm++;
+        if (e.type == HT2_EDIT_MM) { if (e.snpID >= nAlts) num_mm++; }
         else if (e.type == HT2_EDIT_READ_GAP) {
-            num_go++; num_gx++;
-            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos && rs->edits[i + 1].type == HT2_EDIT_READ_GAP) { i++; num_gx++; }
+            if (e.snpID >= nAlts) { num_go++; num_gx++; }
+            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos && rs->edits[i + 1].type == HT2_EDIT_READ_GAP) {
+                i++; if (rs->edits[i].snpID >= nAlts) num_gx++;
+            }
         } else if (e.type == HT2_EDIT_REF_GAP) {
-            num_go++; num_gx++;
-            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos + 1 && rs->edits[i + 1].type == HT2_EDIT_REF_GAP) { i++; num_gx++; }
+            if (e.snpID >= nAlts) { num_go++; num_gx++; }
+            while (i < (size_t)rs->nedits - 1 && rs->edits[i + 1].pos == rs->edits[i].pos + 1 && rs->edits[i + 1].type == HT2_EDIT_REF_GAP) {
+                i++; if (rs->edits[i].snpID >= nAlts) num_gx++;
+            }
         }
     }
     o += "\tXM:i:"; o += std::to_string(num_mm);
@@ -656,6 +665,44 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2HostRead& r
     appendYF(o, f);
     if (fl.concordant() || fl.discordant()) { o += "\tNH:i:"; o += std::to_string(summ.numAlnsPaired); }
     else { o += "\tNH:i:"; o += std::to_string((fl.pairing == PAIR_UNPAIRED || fl.readMate1()) ? summ.numAlns[0] : summ.numAlns[1]); }
+    // Zs:Z: the known ALTs the alignment went through (sam.h:983-1032)
+    if (nAlts > 0) {
+        std::vector<Ht2Edit> ned(rs->edits, rs->edits + rs->nedits);
+        const size_t len_trimmed = rd.seq.size() - rs->trim5p - rs->trim3p;
+        if (!rs->fw) {   // Edit::invertPoss (edit.cpp:70-111), sort = false
+            std::reverse(ned.begin(), ned.end());
+            for (Ht2Edit& e : ned) e.pos = (e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_SPL) ? (uint32_t)(len_trimmed - e.pos) : (uint32_t)(len_trimmed - e.pos - 1);
+        }
+        bool first = true;
+        uint32_t prev = 0xffffffffu;
+        const char* names = (const char*)img.blob.data() + IH->o_altNames;
+        for (size_t i = 0; i < ned.size(); i++) {
+            if (ned[i].snpID >= nAlts) continue;
+            const uint32_t si = ned[i].snpID;
+            const Ht2Alt& snp = altTab[si];
+            if (si == prev) continue;
+            o += first ? "\tZs:Z:" : ",";
+            uint64_t pos = ned[i].pos;
+            size_t j = i;
+            while (j > 0) {
+                if (ned[j - 1].snpID < nAlts) {
+                    const Ht2Alt& snp2 = altTab[ned[j - 1].snpID];
+                    if (snp2.type == HT2_ALT_SNP_SGL) pos -= (ned[j - 1].pos + 1);
+                    else if (snp2.type == HT2_ALT_SNP_DEL) pos -= ned[j - 1].pos;
+                    else if (snp2.type == HT2_ALT_SNP_INS) pos -= (ned[j - 1].pos + snp.len);
+                    break;
+                }
+                j--;
+            }
+            o += std::to_string(pos);
+            o += (snp.type == HT2_ALT_SNP_SGL) ? "|S|" : (snp.type == HT2_ALT_SNP_DEL ? "|D|" : "|I|");
+            const char* nm = names;
+            for (uint32_t k = 0; k < si; k++) nm += strlen(nm) + 1;
+            o += nm;
+            first = false;
+            prev = si;
+        }
+    }
     o.push_back('\n');
 }
 

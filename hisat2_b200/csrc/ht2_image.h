@@ -28,7 +28,7 @@
 #endif
 
 #define HT2_MAGIC 0x42325448u /* "HT2B" */
-#define HT2_IMAGE_VERSION 4u
+#define HT2_IMAGE_VERSION 5u
 
 // Local-index constants (hier_idx_common.h:23-41).
 #define HT2_LOCAL_INDEX_SIZE     57344u
@@ -97,7 +97,16 @@ struct Ht2RefRecord {
     uint32_t pad;
 };
 
-// ALT record (alt.h:43-204); 'left'/'right' alias pos/len for splice sites.
+// ALT record (alt.h:43-204); 'left'/'right' alias pos/len for splice sites.  As in the reference's
+// union, the low byte of 'seq' doubles as the 'reversed' flag of the deletion copies the loader
+// appends (gfm.h:856-872); 'reversed' mirrors it for convenience.
+#define HT2_ALT_NONE 0u
+#define HT2_ALT_SNP_SGL 1u
+#define HT2_ALT_SNP_INS 2u
+#define HT2_ALT_SNP_DEL 3u
+#define HT2_ALT_SNP_ALT 4u
+#define HT2_ALT_SPLICESITE 5u
+#define HT2_ALT_EXON 6u
 struct Ht2Alt {
     uint32_t pos;
     uint32_t type;
@@ -128,7 +137,11 @@ struct Ht2ImageHeader {
     // ALTs
     uint32_t nAlts;
     uint32_t pad2;
-    uint64_t o_alts;       // Ht2Alt[nAlts]
+    uint64_t o_alts;       // Ht2Alt[nAlts]: augmented with reversed deletions and sorted like the reference's loader
+    uint64_t o_altNames;   // '\0'-separated, nAlts entries (host side: Zs:Z)
+    uint64_t altNamesBytes;
+    uint32_t altsUnsupported; // 1 when the ALT list holds splice sites / exons (not handled by this build)
+    uint32_t pad3;
     // reference names (host side only, for SAM headers)
     uint64_t o_names;      // '\0'-separated, nRefs entries
     uint64_t namesBytes;

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -365,10 +366,11 @@ Ht2Image* ht2_image_load(const char* base_c, std::string& err)
             b.alloc(16, 16);
         }
 
-        // ---- .7.ht2 : ALTs (graph indexes) -----------------------------
+        // ---- .7/.8.ht2 : ALTs and their names (gfm.h:714-903) ------------
         {
-            FileBuf f7(base + ".7.ht2", true);
+            FileBuf f7(base + ".7.ht2", true), f8(base + ".8.ht2", true);
             std::vector<Ht2Alt> alts;
+            std::vector<std::string> names;
             if (f7.d.size() >= 8) {
                 f7.u32(); // endian hint
                 uint32_t nalt = f7.u32();
@@ -378,9 +380,60 @@ Ht2Image* ht2_image_load(const char* base_c, std::string& err)
                     a.seq = f7.u64();
                     alts.push_back(a);
                 }
+                // names: whitespace-separated tokens after two 32-bit words
+                size_t p8 = 8;
+                while (names.size() < alts.size()) {
+                    while (p8 < f8.d.size() && isspace((unsigned char)f8.d[p8])) p8++;
+                    std::string nm;
+                    while (p8 < f8.d.size() && !isspace((unsigned char)f8.d[p8])) nm.push_back((char)f8.d[p8++]);
+                    names.push_back(nm);
+                }
+            }
+            const size_t nalts = alts.size();
+            for (size_t s2 = 0; s2 < nalts; s2++) {
+                const Ht2Alt a = alts[s2];
+                if (a.type == HT2_ALT_SPLICESITE || a.type == HT2_ALT_EXON || a.type == HT2_ALT_SNP_ALT) h.altsUnsupported = 1;
+                if (a.type == HT2_ALT_SNP_DEL) {       // reversed copy at the deletion's last base (gfm.h:866-872)
+                    Ht2Alt r = a;
+                    r.pos = a.pos + a.len - 1;
+                    r.reversed = 1;
+                    r.seq = (a.seq & ~(uint64_t)0xff) | 1u;
+                    alts.push_back(r);
+                    names.push_back(names[s2]);
+                }
+            }
+            if (alts.size() > 1 && alts.size() > nalts) {
+                // EList<pair<ALT, index>>::sort with ALT::operator< (alt.h:89-103)
+                auto altLess = [](const Ht2Alt& x, const Ht2Alt& y) {
+                    if (x.pos != y.pos) return x.pos < y.pos;
+                    if (x.type != y.type) {
+                        if (x.type == HT2_ALT_NONE || y.type == HT2_ALT_NONE) return x.type == HT2_ALT_NONE;
+                        if (x.type == HT2_ALT_SNP_INS) return true;
+                        else if (y.type == HT2_ALT_SNP_INS) return false;
+                        return x.type < y.type;
+                    }
+                    if (x.len != y.len) return x.len < y.len;
+                    if (x.seq != y.seq) return x.seq < y.seq;
+                    return false;
+                };
+                std::vector<uint32_t> order(alts.size());
+                for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+                std::sort(order.begin(), order.end(), [&](uint32_t i, uint32_t j) {
+                    if (altLess(alts[i], alts[j])) return true;
+                    if (altLess(alts[j], alts[i])) return false;
+                    return i < j;
+                });
+                std::vector<Ht2Alt> a2(alts.size());
+                std::vector<std::string> n2(alts.size());
+                for (size_t i = 0; i < order.size(); i++) { a2[i] = alts[order[i]]; n2[i] = names[order[i]]; }
+                alts.swap(a2); names.swap(n2);
             }
             h.nAlts = (uint32_t)alts.size();
             h.o_alts = b.put(alts.data(), alts.size() * sizeof(Ht2Alt), 16);
+            std::string packed;
+            for (size_t i = 0; i < names.size(); i++) { packed += names[i]; packed.push_back('\0'); }
+            h.o_altNames = b.put(packed.data(), packed.size(), 16);
+            h.altNamesBytes = packed.size();
         }
 
         b.alloc(0, 128);

@@ -139,6 +139,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
         Ht2Hit* tp = poolAlloc();
         Ht2Hit& tempHit = *tp;
         initHit(tempHit, coord.fw != 0, f.extoff + 1 - f.extlen, f.extlen, 0, 0, coord.ref, coord.off, coord.joinedOff);
+        if (GRAPH && !adjustWithALT(tempHit, rdi)) { W->poolTop--; f.ri--; break; }   // spliced_aligner.h:946, 1139, 1635, 1826
         if (!compatibleWith(tempHit, hit, rdi)) {
             W->poolTop--;
             if (f.count == 1) { f.ri--; break; }
@@ -224,6 +225,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
         Ht2Hit* tp = poolAlloc();
         Ht2Hit& tempHit = *tp;
         initHit(tempHit, coord.fw != 0, f.extoff + 1 - f.extlen, f.extlen, 0, 0, coord.ref, coord.off, coord.joinedOff);
+        if (GRAPH && !adjustWithALT(tempHit, rdi)) { W->poolTop--; f.ri--; break; }   // spliced_aligner.h:946, 1139, 1635, 1826
         if (!compatibleWith(tempHit, hit, rdi)) { W->poolTop--; f.ri--; break; }
         if (f.uniqueStop) {
             uint32_t leftext = HT2_IDX_MAX32, rightext = 0;
@@ -367,6 +369,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
         Ht2Hit* tp = poolAlloc();
         Ht2Hit& tempHit = *tp;
         initHit(tempHit, coord.fw != 0, f.extoff + 1 - f.extlen, f.extlen, 0, 0, coord.ref, coord.off, coord.joinedOff);
+        if (GRAPH && !adjustWithALT(tempHit, rdi)) { W->poolTop--; f.ri++; break; }   // spliced_aligner.h:946, 1139, 1635, 1826
         if (!compatibleWith(hit, tempHit, rdi)) {
             W->poolTop--;
             if (f.count == 1) { f.ri++; break; }
@@ -456,6 +459,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
         Ht2Hit* tp = poolAlloc();
         Ht2Hit& tempHit = *tp;
         initHit(tempHit, coord.fw != 0, f.extoff + 1 - f.extlen, f.extlen, 0, 0, coord.ref, coord.off, coord.joinedOff);
+        if (GRAPH && !adjustWithALT(tempHit, rdi)) { W->poolTop--; f.ri++; break; }   // spliced_aligner.h:946, 1139, 1635, 1826
         if (!compatibleWith(hit, tempHit, rdi)) { W->poolTop--; f.ri++; break; }
         uint32_t leftext = 0, rightext = HT2_IDX_MAX32;
         extend(tempHit, rdi, leftext, rightext, 0);
@@ -641,6 +645,9 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
             uint32_t leftext = HT2_IDX_MAX32, rightext = HT2_IDX_MAX32;
             extend(W->genomeHits[hi], rdi, leftext, rightext, 0);
         }
+#if !defined(__CUDA_ARCH__) && defined(HT2_TRACE)
+        for (uint32_t gi = 0; gi < W->nGenomeHits; gi++) { Ht2Hit& g = W->genomeHits[gi]; fprintf(stderr, "ext %u rdoff %u len %u toff %u joined %u hitcount %u ned %u score %lld\n", gi, g.rdoff, g.len, g.toff, g.joinedOff, g.hitcount, g.nedits, (long long)g.score); }
+#endif
         for (uint32_t i = 0; i < W->nGenomeHits; i++) W->genomeHitsDone[i] = 0;
         W->hybIter = 0;
         W->st = TS_HYB_PICK;

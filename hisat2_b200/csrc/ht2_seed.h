@@ -24,8 +24,8 @@ struct Ht2SeedState {          // ReadBWTHit cursor (hi_aligner.h:216-391)
 };
 
 // One step of the search on base c from [top,bot): linear -> ht2_lf2, graph -> mapGLF / mapGLF1.
-template <bool GRAPH>
-HT2_HD void ht2_seed_step(const Ht2Fm<uint32_t>& fm, uint32_t top, uint32_t bot, int c, uint32_t kseeds,
+template <bool GRAPH, typename IT>
+HT2_HD void ht2_seed_step(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c, uint32_t kseeds,
                           uint32_t& ntop, uint32_t& nbot, uint32_t& nntop, uint32_t& nnbot,
                           uint16_t (*ie)[2], uint32_t& nie, Ht2SeedState& st) {
     nie = 0;
@@ -85,7 +85,7 @@ HT2_HD void ht2_seed_partial(const Ht2Fm<uint32_t>& fm, const Ht2Params& P, cons
         const int c = seq[len - dep - 1];
         uint32_t ttop = 0, tbot = 0, tntop = 0, tnbot = 0;
         ntie = 0;
-        if (c <= 3) ht2_seed_step<GRAPH>(fm, top, bot, c, P.kseeds, ttop, tbot, tntop, tnbot, tie, ntie, st);
+        if (c <= 3) ht2_seed_step<GRAPH, uint32_t>(fm, top, bot, c, P.kseeds, ttop, tbot, tntop, tnbot, tie, ntie, st);
         if (ttop >= tbot) break;
         const uint32_t nw = tnbot - tntop, ow = nbot - ntop;
         if (pseudogeneStop_) {

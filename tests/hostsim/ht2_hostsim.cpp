@@ -15,9 +15,10 @@
 
 // HT2_RECURSIVE=1 runs the recursive formulation (ht2_core_impl.h) instead of the
 // explicit-stack state machine the kernels use (ht2_machine.h); both must agree.
-static void runRead(Ht2Aligner& A) {
+template <typename ALIGNER>
+static void runRead(ALIGNER& A) {
     static const bool recursive = getenv("HT2_RECURSIVE") != NULL;
-    if (recursive) { runRead(A); return; }
+    if (recursive) { A.go(); return; }
     A.machineStart();
     while (!A.machineDone()) A.machineStep();
 }
@@ -71,57 +72,13 @@ static void seedDump(const Ht2Image& img, const Ht2Params& P, const std::vector<
     }
 }
 
-int main(int argc, char** argv) {
-    if (argc >= 5 && !strcmp(argv[1], "--seed-dump")) {
-        std::string err;
-        Ht2Image* img = ht2_image_load(argv[2], err);
-        if (!img) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-        std::vector<Ht2HostRead> reads;
-        if (!ht2_read_fasta(argv[3], reads, 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-        Ht2Params P;
-        ht2_default_params(P, *img, atoi(argv[4]) != 0);
-        const Ht2ImageHeader* H = (const Ht2ImageHeader*)img->blob.data();
-        if (H->global.linearFM) seedDump<false>(*img, P, reads); else seedDump<true>(*img, P, reads);
-        return 0;
-    }
-    if (argc < 4) { fprintf(stderr, "usage: %s index reads.fa out.sam\n", argv[0]); return 2; }
-    std::string err;
-    Ht2Image* img = ht2_image_load(argv[1], err);
-    if (!img) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-    std::vector<Ht2HostRead> reads;
-    // usage: ht2_hostsim index reads.fa out.sam            (unpaired)
-    //        ht2_hostsim index reads_1.fa out.sam reads_2.fa (paired, --fr)
-    const bool pairedMode = argc > 4;
-    if (!ht2_read_reads(argv[2], reads, pairedMode ? 1 : 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-    std::vector<Ht2HostRead> reads2;
-    if (pairedMode && !ht2_read_reads(argv[4], reads2, 2, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-    Ht2Params P;
-    ht2_default_params(P, *img, true);
-    // HT2_OPTS="khits=1,mp_max=4,...": the ht2gpu_options_t fields, mapped like applyOptions (ht2_gpu.cu)
-    if (const char* os = getenv("HT2_OPTS")) {
-        std::string o(os); size_t p0 = 0;
-        bool kseedsGiven = false;
-        while (p0 < o.size()) {
-            size_t c = o.find(',', p0); if (c == std::string::npos) c = o.size();
-            std::string kv = o.substr(p0, c - p0); p0 = c + 1;
-            size_t e = kv.find('='); if (e == std::string::npos) continue;
-            std::string k = kv.substr(0, e); int v = atoi(kv.c_str() + e + 1);
-            if (k == "khits") P.khits = (uint32_t)v; else if (k == "max_seeds") { P.kseeds = (uint32_t)v; kseedsGiven = true; }
-            else if (k == "secondary") P.secondary = v; else if (k == "mp_max") P.mmpMax = v; else if (k == "mp_min") P.mmpMin = v;
-            else if (k == "sp_max") P.scpMax = v; else if (k == "sp_min") P.scpMin = v; else if (k == "np") P.npen = v;
-            else if (k == "rdg_const") P.rdGapConst = v; else if (k == "rdg_linear") P.rdGapLinear = v;
-            else if (k == "rfg_const") P.rfGapConst = v; else if (k == "rfg_linear") P.rfGapLinear = v;
-            else if (k == "ignore_quals") P.mmcostConstant = v; else if (k == "nofw") P.nofw = v; else if (k == "norc") P.norc = v;
-            else if (k == "min_frag") P.minFrag = (uint32_t)v; else if (k == "max_frag") P.maxFrag = (uint32_t)v;
-            else if (k == "no_mixed") P.mixed = v ? 0 : 1; else if (k == "no_discordant") P.discord = v ? 0 : 1;
-            else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
-        }
-        if (!kseedsGiven) P.kseeds = P.khits * 2 > 5 ? P.khits * 2 : 5;
-    }
+template <bool GRAPH>
+static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads, std::vector<Ht2HostRead>& reads2, bool pairedMode,
+                    const char* outPath) {
     std::string sam;
     ht2_sam_header(sam, *img);
     Ht2Work* W = new Ht2Work();
-    Ht2Aligner A;
+    Ht2AlignerT<GRAPH> A;
     size_t nerr = 0;
     uint64_t nLF = 0;
     long long finishNs = 0;
@@ -192,10 +149,63 @@ int main(int argc, char** argv) {
         out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
         { auto t0 = std::chrono::steady_clock::now(); ht2_finish_unpaired(sam, *img, P, rd, f, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
     }
-    FILE* fo = fopen(argv[3], "wb");
+    FILE* fo = fopen(outPath, "wb");
     fwrite(sam.data(), 1, sam.size(), fo);
     fclose(fo);
     fprintf(stderr, "SAM back end: %.1f ms total, %.2f us per read\n", finishNs / 1e6, finishNs / 1e3 / (double)reads.size());
     fprintf(stderr, "reads=%zu errors=%zu LF=%llu maxPool=%u maxDepth=%u maxEdits=%u maxSearched=%u maxRes=%u maxGH=%u maxPH=%u/%u sizeof(Work)=%zu\n", reads.size(), nerr, (unsigned long long)nLF, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[6], mx[7], sizeof(Ht2Work));
     return 0;
 }
+
+int main(int argc, char** argv) {
+    if (argc >= 5 && !strcmp(argv[1], "--seed-dump")) {
+        std::string err;
+        Ht2Image* img = ht2_image_load(argv[2], err);
+        if (!img) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        std::vector<Ht2HostRead> reads;
+        if (!ht2_read_fasta(argv[3], reads, 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        Ht2Params P;
+        ht2_default_params(P, *img, atoi(argv[4]) != 0);
+        const Ht2ImageHeader* H = (const Ht2ImageHeader*)img->blob.data();
+        if (H->global.linearFM) seedDump<false>(*img, P, reads); else seedDump<true>(*img, P, reads);
+        return 0;
+    }
+    if (argc < 4) { fprintf(stderr, "usage: %s index reads.fa out.sam\n", argv[0]); return 2; }
+    std::string err;
+    Ht2Image* img = ht2_image_load(argv[1], err);
+    if (!img) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    std::vector<Ht2HostRead> reads;
+    // usage: ht2_hostsim index reads.fa out.sam            (unpaired)
+    //        ht2_hostsim index reads_1.fa out.sam reads_2.fa (paired, --fr)
+    const bool pairedMode = argc > 4;
+    if (!ht2_read_reads(argv[2], reads, pairedMode ? 1 : 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    std::vector<Ht2HostRead> reads2;
+    if (pairedMode && !ht2_read_reads(argv[4], reads2, 2, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    Ht2Params P;
+    ht2_default_params(P, *img, true);
+    // HT2_OPTS="khits=1,mp_max=4,...": the ht2gpu_options_t fields, mapped like applyOptions (ht2_gpu.cu)
+    if (const char* os = getenv("HT2_OPTS")) {
+        std::string o(os); size_t p0 = 0;
+        bool kseedsGiven = false;
+        while (p0 < o.size()) {
+            size_t c = o.find(',', p0); if (c == std::string::npos) c = o.size();
+            std::string kv = o.substr(p0, c - p0); p0 = c + 1;
+            size_t e = kv.find('='); if (e == std::string::npos) continue;
+            std::string k = kv.substr(0, e); int v = atoi(kv.c_str() + e + 1);
+            if (k == "khits") P.khits = (uint32_t)v; else if (k == "max_seeds") { P.kseeds = (uint32_t)v; kseedsGiven = true; }
+            else if (k == "secondary") P.secondary = v; else if (k == "mp_max") P.mmpMax = v; else if (k == "mp_min") P.mmpMin = v;
+            else if (k == "sp_max") P.scpMax = v; else if (k == "sp_min") P.scpMin = v; else if (k == "np") P.npen = v;
+            else if (k == "rdg_const") P.rdGapConst = v; else if (k == "rdg_linear") P.rdGapLinear = v;
+            else if (k == "rfg_const") P.rfGapConst = v; else if (k == "rfg_linear") P.rfGapLinear = v;
+            else if (k == "ignore_quals") P.mmcostConstant = v; else if (k == "nofw") P.nofw = v; else if (k == "norc") P.norc = v;
+            else if (k == "min_frag") P.minFrag = (uint32_t)v; else if (k == "max_frag") P.maxFrag = (uint32_t)v;
+            else if (k == "no_mixed") P.mixed = v ? 0 : 1; else if (k == "no_discordant") P.discord = v ? 0 : 1;
+            else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
+        }
+        if (!kseedsGiven) P.kseeds = P.khits * 2 > 5 ? P.khits * 2 : 5;
+    }
+    const Ht2ImageHeader* Hh = (const Ht2ImageHeader*)img->blob.data();
+    return Hh->global.linearFM ? alignAll<false>(img, P, reads, reads2, pairedMode, argv[3])
+                               : alignAll<true>(img, P, reads, reads2, pairedMode, argv[3]);
+}
+

@@ -97,7 +97,7 @@ def test_image_build_is_host_only_and_consistent(lib):
     img = api.Index.build_image(os.path.join(GOLDEN, "tiny"))
     assert img[:4].tobytes() == b"HT2B"
     hdr = np.frombuffer(img[:16].tobytes(), dtype="<u4")
-    assert hdr[1] == 4  # image version
+    assert hdr[1] == 5  # image version
     total = int(np.frombuffer(img[8:16].tobytes(), dtype="<u8")[0])
     assert total == img.nbytes and total % 128 == 0
     # global geometry (Ht2Gfm at offset 16): len, gbwtLen, numNodes, eftabLen, linearFM, sideSz, sideGbwtSz, sideGbwtLen
