@@ -28,12 +28,12 @@
     // tmp_edits helpers
     HT2_HD bool tmpPush(const Ht2Edit& e) {
         Ht2AltScratch& S = W->alt;
-        if (S.ntmp >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
+        if (S.ntmp >= HT2_ALT_TMP_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
         S.tmp[S.ntmp++] = e; return true;
     }
     HT2_HD bool tmpInsertFront(const Ht2Edit& e) {
         Ht2AltScratch& S = W->alt;
-        if (S.ntmp >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
+        if (S.ntmp >= HT2_ALT_TMP_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
         for (uint32_t i = S.ntmp; i > 0; i--) S.tmp[i] = S.tmp[i - 1];
         S.tmp[0] = e; S.ntmp++; return true;
     }
@@ -42,12 +42,18 @@
         for (uint32_t i = 0; i + n < S.ntmp; i++) S.tmp[i] = S.tmp[i + n];
         S.ntmp -= n;
     }
-    HT2_HD void editsFromTmp(Ht2Hit& h) { for (uint32_t i = 0; i < W->alt.ntmp; i++) h.edits[i] = W->alt.tmp[i]; h.nedits = W->alt.ntmp; }
+    HT2_HD void editsFromTmp(Ht2Hit& h) {
+        uint32_t n = W->alt.ntmp;
+        if (n > HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; n = HT2_MAX_EDITS; }   // the alignment itself needs more edits than a hit holds
+        for (uint32_t i = 0; i < n; i++) h.edits[i] = W->alt.tmp[i];
+        h.nedits = n;
+    }
     HT2_HD void candClear() { W->alt.ncand = 0; }
     HT2_HD void candPushTmp() {
         Ht2AltScratch& S = W->alt;
         if (!S.wantCands) return;
         if (S.ncand >= HT2_ALT_CANDS) { HT2_GERR(1); return; }
+        if (S.ntmp > HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return; }
         for (uint32_t i = 0; i < S.ntmp; i++) S.cand[S.ncand][i] = S.tmp[i];
         S.candN[S.ncand] = (uint8_t)S.ntmp;
         S.ncand++;

@@ -23,11 +23,11 @@
 #ifndef HT2_MAX_RDLEN
 #define HT2_MAX_RDLEN 256
 #endif
-#define HT2_MAX_EDITS 24
+#define HT2_MAX_EDITS 40
 #define HT2_MAX_PHITS 64
 #define HT2_MAX_GHITS 24
 #define HT2_POOL 40
-#define HT2_IE_POOL 224          /* in-edge entries per strand (graph indexes) */
+#define HT2_IE_POOL 96           /* in-edge entries per strand (graph indexes) */
 #define HT2_SEARCHED_BYTES 24576   /* ~600 searched hits (40 B typical) for both mates */
 
 #define HT2_MAX_RES 64
@@ -157,11 +157,12 @@ struct Ht2Frame {
 };
 
 // Scratch of one alignWithALTs call (graph indexes; ht2_alt.h)
+#define HT2_ALT_TMP_EDITS 72     /* trial edit list of the ALT recursion: a 27-base deletion ALT alone is 27 read-gap edits */
 #define HT2_ALT_CANDS 4
 #define HT2_ALT_BUFS 4
 #define HT2_ALT_MAXDEP 24
 struct Ht2AltScratch {
-    Ht2Edit  tmp[HT2_MAX_EDITS];            // tmp_edits
+    Ht2Edit  tmp[HT2_ALT_TMP_EDITS];        // tmp_edits
     uint32_t ntmp;
     int32_t  best_rdoff;
     uint32_t numALTsTried;

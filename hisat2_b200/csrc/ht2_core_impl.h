@@ -580,7 +580,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::go()
     for (uint32_t rdi = 0; rdi < 2; rdi++) {
         for (uint32_t fwi = 0; fwi < 2; fwi++) {
             Ht2ReadHits& h = W->hits[rdi][fwi];
-            h.len = W->rd[rdi].len; h.cur = 0; h.done = 0; h.numPartialSearch = 0; h.numUniqueSearch = 0; h.nhits = 0;
+            h.len = W->rd[rdi].len; h.cur = 0; h.done = 0; h.numPartialSearch = 0; h.numUniqueSearch = 0; h.nhits = 0; h.nie = 0;
         }
         W->nSearched[rdi] = 0;
     }
