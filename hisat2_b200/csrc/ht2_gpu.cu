@@ -83,7 +83,8 @@ __device__ __forceinline__ bool ht2_dev_filter(const DevBatch& b, uint32_t ri, i
 
 // Set up workspace W for unit u (one read or one pair): filters, seeds, reads.
 // Returns true when there is something to align (machineStart() was called).
-__device__ __noinline__ bool ht2_setup_unit(Ht2Aligner& A, const Ht2Params& P, const DevBatch& b, uint32_t u, uint32_t& filtBits)
+template <typename ALIGNER>
+__device__ __noinline__ bool ht2_setup_unit(ALIGNER& A, const Ht2Params& P, const DevBatch& b, uint32_t u, uint32_t& filtBits)
 {
     Ht2Work* W = A.W;
     W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0;
@@ -461,7 +462,7 @@ ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, De
 #define RG_BUSY 254u
 #define PL_MIN_GROUP 16
 
-template <int NW, int K>
+template <int NW, int K, bool GRAPH>
 __global__ void __launch_bounds__(32 * NW)
 ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
 {
@@ -477,7 +478,7 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b,
     for (int i = t; i < S; i += 32 * NW) sCode[i] = RG_NEED;
     if (t < RG_BINS) sCount[t] = (t == RG_NEED) ? S : 0;
     if (t == 0) { sTarget = RG_NEED; sExit = 0; sLock = 0; }
-    Ht2Aligner A;
+    Ht2AlignerT<GRAPH> A;
     A.bind(blob, &P, base);
     __syncthreads();
     volatile unsigned int* vCode = sCode;
@@ -774,7 +775,7 @@ static int finishOpen(ht2gpu_handle* h)
     const Ht2ImageHeader* H = h->img->header();
     if (H->magic != HT2_MAGIC || H->version != HT2_IMAGE_VERSION) { h->err = "bad index image"; return HT2GPU_ERR_INDEX; }
     if (!h->opt.no_spliced_alignment) { h->err = "spliced alignment is not implemented in this build; pass --no-spliced-alignment"; return HT2GPU_ERR_UNSUPPORTED; }
-    h->graph = !H->global.linearFM;   // graph indexes: seed search only (ht2gpu_seed_search); alignment refuses them
+    h->graph = !H->global.linearFM;   // graph (SNP) indexes: ALT-aware aligner instantiation, graph seed kernel
     applyOptions(h->P, *h->img, h->opt);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -787,6 +788,10 @@ static int finishOpen(ht2gpu_handle* h)
     if (h->opt.warp_per_read == 3) h->regroup = false; // 3 = plain one-lane-per-read dispatcher
     h->blockRegroup = (h->opt.warp_per_read == 4);
     h->pool = (h->opt.warp_per_read == 5 || h->opt.warp_per_read == 0);   // default
+    if (h->graph) {   // graph indexes run the pool kernel <8,4> only
+        h->pool = true; h->blockRegroup = false; h->regroup = true; h->lanes = 1;
+        h->opt.threads_per_block = 256; h->opt.slots_per_lane = 4;
+    }
     if (h->blockRegroup || h->pool) h->regroup = true;
     if (h->regroup) {
         h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 32 * RG_WARPS;
@@ -998,14 +1003,19 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
     CK(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned int), h->stream));
     if (h->regroup) {
         uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
+        if (h->graph) {     // graph (SNP) indexes: the pool kernel with the ALT-aware aligner
+            ht2_align_pool_kernel<8, 4, true><<<grid, 256, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
+            CK(cudaGetLastError());
+            return HT2GPU_OK;
+        }
         if (h->pool) {
             const int key = h->poolWarps * 100 + h->rgK;
             switch (key) {
-                case 802:  ht2_align_pool_kernel<8, 2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                case 808:  ht2_align_pool_kernel<8, 8><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                case 1602: ht2_align_pool_kernel<16, 2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                case 1604: ht2_align_pool_kernel<16, 4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                default:   ht2_align_pool_kernel<8, 4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 802:  ht2_align_pool_kernel<8, 2, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 808:  ht2_align_pool_kernel<8, 8, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 1602: ht2_align_pool_kernel<16, 2, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                case 1604: ht2_align_pool_kernel<16, 4, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+                default:   ht2_align_pool_kernel<8, 4, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
             }
             CK(cudaGetLastError());
             return HT2GPU_OK;
@@ -1076,9 +1086,9 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
     if (!h || !b || !res) return HT2GPU_ERR_ARG;
     if (b->paired && (b->n_reads & 1)) { h->err = "paired batch needs an even number of reads"; return HT2GPU_ERR_ARG; }
     memset(res, 0, sizeof(*res));
-    if (h->graph) {
-        h->err = "alignment over graph (SNP) indexes is not implemented in this build (ALT-aware extension); "
-                 "ht2gpu_seed_search supports them";
+    if (h->graph && h->img->header()->altsUnsupported) {
+        h->err = "this graph index holds splice-site / exon ALTs; alignment through them is not implemented in this build "
+                 "(SNP / indel ALTs are; ht2gpu_seed_search works on any graph index)";
         return HT2GPU_ERR_UNSUPPORTED;
     }
     if (b->n_reads == 0) return HT2GPU_OK;

@@ -28,6 +28,10 @@ for L in 36 150 250; do
     python ../tools/simreads.py $D/22_20-21M.fa 20000 $D/len${L} --seed $((70 + L)) --paired --indel 0.004 --nrate 0.002 --sub 0.01 --ragged --rdlen $L
   fi
 done
+# reads carrying ALT alleles of the bundled SNP list (graph index 22_20-21M_snp)
+if [ ! -f $D/alt20k_1.fa ]; then
+  python ../tools/altreads.py $D/22_20-21M.fa $D/22_20-21M.snp 20000 $D/alt20k --seed 9 --paired
+fi
 if [ ! -f $D/sim200k_1.fa ]; then
   python ../tools/simreads.py $D/22_20-21M.fa 200000 $D/sim200k --seed 5 --paired
 fi

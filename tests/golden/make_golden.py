@@ -14,6 +14,7 @@
   tiny.snp           seeded SNP list (single / deletion / insertion) over tiny.fa
   tiny_snp.{1..8}.ht2  hisat2-build-s --ftabchars 7 --snp tiny.snp tiny.fa tiny_snp  (GRAPH index)
   tiny_snp_dump.txt  ref_dump on the graph index: H/C lines plus G lines (node range, in-edge list)
+  tiny_snp_{se,pe,se_fq}.sam  hisat2-align-s --no-spliced-alignment -x tiny_snp on the tiny read sets (Zs:Z tags)
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import os, subprocess, sys
@@ -111,6 +112,23 @@ def graph():
                          stdout=subprocess.PIPE).stdout.decode().splitlines(True)
     with open(os.path.join(G, "tiny_snp_dump.txt"), "w") as fo:
         fo.writelines(l for l in out if int(l.split()[1]) in keep)
+    graph_sams()
+
+
+def graph_sams():
+    """full-path goldens on the graph index (ALT-aware extension, Zs:Z)"""
+    al = os.path.join(REF, "hisat2-align-s")
+    # tiny_alt_{1,2}.fa: reads sampled from the reference with half of the ALTs applied (tools/altreads.py --seed 4)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "altreads.py"), os.path.join(G, "tiny.fa"), os.path.join(G, "tiny.snp"),
+                    "400", os.path.join(G, "tiny_alt"), "--seed", "4", "--paired"], check=True)
+    for args, outname in ((["-f", "-U", "tiny_se.fa"], "tiny_snp_se.sam"), (["-f", "-1", "tiny_pe_1.fa", "-2", "tiny_pe_2.fa"], "tiny_snp_pe.sam"),
+                          (["-q", "-U", "tiny_se.fq"], "tiny_snp_se_fq.sam"), (["-f", "-U", "tiny_alt_1.fa"], "tiny_snp_alt_se.sam"),
+                          (["-f", "-1", "tiny_alt_1.fa", "-2", "tiny_alt_2.fa"], "tiny_snp_alt_pe.sam")):
+        subprocess.run([al, "--no-spliced-alignment", "-x", "tiny_snp"] + args + ["-S", outname + ".tmp"], check=True, cwd=G,
+                       stderr=subprocess.DEVNULL)
+        with open(os.path.join(G, outname + ".tmp")) as fi, open(os.path.join(G, outname), "w") as fo:
+            fo.writelines(l for l in fi if not l.startswith("@PG"))
+        os.remove(os.path.join(G, outname + ".tmp"))
 
 
 def fastq():
@@ -190,6 +208,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fastq":
         fastq()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "graph_sams":
+        graph_sams()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "graph":
         graph()

@@ -189,9 +189,39 @@ def test_seed_search_kernel_matches_reference_dump(h2, idx, name):
     want = open(os.path.join(GOLDEN, name)).readlines()
     assert got == want
     assert res.n_lf > 0 and res.alg_bytes > 0 and res.err == 0
-    if idx == "tiny_snp":   # alignment over graph indexes is refused loudly, never silently wrong
-        with pytest.raises(h2.Ht2GpuError):
-            index.align(batch)
+    index.close()
+
+
+def test_graph_index_alignment_matches_golden_reference_sam(h2):
+    """GRAPH (SNP) index end to end on the GPU (pool kernel with the ALT-aware aligner): SE, PE, FASTQ and
+    reads carrying ALT alleles; byte-identical SAM incl. Zs:Z tags."""
+    index = h2.Index(os.path.join(GOLDEN, "tiny_snp"))
+    for args, gold in ((("tiny_se.fa",), "tiny_snp_se.sam"), (("tiny_pe_1.fa", "tiny_pe_2.fa"), "tiny_snp_pe.sam"),
+                       (("tiny_se.fq",), "tiny_snp_se_fq.sam"), (("tiny_alt_1.fa",), "tiny_snp_alt_se.sam"),
+                       (("tiny_alt_1.fa", "tiny_alt_2.fa"), "tiny_snp_alt_pe.sam")):
+        rd = h2.ReadBatch.from_fastq if args[0].endswith(".fq") else h2.ReadBatch.from_fasta
+        batch = rd(os.path.join(GOLDEN, args[0]), path2=os.path.join(GOLDEN, args[1]) if len(args) > 1 else None)
+        sam, _ = gpu_sam(index, batch)
+        assert sam_lines(sam) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), gold
+    index.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("name,paired", [("reads", False), ("hard20k", False), ("alt20k", False), ("sim10k", True), ("alt20k", True)])
+def test_bundled_graph_index_matches_reference_binary_run_here(h2, name, paired, tmp_path):
+    """The reference's bundled example index 22_20-21M_snp (BASELINE configs[0] literally): SAM identical to the
+    reference run on this box, incl. 20k reads / pairs that carry ALT alleles (3.5k alignments through ALTs)."""
+    base = os.path.join(DATA, "22_20-21M_snp")
+    f1, f2 = os.path.join(DATA, name + "_1.fa"), os.path.join(DATA, name + "_2.fa")
+    if not (os.path.exists(base + ".1.ht2") and os.path.exists(f1)):
+        pytest.skip("data/ not staged")
+    index = h2.Index(base)
+    batch = h2.ReadBatch.from_fasta(f1, path2=f2 if paired else None)
+    sam, _ = gpu_sam(index, batch)
+    out = str(tmp_path / "ref.sam")
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", base] + (["-1", f1, "-2", f2] if paired else ["-U", f1]) +
+                   ["-S", out, "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    assert sam_lines(sam) == sam_lines(open(out, "rb").read())
     index.close()
 
 
