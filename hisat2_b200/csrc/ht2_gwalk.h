@@ -288,6 +288,14 @@ struct Ht2GroupWalk {
         G.nst = 0; G.err = 0; G.nLF = 0;
         if (nelt > HT2_GW_MAXELT) { G.err |= 16; nelt = HT2_GW_MAXELT; }
         G.nelt = nelt;
+        if (nelt == 1) {
+            // one node: the walk follows its first row only (extra incoming edges are skipped by advance(),
+            // group_walk.h:1065-1090), i.e. it is GFM::getOffset(row, node) -- no state machinery needed
+            uint32_t steps = 0;
+            G.offs[0] = ht2g_get_offset(fm, top, node_top, steps);
+            G.nLF += steps;
+            return;
+        }
         for (uint32_t i = 0; i < nelt; i++) { G.offs[i] = HT2_GW_MASK; G.fmapRange[i] = 0; }
         const uint32_t r = newState();
         Ht2GwState& S = G.st[r];

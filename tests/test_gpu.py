@@ -301,7 +301,7 @@ def test_chr22_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
 def test_long_pairs_capacity_errors_are_flagged_never_silent(h2, chr22, tmp_path):
-    """2x250 bp pairs with indels and Ns: a handful of pairs need more than HT2_MAX_EDITS (24) edits in one
+    """2x250 bp pairs with indels and Ns: a handful of pairs need more than HT2_MAX_EDITS (40) edits in one
     alignment; those are flagged (err != 0, HT2GPU_ERR_CAPACITY) and every OTHER pair is byte-identical."""
     f1, f2 = os.path.join(DATA, "len250_1.fa"), os.path.join(DATA, "len250_2.fa")
     if not os.path.exists(f1):

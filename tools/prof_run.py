@@ -8,7 +8,7 @@ fa = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "data", "sim200k_1
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 opts = dict(kv.split("=") for kv in sys.argv[3:])
 opts = {k: int(v) for k, v in opts.items()}
-idx = h2.Index(os.path.join(ROOT, "data", "22_20-21M"), **opts)
+idx = h2.Index(os.path.join(ROOT, "data", os.environ.get("HT2_INDEX", "22_20-21M")), **opts)
 print("opts", opts)
 if fa.startswith("synth:"):          # bench.py's synthetic workload, e.g. synth:1000000
     import numpy as np
