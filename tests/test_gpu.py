@@ -129,10 +129,11 @@ def test_command_line_front_end_matches_golden(tmp_path):
     cli = os.path.join(ROOT, "hisat2_b200", "hisat2-b200")
     if not os.path.exists(cli):
         pytest.skip("CLI not built (python -m hisat2_b200.build)")
-    for args, gold in ((["-q", "-U", "tiny_se.fq"], "tiny_se_fq.sam"), (["-f", "-U", "tiny_se.fa"], "tiny_se.sam"),
-                       (["-q", "-1", "tiny_pe_1.fq", "-2", "tiny_pe_2.fq"], "tiny_pe_fq.sam")):
+    for index, args, gold in (("tiny", ["-q", "-U", "tiny_se.fq"], "tiny_se_fq.sam"), ("tiny", ["-f", "-U", "tiny_se.fa"], "tiny_se.sam"),
+                              ("tiny", ["-q", "-1", "tiny_pe_1.fq", "-2", "tiny_pe_2.fq"], "tiny_pe_fq.sam"),
+                              ("tiny_snp", ["-f", "-1", "tiny_alt_1.fa", "-2", "tiny_alt_2.fa"], "tiny_snp_alt_pe.sam")):   # graph index
         out = str(tmp_path / "cli.sam")
-        subprocess.run([cli, "--no-spliced-alignment", "-x", "tiny"] + args + ["-S", out, "-p", "4"], cwd=GOLDEN, check=True,
+        subprocess.run([cli, "--no-spliced-alignment", "-x", index] + args + ["-S", out, "-p", "4"], cwd=GOLDEN, check=True,
                        stderr=subprocess.DEVNULL)
         assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), args
     # anything the build cannot honour bit-exactly is refused with a non-zero exit code
@@ -207,7 +208,8 @@ def test_graph_index_alignment_matches_golden_reference_sam(h2):
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
-@pytest.mark.parametrize("name,paired", [("reads", False), ("hard20k", False), ("alt20k", False), ("sim10k", True), ("alt20k", True)])
+@pytest.mark.parametrize("name,paired", [("reads", False), ("hard20k", False), ("alt20k", False), ("sim200k", False), ("sim10k", True),
+                                         ("alt20k", True), ("hard20k", True)])
 def test_bundled_graph_index_matches_reference_binary_run_here(h2, name, paired, tmp_path):
     """The reference's bundled example index 22_20-21M_snp (BASELINE configs[0] literally): SAM identical to the
     reference run on this box, incl. 20k reads / pairs that carry ALT alleles (3.5k alignments through ALTs)."""
