@@ -63,6 +63,8 @@ int main(int argc, char** argv)
     o.no_spliced_alignment = 0; // must be requested explicitly, like the reference's default is spliced
     const char *idx = NULL, *u = NULL, *m1 = NULL, *m2 = NULL, *out = NULL;
     bool fastq = true; size_t batchSz = 1000000; uint32_t gseed = 0;
+    bool mpGiven = false;   // "--mp a,b" becomes MMP=Q,a,b, which switches the cost model back to quality-aware even
+                            // under --ignore-quals (aligner_seed_policy.cpp:396-418)
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(1); } return argv[++i]; };
@@ -71,7 +73,7 @@ int main(int argc, char** argv)
         else if (a == "--no-spliced-alignment") o.no_spliced_alignment = 1;
         else if (a == "-k") o.khits = atoi(next()); else if (a == "--max-seeds") o.max_seeds = atoi(next());
         else if (a == "--secondary") o.secondary = 1;
-        else if (a == "--mp") two(next(), o.mp_max, o.mp_min); else if (a == "--sp") { two(next(), o.sp_max, o.sp_min); o.sp_min = o.sp_max; /* the reference reads BOTH values from the first number, aligner_seed_policy.cpp:438-441 */ }
+        else if (a == "--mp") { two(next(), o.mp_max, o.mp_min); mpGiven = true; } else if (a == "--sp") { two(next(), o.sp_max, o.sp_min); o.sp_min = o.sp_max; /* the reference reads BOTH values from the first number, aligner_seed_policy.cpp:438-441 */ }
         else if (a == "--np") o.np = atoi(next()); else if (a == "--rdg") two(next(), o.rdg_const, o.rdg_linear);
         else if (a == "--rfg") two(next(), o.rfg_const, o.rfg_linear); else if (a == "--ignore-quals") o.ignore_quals = 1;
         else if (a == "--nofw") o.nofw = 1; else if (a == "--norc") o.norc = 1;
@@ -85,6 +87,7 @@ int main(int argc, char** argv)
     }
     if (!idx || (!u && !(m1 && m2))) { usage(); return 1; }
     if (!o.no_spliced_alignment) { fprintf(stderr, "Error: spliced alignment is not implemented; pass --no-spliced-alignment\n"); return 1; }
+    if (mpGiven) o.ignore_quals = 0;
     o.seed = gseed;
     ht2gpu_handle_t* h = NULL;
     if (ht2gpu_open(idx, &o, &h) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(h)); return 1; }

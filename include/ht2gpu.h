@@ -51,7 +51,9 @@ typedef struct {
     int32_t  np;                     /* --np 1 */
     int32_t  rdg_const, rdg_linear;  /* --rdg 5,3 */
     int32_t  rfg_const, rfg_linear;  /* --rfg 5,3 */
-    int32_t  ignore_quals;           /* --ignore-quals */
+    int32_t  ignore_quals;           /* --ignore-quals WITHOUT --mp: the reference turns "--mp a,b" into MMP=Q,a,b, which
+                                        re-enables quality-aware penalties (aligner_seed_policy.cpp:396-418); the CLI
+                                        clears this flag when --mp is given */
     int32_t  nofw, norc;             /* --nofw / --norc */
     int32_t  min_frag, max_frag;     /* -I / -X */
     int32_t  no_mixed, no_discordant;
