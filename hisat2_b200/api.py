@@ -24,7 +24,9 @@ class Options(C.Structure):
         "device", "no_spliced_alignment", "khits", "max_seeds", "secondary", "mp_max", "mp_min",
         "sp_max", "sp_min", "np", "rdg_const", "rdg_linear", "rfg_const", "rfg_linear",
         "ignore_quals", "nofw", "norc", "min_frag", "max_frag", "no_mixed", "no_discordant")] + [
-        ("seed", C.c_uint32), ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32), ("slots_per_lane", C.c_int32), ("warp_per_read", C.c_int32)]
+        ("seed", C.c_uint32), ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32), ("slots_per_lane", C.c_int32), ("warp_per_read", C.c_int32),
+        ("bowtie2_dp", C.c_int32), ("gbar", C.c_int32), ("score_min_type", C.c_int32),
+        ("score_min_const", C.c_double), ("score_min_coeff", C.c_double)]
 
 
 class CReadBatch(C.Structure):

@@ -53,7 +53,8 @@ static bool parseFile(const char* path, bool fastq, std::vector<std::string>& na
 static void usage() {
     fprintf(stderr, "hisat2-b200 -x <index> {-U <r> | -1 <m1> -2 <m2>} [-S out.sam] [-f|-q] --no-spliced-alignment [-k N]\n"
                     "            [--mp MX,MN] [--sp MX,MN] [--np N] [--rdg C,L] [--rfg C,L] [--ignore-quals] [--nofw] [--norc]\n"
-                    "            [-I N] [-X N] [--no-mixed] [--no-discordant] [--seed N] [--batch N] [--device N]\n");
+                    "            [-I N] [-X N] [--no-mixed] [--no-discordant] [--seed N] [--batch N] [--device N]\n"
+                    "            [--bowtie2-dp 0|1|2] [--score-min F,C,L] [--gbar N] [--sensitive] [--very-sensitive] [--fast]\n");
 }
 static void two(const char* a, int32_t& x, int32_t& y) { sscanf(a, "%d,%d", &x, &y); }
 
@@ -63,6 +64,7 @@ int main(int argc, char** argv)
     o.no_spliced_alignment = 0; // must be requested explicitly, like the reference's default is spliced
     const char *idx = NULL, *u = NULL, *m1 = NULL, *m2 = NULL, *out = NULL;
     bool fastq = true; size_t batchSz = 1000000; uint32_t gseed = 0;
+    bool sensitive = false, verySensitive = false, fast = false;
     bool mpGiven = false;   // "--mp a,b" becomes MMP=Q,a,b, which switches the cost model back to quality-aware even
                             // under --ignore-quals (aligner_seed_policy.cpp:396-418)
     for (int i = 1; i < argc; i++) {
@@ -81,6 +83,16 @@ int main(int argc, char** argv)
         else if (a == "--no-mixed") o.no_mixed = 1; else if (a == "--no-discordant") o.no_discordant = 1;
         else if (a == "--seed") gseed = (uint32_t)atoi(next()); else if (a == "--batch") batchSz = (size_t)atol(next());
         else if (a == "--device") o.device = atoi(next());
+        else if (a == "--bowtie2-dp") { o.bowtie2_dp = atoi(next()); if (o.bowtie2_dp < 0 || o.bowtie2_dp > 2) { fprintf(stderr, "Error: --bowtie2-dp arg must be 0, 1, or 2\n"); return 1; } }
+        else if (a == "--gbar") o.gbar = atoi(next());
+        else if (a == "--score-min" || a == "--min-score") {   // <type>,<const>,<coeff>; missing tokens keep the default (PARSE_FUNC, aligner_seed_policy.cpp:47-62)
+            std::string v = next(); size_t c1 = v.find(','), c2 = c1 == std::string::npos ? c1 : v.find(',', c1 + 1);
+            if (!v.empty()) o.score_min_type = v[0];
+            if (c1 != std::string::npos) o.score_min_const = atof(v.c_str() + c1 + 1);
+            if (c2 != std::string::npos) o.score_min_coeff = atof(v.c_str() + c2 + 1);
+            if (o.score_min_type != 'C' && o.score_min_type != 'L' && o.score_min_type != 'S' && o.score_min_type != 'G') { fprintf(stderr, "Error: bad function type in --score-min\n"); return 1; }
+        }
+        else if (a == "--sensitive") sensitive = true; else if (a == "--very-sensitive") verySensitive = true; else if (a == "--fast") fast = true;
         else if (a == "-p" || a == "--threads") next(); else if (a == "--reorder" || a == "-t" || a == "--fr") {}
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else { fprintf(stderr, "Error: option %s is not supported by hisat2-b200\n", a.c_str()); return 1; }
@@ -88,6 +100,17 @@ int main(int argc, char** argv)
     if (!idx || (!u && !(m1 && m2))) { usage(); return 1; }
     if (!o.no_spliced_alignment) { fprintf(stderr, "Error: spliced alignment is not implemented; pass --no-spliced-alignment\n"); return 1; }
     if (mpGiven) o.ignore_quals = 0;
+    // presets, spelled out the way hisat2.cpp:1889-1909 applies them after option parsing
+    if (fast) {}
+    else if (sensitive) {
+        if (o.bowtie2_dp == 0) o.bowtie2_dp = 1;
+        if (o.khits > 0 && o.khits < 10) o.khits = 10;   // an omitted -k stays "index default": the parse-time default is 10 (hisat2.cpp:336, 3903-3906)
+        o.score_min_type = 'L'; o.score_min_const = (double)0.0f; o.score_min_coeff = (double)-0.5f;
+    } else if (verySensitive) {
+        o.bowtie2_dp = 2;
+        if (o.khits < 30) o.khits = 30;
+        o.score_min_type = 'L'; o.score_min_const = (double)0.0f; o.score_min_coeff = (double)-1.0f;
+    }
     o.seed = gseed;
     ht2gpu_handle_t* h = NULL;
     if (ht2gpu_open(idx, &o, &h) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(h)); return 1; }

@@ -25,17 +25,17 @@
 #endif
 #define HT2_MAX_EDITS 40
 #define HT2_MAX_PHITS 64
-#define HT2_MAX_GHITS 24
+#define HT2_MAX_GHITS 64   /* max(khits, kseeds) anchors: --very-sensitive runs -k 30, i.e. 60 seeds */
 #define HT2_POOL 40
 #define HT2_IE_POOL 96           /* in-edge entries per strand (graph indexes) */
 #define HT2_SEARCHED_BYTES 24576   /* ~600 searched hits (40 B typical) for both mates */
 
 #define HT2_MAX_RES 64
 #define HT2_MAX_PAIRS 96
-#define HT2_MAX_COORDS 24
+#define HT2_MAX_COORDS 64
 #define HT2_MAX_DEPTH 128
-#define HT2_DEPTH_CAP 24   /* recursion depth the workspace/stack is sized for */
-#define HT2_REFBUF (HT2_MAX_RDLEN + 64)
+#define HT2_DEPTH_CAP 32   /* recursion depth the workspace/stack is sized for */
+#define HT2_REFBUF (HT2_MAX_RDLEN + 128)   /* read + the read gaps minsc allows (combineWith window): 83 at minsc -256 with the default --rdg */
 
 #define HT2_MIN_I64 ((int64_t)0x8000000000000000ll)
 #define HT2_MIN_SCORE (HT2_MIN_I64 / 2)   /* getMinScore(), aln_sink.h:34 */
@@ -53,6 +53,7 @@
 #define HT2_ERR_GRAPH   512u
 #define HT2_ERR_DEPTH  1024u
 #define HT2_ERR_OUTPUT 2048u
+#define HT2_ERR_SW     4096u   /* --bowtie2-dp scratch missing / rectangle wider than the scratch */
 
 enum { HT2_EDIT_READ_GAP = 1, HT2_EDIT_REF_GAP, HT2_EDIT_MM, HT2_EDIT_SNP, HT2_EDIT_SPL };
 enum { HT2_CANDIDATE_HIT = 1, HT2_PSEUDOGENE_HIT, HT2_ANCHOR_HIT }; // hi_aligner.h:96-100
@@ -172,6 +173,21 @@ struct Ht2AltScratch {
     alignas(8) uint8_t ref[HT2_ALT_BUFS][HT2_REFBUF + 16];
 };
 
+// Scratch of one --bowtie2-dp problem (ht2_sw.h).  One per EXECUTING lane (a
+// problem starts and ends inside one state-machine segment), not per read slot,
+// and only allocated when --bowtie2-dp is on.
+#define HT2_SW_MAXGAP 10
+#define HT2_SW_MAXCOLS (HT2_MAX_RDLEN + 4 * HT2_SW_MAXGAP)
+#define HT2_SW_MAX_EDITS 160
+struct Ht2SwScratch {
+    uint16_t mask[(size_t)HT2_SW_MAXCOLS * HT2_MAX_RDLEN];   // [col][row]: admissible moves per cell + reported-through bit
+    int32_t  hcol[HT2_MAX_RDLEN], ecol[HT2_MAX_RDLEN];       // H / E of the previous column
+    int32_t  lastH[HT2_SW_MAXCOLS];                          // last-row H per column (the candidates)
+    uint8_t  rowPen[HT2_MAX_RDLEN];                          // mismatch penalty of each read row
+    alignas(8) uint8_t rf[HT2_SW_MAXCOLS + 16];              // reference window, codes 0..4
+    Ht2Edit  ned[HT2_SW_MAX_EDITS];
+};
+
 // Per-read (pair) workspace.  One per in-flight GPU thread.
 struct Ht2Work {
     Ht2Read     rd[2];
@@ -284,6 +300,7 @@ struct Ht2AlignerT {
     Ht2Fm<uint32_t>       gfm;
     const Ht2Params*      P;
     Ht2Work*              W;
+    Ht2SwScratch*         sw;      // --bowtie2-dp scratch of this lane (NULL when dp is off)
     bool     paired;
     bool     rightendonly;
     bool     nofw[2], norc[2];
@@ -307,6 +324,7 @@ struct Ht2AlignerT {
         gfm.init(blob_, &H->global);
         P = P_;
         W = W_;
+        sw = NULL;
     }
 
     // ---- edits / hits ---------------------------------------------------
@@ -1492,7 +1510,7 @@ struct Ht2AlignerT {
         return true;
     }
 
-    // SplicedAligner::hybridSearch (spliced_aligner.h:112-322), bowtie2_dp == 0
+    // SplicedAligner::hybridSearch (spliced_aligner.h:112-322)
     HT2_NI void hybridSearch(uint32_t rdi, bool fw) {
         (void)fw;
         for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
@@ -1510,7 +1528,10 @@ struct Ht2AlignerT {
                 if (gk.hitcount > gj.hitcount || (gk.hitcount == gj.hitcount && gk.len > gj.len)) hj = hk;
             }
             Ht2Hit& gh = W->genomeHits[hj];
-            hybridSearchRecur(rdi, gh, gh.rdoff, gh.len, false, 0);
+            int64_t maxsc = hybridSearchRecur(rdi, gh, gh.rdoff, gh.len, false, 0);
+            if (P->bowtie2Dp == 2 || (P->bowtie2Dp == 1 && maxsc < minsc[rdi])) {   // spliced_aligner.h:209-297
+                if (!W->err && swExtendAnchor(rdi, gh)) hybridSearchRecur(rdi, gh, gh.rdoff, gh.len, false, 0);
+            }
             W->genomeHitsDone[hj] = 1;
         }
     }
@@ -1548,6 +1569,7 @@ struct Ht2AlignerT {
     HT2_HD void machineRun();
 
 #include "ht2_alt.h"
+#include "ht2_sw.h"
 };
 typedef Ht2AlignerT<false> Ht2Aligner;        // linear indexes
 typedef Ht2AlignerT<true>  Ht2GraphAligner;   // graph (SNP) indexes

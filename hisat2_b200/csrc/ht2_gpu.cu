@@ -32,6 +32,7 @@ struct DevBatch {
     const uint32_t* seeds;
     uint32_t        n_units;
     int32_t         paired;
+    Ht2SwScratch*   sw;     // --bowtie2-dp scratch, one per launched thread (NULL when dp is off)
 };
 
 struct DevOut {
@@ -64,14 +65,14 @@ __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, u
 
 // Per-read filters and minimum score (hisat2.cpp:3387-3440): length filter,
 // N filter (Scoring::nFilter, nCeil = L,0,0.15 -- the parseString default, aligner_seed_policy.cpp:293-296), score filter
-// (minsc = L,0,-0.2 clamped to <= 0 -- hisat2.cpp:441, 3395-3402).  All products
-// are exact in double (24-bit constants x lengths < 2^9), so host
-// (ht2_host.cpp:ht2_minsc/ht2_filters) and device agree bit for bit.
-__device__ __forceinline__ bool ht2_dev_filter(const DevBatch& b, uint32_t ri, int64_t& minsc)
+// (minsc = --score-min(len), default L,0,-0.2, clamped to <= 0 -- hisat2.cpp:441, 3380-3402; the
+// function is tabulated per read length on the host, Ht2Params::minscTab).  The N-ceiling product is
+// exact in double (24-bit constant x length < 2^9), so host (ht2_host.cpp:ht2_filters) and device agree.
+__device__ __forceinline__ bool ht2_dev_filter(const Ht2Params& P, const DevBatch& b, uint32_t ri, int64_t& minsc)
 {
     const uint64_t o0 = b.offs[ri];
     const uint32_t len = (uint32_t)(b.offs[ri + 1] - o0);
-    int64_t m = (int64_t)((double)-0.2f * (double)len);
+    int64_t m = P.minscTab[len <= HT2_PARAMS_MAX_RDLEN ? len : HT2_PARAMS_MAX_RDLEN];   // --score-min, tabulated on the host (ht2_set_score_min)
     if (m > 0) m = 0;
     minsc = m;
     const uint32_t maxns = (uint32_t)((double)0.0f + (double)0.15f * (double)len);   // nCeil = L,0,0.15 (aligner_seed_policy.cpp:293-296)
@@ -97,7 +98,7 @@ __device__ __noinline__ bool ht2_setup_unit(ALIGNER& A, const Ht2Params& P, cons
         A.paired = false; A.rightendonly = false;
         A.nofw[0] = P.nofw != 0; A.norc[0] = P.norc != 0; A.nofw[1] = true; A.norc[1] = true;
         int64_t ms;
-        const bool f0 = ht2_dev_filter(b, ri, ms);
+        const bool f0 = ht2_dev_filter(P, b, ri, ms);
         A.minsc[0] = ms; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
         W->rnd.init(b.seeds[ri]);
         A.sinkReset(false);
@@ -109,7 +110,7 @@ __device__ __noinline__ bool ht2_setup_unit(ALIGNER& A, const Ht2Params& P, cons
     } else {
         const uint32_t r1 = 2 * u, r2 = 2 * u + 1;
         int64_t ms1, ms2;
-        const bool f1 = ht2_dev_filter(b, r1, ms1), f2 = ht2_dev_filter(b, r2, ms2);
+        const bool f1 = ht2_dev_filter(P, b, r1, ms1), f2 = ht2_dev_filter(P, b, r2, ms2);
         filtBits = (f1 ? 1u : 0u) | (f2 ? 2u : 0u);
         // nofw/norc per mate (hisat2.cpp:3444-3447)
         A.nofw[0] = P.gMate1fw ? (P.nofw != 0) : (P.norc != 0);
@@ -217,6 +218,7 @@ ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevO
     Ht2Work* W = work + tid;
     Ht2Aligner A;
     A.bind(blob, &P, W);
+    A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
     // 0 = needs a unit, 1 = running, 2 = no work left.  Every lane stays in the loop
     // until the whole warp is out of work: the warp vote at the top is the point
     // where the lanes re-converge before the next segment.
@@ -286,6 +288,7 @@ ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch
     for (int j = 0; j < RG_K; j++) code[lane + 32 * j] = RG_NEED;
     Ht2Aligner A;
     A.bind(blob, &P, base);
+    A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
     __syncwarp();
     for (;;) {
         // ---- histogram of live slot states
@@ -375,6 +378,7 @@ ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, De
     for (int j = 0; j < RG_K; j++) sCode[t + NT * j] = RG_NEED;
     Ht2Aligner A;
     A.bind(blob, &P, base);
+    A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
     __syncthreads();
     for (;;) {
         if (t < RG_BINS) sHist[t] = 0;
@@ -480,6 +484,7 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b,
     if (t == 0) { sTarget = RG_NEED; sExit = 0; sLock = 0; }
     Ht2AlignerT<GRAPH> A;
     A.bind(blob, &P, base);
+    A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
     __syncthreads();
     volatile unsigned int* vCode = sCode;
     volatile int* vCount = sCount;
@@ -692,6 +697,7 @@ struct ht2gpu_handle {
     int            poolWarps;
     int            rgK;
     Ht2Work*       dWork;
+    Ht2SwScratch*  dSw;      // --bowtie2-dp: one scratch per launched thread
     size_t         nWork;
     cudaStream_t   stream;
     cudaEvent_t    ev[4];
@@ -754,6 +760,8 @@ extern "C" void ht2gpu_default_options(ht2gpu_options_t* o)
     o->mp_max = 6; o->mp_min = 2; o->sp_max = 2; o->sp_min = 1; o->np = 1;
     o->rdg_const = 5; o->rdg_linear = 3; o->rfg_const = 5; o->rfg_linear = 3;
     o->min_frag = 0; o->max_frag = 1000;
+    o->bowtie2_dp = 0; o->gbar = 4;
+    o->score_min_type = 'L'; o->score_min_const = (double)0.0f; o->score_min_coeff = (double)-0.2f;   // hisat2.cpp:441
 }
 
 static void applyOptions(Ht2Params& P, const Ht2Image& img, const ht2gpu_options_t& o)
@@ -768,6 +776,8 @@ static void applyOptions(Ht2Params& P, const Ht2Image& img, const ht2gpu_options
     P.nofw = o.nofw ? 1 : 0; P.norc = o.norc ? 1 : 0;
     P.minFrag = (uint32_t)o.min_frag; P.maxFrag = (uint32_t)o.max_frag;
     P.mixed = o.no_mixed ? 0 : 1; P.discord = o.no_discordant ? 0 : 1;
+    P.bowtie2Dp = (uint32_t)o.bowtie2_dp; P.gapbar = o.gbar < 1 ? 1 : o.gbar;   // hisat2.cpp:1969-1973
+    if (o.score_min_type != 0) ht2_set_score_min(P, (char)o.score_min_type, o.score_min_const, o.score_min_coeff);
 }
 
 static int finishOpen(ht2gpu_handle* h)
@@ -812,6 +822,10 @@ static int finishOpen(ht2gpu_handle* h)
     h->nWork = (size_t)h->nSM * h->bpsm * h->tpb / h->lanes;
     CK(cudaMalloc(&h->dWork, h->nWork * sizeof(Ht2Work)));
     CK(cudaMemset(h->dWork, 0, h->nWork * sizeof(Ht2Work)));
+    if (h->P.bowtie2Dp) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
+        size_t nThreads = h->regroup ? (size_t)h->nSM * h->bpsm * (size_t)(h->tpb > 256 ? h->tpb : 256) : h->nWork * h->lanes;
+        CK(cudaMalloc(&h->dSw, nThreads * sizeof(Ht2SwScratch)));
+    }
     CK(cudaDeviceSetLimit(cudaLimitStackSize, 40 * 1024));
     CK(cudaStreamCreate(&h->stream));
     for (int i = 0; i < 4; i++) CK(cudaEventCreate(&h->ev[i]));
@@ -821,7 +835,7 @@ static int finishOpen(ht2gpu_handle* h)
 static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
-    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0;
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL;
     h->stream = 0;
     h->dSeq = h->dQual = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->capBases = h->capReads = 0;
     h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL; h->dStats = NULL;
@@ -922,6 +936,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     if (!h) return HT2GPU_OK;
     if (h->dBlob && h->ownBlob) cudaFree(h->dBlob);
     if (h->dWork) cudaFree(h->dWork);
+    if (h->dSw) cudaFree(h->dSw);
     cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dOffs); cudaFree(h->dSeeds);
     cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters); cudaFree(h->dStats);
     if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
@@ -994,7 +1009,7 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
 {
     DevBatch db;
     db.seq = h->dSeq; db.qual = b->qual ? h->dQual : NULL; db.offs = h->dOffs; db.seeds = h->dSeeds;
-    db.n_units = units; db.paired = b->paired;
+    db.n_units = units; db.paired = b->paired; db.sw = h->dSw;
     DevOut o;
     o.reads = h->dReads; o.alns = h->dAlns; o.edits = h->dEdits; o.pairs = h->dPairs;
     o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
@@ -1197,7 +1212,7 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     int rc = uploadBatch(h, b, h2d);
     if (rc) return rc;
     DevBatch db;
-    db.seq = h->dSeq; db.qual = NULL; db.offs = h->dOffs; db.seeds = h->dSeeds; db.n_units = n; db.paired = 0;
+    db.seq = h->dSeq; db.qual = NULL; db.offs = h->dOffs; db.seeds = h->dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL;
     uint32_t *dCounts = NULL, *dOffs3 = NULL;
     unsigned long long* dTot = NULL;
     SeedOut so; memset(&so, 0, sizeof(so));
@@ -1303,9 +1318,9 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
         Ht2HostRead rd1, rd2;
         if (b->paired) { mkRead(2 * u, 1, rd1); mkRead(2 * u + 1, 2, rd2); }
         else mkRead(u, 0, rd1);
-        Ht2ReadFilters f1 = ht2_filters(rd1, ht2_minsc((uint32_t)rd1.seq.size()));
+        Ht2ReadFilters f1 = ht2_filters(rd1, ht2_minsc(h->P, (uint32_t)rd1.seq.size()));
         Ht2ReadFilters f2 = f1;
-        if (b->paired) f2 = ht2_filters(rd2, ht2_minsc((uint32_t)rd2.seq.size()));
+        if (b->paired) f2 = ht2_filters(rd2, ht2_minsc(h->P, (uint32_t)rd2.seq.size()));
         const ht2gpu_read_result_t& rr = res->reads[u];
         Ht2ReadOut o;
         o.rngLast = rr.rng_state; o.err = rr.err;

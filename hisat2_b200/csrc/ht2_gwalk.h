@@ -12,9 +12,9 @@
 
 #include "ht2_graph.h"
 
-#define HT2_GW_MAXELT 24
-#define HT2_GW_MAXROWS 64
-#define HT2_GW_MAXST 40
+#define HT2_GW_MAXELT 64      /* max(khits, kseeds) elements: --very-sensitive runs -k 30, i.e. 60 seeds */
+#define HT2_GW_MAXROWS 128
+#define HT2_GW_MAXST 96
 #define HT2_GW_MASK 0xffffffffu
 
 struct Ht2GwState {

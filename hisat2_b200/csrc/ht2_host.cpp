@@ -3,6 +3,7 @@
 
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 
 #include <algorithm>
 
@@ -32,6 +33,25 @@ void ht2_default_params(Ht2Params& P, const Ht2Image& img, bool noSplicedAlignme
     P.pePolicy = 2; P.minFrag = 0; P.maxFrag = 1000;
     P.gMate1fw = 1; P.gMate2fw = 0;
     P.nofw = 0; P.norc = 0; P.mixed = 1; P.discord = 1;
+    P.bowtie2Dp = 0; P.gapbar = 4;                      // hisat2.cpp:529, 419
+    ht2_set_score_min(P, 'L', (double)0.0f, (double)-0.2f);   // hisat2.cpp:441
+}
+
+// SimpleFunc::f<TAlScore> (simple_func.h:86-108) with min = -DBL_MAX, max = DBL_MAX
+// (SimpleFunc::init(type, C, L)), tabulated for every supported read length.
+bool ht2_set_score_min(Ht2Params& P, char type, double C, double L)
+{
+    if (type != 'C' && type != 'L' && type != 'S' && type != 'G') return false;
+    for (uint32_t len = 0; len <= HT2_PARAMS_MAX_RDLEN; len++) {
+        double x = (double)len, X;
+        if (type == 'C') X = 0.0; else if (type == 'L') X = x; else if (type == 'S') X = sqrt(x); else X = log(x);
+        double v = std::max(-1.7976931348623157e308, std::min(1.7976931348623157e308, C + L * X));
+        if (!(v == v)) v = 0.0;
+        if (v > 2147483647.0) v = 2147483647.0;
+        if (v < -2147483648.0) v = -2147483648.0;
+        P.minscTab[len] = (int32_t)(int64_t)v;
+    }
+    return true;
 }
 
 // SimpleFunc::f<T> for the linear functions the defaults use (simple_func.h:86-108)
@@ -39,11 +59,10 @@ static double simpleLinear(double I, double X, double C, double L, double x) {
     return std::max(I, std::min(X, C + L * x));
 }
 
-int64_t ht2_minsc(uint32_t rdlen)
+int64_t ht2_minsc(const Ht2Params& P, uint32_t rdlen)
 {
-    // scoreMin = L,0,-0.2 (hisat2.cpp:441); clamped to <= 0 in end-to-end mode (:3395-3402)
-    double v = simpleLinear(-1.7976931348623157e308, 1.7976931348623157e308, (double)0.0f, (double)-0.2f, (double)rdlen);
-    int64_t m = (int64_t)v;
+    // scoreMin.f(rdlen) (default L,0,-0.2, hisat2.cpp:441); clamped to <= 0 in end-to-end mode (:3395-3402)
+    int64_t m = P.minscTab[rdlen <= HT2_PARAMS_MAX_RDLEN ? rdlen : HT2_PARAMS_MAX_RDLEN];
     if (m > 0) m = 0;
     return m;
 }
@@ -335,7 +354,7 @@ struct Summ { // AlnSetSumm (aligner_result.cpp:1167-1260)
 
 // BowtieMapq2::mapq (unique.h:170-400) for monotone scoring, canMax=false,
 // exhausted=false.
-int mapqV2(const Summ& s, bool mate1, size_t rdlen, size_t ordlen)
+int mapqV2(const Ht2Params& P, const Summ& s, bool mate1, size_t rdlen, size_t ordlen)
 {
     const ScoreKey& bst = s.paired ? s.bestPaired : s.best[mate1 ? 0 : 1];
     const ScoreKey& sec = s.paired ? s.secbestPaired : s.secbest[mate1 ? 0 : 1];
@@ -343,8 +362,9 @@ int mapqV2(const Summ& s, bool mate1, size_t rdlen, size_t ordlen)
     bool equalSecbest = hasSecbest && keyEq(bst, sec);
     if (!hasSecbest || !equalSecbest) return 60;
     int64_t scPer = 0;
-    int64_t scMin = (int64_t)((double)0.0f + (double)-0.2f * (double)(float)rdlen);
-    if (s.paired) scMin += (int64_t)((double)0.0f + (double)-0.2f * (double)(float)ordlen);
+    // scoreMin_.f<TAlScore>((float)rdlen) (unique.h:200-203), from the per-length table
+    int64_t scMin = P.minscTab[rdlen <= HT2_PARAMS_MAX_RDLEN ? rdlen : HT2_PARAMS_MAX_RDLEN];
+    if (s.paired) scMin += P.minscTab[ordlen <= HT2_PARAMS_MAX_RDLEN ? ordlen : HT2_PARAMS_MAX_RDLEN];
     int64_t diff = scPer - scMin;
     int64_t best = bst.score;
     int64_t bestOver = best - scMin;
@@ -567,7 +587,7 @@ static int64_t fragmentLength(const Ht2Res& me, const Ht2Res& o, bool meMate1)
 }
 
 // AlnSinkSam::appendMate (aln_sink.h:3024-3250)
-static void appendMate(std::string& o, const Ht2Image& img, const Ht2HostRead& rd, size_t ordlen, const Ht2ReadFilters& f,
+static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, const Ht2HostRead& rd, size_t ordlen, const Ht2ReadFilters& f,
                        const Ht2Res* rs, const Ht2Res* rso, const Summ& summ, const MateFlags& fl,
                        bool fraglenSet, int64_t fraglen, bool haveOscore)
 {
@@ -616,7 +636,7 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2HostRead& r
     o.push_back('\t');
     o += std::to_string((int64_t)rs->toff + 1);
     o.push_back('\t');
-    o += std::to_string(mapqV2(summ, rd.mate < 2, rd.seq.size(), ordlen));
+    o += std::to_string(mapqV2(P, summ, rd.mate < 2, rd.seq.size(), ordlen));
     o.push_back('\t');
     st.cigar(o);
     o.push_back('\t');
@@ -721,10 +741,10 @@ void ht2_finish_unpaired(std::string& o, const Ht2Image& img, const Ht2Params& P
         summ.numAlns[0] = select.size();
         for (size_t i = 0; i < select.size(); i++) {
             fl.primary = (i == 0);
-            appendMate(o, img, rd, 0, f, &rs[select[i]], NULL, summ, fl, false, 0, false);
+            appendMate(o, img, P, rd, 0, f, &rs[select[i]], NULL, summ, fl, false, 0, false);
         }
     } else {
-        appendMate(o, img, rd, 0, f, NULL, NULL, summ, fl, false, 0, false);
+        appendMate(o, img, P, rd, 0, f, NULL, NULL, summ, fl, false, 0, false);
     }
     out.rngLast = rnd.last;
 }
@@ -767,8 +787,8 @@ void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
         for (size_t i = 0; i < select.size(); i++) {
             const Ht2Res& a = rs1u[out.pairs[select[i]].first]; const Ht2Res& b = rs2u[out.pairs[select[i]].second];
             fl1.primary = fl2.primary = (i == 0);
-            appendMate(o, img, rd1, rd2.seq.size(), f1, &a, &b, summ, fl1, true, fragmentLength(a, b, true), true);
-            appendMate(o, img, rd2, rd1.seq.size(), f2, &b, &a, summ, fl2, true, fragmentLength(b, a, false), true);
+            appendMate(o, img, P, rd1, rd2.seq.size(), f1, &a, &b, summ, fl1, true, fragmentLength(a, b, true), true);
+            appendMate(o, img, P, rd2, rd1.seq.size(), f2, &b, &a, summ, fl2, true, fragmentLength(b, a, false), true);
         }
         out.rngLast = rnd.last;
         return;
@@ -788,8 +808,8 @@ void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
         MateFlags fl1 = {PAIR_DISCORD_MATE1, true, true}, fl2 = {PAIR_DISCORD_MATE2, true, true};
         const Ht2Res& a = rs1u[0]; const Ht2Res& b = rs2u[0];
         bool sameRef = a.tidx == b.tidx; // setMateParams (aligner_result.h:1594-1618)
-        appendMate(o, img, rd1, rd2.seq.size(), f1, &a, &b, summ, fl1, sameRef, sameRef ? fragmentLength(a, b, true) : 0, true);
-        appendMate(o, img, rd2, rd1.seq.size(), f2, &b, &a, summ, fl2, sameRef, sameRef ? fragmentLength(b, a, false) : 0, true);
+        appendMate(o, img, P, rd1, rd2.seq.size(), f1, &a, &b, summ, fl1, sameRef, sameRef ? fragmentLength(a, b, true) : 0, true);
+        appendMate(o, img, P, rd2, rd1.seq.size(), f2, &b, &a, summ, fl2, sameRef, sameRef ? fragmentLength(b, a, false) : 0, true);
         out.rngLast = rnd.last;
         return;
     }
@@ -823,18 +843,18 @@ void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
         // AlnSink::reportHits (aln_sink.h:730-790)
         if (repRs2 != NULL) {
             const Ht2Res* r1pri = &rs1u[select1[0]]; const Ht2Res* r2pri = &rs2u[select2[0]];
-            appendMate(o, img, rd1, rd2.seq.size(), f1, r1pri, r2pri, summ1, fl1, false, 0, false);
-            appendMate(o, img, rd2, rd1.seq.size(), f2, r2pri, r1pri, summ1, fl2, false, 0, false);
+            appendMate(o, img, P, rd1, rd2.seq.size(), f1, r1pri, r2pri, summ1, fl1, false, 0, false);
+            appendMate(o, img, P, rd2, rd1.seq.size(), f2, r2pri, r1pri, summ1, fl2, false, 0, false);
             fl1.primary = fl2.primary = false;
             for (size_t i = 1; i < select1.size(); i++)
-                appendMate(o, img, rd1, rd2.seq.size(), f1, &rs1u[select1[i]], r2pri, summ1, fl1, false, 0, false);
+                appendMate(o, img, P, rd1, rd2.seq.size(), f1, &rs1u[select1[i]], r2pri, summ1, fl1, false, 0, false);
             for (size_t i = 1; i < select2.size(); i++)
-                appendMate(o, img, rd2, rd1.seq.size(), f2, &rs2u[select2[i]], r1pri, summ1, fl2, false, 0, false);
+                appendMate(o, img, P, rd2, rd1.seq.size(), f2, &rs2u[select2[i]], r1pri, summ1, fl2, false, 0, false);
             fl1.primary = fl2.primary = true;
         } else {
             for (size_t i = 0; i < select1.size(); i++) {
                 fl1.primary = (i == 0);
-                appendMate(o, img, rd1, 0, f1, &rs1u[select1[i]], NULL, summ1, fl1, false, 0, false);
+                appendMate(o, img, P, rd1, 0, f1, &rs1u[select1[i]], NULL, summ1, fl1, false, 0, false);
             }
             fl1.primary = true;
         }
@@ -843,7 +863,7 @@ void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
     if (rep2 && !rep1) {
         for (size_t i = 0; i < select2.size(); i++) {
             fl2.primary = (i == 0);
-            appendMate(o, img, rd2, 0, f2, &rs2u[select2[i]], NULL, summ2, fl2, false, 0, false);
+            appendMate(o, img, P, rd2, 0, f2, &rs2u[select2[i]], NULL, summ2, fl2, false, 0, false);
         }
         fl2.primary = true;
         refid = rs2u[select2[0]].tidx; refoff = rs2u[select2[0]].toff;
@@ -852,13 +872,13 @@ void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
         Summ s; s.reset();
         if (nunpair2 > 0) { s.orefid = refid; s.orefoff = refoff; }
         MateFlags fl = {PAIR_UNPAIRED_MATE1, true, repRs2 != NULL};
-        appendMate(o, img, rd1, 0, f1, NULL, NULL, s, fl, false, 0, false);
+        appendMate(o, img, P, rd1, 0, f1, NULL, NULL, s, fl, false, 0, false);
     }
     if (nunpair2 == 0) {
         Summ s; s.reset();
         if (nunpair1 > 0) { s.orefid = refid; s.orefoff = refoff; }
         MateFlags fl = {PAIR_UNPAIRED_MATE2, true, repRs1 != NULL};
-        appendMate(o, img, rd2, 0, f2, NULL, NULL, s, fl, false, 0, false);
+        appendMate(o, img, P, rd2, 0, f2, NULL, NULL, s, fl, false, 0, false);
     }
     out.rngLast = rnd.last;
 }

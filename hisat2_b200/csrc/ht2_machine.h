@@ -17,7 +17,7 @@
 
 enum {
     // top-level states (HI_Aligner::go, hi_aligner.h:4048-4149)
-    TS_START = 0, TS_NEXTBWT, TS_PS, TS_ALIGN, TS_HYB_EXTEND, TS_HYB_PICK, TS_HYB_RET, TS_POST_ALIGN,
+    TS_START = 0, TS_NEXTBWT, TS_PS, TS_ALIGN, TS_HYB_EXTEND, TS_HYB_PICK, TS_HYB_RET, TS_HYB_DP_RET, TS_POST_ALIGN,
     TS_AFTER_LOOP, TS_MATE_NEXT, TS_MATE_SEARCH, TS_MATE_ANCHOR, TS_MATE_RET, TS_MATE_DONE, TS_DONE
 };
 enum {
@@ -671,6 +671,22 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
         break;
     }
     case TS_HYB_RET: {
+        // --bowtie2-dp: dynamic programming around the anchor, then one more recursion on the
+        // full-length hit (spliced_aligner.h:209-320)
+        if (P->bowtie2Dp == 2 || (P->bowtie2Dp == 1 && W->childRet < minsc[W->curRdi])) {
+            Ht2Hit& gh = W->genomeHits[W->hybHj];
+            if (!W->err && swExtendAnchor(W->curRdi, gh)) {
+                W->st = TS_HYB_DP_RET;
+                pushFrame(W->curRdi, &gh, gh.rdoff, gh.len, false, 0);
+                break;
+            }
+        }
+        W->genomeHitsDone[W->hybHj] = 1;
+        W->hybIter++;
+        W->st = TS_HYB_PICK;
+        break;
+    }
+    case TS_HYB_DP_RET: {
         W->genomeHitsDone[W->hybHj] = 1;
         W->hybIter++;
         W->st = TS_HYB_PICK;
@@ -756,6 +772,7 @@ template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineAtHeavyState() cons
     }
     switch (W->st) {
         case TS_PS: case TS_ALIGN: case TS_HYB_EXTEND: case TS_MATE_SEARCH: case TS_MATE_ANCHOR: case TS_DONE: return true;
+        case TS_HYB_RET: return P->bowtie2Dp != 0;   // the dynamic-programming extension runs here
         default: return false;
     }
 }

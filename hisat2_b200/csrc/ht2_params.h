@@ -9,6 +9,8 @@
 
 #include <stdint.h>
 
+#define HT2_PARAMS_MAX_RDLEN 256
+
 struct Ht2Params {
     // Scoring
     int32_t mmpMax;        // --mp max (6)
@@ -48,6 +50,13 @@ struct Ht2Params {
     uint32_t norc;         // --norc
     uint32_t mixed;        // !--no-mixed
     uint32_t discord;      // !--no-discordant
+    // --bowtie2-dp (hisat2.cpp:293, 1770): 0 off, 1 when the anchor search found nothing >= minsc, 2 always
+    uint32_t bowtie2Dp;
+    int32_t  gapbar;       // --gbar (4): no gaps within this many rows of either read end (DP only)
+    // --score-min as a table: SimpleFunc::f<TAlScore>(len) for every read length (hisat2.cpp:3380,
+    // simple_func.h:86-108), computed once on the host so that host and device agree for every
+    // function type (C, L, S = sqrt, G = log).  NOT yet clamped to <= 0.
+    int32_t  minscTab[HT2_PARAMS_MAX_RDLEN + 1];
 };
 
 #endif

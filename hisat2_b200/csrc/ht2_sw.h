@@ -1,0 +1,322 @@
+// ht2_sw.h -- the --bowtie2-dp seed extension: end-to-end dynamic programming
+// around an anchor, then a deterministic backtrace.  Textually included inside
+// Ht2AlignerT (ht2_core.h).
+//
+// What the reference does (SplicedAligner::hybridSearch, spliced_aligner.h:209-297):
+// after the first hybridSearch_recur on an anchor, when --bowtie2-dp is 2, or 1
+// and the recursion found nothing >= minsc, it frames a rectangle of
+// rdlen x (rdlen + 40) cells around the anchor's diagonal
+// (DynProgFramer::frameSeedExtensionRect, dp_framer.cpp:81-132), fills E/F/H
+// with the striped 8-bit (or 16-bit when minsc < -254) SSE kernel
+// (aligner_swsse_ee_u8.cpp:791-1163 / _i16.cpp), gathers the last-row cells
+// >= minsc as candidates (aligner_swsse_ee_u8.cpp:1202-1233), sorted by
+// (score desc, col desc) (aligner_sw_nuc.h:149-157), and backtraces from the first
+// candidate that succeeds (SwAligner::nextAlignment aligner_sw.cpp:709-1122,
+// backtraceNucleotidesEnd2EndSseU8 aligner_swsse_ee_u8.cpp:1309-1902).  The
+// result replaces the anchor with a full-length hit.
+//
+// Restated here without the striping: the striped kernel plus its lazy-F loop
+// computes exactly the saturating Gotoh recurrences
+//     E[i][j] = max(E[i][j-1] (-) rdgape, (H[i][j-1] (-) rdgapo) (-) bar_i)
+//     F[i][j] = max(F[i-1][j] (-) rfgape,  H[i-1][j] (-) rfgapo) (-) bar_i
+//     H[i][j] = max(Hd (-) pen(i,j), E[i][j], F[i][j]),  Hd = top for row 0, floor for column 0
+// ((-) = subtraction saturating at the floor; bar_i = "infinite" inside the gap
+// barrier rows), column by column.  The backtrace only ever compares stored
+// cell values for equality, so the set of admissible moves of every cell is
+// computed while filling and kept as a 13-bit word per cell -- the same bits
+// the reference keeps in SSEMatrix::masks_ (sse_util.h) -- instead of three
+// score matrices: 2 bytes/cell instead of 3 + 2.
+//
+// The backtrace is deterministic in this reference (the randomised choices are
+// compiled out, aligner_swsse_ee_u8.cpp:1405, 1461, 1532): preference diag > H up
+// > F up > H left > E left.  Its backtrack stack never helps: a popped branch
+// cell is already marked reported-through, so the pop cascades until the stack
+// is empty (aligner_swsse_ee_u8.cpp:1353-1361, 1580-1606); a blocked cell
+// therefore simply fails the candidate, with the marks left in place for the
+// next candidate.
+
+#define HT2_SWM_H(c)      ((c) & 31u)
+#define HT2_SWM_E(c)      (((c) >> 5) & 3u)
+#define HT2_SWM_F(c)      (((c) >> 7) & 3u)
+#define HT2_SWM_REP       (1u << 9)
+#define HT2_SWM_OH        (1u << 10)
+#define HT2_SWM_OE        (1u << 11)
+#define HT2_SWM_OF        (1u << 12)
+
+struct SwRect { int64_t refl, refr; uint32_t triml, trimr, corel, corer; };
+
+// DynProgFramer::frameSeedExtensionRect with readGaps = refGaps = maxhalf = 10, nceil = 0,
+// trimToRef = false (the arguments of spliced_aligner.h:226-239)
+HT2_HD static bool swFrameRect(int64_t off, uint32_t rdlen, int64_t reflen, SwRect& r) {
+    const int64_t maxgap = HT2_SW_MAXGAP;
+    int64_t refl = off - 2 * maxgap, refr = off + ((int64_t)rdlen - 1) + 2 * maxgap;
+    int64_t maxns = 0;
+    if (maxns == (int64_t)rdlen) maxns--;
+    uint32_t triml = 0, trimr = 0;
+    if (refr >= reflen + maxns) trimr = (uint32_t)(refr - (reflen + maxns - 1));
+    if (refl < -maxns) triml = (uint32_t)((-refl) - maxns);
+    r.refl = refl + triml; r.refr = refr - trimr; r.triml = triml; r.trimr = trimr;
+    r.corel = (uint32_t)maxgap; r.corer = r.corel + 2 * (uint32_t)maxgap;
+    return r.refr >= r.refl;
+}
+
+HT2_HD static uint8_t swMask2dna(int code) { return (uint8_t)("ACGTN"[code]); }
+
+// Fill + gather.  Returns the best last-row score (score space: 0 = perfect), or
+// HT2_MIN_I64 when nothing reaches minsc.
+HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const uint8_t* rf, uint32_t ncol, int64_t minscR, bool use16) {
+    Ht2SwScratch& S = *sw;
+    const int FLOOR = use16 ? -65535 : -255;
+    const int rdgapo = P->rdGapConst + P->rdGapLinear, rdgape = P->rdGapLinear;
+    const int rfgapo = P->rfGapConst + P->rfGapLinear, rfgape = P->rfGapLinear;
+    const uint32_t gapbar = (uint32_t)P->gapbar;
+    for (uint32_t i = 0; i < nrow; i++) { S.hcol[i] = FLOOR; S.ecol[i] = FLOOR; S.rowPen[i] = (uint8_t)ht2_mmpen(*P, (int)qu[i] - 33); }
+    int best = FLOOR;
+    for (uint32_t j = 0; j < ncol; j++) {
+        const int refc = rf[j];
+        uint16_t* mcol = S.mask + (size_t)j * nrow;
+        int hPrev = FLOOR, fPrev = FLOOR, hAboveLeft = FLOOR;
+        for (uint32_t i = 0; i < nrow; i++) {
+            const int hleft = S.hcol[i], eleft = S.ecol[i];
+            const int hd = (i == 0) ? 0 : hAboveLeft;
+            const bool gb = (i < gapbar) || (nrow - 1 - i < gapbar);
+            const int rdc = rd[i];
+            const int pen = (rdc > 3 || refc > 3) ? P->npen : (rdc == refc ? 0 : (int)S.rowPen[i]);
+            int e = eleft - rdgape; if (e < FLOOR) e = FLOOR;
+            if (!gb) { int t = hleft - rdgapo; if (t > e) e = t; }
+            int f = FLOOR;
+            if (i > 0 && !gb) {
+                f = fPrev - rfgape; if (f < FLOOR) f = FLOOR;
+                int t = hPrev - rfgapo; if (t > f) f = t;
+            }
+            int h = hd - pen; if (h < FLOOR) h = FLOOR;
+            if (e > h) h = e;
+            if (f > h) h = f;
+            uint32_t cell = 0;
+            if (i > 0) {
+                uint32_t hm = 0, em = 0, fm = 0;
+                if (!gb) {
+                    if (h + rfgapo == hPrev) hm |= 1;
+                    if (j > 0 && h + rdgapo == hleft) hm |= 2;
+                    if (h + rfgape == fPrev) hm |= 4;
+                    if (j > 0 && h + rdgape == eleft) hm |= 8;
+                }
+                if (j > 0 && h + pen == hd) hm |= 16;
+                if (j > 0) { if (hleft - rdgapo == e) em |= 1; if (eleft - rdgape == e) em |= 2; }
+                if (hPrev - rfgapo == f) fm |= 1;
+                if (fPrev - rfgape == f) fm |= 2;
+                cell = hm | (em << 5) | (fm << 7) | (hm ? HT2_SWM_OH : 0) | (em ? HT2_SWM_OE : 0) | (fm ? HT2_SWM_OF : 0);
+            }
+            mcol[i] = (uint16_t)cell;
+            hAboveLeft = hleft;
+            S.hcol[i] = h; S.ecol[i] = e;
+            hPrev = h; fPrev = f;
+        }
+        S.lastH[j] = hPrev;
+        if (hPrev > best) best = hPrev;
+    }
+    if ((int64_t)best < minscR) return HT2_MIN_I64;
+    if (best == FLOOR) return HT2_MIN_I64;   // "could have saturated" (aligner_swsse_ee_u8.cpp:1149-1154)
+    return best;
+}
+
+// One backtrace (aligner_swsse_ee_u8.cpp:1309-1902).  Edits land in S.ned (left to right).
+HT2_NI bool swBacktrace(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const uint8_t* rf, const SwRect& rect, int nceil,
+                        uint32_t row, uint32_t col, uint32_t& nedOut, uint32_t& offOut, int64_t& scoreOut) {
+    Ht2SwScratch& S = *sw;
+    const int rdgapo = P->rdGapConst + P->rdGapLinear, rdgape = P->rdGapLinear;
+    const int rfgapo = P->rfGapConst + P->rfGapLinear, rfgape = P->rfGapLinear;
+    enum { CT_H = 0, CT_E = 1, CT_F = 2 };
+    enum { MV_DIAG, MV_REF_OPEN, MV_RFGAP_EXT, MV_READ_OPEN, MV_RDGAP_EXT };
+    int ct = CT_H;
+    uint32_t ned = 0;
+    int64_t score = 0; int ns = 0;
+    bool ovl = false;
+    for (;;) {
+        uint16_t& cellRef = S.mask[(size_t)col * nrow + row];
+        uint32_t cell = cellRef;
+        bool empty = false, canMoveThru = true;
+        int cur = -1;
+        if (cell & HT2_SWM_REP) canMoveThru = false;
+        else if (row > 0) {
+            if (ct == CT_E) {
+                const uint32_t m = HT2_SWM_E(cell);
+                uint32_t nm = 0;
+                if (m == 3) { cur = MV_READ_OPEN; nm = 2; }
+                else if (m == 2) cur = MV_RDGAP_EXT;
+                else if (m == 1) cur = MV_READ_OPEN;
+                else { empty = true; canMoveThru = (cell & HT2_SWM_OE) == 0; }
+                cell = (cell & ~(3u << 5)) | (nm << 5);
+            } else if (ct == CT_F) {
+                const uint32_t m = HT2_SWM_F(cell);
+                uint32_t nm = 0;
+                if (m == 3) { cur = MV_REF_OPEN; nm = 2; }
+                else if (m == 2) cur = MV_RFGAP_EXT;
+                else if (m == 1) cur = MV_REF_OPEN;
+                else { empty = true; canMoveThru = (cell & HT2_SWM_OF) == 0; }
+                cell = (cell & ~(3u << 7)) | (nm << 7);
+            } else {
+                uint32_t m = HT2_SWM_H(cell);
+                int select = -1;
+                if (m != 0) {
+                    if (m & 16) select = 4;        // H diag
+                    else if (m & 1) select = 0;    // H up
+                    else if (m & 4) select = 2;    // F up
+                    else if (m & 2) select = 1;    // H left
+                    else select = 3;               // E left
+                    m &= ~(1u << select);
+                    cell = (cell & ~31u) | m;
+                    cur = select == 4 ? MV_DIAG : select == 0 ? MV_REF_OPEN : select == 1 ? MV_READ_OPEN : select == 2 ? MV_RFGAP_EXT : MV_RDGAP_EXT;
+                } else { empty = true; canMoveThru = (cell & HT2_SWM_OH) == 0; }
+            }
+        }
+        cellRef = (uint16_t)(cell | HT2_SWM_REP);
+        if (!canMoveThru) return false;
+        {   // the cell joins the path: does it sit on a core diagonal?
+            int64_t diagi = (int64_t)col - (int64_t)row + (int64_t)rect.triml;
+            if (diagi >= 0 && (uint64_t)diagi >= rect.corel && (uint64_t)diagi <= rect.corer) ovl = true;
+        }
+        if (empty || row == 0) break;
+        const int rdc = rd[row];
+        const int refc = rf[col];
+        if (ned >= HT2_SW_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
+        switch (cur) {
+        case MV_DIAG: {
+            const bool amb = (rdc > 3 || refc > 3);
+            if (amb || rdc != refc) {
+                S.ned[ned++] = mkEdit(row, swMask2dna(refc), ht2_code2asc(rdc), HT2_EDIT_MM);
+                score -= amb ? P->npen : (int)S.rowPen[row];
+            }
+            if (amb) ns++;
+            row--; col--; ct = CT_H;
+            break;
+        }
+        case MV_REF_OPEN: case MV_RFGAP_EXT:
+            S.ned[ned++] = mkEdit(row, '-', ht2_code2asc(rdc), HT2_EDIT_REF_GAP);
+            row--;
+            if (cur == MV_REF_OPEN) { ct = CT_H; score -= rfgapo; } else { ct = CT_F; score -= rfgape; }
+            break;
+        default: // MV_READ_OPEN / MV_RDGAP_EXT
+            S.ned[ned++] = mkEdit(row + 1, swMask2dna(refc), '-', HT2_EDIT_READ_GAP);
+            col--;
+            if (cur == MV_READ_OPEN) { ct = CT_H; score -= rdgapo; } else { ct = CT_E; score -= rdgape; }
+            break;
+        }
+    }
+    if (!ovl) return false;   // must overlap a core diagonal (aligner_swsse_ee_u8.cpp:1789-1822)
+    {
+        const int rdc = rd[row], refc = rf[col];
+        const bool amb = (rdc > 3 || refc > 3);
+        if (amb || rdc != refc) {
+            if (ned >= HT2_SW_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
+            S.ned[ned++] = mkEdit(row, swMask2dna(refc), ht2_code2asc(rdc), HT2_EDIT_MM);
+            score -= amb ? P->npen : (int)S.rowPen[row];
+        }
+        if (amb) ns++;
+    }
+    if (ns > nceil) return false;
+    for (uint32_t a = 0, b = ned; a + 1 < b; a++, b--) { Ht2Edit t = S.ned[a]; S.ned[a] = S.ned[b - 1]; S.ned[b - 1] = t; }
+    (void)qu;
+    nedOut = ned; offOut = col; scoreOut = score;
+    return true;
+}
+
+// GenomeHit::replace_edits_with_alts (hi_aligner.h:1229-1330)
+HT2_NI void replaceEditsWithAlts(Ht2Hit& h, uint32_t rdi) {
+    if (!GRAPH) return;
+    const uint32_t nalts = numAlts();
+    if (nalts == 0 || h.nedits == 0) return;
+    const Ht2Alt* alts = altTable();
+    int64_t offset = 0;
+    uint32_t i = 0;
+    while (i < h.nedits) {
+        uint32_t next_i = i + 1;
+        Ht2Edit& ed = h.edits[i];
+        if (ed.type == HT2_EDIT_READ_GAP || ed.type == HT2_EDIT_REF_GAP)
+            for (; next_i < h.nedits; next_i++) if (h.edits[next_i].type != ed.type) break;
+        const uint32_t gap = next_i - i;
+        if (ed.snpID == HT2_IDX_MAX32) {
+            const uint32_t key = (uint32_t)((int64_t)h.joinedOff + (int64_t)ed.pos + offset);
+            for (uint32_t ai = altLoBound(key); ai < nalts; ai++) {
+                const Ht2Alt& alt = alts[ai];
+                if (alt.pos > key) break;
+                if (ed.type == HT2_EDIT_MM) {
+                    if (alt.type != HT2_ALT_SNP_SGL) continue;
+                    if (alt.seq < 4 && "ACGT"[alt.seq] == (char)ed.qchr) { ed.snpID = ai; break; }
+                } else if (ed.type == HT2_EDIT_READ_GAP) {
+                    if (alt.type != HT2_ALT_SNP_DEL) continue;
+                    if (alt.len == gap) { for (uint32_t ii = i; ii < next_i; ii++) h.edits[ii].snpID = ai; break; }
+                } else {
+                    if (alt.type != HT2_ALT_SNP_INS) continue;
+                    if (alt.len == gap) {
+                        uint64_t seq = 0;
+                        for (uint32_t ii = i; ii < next_i; ii++) seq = (seq << 2) | (uint64_t)(ht2_asc2code(h.edits[ii].qchr) & 3);
+                        if (alt.seq == seq) { for (uint32_t ii = i; ii < next_i; ii++) h.edits[ii].snpID = ai; break; }
+                    }
+                }
+            }
+        }
+        if (ed.type == HT2_EDIT_READ_GAP) offset += gap;
+        else if (ed.type == HT2_EDIT_REF_GAP) offset -= gap;
+        i = next_i;
+    }
+    calculateScore(h, rdi);
+}
+
+// The dp block of SplicedAligner::hybridSearch (spliced_aligner.h:209-297).  Returns
+// 'found': true when the caller has to run hybridSearch_recur on gh once more.
+HT2_NI bool swExtendAnchor(uint32_t rdi, Ht2Hit& gh) {
+    const Ht2Read& R = W->rd[rdi];
+    const uint32_t rdlen = R.len;
+    if (gh.len >= rdlen) return true;
+    if (sw == NULL) { W->err |= HT2_ERR_SW; return false; }
+    Ht2SwScratch& S = *sw;
+    const bool fw = gh.fw != 0;
+    const uint8_t* rd = R.seq[fw ? 0 : 1];
+    const uint8_t* qu = R.qual[fw ? 0 : 1];
+    const int64_t tlen = (int64_t)refLen(gh.tidx);
+    const uint32_t refoff = gh.toff > gh.rdoff ? gh.toff - gh.rdoff : 0;
+    SwRect rect;
+    if (!swFrameRect((int64_t)refoff, rdlen, tlen, rect)) return false;
+    const uint32_t ncol = (uint32_t)(rect.refr - rect.refl + 1);
+    if (ncol > HT2_SW_MAXCOLS) { W->err |= HT2_ERR_SW; return false; }
+    // reference window; positions past the end of the sequence read as N (aligner_sw.cpp:160-212)
+    const uint8_t* rf = getStretch(S.rf, gh.tidx, (uint32_t)rect.refl, ncol);
+    const int64_t msc = minsc[rdi];
+    const bool use16 = !(msc >= -254);                    // aligner_sw.cpp:496
+    // nCeil = L,0,0.15 (SwAligner::initRead, aligner_sw.cpp:45)
+    const int nceil = (int)((double)0.0f + (double)0.15f * (double)rdlen);
+    const int64_t best = swFill(rd, qu, rdlen, rf, ncol, msc, use16);
+    if (best == HT2_MIN_I64) return false;
+    // SwAligner::nextAlignment: candidates in (score desc, col desc) order
+    int64_t prevScore = 0; uint32_t prevCol = 0; bool havePrev = false;
+    for (;;) {
+        int64_t cs = HT2_MIN_I64; uint32_t cc = 0; bool got = false;
+        for (uint32_t j = 0; j < ncol; j++) {
+            const int64_t s = S.lastH[j];
+            if (s < msc) continue;
+            if (havePrev && !(s < prevScore || (s == prevScore && j < prevCol))) continue;
+            if (!got || s > cs || (s == cs && j > cc)) { cs = s; cc = j; got = true; }
+        }
+        if (!got) return false;
+        prevScore = cs; prevCol = cc; havePrev = true;
+        if (S.mask[(size_t)cc * rdlen + (rdlen - 1)] & HT2_SWM_REP) continue;   // starting cell already covered
+        uint32_t reseed = W->rnd.nextU32() + 1;
+        if (!use16) W->rnd.init(reseed);
+        uint32_t ned = 0, off = 0; int64_t score = 0;
+        const bool ok = swBacktrace(rd, qu, rdlen, rf, rect, nceil, rdlen - 1, cc, ned, off, score);
+        W->rnd.init(use16 ? reseed : reseed + 1);
+        if (W->err) return false;
+        if (!ok) continue;
+        if (ned > HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
+        const uint32_t coordOff = (uint32_t)(rect.refl + off);
+        const uint32_t joinedOff = gh.joinedOff + coordOff - gh.toff;
+        initHit(gh, fw, 0, rdlen, 0, 0, gh.tidx, coordOff, joinedOff);
+        gh.score = score;
+        gh.nedits = ned;
+        for (uint32_t k = 0; k < ned; k++) gh.edits[k] = S.ned[k];
+        if (ned > W->maxEdits) W->maxEdits = ned;
+        replaceEditsWithAlts(gh, rdi);
+        return true;
+    }
+}

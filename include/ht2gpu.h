@@ -62,6 +62,16 @@ typedef struct {
     int32_t  blocks_per_sm;          /* 0 = default */
     int32_t  slots_per_lane;         /* state-regrouping mode: read slots per lane (2,4,8,16); 0 = default */
     int32_t  warp_per_read;          /* execution mode: 0/5 = block-shared slot pool (default), 2 = per-warp state regrouping, 4 = block-synchronous regrouping, 1 = one warp per read, 3 = one lane per read */
+    /* --bowtie2-dp (hisat2.cpp:293, 1770; SplicedAligner::hybridSearch spliced_aligner.h:209-297): 0 = off,
+     * 1 = dynamic-programming extension when the anchor search found nothing >= the minimum score, 2 = always.
+     * The presets are spelled out by the caller exactly as hisat2.cpp:1892-1909 does:
+     *   --sensitive      = bowtie2_dp 1 (unless given), khits raised to 10 only when -k < 10 was GIVEN, score-min L,0,-0.5
+     *   --very-sensitive = bowtie2_dp 2, khits = max(k, 30), score-min L,0,-1 */
+    int32_t  bowtie2_dp;
+    int32_t  gbar;                   /* --gbar 4: no gaps within this many positions of either read end (DP only) */
+    int32_t  score_min_type;         /* --score-min <type>,<const>,<coeff>: 'C', 'L', 'S' (sqrt) or 'G' (log); default L,0,-0.2 */
+    double   score_min_const;
+    double   score_min_coeff;
 } ht2gpu_options_t;
 
 /* A batch of reads, structure-of-arrays, host memory.  Read i occupies

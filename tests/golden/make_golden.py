@@ -183,7 +183,26 @@ OPTION_CASES = [
     ("min_frag=150,max_frag=320", ["-I", "150", "-X", "320"], True),
     ("nofw=1", ["--nofw"], True),
     ("khits=3", ["-k", "3"], True),
+    # "--mp a,b" becomes MMP=Q,a,b, which switches back to quality-aware penalties even under
+    # --ignore-quals (aligner_seed_policy.cpp:396-418); the CLI clears ignore_quals when --mp is given
+    ("mp_max=4,mp_min=2", ["--mp", "4,2", "--ignore-quals"], False),
+    # --score-min and the --bowtie2-dp seed extension (spliced_aligner.h:209-297); the presets are spelled
+    # out the way hisat2.cpp:1892-1909 applies them (an omitted -k stays the index default under --sensitive)
+    ("score_min_type=71,score_min_const=-5,score_min_coeff=-8", ["--score-min", "G,-5,-8"], False),
+    ("bowtie2_dp=2", ["--bowtie2-dp", "2"], False),
+    ("bowtie2_dp=1,score_min_type=76,score_min_const=0,score_min_coeff=-0.5", ["--sensitive"], False),
+    ("bowtie2_dp=2,khits=30,score_min_type=76,score_min_const=0,score_min_coeff=-1", ["--very-sensitive"], True),
+    ("bowtie2_dp=2,gbar=10,score_min_type=76,score_min_const=0,score_min_coeff=-0.6,rdg_const=4,rdg_linear=2",
+     ["--bowtie2-dp", "2", "--gbar", "10", "--score-min", "L,0,-0.6", "--rdg", "4,2"], True),
+    ("bowtie2_dp=1,khits=10,score_min_type=76,score_min_const=0,score_min_coeff=-0.5", ["--sensitive", "-k", "4"], True),
+    # graph index, reads carrying ALT alleles (FASTA)
+    ("bowtie2_dp=2,khits=30,score_min_type=76,score_min_const=0,score_min_coeff=-1", ["--very-sensitive"], False, "snp"),
+    ("bowtie2_dp=2", ["--bowtie2-dp", "2"], True, "snp"),
 ]
+OPTION_SETS = {   # name -> (index, format flag, SE file, PE files)
+    "tiny": ("tiny", "-q", "tiny_se.fq", ("tiny_pe_1.fq", "tiny_pe_2.fq")),
+    "snp": ("tiny_snp", "-f", "tiny_alt_1.fa", ("tiny_alt_1.fa", "tiny_alt_2.fa")),
+}
 
 
 def options():
@@ -191,13 +210,16 @@ def options():
     import hashlib, json
     al = os.path.join(REF, "hisat2-align-s")
     out = []
-    for opts, flags, paired in OPTION_CASES:
-        inp = ["-1", "tiny_pe_1.fq", "-2", "tiny_pe_2.fq"] if paired else ["-U", "tiny_se.fq"]
-        subprocess.run([al, "--no-spliced-alignment", "-q", "-x", "tiny"] + flags + inp + ["-S", "opt.tmp"], check=True, cwd=G,
+    for case in OPTION_CASES:
+        opts, flags, paired = case[:3]
+        setname = case[3] if len(case) > 3 else "tiny"
+        index, fmt, se, pe = OPTION_SETS[setname]
+        inp = ["-1", pe[0], "-2", pe[1]] if paired else ["-U", se]
+        subprocess.run([al, "--no-spliced-alignment", fmt, "-x", index] + flags + inp + ["-S", "opt.tmp"], check=True, cwd=G,
                        stderr=subprocess.DEVNULL)
         data = b"".join(l for l in open(os.path.join(G, "opt.tmp"), "rb") if not l.startswith(b"@PG"))
         out.append({"options": opts, "flags": flags, "paired": paired, "md5": hashlib.md5(data).hexdigest(),
-                    "records": data.count(b"\n")})
+                    "records": data.count(b"\n"), "index": index, "format": fmt, "reads": list(pe) if paired else [se]})
     os.remove(os.path.join(G, "opt.tmp"))
     json.dump(out, open(os.path.join(G, "option_matrix.json"), "w"), indent=1)
 

@@ -78,6 +78,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
     std::string sam;
     ht2_sam_header(sam, *img);
     Ht2Work* W = new Ht2Work();
+    Ht2SwScratch* swScratch = P.bowtie2Dp ? new Ht2SwScratch() : NULL;
     Ht2AlignerT<GRAPH> A;
     size_t nerr = 0;
     uint64_t nLF = 0;
@@ -86,10 +87,10 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
     for (size_t i = 0; pairedMode && i < reads.size(); i++) {
         Ht2HostRead& r1 = reads[i]; Ht2HostRead& r2 = reads2[i];
         r1.seed = ht2_gen_rand_seed(r1, 0); r2.seed = ht2_gen_rand_seed(r2, 0);
-        int64_t ms1 = ht2_minsc((uint32_t)r1.seq.size()), ms2 = ht2_minsc((uint32_t)r2.seq.size());
+        int64_t ms1 = ht2_minsc(P, (uint32_t)r1.seq.size()), ms2 = ht2_minsc(P, (uint32_t)r2.seq.size());
         Ht2ReadFilters f1 = ht2_filters(r1, ms1), f2 = ht2_filters(r2, ms2);
         Ht2ReadOut out; out.err = 0;
-        A.bind(img->blob.data(), &P, W);
+        A.bind(img->blob.data(), &P, W); A.sw = swScratch;
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         bool p1 = f1.pass(), p2 = f2.pass();
         W->rnd.init((p1 && p2) ? (r1.seed ^ r2.seed) : r1.seed);
@@ -123,11 +124,11 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
     for (size_t i = 0; !pairedMode && i < reads.size(); i++) {
         Ht2HostRead& rd = reads[i];
         rd.seed = ht2_gen_rand_seed(rd, 0);
-        int64_t minsc = ht2_minsc((uint32_t)rd.seq.size());
+        int64_t minsc = ht2_minsc(P, (uint32_t)rd.seq.size());
         Ht2ReadFilters f = ht2_filters(rd, minsc);
         Ht2ReadOut out;
         out.err = 0;
-        A.bind(img->blob.data(), &P, W);
+        A.bind(img->blob.data(), &P, W); A.sw = swScratch;
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         W->rnd.init(rd.seed);
         A.paired = false; A.rightendonly = false;
@@ -187,6 +188,7 @@ int main(int argc, char** argv) {
     if (const char* os = getenv("HT2_OPTS")) {
         std::string o(os); size_t p0 = 0;
         bool kseedsGiven = false;
+        char smT = 0; double smC = (double)0.0f, smL = (double)-0.2f;
         while (p0 < o.size()) {
             size_t c = o.find(',', p0); if (c == std::string::npos) c = o.size();
             std::string kv = o.substr(p0, c - p0); p0 = c + 1;
@@ -200,9 +202,17 @@ int main(int argc, char** argv) {
             else if (k == "ignore_quals") P.mmcostConstant = v; else if (k == "nofw") P.nofw = v; else if (k == "norc") P.norc = v;
             else if (k == "min_frag") P.minFrag = (uint32_t)v; else if (k == "max_frag") P.maxFrag = (uint32_t)v;
             else if (k == "no_mixed") P.mixed = v ? 0 : 1; else if (k == "no_discordant") P.discord = v ? 0 : 1;
+            else if (k == "bowtie2_dp") P.bowtie2Dp = (uint32_t)v; else if (k == "gbar") P.gapbar = v;
+            else if (k == "score_min_type") smT = (char)v; else if (k == "score_min_const") { smC = atof(kv.c_str() + e + 1); if (!smT) smT = 'L'; }
+            else if (k == "score_min_coeff") { smL = atof(kv.c_str() + e + 1); if (!smT) smT = 'L'; }
+            else if (k == "score_min") {   // score_min=L:0:-0.5
+                const char* t = kv.c_str() + e + 1; char ty = t[0]; double C = 0, L = 0;
+                if (sscanf(t + 1, ":%lf:%lf", &C, &L) < 1 || !ht2_set_score_min(P, ty, C, L)) { fprintf(stderr, "bad score_min %s\n", t); return 2; }
+            }
             else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
         }
         if (!kseedsGiven) P.kseeds = P.khits * 2 > 5 ? P.khits * 2 : 5;
+        if (smT && !ht2_set_score_min(P, smT, smC, smL)) { fprintf(stderr, "bad score_min_type\n"); return 2; }
     }
     const Ht2ImageHeader* Hh = (const Ht2ImageHeader*)img->blob.data();
     return Hh->global.linearFM ? alignAll<false>(img, P, reads, reads2, pairedMode, argv[3])

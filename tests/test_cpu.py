@@ -82,16 +82,19 @@ def test_host_graph_index_alignment_matches_golden_reference_sam(hostsim_bin, tm
 
 def test_host_state_machine_option_matrix(hostsim_bin, tmp_path):
     """Every option of the reference's command line that reaches the path (-k, --mp, --np, --rdg, --rfg,
-    --sp, --ignore-quals, --nofw/--norc, --secondary, --no-mixed, --no-discordant, -I/-X) against the md5
-    of the unmodified reference's SAM for the same flags (tests/golden/option_matrix.json)."""
+    --sp, --ignore-quals, --nofw/--norc, --secondary, --no-mixed, --no-discordant, -I/-X, --score-min,
+    --bowtie2-dp, --gbar, --sensitive, --very-sensitive) against the md5 of the unmodified reference's SAM
+    for the same flags (tests/golden/option_matrix.json), on the linear and the graph index."""
     import hashlib, json
     cases = json.load(open(os.path.join(GOLDEN, "option_matrix.json")))
-    assert len(cases) >= 14
+    assert len(cases) >= 23
+    assert sum("bowtie2_dp" in c["options"] for c in cases) >= 7
     for c in cases:
         out = str(tmp_path / "o.sam")
-        args = ["tiny_pe_1.fq", out, "tiny_pe_2.fq"] if c["paired"] else ["tiny_se.fq", out]
-        subprocess.run([hostsim_bin, "tiny"] + args, cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL,
-                       env=dict(os.environ, HT2_OPTS=c["options"]))
+        args = [c["reads"][0], out] + c["reads"][1:]
+        r = subprocess.run([hostsim_bin, c["index"]] + args, cwd=GOLDEN, check=True, stderr=subprocess.PIPE,
+                           env=dict(os.environ, HT2_OPTS=c["options"]))
+        assert b"err=" not in r.stderr, c
         got = hashlib.md5(b"\n".join(sam_lines(open(out, "rb").read())) + b"\n").hexdigest()
         assert got == c["md5"], c
 

@@ -147,29 +147,31 @@ def _option_cases():
     return json.load(open(os.path.join(GOLDEN, "option_matrix.json")))
 
 
-@pytest.mark.parametrize("case", range(14))
+@pytest.mark.parametrize("case", range(23))
 def test_option_matrix_matches_reference(h2, case, tmp_path):
     """Same option names and meaning as the reference's command line (-k, --mp, --np, --rdg, --rfg, --sp,
-    --ignore-quals, --nofw/--norc, --secondary, --no-mixed, --no-discordant, -I/-X): md5 of the SAM equals
+    --ignore-quals, --nofw/--norc, --secondary, --no-mixed, --no-discordant, -I/-X, --score-min, --bowtie2-dp,
+    --gbar and the --sensitive / --very-sensitive presets; linear and graph index): md5 of the SAM equals
     the committed md5 of the unmodified reference's output, and the reference is re-run on this box when
     oracle/_ref is present."""
     import hashlib
     c = _option_cases()[case]
-    opts = {k: int(v) for k, v in (kv.split("=") for kv in c["options"].split(","))}
-    idx = h2.Index(os.path.join(GOLDEN, "tiny"), **opts)
+    opts = {k: (float(v) if k in ("score_min_const", "score_min_coeff") else int(v))
+            for k, v in (kv.split("=") for kv in c["options"].split(","))}
+    idx = h2.Index(os.path.join(GOLDEN, c["index"]), **opts)
+    files = [os.path.join(GOLDEN, f) for f in c["reads"]]
+    reader = h2.ReadBatch.from_fastq if c["format"] == "-q" else h2.ReadBatch.from_fasta
     if c["paired"]:
-        f1, f2 = os.path.join(GOLDEN, "tiny_pe_1.fq"), os.path.join(GOLDEN, "tiny_pe_2.fq")
-        batch = h2.ReadBatch.from_fastq(f1, path2=f2)
-        inp = ["-1", f1, "-2", f2]
+        batch = reader(files[0], path2=files[1])
+        inp = ["-1", files[0], "-2", files[1]]
     else:
-        f1 = os.path.join(GOLDEN, "tiny_se.fq")
-        batch = h2.ReadBatch.from_fastq(f1)
-        inp = ["-U", f1]
+        batch = reader(files[0])
+        inp = ["-U", files[0]]
     sam, _ = gpu_sam(idx, batch)
     assert hashlib.md5(b"\n".join(sam_lines(sam)) + b"\n").hexdigest() == c["md5"]
     if os.path.exists(REFBIN):
         out = str(tmp_path / "ref.sam")
-        subprocess.run([REFBIN, "--no-spliced-alignment", "-q", "-x", os.path.join(GOLDEN, "tiny")] + c["flags"] + inp + ["-S", out],
+        subprocess.run([REFBIN, "--no-spliced-alignment", c["format"], "-x", os.path.join(GOLDEN, c["index"])] + c["flags"] + inp + ["-S", out],
                        check=True, stderr=subprocess.DEVNULL)
         assert sam_lines(sam) == sam_lines(open(out, "rb").read())
     idx.close()
