@@ -77,7 +77,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _LIBPATH
+    p = path or os.environ.get("HT2GPU_LIB") or _LIBPATH
     if not os.path.exists(p):
         raise Ht2GpuError("%s not found: run `python -m hisat2_b200.build` (no CPU fallback exists)" % p)
     lib = C.CDLL(p)

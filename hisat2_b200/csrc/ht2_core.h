@@ -25,17 +25,25 @@
 #endif
 #define HT2_MAX_EDITS 40
 #define HT2_MAX_PHITS 64
+#ifndef HT2_MAX_GHITS
 #define HT2_MAX_GHITS 64   /* max(khits, kseeds) anchors: --very-sensitive runs -k 30, i.e. 60 seeds */
+#endif
 #define HT2_POOL 40
 #define HT2_IE_POOL 96           /* in-edge entries per strand (graph indexes) */
 #define HT2_SEARCHED_BYTES 24576   /* ~600 searched hits (40 B typical) for both mates */
 
 #define HT2_MAX_RES 64
 #define HT2_MAX_PAIRS 96
+#ifndef HT2_MAX_COORDS
 #define HT2_MAX_COORDS 64
+#endif
 #define HT2_MAX_DEPTH 128
+#ifndef HT2_DEPTH_CAP
 #define HT2_DEPTH_CAP 32   /* recursion depth the workspace/stack is sized for */
+#endif
+#ifndef HT2_REFBUF
 #define HT2_REFBUF (HT2_MAX_RDLEN + 128)   /* read + the read gaps minsc allows (combineWith window): 83 at minsc -256 with the default --rdg */
+#endif
 
 #define HT2_MIN_I64 ((int64_t)0x8000000000000000ll)
 #define HT2_MIN_SCORE (HT2_MIN_I64 / 2)   /* getMinScore(), aln_sink.h:34 */
@@ -250,7 +258,7 @@ struct Ht2Work {
 // ------------------------------------------------------------------------
 // Scoring helpers (scoring.h:259-318, 96-130)
 // ------------------------------------------------------------------------
-HT2_HD int ht2_mmpen(const Ht2Params& P, int q) {
+HT2_HD int ht2_mmpen(const Ht2ParamsCore& P, int q) {
     if (P.mmcostConstant) return P.mmpMax;
     if (q < 0) q = 0;
     int ii = q < 40 ? q : 40;
@@ -258,13 +266,13 @@ HT2_HD int ht2_mmpen(const Ht2Params& P, int q) {
     return P.mmpMin + (int)(frac * (float)(P.mmpMax - P.mmpMin));
 }
 // Scoring::score(rdc, refm, q)
-HT2_HD int ht2_score(const Ht2Params& P, int rdc, int refm, int q) {
+HT2_HD int ht2_score(const Ht2ParamsCore& P, int rdc, int refm, int q) {
     if (rdc > 3 || refm > 15) return -P.npen;
     if ((refm & (1 << rdc)) != 0) return 0;
     return -ht2_mmpen(P, q);
 }
 // Scoring::sc(q) soft-clip penalty (scoring.h:312-318)
-HT2_HD int ht2_scpen(const Ht2Params& P, int q) {
+HT2_HD int ht2_scpen(const Ht2ParamsCore& P, int q) {
     if (q <= 33) return P.scpMin;
     q -= 33;
     if (q > 40) q = 40;
@@ -298,7 +306,7 @@ struct Ht2AlignerT {
     const uint8_t*        blob;
     const Ht2ImageHeader* H;
     Ht2Fm<uint32_t>       gfm;
-    const Ht2Params*      P;
+    const Ht2ParamsCore*  P;
     Ht2Work*              W;
     Ht2SwScratch*         sw;      // --bowtie2-dp scratch of this lane (NULL when dp is off)
     bool     paired;
@@ -318,7 +326,7 @@ struct Ht2AlignerT {
         nofw[0] = W->cfgNofw[0] != 0; nofw[1] = W->cfgNofw[1] != 0; norc[0] = W->cfgNorc[0] != 0; norc[1] = W->cfgNorc[1] != 0;
         minsc[0] = W->cfgMinsc[0]; minsc[1] = W->cfgMinsc[1];
     }
-    HT2_HD void bind(const uint8_t* blob_, const Ht2Params* P_, Ht2Work* W_) {
+    HT2_HD void bind(const uint8_t* blob_, const Ht2ParamsCore* P_, Ht2Work* W_) {
         blob = blob_;
         H = (const Ht2ImageHeader*)blob_;
         gfm.init(blob_, &H->global);

@@ -33,6 +33,7 @@ struct DevBatch {
     uint32_t        n_units;
     int32_t         paired;
     Ht2SwScratch*   sw;     // --bowtie2-dp scratch, one per launched thread (NULL when dp is off)
+    const int32_t*  minscTab; // --score-min per read length (Ht2Params::minscTab)
 };
 
 struct DevOut {
@@ -68,11 +69,11 @@ __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, u
 // (minsc = --score-min(len), default L,0,-0.2, clamped to <= 0 -- hisat2.cpp:441, 3380-3402; the
 // function is tabulated per read length on the host, Ht2Params::minscTab).  The N-ceiling product is
 // exact in double (24-bit constant x length < 2^9), so host (ht2_host.cpp:ht2_filters) and device agree.
-__device__ __forceinline__ bool ht2_dev_filter(const Ht2Params& P, const DevBatch& b, uint32_t ri, int64_t& minsc)
+__device__ __forceinline__ bool ht2_dev_filter(const DevBatch& b, uint32_t ri, int64_t& minsc)
 {
     const uint64_t o0 = b.offs[ri];
     const uint32_t len = (uint32_t)(b.offs[ri + 1] - o0);
-    int64_t m = P.minscTab[len <= HT2_PARAMS_MAX_RDLEN ? len : HT2_PARAMS_MAX_RDLEN];   // --score-min, tabulated on the host (ht2_set_score_min)
+    int64_t m = b.minscTab[len <= HT2_PARAMS_MAX_RDLEN ? len : HT2_PARAMS_MAX_RDLEN];   // --score-min, tabulated on the host (ht2_set_score_min)
     if (m > 0) m = 0;
     minsc = m;
     const uint32_t maxns = (uint32_t)((double)0.0f + (double)0.15f * (double)len);   // nCeil = L,0,0.15 (aligner_seed_policy.cpp:293-296)
@@ -85,7 +86,7 @@ __device__ __forceinline__ bool ht2_dev_filter(const Ht2Params& P, const DevBatc
 // Set up workspace W for unit u (one read or one pair): filters, seeds, reads.
 // Returns true when there is something to align (machineStart() was called).
 template <typename ALIGNER>
-__device__ __noinline__ bool ht2_setup_unit(ALIGNER& A, const Ht2Params& P, const DevBatch& b, uint32_t u, uint32_t& filtBits)
+__device__ __noinline__ bool ht2_setup_unit(ALIGNER& A, const Ht2ParamsCore& P, const DevBatch& b, uint32_t u, uint32_t& filtBits)
 {
     Ht2Work* W = A.W;
     W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0;
@@ -98,7 +99,7 @@ __device__ __noinline__ bool ht2_setup_unit(ALIGNER& A, const Ht2Params& P, cons
         A.paired = false; A.rightendonly = false;
         A.nofw[0] = P.nofw != 0; A.norc[0] = P.norc != 0; A.nofw[1] = true; A.norc[1] = true;
         int64_t ms;
-        const bool f0 = ht2_dev_filter(P, b, ri, ms);
+        const bool f0 = ht2_dev_filter(b, ri, ms);
         A.minsc[0] = ms; A.minsc[1] = (int64_t)HT2_IDX_MAX32;
         W->rnd.init(b.seeds[ri]);
         A.sinkReset(false);
@@ -110,7 +111,7 @@ __device__ __noinline__ bool ht2_setup_unit(ALIGNER& A, const Ht2Params& P, cons
     } else {
         const uint32_t r1 = 2 * u, r2 = 2 * u + 1;
         int64_t ms1, ms2;
-        const bool f1 = ht2_dev_filter(P, b, r1, ms1), f2 = ht2_dev_filter(P, b, r2, ms2);
+        const bool f1 = ht2_dev_filter(b, r1, ms1), f2 = ht2_dev_filter(b, r2, ms2);
         filtBits = (f1 ? 1u : 0u) | (f2 ? 2u : 0u);
         // nofw/norc per mate (hisat2.cpp:3444-3447)
         A.nofw[0] = P.gMate1fw ? (P.nofw != 0) : (P.norc != 0);
@@ -210,7 +211,7 @@ __device__ __noinline__ void ht2_finish_unit(Ht2Work* W, const DevOut& o, uint32
 //             machine on the warp's single workspace, lane 0 publishes.
 template <int LANES>
 __global__ void __launch_bounds__(128)
-ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
 {
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t tid = gtid / LANES;
@@ -273,7 +274,7 @@ __device__ __forceinline__ uint32_t rg_code(const Ht2Work* W)
 
 template <int RG_K>
 __global__ void __launch_bounds__(32 * RG_WARPS)
-ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
 {
     constexpr int RG_SLOTS = 32 * RG_K;
     __shared__ uint8_t  sCode[RG_WARPS][RG_SLOTS];
@@ -364,7 +365,7 @@ ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch
 #define BRG_WARPS 8
 template <int RG_K>
 __global__ void __launch_bounds__(32 * BRG_WARPS)
-ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
 {
     constexpr int NT = 32 * BRG_WARPS;
     constexpr int SLOTS = NT * RG_K;
@@ -468,7 +469,7 @@ ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2Params P, De
 
 template <int NW, int K, bool GRAPH>
 __global__ void __launch_bounds__(32 * NW)
-ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, DevOut o, Ht2Work* work)
+ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
 {
     constexpr int S = NW * 32 * K;      // slots of this block
     constexpr int NJ = S / 32;          // slots a lane may claim: lane + 32*j
@@ -605,7 +606,7 @@ struct SeedOut {
 
 template <bool GRAPH, bool FILL>
 __global__ void __launch_bounds__(128)
-ht2_seed_kernel(const uint8_t* __restrict__ blob, Ht2Params P, DevBatch b, uint32_t nReads, uint32_t maxRange, SeedOut o)
+ht2_seed_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, uint32_t nReads, uint32_t maxRange, SeedOut o)
 {
     const Ht2ImageHeader* H = (const Ht2ImageHeader*)blob;
     Ht2Fm<uint32_t> fm;
@@ -697,6 +698,7 @@ struct ht2gpu_handle {
     int            poolWarps;
     int            rgK;
     Ht2Work*       dWork;
+    int32_t*       dMinsc;   // --score-min table on the device (Ht2Params::minscTab)
     Ht2SwScratch*  dSw;      // --bowtie2-dp: one scratch per launched thread
     size_t         nWork;
     cudaStream_t   stream;
@@ -820,6 +822,8 @@ static int finishOpen(ht2gpu_handle* h)
         h->nWork = (size_t)h->nSM * h->bpsm * (h->tpb / 32) * 32 * h->rgK;
     } else
     h->nWork = (size_t)h->nSM * h->bpsm * h->tpb / h->lanes;
+    CK(cudaMalloc(&h->dMinsc, sizeof(h->P.minscTab)));
+    CK(cudaMemcpy(h->dMinsc, h->P.minscTab, sizeof(h->P.minscTab), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->dWork, h->nWork * sizeof(Ht2Work)));
     CK(cudaMemset(h->dWork, 0, h->nWork * sizeof(Ht2Work)));
     if (h->P.bowtie2Dp) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
@@ -835,7 +839,7 @@ static int finishOpen(ht2gpu_handle* h)
 static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
-    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL;
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL; h->dMinsc = NULL;
     h->stream = 0;
     h->dSeq = h->dQual = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->capBases = h->capReads = 0;
     h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL; h->dStats = NULL;
@@ -937,6 +941,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     if (h->dBlob && h->ownBlob) cudaFree(h->dBlob);
     if (h->dWork) cudaFree(h->dWork);
     if (h->dSw) cudaFree(h->dSw);
+    if (h->dMinsc) cudaFree(h->dMinsc);
     cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dOffs); cudaFree(h->dSeeds);
     cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters); cudaFree(h->dStats);
     if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
@@ -1009,7 +1014,7 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
 {
     DevBatch db;
     db.seq = h->dSeq; db.qual = b->qual ? h->dQual : NULL; db.offs = h->dOffs; db.seeds = h->dSeeds;
-    db.n_units = units; db.paired = b->paired; db.sw = h->dSw;
+    db.n_units = units; db.paired = b->paired; db.sw = h->dSw; db.minscTab = h->dMinsc;
     DevOut o;
     o.reads = h->dReads; o.alns = h->dAlns; o.edits = h->dEdits; o.pairs = h->dPairs;
     o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
@@ -1212,7 +1217,7 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     int rc = uploadBatch(h, b, h2d);
     if (rc) return rc;
     DevBatch db;
-    db.seq = h->dSeq; db.qual = NULL; db.offs = h->dOffs; db.seeds = h->dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL;
+    db.seq = h->dSeq; db.qual = NULL; db.offs = h->dOffs; db.seeds = h->dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.minscTab = h->dMinsc;
     uint32_t *dCounts = NULL, *dOffs3 = NULL;
     unsigned long long* dTot = NULL;
     SeedOut so; memset(&so, 0, sizeof(so));

@@ -12,9 +12,15 @@
 
 #include "ht2_graph.h"
 
+#ifndef HT2_GW_MAXELT
 #define HT2_GW_MAXELT 64      /* max(khits, kseeds) elements: --very-sensitive runs -k 30, i.e. 60 seeds */
+#endif
+#ifndef HT2_GW_MAXROWS
 #define HT2_GW_MAXROWS 128
+#endif
+#ifndef HT2_GW_MAXST
 #define HT2_GW_MAXST 96
+#endif
 #define HT2_GW_MASK 0xffffffffu
 
 struct Ht2GwState {

@@ -673,6 +673,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
     case TS_HYB_RET: {
         // --bowtie2-dp: dynamic programming around the anchor, then one more recursion on the
         // full-length hit (spliced_aligner.h:209-320)
+#ifndef HT2_NO_DP
         if (P->bowtie2Dp == 2 || (P->bowtie2Dp == 1 && W->childRet < minsc[W->curRdi])) {
             Ht2Hit& gh = W->genomeHits[W->hybHj];
             if (!W->err && swExtendAnchor(W->curRdi, gh)) {
@@ -681,6 +682,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
                 break;
             }
         }
+#endif
         W->genomeHitsDone[W->hybHj] = 1;
         W->hybIter++;
         W->st = TS_HYB_PICK;

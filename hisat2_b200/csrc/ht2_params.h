@@ -11,7 +11,8 @@
 
 #define HT2_PARAMS_MAX_RDLEN 256
 
-struct Ht2Params {
+// The part the kernels receive BY VALUE (kernel parameter space, read through the constant cache).
+struct Ht2ParamsCore {
     // Scoring
     int32_t mmpMax;        // --mp max (6)
     int32_t mmpMin;        // --mp min (2)
@@ -53,6 +54,13 @@ struct Ht2Params {
     // --bowtie2-dp (hisat2.cpp:293, 1770): 0 off, 1 when the anchor search found nothing >= minsc, 2 always
     uint32_t bowtie2Dp;
     int32_t  gapbar;       // --gbar (4): no gaps within this many rows of either read end (DP only)
+};
+
+// Host-side parameters = the core + the --score-min table.  The table reaches the device as a
+// separate 1 KB buffer (DevBatch::minscTab): keeping it out of the by-value kernel parameter keeps
+// every Ht2ParamsCore field a constant-bank read (a 1.2 KB parameter indexed dynamically, or the
+// whole struct behind a global pointer, cost 6 % of the aligner's throughput).
+struct Ht2Params : Ht2ParamsCore {
     // --score-min as a table: SimpleFunc::f<TAlScore>(len) for every read length (hisat2.cpp:3380,
     // simple_func.h:86-108), computed once on the host so that host and device agree for every
     // function type (C, L, S = sqrt, G = log).  NOT yet clamped to <= 0.

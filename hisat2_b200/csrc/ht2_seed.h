@@ -52,7 +52,7 @@ HT2_HD void ht2_seed_step(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c
 
 // HI_Aligner::partialSearch.  pseudogeneStop / anchorStop are in/out like the reference's.
 template <bool GRAPH>
-HT2_HD void ht2_seed_partial(const Ht2Fm<uint32_t>& fm, const Ht2Params& P, const uint8_t* seq, Ht2SeedState& st,
+HT2_HD void ht2_seed_partial(const Ht2Fm<uint32_t>& fm, const Ht2ParamsCore& P, const uint8_t* seq, Ht2SeedState& st,
                              Ht2SeedHit& ph, bool& pseudogeneStop, bool& anchorStop) {
     bool pseudogeneStop_ = pseudogeneStop, anchorStop_ = anchorStop;
     pseudogeneStop = anchorStop = false;

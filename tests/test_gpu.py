@@ -229,6 +229,41 @@ def test_bundled_graph_index_matches_reference_binary_run_here(h2, name, paired,
     index.close()
 
 
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("index,name,paired,flags,opts", [
+    ("22_20-21M", "hard20k", False, ["--bowtie2-dp", "2"], dict(bowtie2_dp=2)),
+    ("22_20-21M", "hard20k", True, ["--sensitive"], dict(bowtie2_dp=1, score_min_type=ord("L"), score_min_const=0.0, score_min_coeff=-0.5)),
+    ("22_20-21M_snp", "alt20k", True, ["--very-sensitive"], dict(bowtie2_dp=2, khits=30, score_min_type=ord("L"), score_min_const=0.0, score_min_coeff=-1.0)),
+    ("22_20-21M", "len150", False, ["--bowtie2-dp", "1", "--score-min", "L,0,-0.4", "--gbar", "2"],
+     dict(bowtie2_dp=1, gbar=2, score_min_type=ord("L"), score_min_const=0.0, score_min_coeff=-0.4)),
+])
+def test_dynamic_programming_extension_matches_reference_binary_run_here(h2, index, name, paired, flags, opts, tmp_path):
+    """--bowtie2-dp / --sensitive / --very-sensitive (the SwAligner seed extension): SAM identical to
+    the reference run on this box wherever no read hit a fixed device capacity (such reads are flagged, and
+    must be rare)."""
+    base = os.path.join(DATA, index)
+    f1, f2 = os.path.join(DATA, name + "_1.fa"), os.path.join(DATA, name + "_2.fa")
+    if not (os.path.exists(base + ".1.ht2") and os.path.exists(f1)):
+        pytest.skip("data/ not staged")
+    idx = h2.Index(base, **opts)
+    batch = h2.ReadBatch.from_fasta(f1, path2=f2 if paired else None)
+    res = idx.align(batch, allow_capacity=True)
+    errs = np.nonzero(res.reads["err"])[0]
+    assert len(errs) <= 0.002 * len(res.reads["err"])
+    sam = idx.sam_header() + idx.format_sam(batch, res)
+    out = str(tmp_path / "ref.sam")
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", base] + flags + (["-1", f1, "-2", f2] if paired else ["-U", f1]) +
+                   ["-S", out, "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    got, want = sam_lines(sam), sam_lines(open(out, "rb").read())
+    if len(errs) == 0:
+        assert got == want
+    else:
+        bad = set(batch.names[int(u) * (2 if paired else 1)].split(b"/")[0] for u in errs)
+        keep = lambda ls: [l for l in ls if l.split(b"\t")[0] not in bad]
+        assert keep(got) == keep(want)
+    idx.close()
+
+
 def test_seed_search_bundled_graph_index_matches_oracle(h2, oracle_bin):
     """The reference's bundled example index (22_20-21M_snp: 3,689 SNPs/indels, 958,359 rows over
     954,773 nodes): every H/G/C record of 20k hard reads equals the pinned oracle's."""
