@@ -187,9 +187,15 @@ struct Ht2AltScratch {
 #define HT2_SW_MAXGAP 10
 #define HT2_SW_MAXCOLS (HT2_MAX_RDLEN + 4 * HT2_SW_MAXGAP)
 #define HT2_SW_MAX_EDITS 160
+#define HT2_SW_SEG ((HT2_MAX_RDLEN + 1) / 2)     /* words per column: 2 rows (s16 halves) per 32-bit word */
 struct Ht2SwScratch {
-    uint16_t mask[(size_t)HT2_SW_MAXCOLS * HT2_MAX_RDLEN];   // [col][row]: admissible moves per cell + reported-through bit
-    int32_t  hcol[HT2_MAX_RDLEN], ecol[HT2_MAX_RDLEN];       // H / E of the previous column
+    // the three score matrices, striped (row i = half i / seg of word i % seg), column-major; one spare column
+    uint32_t H[(HT2_SW_MAXCOLS + 1) * HT2_SW_SEG];
+    uint32_t E[(HT2_SW_MAXCOLS + 1) * HT2_SW_SEG];
+    uint32_t F[(HT2_SW_MAXCOLS + 1) * HT2_SW_SEG];
+    uint32_t prof[5][HT2_SW_SEG], gbar[HT2_SW_SEG], rdoBar[HT2_SW_SEG];   // negated query profile / barrier / barrier + read-gap-open words
+    uint32_t rep[((size_t)HT2_SW_MAXCOLS * HT2_MAX_RDLEN + 31) / 32];   // reported-through bit per cell (col * nrow + row)
+    uint32_t nrow, seg;
     int32_t  lastH[HT2_SW_MAXCOLS];                          // last-row H per column (the candidates)
     uint8_t  rowPen[HT2_MAX_RDLEN];                          // mismatch penalty of each read row
     alignas(8) uint8_t rf[HT2_SW_MAXCOLS + 16];              // reference window, codes 0..4
@@ -297,6 +303,40 @@ HT2_HD int ht2_max_gaps(int64_t minsc, int open, int ext) {
     }
     return num - 1;
 }
+
+// ------------------------------------------------------------------------
+// 2 x s16 SIMD-in-word: the DPX instructions of sm_90+/sm_100 (VIADDMNMX / VIMNMX3 .S16x2), with
+// portable forms for the host test build
+// ------------------------------------------------------------------------
+HT2_HD uint32_t ht2_v2_addmax(uint32_t a, uint32_t b, uint32_t c) {   // per half: max(a + b, c), signed
+#ifdef __CUDA_ARCH__
+    return __viaddmax_s16x2(a, b, c);
+#else
+    uint32_t r = 0;
+    for (int k = 0; k < 32; k += 16) {
+        int x = (int16_t)(a >> k) + (int16_t)(b >> k), y = (int16_t)(c >> k);
+        r |= (uint32_t)(uint16_t)(x > y ? x : y) << k;
+    }
+    return r;
+#endif
+}
+HT2_HD uint32_t ht2_v2_max(uint32_t a, uint32_t b) {                  // per half: signed max
+#ifdef __CUDA_ARCH__
+    return __vmaxs2(a, b);
+#else
+    uint32_t r = 0;
+    for (int k = 0; k < 32; k += 16) { int x = (int16_t)(a >> k), y = (int16_t)(b >> k); r |= (uint32_t)(uint16_t)(x > y ? x : y) << k; }
+    return r;
+#endif
+}
+HT2_HD uint32_t ht2_v2_max3(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    return __vimax3_s16x2(a, b, c);
+#else
+    return ht2_v2_max(ht2_v2_max(a, b), c);
+#endif
+}
+HT2_HD uint32_t ht2_v2_splat(int v) { return (uint32_t)(uint16_t)v * 0x00010001u; }
 
 // ------------------------------------------------------------------------
 // The aligner

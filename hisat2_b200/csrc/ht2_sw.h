@@ -15,25 +15,34 @@
 // backtraceNucleotidesEnd2EndSseU8 aligner_swsse_ee_u8.cpp:1309-1902).  The
 // result replaces the anchor with a full-length hit.
 //
-// Restated here without the striping: the striped kernel plus its lazy-F loop
-// computes exactly the saturating Gotoh recurrences
+// Restated here: swFill IS the striped kernel, two rows per 32-bit word as signed 16-bit halves instead of
+// 16 (or 8) per SSE register, because sm_100a executes max(a + b, c) on s16x2 and the 3-input max in ONE
+// instruction each (the DPX family: __viaddmax_s16x2, __vimax3_s16x2) while the byte-wise video
+// instructions (__vsubus4, __vmaxu4) are emulated (about 6 and 4 instructions, measured in the SASS): a
+// column costs 8 SIMD instructions per word = 4 per cell.  Saturating subtraction a (-) b is
+// max(a + (-b), 0); the gap barrier is a penalty larger than any value.  The striped kernel plus its
+// lazy-F loop computes exactly the saturating Gotoh recurrences
 //     E[i][j] = max(E[i][j-1] (-) rdgape, (H[i][j-1] (-) rdgapo) (-) bar_i)
 //     F[i][j] = max(F[i-1][j] (-) rfgape,  H[i-1][j] (-) rfgapo) (-) bar_i
 //     H[i][j] = max(Hd (-) pen(i,j), E[i][j], F[i][j]),  Hd = top for row 0, floor for column 0
-// ((-) = subtraction saturating at the floor; bar_i = "infinite" inside the gap
-// barrier rows), column by column.  The backtrace only ever compares stored
-// cell values for equality, so the set of admissible moves of every cell is
-// computed while filling and kept as a 13-bit word per cell -- the same bits
-// the reference keeps in SSEMatrix::masks_ (sse_util.h) -- instead of three
-// score matrices: 2 bytes/cell instead of 3 + 2.
+// and the same code serves the reference's 8-bit and 16-bit paths: their floors (255 resp. 65535 below
+// the top) only clamp cells below minsc - 255, and such cells are never candidates, never on a path
+// (scores along a backtrace only rise towards row 0), never win a max against a cell >= minsc, and never
+// satisfy one of the backtrace's equality tests against a cell on the path -- so a floor 16383 below the
+// top gives the same candidates, paths and edits (minsc below -15000 is refused as a capacity error).
+//
+// The H, E and F planes are kept (6 B/cell, one 32-bit store per 2 cells per plane).  The backtrace only
+// ever compares stored cell values for equality; the move bits of a cell (the bits the reference keeps in
+// SSEMatrix::masks_, sse_util.h) are derived from the planes for the ~rdlen cells a backtrace visits.
 //
 // The backtrace is deterministic in this reference (the randomised choices are
 // compiled out, aligner_swsse_ee_u8.cpp:1405, 1461, 1532): preference diag > H up
 // > F up > H left > E left.  Its backtrack stack never helps: a popped branch
 // cell is already marked reported-through, so the pop cascades until the stack
 // is empty (aligner_swsse_ee_u8.cpp:1353-1361, 1580-1606); a blocked cell
-// therefore simply fails the candidate, with the marks left in place for the
-// next candidate.
+// therefore simply fails the candidate.  For the same reason the in-place mask updates
+// (hMaskSet / eMaskSet / fMaskSet) are never observed: the only mutable per-cell state that matters is
+// the reported-through bit, kept as one bit per cell for the candidates that follow.
 
 #define HT2_SWM_H(c)      ((c) & 31u)
 #define HT2_SWM_E(c)      (((c) >> 5) & 3u)
@@ -62,62 +71,129 @@ HT2_HD static bool swFrameRect(int64_t off, uint32_t rdlen, int64_t reflen, SwRe
 
 HT2_HD static uint8_t swMask2dna(int code) { return (uint8_t)("ACGTN"[code]); }
 
-// Fill + gather.  Returns the best last-row score (score space: 0 = perfect), or
+#define HT2_SW_TOP 16383      /* raw value of a perfect score; 0 = floor */
+#define HT2_SW_BAR 16384      /* gap-barrier penalty: larger than any raw value */
+
+// Striped fill + gather (alignNucleotidesEnd2EndSseU8 / SseI16, aligner_swsse_ee_u8.cpp:791-1163).
+// Row i lives in half i / seg of word i % seg.  Returns the best last-row score (0 = perfect), or
 // HT2_MIN_I64 when nothing reaches minsc.
-HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const uint8_t* rf, uint32_t ncol, int64_t minscR, bool use16) {
+HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const uint8_t* rf, uint32_t ncol, int64_t minscR) {
     Ht2SwScratch& S = *sw;
-    const int FLOOR = use16 ? -65535 : -255;
+    const uint32_t seg = (nrow + 1) >> 1;
+    const uint32_t gapbar = (uint32_t)P->gapbar;
+    const int rdgapo = P->rdGapConst + P->rdGapLinear;
+    S.nrow = nrow; S.seg = seg;
+    for (uint32_t k = 0, n = (ncol * nrow + 31) >> 5; k < n; k++) S.rep[k] = 0;   // reported-through bits
+    for (uint32_t i = 0; i < nrow; i++) S.rowPen[i] = (uint8_t)ht2_mmpen(*P, (int)qu[i] - 33);
+    for (uint32_t s = 0; s < seg; s++) {   // negated query profile / gap-barrier words (buildQueryProfileEnd2EndSseU8, :76-140)
+        uint32_t g = 0, go = 0, w[5] = {0, 0, 0, 0, 0};
+        for (uint32_t k = 0; k < 2; k++) {
+            const uint32_t i = k * seg + s;
+            int bar = 0;
+            if (i < nrow) {
+                if (i < gapbar || nrow - 1 - i < gapbar) bar = HT2_SW_BAR;
+                const int rdc = rd[i];
+                for (int refc = 0; refc < 5; refc++) {
+                    const int pen = (rdc > 3 || refc > 3) ? P->npen : (rdc == refc ? 0 : (int)S.rowPen[i]);
+                    w[refc] |= (uint32_t)(uint16_t)(-pen) << (16 * k);
+                }
+            }
+            g  |= (uint32_t)(uint16_t)(-bar) << (16 * k);
+            go |= (uint32_t)(uint16_t)(-(bar + rdgapo)) << (16 * k);
+        }
+        S.gbar[s] = g; S.rdoBar[s] = go;
+        for (int refc = 0; refc < 5; refc++) S.prof[refc][s] = w[refc];
+    }
+    const uint32_t nRDE = ht2_v2_splat(-P->rdGapLinear);
+    const uint32_t nRFO = ht2_v2_splat(-(P->rfGapConst + P->rfGapLinear)), nRFE = ht2_v2_splat(-P->rfGapLinear);
+    uint32_t* const Hz = S.H + (size_t)ncol * seg;   // an all-floor column standing in for column -1
+    for (uint32_t s = 0; s < seg; s++) { Hz[s] = 0; S.E[s] = 0; }
+    const uint32_t lastW = (nrow - 1) % seg, lastB = 16 * ((nrow - 1) / seg);
+    int best = 0;
+    for (uint32_t j = 0; j < ncol; j++) {
+        const uint32_t* prof = S.prof[rf[j] > 4 ? 4 : rf[j]];
+        uint32_t* Hc = S.H + (size_t)j * seg; uint32_t* Fc = S.F + (size_t)j * seg;
+        const uint32_t* Ec = S.E + (size_t)j * seg; uint32_t* En = S.E + (size_t)(j + 1) * seg;
+        const uint32_t* Hp = j ? S.H + (size_t)(j - 1) * seg : Hz;
+        uint32_t vF = 0;
+        uint32_t vH = (Hp[seg - 1] << 16) | (uint32_t)HT2_SW_TOP;   // diagonal of row 0 = perfect; of row seg = last row of half 0
+        for (uint32_t s = 0; s < seg; s++) {
+            uint32_t vE = Ec[s];
+            vF = ht2_v2_addmax(vF, S.gbar[s], 0);                       // veto ref-gap extensions in barrier rows
+            Fc[s] = vF;
+            vH = ht2_v2_addmax(vH, prof[s], 0);                         // match / mismatch
+            vH = ht2_v2_max3(vH, vE, vF);
+            Hc[s] = vH;
+            vE = ht2_v2_addmax(vE, nRDE, ht2_v2_addmax(vH, S.rdoBar[s], 0));   // E of the next column
+            En[s] = vE;
+            vF = ht2_v2_addmax(vF, nRFE, ht2_v2_addmax(vH, nRFO, 0));   // F of the next row
+            vH = Hp[s];
+        }
+        // lazy F: carry each half's last F into the other half's first rows while it still improves
+        {
+            uint32_t s = 0;
+            vF = ht2_v2_addmax(vF << 16, S.gbar[0], 0);
+            for (;;) {
+                const uint32_t old = Fc[s];
+                const uint32_t nf = ht2_v2_max(old, vF);
+                if (nf == old) break;
+                Fc[s] = nf;
+                const uint32_t vh = ht2_v2_max(Hc[s], nf);
+                Hc[s] = vh;
+                En[s] = ht2_v2_max(En[s], ht2_v2_addmax(vh, S.rdoBar[s], 0));
+                vF = nf;
+                if (++s == seg) { s = 0; vF <<= 16; }
+                vF = ht2_v2_addmax(ht2_v2_addmax(vF, nRFE, 0), S.gbar[s], 0);
+            }
+        }
+        const int lr = (int)((Hc[lastW] >> lastB) & 0xffffu);
+        S.lastH[j] = lr - HT2_SW_TOP;
+        if (lr > best) best = lr;
+    }
+    if ((int64_t)(best - HT2_SW_TOP) < minscR) return HT2_MIN_I64;
+    return best - HT2_SW_TOP;
+}
+
+HT2_HD static int swRaw(const uint32_t* plane, uint32_t seg, uint32_t row, uint32_t col) {
+    return (int)((plane[(size_t)col * seg + row % seg] >> (16 * (row / seg))) & 0xffffu);
+}
+// Move bits of a cell from the score planes (what the reference recomputes at every visited cell,
+// aligner_swsse_ee_u8.cpp:1376-1545); row > 0.
+HT2_NI uint32_t swCellFromPlanes(const uint8_t* rd, const uint8_t* rf, uint32_t row, uint32_t col) const {
+    const Ht2SwScratch& S = *sw;
+    const uint32_t seg = S.seg, nrow = S.nrow;
     const int rdgapo = P->rdGapConst + P->rdGapLinear, rdgape = P->rdGapLinear;
     const int rfgapo = P->rfGapConst + P->rfGapLinear, rfgape = P->rfGapLinear;
     const uint32_t gapbar = (uint32_t)P->gapbar;
-    for (uint32_t i = 0; i < nrow; i++) { S.hcol[i] = FLOOR; S.ecol[i] = FLOOR; S.rowPen[i] = (uint8_t)ht2_mmpen(*P, (int)qu[i] - 33); }
-    int best = FLOOR;
-    for (uint32_t j = 0; j < ncol; j++) {
-        const int refc = rf[j];
-        uint16_t* mcol = S.mask + (size_t)j * nrow;
-        int hPrev = FLOOR, fPrev = FLOOR, hAboveLeft = FLOOR;
-        for (uint32_t i = 0; i < nrow; i++) {
-            const int hleft = S.hcol[i], eleft = S.ecol[i];
-            const int hd = (i == 0) ? 0 : hAboveLeft;
-            const bool gb = (i < gapbar) || (nrow - 1 - i < gapbar);
-            const int rdc = rd[i];
-            const int pen = (rdc > 3 || refc > 3) ? P->npen : (rdc == refc ? 0 : (int)S.rowPen[i]);
-            int e = eleft - rdgape; if (e < FLOOR) e = FLOOR;
-            if (!gb) { int t = hleft - rdgapo; if (t > e) e = t; }
-            int f = FLOOR;
-            if (i > 0 && !gb) {
-                f = fPrev - rfgape; if (f < FLOOR) f = FLOOR;
-                int t = hPrev - rfgapo; if (t > f) f = t;
-            }
-            int h = hd - pen; if (h < FLOOR) h = FLOOR;
-            if (e > h) h = e;
-            if (f > h) h = f;
-            uint32_t cell = 0;
-            if (i > 0) {
-                uint32_t hm = 0, em = 0, fm = 0;
-                if (!gb) {
-                    if (h + rfgapo == hPrev) hm |= 1;
-                    if (j > 0 && h + rdgapo == hleft) hm |= 2;
-                    if (h + rfgape == fPrev) hm |= 4;
-                    if (j > 0 && h + rdgape == eleft) hm |= 8;
-                }
-                if (j > 0 && h + pen == hd) hm |= 16;
-                if (j > 0) { if (hleft - rdgapo == e) em |= 1; if (eleft - rdgape == e) em |= 2; }
-                if (hPrev - rfgapo == f) fm |= 1;
-                if (fPrev - rfgape == f) fm |= 2;
-                cell = hm | (em << 5) | (fm << 7) | (hm ? HT2_SWM_OH : 0) | (em ? HT2_SWM_OE : 0) | (fm ? HT2_SWM_OF : 0);
-            }
-            mcol[i] = (uint16_t)cell;
-            hAboveLeft = hleft;
-            S.hcol[i] = h; S.ecol[i] = e;
-            hPrev = h; fPrev = f;
-        }
-        S.lastH[j] = hPrev;
-        if (hPrev > best) best = hPrev;
+    const bool gb = (row < gapbar) || (nrow - 1 - row < gapbar);
+    const int h = swRaw(S.H, seg, row, col), e = swRaw(S.E, seg, row, col), f = swRaw(S.F, seg, row, col);
+    const int hup = swRaw(S.H, seg, row - 1, col), fup = swRaw(S.F, seg, row - 1, col);
+    uint32_t hm = 0, em = 0, fm = 0;
+    if (!gb) { if (h + rfgapo == hup) hm |= 1; if (h + rfgape == fup) hm |= 4; }
+    if (col > 0) {
+        const int hleft = swRaw(S.H, seg, row, col - 1), eleft = swRaw(S.E, seg, row, col - 1);
+        const int hd = swRaw(S.H, seg, row - 1, col - 1);
+        const int rdc = rd[row], refc = rf[col];
+        const int pen = (rdc > 3 || refc > 3) ? P->npen : (rdc == refc ? 0 : (int)S.rowPen[row]);
+        if (!gb) { if (h + rdgapo == hleft) hm |= 2; if (h + rdgape == eleft) hm |= 8; }
+        if (h + pen == hd) hm |= 16;
+        if (hleft - rdgapo == e) em |= 1;
+        if (eleft - rdgape == e) em |= 2;
     }
-    if ((int64_t)best < minscR) return HT2_MIN_I64;
-    if (best == FLOOR) return HT2_MIN_I64;   // "could have saturated" (aligner_swsse_ee_u8.cpp:1149-1154)
-    return best;
+    if (hup - rfgapo == f) fm |= 1;
+    if (fup - rfgape == f) fm |= 2;
+    return hm | (em << 5) | (fm << 7) | (hm ? HT2_SWM_OH : 0) | (em ? HT2_SWM_OE : 0) | (fm ? HT2_SWM_OF : 0);
+}
+HT2_NI uint32_t swGetCell(const uint8_t* rd, const uint8_t* rf, uint32_t row, uint32_t col) const {
+    const Ht2SwScratch& S = *sw;
+    const uint32_t bit = col * S.nrow + row;
+    if ((S.rep[bit >> 5] >> (bit & 31)) & 1u) return HT2_SWM_REP;
+    return row > 0 ? swCellFromPlanes(rd, rf, row, col) : 0;
+}
+HT2_HD void swMarkCell(uint32_t row, uint32_t col) {
+    Ht2SwScratch& S = *sw;
+    const uint32_t bit = col * S.nrow + row;
+    S.rep[bit >> 5] |= 1u << (bit & 31);
 }
 
 // One backtrace (aligner_swsse_ee_u8.cpp:1309-1902).  Edits land in S.ned (left to right).
@@ -133,30 +209,23 @@ HT2_NI bool swBacktrace(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, con
     int64_t score = 0; int ns = 0;
     bool ovl = false;
     for (;;) {
-        uint16_t& cellRef = S.mask[(size_t)col * nrow + row];
-        uint32_t cell = cellRef;
+        const uint32_t cell = swGetCell(rd, rf, row, col);
         bool empty = false, canMoveThru = true;
         int cur = -1;
         if (cell & HT2_SWM_REP) canMoveThru = false;
         else if (row > 0) {
             if (ct == CT_E) {
                 const uint32_t m = HT2_SWM_E(cell);
-                uint32_t nm = 0;
-                if (m == 3) { cur = MV_READ_OPEN; nm = 2; }
+                if (m == 3 || m == 1) cur = MV_READ_OPEN;          // H -> E preferred (:1405)
                 else if (m == 2) cur = MV_RDGAP_EXT;
-                else if (m == 1) cur = MV_READ_OPEN;
                 else { empty = true; canMoveThru = (cell & HT2_SWM_OE) == 0; }
-                cell = (cell & ~(3u << 5)) | (nm << 5);
             } else if (ct == CT_F) {
                 const uint32_t m = HT2_SWM_F(cell);
-                uint32_t nm = 0;
-                if (m == 3) { cur = MV_REF_OPEN; nm = 2; }
+                if (m == 3 || m == 1) cur = MV_REF_OPEN;           // H -> F preferred (:1461)
                 else if (m == 2) cur = MV_RFGAP_EXT;
-                else if (m == 1) cur = MV_REF_OPEN;
                 else { empty = true; canMoveThru = (cell & HT2_SWM_OF) == 0; }
-                cell = (cell & ~(3u << 7)) | (nm << 7);
             } else {
-                uint32_t m = HT2_SWM_H(cell);
+                const uint32_t m = HT2_SWM_H(cell);
                 int select = -1;
                 if (m != 0) {
                     if (m & 16) select = 4;        // H diag
@@ -164,13 +233,11 @@ HT2_NI bool swBacktrace(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, con
                     else if (m & 4) select = 2;    // F up
                     else if (m & 2) select = 1;    // H left
                     else select = 3;               // E left
-                    m &= ~(1u << select);
-                    cell = (cell & ~31u) | m;
                     cur = select == 4 ? MV_DIAG : select == 0 ? MV_REF_OPEN : select == 1 ? MV_READ_OPEN : select == 2 ? MV_RFGAP_EXT : MV_RDGAP_EXT;
                 } else { empty = true; canMoveThru = (cell & HT2_SWM_OH) == 0; }
             }
         }
-        cellRef = (uint16_t)(cell | HT2_SWM_REP);
+        swMarkCell(row, col);
         if (!canMoveThru) return false;
         {   // the cell joins the path: does it sit on a core diagonal?
             int64_t diagi = (int64_t)col - (int64_t)row + (int64_t)rect.triml;
@@ -283,10 +350,11 @@ HT2_NI bool swExtendAnchor(uint32_t rdi, Ht2Hit& gh) {
     // reference window; positions past the end of the sequence read as N (aligner_sw.cpp:160-212)
     const uint8_t* rf = getStretch(S.rf, gh.tidx, (uint32_t)rect.refl, ncol);
     const int64_t msc = minsc[rdi];
-    const bool use16 = !(msc >= -254);                    // aligner_sw.cpp:496
+    const bool use16 = !(msc >= -254);                    // the reference's 16-bit path (aligner_sw.cpp:496): only the RNG reseeding differs
+    if (msc < -15000) { W->err |= HT2_ERR_SW; return false; }
     // nCeil = L,0,0.15 (SwAligner::initRead, aligner_sw.cpp:45)
     const int nceil = (int)((double)0.0f + (double)0.15f * (double)rdlen);
-    const int64_t best = swFill(rd, qu, rdlen, rf, ncol, msc, use16);
+    const int64_t best = swFill(rd, qu, rdlen, rf, ncol, msc);
     if (best == HT2_MIN_I64) return false;
     // SwAligner::nextAlignment: candidates in (score desc, col desc) order
     int64_t prevScore = 0; uint32_t prevCol = 0; bool havePrev = false;
@@ -300,7 +368,7 @@ HT2_NI bool swExtendAnchor(uint32_t rdi, Ht2Hit& gh) {
         }
         if (!got) return false;
         prevScore = cs; prevCol = cc; havePrev = true;
-        if (S.mask[(size_t)cc * rdlen + (rdlen - 1)] & HT2_SWM_REP) continue;   // starting cell already covered
+        if (swGetCell(rd, rf, rdlen - 1, cc) & HT2_SWM_REP) continue;   // starting cell already covered
         uint32_t reseed = W->rnd.nextU32() + 1;
         if (!use16) W->rnd.init(reseed);
         uint32_t ned = 0, off = 0; int64_t score = 0;
