@@ -1319,21 +1319,23 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
     // host threads over contiguous unit ranges and the chunks are concatenated in order.
     auto doRange = [&](uint32_t u0, uint32_t u1, std::string& sam) {
       sam.reserve((size_t)(u1 - u0) * (b->paired ? 800 : 400));
+      Ht2HostRead rd1, rd2;      // reused across the range: no per-read heap traffic once the buffers have grown
+      Ht2ReadOut o;
       for (uint32_t u = u0; u < u1; u++) {
-        Ht2HostRead rd1, rd2;
         if (b->paired) { mkRead(2 * u, 1, rd1); mkRead(2 * u + 1, 2, rd2); }
         else mkRead(u, 0, rd1);
         Ht2ReadFilters f1 = ht2_filters(rd1, ht2_minsc(h->P, (uint32_t)rd1.seq.size()));
         Ht2ReadFilters f2 = f1;
         if (b->paired) f2 = ht2_filters(rd2, ht2_minsc(h->P, (uint32_t)rd2.seq.size()));
         const ht2gpu_read_result_t& rr = res->reads[u];
-        Ht2ReadOut o;
         o.rngLast = rr.rng_state; o.err = rr.err;
+        o.pairs.clear();
         uint32_t a = rr.aln_off;
         for (uint32_t m = 0; m < 2; m++) {
+            o.res[m].resize(rr.n_aln[m]);
             for (uint32_t k = 0; k < rr.n_aln[m]; k++, a++) {
                 const ht2gpu_aln_t& al = res->alns[a];
-                Ht2Res r;
+                Ht2Res& r = o.res[m][k];
                 r.tidx = al.tidx; r.toff = al.toff; r.fw = al.fw; r.score = al.score;
                 r.rdlen = (uint32_t)((m == 0 || !b->paired) ? rd1.seq.size() : rd2.seq.size());
                 r.trim5p = al.trim5; r.trim3p = al.trim3; r.rfextent = al.ref_extent; r.nedits = al.n_edits;
@@ -1342,7 +1344,6 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
                     r.edits[e].pos = se.pos; r.edits[e].chr = se.chr; r.edits[e].qchr = se.qchr; r.edits[e].type = se.type;
                     r.edits[e].pad = 0; r.edits[e].snpID = se.snp_id;
                 }
-                o.res[m].push_back(r);
             }
         }
         for (uint32_t k = 0; k < rr.n_pairs; k++)
@@ -1366,10 +1367,16 @@ extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* 
         for (auto& x : th) x.join();
     }
     size_t total = 0;
-    for (auto& s2 : parts) total += s2.size();
+    std::vector<size_t> at(parts.size());
+    for (size_t t = 0; t < parts.size(); t++) { at[t] = total; total += parts[t].size(); }
     char* p = (char*)malloc(total + 1);
-    size_t at = 0;
-    for (auto& s2 : parts) { memcpy(p + at, s2.data(), s2.size()); at += s2.size(); }
+    if (!p) return HT2GPU_ERR_ARG;
+    if (nth == 1) memcpy(p, parts[0].data(), parts[0].size());
+    else {   // every thread places its own chunk (first touch of the output pages is spread out too)
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth; t++) th.emplace_back([&, t]() { memcpy(p + at[t], parts[t].data(), parts[t].size()); });
+        for (auto& x : th) x.join();
+    }
     p[total] = 0;
     *out = p; if (out_len) *out_len = total;
     return HT2GPU_OK;

@@ -7,6 +7,15 @@
 
 #include <algorithm>
 
+// decimal append without a temporary std::string
+static inline void appendInt(std::string& o, int64_t v) {
+    char buf[24]; int n = 0;
+    uint64_t u = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) o.push_back('-');
+    while (n) o.push_back(buf[--n]);
+}
+
 // ---------------------------------------------------------------------------
 // parameters
 // ---------------------------------------------------------------------------
@@ -254,7 +263,7 @@ void ht2_sam_header(std::string& o, const Ht2Image& img)
         const char* nm = img.refName(i);
         for (const char* c = nm; *c && !isspace((unsigned char)*c); c++) o.push_back(*c);
         o += "\tLN:";
-        o += std::to_string(img.refPlen(i));
+        appendInt(o, img.refPlen(i));
         o += "\n";
     }
 }
@@ -463,7 +472,7 @@ struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660
         }
     }
     void cigar(std::string& o) const {
-        if (trimLS > 0) { o += std::to_string(trimLS); o.push_back('S'); }
+        if (trimLS > 0) { appendInt(o, trimLS); o.push_back('S'); }
         size_t ln = ref.size();
         for (size_t i = 0; i < ln; i++) {
             char op = rel[i];
@@ -475,9 +484,9 @@ struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660
                 if (op2 != op) break;
             }
             i += (run - 1);
-            o += std::to_string(run); o.push_back(op);
+            appendInt(o, run); o.push_back(op);
         }
-        if (trimRS > 0) { o += std::to_string(trimRS); o.push_back('S'); }
+        if (trimRS > 0) { appendInt(o, trimRS); o.push_back('S'); }
     }
     void mdz(std::string& o) const {
         bool mm_last = false, rdgap_last = false, first_print = true;
@@ -493,7 +502,7 @@ struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660
                 }
                 i += (run - 1);
                 size_t r = run - ninserts;
-                if (r > 0) { o += std::to_string(r); first_print = false; mm_last = false; rdgap_last = false; }
+                if (r > 0) { appendInt(o, r); first_print = false; mm_last = false; rdgap_last = false; }
             } else if (op == 'X') {
                 if (rdgap_last || mm_last || first_print) o.push_back('0');
                 o.push_back(ref[i]);
@@ -533,11 +542,16 @@ void appendRefName(std::string& o, const Ht2Image& img, uint32_t tidx) {
 void appendSeqQual(std::string& o, const Ht2HostRead& rd, bool fw) {
     size_t n = rd.seq.size();
     if (n == 0) { o += "*\t*"; return; }   // aln_sink.h:3194, 3210
-    if (fw) for (size_t i = 0; i < n; i++) o.push_back("ACGTN"[rd.seq[i]]);
-    else for (size_t i = 0; i < n; i++) { uint8_t c = rd.seq[n - i - 1]; o.push_back("ACGTN"[c < 4 ? (c ^ 3) : 4]); }
-    o.push_back('\t');
-    if (fw) for (size_t i = 0; i < n; i++) o.push_back((char)rd.qual[i]);
-    else for (size_t i = 0; i < n; i++) o.push_back((char)rd.qual[n - i - 1]);
+    const size_t at = o.size();
+    o.resize(at + 2 * n + 1);
+    char* d = &o[at];
+    const uint8_t* sq = rd.seq.data(); const uint8_t* ql = rd.qual.data();
+    if (fw) { for (size_t i = 0; i < n; i++) d[i] = "ACGTN"[sq[i]]; }
+    else for (size_t i = 0; i < n; i++) { uint8_t c = sq[n - i - 1]; d[i] = "TGCAN"[c < 4 ? c : 4]; }
+    d[n] = '\t';
+    d += n + 1;
+    if (fw) memcpy(d, ql, n);
+    else for (size_t i = 0; i < n; i++) d[i] = (char)ql[n - i - 1];
 }
 void appendYF(std::string& o, const Ht2ReadFilters& f) {
     const char* flag = "";
@@ -604,11 +618,11 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, 
     if (!fl.primary) flag |= 256;
     if (rs != NULL && !rs->fw) flag |= 16;
     if (rs == NULL) flag |= 4;
-    o += std::to_string(flag);
+    appendInt(o, flag);
     o.push_back('\t');
     const char* ytz = fl.concordant() ? "CP" : fl.discordant() ? "DP" : fl.unpairedMate() ? "UP" : "UU";
     if (rs == NULL) {
-        if (summ.orefid != -1) { appendRefName(o, img, (uint32_t)summ.orefid); o.push_back('\t'); o += std::to_string(summ.orefoff + 1); o += "\t0\t*\t=\t"; o += std::to_string(summ.orefoff + 1); o += "\t0\t"; }
+        if (summ.orefid != -1) { appendRefName(o, img, (uint32_t)summ.orefid); o.push_back('\t'); appendInt(o, summ.orefoff + 1); o += "\t0\t*\t=\t"; appendInt(o, summ.orefoff + 1); o += "\t0\t"; }
         else o += "*\t0\t0\t*\t*\t0\t0\t";
         appendSeqQual(o, rd, true);
         o += "\tYT:Z:"; o += ytz;
@@ -616,43 +630,55 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, 
         o.push_back('\n');
         return;
     }
-    Stacked st;
-    {
+    // Gapless alignments (mismatches only; the vast majority): CIGAR and MD:Z follow from the edit
+    // positions directly -- what StackedAln::buildCigar / buildMdz (aligner_result.cpp:793-1000) print for a
+    // stack without I/D columns, with nothing for leftAlign to move.  Everything else goes through the
+    // stacked form.
+    bool gapless = true;
+    for (uint32_t i = 0; i < rs->nedits; i++) if (rs->edits[i].type != HT2_EDIT_MM) { gapless = false; break; }
+    static thread_local Stacked st;
+    static thread_local std::vector<Ht2Edit> nedBuf;
+    static thread_local std::vector<uint8_t> seqBuf;
+    size_t trimLS = rs->trim5p, trimRS = rs->trim3p;
+    const size_t len_trimmed = rd.seq.size() - trimLS - trimRS;
+    if (!rs->fw) std::swap(trimLS, trimRS);
+    if (!gapless) {
         // AlnRes::initStacked (aligner_result.h:1856-1873)
-        size_t trimLS = rs->trim5p, trimRS = rs->trim3p;
-        size_t len_trimmed = rd.seq.size() - trimLS - trimRS;
-        std::vector<Ht2Edit> ned(rs->edits, rs->edits + rs->nedits);
-        std::vector<uint8_t> s(rd.seq);
+        nedBuf.assign(rs->edits, rs->edits + rs->nedits);
+        seqBuf.assign(rd.seq.begin(), rd.seq.end());
         if (!rs->fw) {
-            invertPossHost(ned, len_trimmed);
-            std::swap(trimLS, trimRS);
-            size_t n = s.size();
-            for (size_t i = 0; i < n; i++) { uint8_t c = rd.seq[n - i - 1]; s[i] = c < 4 ? (uint8_t)(c ^ 3) : (uint8_t)4; }
+            invertPossHost(nedBuf, len_trimmed);
+            size_t n = seqBuf.size();
+            for (size_t i = 0; i < n; i++) { uint8_t c = rd.seq[n - i - 1]; seqBuf[i] = c < 4 ? (uint8_t)(c ^ 3) : (uint8_t)4; }
         }
-        st.init(s, ned.data(), ned.size(), trimLS, trimRS);
+        st.init(seqBuf, nedBuf.data(), nedBuf.size(), trimLS, trimRS);
         st.leftAlign(false);
     }
     appendRefName(o, img, rs->tidx);
     o.push_back('\t');
-    o += std::to_string((int64_t)rs->toff + 1);
+    appendInt(o, (int64_t)rs->toff + 1);
     o.push_back('\t');
-    o += std::to_string(mapqV2(P, summ, rd.mate < 2, rd.seq.size(), ordlen));
+    appendInt(o, mapqV2(P, summ, rd.mate < 2, rd.seq.size(), ordlen));
     o.push_back('\t');
-    st.cigar(o);
+    if (gapless) {
+        if (trimLS > 0) { appendInt(o, trimLS); o.push_back('S'); }
+        if (len_trimmed > 0) { appendInt(o, len_trimmed); o.push_back('M'); }
+        if (trimRS > 0) { appendInt(o, trimRS); o.push_back('S'); }
+    } else st.cigar(o);
     o.push_back('\t');
     if (fl.partOfPair()) {
         if (rso != NULL && rs->tidx != rso->tidx) { appendRefName(o, img, rso->tidx); o.push_back('\t'); }
         else o += "=\t";
-        o += std::to_string((int64_t)(rso ? rso->toff : rs->toff) + 1);
+        appendInt(o, (int64_t)(rso ? rso->toff : rs->toff) + 1);
         o.push_back('\t');
     } else o += "*\t0\t";
-    o += fraglenSet ? std::to_string(fraglen) : std::string("0");
+    appendInt(o, fraglenSet ? fraglen : 0);
     o.push_back('\t');
     appendSeqQual(o, rd, rs->fw != 0);
     // optional flags (sam.h:525-1010)
-    o += "\tAS:i:"; o += std::to_string(rs->score);
+    o += "\tAS:i:"; appendInt(o, rs->score);
     const ScoreKey& sb = summ.secbest[rd.mate < 2 ? 0 : 1];
-    if (sb.valid) { o += "\tZS:i:"; o += std::to_string(sb.score); }
+    if (sb.valid) { o += "\tZS:i:"; appendInt(o, sb.score); }
     o += "\tXN:i:0";
     // counts exclude edits that are known ALTs (snpID < #alts, sam.h:574-647)
     const Ht2ImageHeader* IH = img.header();
@@ -675,16 +701,27 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, 
             }
         }
     }
-    o += "\tXM:i:"; o += std::to_string(num_mm);
-    o += "\tXO:i:"; o += std::to_string(num_go);
-    o += "\tXG:i:"; o += std::to_string(num_gx);
-    o += "\tNM:i:"; o += std::to_string(NM);
-    o += "\tMD:Z:"; st.mdz(o);
-    if (summ.paired && haveOscore && rso) { o += "\tYS:i:"; o += std::to_string(rso->score); }
+    o += "\tXM:i:"; appendInt(o, num_mm);
+    o += "\tXO:i:"; appendInt(o, num_go);
+    o += "\tXG:i:"; appendInt(o, num_gx);
+    o += "\tNM:i:"; appendInt(o, NM);
+    o += "\tMD:Z:";
+    if (gapless) {   // <matches>[<ref char><matches>]..., a 0 between adjacent mismatches and at either end
+        size_t prevEnd = 0;
+        for (uint32_t k = 0; k < rs->nedits; k++) {
+            const Ht2Edit& e = rs->fw ? rs->edits[k] : rs->edits[rs->nedits - 1 - k];
+            const size_t p = rs->fw ? (size_t)e.pos : len_trimmed - (size_t)e.pos - 1;
+            appendInt(o, (int64_t)(p - prevEnd));
+            o.push_back((char)e.chr);
+            prevEnd = p + 1;
+        }
+        appendInt(o, (int64_t)(len_trimmed - prevEnd));
+    } else st.mdz(o);
+    if (summ.paired && haveOscore && rso) { o += "\tYS:i:"; appendInt(o, rso->score); }
     o += "\tYT:Z:"; o += ytz;
     appendYF(o, f);
-    if (fl.concordant() || fl.discordant()) { o += "\tNH:i:"; o += std::to_string(summ.numAlnsPaired); }
-    else { o += "\tNH:i:"; o += std::to_string((fl.pairing == PAIR_UNPAIRED || fl.readMate1()) ? summ.numAlns[0] : summ.numAlns[1]); }
+    if (fl.concordant() || fl.discordant()) { o += "\tNH:i:"; appendInt(o, summ.numAlnsPaired); }
+    else { o += "\tNH:i:"; appendInt(o, (fl.pairing == PAIR_UNPAIRED || fl.readMate1()) ? summ.numAlns[0] : summ.numAlns[1]); }
     // Zs:Z: the known ALTs the alignment went through (sam.h:983-1032)
     if (nAlts > 0) {
         std::vector<Ht2Edit> ned(rs->edits, rs->edits + rs->nedits);
@@ -714,7 +751,7 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, 
                 }
                 j--;
             }
-            o += std::to_string(pos);
+            appendInt(o, pos);
             o += (snp.type == HT2_ALT_SNP_SGL) ? "|S|" : (snp.type == HT2_ALT_SNP_DEL ? "|D|" : "|I|");
             const char* nm = names;
             for (uint32_t k = 0; k < si; k++) nm += strlen(nm) + 1;
