@@ -6,6 +6,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <thread>
 
 // decimal append without a temporary std::string
 static inline void appendInt(std::string& o, int64_t v) {
@@ -918,4 +919,89 @@ void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
         appendMate(o, img, P, rd2, 0, f2, NULL, NULL, s, fl, false, 0, false);
     }
     out.rngLast = rnd.last;
+}
+
+// The SAM back end of one batch (ht2gpu_format_sam): structured results -> SAM records, on host
+// threads over contiguous unit ranges, chunks placed in read order (= --reorder).
+bool ht2_format_batch(const Ht2Image& img, const Ht2Params& P, const ht2gpu_read_batch_t* b, const char* names,
+                      const ht2gpu_result_batch_t* res, char** out, size_t* out_len, unsigned nth)
+{
+    const uint32_t units = b->paired ? b->n_reads / 2 : b->n_reads;
+    // read-name table (names are '\0'-terminated, concatenated)
+    std::vector<const char*> nameOf((size_t)b->n_reads + 1);
+    {
+        const char* nm = names;
+        for (uint32_t i = 0; i < b->n_reads; i++) { nameOf[i] = nm; nm += strlen(nm) + 1; }
+    }
+    auto mkRead = [&](uint32_t i, int mate, Ht2HostRead& rd) {
+        rd.name = nameOf[i];
+        rd.mate = mate;
+        const uint8_t* s = b->seq + b->offs[i];
+        uint32_t len = (uint32_t)(b->offs[i + 1] - b->offs[i]);
+        rd.seq.assign(s, s + len);
+        if (b->qual) rd.qual.assign(b->qual + b->offs[i], b->qual + b->offs[i] + len); else rd.qual.assign(len, (uint8_t)'I');
+    };
+    // Reads are independent (each carries its own RNG state), so the back end runs on
+    // host threads over contiguous unit ranges and the chunks are concatenated in order.
+    auto doRange = [&](uint32_t u0, uint32_t u1, std::string& sam) {
+      sam.reserve((size_t)(u1 - u0) * (b->paired ? 800 : 400));
+      Ht2HostRead rd1, rd2;      // reused across the range: no per-read heap traffic once the buffers have grown
+      Ht2ReadOut o;
+      for (uint32_t u = u0; u < u1; u++) {
+        if (b->paired) { mkRead(2 * u, 1, rd1); mkRead(2 * u + 1, 2, rd2); }
+        else mkRead(u, 0, rd1);
+        Ht2ReadFilters f1 = ht2_filters(rd1, ht2_minsc(P, (uint32_t)rd1.seq.size()));
+        Ht2ReadFilters f2 = f1;
+        if (b->paired) f2 = ht2_filters(rd2, ht2_minsc(P, (uint32_t)rd2.seq.size()));
+        const ht2gpu_read_result_t& rr = res->reads[u];
+        o.rngLast = rr.rng_state; o.err = rr.err;
+        o.pairs.clear();
+        uint32_t a = rr.aln_off;
+        for (uint32_t m = 0; m < 2; m++) {
+            o.res[m].resize(rr.n_aln[m]);
+            for (uint32_t k = 0; k < rr.n_aln[m]; k++, a++) {
+                const ht2gpu_aln_t& al = res->alns[a];
+                Ht2Res& r = o.res[m][k];
+                r.tidx = al.tidx; r.toff = al.toff; r.fw = al.fw; r.score = al.score;
+                r.rdlen = (uint32_t)((m == 0 || !b->paired) ? rd1.seq.size() : rd2.seq.size());
+                r.trim5p = al.trim5; r.trim3p = al.trim3; r.rfextent = al.ref_extent; r.nedits = al.n_edits;
+                for (uint32_t e = 0; e < al.n_edits && e < HT2_MAX_EDITS; e++) {
+                    const ht2gpu_edit_t& se = res->edits[al.edit_off + e];
+                    r.edits[e].pos = se.pos; r.edits[e].chr = se.chr; r.edits[e].qchr = se.qchr; r.edits[e].type = se.type;
+                    r.edits[e].pad = 0; r.edits[e].snpID = se.snp_id;
+                }
+            }
+        }
+        for (uint32_t k = 0; k < rr.n_pairs; k++)
+            o.pairs.push_back(std::make_pair(res->pairs[2 * (rr.pair_off + k)], res->pairs[2 * (rr.pair_off + k) + 1]));
+        if (b->paired) ht2_finish_paired(sam, img, P, rd1, rd2, f1, f2, o);
+        else ht2_finish_unpaired(sam, img, P, rd1, f1, o);
+      }
+    };
+    if (nth > 64) nth = 64;
+    if (nth < 1 || units < 4096) nth = 1;
+    std::vector<std::string> parts(nth);
+    if (nth == 1) doRange(0, units, parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth; t++) {
+            const uint32_t u0 = (uint32_t)((uint64_t)units * t / nth), u1 = (uint32_t)((uint64_t)units * (t + 1) / nth);
+            th.emplace_back([&, t, u0, u1]() { doRange(u0, u1, parts[t]); });
+        }
+        for (auto& x : th) x.join();
+    }
+    size_t total = 0;
+    std::vector<size_t> at(parts.size());
+    for (size_t t = 0; t < parts.size(); t++) { at[t] = total; total += parts[t].size(); }
+    char* p = (char*)malloc(total + 1);
+    if (!p) return false;
+    if (nth == 1) memcpy(p, parts[0].data(), parts[0].size());
+    else {   // every thread places its own chunk (first touch of the output pages is spread out too)
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth; t++) th.emplace_back([&, t]() { memcpy(p + at[t], parts[t].data(), parts[t].size()); });
+        for (auto& x : th) x.join();
+    }
+    p[total] = 0;
+    *out = p; if (out_len) *out_len = total;
+    return true;
 }

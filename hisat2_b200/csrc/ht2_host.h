@@ -14,6 +14,7 @@
 
 #include "ht2_core.h"
 #include "ht2_index.h"
+#include "../../include/ht2gpu.h"
 
 struct Ht2HostRead {
     std::string name;
@@ -62,5 +63,9 @@ void ht2_finish_unpaired(std::string& o, const Ht2Image& img, const Ht2Params& P
 void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
                        const Ht2HostRead& rd1, const Ht2HostRead& rd2,
                        const Ht2ReadFilters& f1, const Ht2ReadFilters& f2, Ht2ReadOut& out);
+
+// ht2gpu_format_sam's body: host-only, shared with the test build
+bool ht2_format_batch(const Ht2Image& img, const Ht2Params& P, const ht2gpu_read_batch_t* b, const char* names,
+                      const ht2gpu_result_batch_t* res, char** out, size_t* out_len, unsigned nthreads);
 
 #endif

@@ -77,6 +77,31 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
                     const char* outPath) {
     std::string sam;
     ht2_sam_header(sam, *img);
+    // HT2_VIA_BATCH=1: hand the results over in the C ABI's batch structures (what the kernels' finish step
+    // writes, ht2_gpu.cu ht2_finish_unit) and let ht2_format_batch -- the body of ht2gpu_format_sam -- print
+    // them, on HT2_THREADS host threads
+    const bool viaBatch = getenv("HT2_VIA_BATCH") != NULL;
+    std::vector<ht2gpu_read_result_t> bReads; std::vector<ht2gpu_aln_t> bAlns; std::vector<ht2gpu_edit_t> bEdits; std::vector<uint16_t> bPairs;
+    auto collect = [&](const Ht2Work* Wk) {
+        ht2gpu_read_result_t rr; memset(&rr, 0, sizeof(rr));
+        rr.aln_off = (uint32_t)bAlns.size(); rr.pair_off = (uint32_t)(bPairs.size() / 2);
+        rr.n_aln[0] = (uint16_t)Wk->nRes[0]; rr.n_aln[1] = (uint16_t)Wk->nRes[1]; rr.n_pairs = Wk->nPairs;
+        rr.rng_state = Wk->rnd.last; rr.err = Wk->err;
+        for (uint32_t m = 0; m < 2; m++) for (uint32_t i = 0; i < Wk->nRes[m]; i++) {
+            const Ht2Res& r = Wk->res[m][i];
+            ht2gpu_aln_t d; memset(&d, 0, sizeof(d));
+            d.tidx = r.tidx; d.toff = r.toff; d.score = (int32_t)r.score; d.fw = (uint8_t)r.fw; d.mate = (uint8_t)m;
+            d.n_edits = (uint16_t)r.nedits; d.trim5 = (uint16_t)r.trim5p; d.trim3 = (uint16_t)r.trim3p; d.ref_extent = r.rfextent;
+            d.edit_off = (uint32_t)bEdits.size();
+            for (uint32_t k = 0; k < r.nedits; k++) {
+                ht2gpu_edit_t e; e.pos = r.edits[k].pos; e.chr = r.edits[k].chr; e.qchr = r.edits[k].qchr; e.type = r.edits[k].type; e.pad = 0; e.snp_id = r.edits[k].snpID;
+                bEdits.push_back(e);
+            }
+            bAlns.push_back(d);
+        }
+        for (uint32_t k = 0; k < Wk->nPairs; k++) { bPairs.push_back(Wk->pairs[k][0]); bPairs.push_back(Wk->pairs[k][1]); }
+        bReads.push_back(rr);
+    };
     Ht2Work* W = new Ht2Work();
     Ht2SwScratch* swScratch = P.bowtie2Dp ? new Ht2SwScratch() : NULL;
     Ht2AlignerT<GRAPH> A;
@@ -119,7 +144,8 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
         out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
         for (uint32_t k = 0; k < W->nPairs; k++) out.pairs.push_back(std::make_pair(W->pairs[k][0], W->pairs[k][1]));
-        { auto t0 = std::chrono::steady_clock::now(); ht2_finish_paired(sam, *img, P, r1, r2, f1, f2, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
+        if (viaBatch) { if (!(p1 || p2) || (W->err & HT2_ERR_RDLEN)) { W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0; } collect(W); }
+        else { auto t0 = std::chrono::steady_clock::now(); ht2_finish_paired(sam, *img, P, r1, r2, f1, f2, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
     }
     for (size_t i = 0; !pairedMode && i < reads.size(); i++) {
         Ht2HostRead& rd = reads[i];
@@ -148,7 +174,25 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         if (W->err) { nerr++; fprintf(stderr, "read %zu (%s): err=0x%x\n", i, rd.name.c_str(), W->err); }
         out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
         out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
-        { auto t0 = std::chrono::steady_clock::now(); ht2_finish_unpaired(sam, *img, P, rd, f, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
+        if (viaBatch) { if (!f.pass() || (W->err & HT2_ERR_RDLEN)) { W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0; } collect(W); }
+        else { auto t0 = std::chrono::steady_clock::now(); ht2_finish_unpaired(sam, *img, P, rd, f, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
+    }
+    if (viaBatch) {
+        std::vector<uint8_t> seq, qual; std::vector<uint64_t> offs(1, 0); std::string names;
+        auto add = [&](const Ht2HostRead& r) { seq.insert(seq.end(), r.seq.begin(), r.seq.end()); qual.insert(qual.end(), r.qual.begin(), r.qual.end());
+                                               offs.push_back(seq.size()); names += r.name; names.push_back('\0'); };
+        for (size_t i = 0; i < reads.size(); i++) { add(reads[i]); if (pairedMode) add(reads2[i]); }
+        ht2gpu_read_batch_t rb; memset(&rb, 0, sizeof(rb));
+        rb.n_reads = (uint32_t)(offs.size() - 1); rb.paired = pairedMode ? 1 : 0; rb.seq = seq.data(); rb.qual = qual.data(); rb.offs = offs.data();
+        ht2gpu_result_batch_t res; memset(&res, 0, sizeof(res));
+        res.n_reads = (uint32_t)bReads.size(); res.reads = bReads.data(); res.n_alns = (uint32_t)bAlns.size(); res.alns = bAlns.data();
+        res.n_edits = (uint32_t)bEdits.size(); res.edits = bEdits.data(); res.n_pairs = (uint32_t)(bPairs.size() / 2); res.pairs = bPairs.data();
+        char* txt = NULL; size_t len = 0;
+        const unsigned nth = getenv("HT2_THREADS") ? (unsigned)atoi(getenv("HT2_THREADS")) : 1;
+        auto t0 = std::chrono::steady_clock::now();
+        if (!ht2_format_batch(*img, P, &rb, names.c_str(), &res, &txt, &len, nth)) { fprintf(stderr, "ht2_format_batch failed\n"); return 1; }
+        finishNs += (std::chrono::steady_clock::now() - t0).count();
+        sam.append(txt, len); free(txt);
     }
     FILE* fo = fopen(outPath, "wb");
     fwrite(sam.data(), 1, sam.size(), fo);

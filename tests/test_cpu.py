@@ -99,6 +99,35 @@ def test_host_state_machine_option_matrix(hostsim_bin, tmp_path):
         assert got == c["md5"], c
 
 
+def test_batch_sam_back_end_matches_golden_and_is_thread_invariant(hostsim_bin, tmp_path):
+    """ht2_format_batch -- the body of ht2gpu_format_sam: C-ABI result batch -> SAM on host threads --
+    fed with the host state machine's results: golden SAM on the tiny fixtures, and the same text for 1
+    and 7 threads on a batch large enough (> 4096 units) to be split."""
+    env = dict(os.environ, HT2_VIA_BATCH="1")
+    for idx, args, gold in (("tiny", ["tiny_pe_1.fa", "tiny_pe_2.fa"], "tiny_pe.sam"),
+                            ("tiny_snp", ["tiny_alt_1.fa", "tiny_alt_2.fa"], "tiny_snp_alt_pe.sam"),
+                            ("tiny", ["tiny_se.fq"], "tiny_se_fq.sam")):
+        out = str(tmp_path / "o.sam")
+        subprocess.run([hostsim_bin, idx, args[0], out] + args[1:], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL, env=env)
+        assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), gold
+    big = str(tmp_path / "big.fa")
+    recs = open(os.path.join(GOLDEN, "tiny_se.fa")).read().split(">")[1:]
+    with open(big, "w") as f:
+        for rep in range(7):
+            for r in recs:
+                name, rest = r.split("\n", 1)
+                f.write(">%s_%d\n%s" % (name, rep, rest))
+    outs = []
+    for threads, via in (("1", "1"), ("7", "1"), ("1", None)):
+        out = str(tmp_path / ("big_%s_%s.sam" % (threads, via)))
+        e = dict(os.environ, HT2_THREADS=threads)
+        if via:
+            e["HT2_VIA_BATCH"] = via
+        subprocess.run([hostsim_bin, "tiny", big, out], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL, env=e)
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] == outs[2] and outs[0].count(b"\n") > 4900
+
+
 def test_abi_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))
