@@ -61,6 +61,7 @@
 #define HT2_ERR_GRAPH   512u
 #define HT2_ERR_DEPTH  1024u
 #define HT2_ERR_OUTPUT 2048u
+#define HT2_ERR_SPLICE 8192u   /* spliced mode (test build only): a spliced join was needed; that branch is not built yet */
 #define HT2_ERR_SW     4096u   /* --bowtie2-dp scratch missing / rectangle wider than the scratch */
 
 enum { HT2_EDIT_READ_GAP = 1, HT2_EDIT_REF_GAP, HT2_EDIT_MM, HT2_EDIT_SNP, HT2_EDIT_SPL };
@@ -73,7 +74,15 @@ struct Ht2Edit {          // edit.h:41-330
     uint8_t  type;
     uint8_t  pad;
     uint32_t snpID;
+#ifdef HT2_ENABLE_SPLICED /* spliced alignment, host test build only for now */
+    uint32_t splLen;      // EDIT_TYPE_SPL: intron length
+    uint8_t  splDir;      // HT2_SPL_*
+    uint8_t  knownSpl;
+    uint8_t  pad2[2];
+    int64_t  donor_seq, acceptor_seq;
+#endif
 };
+enum { HT2_SPL_UNKNOWN = 1, HT2_SPL_FW, HT2_SPL_RC, HT2_SPL_SEMI_FW, HT2_SPL_SEMI_RC };   // splice_site.h:37-43
 
 struct Ht2Hit {           // GenomeHit, hi_aligner.h:431-1369
     uint32_t fw;
@@ -82,6 +91,9 @@ struct Ht2Hit {           // GenomeHit, hi_aligner.h:431-1369
     int64_t  score;
     uint32_t hitcount;
     uint32_t nedits;
+#ifdef HT2_ENABLE_SPLICED
+    double   splicescore;
+#endif
     Ht2Edit  edits[HT2_MAX_EDITS];
 };
 
@@ -126,6 +138,11 @@ struct Ht2Res {
     uint32_t trim5p, trim3p;  // 5'/3' soft trimming in read orientation
     uint32_t rfextent;        // # reference chars covered
     uint32_t nedits;
+#ifdef HT2_ENABLE_SPLICED
+    double   splicescore;     // AlnScore::splicescore_
+    uint32_t spliced;         // GenomeHit::spliced().first (also "near splice sites")
+    uint32_t knownTranscripts;
+#endif
     Ht2Edit  edits[HT2_MAX_EDITS]; // AlnRes::ned(): 5'->3', relative to trim5p
 };
 
@@ -222,6 +239,9 @@ struct Ht2Work {
     uint32_t    nPairs;
     // AlnSinkWrap best-score tracking (aln_sink.h:2600-2655)
     int64_t     bestPair, best2Pair, bestUnp[2], best2Unp[2];
+#ifdef HT2_ENABLE_SPLICED
+    uint32_t    bestSplicedUnp[2];          // # splice edits of the best unpaired alignment (aln_sink.h:2610-2640)
+#endif
     // ReportingState (aln_sink.cpp:33-340), reduced to what the path reads back
     uint32_t    nconcord, nunpair[2];
     uint32_t    doneConcord, doneUnpair[2], stDone;
@@ -338,6 +358,89 @@ HT2_HD uint32_t ht2_v2_max3(uint32_t a, uint32_t b, uint32_t c) {
 }
 HT2_HD uint32_t ht2_v2_splat(int v) { return (uint32_t)(uint16_t)v * 0x00010001u; }
 
+#ifdef HT2_ENABLE_SPLICED
+#include <math.h>
+// ------------------------------------------------------------------------
+// Spliced alignment (host test build only for now).
+// Splice-site probability model (splice_site.cpp:30-111, 788-850, the model compiled in by default):
+// position weight matrices for the donor (3 exonic + 6 intronic bases, Yeo & Burge 2004) and the acceptor
+// (14 intronic + 1 exonic bases, Solovyev), turned into exp(-sum log(p / background)) tables exactly
+// like init_junction_prob (float logf / expf: bit-identical to the reference's tables, checked against
+// a dump of the compiled reference).
+// ------------------------------------------------------------------------
+struct Ht2SplTables { float donor[1 << 18], acc1[1 << 14], acc2[1 << 16]; };
+inline const Ht2SplTables& ht2_spl_tables() {
+    static Ht2SplTables* T = NULL;
+    if (T) return *T;
+    static const float bg[4] = {0.27f, 0.23f, 0.23f, 0.27f};
+    static const float donorP[4][9] = {
+        {0.340f, 0.604f, 0.092f, 0.001f, 0.001f, 0.526f, 0.713f, 0.071f, 0.160f},
+        {0.363f, 0.129f, 0.033f, 0.001f, 0.001f, 0.028f, 0.076f, 0.055f, 0.165f},
+        {0.183f, 0.125f, 0.803f, 1.000f, 0.001f, 0.419f, 0.118f, 0.814f, 0.209f},
+        {0.114f, 0.142f, 0.073f, 0.001f, 1.000f, 0.025f, 0.093f, 0.059f, 0.462f}};
+    static const float accP[4][15] = {
+        {0.090f, 0.084f, 0.075f, 0.068f, 0.076f, 0.080f, 0.097f, 0.092f, 0.076f, 0.078f, 0.237f, 0.042f, 1.000f, 0.001f, 0.239f},
+        {0.310f, 0.310f, 0.307f, 0.293f, 0.326f, 0.330f, 0.373f, 0.385f, 0.410f, 0.352f, 0.309f, 0.708f, 0.001f, 0.001f, 0.138f},
+        {0.125f, 0.115f, 0.106f, 0.104f, 0.110f, 0.113f, 0.113f, 0.085f, 0.066f, 0.064f, 0.212f, 0.003f, 0.001f, 1.000f, 0.520f},
+        {0.463f, 0.440f, 0.470f, 0.494f, 0.471f, 0.463f, 0.408f, 0.429f, 0.445f, 0.504f, 0.240f, 0.246f, 0.001f, 0.001f, 0.104f}};
+    Ht2SplTables* t = new Ht2SplTables();
+    float d[4][9], a[4][15];
+    for (int i = 0; i < 9; i++) for (int j = 0; j < 4; j++) d[j][i] = logf(donorP[j][i] / bg[j]);
+    for (int i = 0; i < 15; i++) for (int j = 0; j < 4; j++) a[j][i] = logf(accP[j][i] / bg[j]);
+    for (uint32_t i = 0; i < (1u << 18); i++) { float sum = 0.0f; for (int j = 0; j < 9; j++) sum += d[(i >> (j << 1)) & 3][9 - j - 1]; t->donor[i] = expf(-sum); }
+    for (uint32_t i = 0; i < (1u << 14); i++) { float sum = 0.0f; for (int j = 0; j < 7; j++) sum += a[(i >> (j << 1)) & 3][7 - j - 1]; t->acc1[i] = expf(-sum); }
+    for (uint32_t i = 0; i < (1u << 16); i++) { float sum = 0.0f; for (int j = 0; j < 8; j++) sum += a[(i >> (j << 1)) & 3][15 - j - 1]; t->acc2[i] = expf(-sum); }
+    T = t;
+    return *T;
+}
+// SpliceSiteDB::probscore (splice_site.cpp:832-850)
+inline float ht2_spl_probscore(int64_t donor_seq, int64_t acceptor_seq) {
+    const Ht2SplTables& T = ht2_spl_tables();
+    float probscore = T.donor[donor_seq & 0x3ffff];
+    probscore *= T.acc1[(acceptor_seq >> 16) & 0x3fff];
+    probscore *= T.acc2[acceptor_seq % (1 << 16)];
+    probscore = (float)(1.0 / (1.0 + probscore));
+    return probscore;
+}
+// MaxIntronLen / intronLen_prob (hi_aligner.h:48-89)
+inline uint32_t ht2_max_intron_len(uint32_t anchor, uint32_t minAnchorLen) {
+    uint32_t intronLen = 0;
+    if (anchor >= minAnchorLen) { if (anchor < 2) anchor = 2; uint32_t shift = (anchor << 1) - 4; shift = shift < 13 ? 13 : shift; shift = shift > 30 ? 30 : shift; intronLen = 1u << shift; }
+    return intronLen;
+}
+inline uint32_t ht2_max_intron_len_noncan(uint32_t anchor, uint32_t minAnchorLenNoncan) {
+    uint32_t intronLen = 0;
+    if (anchor >= minAnchorLenNoncan) { if (anchor < 5) anchor = 5; uint32_t shift = (anchor << 1) - 10; shift = shift > 30 ? 30 : shift; intronLen = 1u << shift; }
+    return intronLen;
+}
+inline float ht2_intron_len_prob(uint32_t anchor, uint32_t intronLen, uint32_t maxIntronLen) {
+    uint32_t expected = maxIntronLen;
+    if (anchor < 14) expected = 1u << ((anchor << 1) + 4);
+    if (expected > maxIntronLen) expected = maxIntronLen;
+    float result = ((float)intronLen) / ((float)expected);
+    if (result > 1.0f) result = 1.0f;
+    return result;
+}
+inline float ht2_intron_len_prob_noncan(uint32_t anchor, uint32_t intronLen, uint32_t maxIntronLen) {
+    uint32_t expected = maxIntronLen;
+    if (anchor < 16) expected = 1u << (anchor << 1);
+    if (expected > maxIntronLen) expected = maxIntronLen;
+    float result = ((float)intronLen) / ((float)expected);
+    if (result > 1.0f) result = 1.0f;
+    return result;
+}
+// Scoring::canSpl / noncanSpl (scoring.h:473-487) with the default penalty functions
+// (--pen-cansplice 0, --pen-noncansplice 12, --pen-canintronlen / --pen-noncanintronlen G,-8,1; hisat2.cpp:493-497)
+#define HT2_PEN_NONCANSPLICE 12
+#define HT2_PEN_CONFLICTSPLICE 1000000
+inline int64_t ht2_intron_pen(int intronlen) {
+    int pen = 0;
+    if (intronlen > 0) { double v = -8.0 + 1.0 * log((double)intronlen); pen = (int)v; }
+    if (pen < 0) pen = 0;
+    return pen;
+}
+#endif // HT2_ENABLE_SPLICED
+
 // ------------------------------------------------------------------------
 // The aligner
 // ------------------------------------------------------------------------
@@ -380,6 +483,9 @@ struct Ht2AlignerT {
         d.fw = s.fw; d.rdoff = s.rdoff; d.len = s.len; d.trim5 = s.trim5; d.trim3 = s.trim3;
         d.tidx = s.tidx; d.toff = s.toff; d.joinedOff = s.joinedOff; d.score = s.score;
         d.hitcount = 1; // GenomeHit::init resets _hitcount (hi_aligner.h:569)
+#ifdef HT2_ENABLE_SPLICED
+        d.splicescore = s.splicescore;
+#endif
         d.nedits = s.nedits;
         for (uint32_t i = 0; i < s.nedits; i++) d.edits[i] = s.edits[i];
     }
@@ -387,9 +493,16 @@ struct Ht2AlignerT {
                                uint32_t tidx, uint32_t toff, uint32_t joinedOff) {
         h.fw = fw ? 1 : 0; h.rdoff = rdoff; h.len = len; h.trim5 = trim5; h.trim3 = trim3;
         h.tidx = tidx; h.toff = toff; h.joinedOff = joinedOff; h.score = 0; h.hitcount = 1; h.nedits = 0;
+#ifdef HT2_ENABLE_SPLICED
+        h.splicescore = 0.0;
+#endif
     }
     HT2_HD static Ht2Edit mkEdit(uint32_t pos, uint8_t chr, uint8_t qchr, uint8_t type) {
-        Ht2Edit e; e.pos = pos; e.chr = chr; e.qchr = qchr; e.type = type; e.pad = 0; e.snpID = HT2_IDX_MAX32; return e;
+        Ht2Edit e; e.pos = pos; e.chr = chr; e.qchr = qchr; e.type = type; e.pad = 0; e.snpID = HT2_IDX_MAX32;
+#ifdef HT2_ENABLE_SPLICED
+        e.splLen = 0; e.splDir = HT2_SPL_UNKNOWN; e.knownSpl = 0; e.pad2[0] = e.pad2[1] = 0; e.donor_seq = e.acceptor_seq = 0;
+#endif
+        return e;
     }
     HT2_HD bool pushEdit(Ht2Hit& h, const Ht2Edit& e) {
         if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
@@ -403,6 +516,9 @@ struct Ht2AlignerT {
     HT2_HD static bool editEq(const Ht2Edit& a, const Ht2Edit& b) { // Edit::operator== (edit.h)
         if (a.type != b.type) return false;
         if (a.pos != b.pos) return false;
+#ifdef HT2_ENABLE_SPLICED
+        if (a.type == HT2_EDIT_SPL) return a.splLen == b.splLen && a.splDir == b.splDir;
+#endif
         return a.chr == b.chr && a.qchr == b.qchr;
     }
     HT2_HD static bool isGapOrSnp(const Ht2Edit& e) {
@@ -454,6 +570,9 @@ struct Ht2AlignerT {
         for (uint32_t i = 0; i < h.nedits; i++) {
             if (h.edits[i].type == HT2_EDIT_READ_GAP) toff++;
             else if (h.edits[i].type == HT2_EDIT_REF_GAP) toff--;
+#ifdef HT2_ENABLE_SPLICED
+            else if (h.edits[i].type == HT2_EDIT_SPL) toff += h.edits[i].splLen;
+#endif
         }
         return toff;
     }
@@ -478,15 +597,24 @@ struct Ht2AlignerT {
         }
     }
 
-    // GenomeHit::calculateScore (hi_aligner.h:3711-3891), no splice edits.
+    // GenomeHit::calculateScore (hi_aligner.h:3711-3891); splice edits in the HT2_ENABLE_SPLICED build.
     HT2_NI int64_t calculateScore(Ht2Hit& h, uint32_t rdi) const {
         int64_t score = 0;
         const uint8_t* qual = W->rd[rdi].qual[h.fw ? 0 : 1];
+#ifdef HT2_ENABLE_SPLICED
+        double splicescore = 0; uint32_t numsplices = 0, mm = 0;
+        bool conflict_splicesites = false; uint8_t whichsense = HT2_SPL_UNKNOWN;
+        const uint32_t rdlenS = W->rd[rdi].len;
+#endif
         for (uint32_t i = 0; i < h.nedits; i++) {
             const Ht2Edit& e = h.edits[i];
             if (e.type == HT2_EDIT_MM) {
-                if (e.snpID == HT2_IDX_MAX32)
+                if (e.snpID == HT2_IDX_MAX32) {
                     score += ht2_score(*P, ht2_asc2code(e.qchr), ht2_asc2mask(e.chr), (int)qual[h.rdoff + e.pos] - 33);
+#ifdef HT2_ENABLE_SPLICED
+                    mm++;
+#endif
+                }
             } else if (e.type == HT2_EDIT_READ_GAP) {
                 bool open = true;
                 if (i > 0 && h.edits[i - 1].type == HT2_EDIT_READ_GAP && h.edits[i - 1].pos == e.pos) open = false;
@@ -496,10 +624,73 @@ struct Ht2AlignerT {
                 if (i > 0 && h.edits[i - 1].type == HT2_EDIT_REF_GAP && h.edits[i - 1].pos + 1 == e.pos) open = false;
                 if (e.snpID == HT2_IDX_MAX32) score -= open ? (P->rfGapConst + P->rfGapLinear) : P->rfGapLinear;
             }
+#ifdef HT2_ENABLE_SPLICED
+            else if (e.type == HT2_EDIT_SPL) {   // hi_aligner.h:3745-3838
+                const bool canon = (e.splDir == HT2_SPL_FW || e.splDir == HT2_SPL_RC);
+                if (!e.knownSpl) {
+                    int left_anchor_len = (int)(h.rdoff + e.pos);
+                    int right_anchor_len = (int)rdlenS - left_anchor_len;
+                    uint32_t mm2 = 0;
+                    for (uint32_t j = i + 1; j < h.nedits; j++) {
+                        const uint8_t t2 = h.edits[j].type;
+                        if (t2 == HT2_EDIT_MM || t2 == HT2_EDIT_READ_GAP || t2 == HT2_EDIT_REF_GAP) mm2++;
+                    }
+                    left_anchor_len -= (int)(mm * 2);
+                    right_anchor_len -= (int)(mm2 * 2);
+                    int shorter_anchor_len = left_anchor_len < right_anchor_len ? left_anchor_len : right_anchor_len;
+                    if (shorter_anchor_len <= 0) shorter_anchor_len = 1;
+                    const uint32_t intronLen_thresh = canon ? ht2_max_intron_len((uint32_t)shorter_anchor_len, P->minAnchorLen)
+                                                            : ht2_max_intron_len_noncan((uint32_t)shorter_anchor_len, P->minAnchorLenNoncan);
+                    if (intronLen_thresh < P->maxIntronLen) {
+                        if (e.splLen > intronLen_thresh) score += (int64_t)INT32_MIN;
+                        if (canon) {
+                            const float probscore = ht2_spl_probscore(e.donor_seq, e.acceptor_seq);
+                            float thresh = 0.8f;
+                            if (e.splLen >> 16) thresh = 0.99f;
+                            else if (e.splLen >> 15) thresh = 0.97f;
+                            else if (e.splLen >> 14) thresh = 0.94f;
+                            else if (e.splLen >> 13) thresh = 0.91f;
+                            else if (e.splLen >> 12) thresh = 0.88f;
+                            if (probscore < thresh) score += (int64_t)INT32_MIN;
+                        }
+                        if (shorter_anchor_len == left_anchor_len) {
+                            if (h.trim5 > 0) score += (int64_t)INT32_MIN;
+                            for (int j = (int)i - 1; j >= 0; j--) {
+                                const uint8_t t2 = h.edits[j].type;
+                                if (t2 == HT2_EDIT_MM || t2 == HT2_EDIT_READ_GAP || t2 == HT2_EDIT_REF_GAP) score += (int64_t)INT32_MIN;
+                            }
+                        } else {
+                            if (h.trim3 > 0) score += (int64_t)INT32_MIN;
+                            for (uint32_t j = i + 1; j < h.nedits; j++) {
+                                const uint8_t t2 = h.edits[j].type;
+                                if (t2 == HT2_EDIT_MM || t2 == HT2_EDIT_READ_GAP || t2 == HT2_EDIT_REF_GAP) score += (int64_t)INT32_MIN;
+                            }
+                        }
+                    }
+                    if (e.snpID == HT2_IDX_MAX32) {
+                        if (canon) score -= ht2_intron_pen((int)e.splLen) + P->canSplPen;
+                        else score -= ht2_intron_pen((int)e.splLen) + HT2_PEN_NONCANSPLICE;
+                    }
+                    if (shorter_anchor_len <= 15) { numsplices += 1; splicescore += (double)e.splLen; }
+                }
+                if (!conflict_splicesites) {
+                    if (whichsense == HT2_SPL_UNKNOWN) whichsense = e.splDir;
+                    else if (e.splDir != HT2_SPL_UNKNOWN) {
+                        if (e.splDir == HT2_SPL_FW || e.splDir == HT2_SPL_SEMI_FW) { if (whichsense != HT2_SPL_FW && whichsense != HT2_SPL_SEMI_FW) conflict_splicesites = true; }
+                        if (e.splDir == HT2_SPL_RC || e.splDir == HT2_SPL_SEMI_RC) { if (whichsense != HT2_SPL_RC && whichsense != HT2_SPL_SEMI_RC) conflict_splicesites = true; }
+                    }
+                }
+            }
+#endif
         }
         // soft-clip penalty indexes qual[i], not the clipped position (hi_aligner.h:3872-3878)
         for (uint32_t i = 0; i < h.trim5; i++) score -= ht2_scpen(*P, qual[i]);
         for (uint32_t i = 0; i < h.trim3; i++) score -= ht2_scpen(*P, qual[i]);
+#ifdef HT2_ENABLE_SPLICED
+        if (conflict_splicesites) score -= HT2_PEN_CONFLICTSPLICE;
+        if (numsplices > 1) splicescore /= (double)numsplices;
+        h.splicescore = splicescore;
+#endif
         h.score = score;
         return score;
     }
@@ -1115,8 +1306,10 @@ struct Ht2AlignerT {
                 else del = true;
             } else ins = true;
         }
-        if (spliced) return false; // spliced joins are outside this build's scope
-        if (!ins && !del && this_rdoff + this_len == other_rdoff) {
+#ifndef HT2_ENABLE_SPLICED
+        if (spliced) { W->err |= HT2_ERR_SPLICE; return false; } // spliced joins exist in the host test build only; the C ABI refuses spliced mode
+#endif
+        if (!spliced && !ins && !del && this_rdoff + this_len == other_rdoff) {
             uint32_t addoff = o.rdoff - a.rdoff;
             for (uint32_t i = 0; i < o.nedits; i++) {
                 if (!pushEdit(a, o.edits[i])) return false;
@@ -1131,12 +1324,19 @@ struct Ht2AlignerT {
         const uint32_t rdlen = W->rd[rdi].len;
         int64_t remainsc = minsc_ - (a.score - this_score) - (o.score - other_score);
         if (remainsc > 0) remainsc = 0;
-        int read_gaps = ht2_max_gaps(remainsc + P->canSplPen, P->rdGapConst + P->rdGapLinear, P->rdGapLinear);
-        int ref_gaps = ht2_max_gaps(remainsc + P->canSplPen, P->rfGapConst + P->rfGapLinear, P->rfGapLinear);
+        int read_gaps = 0, ref_gaps = 0;
+        if (!spliced) {
+            read_gaps = ht2_max_gaps(remainsc + P->canSplPen, P->rdGapConst + P->rdGapLinear, P->rdGapLinear);
+            ref_gaps = ht2_max_gaps(remainsc + P->canSplPen, P->rfGapConst + P->rfGapLinear, P->rfGapLinear);
+        }
         (void)rdlen;
         if (ins) { if (refdif + (uint32_t)ref_gaps < rddif) return false; }
         else if (del) { if (rddif + (uint32_t)read_gaps < refdif) return false; }
         int this_ref_ext = read_gaps;
+#ifdef HT2_ENABLE_SPLICED
+        const int intronic_len = 14;   // max(donor_intronic_len 6, acceptor_intronic_len 14), splice_site.h:76
+        if (spliced) this_ref_ext += intronic_len;
+#endif
         if (this_toff + len > reflen) return false;
         if (this_toff + len + (uint32_t)this_ref_ext > reflen) this_ref_ext = (int)(reflen - (this_toff + len));
         if (len + (uint32_t)this_ref_ext > HT2_REFBUF || len > HT2_MAX_RDLEN) { W->err |= HT2_ERR_RDLEN; return false; }
@@ -1144,6 +1344,89 @@ struct Ht2AlignerT {
         const uint8_t* refbuf2 = NULL;
         uint32_t maxscorei = HT2_IDX_MAX32;
         int64_t maxscore = HT2_MIN_I64;
+#ifdef HT2_ENABLE_SPLICED
+        uint32_t maxspldir = HT2_SPL_UNKNOWN; float maxsplscore = 0.0f; int64_t donor_seq = 0, acceptor_seq = 0;
+        if (spliced) {   // hi_aligner.h:1576-1758, 1796-1816
+            int other_ref_ext = read_gaps + intronic_len;
+            { int lim = (int)(other_toff + other_len - len); if (lim < other_ref_ext) other_ref_ext = lim; }
+            if ((int)len + other_ref_ext > (int)HT2_REFBUF || other_ref_ext < 0) { W->err |= HT2_ERR_RDLEN; return false; }
+            refbuf2 = getStretch(W->refbuf2, o.tidx, other_toff + other_len - len - (uint32_t)other_ref_ext, len + (uint32_t)other_ref_ext)
+                      + other_ref_ext;
+            int64_t* ts = W->tscores; int64_t* ts2 = W->tscores2;
+            const int GT = 0x23, AG = 0x02, GTrc = 0x01, AGrc = 0x13, GC = 0x21, GCrc = 0x21, AT = 0x03, AC = 0x01, ATrc = 0x03, ACrc = 0x20;
+            const int donor_exonic_len = 3, donor_intronic_len = 6, acceptor_intronic_len = 14, acceptor_exonic_len = 1;
+            int i;
+            for (i = 0; i < (int)len; i++) {
+                int rdc = seq[this_rdoff + i], rfc = refbuf[i];
+                ts[i] = i > 0 ? ts[i - 1] : 0;
+                if (rdc != rfc) ts[i] += ht2_score(*P, rdc, 1 << rfc, (int)qual[this_rdoff + i] - 33);
+                if (ts[i] < remainsc) break;
+            }
+            int i_limit = i < (int)len ? i : (int)len;
+            int i2;
+            for (i2 = (int)len - 1; i2 >= 0; i2--) {
+                int rdc = seq[this_rdoff + i2], rfc = refbuf2[i2];
+                ts2[i2] = ((uint32_t)(i2 + 1) < len) ? ts2[i2 + 1] : 0;
+                if (rdc != rfc) ts2[i2] += ht2_score(*P, rdc, 1 << rfc, (int)qual[this_rdoff + i2] - 33);
+                if (ts2[i2] < remainsc) break;
+            }
+            int i2_limit = i2 > 0 ? i2 : 0;
+            for (i = i2_limit, i2 = i2_limit + 1; i < i_limit && i2 < (int)len; i++, i2++) {
+                int64_t tempscore = ts[i] + ts2[i2];
+                int donor = 0xff, acceptor = 0xff;   // (char)0xff in the reference: compares unequal to every motif
+                if ((uint32_t)(i + 2) < len + (uint32_t)this_ref_ext) donor = (int)(int8_t)(uint8_t)(((uint8_t)refbuf[i + 1] << 4) | (uint8_t)refbuf[i + 2]);
+                if (i2 - 2 >= -other_ref_ext) acceptor = (int)(int8_t)(uint8_t)(((uint8_t)refbuf2[i2 - 2] << 4) | (uint8_t)refbuf2[i2 - 1]);
+                bool canonical = false, semi_canonical = false;
+                uint32_t spldir = HT2_SPL_UNKNOWN;
+                if (donor == GT && acceptor == AG) { spldir = HT2_SPL_FW; canonical = true; }
+                else if (donor == AGrc && acceptor == GTrc) { spldir = HT2_SPL_RC; canonical = true; }
+                else if ((donor == GC && acceptor == AG) || (donor == AT && acceptor == AC)) { spldir = HT2_SPL_SEMI_FW; semi_canonical = true; }
+                else if ((donor == AGrc && acceptor == GCrc) || (donor == ACrc && acceptor == ATrc)) { spldir = HT2_SPL_SEMI_RC; semi_canonical = true; }
+                tempscore -= (canonical ? (int64_t)P->canSplPen : (int64_t)HT2_PEN_NONCANSPLICE);
+                int64_t temp_donor_seq = 0, temp_acceptor_seq = 0;
+                float splscore = 0.0f;
+                if (canonical) {
+                    if (spldir == HT2_SPL_FW) {
+                        if (i + 1 >= donor_exonic_len && (int)(len + (uint32_t)this_ref_ext) > i + donor_intronic_len &&
+                            i2 + other_ref_ext >= acceptor_intronic_len && (int)len > i2 + acceptor_exonic_len - 1) {
+                            int from = i + 1 - donor_exonic_len, to = i + donor_intronic_len;
+                            for (int j = from; j <= to; j++) { int base = refbuf[j]; if (base > 3) base = 0; temp_donor_seq = temp_donor_seq << 2 | base; }
+                            from = i2 - acceptor_intronic_len; to = i2 + acceptor_exonic_len - 1;
+                            for (int j = from; j <= to; j++) { int base = refbuf2[j]; if (base > 3) base = 0; temp_acceptor_seq = temp_acceptor_seq << 2 | base; }
+                        }
+                    } else {
+                        if (i + 1 >= acceptor_exonic_len && (int)(len + (uint32_t)this_ref_ext) > i + acceptor_intronic_len &&
+                            i2 + other_ref_ext >= donor_intronic_len && (int)len > i2 + donor_exonic_len - 1) {
+                            int from = i + 1 - acceptor_exonic_len, to = i + acceptor_intronic_len;
+                            for (int j = to; j >= from; j--) { int base = refbuf[j]; if (base > 3) base = 0; temp_acceptor_seq = temp_acceptor_seq << 2 | (base ^ 0x3); }
+                            from = i2 - donor_intronic_len; to = i2 + donor_exonic_len - 1;
+                            for (int j = to; j >= from; j--) { int base = refbuf2[j]; if (base > 3) base = 0; temp_donor_seq = temp_donor_seq << 2 | (base ^ 0x3); }
+                        }
+                    }
+                    splscore = ht2_spl_probscore(temp_donor_seq, temp_acceptor_seq);
+                }
+                const bool mu = (maxspldir == HT2_SPL_UNKNOWN), su = (spldir == HT2_SPL_UNKNOWN);
+                if ((mu && su && maxscore < tempscore) || (mu && su && maxscore == tempscore && semi_canonical) ||
+                    (!mu && !su && (maxscore < tempscore || (maxscore == tempscore && maxsplscore < splscore))) || (mu && !su)) {
+                    maxscore = tempscore; maxscorei = (uint32_t)i; maxspldir = spldir; maxsplscore = splscore;
+                    if (maxspldir != HT2_SPL_UNKNOWN) { donor_seq = temp_donor_seq; acceptor_seq = temp_acceptor_seq; }
+                    else { donor_seq = 0; acceptor_seq = 0; }
+                }
+            }
+            if (maxscore == HT2_MIN_I64) return false;
+            {
+                uint32_t shorter_anchor_len = maxscorei + 1 < len - maxscorei - 1 ? maxscorei + 1 : len - maxscorei - 1;
+                if (maxspldir == HT2_SPL_SEMI_FW || maxspldir == HT2_SPL_SEMI_RC || maxspldir == HT2_SPL_UNKNOWN) {
+                    if (shorter_anchor_len < P->minAnchorLenNoncan) {
+                        if (ht2_intron_len_prob_noncan(shorter_anchor_len, other_toff - this_toff, P->maxIntronLen) > 0.01f) return false;
+                    }
+                } else if (shorter_anchor_len < P->minAnchorLen) {
+                    if (ht2_intron_len_prob(shorter_anchor_len, other_toff - this_toff, P->maxIntronLen) > 0.01f) return false;
+                }
+            }
+            if (maxscore < remainsc) return false;
+        }
+#endif
         if (ins || del) {
             int other_ref_ext = read_gaps;
             int lim = (int)(other_toff + other_len - len);
@@ -1189,6 +1472,24 @@ struct Ht2AlignerT {
             }
             if (clear) a.nedits = 0;
         }
+#ifdef HT2_ENABLE_SPLICED
+        if (spliced) {   // hi_aligner.h:1832-1880 (splice_gap_off is always 0 there)
+            const uint32_t addoff = this_rdoff - a.rdoff;
+            for (uint32_t i = 0; i < len; i++) {
+                int rdc = seq[this_rdoff + i];
+                int rfc = (i <= maxscorei ? refbuf[i] : refbuf2[i]);
+                if (rdc != rfc) { if (!pushEdit(a, mkEdit(i + addoff, ht2_code2asc(rfc), ht2_code2asc(rdc), HT2_EDIT_MM))) return false; }
+                if (i == maxscorei) {
+                    uint32_t left = this_toff + i + 1;
+                    uint32_t right = other_toff + other_len - (len - i - 1);
+                    Ht2Edit e = mkEdit(i + 1 + addoff, 'A', 'A', HT2_EDIT_SPL);
+                    e.splLen = right - left; e.splDir = (uint8_t)maxspldir; e.knownSpl = 0;
+                    e.donor_seq = donor_seq; e.acceptor_seq = acceptor_seq;
+                    if (!pushEdit(a, e)) return false;
+                }
+            }
+        } else
+#endif
         {
             uint32_t ins_len = 0;
             for (uint32_t i = 0; i < len; i++) {
@@ -1256,6 +1557,9 @@ struct Ht2AlignerT {
         // AlnSinkWrap::nextRead starts these at numeric_limits<THitInt>::min() (aln_sink.h:1896-1898)
         W->bestPair = W->best2Pair = HT2_MIN_I64;
         W->bestUnp[0] = W->best2Unp[0] = W->bestUnp[1] = W->best2Unp[1] = HT2_MIN_I64;
+#ifdef HT2_ENABLE_SPLICED
+        W->bestSplicedUnp[0] = W->bestSplicedUnp[1] = 0;
+#endif
         W->nconcord = 0; W->nunpair[0] = W->nunpair[1] = 0;
         // ReportingState::nextRead (aln_sink.cpp:33-66)
         if (paired_) {
@@ -1268,7 +1572,14 @@ struct Ht2AlignerT {
         W->stDone = 0;
         W->concordBest = HT2_MIN_SCORE;
     }
-    HT2_HD void reportUnpaired(uint32_t mate /*0 or 1 == rs1/rs2*/, int64_t score) {
+    HT2_HD uint32_t bestSpliced(uint32_t mate) const {
+#ifdef HT2_ENABLE_SPLICED
+        return W->bestSplicedUnp[mate];
+#else
+        (void)mate; return 0;   // no splice edits without spliced alignment
+#endif
+    }
+    HT2_HD void reportUnpaired(uint32_t mate /*0 or 1 == rs1/rs2*/, int64_t score, uint32_t numSpliced = 0) {
         // ReportingState::foundUnpaired (aln_sink.cpp:96-132), -k mode (mhits unset)
         W->nunpair[mate]++;
         if (!W->doneUnpair[mate]) {
@@ -1277,8 +1588,14 @@ struct Ht2AlignerT {
                 if (W->doneUnpair[0] && W->doneUnpair[1]) { /* updateDone */ }
             }
         }
-        if (score > W->bestUnp[mate]) { W->best2Unp[mate] = W->bestUnp[mate]; W->bestUnp[mate] = score; }
+        if (score > W->bestUnp[mate]) {
+            W->best2Unp[mate] = W->bestUnp[mate]; W->bestUnp[mate] = score;
+#ifdef HT2_ENABLE_SPLICED
+            W->bestSplicedUnp[mate] = numSpliced;
+#endif
+        }
         else if (score > W->best2Unp[mate]) W->best2Unp[mate] = score;
+        (void)numSpliced;
     }
 
     // HI_Aligner::reportHit (hi_aligner.h:6064-6198), unpaired form.
@@ -1306,7 +1623,18 @@ struct Ht2AlignerT {
             else if (r.edits[i].type == HT2_EDIT_READ_GAP) rfextent++;
         }
         r.rfextent = rfextent;
-        reportUnpaired(slot, hit.score);
+#ifdef HT2_ENABLE_SPLICED
+        {   // GenomeHit::spliced() -> AlnScore(..., splicescore, knownTranscripts, nearSpliceSites, ...) (hi_aligner.h:6100-6145)
+            bool spl = false, known = true;
+            for (uint32_t i = 0; i < hit.nedits; i++) if (hit.edits[i].type == HT2_EDIT_SPL) { spl = true; known = known && hit.edits[i].knownSpl; }
+            r.spliced = spl ? 1 : 0; r.knownTranscripts = (spl && known) ? 1 : 0; r.splicescore = hit.splicescore;
+        }
+#endif
+        {
+            uint32_t nspl = 0;
+            for (uint32_t i = 0; i < hit.nedits; i++) if (hit.edits[i].type == HT2_EDIT_SPL) nspl++;
+            reportUnpaired(slot, hit.score, nspl);
+        }
         return true;
     }
 
@@ -1349,6 +1677,12 @@ struct Ht2AlignerT {
                 const Ht2SearchedEdit& e = ed[i]; const Ht2Edit& oe = hit.edits[i];
                 if (e.type == HT2_EDIT_READ_GAP) { if (oe.type != HT2_EDIT_READ_GAP) same = false; }
                 else if (e.type == HT2_EDIT_REF_GAP) { if (oe.type != HT2_EDIT_REF_GAP) same = false; }
+#ifdef HT2_ENABLE_SPLICED
+                else if (e.type == HT2_EDIT_SPL) {
+                    const uint32_t v = (oe.splLen & 0xfffffu) | ((uint32_t)oe.splDir << 20);
+                    if (oe.type != HT2_EDIT_SPL || e.pos != oe.pos || e.chr != (uint8_t)v || e.qchr != (uint8_t)(v >> 8) || e.pad != (uint8_t)(v >> 16)) same = false;
+                }
+#endif
                 else if (e.type != oe.type || e.pos != oe.pos || e.chr != oe.chr || e.qchr != oe.qchr) same = false;
             }
             if (same) return true;
@@ -1365,6 +1699,12 @@ struct Ht2AlignerT {
         Ht2SearchedEdit* ed = (Ht2SearchedEdit*)(W->searched + W->searchedTop + sizeof(Ht2SearchedRec));
         for (uint32_t i = 0; i < hit.nedits; i++) {
             ed[i].pos = hit.edits[i].pos; ed[i].type = hit.edits[i].type; ed[i].chr = hit.edits[i].chr; ed[i].qchr = hit.edits[i].qchr; ed[i].pad = 0;
+#ifdef HT2_ENABLE_SPLICED
+            if (hit.edits[i].type == HT2_EDIT_SPL) {   // Edit::operator== compares splLen and splDir of splice edits (edit.h:195-210)
+                const uint32_t v = (hit.edits[i].splLen & 0xfffffu) | ((uint32_t)hit.edits[i].splDir << 20);
+                ed[i].chr = (uint8_t)v; ed[i].qchr = (uint8_t)(v >> 8); ed[i].pad = (uint8_t)(v >> 16);
+            }
+#endif
         }
         W->searchedTop += need;
         W->nSearched[rdi]++;
@@ -1411,7 +1751,7 @@ struct Ht2AlignerT {
                 int64_t bestScore = W->bestUnp[rdi];
                 if (bestScore >= minsc[rdi]) {
                     uint32_t maxmm = (uint32_t)((-bestScore + P->mmpMax - 1) / P->mmpMax);
-                    if (numSearched > maxmm + 0 /*bestSplicedUnp*/ + 1) {
+                    if (numSearched > maxmm + bestSpliced(rdi) + 1) {
                         hit.done = 1;
                         if (paired) {
                             if (W->bestUnp[1 - rdi] >= minsc[1 - rdi] && W->nPairs > 0) return false;
@@ -1547,7 +1887,7 @@ struct Ht2AlignerT {
         if (bestScore < minsc[rdi]) bestScore = minsc[rdi];
         uint32_t maxmm = (uint32_t)((-bestScore + P->mmpMax - 1) / P->mmpMax);
         uint32_t numActualPartialSearch = hit.numPartialSearch - hit.numUniqueSearch;
-        if (!P->secondary && numActualPartialSearch > maxmm + 0 + 1) return true;
+        if (!P->secondary && numActualPartialSearch > maxmm + bestSpliced(rdi) + 1) return true;
         const uint32_t maxsize = P->khits > P->kseeds ? P->khits : P->kseeds;
         W->nGenomeHits = 0;
         uint32_t numHits = getAnchorHits(rdi, fw, maxsize);

@@ -278,10 +278,15 @@ int64_t hisat2Score(const Ht2Res& r)
     int64_t score = r.score;
     if (score > 0x7fffffffll) score = 0x7fffffffll;
     else if (score < -0x80000000ll) score = -0x80000000ll;
-    int64_t splicescore = 255;
+    int64_t splicescore = 255, transcript_score = 0;
+#ifdef HT2_ENABLE_SPLICED
+    splicescore = (int64_t)(r.splicescore / 100);     // TAlScore splicescore = splicescore_ / 100 (aligner_result.h:339)
+    if (splicescore > 255) splicescore = 0; else splicescore = 255 - splicescore;
+    transcript_score = r.knownTranscripts ? 2 : (r.spliced ? 1 : 0);
+#endif
     int64_t trim = (int64_t)r.trim5p + (int64_t)r.trim3p; // leftTrim+rightTrim (hit.trim5+hit.trim3)
     if (trim > 65535) trim = 0; else trim = 65535 - trim;
-    return (int64_t)((uint64_t)score << 32) | (splicescore << 16) | trim;
+    return (int64_t)((uint64_t)score << 32) | (transcript_score << 24) | (splicescore << 16) | trim;
 }
 
 struct ScoreKey { int64_t score; int64_t h2; bool valid; };
@@ -422,9 +427,10 @@ int mapqV2(const Ht2Params& P, const Summ& s, bool mate1, size_t rdlen, size_t o
 struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660-1000)
     std::string ref, rel, read;
     std::vector<bool> snp;
+    std::vector<uint32_t> skip;   // intron lengths of the 'N' columns, in order
     size_t trimLS, trimRS;
     void init(const std::vector<uint8_t>& s, const Ht2Edit* ed, size_t ned, size_t tLS, size_t tRS) {
-        ref.clear(); rel.clear(); read.clear(); snp.clear();
+        ref.clear(); rel.clear(); read.clear(); snp.clear(); skip.clear();
         trimLS = tLS; trimRS = tRS;
         size_t rdoff = tLS;
         for (size_t i = 0; i < ned; i++) {
@@ -443,6 +449,11 @@ struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660
             } else if (ed[i].type == HT2_EDIT_READ_GAP) {
                 ref.push_back((char)ed[i].chr); rel.push_back('D'); snp.push_back(isSnp); read.push_back('-');
             }
+#ifdef HT2_ENABLE_SPLICED
+            else if (ed[i].type == HT2_EDIT_SPL) {   // aligner_result.cpp:711-718
+                ref.push_back('N'); rel.push_back('N'); snp.push_back(false); read.push_back('N'); skip.push_back(ed[i].splLen);
+            }
+#endif
         }
         while (rdoff < s.size() - tRS) {
             int c = s[rdoff++];
@@ -474,17 +485,19 @@ struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660
     }
     void cigar(std::string& o) const {
         if (trimLS > 0) { appendInt(o, trimLS); o.push_back('S'); }
-        size_t ln = ref.size();
+        size_t ln = ref.size(), numSkips = 0;
         for (size_t i = 0; i < ln; i++) {
             char op = rel[i];
             if (op == 'X' || op == '=') op = 'M';
             size_t run = 1;
-            for (; i + run < ln; run++) {
-                char op2 = rel[i + run];
-                if (op2 == 'X' || op2 == '=') op2 = 'M';
-                if (op2 != op) break;
-            }
-            i += (run - 1);
+            if (op != 'N') {
+                for (; i + run < ln; run++) {
+                    char op2 = rel[i + run];
+                    if (op2 == 'X' || op2 == '=') op2 = 'M';
+                    if (op2 != op) break;
+                }
+                i += (run - 1);
+            } else run = skip[numSkips++];   // aligner_result.cpp:815-833
             appendInt(o, run); o.push_back(op);
         }
         if (trimRS > 0) { appendInt(o, trimRS); o.push_back('S'); }
@@ -498,7 +511,7 @@ struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660
                 size_t run = 1, ninserts = 0;
                 for (; i + run < ln; run++) {
                     if (rel[i + run] == '=') {}
-                    else if (rel[i + run] == 'I') ninserts++;
+                    else if (rel[i + run] == 'I' || rel[i + run] == 'N') ninserts++;   // insertions and introns do not count (aligner_result.cpp:862-879)
                     else break;
                 }
                 i += (run - 1);
@@ -581,13 +594,20 @@ struct MateFlags {
 // AlnRes::setFragmentLength (aligner_result.h:1631-1694) without splice sites
 static int64_t fragmentLength(const Ht2Res& me, const Ht2Res& o, bool meMate1)
 {
-    auto ext = [](const Ht2Res& r, int64_t& st, int64_t& en) {
+    // AlnRes::setFragmentLength (aligner_result.h:1631-1697) with an empty splice-site DB; st2/en2 are the
+    // extents shifted right by the alignment's own introns (getCoords, :1132-1147)
+    auto ext = [](const Ht2Res& r, int64_t& st, int64_t& en, int64_t& st2, int64_t& en2) {
         int64_t trim_st = r.fw ? r.trim5p : r.trim3p, trim_en = r.fw ? r.trim3p : r.trim5p;
+        int64_t introns = 0;
+#ifdef HT2_ENABLE_SPLICED
+        for (uint32_t e = 0; e < r.nedits; e++) if (r.edits[e].type == HT2_EDIT_SPL) introns += r.edits[e].splLen;
+#endif
         st = (int64_t)r.toff - trim_st;
         en = (int64_t)r.toff + r.rfextent - 1 + trim_en;
+        st2 = st + introns; en2 = en + introns;
     };
-    int64_t st, en, ost, oen;
-    ext(me, st, en); ext(o, ost, oen);
+    int64_t st, en, st2, en2, ost, oen, ost2, oen2;
+    ext(me, st, en, st2, en2); ext(o, ost, oen, ost2, oen2);
     bool imUpstream;
     if (st < ost) imUpstream = true;
     else if (st == ost) {
@@ -595,7 +615,9 @@ static int64_t fragmentLength(const Ht2Res& me, const Ht2Res& o, bool meMate1)
         else if (me.fw && !o.fw) imUpstream = true;
         else imUpstream = false;
     } else imUpstream = false;
-    int64_t up = std::min(st, ost), dn = std::max(en, oen);
+    int64_t up, dn;
+    if (imUpstream) { up = std::min(st2, ost); dn = std::max(en2, oen); }
+    else { up = std::min(st, ost2); dn = std::max(en, oen2); }
     int64_t fraglen = 1 + dn - up;
     if (!imUpstream) fraglen = -fraglen;
     return fraglen;
@@ -721,6 +743,22 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, 
     if (summ.paired && haveOscore && rso) { o += "\tYS:i:"; appendInt(o, rso->score); }
     o += "\tYT:Z:"; o += ytz;
     appendYF(o, f);
+#ifdef HT2_ENABLE_SPLICED
+    {   // XS:A: AlnRes::spliced_whichsense_transcript (aligner_result.h:1288-1318, sam.h:925-937)
+        uint8_t whichsense = HT2_SPL_UNKNOWN; bool any = false;
+        for (uint32_t i = 0; i < rs->nedits; i++) {
+            const Ht2Edit& e = rs->edits[i];
+            if (e.type != HT2_EDIT_SPL) continue;
+            any = true;
+            if (whichsense == HT2_SPL_UNKNOWN) whichsense = e.splDir;
+            else if (e.splDir != HT2_SPL_UNKNOWN) {
+                if ((whichsense == HT2_SPL_FW || whichsense == HT2_SPL_SEMI_FW) && e.splDir != HT2_SPL_FW && e.splDir != HT2_SPL_SEMI_FW) { whichsense = HT2_SPL_UNKNOWN; break; }
+                if ((whichsense == HT2_SPL_RC || whichsense == HT2_SPL_SEMI_RC) && e.splDir != HT2_SPL_RC && e.splDir != HT2_SPL_SEMI_RC) { whichsense = HT2_SPL_UNKNOWN; break; }
+            }
+        }
+        if (any && whichsense != HT2_SPL_UNKNOWN) { o += "\tXS:A:"; o.push_back((whichsense == HT2_SPL_FW || whichsense == HT2_SPL_SEMI_FW) ? '+' : '-'); }
+    }
+#endif
     if (fl.concordant() || fl.discordant()) { o += "\tNH:i:"; appendInt(o, summ.numAlnsPaired); }
     else { o += "\tNH:i:"; appendInt(o, (fl.pairing == PAIR_UNPAIRED || fl.readMate1()) ? summ.numAlns[0] : summ.numAlns[1]); }
     // Zs:Z: the known ALTs the alignment went through (sam.h:983-1032)

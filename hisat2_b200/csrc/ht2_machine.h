@@ -584,7 +584,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
             int64_t bestScore = W->bestUnp[rdi];
             if (bestScore >= minsc[rdi]) {
                 uint32_t maxmm = (uint32_t)((-bestScore + P->mmpMax - 1) / P->mmpMax);
-                if (numSearched > maxmm + 0 + 1) {
+                if (numSearched > maxmm + bestSpliced(rdi) + 1) {
                     hit.done = 1;
                     if (paired) {
                         if (W->bestUnp[1 - rdi] >= minsc[1 - rdi] && W->nPairs > 0) W->st = TS_AFTER_LOOP;
@@ -628,7 +628,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
         if (bestScore < minsc[rdi]) bestScore = minsc[rdi];
         uint32_t maxmm = (uint32_t)((-bestScore + P->mmpMax - 1) / P->mmpMax);
         uint32_t numActualPartialSearch = hit.numPartialSearch - hit.numUniqueSearch;
-        if (!P->secondary && numActualPartialSearch > maxmm + 0 + 1) { W->alignRet = 1; W->st = TS_POST_ALIGN; break; }
+        if (!P->secondary && numActualPartialSearch > maxmm + bestSpliced(rdi) + 1) { W->alignRet = 1; W->st = TS_POST_ALIGN; break; }
         const uint32_t maxsize = P->khits > P->kseeds ? P->khits : P->kseeds;
         W->nGenomeHits = 0;
         uint32_t numHits = getAnchorHits(rdi, fw, maxsize);

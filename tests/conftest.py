@@ -41,6 +41,17 @@ def hostsim_bin(tmp_path_factory):
     return out
 
 
+@pytest.fixture(scope="session")
+def hostsim_spliced_bin(tmp_path_factory):
+    """TEST-ONLY host build with -DHT2_ENABLE_SPLICED: the spliced-alignment pieces (splice edits, the spliced
+    branch of combineWith, splice scoring, N/XS:A in SAM) that are not in the CUDA library yet."""
+    out = str(tmp_path_factory.mktemp("hostsim_spl") / "ht2_hostsim_spliced")
+    c = os.path.join(ROOT, "hisat2_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++14", "-DHT2_ENABLE_SPLICED", "-o", out, os.path.join(ROOT, "tests", "hostsim", "ht2_hostsim.cpp"),
+                    os.path.join(c, "ht2_index.cpp"), os.path.join(c, "ht2_host.cpp"), "-lpthread"], check=True)
+    return out
+
+
 def sam_lines(data):
     if isinstance(data, str):
         data = data.encode()

@@ -205,6 +205,66 @@ OPTION_SETS = {   # name -> (index, format flag, SE file, PE files)
 }
 
 
+def spliced():
+    """Spliced mode (the reference's default) with --no-temp-splicesite, i.e. with an empty splice-site DB
+    (hisat2.cpp:4092-4093): order-independent, the parity target of SURVEY 8(e).  Golden SAM for the tiny
+    fixtures; the chr22-scale sets are compared against the reference run in place (tools/fuzz_parity.py)."""
+    al = os.path.join(REF, "hisat2-align-s")
+    # RNA-like reads: 101 bases over one or two GT..AG (or, one in five, arbitrary) "introns" of tiny.fa, 0.5 % substitutions
+    import random
+    rng = random.Random(11)
+    refs, name = {}, None
+    for l in open(os.path.join(G, "tiny.fa")):
+        if l.startswith(">"):
+            name = l[1:].split()[0]; refs[name] = []
+        else:
+            refs[name].append(l.strip().upper())
+    refs = {k: "".join(v) for k, v in refs.items()}
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    recs = []
+    while len(recs) < 400:
+        chrom = rng.choice(list(refs)); seq = refs[chrom]
+        nint = rng.choice([1, 1, 1, 2]); pos = rng.randrange(0, len(seq) - 12000); parts = []; left = 101; ok = True
+        for k in range(nint + 1):
+            ln = left if k == nint else rng.randrange(12, left - 12 * (nint - k))
+            parts.append(seq[pos:pos + ln]); left -= ln; pos += ln
+            if k < nint:
+                if rng.random() < 0.8:
+                    g = seq.find("GT", pos, pos + 1)
+                    if g != pos:
+                        ok = False; break
+                    e = -1
+                    for _ in range(50):
+                        cand = pos + rng.randrange(60, 4000)
+                        a = seq.find("AG", cand, cand + 200)
+                        if a > 0:
+                            e = a + 2; break
+                    if e < 0:
+                        ok = False; break
+                    pos = e
+                else:
+                    pos += rng.randrange(30, 3000)
+        rd = "".join(parts)
+        if not ok or len(rd) != 101 or "N" in rd:
+            continue
+        rd = "".join(rng.choice("ACGT".replace(c, "")) if rng.random() < 0.005 else c for c in rd)
+        if rng.random() < 0.5:
+            rd = "".join(comp[c] for c in reversed(rd))
+        recs.append(rd)
+    with open(os.path.join(G, "tiny_rna.fa"), "w") as f:
+        for i, r in enumerate(recs):
+            f.write(">t%d\n%s\n" % (i, r))
+    for idx, fmt, args, out in (("tiny", "-f", ["-U", "tiny_rna.fa"], "tiny_spliced_rna.sam"),
+                                ("tiny", "-f", ["-U", "tiny_se.fa"], "tiny_spliced_se.sam"),
+                                ("tiny", "-q", ["-1", "tiny_pe_1.fq", "-2", "tiny_pe_2.fq"], "tiny_spliced_pe_fq.sam"),
+                                ("tiny_snp", "-f", ["-1", "tiny_alt_1.fa", "-2", "tiny_alt_2.fa"], "tiny_snp_spliced_alt_pe.sam")):
+        subprocess.run([al, "--no-temp-splicesite", fmt, "-x", idx] + args + ["-S", "spl.tmp"], check=True, cwd=G, stderr=subprocess.DEVNULL)
+        data = b"".join(l for l in open(os.path.join(G, "spl.tmp"), "rb") if not l.startswith(b"@PG"))
+        open(os.path.join(G, out), "wb").write(data)
+        print(out, data.count(b"\n"), "records,", sum(1 for l in data.splitlines() if not l.startswith(b"@") and b"N" in l.split(b"\t")[5]), "spliced")
+    os.remove(os.path.join(G, "spl.tmp"))
+
+
 def options():
     """md5 of the reference's SAM (minus @PG) for every option case -> option_matrix.json."""
     import hashlib, json
@@ -225,6 +285,9 @@ def options():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "spliced":
+        spliced()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "options":
         options()
         sys.exit(0)

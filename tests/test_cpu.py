@@ -128,6 +128,31 @@ def test_batch_sam_back_end_matches_golden_and_is_thread_invariant(hostsim_bin, 
     assert outs[0] == outs[1] == outs[2] and outs[0].count(b"\n") > 4900
 
 
+def test_spliced_alignment_host_build_matches_golden_reference_sam(hostsim_spliced_bin, tmp_path):
+    """Spliced alignment (the reference's default mode, run with --no-temp-splicesite so that the splice-site
+    DB stays empty and reads are independent): the host build with the spliced pieces enabled -- splice
+    edits, the spliced branch of combineWith (motif classes, intron-length rules, probability model),
+    calculateScore for splice edits, N / XS:A / fragment lengths in SAM -- against golden SAM of the
+    unmodified reference: 400 RNA-like reads over one or two introns (340 spliced alignments), the DNA
+    fixtures SE / PE FASTQ, and ALT-allele pairs on the graph index.  The CUDA library still refuses
+    spliced mode (these pieces are not on the device yet)."""
+    env = dict(os.environ, HT2_OPTS="spliced=1")
+    for idx, args, gold in (("tiny", ["tiny_rna.fa"], "tiny_spliced_rna.sam"), ("tiny", ["tiny_se.fa"], "tiny_spliced_se.sam"),
+                            ("tiny", ["tiny_pe_1.fq", "tiny_pe_2.fq"], "tiny_spliced_pe_fq.sam"),
+                            ("tiny_snp", ["tiny_alt_1.fa", "tiny_alt_2.fa"], "tiny_snp_spliced_alt_pe.sam")):
+        out = str(tmp_path / "o.sam")
+        r = subprocess.run([hostsim_spliced_bin, idx, args[0], out] + args[1:], cwd=GOLDEN, check=True, stderr=subprocess.PIPE, env=env)
+        assert b"err=" not in r.stderr, gold
+        assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), gold
+    rna = open(os.path.join(GOLDEN, "tiny_spliced_rna.sam")).read().splitlines()
+    assert sum(1 for l in rna if not l.startswith("@") and "N" in l.split("\t")[5]) >= 300
+    assert any("XS:A:+" in l for l in rna) and any("XS:A:-" in l for l in rna)
+    # and the same build without spliced mode still reproduces the --no-spliced-alignment goldens
+    out = str(tmp_path / "o2.sam")
+    subprocess.run([hostsim_spliced_bin, "tiny", "tiny_pe_1.fa", out, "tiny_pe_2.fa"], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL)
+    assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe.sam"), "rb").read())
+
+
 def test_abi_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))
