@@ -1213,6 +1213,9 @@ struct Ht2AlignerT {
                         const Ht2Edit& e = h.edits[ei];
                         if (e.type == HT2_EDIT_REF_GAP) ref_ext--;
                         else if (e.type == HT2_EDIT_READ_GAP) ref_ext++;
+#ifdef HT2_ENABLE_SPLICED
+                        else if (e.type == HT2_EDIT_SPL) ref_ext += (int)e.splLen;
+#endif
                         else if (e.type == HT2_EDIT_MM && e.chr == 'N') ref_ext--;
                     }
                     best_ext = alignWithALTs(h, seq, h.joinedOff + (uint32_t)ref_ext, h.rdoff, h.rdoff + h.len, rdlen - (h.rdoff + h.len),

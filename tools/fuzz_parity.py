@@ -6,6 +6,7 @@ error; anything else is reported as UNEXPLAINED.
 
   python tools/fuzz_parity.py SEED N            # tiny fixtures (tests/golden), all options incl. presets
   python tools/fuzz_parity.py SEED N --big      # chr22 sets (data/, oracle/make_data.sh), dp-centred
+  ... --spliced                                   # spliced mode (--no-temp-splicesite) instead of --no-spliced-alignment
 
 Option spelling follows the reference's parser quirks exactly like the CLI does (hisat2_b200_main.cpp):
 --sp reads both bounds from the first number, --mp re-enables quality-aware penalties under
@@ -23,7 +24,8 @@ TMP = tempfile.mkdtemp(prefix="ht2fuzz")
 def build_hostsim():
     out = os.path.join(TMP, "ht2_hostsim")
     c = os.path.join(ROOT, "hisat2_b200", "csrc")
-    subprocess.run(["g++", "-O2", "-std=c++14", "-o", out, os.path.join(ROOT, "tests", "hostsim", "ht2_hostsim.cpp"),
+    subprocess.run(["g++", "-O2", "-std=c++14"] + (["-DHT2_ENABLE_SPLICED"] if "--spliced" in sys.argv else []) +
+                   ["-o", out, os.path.join(ROOT, "tests", "hostsim", "ht2_hostsim.cpp"),
                     os.path.join(c, "ht2_index.cpp"), os.path.join(c, "ht2_host.cpp"), "-lpthread"], check=True)
     return out
 
@@ -47,10 +49,16 @@ def fq_from_fa(fa, fq, seed):
             f.write(b"@" + n.encode() + b"\n" + s.encode() + b"\n+\n" + bytes((q + 33).astype(np.uint8)) + b"\n")
 
 
+SPLICED = "--spliced" in sys.argv   # spliced mode with --no-temp-splicesite (host build with -DHT2_ENABLE_SPLICED)
+
+
 def compare(hs, index, fmt, flags, hostopts, f1, f2, threads=1):
     inp = ["-1", f1, "-2", f2] if f2 else ["-U", f1]
     rs, hsam = os.path.join(TMP, "r.sam"), os.path.join(TMP, "h.sam")
-    subprocess.run([R, "--no-spliced-alignment", fmt, "-x", index, "-p", str(threads), "--reorder"] + flags + inp + ["-S", rs],
+    mode = "--no-temp-splicesite" if SPLICED else "--no-spliced-alignment"
+    if SPLICED:
+        hostopts = list(hostopts) + ["spliced=1"]
+    subprocess.run([R, mode, fmt, "-x", index, "-p", str(threads), "--reorder"] + flags + inp + ["-S", rs],
                    stderr=subprocess.DEVNULL, check=True)
     env = dict(os.environ)
     if hostopts:
@@ -119,7 +127,7 @@ def main():
     rng = random.Random(seed)
     hs = build_hostsim()
     bad = 0
-    tiny_sets = {"tiny": [("tiny_se.fa", None), ("tiny_pe_1.fa", "tiny_pe_2.fa")],
+    tiny_sets = {"tiny": [("tiny_se.fa", None), ("tiny_pe_1.fa", "tiny_pe_2.fa"), ("tiny_rna.fa", None)],
                  "tiny_snp": [("tiny_alt_1.fa", None), ("tiny_alt_1.fa", "tiny_alt_2.fa"), ("tiny_se.fa", None)]}
     big_sets = [("22_20-21M", "hard20k_1.fa", None), ("22_20-21M", "hard20k_1.fa", "hard20k_2.fa"), ("22_20-21M", "len150_1.fa", None),
                 ("22_20-21M", "len36_1.fa", "len36_2.fa"), ("22_20-21M_snp", "alt20k_1.fa", "alt20k_2.fa"),
