@@ -433,10 +433,14 @@ inline float ht2_intron_len_prob_noncan(uint32_t anchor, uint32_t intronLen, uin
 // (--pen-cansplice 0, --pen-noncansplice 12, --pen-canintronlen / --pen-noncanintronlen G,-8,1; hisat2.cpp:493-497)
 #define HT2_PEN_NONCANSPLICE 12
 #define HT2_PEN_CONFLICTSPLICE 1000000
+// max(0, (int)(-8 + ln(x))) as integer breakpoints (the first x at which the value becomes k, found by
+// scanning the double-precision expression; exhaustively equal to it for x <= 2e6): no libm call, so the
+// device build will agree with the host bit for bit
 inline int64_t ht2_intron_pen(int intronlen) {
+    static const uint32_t bp[13] = {8104u, 22027u, 59875u, 162755u, 442414u, 1202605u, 3269018u, 8886111u, 24154953u,
+                                    65659970u, 178482301u, 485165196u, 1318815735u};
     int pen = 0;
-    if (intronlen > 0) { double v = -8.0 + 1.0 * log((double)intronlen); pen = (int)v; }
-    if (pen < 0) pen = 0;
+    if (intronlen > 0) for (int k = 0; k < 13 && (uint32_t)intronlen >= bp[k]; k++) pen = k + 1;
     return pen;
 }
 #endif // HT2_ENABLE_SPLICED
