@@ -74,15 +74,21 @@ struct Ht2Edit {          // edit.h:41-330
     uint8_t  type;
     uint8_t  pad;
     uint32_t snpID;
-#ifdef HT2_ENABLE_SPLICED /* spliced alignment, host test build only for now */
-    uint32_t splLen;      // EDIT_TYPE_SPL: intron length
-    uint8_t  splDir;      // HT2_SPL_*
-    uint8_t  knownSpl;
-    uint8_t  pad2[2];
-    int64_t  donor_seq, acceptor_seq;
-#endif
 };
 enum { HT2_SPL_UNKNOWN = 1, HT2_SPL_FW, HT2_SPL_RC, HT2_SPL_SEMI_FW, HT2_SPL_SEMI_RC };   // splice_site.h:37-43
+// A splice edit (type HT2_EDIT_SPL; spliced alignment, host test build only for now) keeps the
+// same 12 bytes: intron length (20 bits) in chr | qchr << 8 | (pad & 15) << 16, direction in pad bits 4-6,
+// "known site" in pad bit 7, and -- instead of the reference's donor / acceptor context words, whose only
+// consumer is SpliceSiteDB::probscore in calculateScore -- that probability itself (float bits) in snpID.
+HT2_HD uint32_t ht2_spl_len(const Ht2Edit& e) { return (uint32_t)e.chr | ((uint32_t)e.qchr << 8) | ((uint32_t)(e.pad & 15) << 16); }
+HT2_HD uint32_t ht2_spl_dir(const Ht2Edit& e) { return (e.pad >> 4) & 7u; }
+HT2_HD bool ht2_spl_known(const Ht2Edit& e) { return (e.pad >> 7) != 0; }
+HT2_HD float ht2_spl_prob(const Ht2Edit& e) { union { uint32_t u; float f; } c; c.u = e.snpID; return c.f; }
+HT2_HD void ht2_spl_set(Ht2Edit& e, uint32_t len, uint32_t dir, bool known, float prob) {
+    e.chr = (uint8_t)len; e.qchr = (uint8_t)(len >> 8); e.pad = (uint8_t)(((len >> 16) & 15u) | ((dir & 7u) << 4) | (known ? 128u : 0u));
+    union { uint32_t u; float f; } c; c.f = prob; e.snpID = c.u;
+}
+#define HT2_MAX_SPL_LEN 0xfffffu
 
 struct Ht2Hit {           // GenomeHit, hi_aligner.h:431-1369
     uint32_t fw;
@@ -502,11 +508,7 @@ struct Ht2AlignerT {
 #endif
     }
     HT2_HD static Ht2Edit mkEdit(uint32_t pos, uint8_t chr, uint8_t qchr, uint8_t type) {
-        Ht2Edit e; e.pos = pos; e.chr = chr; e.qchr = qchr; e.type = type; e.pad = 0; e.snpID = HT2_IDX_MAX32;
-#ifdef HT2_ENABLE_SPLICED
-        e.splLen = 0; e.splDir = HT2_SPL_UNKNOWN; e.knownSpl = 0; e.pad2[0] = e.pad2[1] = 0; e.donor_seq = e.acceptor_seq = 0;
-#endif
-        return e;
+        Ht2Edit e; e.pos = pos; e.chr = chr; e.qchr = qchr; e.type = type; e.pad = 0; e.snpID = HT2_IDX_MAX32; return e;
     }
     HT2_HD bool pushEdit(Ht2Hit& h, const Ht2Edit& e) {
         if (h.nedits >= HT2_MAX_EDITS) { W->err |= HT2_ERR_EDITS; return false; }
@@ -521,7 +523,7 @@ struct Ht2AlignerT {
         if (a.type != b.type) return false;
         if (a.pos != b.pos) return false;
 #ifdef HT2_ENABLE_SPLICED
-        if (a.type == HT2_EDIT_SPL) return a.splLen == b.splLen && a.splDir == b.splDir;
+        if (a.type == HT2_EDIT_SPL) return ht2_spl_len(a) == ht2_spl_len(b) && ht2_spl_dir(a) == ht2_spl_dir(b);
 #endif
         return a.chr == b.chr && a.qchr == b.qchr;
     }
@@ -575,7 +577,7 @@ struct Ht2AlignerT {
             if (h.edits[i].type == HT2_EDIT_READ_GAP) toff++;
             else if (h.edits[i].type == HT2_EDIT_REF_GAP) toff--;
 #ifdef HT2_ENABLE_SPLICED
-            else if (h.edits[i].type == HT2_EDIT_SPL) toff += h.edits[i].splLen;
+            else if (h.edits[i].type == HT2_EDIT_SPL) toff += ht2_spl_len(h.edits[i]);
 #endif
         }
         return toff;
@@ -630,8 +632,9 @@ struct Ht2AlignerT {
             }
 #ifdef HT2_ENABLE_SPLICED
             else if (e.type == HT2_EDIT_SPL) {   // hi_aligner.h:3745-3838
-                const bool canon = (e.splDir == HT2_SPL_FW || e.splDir == HT2_SPL_RC);
-                if (!e.knownSpl) {
+                const uint32_t eDir = ht2_spl_dir(e), eLen = ht2_spl_len(e);
+                const bool canon = (eDir == HT2_SPL_FW || eDir == HT2_SPL_RC);
+                if (!ht2_spl_known(e)) {
                     int left_anchor_len = (int)(h.rdoff + e.pos);
                     int right_anchor_len = (int)rdlenS - left_anchor_len;
                     uint32_t mm2 = 0;
@@ -646,15 +649,15 @@ struct Ht2AlignerT {
                     const uint32_t intronLen_thresh = canon ? ht2_max_intron_len((uint32_t)shorter_anchor_len, P->minAnchorLen)
                                                             : ht2_max_intron_len_noncan((uint32_t)shorter_anchor_len, P->minAnchorLenNoncan);
                     if (intronLen_thresh < P->maxIntronLen) {
-                        if (e.splLen > intronLen_thresh) score += (int64_t)INT32_MIN;
+                        if (eLen > intronLen_thresh) score += (int64_t)INT32_MIN;
                         if (canon) {
-                            const float probscore = ht2_spl_probscore(e.donor_seq, e.acceptor_seq);
+                            const float probscore = ht2_spl_prob(e);   // SpliceSiteDB::probscore of the site, taken when the edit was made
                             float thresh = 0.8f;
-                            if (e.splLen >> 16) thresh = 0.99f;
-                            else if (e.splLen >> 15) thresh = 0.97f;
-                            else if (e.splLen >> 14) thresh = 0.94f;
-                            else if (e.splLen >> 13) thresh = 0.91f;
-                            else if (e.splLen >> 12) thresh = 0.88f;
+                            if (eLen >> 16) thresh = 0.99f;
+                            else if (eLen >> 15) thresh = 0.97f;
+                            else if (eLen >> 14) thresh = 0.94f;
+                            else if (eLen >> 13) thresh = 0.91f;
+                            else if (eLen >> 12) thresh = 0.88f;
                             if (probscore < thresh) score += (int64_t)INT32_MIN;
                         }
                         if (shorter_anchor_len == left_anchor_len) {
@@ -671,17 +674,17 @@ struct Ht2AlignerT {
                             }
                         }
                     }
-                    if (e.snpID == HT2_IDX_MAX32) {
-                        if (canon) score -= ht2_intron_pen((int)e.splLen) + P->canSplPen;
-                        else score -= ht2_intron_pen((int)e.splLen) + HT2_PEN_NONCANSPLICE;
+                    {   // (edit.snpID is always "none" here: splice-site ALTs are not built)
+                        if (canon) score -= ht2_intron_pen((int)eLen) + P->canSplPen;
+                        else score -= ht2_intron_pen((int)eLen) + HT2_PEN_NONCANSPLICE;
                     }
-                    if (shorter_anchor_len <= 15) { numsplices += 1; splicescore += (double)e.splLen; }
+                    if (shorter_anchor_len <= 15) { numsplices += 1; splicescore += (double)eLen; }
                 }
                 if (!conflict_splicesites) {
-                    if (whichsense == HT2_SPL_UNKNOWN) whichsense = e.splDir;
-                    else if (e.splDir != HT2_SPL_UNKNOWN) {
-                        if (e.splDir == HT2_SPL_FW || e.splDir == HT2_SPL_SEMI_FW) { if (whichsense != HT2_SPL_FW && whichsense != HT2_SPL_SEMI_FW) conflict_splicesites = true; }
-                        if (e.splDir == HT2_SPL_RC || e.splDir == HT2_SPL_SEMI_RC) { if (whichsense != HT2_SPL_RC && whichsense != HT2_SPL_SEMI_RC) conflict_splicesites = true; }
+                    if (whichsense == HT2_SPL_UNKNOWN) whichsense = (uint8_t)eDir;
+                    else if (eDir != HT2_SPL_UNKNOWN) {
+                        if (eDir == HT2_SPL_FW || eDir == HT2_SPL_SEMI_FW) { if (whichsense != HT2_SPL_FW && whichsense != HT2_SPL_SEMI_FW) conflict_splicesites = true; }
+                        if (eDir == HT2_SPL_RC || eDir == HT2_SPL_SEMI_RC) { if (whichsense != HT2_SPL_RC && whichsense != HT2_SPL_SEMI_RC) conflict_splicesites = true; }
                     }
                 }
             }
@@ -1218,7 +1221,7 @@ struct Ht2AlignerT {
                         if (e.type == HT2_EDIT_REF_GAP) ref_ext--;
                         else if (e.type == HT2_EDIT_READ_GAP) ref_ext++;
 #ifdef HT2_ENABLE_SPLICED
-                        else if (e.type == HT2_EDIT_SPL) ref_ext += (int)e.splLen;
+                        else if (e.type == HT2_EDIT_SPL) ref_ext += (int)ht2_spl_len(e);
 #endif
                         else if (e.type == HT2_EDIT_MM && e.chr == 'N') ref_ext--;
                     }
@@ -1490,8 +1493,8 @@ struct Ht2AlignerT {
                     uint32_t left = this_toff + i + 1;
                     uint32_t right = other_toff + other_len - (len - i - 1);
                     Ht2Edit e = mkEdit(i + 1 + addoff, 'A', 'A', HT2_EDIT_SPL);
-                    e.splLen = right - left; e.splDir = (uint8_t)maxspldir; e.knownSpl = 0;
-                    e.donor_seq = donor_seq; e.acceptor_seq = acceptor_seq;
+                    if (right - left > HT2_MAX_SPL_LEN) { W->err |= HT2_ERR_SPLICE; return false; }
+                    ht2_spl_set(e, right - left, maxspldir, false, ht2_spl_probscore(donor_seq, acceptor_seq));
                     if (!pushEdit(a, e)) return false;
                 }
             }
@@ -1633,7 +1636,7 @@ struct Ht2AlignerT {
 #ifdef HT2_ENABLE_SPLICED
         {   // GenomeHit::spliced() -> AlnScore(..., splicescore, knownTranscripts, nearSpliceSites, ...) (hi_aligner.h:6100-6145)
             bool spl = false, known = true;
-            for (uint32_t i = 0; i < hit.nedits; i++) if (hit.edits[i].type == HT2_EDIT_SPL) { spl = true; known = known && hit.edits[i].knownSpl; }
+            for (uint32_t i = 0; i < hit.nedits; i++) if (hit.edits[i].type == HT2_EDIT_SPL) { spl = true; known = known && ht2_spl_known(hit.edits[i]); }
             r.spliced = spl ? 1 : 0; r.knownTranscripts = (spl && known) ? 1 : 0; r.splicescore = hit.splicescore;
         }
 #endif
@@ -1686,7 +1689,7 @@ struct Ht2AlignerT {
                 else if (e.type == HT2_EDIT_REF_GAP) { if (oe.type != HT2_EDIT_REF_GAP) same = false; }
 #ifdef HT2_ENABLE_SPLICED
                 else if (e.type == HT2_EDIT_SPL) {
-                    const uint32_t v = (oe.splLen & 0xfffffu) | ((uint32_t)oe.splDir << 20);
+                    const uint32_t v = (ht2_spl_len(oe) & 0xfffffu) | (ht2_spl_dir(oe) << 20);
                     if (oe.type != HT2_EDIT_SPL || e.pos != oe.pos || e.chr != (uint8_t)v || e.qchr != (uint8_t)(v >> 8) || e.pad != (uint8_t)(v >> 16)) same = false;
                 }
 #endif
@@ -1708,7 +1711,7 @@ struct Ht2AlignerT {
             ed[i].pos = hit.edits[i].pos; ed[i].type = hit.edits[i].type; ed[i].chr = hit.edits[i].chr; ed[i].qchr = hit.edits[i].qchr; ed[i].pad = 0;
 #ifdef HT2_ENABLE_SPLICED
             if (hit.edits[i].type == HT2_EDIT_SPL) {   // Edit::operator== compares splLen and splDir of splice edits (edit.h:195-210)
-                const uint32_t v = (hit.edits[i].splLen & 0xfffffu) | ((uint32_t)hit.edits[i].splDir << 20);
+                const uint32_t v = (ht2_spl_len(hit.edits[i]) & 0xfffffu) | (ht2_spl_dir(hit.edits[i]) << 20);
                 ed[i].chr = (uint8_t)v; ed[i].qchr = (uint8_t)(v >> 8); ed[i].pad = (uint8_t)(v >> 16);
             }
 #endif

@@ -186,7 +186,7 @@ __device__ __noinline__ void ht2_finish_unit(Ht2Work* W, const DevOut& o, uint32
                 for (uint32_t k = 0; k < r.nedits; k++) {
                     ht2gpu_edit_t& de = o.edits[e++];
                     de.pos = r.edits[k].pos; de.chr = r.edits[k].chr; de.qchr = r.edits[k].qchr;
-                    de.type = r.edits[k].type; de.pad = 0; de.snp_id = r.edits[k].snpID;
+                    de.type = r.edits[k].type; de.pad = r.edits[k].pad; de.snp_id = r.edits[k].snpID;
                 }
             }
         }

@@ -451,7 +451,7 @@ struct Stacked { // StackedAln (aligner_result.h:723-895, aligner_result.cpp:660
             }
 #ifdef HT2_ENABLE_SPLICED
             else if (ed[i].type == HT2_EDIT_SPL) {   // aligner_result.cpp:711-718
-                ref.push_back('N'); rel.push_back('N'); snp.push_back(false); read.push_back('N'); skip.push_back(ed[i].splLen);
+                ref.push_back('N'); rel.push_back('N'); snp.push_back(false); read.push_back('N'); skip.push_back(ht2_spl_len(ed[i]));
             }
 #endif
         }
@@ -600,7 +600,7 @@ static int64_t fragmentLength(const Ht2Res& me, const Ht2Res& o, bool meMate1)
         int64_t trim_st = r.fw ? r.trim5p : r.trim3p, trim_en = r.fw ? r.trim3p : r.trim5p;
         int64_t introns = 0;
 #ifdef HT2_ENABLE_SPLICED
-        for (uint32_t e = 0; e < r.nedits; e++) if (r.edits[e].type == HT2_EDIT_SPL) introns += r.edits[e].splLen;
+        for (uint32_t e = 0; e < r.nedits; e++) if (r.edits[e].type == HT2_EDIT_SPL) introns += ht2_spl_len(r.edits[e]);
 #endif
         st = (int64_t)r.toff - trim_st;
         en = (int64_t)r.toff + r.rfextent - 1 + trim_en;
@@ -750,10 +750,11 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, 
             const Ht2Edit& e = rs->edits[i];
             if (e.type != HT2_EDIT_SPL) continue;
             any = true;
-            if (whichsense == HT2_SPL_UNKNOWN) whichsense = e.splDir;
-            else if (e.splDir != HT2_SPL_UNKNOWN) {
-                if ((whichsense == HT2_SPL_FW || whichsense == HT2_SPL_SEMI_FW) && e.splDir != HT2_SPL_FW && e.splDir != HT2_SPL_SEMI_FW) { whichsense = HT2_SPL_UNKNOWN; break; }
-                if ((whichsense == HT2_SPL_RC || whichsense == HT2_SPL_SEMI_RC) && e.splDir != HT2_SPL_RC && e.splDir != HT2_SPL_SEMI_RC) { whichsense = HT2_SPL_UNKNOWN; break; }
+            const uint8_t d = (uint8_t)ht2_spl_dir(e);
+            if (whichsense == HT2_SPL_UNKNOWN) whichsense = d;
+            else if (d != HT2_SPL_UNKNOWN) {
+                if ((whichsense == HT2_SPL_FW || whichsense == HT2_SPL_SEMI_FW) && d != HT2_SPL_FW && d != HT2_SPL_SEMI_FW) { whichsense = HT2_SPL_UNKNOWN; break; }
+                if ((whichsense == HT2_SPL_RC || whichsense == HT2_SPL_SEMI_RC) && d != HT2_SPL_RC && d != HT2_SPL_SEMI_RC) { whichsense = HT2_SPL_UNKNOWN; break; }
             }
         }
         if (any && whichsense != HT2_SPL_UNKNOWN) { o += "\tXS:A:"; o.push_back((whichsense == HT2_SPL_FW || whichsense == HT2_SPL_SEMI_FW) ? '+' : '-'); }
@@ -773,7 +774,7 @@ static void appendMate(std::string& o, const Ht2Image& img, const Ht2Params& P, 
         uint32_t prev = 0xffffffffu;
         const char* names = (const char*)img.blob.data() + IH->o_altNames;
         for (size_t i = 0; i < ned.size(); i++) {
-            if (ned[i].snpID >= nAlts) continue;
+            if (ned[i].type == HT2_EDIT_SPL || ned[i].snpID >= nAlts) continue;   // a splice edit keeps its site probability in the snpID word
             const uint32_t si = ned[i].snpID;
             const Ht2Alt& snp = altTab[si];
             if (si == prev) continue;
@@ -1006,8 +1007,37 @@ bool ht2_format_batch(const Ht2Image& img, const Ht2Params& P, const ht2gpu_read
                 for (uint32_t e = 0; e < al.n_edits && e < HT2_MAX_EDITS; e++) {
                     const ht2gpu_edit_t& se = res->edits[al.edit_off + e];
                     r.edits[e].pos = se.pos; r.edits[e].chr = se.chr; r.edits[e].qchr = se.qchr; r.edits[e].type = se.type;
-                    r.edits[e].pad = 0; r.edits[e].snpID = se.snp_id;
+                    r.edits[e].pad = se.pad; r.edits[e].snpID = se.snp_id;
                 }
+#ifdef HT2_ENABLE_SPLICED
+                {   // the splice part of the HISAT2 score key, from the edits alone: GenomeHit::spliced() and the
+                    // splicescore rule of calculateScore (hi_aligner.h:3745-3817) in the hit's (reference-forward) orientation
+                    const uint32_t rdlen = r.rdlen, n = r.nedits;
+                    bool spl = false, known = true; double ss = 0; uint32_t nss = 0;
+                    for (uint32_t e = 0; e < n; e++) {
+                        const Ht2Edit& ed = r.edits[e];
+                        if (ed.type != HT2_EDIT_SPL) continue;
+                        spl = true; known = known && ht2_spl_known(ed);
+                        if (ht2_spl_known(ed)) continue;
+                        uint32_t before = 0, after = 0;   // in hit order: plain mismatches before, mismatches + gaps after
+                        for (uint32_t k = 0; k < n; k++) {
+                            if (k == e) continue;
+                            const Ht2Edit& o2 = r.edits[k];
+                            const bool isBefore = r.fw ? (k < e) : (k > e);
+                            if (isBefore) { if (o2.type == HT2_EDIT_MM && o2.snpID == HT2_IDX_MAX32) before++; }
+                            else if (o2.type == HT2_EDIT_MM || o2.type == HT2_EDIT_READ_GAP || o2.type == HT2_EDIT_REF_GAP) after++;
+                        }
+                        const uint32_t q = ed.pos + r.trim5p;                  // 5'->3' offset of the splice in the read
+                        int left_anchor = (int)(r.fw ? q : rdlen - q), right_anchor = (int)rdlen - left_anchor;
+                        left_anchor -= (int)(before * 2); right_anchor -= (int)(after * 2);
+                        int shorter = left_anchor < right_anchor ? left_anchor : right_anchor;
+                        if (shorter <= 0) shorter = 1;
+                        if (shorter <= 15) { nss++; ss += (double)ht2_spl_len(ed); }
+                    }
+                    if (nss > 1) ss /= (double)nss;
+                    r.spliced = spl ? 1 : 0; r.knownTranscripts = (spl && known) ? 1 : 0; r.splicescore = ss;
+                }
+#endif
             }
         }
         for (uint32_t k = 0; k < rr.n_pairs; k++)

@@ -95,9 +95,10 @@ typedef struct {
     uint32_t pos;
     uint8_t  chr;      /* reference char, '-' for a reference gap */
     uint8_t  qchr;     /* read char, '-' for a read gap */
-    uint8_t  type;     /* 1 read gap, 2 ref gap, 3 mismatch */
-    uint8_t  pad;
-    uint32_t snp_id;   /* ALT index or 0xffffffff */
+    uint8_t  type;     /* 1 read gap, 2 ref gap, 3 mismatch, 5 splice (spliced mode; not produced by this build yet) */
+    uint8_t  pad;      /* 0; splice: intron length bits 16-19, direction (1 unknown, 2 +, 3 -, 4 semi +, 5 semi -) in bits 4-6 */
+    uint32_t snp_id;   /* ALT index or 0xffffffff; splice: IEEE-754 bits of the site's donor/acceptor probability.
+                          A splice edit keeps the low 16 bits of the intron length in chr | qchr << 8 */
 } ht2gpu_edit_t;
 
 /* One reported alignment == the arguments reportHit gives AlnRes::init

@@ -94,7 +94,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
             d.n_edits = (uint16_t)r.nedits; d.trim5 = (uint16_t)r.trim5p; d.trim3 = (uint16_t)r.trim3p; d.ref_extent = r.rfextent;
             d.edit_off = (uint32_t)bEdits.size();
             for (uint32_t k = 0; k < r.nedits; k++) {
-                ht2gpu_edit_t e; e.pos = r.edits[k].pos; e.chr = r.edits[k].chr; e.qchr = r.edits[k].qchr; e.type = r.edits[k].type; e.pad = 0; e.snp_id = r.edits[k].snpID;
+                ht2gpu_edit_t e; e.pos = r.edits[k].pos; e.chr = r.edits[k].chr; e.qchr = r.edits[k].qchr; e.type = r.edits[k].type; e.pad = r.edits[k].pad; e.snp_id = r.edits[k].snpID;
                 bEdits.push_back(e);
             }
             bAlns.push_back(d);

@@ -144,6 +144,11 @@ def test_spliced_alignment_host_build_matches_golden_reference_sam(hostsim_splic
         r = subprocess.run([hostsim_spliced_bin, idx, args[0], out] + args[1:], cwd=GOLDEN, check=True, stderr=subprocess.PIPE, env=env)
         assert b"err=" not in r.stderr, gold
         assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), gold
+    # the same through the C ABI's result structures (splice edits packed into ht2gpu_edit_t) and ht2_format_batch
+    out = str(tmp_path / "ob.sam")
+    subprocess.run([hostsim_spliced_bin, "tiny", "tiny_rna.fa", out], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL,
+                   env=dict(env, HT2_VIA_BATCH="1"))
+    assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_spliced_rna.sam"), "rb").read())
     rna = open(os.path.join(GOLDEN, "tiny_spliced_rna.sam")).read().splitlines()
     assert sum(1 for l in rna if not l.startswith("@") and "N" in l.split("\t")[5]) >= 300
     assert any("XS:A:+" in l for l in rna) and any("XS:A:-" in l for l in rna)
