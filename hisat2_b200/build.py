@@ -37,6 +37,8 @@ def build_lib(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs
+    if os.environ.get("HT2_SPLICED"):   # experimental: spliced alignment compiled in; not the default
+        cmd.insert(1, "-DHT2_ENABLE_SPLICED")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True, cwd=CSRC)

@@ -64,7 +64,7 @@ int main(int argc, char** argv)
     o.no_spliced_alignment = 0; // must be requested explicitly, like the reference's default is spliced
     const char *idx = NULL, *u = NULL, *m1 = NULL, *m2 = NULL, *out = NULL;
     bool fastq = true; size_t batchSz = 1000000; uint32_t gseed = 0;
-    bool sensitive = false, verySensitive = false, fast = false;
+    bool sensitive = false, verySensitive = false, fast = false, noTempSpliceSite = false;
     bool mpGiven = false;   // "--mp a,b" becomes MMP=Q,a,b, which switches the cost model back to quality-aware even
                             // under --ignore-quals (aligner_seed_policy.cpp:396-418)
     for (int i = 1; i < argc; i++) {
@@ -73,6 +73,7 @@ int main(int argc, char** argv)
         if (a == "-x") idx = next(); else if (a == "-U") u = next(); else if (a == "-1") m1 = next(); else if (a == "-2") m2 = next();
         else if (a == "-S") out = next(); else if (a == "-f") fastq = false; else if (a == "-q") fastq = true;
         else if (a == "--no-spliced-alignment") o.no_spliced_alignment = 1;
+        else if (a == "--no-temp-splicesite") noTempSpliceSite = true;   // spliced mode with an empty splice-site DB: the only spliced form a (HT2_SPLICED=1) library build honours
         else if (a == "-k") o.khits = atoi(next()); else if (a == "--max-seeds") o.max_seeds = atoi(next());
         else if (a == "--secondary") o.secondary = 1;
         else if (a == "--mp") { two(next(), o.mp_max, o.mp_min); mpGiven = true; } else if (a == "--sp") { two(next(), o.sp_max, o.sp_min); o.sp_min = o.sp_max; /* the reference reads BOTH values from the first number, aligner_seed_policy.cpp:438-441 */ }
@@ -98,7 +99,11 @@ int main(int argc, char** argv)
         else { fprintf(stderr, "Error: option %s is not supported by hisat2-b200\n", a.c_str()); return 1; }
     }
     if (!idx || (!u && !(m1 && m2))) { usage(); return 1; }
-    if (!o.no_spliced_alignment) { fprintf(stderr, "Error: spliced alignment is not implemented; pass --no-spliced-alignment\n"); return 1; }
+    if (!o.no_spliced_alignment && !noTempSpliceSite) {
+        fprintf(stderr, "Error: spliced alignment with temporary splice sites is order-dependent and not implemented; pass --no-spliced-alignment\n"
+                        "       (--no-temp-splicesite is honoured by an experimental HT2_SPLICED=1 library build only)\n");
+        return 1;
+    }
     if (mpGiven) o.ignore_quals = 0;
     // presets, spelled out the way hisat2.cpp:1889-1909 applies them after option parsing
     if (fast) {}

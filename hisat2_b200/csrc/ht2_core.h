@@ -375,7 +375,7 @@ HT2_HD uint32_t ht2_v2_splat(int v) { return (uint32_t)(uint16_t)v * 0x00010001u
 // a dump of the compiled reference).
 // ------------------------------------------------------------------------
 struct Ht2SplTables { float donor[1 << 18], acc1[1 << 14], acc2[1 << 16]; };
-inline const Ht2SplTables& ht2_spl_tables() {
+inline const Ht2SplTables& ht2_spl_tables() {   // host function: a device build receives the tables as a buffer
     static Ht2SplTables* T = NULL;
     if (T) return *T;
     static const float bg[4] = {0.27f, 0.23f, 0.23f, 0.27f};
@@ -400,8 +400,7 @@ inline const Ht2SplTables& ht2_spl_tables() {
     return *T;
 }
 // SpliceSiteDB::probscore (splice_site.cpp:832-850)
-inline float ht2_spl_probscore(int64_t donor_seq, int64_t acceptor_seq) {
-    const Ht2SplTables& T = ht2_spl_tables();
+HT2_HD float ht2_spl_probscore(const Ht2SplTables& T, int64_t donor_seq, int64_t acceptor_seq) {
     float probscore = T.donor[donor_seq & 0x3ffff];
     probscore *= T.acc1[(acceptor_seq >> 16) & 0x3fff];
     probscore *= T.acc2[acceptor_seq % (1 << 16)];
@@ -409,17 +408,17 @@ inline float ht2_spl_probscore(int64_t donor_seq, int64_t acceptor_seq) {
     return probscore;
 }
 // MaxIntronLen / intronLen_prob (hi_aligner.h:48-89)
-inline uint32_t ht2_max_intron_len(uint32_t anchor, uint32_t minAnchorLen) {
+HT2_HD uint32_t ht2_max_intron_len(uint32_t anchor, uint32_t minAnchorLen) {
     uint32_t intronLen = 0;
     if (anchor >= minAnchorLen) { if (anchor < 2) anchor = 2; uint32_t shift = (anchor << 1) - 4; shift = shift < 13 ? 13 : shift; shift = shift > 30 ? 30 : shift; intronLen = 1u << shift; }
     return intronLen;
 }
-inline uint32_t ht2_max_intron_len_noncan(uint32_t anchor, uint32_t minAnchorLenNoncan) {
+HT2_HD uint32_t ht2_max_intron_len_noncan(uint32_t anchor, uint32_t minAnchorLenNoncan) {
     uint32_t intronLen = 0;
     if (anchor >= minAnchorLenNoncan) { if (anchor < 5) anchor = 5; uint32_t shift = (anchor << 1) - 10; shift = shift > 30 ? 30 : shift; intronLen = 1u << shift; }
     return intronLen;
 }
-inline float ht2_intron_len_prob(uint32_t anchor, uint32_t intronLen, uint32_t maxIntronLen) {
+HT2_HD float ht2_intron_len_prob(uint32_t anchor, uint32_t intronLen, uint32_t maxIntronLen) {
     uint32_t expected = maxIntronLen;
     if (anchor < 14) expected = 1u << ((anchor << 1) + 4);
     if (expected > maxIntronLen) expected = maxIntronLen;
@@ -427,7 +426,7 @@ inline float ht2_intron_len_prob(uint32_t anchor, uint32_t intronLen, uint32_t m
     if (result > 1.0f) result = 1.0f;
     return result;
 }
-inline float ht2_intron_len_prob_noncan(uint32_t anchor, uint32_t intronLen, uint32_t maxIntronLen) {
+HT2_HD float ht2_intron_len_prob_noncan(uint32_t anchor, uint32_t intronLen, uint32_t maxIntronLen) {
     uint32_t expected = maxIntronLen;
     if (anchor < 16) expected = 1u << (anchor << 1);
     if (expected > maxIntronLen) expected = maxIntronLen;
@@ -442,8 +441,8 @@ inline float ht2_intron_len_prob_noncan(uint32_t anchor, uint32_t intronLen, uin
 // max(0, (int)(-8 + ln(x))) as integer breakpoints (the first x at which the value becomes k, found by
 // scanning the double-precision expression; exhaustively equal to it for x <= 2e6): no libm call, so the
 // device build will agree with the host bit for bit
-inline int64_t ht2_intron_pen(int intronlen) {
-    static const uint32_t bp[13] = {8104u, 22027u, 59875u, 162755u, 442414u, 1202605u, 3269018u, 8886111u, 24154953u,
+HT2_HD int64_t ht2_intron_pen(int intronlen) {
+    const uint32_t bp[13] = {8104u, 22027u, 59875u, 162755u, 442414u, 1202605u, 3269018u, 8886111u, 24154953u,
                                     65659970u, 178482301u, 485165196u, 1318815735u};
     int pen = 0;
     if (intronlen > 0) for (int k = 0; k < 13 && (uint32_t)intronlen >= bp[k]; k++) pen = k + 1;
@@ -462,6 +461,9 @@ struct Ht2AlignerT {
     const Ht2ParamsCore*  P;
     Ht2Work*              W;
     Ht2SwScratch*         sw;      // --bowtie2-dp scratch of this lane (NULL when dp is off)
+#ifdef HT2_ENABLE_SPLICED
+    const Ht2SplTables*   splT;    // donor / acceptor probability tables (spliced mode)
+#endif
     bool     paired;
     bool     rightendonly;
     bool     nofw[2], norc[2];
@@ -486,6 +488,9 @@ struct Ht2AlignerT {
         P = P_;
         W = W_;
         sw = NULL;
+#ifdef HT2_ENABLE_SPLICED
+        splT = NULL;
+#endif
     }
 
     // ---- edits / hits ---------------------------------------------------
@@ -1413,7 +1418,7 @@ struct Ht2AlignerT {
                             for (int j = to; j >= from; j--) { int base = refbuf2[j]; if (base > 3) base = 0; temp_donor_seq = temp_donor_seq << 2 | (base ^ 0x3); }
                         }
                     }
-                    splscore = ht2_spl_probscore(temp_donor_seq, temp_acceptor_seq);
+                    splscore = ht2_spl_probscore(*splT, temp_donor_seq, temp_acceptor_seq);
                 }
                 const bool mu = (maxspldir == HT2_SPL_UNKNOWN), su = (spldir == HT2_SPL_UNKNOWN);
                 if ((mu && su && maxscore < tempscore) || (mu && su && maxscore == tempscore && semi_canonical) ||
@@ -1494,7 +1499,7 @@ struct Ht2AlignerT {
                     uint32_t right = other_toff + other_len - (len - i - 1);
                     Ht2Edit e = mkEdit(i + 1 + addoff, 'A', 'A', HT2_EDIT_SPL);
                     if (right - left > HT2_MAX_SPL_LEN) { W->err |= HT2_ERR_SPLICE; return false; }
-                    ht2_spl_set(e, right - left, maxspldir, false, ht2_spl_probscore(donor_seq, acceptor_seq));
+                    ht2_spl_set(e, right - left, maxspldir, false, ht2_spl_probscore(*splT, donor_seq, acceptor_seq));
                     if (!pushEdit(a, e)) return false;
                 }
             }

@@ -34,6 +34,9 @@ struct DevBatch {
     int32_t         paired;
     Ht2SwScratch*   sw;     // --bowtie2-dp scratch, one per launched thread (NULL when dp is off)
     const int32_t*  minscTab; // --score-min per read length (Ht2Params::minscTab)
+#ifdef HT2_ENABLE_SPLICED
+    const Ht2SplTables* splT; // donor / acceptor probability tables (spliced mode)
+#endif
 };
 
 struct DevOut {
@@ -220,6 +223,9 @@ ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, 
     Ht2Aligner A;
     A.bind(blob, &P, W);
     A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
+#ifdef HT2_ENABLE_SPLICED
+    A.splT = b.splT;
+#endif
     // 0 = needs a unit, 1 = running, 2 = no work left.  Every lane stays in the loop
     // until the whole warp is out of work: the warp vote at the top is the point
     // where the lanes re-converge before the next segment.
@@ -290,6 +296,9 @@ ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevB
     Ht2Aligner A;
     A.bind(blob, &P, base);
     A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
+#ifdef HT2_ENABLE_SPLICED
+    A.splT = b.splT;
+#endif
     __syncwarp();
     for (;;) {
         // ---- histogram of live slot states
@@ -380,6 +389,9 @@ ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P
     Ht2Aligner A;
     A.bind(blob, &P, base);
     A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
+#ifdef HT2_ENABLE_SPLICED
+    A.splT = b.splT;
+#endif
     __syncthreads();
     for (;;) {
         if (t < RG_BINS) sHist[t] = 0;
@@ -486,6 +498,9 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
     Ht2AlignerT<GRAPH> A;
     A.bind(blob, &P, base);
     A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
+#ifdef HT2_ENABLE_SPLICED
+    A.splT = b.splT;
+#endif
     __syncthreads();
     volatile unsigned int* vCode = sCode;
     volatile int* vCount = sCount;
@@ -699,6 +714,7 @@ struct ht2gpu_handle {
     int            rgK;
     Ht2Work*       dWork;
     int32_t*       dMinsc;   // --score-min table on the device (Ht2Params::minscTab)
+    void*          dSplT;    // spliced builds: Ht2SplTables on the device
     Ht2SwScratch*  dSw;      // --bowtie2-dp: one scratch per launched thread
     size_t         nWork;
     cudaStream_t   stream;
@@ -786,7 +802,17 @@ static int finishOpen(ht2gpu_handle* h)
 {
     const Ht2ImageHeader* H = h->img->header();
     if (H->magic != HT2_MAGIC || H->version != HT2_IMAGE_VERSION) { h->err = "bad index image"; return HT2GPU_ERR_INDEX; }
+#ifndef HT2_ENABLE_SPLICED
     if (!h->opt.no_spliced_alignment) { h->err = "spliced alignment is not implemented in this build; pass --no-spliced-alignment"; return HT2GPU_ERR_UNSUPPORTED; }
+#else
+    // experimental library build (HT2_SPLICED=1 python -m hisat2_b200.build): spliced mode == the reference's
+    // --no-temp-splicesite without known splice sites (empty splice-site DB); not yet run on a GPU
+    if (!h->opt.no_spliced_alignment) {
+        const Ht2SplTables& T = ht2_spl_tables();
+        CK(cudaMalloc(&h->dSplT, sizeof(Ht2SplTables)));
+        CK(cudaMemcpy(h->dSplT, &T, sizeof(Ht2SplTables), cudaMemcpyHostToDevice));
+    }
+#endif
     h->graph = !H->global.linearFM;   // graph (SNP) indexes: ALT-aware aligner instantiation, graph seed kernel
     applyOptions(h->P, *h->img, h->opt);
     cudaDeviceProp prop;
@@ -839,7 +865,7 @@ static int finishOpen(ht2gpu_handle* h)
 static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
-    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL; h->dMinsc = NULL;
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL; h->dMinsc = NULL; h->dSplT = NULL;
     h->stream = 0;
     h->dSeq = h->dQual = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->capBases = h->capReads = 0;
     h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL; h->dStats = NULL;
@@ -942,6 +968,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     if (h->dWork) cudaFree(h->dWork);
     if (h->dSw) cudaFree(h->dSw);
     if (h->dMinsc) cudaFree(h->dMinsc);
+    if (h->dSplT) cudaFree(h->dSplT);
     cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dOffs); cudaFree(h->dSeeds);
     cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters); cudaFree(h->dStats);
     if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
@@ -1015,6 +1042,9 @@ static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units
     DevBatch db;
     db.seq = h->dSeq; db.qual = b->qual ? h->dQual : NULL; db.offs = h->dOffs; db.seeds = h->dSeeds;
     db.n_units = units; db.paired = b->paired; db.sw = h->dSw; db.minscTab = h->dMinsc;
+#ifdef HT2_ENABLE_SPLICED
+    db.splT = (const Ht2SplTables*)h->dSplT;
+#endif
     DevOut o;
     o.reads = h->dReads; o.alns = h->dAlns; o.edits = h->dEdits; o.pairs = h->dPairs;
     o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
@@ -1218,6 +1248,9 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     if (rc) return rc;
     DevBatch db;
     db.seq = h->dSeq; db.qual = NULL; db.offs = h->dOffs; db.seeds = h->dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.minscTab = h->dMinsc;
+#ifdef HT2_ENABLE_SPLICED
+    db.splT = NULL;
+#endif
     uint32_t *dCounts = NULL, *dOffs3 = NULL;
     unsigned long long* dTot = NULL;
     SeedOut so; memset(&so, 0, sizeof(so));

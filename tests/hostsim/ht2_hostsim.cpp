@@ -72,6 +72,12 @@ static void seedDump(const Ht2Image& img, const Ht2Params& P, const std::vector<
     }
 }
 
+#ifdef HT2_ENABLE_SPLICED
+#define HT2_SET_SPLT(A) (A).splT = &ht2_spl_tables()
+#else
+#define HT2_SET_SPLT(A) (void)0
+#endif
+
 template <bool GRAPH>
 static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads, std::vector<Ht2HostRead>& reads2, bool pairedMode,
                     const char* outPath) {
@@ -115,7 +121,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         int64_t ms1 = ht2_minsc(P, (uint32_t)r1.seq.size()), ms2 = ht2_minsc(P, (uint32_t)r2.seq.size());
         Ht2ReadFilters f1 = ht2_filters(r1, ms1), f2 = ht2_filters(r2, ms2);
         Ht2ReadOut out; out.err = 0;
-        A.bind(img->blob.data(), &P, W); A.sw = swScratch;
+        A.bind(img->blob.data(), &P, W); A.sw = swScratch; HT2_SET_SPLT(A);
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         bool p1 = f1.pass(), p2 = f2.pass();
         W->rnd.init((p1 && p2) ? (r1.seed ^ r2.seed) : r1.seed);
@@ -154,7 +160,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         Ht2ReadFilters f = ht2_filters(rd, minsc);
         Ht2ReadOut out;
         out.err = 0;
-        A.bind(img->blob.data(), &P, W); A.sw = swScratch;
+        A.bind(img->blob.data(), &P, W); A.sw = swScratch; HT2_SET_SPLT(A);
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         W->rnd.init(rd.seed);
         A.paired = false; A.rightendonly = false;
