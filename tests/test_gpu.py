@@ -264,6 +264,35 @@ def test_dynamic_programming_extension_matches_reference_binary_run_here(h2, ind
     idx.close()
 
 
+def test_spliced_alignment_when_compiled_in(h2, tmp_path):
+    """Spliced mode (== hisat2 --no-temp-splicesite: empty splice-site DB, reads independent).  The default
+    library refuses it (no CPU or approximate path); a library built with HT2_SPLICED=1 must reproduce the
+    committed golden SAM of the reference on the RNA-like fixture (340 spliced alignments) and the DNA
+    fixtures, and, when oracle/_ref is on the box, the reference run in place on 20k chr22 pairs."""
+    try:
+        idx = h2.Index(os.path.join(GOLDEN, "tiny"), no_spliced_alignment=0)
+    except h2.Ht2GpuError as e:
+        assert "spliced" in str(e)
+        pytest.skip("library built without HT2_SPLICED=1: spliced mode is refused loudly")
+    for args, gold, rd in ((("tiny_rna.fa",), "tiny_spliced_rna.sam", h2.ReadBatch.from_fasta), (("tiny_se.fa",), "tiny_spliced_se.sam", h2.ReadBatch.from_fasta),
+                           (("tiny_pe_1.fq", "tiny_pe_2.fq"), "tiny_spliced_pe_fq.sam", h2.ReadBatch.from_fastq)):
+        batch = rd(os.path.join(GOLDEN, args[0]), path2=os.path.join(GOLDEN, args[1]) if len(args) > 1 else None)
+        sam, _ = gpu_sam(idx, batch)
+        assert sam_lines(sam) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), gold
+    idx.close()
+    base = os.path.join(DATA, "22_20-21M")
+    f1, f2 = os.path.join(DATA, "hard20k_1.fa"), os.path.join(DATA, "hard20k_2.fa")
+    if os.path.exists(REFBIN) and os.path.exists(base + ".1.ht2") and os.path.exists(f1):
+        idx = h2.Index(base, no_spliced_alignment=0)
+        batch = h2.ReadBatch.from_fasta(f1, path2=f2)
+        sam, _ = gpu_sam(idx, batch)
+        out = str(tmp_path / "ref.sam")
+        subprocess.run([REFBIN, "--no-temp-splicesite", "-f", "-x", base, "-1", f1, "-2", f2, "-S", out, "-p", str(min(16, os.cpu_count() or 1)), "--reorder"],
+                       check=True, stderr=subprocess.DEVNULL)
+        assert sam_lines(sam) == sam_lines(open(out, "rb").read())
+        idx.close()
+
+
 def test_seed_search_bundled_graph_index_matches_oracle(h2, oracle_bin):
     """The reference's bundled example index (22_20-21M_snp: 3,689 SNPs/indels, 958,359 rows over
     954,773 nodes): every H/G/C record of 20k hard reads equals the pinned oracle's."""
