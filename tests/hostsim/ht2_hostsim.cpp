@@ -208,7 +208,88 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
     return 0;
 }
 
+// --sw-selftest N SEED: pins the striped s16x2 fill (ht2_sw.h swFill) and the plane-derived backtrace against
+// an independent, plain scalar statement of the same saturating Gotoh recurrences: every last-row score must
+// be equal, and the edits returned for the best candidate must turn the read into the reference window
+// they claim, at exactly that score.
+static int swSelfTest(int n, unsigned seed) {
+    Ht2Params P; memset(&P, 0, sizeof(P));
+    Ht2Work* W = new Ht2Work(); Ht2SwScratch* S = new Ht2SwScratch();
+    Ht2AlignerT<false> A; A.blob = NULL; A.H = NULL; A.P = &P; A.W = W; A.sw = S;
+    uint32_t rng = seed ? seed : 1;
+    auto rnd = [&](uint32_t m) { rng = rng * 1664525u + 1013904223u; return (rng >> 8) % m; };
+    int bad = 0; long cells = 0, traced = 0;
+    for (int it = 0; it < n; it++) {
+        P.mmpMax = 2 + rnd(6); P.mmpMin = 1 + rnd(P.mmpMax); P.npen = 1 + rnd(2); P.mmcostConstant = rnd(4) == 0;
+        P.rdGapConst = 1 + rnd(8); P.rdGapLinear = 1 + rnd(4); P.rfGapConst = 1 + rnd(8); P.rfGapLinear = 1 + rnd(4);
+        P.gapbar = 1 + rnd(12);
+        const uint32_t nrow = 20 + rnd(HT2_MAX_RDLEN - 20), ncol = nrow + 40;
+        std::vector<uint8_t> ref(ncol + 8), rd, qu;
+        for (auto& c : ref) c = rnd(50) == 0 ? 4 : rnd(4);
+        for (uint32_t j = 20; rd.size() < nrow && j < ncol;) {   // the read: the window with substitutions and small indels
+            uint32_t r = rnd(100);
+            if (r < 3) { rd.push_back((uint8_t)rnd(4)); }                        // insertion in the read
+            else if (r < 6) { j++; }                                               // deletion
+            else { rd.push_back(r < 12 ? (uint8_t)rnd(5) : ref[j]); j++; }
+        }
+        while (rd.size() < nrow) rd.push_back((uint8_t)rnd(4));
+        for (uint32_t i = 0; i < nrow; i++) qu.push_back((uint8_t)(33 + rnd(42)));
+        const int64_t minsc = -(int64_t)(10 + rnd(3 * nrow));
+        W->err = 0;
+        int64_t best = A.swFill(rd.data(), qu.data(), nrow, ref.data(), ncol, minsc);
+        // scalar statement (score space: 0 = perfect, no floor needed in 64-bit; barrier = -inf)
+        const int64_t NEG = -(1ll << 40);
+        std::vector<int64_t> Hp(nrow, NEG), Ep(nrow, NEG), Hc(nrow), Ec(nrow), last(ncol);
+        const int rdo = P.rdGapConst + P.rdGapLinear, rde = P.rdGapLinear, rfo = P.rfGapConst + P.rfGapLinear, rfe = P.rfGapLinear;
+        for (uint32_t j = 0; j < ncol; j++) {
+            int64_t f = NEG, hup = NEG;
+            for (uint32_t i = 0; i < nrow; i++) {
+                const bool gb = i < (uint32_t)P.gapbar || nrow - 1 - i < (uint32_t)P.gapbar;
+                const int rdc = rd[i], rfc = ref[j];
+                const int pen = (rdc > 3 || rfc > 3) ? P.npen : (rdc == rfc ? 0 : ht2_mmpen(P, (int)qu[i] - 33));
+                int64_t e = NEG; if (!gb && j > 0) e = std::max(Ep[i] - rde, Hp[i] - rdo); else if (j > 0) e = Ep[i] - rde;
+                int64_t ff = NEG; if (!gb && i > 0) ff = std::max(f - rfe, hup - rfo);
+                const int64_t hd = (i == 0) ? 0 : (j == 0 ? NEG : Hp[i - 1]);
+                int64_t h = std::max(std::max(hd - pen, e), ff);
+                if (h < NEG) h = NEG; if (e < NEG) e = NEG;
+                Hc[i] = h; Ec[i] = e; f = ff; hup = h;
+            }
+            last[j] = Hc[nrow - 1]; Hp = Hc; Ep = Ec;
+        }
+        int64_t sbest = NEG; for (uint32_t j = 0; j < ncol; j++) sbest = std::max(sbest, last[j]);
+        cells += (long)nrow * ncol;
+        const bool reach = sbest >= minsc && sbest > -16000;
+        if ((best != HT2_MIN_I64) != reach || (reach && best != sbest)) { fprintf(stderr, "selftest %d: best %lld vs scalar %lld (minsc %lld)\n", it, (long long)best, (long long)sbest, (long long)minsc); bad++; continue; }
+        if (!reach) continue;
+        for (uint32_t j = 0; j < ncol; j++) if (last[j] > -16000 && S->lastH[j] != last[j]) { fprintf(stderr, "selftest %d: column %u %d vs %lld\n", it, j, S->lastH[j], (long long)last[j]); bad++; break; }
+        // backtrace from the best, right-most candidate; check the edits against read and window
+        uint32_t cc = 0; for (uint32_t j = 0; j < ncol; j++) if (last[j] == sbest) cc = j;
+        typename Ht2AlignerT<false>::SwRect rect; rect.refl = 0; rect.refr = ncol - 1; rect.triml = 0; rect.trimr = 0; rect.corel = 0; rect.corer = ncol + nrow;
+        uint32_t ned = 0, off = 0; int64_t score = 0;
+        if (!A.swBacktrace(rd.data(), qu.data(), nrow, ref.data(), rect, (int)nrow, nrow - 1, cc, ned, off, score)) { fprintf(stderr, "selftest %d: backtrace failed\n", it); bad++; continue; }
+        traced++;
+        int64_t sc2 = 0; uint32_t rp = off, k = 0; bool ok = score == sbest; int prevGap = 0; uint32_t prevPos = 0;
+        for (uint32_t i = 0; i < nrow && ok; i++) {
+            while (k < ned && S->ned[k].type == HT2_EDIT_READ_GAP && S->ned[k].pos == i) {   // reference bases skipped before row i
+                ok = ok && S->ned[k].chr == "ACGTN"[ref[rp]]; sc2 -= (prevGap == 1 && prevPos == i) ? rde : rdo; prevGap = 1; prevPos = i; rp++; k++;
+            }
+            if (k < ned && S->ned[k].pos == i && S->ned[k].type == HT2_EDIT_REF_GAP) { sc2 -= (prevGap == 2 && prevPos + 1 == i) ? rfe : rfo; prevGap = 2; prevPos = i; k++; continue; }
+            const int rdc = rd[i], rfc = ref[rp];
+            if (k < ned && S->ned[k].pos == i && S->ned[k].type == HT2_EDIT_MM) {
+                ok = ok && (rdc != rfc || rdc > 3) && S->ned[k].chr == "ACGTN"[rfc] && S->ned[k].qchr == "ACGTN"[rdc];
+                sc2 -= (rdc > 3 || rfc > 3) ? P.npen : ht2_mmpen(P, (int)qu[i] - 33); k++;
+            } else ok = ok && rdc == rfc && rdc <= 3;
+            prevGap = 0; rp++;
+        }
+        ok = ok && k == ned && rp == cc + 1 && sc2 == sbest;
+        if (!ok) { fprintf(stderr, "selftest %d: edits do not reproduce the alignment (score %lld, recomputed %lld, optimum %lld)\n", it, (long long)score, (long long)sc2, (long long)sbest); bad++; }
+    }
+    printf("sw selftest: %d problems, %ld cells, %ld backtraces, %d failures\n", n, cells, traced, bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 3 && !strcmp(argv[1], "--sw-selftest")) return swSelfTest(atoi(argv[2]), argc > 3 ? (unsigned)atoi(argv[3]) : 1u);
     if (argc >= 5 && !strcmp(argv[1], "--seed-dump")) {
         std::string err;
         Ht2Image* img = ht2_image_load(argv[2], err);

@@ -158,6 +158,17 @@ def test_spliced_alignment_host_build_matches_golden_reference_sam(hostsim_splic
     assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe.sam"), "rb").read())
 
 
+def test_striped_dp_fill_and_backtrace_against_plain_scalar_dp(hostsim_bin):
+    """The --bowtie2-dp kernel on its own (ht2_sw.h: striped s16x2 fill with the DPX-style max(a+b,c) steps +
+    plane-derived backtrace) against an independent scalar statement of the recurrences: 400 random problems
+    (read lengths 20-255, random penalties / gap barriers / qualities / Ns): every last-row score equal, and
+    the returned edits turn the read into the reference window at exactly the optimal score."""
+    r = subprocess.run([hostsim_bin, "--sw-selftest", "400", "3"], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    out = r.stdout.decode()
+    assert "400 problems" in out and " 0 failures" in out, out + r.stderr.decode()
+    assert int(out.split(" backtraces")[0].split()[-1]) > 200
+
+
 def test_abi_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))
