@@ -436,7 +436,6 @@ HT2_HD float ht2_intron_len_prob_noncan(uint32_t anchor, uint32_t intronLen, uin
 }
 // Scoring::canSpl / noncanSpl (scoring.h:473-487) with the default penalty functions
 // (--pen-cansplice 0, --pen-noncansplice 12, --pen-canintronlen / --pen-noncanintronlen G,-8,1; hisat2.cpp:493-497)
-#define HT2_PEN_NONCANSPLICE 12
 #define HT2_PEN_CONFLICTSPLICE 1000000
 // max(0, (int)(-8 + ln(x))) as integer breakpoints (the first x at which the value becomes k, found by
 // scanning the double-precision expression; exhaustively equal to it for x <= 2e6): no libm call, so the
@@ -681,7 +680,7 @@ struct Ht2AlignerT {
                     }
                     {   // (edit.snpID is always "none" here: splice-site ALTs are not built)
                         if (canon) score -= ht2_intron_pen((int)eLen) + P->canSplPen;
-                        else score -= ht2_intron_pen((int)eLen) + HT2_PEN_NONCANSPLICE;
+                        else score -= ht2_intron_pen((int)eLen) + P->noncanSplPen;
                     }
                     if (shorter_anchor_len <= 15) { numsplices += 1; splicescore += (double)eLen; }
                 }
@@ -1397,7 +1396,7 @@ struct Ht2AlignerT {
                 else if (donor == AGrc && acceptor == GTrc) { spldir = HT2_SPL_RC; canonical = true; }
                 else if ((donor == GC && acceptor == AG) || (donor == AT && acceptor == AC)) { spldir = HT2_SPL_SEMI_FW; semi_canonical = true; }
                 else if ((donor == AGrc && acceptor == GCrc) || (donor == ACrc && acceptor == ATrc)) { spldir = HT2_SPL_SEMI_RC; semi_canonical = true; }
-                tempscore -= (canonical ? (int64_t)P->canSplPen : (int64_t)HT2_PEN_NONCANSPLICE);
+                tempscore -= (canonical ? (int64_t)P->canSplPen : (int64_t)P->noncanSplPen);
                 int64_t temp_donor_seq = 0, temp_acceptor_seq = 0;
                 float splscore = 0.0f;
                 if (canonical) {

@@ -44,6 +44,9 @@ void ht2_default_params(Ht2Params& P, const Ht2Image& img, bool noSplicedAlignme
     P.gMate1fw = 1; P.gMate2fw = 0;
     P.nofw = 0; P.norc = 0; P.mixed = 1; P.discord = 1;
     P.bowtie2Dp = 0; P.gapbar = 4;                      // hisat2.cpp:529, 419
+#ifdef HT2_ENABLE_SPLICED
+    P.noncanSplPen = 12;                                // hisat2.cpp:494
+#endif
     ht2_set_score_min(P, 'L', (double)0.0f, (double)-0.2f);   // hisat2.cpp:441
 }
 

@@ -54,6 +54,9 @@ struct Ht2ParamsCore {
     // --bowtie2-dp (hisat2.cpp:293, 1770): 0 off, 1 when the anchor search found nothing >= minsc, 2 always
     uint32_t bowtie2Dp;
     int32_t  gapbar;       // --gbar (4): no gaps within this many rows of either read end (DP only)
+#ifdef HT2_ENABLE_SPLICED
+    int32_t  noncanSplPen; // --pen-noncansplice (12); --pen-cansplice is canSplPen above
+#endif
 };
 
 // Host-side parameters = the core + the --score-min table.  The table reaches the device as a

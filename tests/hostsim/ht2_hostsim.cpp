@@ -334,6 +334,11 @@ int main(int argc, char** argv) {
             else if (k == "min_frag") P.minFrag = (uint32_t)v; else if (k == "max_frag") P.maxFrag = (uint32_t)v;
             else if (k == "no_mixed") P.mixed = v ? 0 : 1; else if (k == "no_discordant") P.discord = v ? 0 : 1;
             else if (k == "spliced") P.noSplicedAlignment = v ? 0 : 1;   // experiment only: spliced joins are flagged (HT2_ERR_SPLICE), not built
+            else if (k == "min_intronlen") P.minIntronLen = (uint32_t)v; else if (k == "max_intronlen") P.maxIntronLen = (uint32_t)v;
+            else if (k == "pen_cansplice") P.canSplPen = v;
+#ifdef HT2_ENABLE_SPLICED
+            else if (k == "pen_noncansplice") P.noncanSplPen = v;
+#endif
             else if (k == "bowtie2_dp") P.bowtie2Dp = (uint32_t)v; else if (k == "gbar") P.gapbar = v;
             else if (k == "score_min_type") smT = (char)v; else if (k == "score_min_const") { smC = atof(kv.c_str() + e + 1); if (!smT) smT = 'L'; }
             else if (k == "score_min_coeff") { smL = atof(kv.c_str() + e + 1); if (!smT) smT = 'L'; }

@@ -94,6 +94,8 @@ OPTS = [("khits", [1, 2, 3, 7, 20]), ("mp", [(6, 2), (4, 2), (3, 3), (8, 1)]), (
         ("secondary", [1]), ("dp", [1, 2, 2]), ("score_min", [("L", 0, -0.5), ("L", 0, -1), ("C", -30, 0), ("G", -5, -8), ("S", -3, -4), ("L", -10, -0.3)]),
         ("gbar", [1, 2, 8, 20]), ("preset", ["--sensitive", "--very-sensitive"]),
         ("no_mixed", [1]), ("no_discordant", [1]), ("frag", [(0, 300), (100, 500), (250, 260), (0, 2000)])]
+if "--spliced" in sys.argv:   # options that only matter in spliced mode
+    OPTS += [("pen_cansplice", [1, 3]), ("pen_noncansplice", [0, 5, 20]), ("intronlen", [(20, 2000), (50, 100000), (30, 500000)])]
 
 
 def draw(rng, names, paired):
@@ -113,6 +115,9 @@ def draw(rng, names, paired):
         elif name == "score_min": flags += ["--score-min", "%s,%g,%g" % v]; ho.append("score_min=%s:%g:%g" % v)
         elif name == "gbar": flags += ["--gbar", str(v)]; ho.append("gbar=%d" % v)
         elif name == "preset": flags += [v]; preset = v
+        elif name == "pen_cansplice": flags += ["--pen-cansplice", str(v)]; ho.append("pen_cansplice=%d" % v)
+        elif name == "pen_noncansplice": flags += ["--pen-noncansplice", str(v)]; ho.append("pen_noncansplice=%d" % v)
+        elif name == "intronlen": flags += ["--min-intronlen", str(v[0]), "--max-intronlen", str(v[1])]; ho += ["min_intronlen=%d" % v[0], "max_intronlen=%d" % v[1]]
         else: flags += ["--" + name.replace("_", "-")]; ho.append(name + "=1")
     if any(h.startswith("mp_max") for h in ho):
         ho = [h for h in ho if not h.startswith("ignore_quals")]
