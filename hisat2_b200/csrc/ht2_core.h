@@ -1732,7 +1732,10 @@ struct Ht2AlignerT {
         for (uint32_t i = 0; i < h.nhits; i++) { uint32_t len = h.hits[i].len; score += (int64_t)(uint32_t)(len * len); }
         uint32_t aps = h.numPartialSearch - h.numUniqueSearch;
         score -= (int64_t)aps * penaltyPerOffset;
-        score -= (int64_t)(1 << (aps << 1));
+        // the reference computes 1 << (aps << 1) in 32-bit int (hi_aligner.h:332); from 16 partial searches on the
+        // shift count is >= 32, which its x86 build executes with the count taken mod 32 (SHL) -- a GPU would
+        // produce 0 instead -- and a count of 31 yields INT_MIN: reproduce exactly that, without the undefined shift
+        score -= (int64_t)(int32_t)(1u << ((aps << 1) & 31u));
         return score;
     }
     // HI_Aligner::pickNextReadToSearch (hi_aligner.h:4868-4894)
