@@ -45,8 +45,36 @@ class CResultBatch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("reads", C.c_void_p), ("n_alns", C.c_uint32), ("alns", C.c_void_p),
                 ("n_edits", C.c_uint32), ("edits", C.c_void_p), ("n_pairs", C.c_uint32), ("pairs", C.c_void_p),
                 ("ms_h2d", C.c_float), ("ms_kernel", C.c_float), ("ms_d2h", C.c_float),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32), ("pad", C.c_uint32),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32), ("n_err_reads", C.c_uint32),
                 ("priv", C.c_void_p)]
+
+
+class CSamResult(C.Structure):
+    _fields_ = [("sam", C.c_void_p), ("sam_len", C.c_size_t), ("n_units", C.c_uint32), ("n_alns", C.c_uint32),
+                ("n_err_reads", C.c_uint32), ("n_launches", C.c_uint32),
+                ("ms_h2d", C.c_float), ("ms_align", C.c_float), ("ms_sam", C.c_float), ("ms_d2h", C.c_float),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class CReadsInput(C.Structure):
+    _fields_ = [("path1", C.c_char_p), ("path2", C.c_char_p), ("data1", C.c_void_p), ("len1", C.c_size_t),
+                ("data2", C.c_void_p), ("len2", C.c_size_t), ("format", C.c_int32), ("trim5", C.c_int32), ("trim3", C.c_int32),
+                ("phred64", C.c_int32), ("seed", C.c_uint32), ("skip", C.c_uint64), ("upto", C.c_uint64),
+                ("batch_reads", C.c_uint32), ("threads", C.c_int32)]
+
+
+class CRunStats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_units", C.c_uint64), ("sam_bytes", C.c_uint64), ("n_err_reads", C.c_uint64),
+                ("n_batches", C.c_uint64), ("s_index", C.c_double), ("s_parse", C.c_double), ("s_total", C.c_double),
+                ("ms_h2d", C.c_float), ("ms_align", C.c_float), ("ms_sam", C.c_float), ("ms_d2h", C.c_float),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class CParsedReads(C.Structure):
+    _fields_ = [("batch", CReadBatch), ("names", C.c_void_p), ("name_offs", C.c_void_p), ("names_bytes", C.c_size_t), ("priv", C.c_void_p)]
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
 EXPORTS = [
@@ -55,6 +83,8 @@ EXPORTS = [
     "ht2gpu_align_resident", "ht2gpu_free_results", "ht2gpu_format_sam", "ht2gpu_sam_header", "ht2gpu_free_text",
     "ht2gpu_num_refs", "ht2gpu_ref_name", "ht2gpu_ref_len", "ht2gpu_read_seed", "ht2gpu_last_error", "ht2gpu_close",
     "ht2gpu_seed_search", "ht2gpu_free_seed_results", "ht2gpu_index_is_graph",
+    "ht2gpu_sam_slots", "ht2gpu_submit_sam", "ht2gpu_wait_sam", "ht2gpu_align_sam", "ht2gpu_run_reads",
+    "ht2gpu_host_alloc", "ht2gpu_host_free", "ht2gpu_set_error", "ht2gpu_parse_reads", "ht2gpu_free_parsed",
 ]
 
 
@@ -107,6 +137,16 @@ def load_library(path=None):
     lib.ht2gpu_seed_search.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_uint32, C.POINTER(CSeedResult)]
     lib.ht2gpu_free_seed_results.argtypes = [C.POINTER(CSeedResult)]
     lib.ht2gpu_index_is_graph.argtypes = [C.c_void_p]
+    lib.ht2gpu_sam_slots.argtypes = [C.c_void_p]
+    lib.ht2gpu_submit_sam.argtypes = [C.c_void_p, C.c_int, C.POINTER(CReadBatch), C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.ht2gpu_wait_sam.argtypes = [C.c_void_p, C.c_int, C.POINTER(CSamResult)]
+    lib.ht2gpu_align_sam.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CSamResult)]
+    lib.ht2gpu_run_reads.argtypes = [C.c_void_p, C.POINTER(CReadsInput), SINK_FN, C.c_void_p, C.POINTER(CRunStats)]
+    lib.ht2gpu_host_alloc.argtypes = [C.c_size_t]; lib.ht2gpu_host_alloc.restype = C.c_void_p
+    lib.ht2gpu_host_free.argtypes = [C.c_void_p]
+    lib.ht2gpu_set_error.argtypes = [C.c_void_p, C.c_char_p]
+    lib.ht2gpu_parse_reads.argtypes = [C.POINTER(CReadsInput), C.POINTER(CParsedReads), C.c_char_p, C.c_size_t]
+    lib.ht2gpu_free_parsed.argtypes = [C.POINTER(CParsedReads)]
     if path is None:
         _lib = lib
     return lib
@@ -152,6 +192,51 @@ class ReadBatch(object):
 
     def names_blob(self):
         return b"\0".join(self.names) + b"\0"
+
+    def names_offsets(self):
+        """(blob, uint32 offsets[n+1]) in the layout ht2gpu_submit_sam takes."""
+        lens = np.fromiter((len(x) + 1 for x in self.names), dtype=np.int64, count=len(self.names))
+        offs = np.zeros(len(self.names) + 1, dtype=np.uint32)
+        np.cumsum(lens, out=offs[1:])
+        return self.names_blob(), offs
+
+    @staticmethod
+    def parse(path1=None, path2=None, data1=None, data2=None, fastq=False, lib=None, **kw):
+        """The library's own multi-threaded front end (ht2gpu_parse_reads, csrc/ht2_reads.cpp): the whole input
+        as one batch.  Host only."""
+        lib = lib or load_library()
+        ri = CReadsInput()
+        keep = []
+        if path1 is not None:
+            ri.path1 = os.fsencode(path1)
+        if path2 is not None:
+            ri.path2 = os.fsencode(path2)
+        for name, d in (("1", data1), ("2", data2)):
+            if d is not None:
+                buf = np.frombuffer(d, dtype=np.uint8)
+                keep.append(buf)
+                setattr(ri, "data" + name, buf.ctypes.data)
+                setattr(ri, "len" + name, buf.nbytes)
+        ri.format = 1 if fastq else 0
+        for k, v in kw.items():
+            setattr(ri, k, v)
+        pr = CParsedReads()
+        err = C.create_string_buffer(512)
+        rc = lib.ht2gpu_parse_reads(C.byref(ri), C.byref(pr), err, 512)
+        if rc != 0:
+            raise Ht2GpuError("ht2gpu_parse_reads rc=%d: %s" % (rc, err.value.decode()))
+        n = pr.batch.n_reads
+        v = AlignResult._view
+        offs = v(pr.batch.offs, n + 1, np.dtype("<u8")).copy()
+        nb = int(offs[n]) if n else 0
+        seq = v(pr.batch.seq, nb, np.dtype("u1")).copy()
+        qual = v(pr.batch.qual, nb, np.dtype("u1")).copy() if pr.batch.qual else None
+        seeds = v(pr.batch.seeds, n, np.dtype("<u4")).copy()
+        blob = C.string_at(pr.names, pr.names_bytes) if pr.names_bytes else b""
+        names = blob.split(b"\0")[:-1] if blob else []
+        paired = bool(pr.batch.paired)
+        lib.ht2gpu_free_parsed(C.byref(pr))
+        return ReadBatch(seq, offs, seeds, names, qual, paired=paired)
 
     @staticmethod
     def from_fastq(path, lib=None, global_seed=0, path2=None):
@@ -258,6 +343,7 @@ class AlignResult(object):
         self.pairs = self._view(cres.pairs, cres.n_pairs * 2, np.dtype("<u2")).reshape(-1, 2)
         self.ms_h2d, self.ms_kernel, self.ms_d2h = cres.ms_h2d, cres.ms_kernel, cres.ms_d2h
         self.h2d_bytes, self.d2h_bytes, self.n_launches = cres.h2d_bytes, cres.d2h_bytes, cres.n_launches
+        self.n_err_reads = cres.n_err_reads
 
     @staticmethod
     def _view(ptr, n, dt):
@@ -384,6 +470,49 @@ class Index(object):
         res = AlignResult(self._lib, cr)
         self._check(rc, "ht2gpu_align", allow_capacity)
         return res
+
+    def align_sam(self, batch, with_stats=False):
+        """ht2gpu_align_sam: align + SAM records formatted ON THE DEVICE for one batch (no header)."""
+        cb = batch.c_struct()
+        blob, offs = batch.names_offsets()
+        cr = CSamResult()
+        self._check(self._lib.ht2gpu_align_sam(self._h, C.byref(cb), blob, offs.ctypes.data, len(blob), C.byref(cr)), "ht2gpu_align_sam")
+        s = C.string_at(cr.sam, cr.sam_len) if cr.sam_len else b""
+        if with_stats:
+            return s, {k: getattr(cr, k) for k, _ in CSamResult._fields_ if k != "sam"}
+        return s
+
+    def run_reads(self, path1=None, path2=None, data1=None, data2=None, fastq=False, collect=True, **kw):
+        """ht2gpu_run_reads: FASTA/FASTQ (files or bytes in host memory) -> SAM records through the overlapped
+        pipeline.  Returns (sam bytes or None, stats dict)."""
+        ri = CReadsInput()
+        keep = []
+        if path1 is not None:
+            ri.path1 = os.fsencode(path1)
+        if path2 is not None:
+            ri.path2 = os.fsencode(path2)
+        for name, d in (("1", data1), ("2", data2)):
+            if d is not None:
+                buf = np.frombuffer(d, dtype=np.uint8)
+                keep.append(buf)
+                setattr(ri, "data" + name, buf.ctypes.data)
+                setattr(ri, "len" + name, buf.nbytes)
+        ri.format = 1 if fastq else 0
+        for k, v in kw.items():
+            setattr(ri, k, v)
+        chunks = []
+        total = [0]
+
+        def _sink(ctx, ptr, n):
+            if collect:
+                chunks.append(C.string_at(ptr, n))
+            total[0] += n
+            return 0
+        cb = SINK_FN(_sink) if collect else SINK_FN()     # NULL sink: the text still lands in pinned host memory
+        st = CRunStats()
+        self._check(self._lib.ht2gpu_run_reads(self._h, C.byref(ri), cb, None, C.byref(st)), "ht2gpu_run_reads")
+        stats = {k: getattr(st, k) for k, _ in CRunStats._fields_ if k != "pad"}
+        return (b"".join(chunks) if collect else None), stats
 
     def is_graph(self):
         return bool(self._lib.ht2gpu_index_is_graph(self._h))

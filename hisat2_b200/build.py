@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++14",
     "-Xcompiler", "-fPIC", "-cudart", "static",
 ]
-LIB_SRCS = ["ht2_gpu.cu", "ht2_index.cpp", "ht2_host.cpp"]
+LIB_SRCS = ["ht2_gpu.cu", "ht2_index.cpp", "ht2_host.cpp", "ht2_reads.cpp", "ht2_pipeline.cpp"]
 
 
 def _newer(target, srcs):
@@ -31,14 +31,34 @@ def _csrc_files():
     return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "ht2gpu.h")]
 
 
+def source_hash():
+    """sha1 over the library's sources: ties a profile (profiles/traffic.json) to the kernels it was taken from."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".h", ".cu", ".cpp")):
+            h.update(f.encode())
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def build_tools():
+    """tools/libsimreads.so: the synthetic read generator bench.py and the full-size tests use (test tooling)."""
+    src = os.path.join(ROOT, "tools", "simreads_fast.c")
+    so = os.path.join(ROOT, "tools", "libsimreads.so")
+    if os.path.exists(src) and not _newer(so, [src]):
+        subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
+    return so
+
+
 def build_lib(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in LIB_SRCS]
     if not force and _newer(LIB, _csrc_files()):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs
-    if os.environ.get("HT2_SPLICED"):   # experimental: spliced alignment compiled in; not the default
-        cmd.insert(1, "-DHT2_ENABLE_SPLICED")
+    if os.environ.get("HT2_NO_SPLICED"):   # diagnostic build without the spliced-alignment code (refuses spliced mode)
+        cmd.insert(1, "-DHT2_DISABLE_SPLICED")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True, cwd=CSRC)
@@ -85,4 +105,5 @@ def build_oracle(verbose=False):
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose=True)
     build_cli()
+    build_tools()
     build_oracle(verbose=True)

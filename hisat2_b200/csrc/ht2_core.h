@@ -1892,55 +1892,6 @@ struct Ht2AlignerT {
         return W->nGenomeHits;
     }
 
-    // HI_Aligner::align (hi_aligner.h:5484-5571)
-    HT2_NI bool align(uint32_t rdi, bool fw) {
-        Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
-        {   // ReadBWTHit::minWidth (hi_aligner.h:302-318)
-            bool any = false;
-            for (uint32_t i = 0; i < hit.nhits; i++) if (hit.hits[i].bot > hit.hits[i].top) { any = true; break; }
-            if (!any) return false;
-        }
-        int64_t bestScore = W->bestUnp[rdi];
-        if (bestScore < minsc[rdi]) bestScore = minsc[rdi];
-        uint32_t maxmm = (uint32_t)((-bestScore + P->mmpMax - 1) / P->mmpMax);
-        uint32_t numActualPartialSearch = hit.numPartialSearch - hit.numUniqueSearch;
-        if (!P->secondary && numActualPartialSearch > maxmm + bestSpliced(rdi) + 1) return true;
-        const uint32_t maxsize = P->khits > P->kseeds ? P->khits : P->kseeds;
-        W->nGenomeHits = 0;
-        uint32_t numHits = getAnchorHits(rdi, fw, maxsize);
-        if (numHits <= 0) return false;
-        uint64_t add = (uint64_t)(-minsc[rdi] / P->mmpMax) * numHits * (P->secondary ? 2 : 1);
-        W->maxLocalindexatts = W->localindexatts + (uint32_t)(add > 10 ? add : 10);
-        hybridSearch(rdi, fw);
-        return true;
-    }
-
-    // SplicedAligner::hybridSearch (spliced_aligner.h:112-322)
-    HT2_NI void hybridSearch(uint32_t rdi, bool fw) {
-        (void)fw;
-        for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
-            uint32_t leftext = HT2_IDX_MAX32, rightext = HT2_IDX_MAX32;
-            extend(W->genomeHits[hi], rdi, leftext, rightext, 0);
-        }
-        for (uint32_t i = 0; i < W->nGenomeHits; i++) W->genomeHitsDone[i] = 0;
-        for (uint32_t hi = 0; hi < W->nGenomeHits; hi++) {
-            uint32_t hj = 0;
-            for (; hj < W->nGenomeHits; hj++) if (!W->genomeHitsDone[hj]) break;
-            if (hj >= W->nGenomeHits) break;
-            for (uint32_t hk = hj + 1; hk < W->nGenomeHits; hk++) {
-                if (W->genomeHitsDone[hk]) continue;
-                Ht2Hit& gj = W->genomeHits[hj]; Ht2Hit& gk = W->genomeHits[hk];
-                if (gk.hitcount > gj.hitcount || (gk.hitcount == gj.hitcount && gk.len > gj.len)) hj = hk;
-            }
-            Ht2Hit& gh = W->genomeHits[hj];
-            int64_t maxsc = hybridSearchRecur(rdi, gh, gh.rdoff, gh.len, false, 0);
-            if (P->bowtie2Dp == 2 || (P->bowtie2Dp == 1 && maxsc < minsc[rdi])) {   // spliced_aligner.h:209-297
-                if (!W->err && swExtendAnchor(rdi, gh)) hybridSearchRecur(rdi, gh, gh.rdoff, gh.len, false, 0);
-            }
-            W->genomeHitsDone[hj] = 1;
-        }
-    }
-
     HT2_HD int64_t sinkFloor(uint32_t rdi, int64_t cushion) const {
         int64_t m = minsc[rdi];
         if (!P->secondary) {
@@ -1952,16 +1903,10 @@ struct Ht2AlignerT {
         return m;
     }
 
-    // SplicedAligner::hybridSearch_recur (spliced_aligner.h:331-2052) for an
-    // empty splice-site DB (--no-spliced-alignment / no known sites).
-    HT2_NI int64_t hybridSearchRecur(uint32_t rdi, const Ht2Hit& hit, uint32_t hitoff, uint32_t hitlen,
-                                      bool alignMate, uint32_t dep);
-
-    // HI_Aligner::go (hi_aligner.h:4048-4638), unpaired + paired without repeats
-    HT2_NI void go();
+    // HI_Aligner::pairReads / alignMate anchors (hi_aligner.h:5948, 5600-5717); the control flow of go() /
+    // hybridSearch_recur / alignMate is the explicit-stack machine below (ht2_machine.h)
     HT2_NI void pairReads();
     HT2_NI bool peConcordant(int64_t off1, uint32_t len1, bool fw1, int64_t off2, uint32_t len2, bool fw2) const;
-    HT2_NI bool alignMateFn(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff);
     HT2_NI void alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff);
     // explicit-stack formulation (ht2_machine.h)
     HT2_HD void pushFrame(uint32_t rdi, const Ht2Hit* hit, uint32_t hitoff, uint32_t hitlen, bool alignMate, uint32_t dep);
@@ -1979,7 +1924,7 @@ struct Ht2AlignerT {
 typedef Ht2AlignerT<false> Ht2Aligner;        // linear indexes
 typedef Ht2AlignerT<true>  Ht2GraphAligner;   // graph (SNP) indexes
 
-#include "ht2_core_impl.h"
+#include "ht2_pair.h"
 #include "ht2_machine.h"
 
 #endif // HT2_CORE_H_

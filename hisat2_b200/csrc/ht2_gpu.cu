@@ -1,10 +1,11 @@
 // ht2_gpu.cu -- CUDA kernels + C ABI (include/ht2gpu.h) of the alignment path.
 //
 // Kernel inventory
-//   ht2_align_kernel : one thread runs one read (pair) through the complete
-//                      HI_Aligner::go state machine (ht2_core.h) against the
-//                      HBM-resident index image and appends its alignments to
-//                      the batch result pools.
+//   ht2_align_pool_kernel : the alignment path -- every read (pair) runs the complete HI_Aligner::go state
+//                           machine (ht2_core.h, ht2_machine.h) against the HBM-resident index image and
+//                           appends its alignments to the batch result pools.
+//   ht2_seed_kernel       : the seed search (LF mapping) on its own.
+//   ht2_sam_*_kernel      : the SAM back end on the device (ht2_sam.h): finishRead for every read of the batch.
 // Host code here only moves bytes and launches; it never aligns anything.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -19,6 +20,7 @@
 #include "../../include/ht2gpu.h"
 #include "ht2_core.h"
 #include "ht2_seed.h"
+#include "ht2_sam.h"
 #include "ht2_host.h"
 #include "ht2_index.h"
 
@@ -204,70 +206,11 @@ __device__ __noinline__ void ht2_finish_unit(Ht2Work* W, const DevOut& o, uint32
     if (lane == 0) o.reads[u] = rr;
 }
 
-// LANES = 1 : one lane per read (pair).  Every lane owns a read and all lanes of
-//             a warp spin in the same dispatcher loop; each iteration runs ONE
-//             segment of the lane's state machine (ht2_machine.h), so lanes that
-//             are in the same state fetch and execute the same instructions
-//             together.  Reads are claimed dynamically (atomic ticket) so a slow
-//             read never holds back the rest of its warp's queue.
-// LANES = 32: one warp per read; every lane executes the same scalar state
-//             machine on the warp's single workspace, lane 0 publishes.
-template <int LANES>
-__global__ void __launch_bounds__(128)
-ht2_align_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
-{
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t tid = gtid / LANES;
-    const uint32_t lane = gtid % LANES;
-    Ht2Work* W = work + tid;
-    Ht2Aligner A;
-    A.bind(blob, &P, W);
-    A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
-#ifdef HT2_ENABLE_SPLICED
-    A.splT = b.splT;
-#endif
-    // 0 = needs a unit, 1 = running, 2 = no work left.  Every lane stays in the loop
-    // until the whole warp is out of work: the warp vote at the top is the point
-    // where the lanes re-converge before the next segment.
-    int mode = 0;
-    uint32_t u = 0, filtBits = 0;
-    for (;;) {
-        if (!__any_sync(0xffffffffu, mode != 2)) break;
-        if (mode == 0) {
-            if (LANES == 1) u = atomicAdd(&o.counters[3], 1u);
-            else {
-                if (lane == 0) u = atomicAdd(&o.counters[3], 1u);
-                u = __shfl_sync(0xffffffffu, u, 0);
-            }
-            if (u >= b.n_units) mode = 2;
-            else if (ht2_setup_unit(A, P, b, u, filtBits)) mode = 1;
-            else ht2_finish_unit<LANES>(W, o, u, filtBits, lane);
-        } else if (mode == 1) {
-            A.machineStep();
-            if (A.machineDone()) {
-                ht2_finish_unit<LANES>(W, o, u, filtBits, lane);
-                mode = 0;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// ht2_align_regroup_kernel: state-regrouping execution.
-//
-// A warp owns 32*K read slots (workspaces).  Each round it histograms the
-// states of its live slots, picks the most populous state, gathers up to 32
-// slots that are in that state and runs ONE segment of each on its 32 lanes.
-// All lanes therefore enter the same segment of the state machine together
-// (converged instruction fetch, one I-cache stream per warp) while the other
-// slots simply wait their turn.  Slot states live in shared memory.
-// ---------------------------------------------------------------------------
-#define RG_MAXK 16
-#define RG_WARPS 4
-#define RG_NEED 0u
-#define RG_FINISH 1u
-#define RG_TOP 2u          /* + TS_* */
-#define RG_FRAME 20u       /* + F_*  */
+// Slot state codes of the pool kernel: what a read slot has to do next.
+#define RG_NEED 0u         /* empty: draw the next read */
+#define RG_FINISH 1u       /* machine done: append the results */
+#define RG_TOP 2u          /* + TS_* (top-level state of go()) */
+#define RG_FRAME 20u       /* + F_*  (state of the innermost hybridSearch_recur frame) */
 #define RG_EXIT 255u
 #define RG_BINS 64
 
@@ -276,188 +219,6 @@ __device__ __forceinline__ uint32_t rg_code(const Ht2Work* W)
     if (W->nFrames > 0) return RG_FRAME + W->frames[W->nFrames - 1].pc;
     if (W->st == TS_DONE) return RG_FINISH;
     return RG_TOP + W->st;
-}
-
-template <int RG_K>
-__global__ void __launch_bounds__(32 * RG_WARPS)
-ht2_align_regroup_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
-{
-    constexpr int RG_SLOTS = 32 * RG_K;
-    __shared__ uint8_t  sCode[RG_WARPS][RG_SLOTS];
-    __shared__ uint16_t sHist[RG_WARPS][RG_BINS];
-    __shared__ uint16_t sSel[RG_WARPS][32];
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + wib;
-    Ht2Work* base = work + (size_t)gwarp * RG_SLOTS;
-    uint8_t* code = sCode[wib];
-    uint16_t* hist = sHist[wib];
-    uint16_t* sel = sSel[wib];
-    for (int j = 0; j < RG_K; j++) code[lane + 32 * j] = RG_NEED;
-    Ht2Aligner A;
-    A.bind(blob, &P, base);
-    A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
-#ifdef HT2_ENABLE_SPLICED
-    A.splT = b.splT;
-#endif
-    __syncwarp();
-    for (;;) {
-        // ---- histogram of live slot states
-        hist[lane] = 0; hist[lane + 32] = 0;
-        __syncwarp();
-        for (int j = 0; j < RG_K; j++) {
-            uint32_t c = code[lane + 32 * j];
-            if (c != RG_EXIT) atomicAdd((unsigned int*)(hist) + (c >> 1), (c & 1) ? 0x10000u : 1u); // two u16 bins per word
-        }
-        __syncwarp();
-        uint32_t c0 = hist[lane], c1 = hist[lane + 32];
-        uint32_t best = c0 >= c1 ? ((c0 << 8) | lane) : ((c1 << 8) | (lane + 32));
-        for (int off = 16; off > 0; off >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best, off); best = v > best ? v : best; }
-        if ((best >> 8) == 0) break;                    // no live slot left
-        const uint32_t target = best & 0xff;
-        // ---- gather up to 32 slots in the target state
-        uint32_t taken = 0;
-        for (int j = 0; j < RG_K; j++) {
-            bool m = code[lane + 32 * j] == target;
-            uint32_t mask = __ballot_sync(0xffffffffu, m);
-            uint32_t rank = taken + __popc(mask & ((1u << lane) - 1));
-            if (m && rank < 32) sel[rank] = (uint16_t)(lane + 32 * j);
-            taken += __popc(mask);
-        }
-        __syncwarp();
-        const uint32_t nsel = taken < 32 ? taken : 32;
-        const long long t0 = o.stats ? clock64() : 0;
-        // ---- run one segment on each selected slot
-        if (lane < nsel) {
-            const uint32_t slot = sel[lane];
-            Ht2Work* W = base + slot;
-            uint32_t nc;
-            if (target == RG_NEED) {
-                uint32_t u = atomicAdd(&o.counters[3], 1u);
-                if (u >= b.n_units) nc = RG_EXIT;
-                else {
-                    A.W = W;
-                    uint32_t filtBits;
-                    bool run = ht2_setup_unit(A, P, b, u, filtBits);
-                    if (run) { while (!A.machineAtHeavyState()) A.machineStep(); } // TS_START / TS_NEXTBWT glue
-                    nc = run ? rg_code(W) : RG_FINISH;
-                }
-            } else if (target == RG_FINISH) {
-                ht2_finish_unit<1>(W, o, W->unit, W->filtBits, 0);
-                nc = RG_NEED;
-            } else {
-                A.attach(W);
-                A.machineRun();
-                nc = rg_code(W);
-            }
-            code[slot] = (uint8_t)nc;
-        }
-        __syncwarp();
-        if (o.stats && lane == 0) {
-            const unsigned long long dt = (unsigned long long)(clock64() - t0);
-            atomicAdd(&o.stats[target * 4 + 0], 1ull);
-            atomicAdd(&o.stats[target * 4 + 1], (unsigned long long)nsel);
-            atomicAdd(&o.stats[target * 4 + 2], dt);
-            atomicMax(&o.stats[target * 4 + 3], dt);
-            const uint32_t bk = nsel >= 32 ? 5 : (nsel >= 16 ? 4 : (nsel >= 8 ? 3 : (nsel >= 4 ? 2 : (nsel >= 2 ? 1 : 0))));
-            atomicAdd(&o.stats[1024 + (target * 6 + bk) * 2 + 0], 1ull);
-            atomicAdd(&o.stats[1024 + (target * 6 + bk) * 2 + 1], dt);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// ht2_align_block_regroup_kernel: like the warp version, but the WHOLE block
-// agrees on one state per round, so every warp of the SM (one block per SM)
-// runs the same segment of code at the same time: one instruction stream in the
-// I-cache, several warps per scheduler to hide memory latency.
-// ---------------------------------------------------------------------------
-#define BRG_WARPS 8
-template <int RG_K>
-__global__ void __launch_bounds__(32 * BRG_WARPS)
-ht2_align_block_regroup_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
-{
-    constexpr int NT = 32 * BRG_WARPS;
-    constexpr int SLOTS = NT * RG_K;
-    __shared__ uint8_t  sCode[SLOTS];
-    __shared__ unsigned int sHist[RG_BINS];
-    __shared__ uint16_t sSel[NT];
-    __shared__ unsigned int sWarpCnt[RG_K][BRG_WARPS];
-    __shared__ unsigned int sTarget, sNsel;
-    const uint32_t t = threadIdx.x, lane = t & 31, wib = t >> 5;
-    Ht2Work* base = work + (size_t)blockIdx.x * SLOTS;
-    for (int j = 0; j < RG_K; j++) sCode[t + NT * j] = RG_NEED;
-    Ht2Aligner A;
-    A.bind(blob, &P, base);
-    A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
-#ifdef HT2_ENABLE_SPLICED
-    A.splT = b.splT;
-#endif
-    __syncthreads();
-    for (;;) {
-        if (t < RG_BINS) sHist[t] = 0;
-        __syncthreads();
-        for (int j = 0; j < RG_K; j++) {
-            uint32_t c = sCode[t + NT * j];
-            if (c != RG_EXIT) atomicAdd(&sHist[c], 1u);
-        }
-        __syncthreads();
-        if (wib == 0) {
-            uint32_t c0 = sHist[lane], c1 = sHist[lane + 32];
-            uint32_t best = c0 >= c1 ? ((c0 << 8) | lane) : ((c1 << 8) | (lane + 32));
-            for (int off = 16; off > 0; off >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best, off); best = v > best ? v : best; }
-            if (lane == 0) { sTarget = (best >> 8) ? (best & 0xff) : 0xffffffffu; sNsel = 0; }
-        }
-        __syncthreads();
-        const uint32_t target = sTarget;
-        if (target == 0xffffffffu) break;
-        // ---- block-wide gather of up to NT slots in the target state
-        bool m[RG_K];
-        for (int j = 0; j < RG_K; j++) {
-            m[j] = sCode[t + NT * j] == target;
-            uint32_t mask = __ballot_sync(0xffffffffu, m[j]);
-            if (lane == 0) sWarpCnt[j][wib] = __popc(mask);
-        }
-        __syncthreads();
-        {
-            uint32_t baseRank = 0;
-            for (int j = 0; j < RG_K; j++) {
-                uint32_t before = 0, total = 0;
-                for (int w = 0; w < BRG_WARPS; w++) { uint32_t c = sWarpCnt[j][w]; if (w < (int)wib) before += c; total += c; }
-                uint32_t mask = __ballot_sync(0xffffffffu, m[j]);
-                uint32_t rank = baseRank + before + __popc(mask & ((1u << lane) - 1));
-                if (m[j] && rank < NT) sSel[rank] = (uint16_t)(t + NT * j);
-                baseRank += total;
-            }
-            if (t == 0) sNsel = baseRank < NT ? baseRank : NT;
-        }
-        __syncthreads();
-        const uint32_t nsel = sNsel;
-        if (t < nsel) {
-            const uint32_t slot = sSel[t];
-            Ht2Work* W = base + slot;
-            uint32_t nc;
-            if (target == RG_NEED) {
-                uint32_t u = atomicAdd(&o.counters[3], 1u);
-                if (u >= b.n_units) nc = RG_EXIT;
-                else {
-                    A.W = W;
-                    uint32_t filtBits;
-                    bool run = ht2_setup_unit(A, P, b, u, filtBits);
-                    if (run) { while (!A.machineAtHeavyState()) A.machineStep(); }
-                    nc = run ? rg_code(W) : RG_FINISH;
-                }
-            } else if (target == RG_FINISH) {
-                ht2_finish_unit<1>(W, o, W->unit, W->filtBits, 0);
-                nc = RG_NEED;
-            } else {
-                A.attach(W);
-                A.machineRun();
-                nc = rg_code(W);
-            }
-            sCode[slot] = (uint8_t)nc;
-        }
-        __syncthreads();
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -696,8 +457,95 @@ ht2_seed_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, u
 }
 
 // ---------------------------------------------------------------------------
+// The SAM back end on the device (ht2_sam.h).  One thread formats one unit (read or pair):
+//   ht2_sam_kernel<false> : counting pass -- bytes of SAM text per unit (lens) and per block (blk)
+//   ht2_sam_scan_kernel   : exclusive scan of the block sums (one block), blk[nBlk] = total
+//   ht2_sam_kernel<true>  : writing pass -- unit offset = block offset + in-block exclusive scan of lens
+// Records land in read order (= --reorder), exactly the bytes AlnSinkWrap::finishRead prints.
+// ---------------------------------------------------------------------------
+#define HT2_SAM_TPB 128
+
+template <bool WRITE>
+__global__ void __launch_bounds__(HT2_SAM_TPB)
+ht2_sam_kernel(Ht2SamIn in, uint32_t units, uint32_t* __restrict__ lens, unsigned long long* __restrict__ blk, char* __restrict__ out,
+               unsigned long long cap, unsigned int* counters)
+{
+    __shared__ unsigned long long sWarp[HT2_SAM_TPB / 32];
+    const uint32_t u = blockIdx.x * HT2_SAM_TPB + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    Ht2SamFmt F;
+    F.bind(&in);
+    unsigned long long mine = 0;
+    if (!WRITE) {
+        if (u < units) {
+            Ht2SamOut<false> o; o.p = NULL; o.n = 0;
+            F.unit(o, u);
+            mine = o.n;
+            lens[u] = (uint32_t)o.n;
+            if (in.reads[u].err) atomicAdd(&counters[4], 1u);
+        }
+    } else mine = u < units ? lens[u] : 0;
+    // inclusive warp scan, then across the block's warps
+    unsigned long long incl = mine;
+    for (int off = 1; off < 32; off <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off); if ((int)lane >= off) incl += v; }
+    if (lane == 31) sWarp[wib] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (uint32_t w = 0; w < wib; w++) base += sWarp[w];
+    if (!WRITE) {
+        if (threadIdx.x == HT2_SAM_TPB - 1) blk[blockIdx.x] = base + incl;
+    } else if (u < units) {
+        const unsigned long long at = blk[blockIdx.x] + base + incl - mine;
+        if (at + mine <= cap) {
+            Ht2SamOut<true> o; o.p = out + at; o.n = 0;
+            F.unit(o, u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+ht2_sam_scan_kernel(unsigned long long* blk, uint32_t nBlk)
+{
+    __shared__ unsigned long long sPart[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (nBlk + 1023) / 1024;
+    const uint32_t lo = t * per, hi = lo + per < nBlk ? lo + per : nBlk;
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += blk[i];
+    sPart[t] = sum;
+    __syncthreads();
+    if (t == 0) { unsigned long long acc = 0; for (int i = 0; i < 1024; i++) { const unsigned long long v = sPart[i]; sPart[i] = acc; acc += v; } blk[nBlk] = acc; }
+    __syncthreads();
+    unsigned long long acc = sPart[t];
+    for (uint32_t i = lo; i < hi; i++) { const unsigned long long v = blk[i]; blk[i] = acc; acc += v; }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// One in-flight batch of the SAM path (ht2gpu_submit_sam / ht2gpu_wait_sam): its own stream, device input
+// buffers, device result pools, device SAM text and pinned host output, so that the H2D copy of batch i+1 and
+// the D2H copy of batch i-1 overlap the kernels of batch i.  The alignment workspaces (dWork) are shared by all
+// slots: kernels of different slots are chained through ht2gpu_handle::evCompute.
+#define HT2GPU_N_SLOTS 3
+struct SamSlot {
+    bool         init;
+    cudaStream_t stream;
+    cudaEvent_t  ev[6];            // start, h2d done, kernel start, align done, sam done, d2h done
+    uint8_t *dSeq, *dQual; uint64_t* dOffs; uint32_t* dSeeds; char* dNames; uint32_t* dNameOffs;
+    size_t capSeq, capQual, capOffs, capSeeds, capNames, capNameOffs;
+    ht2gpu_read_result_t* dReads; ht2gpu_aln_t* dAlns; ht2gpu_edit_t* dEdits; uint16_t* dPairs; unsigned int* dCounters;
+    size_t capUnits, capAlns, capEdits, capPairs;
+    uint32_t* dSamLen; size_t capSamLen;          // bytes of SAM text per unit
+    unsigned long long* dBlk; size_t capBlk;      // per-block sums, then exclusive block offsets; [nBlk] = total
+    char* dSam; size_t capSam;
+    char* hSam; size_t capHSam;                   // pinned
+    unsigned long long* hMeta;                    // pinned: [0] total SAM bytes, [1..4] result counters, [5] reads with errors
+    // the submitted batch (for a re-run after a pool overflow)
+    ht2gpu_read_batch_t batch; uint32_t units; size_t namesBytes; uint64_t h2dBytes; uint32_t nLaunch;
+    bool pending;
+};
+
 struct ht2gpu_handle {
     Ht2Image*      img;        // host copy (may hold only the header prefix when adopting a device image)
     uint8_t*       dBlob;
@@ -707,9 +555,8 @@ struct ht2gpu_handle {
     ht2gpu_options_t opt;
     int            device;
     int            nSM;
-    int            tpb, bpsm, lanes;
+    int            tpb, bpsm;
     bool           graph;
-    bool           regroup, blockRegroup, pool;
     int            poolWarps;
     int            rgK;
     Ht2Work*       dWork;
@@ -719,15 +566,11 @@ struct ht2gpu_handle {
     size_t         nWork;
     cudaStream_t   stream;
     cudaEvent_t    ev[4];
+    cudaEvent_t    evCompute;      // recorded after the last kernel that uses dWork / dSw
+    std::mutex     launchMu;       // [wait evCompute, launches, record evCompute] is one critical section
     std::string    err;
-    // device batch buffers (grown on demand)
-    uint8_t *dSeq, *dQual; uint64_t* dOffs; uint32_t* dSeeds;
-    size_t capBases, capReads;
-    // device output buffers
-    ht2gpu_read_result_t* dReads; ht2gpu_aln_t* dAlns; ht2gpu_edit_t* dEdits; uint16_t* dPairs; unsigned int* dCounters;
-    size_t capUnits, capAlns, capEdits, capPairs;
-    unsigned long long* dStats;   // HT2GPU_STATS=1: per-state round statistics of the regroup kernel
-    // host staging for filters
+    unsigned long long* dStats;   // HT2GPU_STATS=1: per-state round statistics of the pool kernel
+    SamSlot        slots[HT2GPU_N_SLOTS];
 };
 
 // Results live in ONE pinned host buffer per batch (D2H at PCIe speed instead of
@@ -802,6 +645,7 @@ static int finishOpen(ht2gpu_handle* h)
 {
     const Ht2ImageHeader* H = h->img->header();
     if (H->magic != HT2_MAGIC || H->version != HT2_IMAGE_VERSION) { h->err = "bad index image"; return HT2GPU_ERR_INDEX; }
+    if (H->totalBytes != h->blobBytes) { h->err = "index image is truncated (header.totalBytes differs from the bytes given)"; return HT2GPU_ERR_INDEX; }
 #ifndef HT2_ENABLE_SPLICED
     if (!h->opt.no_spliced_alignment) { h->err = "spliced alignment is not implemented in this build; pass --no-spliced-alignment"; return HT2GPU_ERR_UNSUPPORTED; }
 #else
@@ -818,47 +662,39 @@ static int finishOpen(ht2gpu_handle* h)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->nSM = prop.multiProcessorCount;
-    h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 128;
-    if (h->tpb > 128) h->tpb = 128;
-    h->bpsm = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 4;
-    h->lanes = h->opt.warp_per_read == 1 ? 32 : 1;
-    h->regroup = (h->opt.warp_per_read == 2);
-    if (h->opt.warp_per_read == 3) h->regroup = false; // 3 = plain one-lane-per-read dispatcher
-    h->blockRegroup = (h->opt.warp_per_read == 4);
-    h->pool = (h->opt.warp_per_read == 5 || h->opt.warp_per_read == 0);   // default
-    if (h->graph) {   // graph indexes run the pool kernel <8,4> only
-        h->pool = true; h->blockRegroup = false; h->regroup = true; h->lanes = 1;
-        h->opt.threads_per_block = 256; h->opt.slots_per_lane = 4;
-    }
-    if (h->blockRegroup || h->pool) h->regroup = true;
-    if (h->regroup) {
-        h->tpb = h->opt.threads_per_block > 0 ? h->opt.threads_per_block : 32 * RG_WARPS;
-        if (h->tpb > 32 * RG_WARPS) h->tpb = 32 * RG_WARPS;
-        h->tpb = (h->tpb / 32) * 32; if (h->tpb < 32) h->tpb = 32;
-        h->bpsm = h->opt.blocks_per_sm > 0 ? h->opt.blocks_per_sm : 1;
-        h->rgK = h->opt.slots_per_lane > 0 ? h->opt.slots_per_lane : 4;
-        if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8 && h->rgK != 16) h->rgK = 4;
-        if (h->blockRegroup) h->tpb = 32 * BRG_WARPS;
-        if (h->pool) {
-            h->poolWarps = (h->opt.threads_per_block >= 512) ? 16 : 8;
-            h->tpb = 32 * h->poolWarps;
-            if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8) h->rgK = 4;
-            if (h->opt.blocks_per_sm <= 0) h->bpsm = 1;
-        }
-        h->nWork = (size_t)h->nSM * h->bpsm * (h->tpb / 32) * 32 * h->rgK;
-    } else
-    h->nWork = (size_t)h->nSM * h->bpsm * h->tpb / h->lanes;
+    // the pool kernel: one block of poolWarps warps per SM, rgK read slots per lane
+    h->poolWarps = (h->opt.threads_per_block >= 512 && !h->graph) ? 16 : 8;
+    h->tpb = 32 * h->poolWarps;
+    h->bpsm = (h->opt.blocks_per_sm > 0 && !h->graph) ? h->opt.blocks_per_sm : 1;
+    h->rgK = (h->opt.slots_per_lane > 0 && !h->graph) ? h->opt.slots_per_lane : 4;
+    if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8) h->rgK = 4;
+    if (h->poolWarps == 16 && h->rgK == 8) h->rgK = 4;
+    h->nWork = (size_t)h->nSM * h->bpsm * h->poolWarps * 32 * h->rgK;
     CK(cudaMalloc(&h->dMinsc, sizeof(h->P.minscTab)));
     CK(cudaMemcpy(h->dMinsc, h->P.minscTab, sizeof(h->P.minscTab), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->dWork, h->nWork * sizeof(Ht2Work)));
     CK(cudaMemset(h->dWork, 0, h->nWork * sizeof(Ht2Work)));
     if (h->P.bowtie2Dp) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
-        size_t nThreads = h->regroup ? (size_t)h->nSM * h->bpsm * (size_t)(h->tpb > 256 ? h->tpb : 256) : h->nWork * h->lanes;
+        size_t nThreads = (size_t)h->nSM * h->bpsm * (size_t)h->tpb;
         CK(cudaMalloc(&h->dSw, nThreads * sizeof(Ht2SwScratch)));
     }
-    CK(cudaDeviceSetLimit(cudaLimitStackSize, 40 * 1024));
+    {   // per-thread stack: what the kernels of this index type need, not a blanket value (the limit is
+        // context-wide and the driver backs it for every resident thread).  Linear indexes have a statically
+        // known call tree; graph indexes recurse through alignWithALTs (ht2_alt.h, depth <= HT2_ALT_MAXDEP).
+        size_t need = 0;
+        cudaFuncAttributes fa;
+        if (h->graph) { CK(cudaFuncGetAttributes(&fa, ht2_align_pool_kernel<8, 4, true>)); need = fa.localSizeBytes + 36 * 1024; }
+        else { CK(cudaFuncGetAttributes(&fa, ht2_align_pool_kernel<8, 4, false>)); need = fa.localSizeBytes + 4 * 1024; }
+        CK(cudaFuncGetAttributes(&fa, ht2_sam_kernel<true>));
+        if (fa.localSizeBytes + 2048 > need) need = fa.localSizeBytes + 2048;
+        size_t cur = 0;
+        CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        if (cur < need) CK(cudaDeviceSetLimit(cudaLimitStackSize, need));
+    }
     CK(cudaStreamCreate(&h->stream));
     for (int i = 0; i < 4; i++) CK(cudaEventCreate(&h->ev[i]));
+    CK(cudaEventCreateWithFlags(&h->evCompute, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->evCompute, h->stream));
     return HT2GPU_OK;
 }
 
@@ -866,10 +702,9 @@ static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
     h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL; h->dMinsc = NULL; h->dSplT = NULL;
-    h->stream = 0;
-    h->dSeq = h->dQual = NULL; h->dOffs = NULL; h->dSeeds = NULL; h->capBases = h->capReads = 0;
-    h->dReads = NULL; h->dAlns = NULL; h->dEdits = NULL; h->dPairs = NULL; h->dCounters = NULL; h->dStats = NULL;
-    h->capUnits = h->capAlns = h->capEdits = h->capPairs = 0;
+    h->stream = 0; h->evCompute = 0;
+    h->dStats = NULL;
+    memset((void*)h->slots, 0, sizeof(h->slots));
     if (opt) h->opt = *opt; else ht2gpu_default_options(&h->opt);
     h->device = h->opt.device;
     return h;
@@ -969,8 +804,20 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     if (h->dSw) cudaFree(h->dSw);
     if (h->dMinsc) cudaFree(h->dMinsc);
     if (h->dSplT) cudaFree(h->dSplT);
-    cudaFree(h->dSeq); cudaFree(h->dQual); cudaFree(h->dOffs); cudaFree(h->dSeeds);
-    cudaFree(h->dReads); cudaFree(h->dAlns); cudaFree(h->dEdits); cudaFree(h->dPairs); cudaFree(h->dCounters); cudaFree(h->dStats);
+    cudaFree(h->dStats);
+    for (int k = 0; k < HT2GPU_N_SLOTS; k++) {
+        SamSlot& S = h->slots[k];
+        if (!S.init) continue;
+        cudaStreamSynchronize(S.stream);
+        cudaFree(S.dSeq); cudaFree(S.dQual); cudaFree(S.dOffs); cudaFree(S.dSeeds); cudaFree(S.dNames); cudaFree(S.dNameOffs);
+        cudaFree(S.dReads); cudaFree(S.dAlns); cudaFree(S.dEdits); cudaFree(S.dPairs); cudaFree(S.dCounters);
+        cudaFree(S.dSamLen); cudaFree(S.dBlk); cudaFree(S.dSam);
+        if (S.hSam) cudaFreeHost(S.hSam);
+        if (S.hMeta) cudaFreeHost(S.hMeta);
+        cudaStreamDestroy(S.stream);
+        for (int i = 0; i < 6; i++) cudaEventDestroy(S.ev[i]);
+    }
+    if (h->evCompute) cudaEventDestroy(h->evCompute);
     if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
     delete h->img;
     delete h;
@@ -998,38 +845,50 @@ static cudaError_t growBuf(T*& p, size_t& cap, size_t need, size_t slackNum = 5,
     return e;
 }
 
-// Stage a batch: H2D copies only (the per-read filters run on the device, ht2_dev_filter).
-static int uploadBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint64_t& h2dBytes)
+static int slotInit(ht2gpu_handle* h, SamSlot& S)
 {
-    const uint32_t n = b->n_reads;
-    const uint64_t nb = b->offs[n];
-    // sequence / quality / offsets / seeds share capBases / capReads growth
-    {
-        size_t c1 = h->capBases, c2 = h->capBases;
-        CK(growBuf(h->dSeq, c1, nb));
-        if (b->qual) { CK(growBuf(h->dQual, c2, nb)); }
-        h->capBases = c1;
-        size_t r1 = h->capReads, r2 = h->capReads;
-        CK(growBuf(h->dOffs, r1, (size_t)n + 1));
-        CK(growBuf(h->dSeeds, r2, (size_t)n + 1));
-        h->capReads = r1;
-    }
-    CK(cudaMemcpyAsync(h->dSeq, b->seq, nb, cudaMemcpyHostToDevice, h->stream));
-    if (b->qual) CK(cudaMemcpyAsync(h->dQual, b->qual, nb, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->dOffs, b->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->dSeeds, b->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    h2dBytes = nb * (b->qual ? 2 : 1) + ((size_t)n + 1) * 8 + (size_t)n * 4;
+    if (S.init) return HT2GPU_OK;
+    CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++) CK(cudaEventCreate(&S.ev[i]));
+    CK(cudaMalloc(&S.dCounters, 8 * sizeof(unsigned int)));
+    CK(cudaHostAlloc(&S.hMeta, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    S.init = true;
     return HT2GPU_OK;
 }
 
-static int ensureOut(ht2gpu_handle* h, uint32_t units, size_t alns, size_t edits, size_t pairs)
+// Stage a batch in a slot: H2D copies only (the per-read filters run on the device, ht2_dev_filter).
+// Every buffer has its own capacity (a FASTA batch leaves dQual untouched).
+static int uploadBatch(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* b, const char* names, const uint32_t* nameOffs,
+                       size_t namesBytes, uint64_t& h2dBytes)
 {
-    CK(growBuf(h->dReads, h->capUnits, units));
-    CK(growBuf(h->dAlns, h->capAlns, alns));
-    CK(growBuf(h->dEdits, h->capEdits, edits));
-    size_t pc = h->capPairs * 2, need = pairs * 2;
-    if (need > pc || !h->dPairs) { CK(growBuf(h->dPairs, pc, need)); h->capPairs = pc / 2; }
-    if (!h->dCounters) CK(cudaMalloc(&h->dCounters, 4 * sizeof(unsigned int)));
+    const uint32_t n = b->n_reads;
+    const uint64_t nb = b->offs[n];
+    CK(growBuf(S.dSeq, S.capSeq, nb + 8));
+    if (b->qual) CK(growBuf(S.dQual, S.capQual, nb + 8));
+    CK(growBuf(S.dOffs, S.capOffs, (size_t)n + 1));
+    CK(growBuf(S.dSeeds, S.capSeeds, (size_t)n + 1));
+    CK(cudaMemcpyAsync(S.dSeq, b->seq, nb, cudaMemcpyHostToDevice, S.stream));
+    if (b->qual) CK(cudaMemcpyAsync(S.dQual, b->qual, nb, cudaMemcpyHostToDevice, S.stream));
+    CK(cudaMemcpyAsync(S.dOffs, b->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, S.stream));
+    CK(cudaMemcpyAsync(S.dSeeds, b->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, S.stream));
+    h2dBytes = nb * (b->qual ? 2 : 1) + ((size_t)n + 1) * 8 + (size_t)n * 4;
+    if (names) {
+        CK(growBuf(S.dNames, S.capNames, namesBytes + 8));
+        CK(growBuf(S.dNameOffs, S.capNameOffs, (size_t)n + 1));
+        CK(cudaMemcpyAsync(S.dNames, names, namesBytes, cudaMemcpyHostToDevice, S.stream));
+        CK(cudaMemcpyAsync(S.dNameOffs, nameOffs, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, S.stream));
+        h2dBytes += namesBytes + ((size_t)n + 1) * 4;
+    }
+    return HT2GPU_OK;
+}
+
+static int ensureOut(ht2gpu_handle* h, SamSlot& S, uint32_t units, size_t alns, size_t edits, size_t pairs)
+{
+    CK(growBuf(S.dReads, S.capUnits, units));
+    CK(growBuf(S.dAlns, S.capAlns, alns));
+    CK(growBuf(S.dEdits, S.capEdits, edits));
+    size_t pc = S.capPairs * 2, need = pairs * 2;
+    if (need > pc || !S.dPairs) { CK(growBuf(S.dPairs, pc, need)); S.capPairs = pc / 2; }
     if (!h->dStats && getenv("HT2GPU_STATS")) {
         CK(cudaMalloc(&h->dStats, (1024 + 256 * 12) * sizeof(unsigned long long)));
         CK(cudaMemset(h->dStats, 0, (1024 + 256 * 12) * sizeof(unsigned long long)));
@@ -1037,68 +896,38 @@ static int ensureOut(ht2gpu_handle* h, uint32_t units, size_t alns, size_t edits
     return HT2GPU_OK;
 }
 
-static int launch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, uint32_t units)
+// Enqueue the alignment kernel of the slot's batch on the slot's stream.  The caller holds h->launchMu and has
+// made the stream wait for h->evCompute (the workspaces are shared by all slots).
+static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* b, uint32_t units)
 {
     DevBatch db;
-    db.seq = h->dSeq; db.qual = b->qual ? h->dQual : NULL; db.offs = h->dOffs; db.seeds = h->dSeeds;
+    db.seq = S.dSeq; db.qual = b->qual ? S.dQual : NULL; db.offs = S.dOffs; db.seeds = S.dSeeds;
     db.n_units = units; db.paired = b->paired; db.sw = h->dSw; db.minscTab = h->dMinsc;
 #ifdef HT2_ENABLE_SPLICED
     db.splT = (const Ht2SplTables*)h->dSplT;
 #endif
     DevOut o;
-    o.reads = h->dReads; o.alns = h->dAlns; o.edits = h->dEdits; o.pairs = h->dPairs;
-    o.capAlns = (uint32_t)h->capAlns; o.capEdits = (uint32_t)h->capEdits; o.capPairs = (uint32_t)h->capPairs;
-    o.counters = h->dCounters;
+    o.reads = S.dReads; o.alns = S.dAlns; o.edits = S.dEdits; o.pairs = S.dPairs;
+    o.capAlns = (uint32_t)S.capAlns; o.capEdits = (uint32_t)S.capEdits; o.capPairs = (uint32_t)S.capPairs;
+    o.counters = S.dCounters;
     o.stats = h->dStats;
-    CK(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned int), h->stream));
-    if (h->regroup) {
-        uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
-        if (h->graph) {     // graph (SNP) indexes: the pool kernel with the ALT-aware aligner
-            ht2_align_pool_kernel<8, 4, true><<<grid, 256, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
-            CK(cudaGetLastError());
-            return HT2GPU_OK;
+    CK(cudaMemsetAsync(S.dCounters, 0, 8 * sizeof(unsigned int), S.stream));
+    const uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
+    if (h->graph) ht2_align_pool_kernel<8, 4, true><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
+    else {
+        switch (h->poolWarps * 100 + h->rgK) {
+            case 802:  ht2_align_pool_kernel<8, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 808:  ht2_align_pool_kernel<8, 8, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 1602: ht2_align_pool_kernel<16, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 1604: ht2_align_pool_kernel<16, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            default:   ht2_align_pool_kernel<8, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
         }
-        if (h->pool) {
-            const int key = h->poolWarps * 100 + h->rgK;
-            switch (key) {
-                case 802:  ht2_align_pool_kernel<8, 2, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                case 808:  ht2_align_pool_kernel<8, 8, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                case 1602: ht2_align_pool_kernel<16, 2, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                case 1604: ht2_align_pool_kernel<16, 4, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                default:   ht2_align_pool_kernel<8, 4, false><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            }
-            CK(cudaGetLastError());
-            return HT2GPU_OK;
-        }
-        if (h->blockRegroup) {
-            switch (h->rgK) {
-                case 2:  ht2_align_block_regroup_kernel<2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                case 8:  ht2_align_block_regroup_kernel<8><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-                default: ht2_align_block_regroup_kernel<4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            }
-            CK(cudaGetLastError());
-            return HT2GPU_OK;
-        }
-        switch (h->rgK) {
-            case 2:  ht2_align_regroup_kernel<2><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 8:  ht2_align_regroup_kernel<8><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 16: ht2_align_regroup_kernel<16><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            default: ht2_align_regroup_kernel<4><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-        }
-        CK(cudaGetLastError());
-        return HT2GPU_OK;
     }
-    uint32_t perBlock = (uint32_t)(h->tpb / h->lanes);
-    uint32_t grid = (uint32_t)(h->nWork / perBlock);
-    uint32_t needBlocks = (units + perBlock - 1) / perBlock;
-    if (needBlocks < grid) grid = needBlocks ? needBlocks : 1;
-    if (h->lanes == 32) ht2_align_kernel<32><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
-    else ht2_align_kernel<1><<<grid, h->tpb, 0, h->stream>>>(h->dBlob, h->P, db, o, h->dWork);
     CK(cudaGetLastError());
     return HT2GPU_OK;
 }
 
-// HT2GPU_STATS=1: per-state statistics of the regroup kernel's rounds (investigation aid).
+// HT2GPU_STATS=1: per-state statistics of the pool kernel's rounds (investigation aid).
 static void dumpStats(ht2gpu_handle* h)
 {
     static const char* topN[] = {"START", "NEXTBWT", "PS", "ALIGN", "HYB_EXTEND", "HYB_PICK", "HYB_RET", "POST_ALIGN", "AFTER_LOOP",
@@ -1131,37 +960,53 @@ static void dumpStats(ht2gpu_handle* h)
     }
 }
 
-static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, ht2gpu_result_batch_t* res, bool timeCopies)
+static int checkBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b)
 {
-    if (!h || !b || !res) return HT2GPU_ERR_ARG;
     if (b->paired && (b->n_reads & 1)) { h->err = "paired batch needs an even number of reads"; return HT2GPU_ERR_ARG; }
-    memset(res, 0, sizeof(*res));
     if (h->graph && h->img->header()->altsUnsupported) {
         h->err = "this graph index holds splice-site / exon ALTs; alignment through them is not implemented in this build "
                  "(SNP / indel ALTs are; ht2gpu_seed_search works on any graph index)";
         return HT2GPU_ERR_UNSUPPORTED;
     }
+    return HT2GPU_OK;
+}
+
+// Structured results (ht2gpu_align_batch / ht2gpu_align_resident): slot 0.
+static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, ht2gpu_result_batch_t* res)
+{
+    if (!h || !b || !res) return HT2GPU_ERR_ARG;
+    memset(res, 0, sizeof(*res));
+    int rc = checkBatch(h, b);
+    if (rc) return rc;
     if (b->n_reads == 0) return HT2GPU_OK;
     CK(cudaSetDevice(h->device));
+    SamSlot& S = h->slots[0];
+    rc = slotInit(h, S);
+    if (rc) return rc;
     const uint32_t units = b->paired ? b->n_reads / 2 : b->n_reads;
     uint64_t h2d = 0;
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    int rc = uploadBatch(h, b, h2d);
+    CK(cudaEventRecord(S.ev[0], S.stream));
+    rc = uploadBatch(h, S, b, NULL, NULL, 0, h2d);
     if (rc) return rc;
     size_t capA = (size_t)b->n_reads * 2 + 1024, capE = (size_t)b->n_reads * 4 + 4096, capP = (size_t)units * 2 + 1024;
     unsigned int counters[4] = {0, 0, 0, 0};
     float msKernel = 0;
     uint32_t nLaunch = 0;
     for (int attempt = 0; attempt < 4; attempt++) {
-        rc = ensureOut(h, units, capA, capE, capP);
+        rc = ensureOut(h, S, units, capA, capE, capP);
         if (rc) return rc;
-        CK(cudaEventRecord(h->ev[1], h->stream));
-        for (int it = 0; it < iters; it++) { rc = launch(h, b, units); if (rc) return rc; nLaunch++; }
-        CK(cudaEventRecord(h->ev[2], h->stream));
-        CK(cudaMemcpyAsync(counters, h->dCounters, sizeof(counters), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        CK(cudaEventElapsedTime(&msKernel, h->ev[1], h->ev[2]));
-        if (counters[0] <= h->capAlns && counters[1] <= h->capEdits && counters[2] <= h->capPairs) break;
+        {
+            std::lock_guard<std::mutex> lk(h->launchMu);
+            CK(cudaStreamWaitEvent(S.stream, h->evCompute, 0));
+            CK(cudaEventRecord(S.ev[1], S.stream));
+            for (int it = 0; it < iters; it++) { rc = launchAlign(h, S, b, units); if (rc) return rc; nLaunch++; }
+            CK(cudaEventRecord(S.ev[2], S.stream));
+            CK(cudaEventRecord(h->evCompute, S.stream));
+        }
+        CK(cudaMemcpyAsync(counters, S.dCounters, sizeof(counters), cudaMemcpyDeviceToHost, S.stream));
+        CK(cudaStreamSynchronize(S.stream));
+        CK(cudaEventElapsedTime(&msKernel, S.ev[1], S.ev[2]));
+        if (counters[0] <= S.capAlns && counters[1] <= S.capEdits && counters[2] <= S.capPairs) break;
         // result pools were too small: grow and re-run (results are deterministic)
         capA = counters[0] + 1024; capE = counters[1] + 4096; capP = counters[2] + 1024;
     }
@@ -1171,20 +1016,21 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
                  szE = up((size_t)counters[1] * sizeof(ht2gpu_edit_t)), szP = up((size_t)counters[2] * 4);
     ResPriv* pv = new ResPriv();
     if (!pinnedGet(szR + szA + szE + szP + 64, *pv)) { delete pv; h->err = "cudaHostAlloc failed for the result batch"; return HT2GPU_ERR_CUDA; }
+    res->priv = pv;   // from here on ht2gpu_free_results returns the buffer, also on error paths
     uint8_t* hb = (uint8_t*)pv->buf;
     ht2gpu_read_result_t* hReads = (ht2gpu_read_result_t*)hb;
     ht2gpu_aln_t* hAlns = (ht2gpu_aln_t*)(hb + szR);
     ht2gpu_edit_t* hEdits = (ht2gpu_edit_t*)(hb + szR + szA);
     uint16_t* hPairs = (uint16_t*)(hb + szR + szA + szE);
-    CK(cudaMemcpyAsync(hReads, h->dReads, (size_t)units * sizeof(ht2gpu_read_result_t), cudaMemcpyDeviceToHost, h->stream));
-    if (counters[0]) CK(cudaMemcpyAsync(hAlns, h->dAlns, (size_t)counters[0] * sizeof(ht2gpu_aln_t), cudaMemcpyDeviceToHost, h->stream));
-    if (counters[1]) CK(cudaMemcpyAsync(hEdits, h->dEdits, (size_t)counters[1] * sizeof(ht2gpu_edit_t), cudaMemcpyDeviceToHost, h->stream));
-    if (counters[2]) CK(cudaMemcpyAsync(hPairs, h->dPairs, (size_t)counters[2] * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(hReads, S.dReads, (size_t)units * sizeof(ht2gpu_read_result_t), cudaMemcpyDeviceToHost, S.stream));
+    if (counters[0]) CK(cudaMemcpyAsync(hAlns, S.dAlns, (size_t)counters[0] * sizeof(ht2gpu_aln_t), cudaMemcpyDeviceToHost, S.stream));
+    if (counters[1]) CK(cudaMemcpyAsync(hEdits, S.dEdits, (size_t)counters[1] * sizeof(ht2gpu_edit_t), cudaMemcpyDeviceToHost, S.stream));
+    if (counters[2]) CK(cudaMemcpyAsync(hPairs, S.dPairs, (size_t)counters[2] * 4, cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaEventRecord(S.ev[3], S.stream));
+    CK(cudaStreamSynchronize(S.stream));
     float msH2d = 0, msD2h = 0;
-    CK(cudaEventElapsedTime(&msH2d, h->ev[0], h->ev[1]));
-    CK(cudaEventElapsedTime(&msD2h, h->ev[2], h->ev[3]));
+    CK(cudaEventElapsedTime(&msH2d, S.ev[0], S.ev[1]));
+    CK(cudaEventElapsedTime(&msD2h, S.ev[2], S.ev[3]));
     res->n_reads = units; res->reads = hReads;
     res->n_alns = counters[0]; res->alns = hAlns;
     res->n_edits = counters[1]; res->edits = hEdits;
@@ -1194,29 +1040,161 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
     res->d2h_bytes = (uint64_t)units * sizeof(ht2gpu_read_result_t) + (uint64_t)counters[0] * sizeof(ht2gpu_aln_t) +
                      (uint64_t)counters[1] * sizeof(ht2gpu_edit_t) + (uint64_t)counters[2] * 4 + sizeof(counters);
     res->n_launches = nLaunch;
-    res->priv = pv;
-    (void)timeCopies;
-    uint32_t anyErr = 0;
-    for (uint32_t i = 0; i < units; i++) anyErr |= hReads[i].err;
-    if (anyErr) {
-        char buf[128]; snprintf(buf, sizeof(buf), "device capacity exceeded for some reads (err bits 0x%x)", anyErr);
+    // Reads that exceeded a device-side capacity are flagged in reads[i].err and counted; the batch itself succeeds
+    // (the reference has no such limits: a caller that needs byte parity must treat flagged reads as failed).
+    uint32_t nErr = 0, anyErr = 0;
+    for (uint32_t i = 0; i < units; i++) if (hReads[i].err) { nErr++; anyErr |= hReads[i].err; }
+    res->n_err_reads = nErr;
+    if (nErr) {
+        char buf[160]; snprintf(buf, sizeof(buf), "device capacity exceeded for %u read(s) (err bits 0x%x); see reads[i].err", nErr, anyErr);
         h->err = buf;
-        return HT2GPU_ERR_CAPACITY;
     }
     return HT2GPU_OK;
 }
 
 extern "C" int ht2gpu_align_batch(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, ht2gpu_result_batch_t* res)
 {
-    return runBatch(h, b, 1, res, true);
+    return runBatch(h, b, 1, res);
 }
 extern "C" int ht2gpu_align_resident(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, int iters, ht2gpu_result_batch_t* res)
 {
-    return runBatch(h, b, iters < 1 ? 1 : iters, res, false);
+    return runBatch(h, b, iters < 1 ? 1 : iters, res);
 }
 extern "C" void ht2gpu_free_results(ht2gpu_result_batch_t* res)
 {
     if (res && res->priv) { ResPriv* pv = (ResPriv*)res->priv; pinnedPut(*pv); delete pv; res->priv = NULL; }
+}
+
+// ---------------------------------------------------------------------------
+// SAM on the device: align + finishRead for a batch, text back in pinned host memory
+// ---------------------------------------------------------------------------
+static Ht2SamIn samIn(const ht2gpu_handle* h, const SamSlot& S)
+{
+    Ht2SamIn in;
+    in.blob = h->dBlob; in.minscTab = h->dMinsc;
+    in.seq = S.dSeq; in.qual = S.batch.qual ? S.dQual : NULL; in.offs = S.dOffs; in.names = S.dNames; in.nameOffs = S.dNameOffs;
+    in.n_reads = S.batch.n_reads; in.paired = S.batch.paired;
+    in.reads = S.dReads; in.alns = S.dAlns; in.edits = S.dEdits; in.pairs = S.dPairs;
+    in.khits = h->P.khits; in.secondary = h->P.secondary; in.mixed = h->P.mixed; in.discord = h->P.discord;
+    return in;
+}
+
+// Enqueue [align, SAM count, block scan, SAM write] for the slot's uploaded batch.  withAlign = false re-runs
+// only the SAM kernels (after the text buffer was grown).
+static int enqueueKernels(ht2gpu_handle* h, SamSlot& S, bool withAlign)
+{
+    const uint32_t units = S.units;
+    const uint32_t nBlk = (units + HT2_SAM_TPB - 1) / HT2_SAM_TPB;
+    CK(growBuf(S.dSamLen, S.capSamLen, units));
+    CK(growBuf(S.dBlk, S.capBlk, (size_t)nBlk + 2));
+    std::lock_guard<std::mutex> lk(h->launchMu);
+    CK(cudaStreamWaitEvent(S.stream, h->evCompute, 0));
+    CK(cudaEventRecord(S.ev[2], S.stream));
+    if (withAlign) { int rc = launchAlign(h, S, &S.batch, units); if (rc) return rc; S.nLaunch++; }
+    CK(cudaEventRecord(S.ev[3], S.stream));
+    const Ht2SamIn in = samIn(h, S);
+    ht2_sam_kernel<false><<<nBlk, HT2_SAM_TPB, 0, S.stream>>>(in, units, S.dSamLen, S.dBlk, NULL, 0, S.dCounters);
+    ht2_sam_scan_kernel<<<1, 1024, 0, S.stream>>>(S.dBlk, nBlk);
+    ht2_sam_kernel<true><<<nBlk, HT2_SAM_TPB, 0, S.stream>>>(in, units, S.dSamLen, S.dBlk, S.dSam, (unsigned long long)S.capSam, S.dCounters);
+    CK(cudaGetLastError());
+    S.nLaunch += 3;
+    CK(cudaEventRecord(S.ev[4], S.stream));
+    CK(cudaEventRecord(h->evCompute, S.stream));
+    // meta: total SAM bytes, result counters, reads with errors
+    CK(cudaMemcpyAsync(&S.hMeta[0], S.dBlk + nBlk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaMemcpyAsync(&S.hMeta[1], S.dCounters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
+    return HT2GPU_OK;
+}
+
+extern "C" int ht2gpu_sam_slots(const ht2gpu_handle_t*) { return HT2GPU_N_SLOTS; }
+extern "C" void* ht2gpu_host_alloc(size_t bytes) { void* p = NULL; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : NULL; }
+extern "C" void ht2gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void ht2gpu_set_error(ht2gpu_handle_t* h, const char* msg) { if (h) h->err = msg ? msg : ""; }
+
+extern "C" int ht2gpu_submit_sam(ht2gpu_handle_t* h, int slot, const ht2gpu_read_batch_t* b, const char* names,
+                                 const uint32_t* name_offs, size_t names_bytes)
+{
+    if (!h || !b || slot < 0 || slot >= HT2GPU_N_SLOTS || (b->n_reads && (!names || !name_offs))) return HT2GPU_ERR_ARG;
+    int rc = checkBatch(h, b);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    SamSlot& S = h->slots[slot];
+    rc = slotInit(h, S);
+    if (rc) return rc;
+    if (S.pending) { h->err = "ht2gpu_submit_sam: the slot still holds a batch (call ht2gpu_wait_sam first)"; return HT2GPU_ERR_ARG; }
+    S.batch = *b; S.units = b->paired ? b->n_reads / 2 : b->n_reads; S.namesBytes = names_bytes; S.nLaunch = 0; S.h2dBytes = 0;
+    S.pending = true;
+    if (b->n_reads == 0) return HT2GPU_OK;
+    CK(cudaEventRecord(S.ev[0], S.stream));
+    rc = uploadBatch(h, S, b, names, name_offs, names_bytes, S.h2dBytes);
+    if (rc) return rc;
+    CK(cudaEventRecord(S.ev[1], S.stream));
+    rc = ensureOut(h, S, S.units, (size_t)b->n_reads * 2 + 1024, (size_t)b->n_reads * 4 + 4096, (size_t)S.units * 2 + 1024);
+    if (rc) return rc;
+    // SAM text: ~2.2 bytes per base + ~170 per record at one record per read; grown from the measured size if short
+    const size_t est = (size_t)((double)b->offs[b->n_reads] * 2.6) + (size_t)b->n_reads * 260 + names_bytes + 4096;
+    if (est > S.capSam) CK(growBuf(S.dSam, S.capSam, est, 1, 1));
+    return enqueueKernels(h, S, true);
+}
+
+extern "C" int ht2gpu_wait_sam(ht2gpu_handle_t* h, int slot, ht2gpu_sam_result_t* out)
+{
+    if (!h || !out || slot < 0 || slot >= HT2GPU_N_SLOTS) return HT2GPU_ERR_ARG;
+    SamSlot& S = h->slots[slot];
+    memset(out, 0, sizeof(*out));
+    if (!S.init || !S.pending) { h->err = "ht2gpu_wait_sam: nothing was submitted on this slot"; return HT2GPU_ERR_ARG; }
+    S.pending = false;
+    out->n_units = S.units;
+    if (S.batch.n_reads == 0) { out->sam = S.hSam ? S.hSam : (char*)""; return HT2GPU_OK; }
+    CK(cudaSetDevice(h->device));
+    for (int attempt = 0; ; attempt++) {
+        CK(cudaStreamSynchronize(S.stream));
+        const unsigned int* c = (const unsigned int*)&S.hMeta[1];
+        const bool poolsOk = c[0] <= S.capAlns && c[1] <= S.capEdits && c[2] <= S.capPairs;
+        const bool textOk = S.hMeta[0] <= S.capSam;
+        if (poolsOk && textOk) break;
+        if (attempt >= 3) { h->err = "ht2gpu_wait_sam: result pools still too small after three re-runs"; return HT2GPU_ERR_CUDA; }
+        // a pool was too small: grow it and re-run (results are deterministic); rare, sizes are kept afterwards
+        if (!poolsOk) { int rc = ensureOut(h, S, S.units, (size_t)c[0] + 1024, (size_t)c[1] + 4096, (size_t)c[2] + 1024); if (rc) return rc; }
+        if (!textOk) CK(growBuf(S.dSam, S.capSam, (size_t)S.hMeta[0] + 4096, 9, 8));
+        int rc = enqueueKernels(h, S, !poolsOk);
+        if (rc) return rc;
+    }
+    const size_t total = (size_t)S.hMeta[0];
+    if (total + 1 > S.capHSam) {
+        if (S.hSam) cudaFreeHost(S.hSam);
+        S.hSam = NULL; S.capHSam = 0;
+        const size_t cap = total + total / 8 + 4096;
+        CK(cudaHostAlloc(&S.hSam, cap, cudaHostAllocDefault));
+        S.capHSam = cap;
+    }
+    CK(cudaMemcpyAsync(S.hSam, S.dSam, total, cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaEventRecord(S.ev[5], S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    S.hSam[total] = 0;
+    if (h->dStats) dumpStats(h);
+    const unsigned int* c = (const unsigned int*)&S.hMeta[1];
+    out->sam = S.hSam; out->sam_len = total;
+    out->n_alns = c[0]; out->n_err_reads = c[4];
+    CK(cudaEventElapsedTime(&out->ms_h2d, S.ev[0], S.ev[1]));
+    CK(cudaEventElapsedTime(&out->ms_align, S.ev[2], S.ev[3]));
+    CK(cudaEventElapsedTime(&out->ms_sam, S.ev[3], S.ev[4]));
+    CK(cudaEventElapsedTime(&out->ms_d2h, S.ev[4], S.ev[5]));
+    out->h2d_bytes = S.h2dBytes; out->d2h_bytes = total + 9 * sizeof(unsigned long long);
+    out->n_launches = S.nLaunch;
+    if (c[4]) {
+        char buf[160]; snprintf(buf, sizeof(buf), "device capacity exceeded for %u read(s) of the batch; their SAM records are unreliable", c[4]);
+        h->err = buf;
+    }
+    return HT2GPU_OK;
+}
+
+extern "C" int ht2gpu_align_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, const char* names, const uint32_t* name_offs,
+                                size_t names_bytes, ht2gpu_sam_result_t* out)
+{
+    int rc = ht2gpu_submit_sam(h, 0, b, names, name_offs, names_bytes);
+    if (rc) { if (h && h->slots[0].init) h->slots[0].pending = false; return rc; }
+    return ht2gpu_wait_sam(h, 0, out);
 }
 
 // ---------------------------------------------------------------------------
@@ -1231,6 +1209,14 @@ struct SeedPriv {
 
 extern "C" int ht2gpu_index_is_graph(const ht2gpu_handle_t* h) { return h && h->graph ? 1 : 0; }
 
+namespace {
+struct DevTmp {   // temporaries of one ht2gpu_seed_search call: freed on every return path
+    std::vector<void*> ptrs;
+    template <typename T> cudaError_t alloc(T*& p, size_t bytes) { void* q = NULL; cudaError_t e = cudaMalloc(&q, bytes); if (e == cudaSuccess) ptrs.push_back(q); p = (T*)q; return e; }
+    ~DevTmp() { for (void* q : ptrs) cudaFree(q); }
+};
+}
+
 extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, uint32_t maxRange, ht2gpu_seed_result_t* res)
 {
     if (!h || !b || !res) return HT2GPU_ERR_ARG;
@@ -1243,36 +1229,40 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     res->first_hit = pv->firstHit.data();
     if (n == 0) return HT2GPU_OK;
     CK(cudaSetDevice(h->device));
+    SamSlot& S = h->slots[0];
+    int rc = slotInit(h, S);
+    if (rc) return rc;
     uint64_t h2d = 0;
-    int rc = uploadBatch(h, b, h2d);
+    rc = uploadBatch(h, S, b, NULL, NULL, 0, h2d);
     if (rc) return rc;
     DevBatch db;
-    db.seq = h->dSeq; db.qual = NULL; db.offs = h->dOffs; db.seeds = h->dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.minscTab = h->dMinsc;
+    db.seq = S.dSeq; db.qual = NULL; db.offs = S.dOffs; db.seeds = S.dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.minscTab = h->dMinsc;
 #ifdef HT2_ENABLE_SPLICED
     db.splT = NULL;
 #endif
+    DevTmp tmp;
     uint32_t *dCounts = NULL, *dOffs3 = NULL;
     unsigned long long* dTot = NULL;
     SeedOut so; memset(&so, 0, sizeof(so));
-    CK(cudaMalloc(&dCounts, (size_t)n * 12));
-    CK(cudaMalloc(&dOffs3, (size_t)n * 12));
-    CK(cudaMalloc(&dTot, 3 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(dTot, 0, 3 * sizeof(unsigned long long), h->stream));
+    CK(tmp.alloc(dCounts, (size_t)n * 12));
+    CK(tmp.alloc(dOffs3, (size_t)n * 12));
+    CK(tmp.alloc(dTot, 3 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(dTot, 0, 3 * sizeof(unsigned long long), S.stream));
     so.counts = dCounts; so.offs = dOffs3; so.totals = dTot;
     const int tpb = 128;
     int grid = (int)((n + tpb - 1) / tpb);
     const int maxGrid = h->nSM * 16;
     if (grid > maxGrid) grid = maxGrid;
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    if (h->graph) ht2_seed_kernel<true, false><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
-    else ht2_seed_kernel<false, false><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    CK(cudaEventRecord(S.ev[1], S.stream));
+    if (h->graph) ht2_seed_kernel<true, false><<<grid, tpb, 0, S.stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    else ht2_seed_kernel<false, false><<<grid, tpb, 0, S.stream>>>(h->dBlob, h->P, db, n, maxRange, so);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaEventRecord(S.ev[2], S.stream));
     std::vector<uint32_t> counts((size_t)n * 3), offs((size_t)n * 3);
-    CK(cudaMemcpyAsync(counts.data(), dCounts, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(counts.data(), dCounts, (size_t)n * 12, cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
     float ms0 = 0, ms1 = 0;
-    CK(cudaEventElapsedTime(&ms0, h->ev[1], h->ev[2]));
+    CK(cudaEventElapsedTime(&ms0, S.ev[1], S.ev[2]));
     uint64_t th = 0, te = 0, tc = 0;
     for (uint32_t i = 0; i < n; i++) {
         offs[3 * (size_t)i] = (uint32_t)th; offs[3 * (size_t)i + 1] = (uint32_t)te; offs[3 * (size_t)i + 2] = (uint32_t)tc;
@@ -1282,25 +1272,24 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     pv->firstHit[n] = (uint32_t)th;
     if (th > 0xfffffff0ull || tc > 0xfffffff0ull) { h->err = "seed search result too large for one batch"; return HT2GPU_ERR_CAPACITY; }
     ht2gpu_seed_hit_t* dHits = NULL; uint16_t* dIe = NULL; ht2gpu_seed_coord_t* dCo = NULL;
-    CK(cudaMalloc(&dHits, (th + 1) * sizeof(ht2gpu_seed_hit_t)));
-    CK(cudaMalloc(&dIe, (te + 1) * 4));
-    CK(cudaMalloc(&dCo, (tc + 1) * sizeof(ht2gpu_seed_coord_t)));
-    CK(cudaMemcpyAsync(dOffs3, offs.data(), (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+    CK(tmp.alloc(dHits, (th + 1) * sizeof(ht2gpu_seed_hit_t)));
+    CK(tmp.alloc(dIe, (te + 1) * 4));
+    CK(tmp.alloc(dCo, (tc + 1) * sizeof(ht2gpu_seed_coord_t)));
+    CK(cudaMemcpyAsync(dOffs3, offs.data(), (size_t)n * 12, cudaMemcpyHostToDevice, S.stream));
     so.hits = dHits; so.iedges = dIe; so.coords = dCo;
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    if (h->graph) ht2_seed_kernel<true, true><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
-    else ht2_seed_kernel<false, true><<<grid, tpb, 0, h->stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    CK(cudaEventRecord(S.ev[1], S.stream));
+    if (h->graph) ht2_seed_kernel<true, true><<<grid, tpb, 0, S.stream>>>(h->dBlob, h->P, db, n, maxRange, so);
+    else ht2_seed_kernel<false, true><<<grid, tpb, 0, S.stream>>>(h->dBlob, h->P, db, n, maxRange, so);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaEventRecord(S.ev[2], S.stream));
     pv->hits.resize(th); pv->iedges.resize(te * 2); pv->coords.resize(tc);
     unsigned long long tot[3] = {0, 0, 0};
-    if (th) CK(cudaMemcpyAsync(pv->hits.data(), dHits, th * sizeof(ht2gpu_seed_hit_t), cudaMemcpyDeviceToHost, h->stream));
-    if (te) CK(cudaMemcpyAsync(pv->iedges.data(), dIe, te * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (tc) CK(cudaMemcpyAsync(pv->coords.data(), dCo, tc * sizeof(ht2gpu_seed_coord_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(tot, dTot, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&ms1, h->ev[1], h->ev[2]));
-    cudaFree(dCounts); cudaFree(dOffs3); cudaFree(dTot); cudaFree(dHits); cudaFree(dIe); cudaFree(dCo);
+    if (th) CK(cudaMemcpyAsync(pv->hits.data(), dHits, th * sizeof(ht2gpu_seed_hit_t), cudaMemcpyDeviceToHost, S.stream));
+    if (te) CK(cudaMemcpyAsync(pv->iedges.data(), dIe, te * 4, cudaMemcpyDeviceToHost, S.stream));
+    if (tc) CK(cudaMemcpyAsync(pv->coords.data(), dCo, tc * sizeof(ht2gpu_seed_coord_t), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaMemcpyAsync(tot, dTot, sizeof(tot), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    CK(cudaEventElapsedTime(&ms1, S.ev[1], S.ev[2]));
     res->n_hits = (uint32_t)th; res->hits = pv->hits.data();
     res->n_iedges = (uint32_t)te; res->iedges = pv->iedges.data();
     res->n_coords = (uint32_t)tc; res->coords = pv->coords.data();

@@ -29,14 +29,6 @@ struct Ht2ReadFilters {
     bool pass() const { return nfilt && scfilt && lenfilt && qcfilt; }
 };
 
-// Everything the device returns for one read (pair).
-struct Ht2ReadOut {
-    std::vector<Ht2Res> res[2];
-    std::vector<std::pair<uint16_t, uint16_t> > pairs;
-    uint32_t rngLast;
-    uint32_t err;
-};
-
 void ht2_default_params(Ht2Params& P, const Ht2Image& img, bool noSplicedAlignment);
 
 // Per-read preprocessing (hisat2.cpp:3387-3467)
@@ -54,16 +46,6 @@ bool ht2_read_reads(const char* path, std::vector<Ht2HostRead>& out, int mate, s
 
 // SAM
 void ht2_sam_header(std::string& o, const Ht2Image& img);
-// finishRead for an unpaired read (aln_sink.h:2213-2557, unpaired branches)
-void ht2_finish_unpaired(std::string& o, const Ht2Image& img, const Ht2Params& P,
-                         const Ht2HostRead& rd, const Ht2ReadFilters& f,
-                         Ht2ReadOut& out);
-
-// finishRead for a pair: concordant / discordant / unpaired-mate branches
-void ht2_finish_paired(std::string& o, const Ht2Image& img, const Ht2Params& P,
-                       const Ht2HostRead& rd1, const Ht2HostRead& rd2,
-                       const Ht2ReadFilters& f1, const Ht2ReadFilters& f2, Ht2ReadOut& out);
-
 // ht2gpu_format_sam's body: host-only, shared with the test build
 bool ht2_format_batch(const Ht2Image& img, const Ht2Params& P, const ht2gpu_read_batch_t* b, const char* names,
                       const ht2gpu_result_batch_t* res, char** out, size_t* out_len, unsigned nthreads);

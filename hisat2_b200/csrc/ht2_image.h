@@ -27,8 +27,13 @@
 #define HT2_NI inline
 #endif
 
+// Spliced alignment (the reference's default mode) is compiled in unless HT2_DISABLE_SPLICED is given.
+#if !defined(HT2_DISABLE_SPLICED) && !defined(HT2_ENABLE_SPLICED)
+#define HT2_ENABLE_SPLICED
+#endif
+
 #define HT2_MAGIC 0x42325448u /* "HT2B" */
-#define HT2_IMAGE_VERSION 5u
+#define HT2_IMAGE_VERSION 6u
 
 // Local-index constants (hier_idx_common.h:23-41).
 #define HT2_LOCAL_INDEX_SIZE     57344u
@@ -145,6 +150,9 @@ struct Ht2ImageHeader {
     // reference names (host side only, for SAM headers)
     uint64_t o_names;      // '\0'-separated, nRefs entries
     uint64_t namesBytes;
+    // name-offset tables (the SAM back end runs on the device: no linear walks over the name blobs)
+    uint64_t o_nameOffs;    // uint32[nRefs + 1]: reference i's name starts at o_names + nameOffs[i]
+    uint64_t o_altNameOffs; // uint32[nAlts + 1]: ALT i's name starts at o_altNames + altNameOffs[i]
 };
 
 #endif // HT2_IMAGE_H_

@@ -265,9 +265,12 @@ Ht2Image* ht2_image_load(const char* base_c, std::string& err)
         while (names.size() < h.nRefs) names.push_back(std::to_string(names.size()));
         {
             std::string packed;
-            for (uint32_t i = 0; i < h.nRefs; i++) { packed += names[i]; packed.push_back('\0'); }
+            std::vector<uint32_t> noffs;
+            for (uint32_t i = 0; i < h.nRefs; i++) { noffs.push_back((uint32_t)packed.size()); packed += names[i]; packed.push_back('\0'); }
+            noffs.push_back((uint32_t)packed.size());
             h.o_names = b.put(packed.data(), packed.size(), 16);
             h.namesBytes = packed.size();
+            h.o_nameOffs = b.put(noffs.data(), noffs.size() * 4, 16);
         }
 
         // ---- .2.ht2 : SA sample ---------------------------------------
@@ -431,9 +434,12 @@ Ht2Image* ht2_image_load(const char* base_c, std::string& err)
             h.nAlts = (uint32_t)alts.size();
             h.o_alts = b.put(alts.data(), alts.size() * sizeof(Ht2Alt), 16);
             std::string packed;
-            for (size_t i = 0; i < names.size(); i++) { packed += names[i]; packed.push_back('\0'); }
+            std::vector<uint32_t> noffs;
+            for (size_t i = 0; i < names.size(); i++) { noffs.push_back((uint32_t)packed.size()); packed += names[i]; packed.push_back('\0'); }
+            noffs.push_back((uint32_t)packed.size());
             h.o_altNames = b.put(packed.data(), packed.size(), 16);
             h.altNamesBytes = packed.size();
+            h.o_altNameOffs = b.put(noffs.data(), noffs.size() * 4, 16);
         }
 
         b.alloc(0, 128);

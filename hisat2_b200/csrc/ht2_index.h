@@ -11,9 +11,7 @@ struct Ht2Image {
     std::vector<uint8_t> blob;
     const Ht2ImageHeader* header() const { return (const Ht2ImageHeader*)blob.data(); }
     const char* refName(uint32_t i) const {
-        const char* p = (const char*)blob.data() + header()->o_names;
-        for (uint32_t k = 0; k < i; k++) { while (*p) p++; p++; }
-        return p;
+        return (const char*)blob.data() + header()->o_names + ((const uint32_t*)(blob.data() + header()->o_nameOffs))[i];
     }
     uint32_t refPlen(uint32_t i) const {
         return ((const uint32_t*)(blob.data() + header()->global.o_plen))[i];

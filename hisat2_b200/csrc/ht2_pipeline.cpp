@@ -1,0 +1,170 @@
+// ht2_pipeline.cpp -- reads in, SAM out: the overlapped host pipeline around the device path.
+//
+// Replaces the reference's worker loop as a whole (multiseedSearchWorker_hisat2, hisat2.cpp:3278-3696: every
+// thread pulls one read under a lock, aligns it, formats it, hands the text to the OutputQueue, outq.cpp:51-99)
+// with three overlapped stages over batches of reads:
+//     parse batch i+1 (all host threads, ht2_reads.cpp)
+//  || H2D -> align kernel -> SAM kernels -> D2H of batch i (ht2gpu_submit_sam / ht2gpu_wait_sam, one slot each)
+//  || hand the SAM text of batch i-1 to the caller's sink, in read order (= --reorder)
+// Host code only parses and moves bytes; selection, MAPQ and SAM formatting run on the device.
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+
+#include "../../include/ht2gpu.h"
+#include "ht2_reads.h"
+
+namespace {
+double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+void* pinAlloc(size_t n) { return ht2gpu_host_alloc(n); }
+void pinFree(void* p) { ht2gpu_host_free(p); }
+}
+
+extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* in, ht2gpu_sink_fn sink, void* ctx, ht2gpu_run_stats_t* st)
+{
+    if (!h || !in) return HT2GPU_ERR_ARG;
+    ht2gpu_run_stats_t S; memset(&S, 0, sizeof(S));
+    const double t0 = nowS();
+    unsigned nth = in->threads > 0 ? (unsigned)in->threads : std::thread::hardware_concurrency();
+    if (nth < 1) nth = 1;
+    if (nth > 64) nth = 64;
+    Ht2ThreadPool pool(nth);
+    Ht2ReadSource a, b;
+    std::string err;
+    const bool paired = in->path2 != NULL || in->data2 != NULL;
+    auto fail = [&](int rc, const std::string& m) { ht2gpu_set_error(h, m.c_str()); ht2_source_close(a); ht2_source_close(b); if (st) *st = S; return rc; };
+    if (in->path1) { if (!ht2_source_open(a, in->path1, err)) return fail(HT2GPU_ERR_ARG, err); }
+    else if (in->data1) ht2_source_memory(a, in->data1, in->len1);
+    else return fail(HT2GPU_ERR_ARG, "ht2gpu_run_reads: no input");
+    if (in->path2) { if (!ht2_source_open(b, in->path2, err)) return fail(HT2GPU_ERR_ARG, err); }
+    else if (in->data2) ht2_source_memory(b, in->data2, in->len2);
+    const bool fastq = in->format == 1;
+    if (!ht2_source_index(a, fastq, pool, err)) return fail(HT2GPU_ERR_ARG, err);
+    if (paired && !ht2_source_index(b, fastq, pool, err)) return fail(HT2GPU_ERR_ARG, err);
+    if (paired && a.nRecords() != b.nRecords())
+        return fail(HT2GPU_ERR_ARG, a.nRecords() < b.nRecords() ? "fewer reads in file specified with -1 than in file specified with -2"
+                                                                : "fewer reads in file specified with -2 than in file specified with -1");
+    S.s_index = nowS() - t0;
+    // -s / -u (hisat2.cpp:1959-1964, 3319): records [skip, min(n, skip + upto))
+    uint64_t r0 = in->skip, r1 = a.nRecords();
+    if (r0 > r1) r0 = r1;
+    if (in->upto && r0 + in->upto < r1) r1 = r0 + in->upto;
+    uint64_t perBatch = in->batch_reads ? in->batch_reads : 1000000;
+    if (paired) perBatch = (perBatch + 1) / 2;   // batch_reads counts reads, a record here is a pair
+    if (perBatch < 1) perBatch = 1;
+    const uint64_t nBatches = (r1 - r0 + perBatch - 1) / perBatch;
+    Ht2ReadsOpts ro; ro.fastq = fastq; ro.trim5 = in->trim5; ro.trim3 = in->trim3; ro.phred64 = in->phred64 != 0; ro.seed = in->seed;
+
+    const int nSlots = ht2gpu_sam_slots(h);
+    std::vector<Ht2HostBatch> stage((size_t)nSlots);
+    for (auto& hb : stage) { hb.alloc = pinAlloc; hb.release = pinFree; }
+    // slot states: 0 free, 1 submitted
+    std::mutex mu; std::condition_variable cv;
+    std::vector<int> state((size_t)nSlots, 0);
+    uint64_t submitted = 0;
+    int prodRc = HT2GPU_OK; std::string prodErr; bool prodDone = false;
+    double parseS = 0;
+
+    std::thread producer([&]() {
+        for (uint64_t i = 0; i < nBatches; i++) {
+            const int slot = (int)(i % (uint64_t)nSlots);
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[slot] == 0 || prodRc != HT2GPU_OK; }); if (prodRc != HT2GPU_OK) break; }
+            const uint64_t q0 = r0 + i * perBatch, q1 = q0 + perBatch < r1 ? q0 + perBatch : r1;
+            const double tp = nowS();
+            std::string e;
+            int rc = HT2GPU_OK;
+            if (!ht2_parse_batch(a, paired ? &b : NULL, q0, q1, ro, stage[slot], pool, e)) rc = HT2GPU_ERR_ARG;
+            parseS += nowS() - tp;
+            if (rc == HT2GPU_OK) {
+                Ht2HostBatch& hb = stage[slot];
+                ht2gpu_read_batch_t rb; memset(&rb, 0, sizeof(rb));
+                rb.n_reads = hb.n_reads; rb.paired = paired ? 1 : 0; rb.seq = hb.seq; rb.qual = hb.haveQual ? hb.qual : NULL; rb.offs = hb.offs; rb.seeds = hb.seeds;
+                rc = ht2gpu_submit_sam(h, slot, &rb, hb.names, hb.nameOffs, hb.namesBytes);
+                if (rc != HT2GPU_OK) e = ht2gpu_last_error(h);
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (rc != HT2GPU_OK) { prodRc = rc; prodErr = e; cv.notify_all(); break; }
+            state[slot] = 1; submitted = i + 1;
+            cv.notify_all();
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        prodDone = true;
+        cv.notify_all();
+    });
+
+    int rc = HT2GPU_OK;
+    for (uint64_t i = 0; i < nBatches; i++) {
+        const int slot = (int)(i % (uint64_t)nSlots);
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return submitted > i || prodRc != HT2GPU_OK || prodDone; });
+            if (submitted <= i) { rc = prodRc != HT2GPU_OK ? prodRc : HT2GPU_ERR_ARG; break; }
+        }
+        ht2gpu_sam_result_t r;
+        rc = ht2gpu_wait_sam(h, slot, &r);
+        if (rc != HT2GPU_OK) { prodErr = ht2gpu_last_error(h); break; }
+        S.n_batches++; S.n_units += r.n_units; S.n_reads += stage[slot].n_reads; S.sam_bytes += r.sam_len; S.n_err_reads += r.n_err_reads;
+        S.ms_align += r.ms_align; S.ms_sam += r.ms_sam; S.ms_h2d += r.ms_h2d; S.ms_d2h += r.ms_d2h;
+        S.h2d_bytes += r.h2d_bytes; S.d2h_bytes += r.d2h_bytes; S.n_launches += r.n_launches;
+        if (sink && r.sam_len) { if (sink(ctx, r.sam, r.sam_len) != 0) { rc = HT2GPU_ERR_ARG; prodErr = "the SAM sink reported an error"; } }
+        { std::lock_guard<std::mutex> lk(mu); state[slot] = 0; if (rc != HT2GPU_OK) prodRc = rc; cv.notify_all(); }
+        if (rc != HT2GPU_OK) break;
+    }
+    { std::lock_guard<std::mutex> lk(mu); if (rc != HT2GPU_OK && prodRc == HT2GPU_OK) prodRc = rc; cv.notify_all(); }
+    producer.join();
+    // drain anything still in flight after an error
+    if (rc != HT2GPU_OK) for (int s = 0; s < nSlots; s++) if (state[s] == 1) { ht2gpu_sam_result_t r; ht2gpu_wait_sam(h, s, &r); }
+    for (auto& hb : stage) hb.freeAll();
+    ht2_source_close(a); ht2_source_close(b);
+    S.s_parse = parseS; S.s_total = nowS() - t0;
+    if (st) *st = S;
+    if (rc != HT2GPU_OK) ht2gpu_set_error(h, prodErr.empty() ? "ht2gpu_run_reads failed" : prodErr.c_str());
+    return rc;
+}
+
+// Host-only: parse a whole input into ONE batch (malloc'ed buffers).  No device is touched: this is the read
+// front end on its own (tests, callers that batch for themselves).
+extern "C" int ht2gpu_parse_reads(const ht2gpu_reads_input_t* in, ht2gpu_parsed_reads_t* out, char* errbuf, size_t errbuf_len)
+{
+    if (!in || !out) return HT2GPU_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    auto fail = [&](const std::string& m) { if (errbuf && errbuf_len) { strncpy(errbuf, m.c_str(), errbuf_len - 1); errbuf[errbuf_len - 1] = 0; } return HT2GPU_ERR_ARG; };
+    unsigned nth = in->threads > 0 ? (unsigned)in->threads : std::thread::hardware_concurrency();
+    if (nth < 1) nth = 1;
+    if (nth > 64) nth = 64;
+    Ht2ThreadPool pool(nth);
+    Ht2ReadSource a, b;
+    std::string err;
+    const bool paired = in->path2 != NULL || in->data2 != NULL;
+    if (in->path1) { if (!ht2_source_open(a, in->path1, err)) return fail(err); }
+    else if (in->data1) ht2_source_memory(a, in->data1, in->len1);
+    else return fail("no input");
+    if (in->path2) { if (!ht2_source_open(b, in->path2, err)) { ht2_source_close(a); return fail(err); } }
+    else if (in->data2) ht2_source_memory(b, in->data2, in->len2);
+    const bool fastq = in->format == 1;
+    bool ok = ht2_source_index(a, fastq, pool, err) && (!paired || ht2_source_index(b, fastq, pool, err));
+    if (ok && paired && a.nRecords() != b.nRecords()) { ok = false; err = "mate files have different numbers of reads"; }
+    Ht2HostBatch* hb = new Ht2HostBatch();
+    if (ok) {
+        uint64_t r0 = in->skip, r1 = a.nRecords();
+        if (r0 > r1) r0 = r1;
+        if (in->upto && r0 + in->upto < r1) r1 = r0 + in->upto;
+        Ht2ReadsOpts ro; ro.fastq = fastq; ro.trim5 = in->trim5; ro.trim3 = in->trim3; ro.phred64 = in->phred64 != 0; ro.seed = in->seed;
+        ok = ht2_parse_batch(a, paired ? &b : NULL, r0, r1, ro, *hb, pool, err);
+    }
+    ht2_source_close(a); ht2_source_close(b);
+    if (!ok) { hb->freeAll(); delete hb; return fail(err); }
+    out->batch.n_reads = hb->n_reads; out->batch.paired = paired ? 1 : 0; out->batch.seq = hb->seq; out->batch.qual = hb->haveQual ? hb->qual : NULL;
+    out->batch.offs = hb->offs; out->batch.seeds = hb->seeds;
+    out->names = hb->names; out->name_offs = hb->nameOffs; out->names_bytes = hb->namesBytes; out->priv = hb;
+    return HT2GPU_OK;
+}
+extern "C" void ht2gpu_free_parsed(ht2gpu_parsed_reads_t* p)
+{
+    if (p && p->priv) { Ht2HostBatch* hb = (Ht2HostBatch*)p->priv; hb->freeAll(); delete hb; p->priv = NULL; }
+}

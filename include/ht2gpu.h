@@ -33,7 +33,8 @@ extern "C" {
 #define HT2GPU_ERR_ARG      -1
 #define HT2GPU_ERR_INDEX    -2   /* index files missing / malformed */
 #define HT2GPU_ERR_CUDA     -3   /* no usable CUDA device or a CUDA call failed */
-#define HT2GPU_ERR_CAPACITY -4   /* a read exceeded a fixed device-side capacity */
+#define HT2GPU_ERR_CAPACITY -4   /* a result did not fit its container (seed search); per-read capacity overruns of the
+                                   alignment path are reported per read, see ht2gpu_result_batch_t.n_err_reads */
 #define HT2GPU_ERR_UNSUPPORTED -5
 
 typedef struct ht2gpu_handle ht2gpu_handle_t;
@@ -145,7 +146,8 @@ typedef struct {
     float                 ms_h2d, ms_kernel, ms_d2h;
     uint64_t              h2d_bytes, d2h_bytes;
     uint32_t              n_launches;
-    uint32_t              pad;
+    uint32_t              n_err_reads; /* reads (pairs) whose reads[i].err != 0: a fixed device-side capacity was exceeded,
+                                          their results are unreliable; the call itself still returns HT2GPU_OK */
     void*                 priv;      /* owned by the library */
 } ht2gpu_result_batch_t;
 
@@ -175,6 +177,88 @@ int ht2gpu_align_batch(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, ht2
 int ht2gpu_align_resident(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, int iters,
                           ht2gpu_result_batch_t* res);
 void ht2gpu_free_results(ht2gpu_result_batch_t* res);
+
+/* ---- SAM straight from the device -------------------------------------------
+ * The whole per-batch pipeline of the reference's worker loop -- nextReadPair .. go() .. AlnSinkWrap::finishRead
+ * (hisat2.cpp:3278-3559, aln_sink.h:1939-2560) -- on the GPU: H2D copy of the reads and their names, the
+ * alignment kernel, the SAM kernels (selectByScore, MAPQ, CIGAR / MD:Z and the optional fields, csrc/ht2_sam.h),
+ * D2H copy of the SAM text into pinned host memory.  Records are in read order (= --reorder) and byte-identical
+ * to the reference's.  names: '\0'-terminated read names, concatenated; name_offs[i] = offset of read i's name,
+ * name_offs[n_reads] = names_bytes.
+ *
+ * ht2gpu_submit_sam enqueues a batch on one of ht2gpu_sam_slots() slots and returns; ht2gpu_wait_sam blocks
+ * until that batch is done and hands back its text (valid until the next submit on the same slot).  Slots have
+ * their own streams and buffers, so the copies of one batch overlap the kernels of another; the host buffers
+ * of a submitted batch must stay valid (ideally pinned) until its wait returns.  One thread at a time per
+ * slot; ht2gpu_align_batch / ht2gpu_align_sam / ht2gpu_seed_search use slot 0. */
+typedef struct {
+    char*    sam;          /* pinned host memory owned by the library, '\0'-terminated */
+    size_t   sam_len;
+    uint32_t n_units;      /* reads (SE) or pairs (PE) of the batch */
+    uint32_t n_alns;       /* alignments the kernel reported (before selection) */
+    uint32_t n_err_reads;  /* units that exceeded a device-side capacity (their records are unreliable) */
+    uint32_t n_launches;   /* kernels launched for this batch */
+    float    ms_h2d, ms_align, ms_sam, ms_d2h;   /* CUDA events on the slot's stream */
+    uint64_t h2d_bytes, d2h_bytes;
+} ht2gpu_sam_result_t;
+
+int ht2gpu_sam_slots(const ht2gpu_handle_t* h);
+int ht2gpu_submit_sam(ht2gpu_handle_t* h, int slot, const ht2gpu_read_batch_t* batch, const char* names,
+                      const uint32_t* name_offs, size_t names_bytes);
+int ht2gpu_wait_sam(ht2gpu_handle_t* h, int slot, ht2gpu_sam_result_t* out);
+/* submit + wait on slot 0 */
+int ht2gpu_align_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* batch, const char* names, const uint32_t* name_offs,
+                     size_t names_bytes, ht2gpu_sam_result_t* out);
+
+/* ---- reads in, SAM out ---------------------------------------------------------
+ * The reference's whole worker loop (multiseedSearchWorker_hisat2 + PatternSource + OutputQueue,
+ * hisat2.cpp:3278-3696, pat.cpp:215-290, outq.cpp:51-99) as one call: FASTA / FASTQ bytes (files or host
+ * memory) are parsed by all host threads, aligned and formatted on the device in overlapped batches, and the SAM
+ * text is handed to 'sink' batch by batch, in read order (= --reorder).  sink receives pointers into pinned
+ * host memory that are valid only during the call; it returns 0 to continue. */
+typedef int (*ht2gpu_sink_fn)(void* ctx, const char* sam, size_t len);
+typedef struct {
+    const char* path1;      /* -U / -1 file ("-" = stdin), or NULL to use data1 */
+    const char* path2;      /* -2 file, or NULL */
+    const char* data1;      /* reads already in host memory */
+    size_t      len1;
+    const char* data2;
+    size_t      len2;
+    int32_t     format;     /* 0 = FASTA (-f), 1 = FASTQ (-q) */
+    int32_t     trim5, trim3;   /* -5 / -3 */
+    int32_t     phred64;    /* --phred64 */
+    uint32_t    seed;       /* --seed (per-read seeds, pat.h:55-91) */
+    uint64_t    skip;       /* -s */
+    uint64_t    upto;       /* -u; 0 = no limit */
+    uint32_t    batch_reads;/* reads per device batch; 0 = 1,000,000 */
+    int32_t     threads;    /* host parser threads (-p); 0 = all cores, at most 64 */
+} ht2gpu_reads_input_t;
+typedef struct {
+    uint64_t n_reads, n_units, sam_bytes, n_err_reads, n_batches;
+    double   s_index, s_parse, s_total;          /* host wall clock: record indexing, batch parsing (overlapped), whole call */
+    float    ms_h2d, ms_align, ms_sam, ms_d2h;   /* summed CUDA-event times of the batches */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t n_launches, pad;
+} ht2gpu_run_stats_t;
+int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* in, ht2gpu_sink_fn sink, void* ctx, ht2gpu_run_stats_t* stats);
+
+/* The read front end on its own, host only (no device): the whole input as ONE batch in the layout
+ * ht2gpu_align_batch / ht2gpu_submit_sam take (FastaPatternSource / FastqPatternSource + genRandSeed +
+ * fixMateName, pat.cpp:725-1290, pat.h:55-91, read.h:171-196). */
+typedef struct {
+    ht2gpu_read_batch_t batch;
+    char*     names;        /* '\0'-terminated names, concatenated */
+    uint32_t* name_offs;    /* batch.n_reads + 1 entries */
+    size_t    names_bytes;
+    void*     priv;
+} ht2gpu_parsed_reads_t;
+int ht2gpu_parse_reads(const ht2gpu_reads_input_t* in, ht2gpu_parsed_reads_t* out, char* errbuf, size_t errbuf_len);
+void ht2gpu_free_parsed(ht2gpu_parsed_reads_t* p);
+
+/* Pinned host memory for batches handed to ht2gpu_submit_sam (asynchronous H2D copies need it). */
+void* ht2gpu_host_alloc(size_t bytes);
+void ht2gpu_host_free(void* p);
+void ht2gpu_set_error(ht2gpu_handle_t* h, const char* msg);
 
 /* ---- seed search on its own (linear AND graph/SNP indexes) -------------------
  * For every read and strand (fw first): the chain of partial searches

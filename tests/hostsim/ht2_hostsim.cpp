@@ -13,12 +13,9 @@
 #include "../../hisat2_b200/csrc/ht2_host.h"
 #include "../../hisat2_b200/csrc/ht2_seed.h"
 
-// HT2_RECURSIVE=1 runs the recursive formulation (ht2_core_impl.h) instead of the
-// explicit-stack state machine the kernels use (ht2_machine.h); both must agree.
+// Runs the explicit-stack state machine the kernels use (ht2_machine.h) to completion.
 template <typename ALIGNER>
 static void runRead(ALIGNER& A) {
-    static const bool recursive = getenv("HT2_RECURSIVE") != NULL;
-    if (recursive) { A.go(); return; }
     A.machineStart();
     while (!A.machineDone()) A.machineStep();
 }
@@ -83,10 +80,10 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
                     const char* outPath) {
     std::string sam;
     ht2_sam_header(sam, *img);
-    // HT2_VIA_BATCH=1: hand the results over in the C ABI's batch structures (what the kernels' finish step
-    // writes, ht2_gpu.cu ht2_finish_unit) and let ht2_format_batch -- the body of ht2gpu_format_sam -- print
-    // them, on HT2_THREADS host threads
-    const bool viaBatch = getenv("HT2_VIA_BATCH") != NULL;
+    // The results are handed over in the C ABI's batch structures (what the kernels' finish step writes,
+    // ht2_gpu.cu ht2_finish_unit) and ht2_format_batch -- the body of ht2gpu_format_sam, i.e. the formatter of
+    // ht2_sam.h that the device SAM kernel also runs -- prints them, on HT2_THREADS host threads
+    const bool viaBatch = true;
     std::vector<ht2gpu_read_result_t> bReads; std::vector<ht2gpu_aln_t> bAlns; std::vector<ht2gpu_edit_t> bEdits; std::vector<uint16_t> bPairs;
     auto collect = [&](const Ht2Work* Wk) {
         ht2gpu_read_result_t rr; memset(&rr, 0, sizeof(rr));
@@ -120,7 +117,6 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         r1.seed = ht2_gen_rand_seed(r1, 0); r2.seed = ht2_gen_rand_seed(r2, 0);
         int64_t ms1 = ht2_minsc(P, (uint32_t)r1.seq.size()), ms2 = ht2_minsc(P, (uint32_t)r2.seq.size());
         Ht2ReadFilters f1 = ht2_filters(r1, ms1), f2 = ht2_filters(r2, ms2);
-        Ht2ReadOut out; out.err = 0;
         A.bind(img->blob.data(), &P, W); A.sw = swScratch; HT2_SET_SPLT(A);
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         bool p1 = f1.pass(), p2 = f2.pass();
@@ -143,23 +139,18 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
                 runRead(A);
             }
         }
-        out.rngLast = W->rnd.last; out.err = W->err; nLF += W->nLF;
+        nLF += W->nLF;
         if (W->err) { nerr++; fprintf(stderr, "pair %zu (%s): err=0x%x\n", i, r1.name.c_str(), W->err); }
         { uint32_t v[8] = {W->maxPool, W->maxDepth, W->maxEdits, W->nSearched[0] > W->nSearched[1] ? W->nSearched[0] : W->nSearched[1], W->nRes[0] > W->nRes[1] ? W->nRes[0] : W->nRes[1], W->nGenomeHits, W->nPairs, 0};
           for (int k = 0; k < 8; k++) if (v[k] > mx[k]) mx[k] = v[k]; }
-        out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
-        out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
-        for (uint32_t k = 0; k < W->nPairs; k++) out.pairs.push_back(std::make_pair(W->pairs[k][0], W->pairs[k][1]));
-        if (viaBatch) { if (!(p1 || p2) || (W->err & HT2_ERR_RDLEN)) { W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0; } collect(W); }
-        else { auto t0 = std::chrono::steady_clock::now(); ht2_finish_paired(sam, *img, P, r1, r2, f1, f2, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
+        if (!(p1 || p2) || (W->err & HT2_ERR_RDLEN)) { W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0; }
+        collect(W);
     }
     for (size_t i = 0; !pairedMode && i < reads.size(); i++) {
         Ht2HostRead& rd = reads[i];
         rd.seed = ht2_gen_rand_seed(rd, 0);
         int64_t minsc = ht2_minsc(P, (uint32_t)rd.seq.size());
         Ht2ReadFilters f = ht2_filters(rd, minsc);
-        Ht2ReadOut out;
-        out.err = 0;
         A.bind(img->blob.data(), &P, W); A.sw = swScratch; HT2_SET_SPLT(A);
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         W->rnd.init(rd.seed);
@@ -172,16 +163,12 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
             ht2_fill_read(W->rd[0], rd);
             runRead(A);
         }
-        out.rngLast = W->rnd.last;
-        out.err = W->err;
         nLF += W->nLF;
         { uint32_t v[8] = {W->maxPool, W->maxDepth, W->maxEdits, W->nSearched[0], W->nRes[0], W->nGenomeHits, W->hits[0][0].nhits, W->hits[0][1].nhits};
           for (int k = 0; k < 8; k++) if (v[k] > mx[k]) mx[k] = v[k]; }
         if (W->err) { nerr++; fprintf(stderr, "read %zu (%s): err=0x%x\n", i, rd.name.c_str(), W->err); }
-        out.res[0].assign(W->res[0], W->res[0] + W->nRes[0]);
-        out.res[1].assign(W->res[1], W->res[1] + W->nRes[1]);
-        if (viaBatch) { if (!f.pass() || (W->err & HT2_ERR_RDLEN)) { W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0; } collect(W); }
-        else { auto t0 = std::chrono::steady_clock::now(); ht2_finish_unpaired(sam, *img, P, rd, f, out); finishNs += (std::chrono::steady_clock::now() - t0).count(); }
+        if (!f.pass() || (W->err & HT2_ERR_RDLEN)) { W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0; }
+        collect(W);
     }
     if (viaBatch) {
         std::vector<uint8_t> seq, qual; std::vector<uint64_t> offs(1, 0); std::string names;

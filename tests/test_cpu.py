@@ -169,6 +169,75 @@ def test_striped_dp_fill_and_backtrace_against_plain_scalar_dp(hostsim_bin):
     assert int(out.split(" backtraces")[0].split()[-1]) > 200
 
 
+def test_read_front_end_matches_python_restatement(lib, tmp_path):
+    """csrc/ht2_reads.cpp (multi-threaded record index + batch parser behind ht2gpu_parse_reads / ht2gpu_run_reads)
+    against the independent Python restatement of FastaPatternSource / FastqPatternSource in api.py: bases,
+    qualities, offsets, names (default names, /1 /2 fixing) and per-read seeds, single- and multi-threaded,
+    CRLF, missing final newline, blank lines between FASTQ records, -5/-3, --phred64, -s/-u."""
+    from hisat2_b200 import api
+    RB = api.ReadBatch
+
+    def same(a, b):
+        assert a.n == b.n and a.paired == b.paired
+        assert np.array_equal(a.offs, b.offs) and np.array_equal(a.seq, b.seq) and np.array_equal(a.seeds, b.seeds)
+        assert a.names == b.names
+        assert (a.qual is None) == (b.qual is None)
+        if a.qual is not None:
+            assert np.array_equal(a.qual, b.qual)
+    g = lambda n: os.path.join(GOLDEN, n)
+    same(RB.parse(g("tiny_se.fa")), RB.from_fasta(g("tiny_se.fa")))
+    same(RB.parse(g("tiny_pe_1.fa"), g("tiny_pe_2.fa")), RB.from_fasta(g("tiny_pe_1.fa"), path2=g("tiny_pe_2.fa")))
+    same(RB.parse(g("tiny_se.fq"), fastq=True), RB.from_fastq(g("tiny_se.fq")))
+    same(RB.parse(g("tiny_pe_1.fq"), g("tiny_pe_2.fq"), fastq=True), RB.from_fastq(g("tiny_pe_1.fq"), path2=g("tiny_pe_2.fq")))
+    same(RB.parse(data1=open(g("tiny_se.fq"), "rb").read(), fastq=True, threads=5), RB.from_fastq(g("tiny_se.fq")))
+    # a file large enough to be indexed and parsed by several threads (> 1 MiB, > 2048 records)
+    rng = np.random.default_rng(11)
+    big = str(tmp_path / "big.fa")
+    with open(big, "wb") as f:
+        for i in range(9000):
+            L = int(rng.integers(1, 250))
+            sq = rng.choice(np.frombuffer(b"ACGTNacgtnRY-", dtype=np.uint8), L).tobytes()
+            if i % 3 == 0 and L > 80:
+                sq = sq[:70] + b"\r\n" + sq[70:]          # multi-line record, CRLF
+            f.write(b">" + (b"" if i % 1000 == 7 else b"r%d some text/%d" % (i, i % 3)) + b"\n" + sq + (b"\n" if i < 8999 else b""))
+    same(RB.parse(big, threads=1), RB.from_fasta(big))
+    same(RB.parse(big, threads=7), RB.from_fasta(big))
+    same(RB.parse(big, big, threads=6), RB.from_fasta(big, path2=big))
+    fq = str(tmp_path / "big.fq")
+    fq_blank = str(tmp_path / "blank.fq")
+    with open(fq, "wb") as f, open(fq_blank, "wb") as fb:
+        for i in range(12000):
+            L = int(rng.integers(1, 200))
+            sq = rng.choice(np.frombuffer(b"ACGTN.", dtype=np.uint8), L, p=[.24, .24, .24, .24, .02, .02]).tobytes()
+            ql = rng.integers(33, 74, L).astype(np.uint8).tobytes()      # '@' (64) occurs at line starts too
+            rec = b"@q%d\n" % i + sq + b"\n+\n" + ql + b"\n"
+            f.write(rec)
+            fb.write(rec + (b"\n" if i % 5 == 0 else b""))
+    same(RB.parse(fq, fastq=True, threads=1), RB.from_fastq(fq))
+    same(RB.parse(fq, fastq=True, threads=8), RB.from_fastq(fq))
+    same(RB.parse(fq_blank, fastq=True, threads=8), RB.from_fastq(fq))           # falls back to the sequential record scan
+    # -s / -u, -5 / -3, --phred64
+    a, b = RB.parse(fq, fastq=True, skip=100, upto=50, threads=4), RB.from_fastq(fq)
+    assert a.n == 50 and a.names == b.names[100:150]
+    t = RB.parse(g("tiny_se.fq"), fastq=True, trim5=3, trim3=5)
+    full = RB.from_fastq(g("tiny_se.fq"))
+    for i in (0, 1, 17, full.n - 1):
+        lo, hi = int(full.offs[i]), int(full.offs[i + 1])
+        keep = slice(lo + 3, max(lo + 3, hi - 5)) if hi - lo > 3 else slice(lo, lo)
+        assert np.array_equal(t.seq[int(t.offs[i]):int(t.offs[i + 1])], full.seq[keep])
+        assert np.array_equal(t.qual[int(t.offs[i]):int(t.offs[i + 1])], full.qual[keep])
+    p64 = str(tmp_path / "p64.fq")
+    src = open(g("tiny_se.fq"), "rb").read().split(b"\n")
+    with open(p64, "wb") as f:
+        for i in range(0, len(src) - 1, 4):
+            f.write(b"\n".join([src[i], src[i + 1], src[i + 2], bytes(c + 31 for c in src[i + 3])]) + b"\n")
+    same(RB.parse(p64, fastq=True, phred64=1), full)
+    with pytest.raises(api.Ht2GpuError):
+        RB.parse(g("tiny_se.fa"), fastq=True)
+    with pytest.raises(api.Ht2GpuError):
+        RB.parse(g("tiny_pe_1.fa"), g("tiny_se.fa"))
+
+
 def test_abi_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))
@@ -184,7 +253,7 @@ def test_image_build_is_host_only_and_consistent(lib):
     img = api.Index.build_image(os.path.join(GOLDEN, "tiny"))
     assert img[:4].tobytes() == b"HT2B"
     hdr = np.frombuffer(img[:16].tobytes(), dtype="<u4")
-    assert hdr[1] == 5  # image version
+    assert hdr[1] == 6  # image version
     total = int(np.frombuffer(img[8:16].tobytes(), dtype="<u8")[0])
     assert total == img.nbytes and total % 128 == 0
     # global geometry (Ht2Gfm at offset 16): len, gbwtLen, numNodes, eftabLen, linearFM, sideSz, sideGbwtSz, sideGbwtLen

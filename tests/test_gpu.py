@@ -43,10 +43,17 @@ def chr22(h2):
 
 
 def gpu_sam(idx, batch):
+    """Header + SAM records of a batch.  The records are formatted ON THE DEVICE (ht2gpu_align_sam: the alignment
+    kernel followed by the SAM kernels, csrc/ht2_sam.h) and must equal, byte for byte, what the host formatter
+    makes of the structured results of ht2gpu_align_batch -- every parity test therefore checks both paths."""
     res = idx.align(batch)
     assert int((res.reads["err"] != 0).sum()) == 0
     assert res.n_launches >= 1
-    return idx.sam_header() + idx.format_sam(batch, res), res
+    host = idx.format_sam(batch, res)
+    dev, st = idx.align_sam(batch, with_stats=True)
+    assert st["n_launches"] >= 4 and st["n_err_reads"] == 0
+    assert dev == host, "device SAM differs from the host formatter's"
+    return idx.sam_header() + dev, res
 
 
 def test_tiny_se_matches_golden_reference_sam(h2, tiny):
@@ -136,10 +143,70 @@ def test_command_line_front_end_matches_golden(tmp_path):
         subprocess.run([cli, "--no-spliced-alignment", "-x", index] + args + ["-S", out, "-p", "4"], cwd=GOLDEN, check=True,
                        stderr=subprocess.DEVNULL)
         assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), args
-    # anything the build cannot honour bit-exactly is refused with a non-zero exit code
-    r = subprocess.run([cli, "-x", "tiny", "-q", "-U", "tiny_se.fq", "-S", str(tmp_path / "x.sam")], cwd=GOLDEN,
+    # the reference's default (spliced, temporary splice sites) runs as --no-temp-splicesite, with a warning
+    out = str(tmp_path / "spl.sam")
+    r = subprocess.run([cli, "-x", "tiny", "-f", "-U", "tiny_rna.fa", "-S", out], cwd=GOLDEN, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and b"no-temp-splicesite" in r.stderr
+    assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_spliced_rna.sam"), "rb").read())
+    # options the build does not know are refused with a non-zero exit code
+    r = subprocess.run([cli, "-x", "tiny", "-q", "-U", "tiny_se.fq", "--local", "-S", str(tmp_path / "x.sam")], cwd=GOLDEN,
                        stderr=subprocess.PIPE)
-    assert r.returncode != 0 and b"spliced" in r.stderr
+    assert r.returncode != 0 and b"not supported" in r.stderr
+
+
+def test_pipeline_reads_in_sam_out_matches_golden(h2, tiny):
+    """ht2gpu_run_reads: FASTA / FASTQ (paths and bytes in host memory) -> SAM through the overlapped pipeline
+    (multi-threaded parser, three device slots, SAM formatted on the device).  Small batches force many
+    batches per run, i.e. slot reuse and ordered hand-over."""
+    g = lambda n: os.path.join(GOLDEN, n)
+    want = sam_lines(open(g("tiny_se.sam"), "rb").read())
+    hdr = tiny.sam_header()
+    for batch_reads in (0, 64, 7):
+        sam, st = tiny.run_reads(path1=g("tiny_se.fa"), batch_reads=batch_reads)
+        assert sam_lines(hdr + sam) == want, batch_reads
+        assert st["n_reads"] == 700 and st["n_err_reads"] == 0 and st["sam_bytes"] == len(sam)
+        assert st["n_batches"] == (1 if batch_reads == 0 else -(-700 // batch_reads))
+    sam, st = tiny.run_reads(data1=open(g("tiny_se.fq"), "rb").read(), fastq=True, batch_reads=100, threads=3)
+    assert sam_lines(hdr + sam) == sam_lines(open(g("tiny_se_fq.sam"), "rb").read())
+    sam, st = tiny.run_reads(path1=g("tiny_pe_1.fq"), path2=g("tiny_pe_2.fq"), fastq=True, batch_reads=90)
+    assert sam_lines(hdr + sam) == sam_lines(open(g("tiny_pe_fq.sam"), "rb").read())
+    assert st["n_units"] * 2 == st["n_reads"]
+    sam, st = tiny.run_reads(data1=open(g("tiny_pe_1.fa"), "rb").read(), data2=open(g("tiny_pe_2.fa"), "rb").read(), batch_reads=128)
+    assert sam_lines(hdr + sam) == sam_lines(open(g("tiny_pe.sam"), "rb").read())
+    # -s / -u select a record range (hisat2.cpp:1959-1964, 3319)
+    sam, st = tiny.run_reads(path1=g("tiny_se.fa"), skip=100, upto=50)
+    recs = [l for l in want if not l.startswith(b"@")]
+    names = []
+    for l in recs:
+        if not names or names[-1] != l.split(b"\t")[0]:
+            names.append(l.split(b"\t")[0])
+    keep = set(names[100:150])
+    assert sam.splitlines() == [l for l in recs if l.split(b"\t")[0] in keep]
+    # mismatching mate files are an error, not a truncation
+    with pytest.raises(h2.Ht2GpuError):
+        tiny.run_reads(path1=g("tiny_pe_1.fa"), path2=g("tiny_se.fa"))
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
+def test_pipeline_and_cli_match_reference_binary_at_scale(h2, chr22, tmp_path):
+    """200k pairs of the chr22 set through ht2gpu_run_reads (50k-read batches: eight batches over three slots)
+    and through the hisat2-b200 command line: both byte-identical to the reference binary run here."""
+    f1, f2 = os.path.join(DATA, "sim200k_1.fa"), os.path.join(DATA, "sim200k_2.fa")
+    if not os.path.exists(f1):
+        pytest.skip(f1 + " not staged")
+    out = str(tmp_path / "ref.sam")
+    base = os.path.join(DATA, "22_20-21M")
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", base, "-1", f1, "-2", f2, "-S", out,
+                    "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    want = sam_lines(open(out, "rb").read())
+    sam, st = chr22.run_reads(path1=f1, path2=f2, batch_reads=50000)
+    assert st["n_batches"] == 8 and st["n_err_reads"] == 0
+    assert sam_lines(chr22.sam_header() + sam) == want
+    cli = os.path.join(ROOT, "hisat2_b200", "hisat2-b200")
+    out2 = str(tmp_path / "cli.sam")
+    subprocess.run([cli, "--no-spliced-alignment", "-f", "-x", base, "-1", f1, "-2", f2, "-S", out2, "--batch", "120000"], check=True,
+                   stderr=subprocess.DEVNULL)
+    assert sam_lines(open(out2, "rb").read()) == want
 
 
 def _option_cases():
@@ -247,7 +314,7 @@ def test_dynamic_programming_extension_matches_reference_binary_run_here(h2, ind
         pytest.skip("data/ not staged")
     idx = h2.Index(base, **opts)
     batch = h2.ReadBatch.from_fasta(f1, path2=f2 if paired else None)
-    res = idx.align(batch, allow_capacity=True)
+    res = idx.align(batch)
     errs = np.nonzero(res.reads["err"])[0]
     assert len(errs) <= 0.002 * len(res.reads["err"])
     sam = idx.sam_header() + idx.format_sam(batch, res)
@@ -347,8 +414,10 @@ def test_edge_cases(h2, tiny):
     assert "YF:Z:NS" in sam[1] and "YF:Z:LN" in sam[2]           # N filter / length filter (hisat2.cpp:3417-3440)
     # over-long read: reported as a capacity error, never silently truncated
     long_ = h2.ReadBatch(rng.integers(0, 4, 300).astype(np.uint8), np.array([0, 300], np.uint64), np.array([1], np.uint32), [b"len300"])
-    res = tiny.align(long_, allow_capacity=True)
-    assert res.reads["err"][0] != 0
+    res = tiny.align(long_)                      # the call succeeds; the read is flagged and counted
+    assert res.reads["err"][0] != 0 and res.n_err_reads == 1
+    sam, st = tiny.align_sam(long_, with_stats=True)
+    assert st["n_err_reads"] == 1
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
@@ -375,7 +444,7 @@ def test_long_pairs_capacity_errors_are_flagged_never_silent(h2, chr22, tmp_path
     if not os.path.exists(f1):
         pytest.skip(f1 + " not staged")
     batch = h2.ReadBatch.from_fasta(f1, path2=f2)
-    res = chr22.align(batch, allow_capacity=True)
+    res = chr22.align(batch)
     bad = set(np.flatnonzero(res.reads["err"] != 0).tolist())
     assert len(bad) <= 10
     sam = chr22.sam_header() + chr22.format_sam(batch, res)
@@ -388,28 +457,35 @@ def test_long_pairs_capacity_errors_are_flagged_never_silent(h2, chr22, tmp_path
     assert keep(sam_lines(sam)) == keep(sam_lines(open(out, "rb").read()))
 
 
-def test_full_size_properties_1M_reads(h2, chr22):
-    """BASELINE configs[1] size (1M x 101 bp): properties that do not need the CPU
-    reference -- every read yields a record set, >= 99% align, reads sampled from
-    the forward strand of the reference without errors align exactly where they
-    were cut, results are identical across two runs, no capacity errors."""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+@pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
+def test_full_size_byte_parity_1M_reads_and_500k_pairs(h2, chr22, tmp_path):
+    """BASELINE configs[1] size (1M x 101 bp SE) and the configs[2] shape (500k pairs 2x101): the bench workload's own
+    generator, FASTA bytes through ht2gpu_run_reads (1M-read device batches), byte-compared with the unmodified
+    reference run on this box; plus determinism of a second pass."""
     sys.path.insert(0, ROOT)
     import bench
-    ascii_reads, codes = bench.gen_reads(1000000, seed=1)
-    names = [b"r%d" % i for i in range(len(codes))]
-    seeds = bench.seeds_for(codes, names)
-    offs = np.arange(0, (len(codes) + 1) * 101, 101, dtype=np.uint64)
-    batch = h2.ReadBatch(codes.reshape(-1), offs, seeds, names)
-    r1 = chr22.align(batch)
-    assert int((r1.reads["err"] != 0).sum()) == 0
-    n_al = (r1.reads["n_aln"][:, 0] > 0).sum()
-    assert n_al >= 0.99 * len(codes)
-    assert (r1.reads["n_aln"][:, 0] <= 64).all()
-    a = r1.alns
-    assert (a["score"] <= 0).all() and (a["score"] >= -20).all()       # minsc(101) = -20
-    assert (a["ref_extent"] > 0).all() and (a["toff"] + a["ref_extent"] <= 1000000).all()
-    r2 = chr22.align(batch)
-    assert np.array_equal(r1.reads["rng_state"], r2.reads["rng_state"])
-    assert np.array_equal(np.sort(r1.alns, order=["toff", "score", "fw", "tidx"])[["toff", "score", "fw"]],
-                          np.sort(r2.alns, order=["toff", "score", "fw", "tidx"])[["toff", "score", "fw"]])
+    base = os.path.join(DATA, "22_20-21M")
+    d1, d2 = bench.sim_fasta(0, 1000000)
+    f1, f2 = str(tmp_path / "m1.fa"), str(tmp_path / "m2.fa")
+    d1.tofile(f1)
+    nthr = str(min(32, os.cpu_count() or 1))
+    out = str(tmp_path / "ref.sam")
+    # 1M single-end reads
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", base, "-U", f1, "-S", out, "-p", nthr, "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    sam, st = chr22.run_reads(data1=d1)
+    assert st["n_reads"] == 1000000 and st["n_err_reads"] == 0
+    want = open(out, "rb").read()
+    body = want[want.index(b"\nr00000000\t") + 1:]
+    assert sam == body
+    assert sam.count(b"\tYT:Z:UU") >= 1000000 and sam.count(b"\n") >= 1000000
+    sam2, _ = chr22.run_reads(data1=d1, batch_reads=300000)
+    assert sam2 == sam                      # batch composition does not change a byte
+    del sam, sam2, want, body
+    # 500k pairs
+    k = 500000
+    d1[:k * bench.RECSZ].tofile(f1); d2[:k * bench.RECSZ].tofile(f2)
+    subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", base, "-1", f1, "-2", f2, "-S", out, "-p", nthr, "--reorder"], check=True, stderr=subprocess.DEVNULL)
+    sam, st = chr22.run_reads(data1=d1[:k * bench.RECSZ], data2=d2[:k * bench.RECSZ])
+    assert st["n_units"] == k and st["n_err_reads"] == 0
+    want = open(out, "rb").read()
+    assert sam == want[want.index(b"\nr00000000\t") + 1:]

@@ -10,17 +10,15 @@ opts = dict(kv.split("=") for kv in sys.argv[3:])
 opts = {k: int(v) for k, v in opts.items()}
 idx = h2.Index(os.path.join(ROOT, "data", os.environ.get("HT2_INDEX", "22_20-21M")), **opts)
 print("opts", opts)
-if fa.startswith("synth:"):          # bench.py's synthetic workload, e.g. synth:1000000
+if fa.startswith("synth"):          # bench.py's synthetic workload, e.g. synth:1000000
     import numpy as np
     sys.path.insert(0, ROOT)
     import bench
-    n = int(fa.split(":")[1])
-    _, codes = bench.gen_reads(n, seed=1)
-    names = [b"r%d" % i for i in range(n)]
-    batch = h2.ReadBatch(codes.reshape(-1), np.arange(0, (n + 1) * 101, 101, dtype=np.uint64), bench.seeds_for(codes, names), names)
+    n = int(fa.split(":")[1])                       # synth:N = N single-end reads, synthpe:N = N pairs
+    d1, d2 = bench.sim_fasta(0, n, paired=fa.startswith("synthpe:"))
+    batch = h2.ReadBatch.parse(data1=d1, data2=d2)
 else:
     batch = h2.ReadBatch.from_fasta(fa)
 for i in range(iters):
-    r = idx.align(batch)
-    print("iter", i, "kernel ms", r.ms_kernel, "reads/s", batch.n / (r.ms_kernel / 1e3))
-    r.close()
+    _, st = idx.align_sam(batch, with_stats=True)
+    print("iter", i, "align ms %.2f  sam ms %.2f  reads/s (align) %.0f" % (st["ms_align"], st["ms_sam"], batch.n / (st["ms_align"] / 1e3)))

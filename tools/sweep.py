@@ -10,9 +10,8 @@ if fa.startswith("synth:"):          # bench.py's synthetic workload, e.g. synth
     sys.path.insert(0, ROOT)
     import bench
     n = int(fa.split(":")[1])
-    _, codes = bench.gen_reads(n, seed=1)
-    names = [b"r%d" % i for i in range(n)]
-    batch = h2.ReadBatch(codes.reshape(-1), np.arange(0, (n + 1) * 101, 101, dtype=np.uint64), bench.seeds_for(codes, names), names)
+    d1, _ = bench.sim_fasta(0, n, paired=False)
+    batch = h2.ReadBatch.parse(data1=d1)
 else:
     batch = h2.ReadBatch.from_fasta(fa)
 ref = None
