@@ -350,6 +350,7 @@ def main():
                 "what": "ht2gpu_run_reads: FASTA text in host memory -> SAM text in (pinned) host memory; record indexing, multi-threaded parsing, "
                         "H2D, alignment kernel, SAM kernels and D2H all inside the timed region (host wall clock, max over ranks)"},
         "kernels_ms_per_step": {"align": align_ms / args.steps, "align_plus_sam": kernel_ms / args.steps},
+        "host_s_per_step_rank0": {k: acc[k] / args.steps for k in ("s_index", "s_parse", "s_submit", "s_wait", "s_sink", "s_total")},
         "lf_map": lf_map,
         "gpu_launches": int(tot[1]),
         "clocks": clocks,

@@ -66,6 +66,7 @@ class CReadsInput(C.Structure):
 class CRunStats(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_units", C.c_uint64), ("sam_bytes", C.c_uint64), ("n_err_reads", C.c_uint64),
                 ("n_batches", C.c_uint64), ("s_index", C.c_double), ("s_parse", C.c_double), ("s_total", C.c_double),
+                ("s_submit", C.c_double), ("s_wait", C.c_double), ("s_sink", C.c_double),
                 ("ms_h2d", C.c_float), ("ms_align", C.c_float), ("ms_sam", C.c_float), ("ms_d2h", C.c_float),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32), ("pad", C.c_uint32)]
 
@@ -85,6 +86,7 @@ EXPORTS = [
     "ht2gpu_seed_search", "ht2gpu_free_seed_results", "ht2gpu_index_is_graph",
     "ht2gpu_sam_slots", "ht2gpu_submit_sam", "ht2gpu_wait_sam", "ht2gpu_align_sam", "ht2gpu_run_reads",
     "ht2gpu_host_alloc", "ht2gpu_host_free", "ht2gpu_set_error", "ht2gpu_parse_reads", "ht2gpu_free_parsed",
+    "ht2gpu_ctx_get", "ht2gpu_ctx_set",
 ]
 
 

@@ -23,7 +23,7 @@
 #ifndef HT2_MAX_RDLEN
 #define HT2_MAX_RDLEN 256
 #endif
-#define HT2_MAX_EDITS 40
+#define HT2_MAX_EDITS 96   /* edits of one (trial) hit: a 250-bp read at --very-sensitive scores admits ~80 deleted bases */
 #define HT2_MAX_PHITS 64
 #ifndef HT2_MAX_GHITS
 #define HT2_MAX_GHITS 64   /* max(khits, kseeds) anchors: --very-sensitive runs -k 30, i.e. 60 seeds */
@@ -32,8 +32,9 @@
 #define HT2_IE_POOL 96           /* in-edge entries per strand (graph indexes) */
 #define HT2_SEARCHED_BYTES 24576   /* ~600 searched hits (40 B typical) for both mates */
 
-#define HT2_MAX_RES 64
-#define HT2_MAX_PAIRS 96
+#define HT2_MAX_RES 128          /* reported alignments per mate (rs1u_ / rs2u_) */
+#define HT2_MAX_PAIRS 256
+#define HT2_RES_EDITS 2048        /* edits of ALL reported alignments of a read (pair): one arena instead of a fixed array per alignment */
 #ifndef HT2_MAX_COORDS
 #define HT2_MAX_COORDS 64
 #endif
@@ -144,12 +145,12 @@ struct Ht2Res {
     uint32_t trim5p, trim3p;  // 5'/3' soft trimming in read orientation
     uint32_t rfextent;        // # reference chars covered
     uint32_t nedits;
+    uint32_t editOff;         // AlnRes::ned() = Ht2Work::resEdits[editOff .. editOff + nedits): 5'->3', relative to trim5p
 #ifdef HT2_ENABLE_SPLICED
     double   splicescore;     // AlnScore::splicescore_
     uint32_t spliced;         // GenomeHit::spliced().first (also "near splice sites")
     uint32_t knownTranscripts;
 #endif
-    Ht2Edit  edits[HT2_MAX_EDITS]; // AlnRes::ned(): 5'->3', relative to trim5p
 };
 
 struct Ht2Read {
@@ -211,12 +212,14 @@ struct Ht2AltScratch {
 #define HT2_SW_MAXCOLS (HT2_MAX_RDLEN + 4 * HT2_SW_MAXGAP)
 #define HT2_SW_MAX_EDITS 160
 #define HT2_SW_SEG ((HT2_MAX_RDLEN + 1) / 2)     /* words per column: 2 rows (s16 halves) per 32-bit word */
+// The three score matrices H, E, F (striped: row i = half i / seg of word i % seg; column-major; one spare column)
+// live OUTSIDE the scratch struct, in a plane pool addressed with a stride: word idx of plane p of a lane is
+// pool[(p * HT2_SW_PLANE_WORDS + idx) * stride + lane].  On the device stride = 32 and the 32 lanes of a warp
+// interleave their words, so that a converged warp -- the lanes of a round run their DP problems together -- writes
+// and reads whole 128-byte lines per instruction instead of 32 separate sectors; the host build uses stride 1.
+#define HT2_SW_PLANE_WORDS ((HT2_SW_MAXCOLS + 1) * HT2_SW_SEG)
+#define HT2_SW_POOL_WORDS (3 * HT2_SW_PLANE_WORDS + 7 * HT2_SW_SEG)   /* per lane: H, E, F + query profile (5) + gap barrier + barrier/read-gap-open words */
 struct Ht2SwScratch {
-    // the three score matrices, striped (row i = half i / seg of word i % seg), column-major; one spare column
-    uint32_t H[(HT2_SW_MAXCOLS + 1) * HT2_SW_SEG];
-    uint32_t E[(HT2_SW_MAXCOLS + 1) * HT2_SW_SEG];
-    uint32_t F[(HT2_SW_MAXCOLS + 1) * HT2_SW_SEG];
-    uint32_t prof[5][HT2_SW_SEG], gbar[HT2_SW_SEG], rdoBar[HT2_SW_SEG];   // negated query profile / barrier / barrier + read-gap-open words
     uint32_t rep[((size_t)HT2_SW_MAXCOLS * HT2_MAX_RDLEN + 31) / 32];   // reported-through bit per cell (col * nrow + row)
     uint32_t nrow, seg;
     int32_t  lastH[HT2_SW_MAXCOLS];                          // last-row H per column (the candidates)
@@ -241,6 +244,8 @@ struct Ht2Work {
     uint32_t    nSearched[2];
     Ht2Res      res[2][HT2_MAX_RES];        // rs1u_/rs2u_ of AlnSinkWrap
     uint32_t    nRes[2];
+    Ht2Edit     resEdits[HT2_RES_EDITS];    // their edits, appended in report order
+    uint32_t    nResEdits;
     uint16_t    pairs[HT2_MAX_PAIRS][2];    // rs1_/rs2_ as indexes into res
     uint32_t    nPairs;
     // AlnSinkWrap best-score tracking (aln_sink.h:2600-2655)
@@ -460,6 +465,8 @@ struct Ht2AlignerT {
     const Ht2ParamsCore*  P;
     Ht2Work*              W;
     Ht2SwScratch*         sw;      // --bowtie2-dp scratch of this lane (NULL when dp is off)
+    uint32_t*             swPl;    // the lane's first word in the H / E / F plane pool
+    uint32_t              swStride;
 #ifdef HT2_ENABLE_SPLICED
     const Ht2SplTables*   splT;    // donor / acceptor probability tables (spliced mode)
 #endif
@@ -1567,7 +1574,7 @@ struct Ht2AlignerT {
 
     // ---- sink: AlnSinkWrap::report (aln_sink.h:2565-2655) + ReportingState ----
     HT2_NI void sinkReset(bool paired_) {
-        W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0;
+        W->nRes[0] = W->nRes[1] = 0; W->nPairs = 0; W->nResEdits = 0;
         // AlnSinkWrap::nextRead starts these at numeric_limits<THitInt>::min() (aln_sink.h:1896-1898)
         W->bestPair = W->best2Pair = HT2_MIN_I64;
         W->bestUnp[0] = W->best2Unp[0] = W->bestUnp[1] = W->best2Unp[1] = HT2_MIN_I64;
@@ -1622,19 +1629,23 @@ struct Ht2AlignerT {
         if (hit.score < minsc[rdi]) return false;
         uint32_t slot = (rdi == 0 && !rightendonly) ? 0 : 1;
         if (W->nRes[slot] >= HT2_MAX_RES) { W->err |= HT2_ERR_RES; return false; }
+        if (W->nResEdits + hit.nedits > HT2_RES_EDITS) { W->err |= HT2_ERR_RES; return false; }
         Ht2Res& r = W->res[slot][W->nRes[slot]++];
         r.tidx = hit.tidx; r.toff = hit.toff; r.fw = hit.fw; r.rdlen = rdlen; r.score = hit.score;
         r.trim5p = hit.fw ? hit.trim5 : hit.trim3;
         r.trim3p = hit.fw ? hit.trim3 : hit.trim5;
         r.nedits = hit.nedits;
-        for (uint32_t i = 0; i < hit.nedits; i++) { r.edits[i] = hit.edits[i]; r.edits[i].pos += hit.trim5; }
-        if (!hit.fw) invertPoss(r.edits, r.nedits, rdlen);
+        r.editOff = W->nResEdits;
+        W->nResEdits += hit.nedits;
+        Ht2Edit* red = W->resEdits + r.editOff;
+        for (uint32_t i = 0; i < hit.nedits; i++) { red[i] = hit.edits[i]; red[i].pos += hit.trim5; }
+        if (!hit.fw) invertPoss(red, r.nedits, rdlen);
         // AlnRes::setShape (aligner_result.cpp:111-129)
-        for (uint32_t i = 0; i < r.nedits; i++) r.edits[i].pos -= r.trim5p;
+        for (uint32_t i = 0; i < r.nedits; i++) red[i].pos -= r.trim5p;
         uint32_t rfextent = rdlen - r.trim5p - r.trim3p;
         for (uint32_t i = 0; i < r.nedits; i++) {
-            if (r.edits[i].type == HT2_EDIT_REF_GAP) rfextent--;
-            else if (r.edits[i].type == HT2_EDIT_READ_GAP) rfextent++;
+            if (red[i].type == HT2_EDIT_REF_GAP) rfextent--;
+            else if (red[i].type == HT2_EDIT_READ_GAP) rfextent++;
         }
         r.rfextent = rfextent;
 #ifdef HT2_ENABLE_SPLICED
@@ -1667,7 +1678,7 @@ struct Ht2AlignerT {
                             if (e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_SPL) e.pos = (uint32_t)(rdlen - e.pos);
                             else e.pos = (uint32_t)(rdlen - e.pos - 1);
                         }
-                        if (!editEq(rsi.edits[eidx], e)) break;
+                        if (!editEq(W->resEdits[rsi.editOff + eidx], e)) break;
                     }
                     if (eidx >= rsi.nedits) return true;
                 }

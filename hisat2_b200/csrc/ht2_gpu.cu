@@ -35,6 +35,7 @@ struct DevBatch {
     uint32_t        n_units;
     int32_t         paired;
     Ht2SwScratch*   sw;     // --bowtie2-dp scratch, one per launched thread (NULL when dp is off)
+    uint32_t*       swPool; // ... and the H / E / F plane pool: HT2_SW_POOL_WORDS words per thread, interleaved per warp
     const int32_t*  minscTab; // --score-min per read length (Ht2Params::minscTab)
 #ifdef HT2_ENABLE_SPLICED
     const Ht2SplTables* splT; // donor / acceptor probability tables (spliced mode)
@@ -188,10 +189,11 @@ __device__ __noinline__ void ht2_finish_unit(Ht2Work* W, const DevOut& o, uint32
                 d.fw = (uint8_t)r.fw; d.mate = (uint8_t)m; d.n_edits = (uint16_t)r.nedits;
                 d.trim5 = (uint16_t)r.trim5p; d.trim3 = (uint16_t)r.trim3p;
                 d.ref_extent = r.rfextent; d.edit_off = e;
+                const Ht2Edit* red = W->resEdits + r.editOff;
                 for (uint32_t k = 0; k < r.nedits; k++) {
                     ht2gpu_edit_t& de = o.edits[e++];
-                    de.pos = r.edits[k].pos; de.chr = r.edits[k].chr; de.qchr = r.edits[k].qchr;
-                    de.type = r.edits[k].type; de.pad = r.edits[k].pad; de.snp_id = r.edits[k].snpID;
+                    de.pos = red[k].pos; de.chr = red[k].chr; de.qchr = red[k].qchr;
+                    de.type = red[k].type; de.pad = red[k].pad; de.snp_id = red[k].snpID;
                 }
             }
         }
@@ -259,6 +261,8 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
     Ht2AlignerT<GRAPH> A;
     A.bind(blob, &P, base);
     A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
+    A.swPl = b.swPool ? b.swPool + ((size_t)blockIdx.x * NW + wib) * ((size_t)HT2_SW_POOL_WORDS * 32) + lane : NULL;
+    A.swStride = 32;
 #ifdef HT2_ENABLE_SPLICED
     A.splT = b.splT;
 #endif
@@ -563,6 +567,7 @@ struct ht2gpu_handle {
     int32_t*       dMinsc;   // --score-min table on the device (Ht2Params::minscTab)
     void*          dSplT;    // spliced builds: Ht2SplTables on the device
     Ht2SwScratch*  dSw;      // --bowtie2-dp: one scratch per launched thread
+    uint32_t*      dSwPool;  //               and the interleaved score-plane pool
     size_t         nWork;
     cudaStream_t   stream;
     cudaEvent_t    ev[4];
@@ -571,6 +576,8 @@ struct ht2gpu_handle {
     std::string    err;
     unsigned long long* dStats;   // HT2GPU_STATS=1: per-state round statistics of the pool kernel
     SamSlot        slots[HT2GPU_N_SLOTS];
+    void*          pipeCtx;       // ht2_pipeline.cpp's per-handle context
+    void         (*pipeCtxFree)(void*);
 };
 
 // Results live in ONE pinned host buffer per batch (D2H at PCIe speed instead of
@@ -677,6 +684,7 @@ static int finishOpen(ht2gpu_handle* h)
     if (h->P.bowtie2Dp) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
         size_t nThreads = (size_t)h->nSM * h->bpsm * (size_t)h->tpb;
         CK(cudaMalloc(&h->dSw, nThreads * sizeof(Ht2SwScratch)));
+        CK(cudaMalloc(&h->dSwPool, nThreads * (size_t)HT2_SW_POOL_WORDS * sizeof(uint32_t)));
     }
     {   // per-thread stack: what the kernels of this index type need, not a blanket value (the limit is
         // context-wide and the driver backs it for every resident thread).  Linear indexes have a statically
@@ -701,10 +709,11 @@ static int finishOpen(ht2gpu_handle* h)
 static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
-    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL; h->dMinsc = NULL; h->dSplT = NULL;
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL; h->dSwPool = NULL; h->dMinsc = NULL; h->dSplT = NULL;
     h->stream = 0; h->evCompute = 0;
     h->dStats = NULL;
     memset((void*)h->slots, 0, sizeof(h->slots));
+    h->pipeCtx = NULL; h->pipeCtxFree = NULL;
     if (opt) h->opt = *opt; else ht2gpu_default_options(&h->opt);
     h->device = h->opt.device;
     return h;
@@ -799,9 +808,11 @@ extern "C" uint32_t ht2gpu_ref_len(const ht2gpu_handle_t* h, uint32_t i) { retur
 extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
 {
     if (!h) return HT2GPU_OK;
+    if (h->pipeCtx && h->pipeCtxFree) h->pipeCtxFree(h->pipeCtx);
     if (h->dBlob && h->ownBlob) cudaFree(h->dBlob);
     if (h->dWork) cudaFree(h->dWork);
     if (h->dSw) cudaFree(h->dSw);
+    if (h->dSwPool) cudaFree(h->dSwPool);
     if (h->dMinsc) cudaFree(h->dMinsc);
     if (h->dSplT) cudaFree(h->dSplT);
     cudaFree(h->dStats);
@@ -902,7 +913,7 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
 {
     DevBatch db;
     db.seq = S.dSeq; db.qual = b->qual ? S.dQual : NULL; db.offs = S.dOffs; db.seeds = S.dSeeds;
-    db.n_units = units; db.paired = b->paired; db.sw = h->dSw; db.minscTab = h->dMinsc;
+    db.n_units = units; db.paired = b->paired; db.sw = h->dSw; db.swPool = h->dSwPool; db.minscTab = h->dMinsc;
 #ifdef HT2_ENABLE_SPLICED
     db.splT = (const Ht2SplTables*)h->dSplT;
 #endif
@@ -1110,6 +1121,8 @@ extern "C" int ht2gpu_sam_slots(const ht2gpu_handle_t*) { return HT2GPU_N_SLOTS;
 extern "C" void* ht2gpu_host_alloc(size_t bytes) { void* p = NULL; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : NULL; }
 extern "C" void ht2gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" void ht2gpu_set_error(ht2gpu_handle_t* h, const char* msg) { if (h) h->err = msg ? msg : ""; }
+extern "C" void* ht2gpu_ctx_get(ht2gpu_handle_t* h) { return h ? h->pipeCtx : NULL; }
+extern "C" void ht2gpu_ctx_set(ht2gpu_handle_t* h, void* ctx, void (*release)(void*)) { if (h) { h->pipeCtx = ctx; h->pipeCtxFree = release; } }
 
 extern "C" int ht2gpu_submit_sam(ht2gpu_handle_t* h, int slot, const ht2gpu_read_batch_t* b, const char* names,
                                  const uint32_t* name_offs, size_t names_bytes)
@@ -1236,7 +1249,7 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     rc = uploadBatch(h, S, b, NULL, NULL, 0, h2d);
     if (rc) return rc;
     DevBatch db;
-    db.seq = S.dSeq; db.qual = NULL; db.offs = S.dOffs; db.seeds = S.dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.minscTab = h->dMinsc;
+    db.seq = S.dSeq; db.qual = NULL; db.offs = S.dOffs; db.seeds = S.dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.swPool = NULL; db.minscTab = h->dMinsc;
 #ifdef HT2_ENABLE_SPLICED
     db.splT = NULL;
 #endif

@@ -23,6 +23,30 @@ namespace {
 double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 void* pinAlloc(size_t n) { return ht2gpu_host_alloc(n); }
 void pinFree(void* p) { ht2gpu_host_free(p); }
+
+// What a handle keeps between ht2gpu_run_reads calls: the parser's thread pool, its per-thread buffers and the
+// pinned staging buffers of every slot (allocating pinned memory costs more than parsing a batch).
+struct PipeCtx {
+    Ht2ThreadPool* pool;
+    Ht2ParseScratch scratch;
+    std::vector<Ht2HostBatch> stage;
+    std::mutex mu;               // one run at a time per handle
+    PipeCtx() : pool(NULL) {}
+    ~PipeCtx() { for (auto& hb : stage) hb.freeAll(); delete pool; }
+};
+void freeCtx(void* p) { delete (PipeCtx*)p; }
+PipeCtx* ctxOf(ht2gpu_handle_t* h, unsigned nth, int nSlots)
+{
+    PipeCtx* c = (PipeCtx*)ht2gpu_ctx_get(h);
+    if (!c) { c = new PipeCtx(); ht2gpu_ctx_set(h, c, freeCtx); }
+    if (!c->pool || c->pool->size() != nth) { delete c->pool; c->pool = new Ht2ThreadPool(nth); }
+    if ((int)c->stage.size() != nSlots) {
+        for (auto& hb : c->stage) hb.freeAll();
+        c->stage.assign((size_t)nSlots, Ht2HostBatch());
+        for (auto& hb : c->stage) { hb.alloc = pinAlloc; hb.release = pinFree; }
+    }
+    return c;
+}
 }
 
 extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* in, ht2gpu_sink_fn sink, void* ctx, ht2gpu_run_stats_t* st)
@@ -33,7 +57,11 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
     unsigned nth = in->threads > 0 ? (unsigned)in->threads : std::thread::hardware_concurrency();
     if (nth < 1) nth = 1;
     if (nth > 64) nth = 64;
-    Ht2ThreadPool pool(nth);
+    const int nSlots = ht2gpu_sam_slots(h);
+    PipeCtx* C = ctxOf(h, nth, nSlots);
+    std::lock_guard<std::mutex> runLock(C->mu);
+    Ht2ThreadPool& pool = *C->pool;
+    std::vector<Ht2HostBatch>& stage = C->stage;
     Ht2ReadSource a, b;
     std::string err;
     const bool paired = in->path2 != NULL || in->data2 != NULL;
@@ -60,15 +88,12 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
     const uint64_t nBatches = (r1 - r0 + perBatch - 1) / perBatch;
     Ht2ReadsOpts ro; ro.fastq = fastq; ro.trim5 = in->trim5; ro.trim3 = in->trim3; ro.phred64 = in->phred64 != 0; ro.seed = in->seed;
 
-    const int nSlots = ht2gpu_sam_slots(h);
-    std::vector<Ht2HostBatch> stage((size_t)nSlots);
-    for (auto& hb : stage) { hb.alloc = pinAlloc; hb.release = pinFree; }
     // slot states: 0 free, 1 submitted
     std::mutex mu; std::condition_variable cv;
     std::vector<int> state((size_t)nSlots, 0);
     uint64_t submitted = 0;
     int prodRc = HT2GPU_OK; std::string prodErr; bool prodDone = false;
-    double parseS = 0;
+    double parseS = 0, submitS = 0, waitS = 0, sinkS = 0;
 
     std::thread producer([&]() {
         for (uint64_t i = 0; i < nBatches; i++) {
@@ -78,13 +103,15 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
             const double tp = nowS();
             std::string e;
             int rc = HT2GPU_OK;
-            if (!ht2_parse_batch(a, paired ? &b : NULL, q0, q1, ro, stage[slot], pool, e)) rc = HT2GPU_ERR_ARG;
+            if (!ht2_parse_batch(a, paired ? &b : NULL, q0, q1, ro, stage[slot], pool, C->scratch, e)) rc = HT2GPU_ERR_ARG;
             parseS += nowS() - tp;
             if (rc == HT2GPU_OK) {
                 Ht2HostBatch& hb = stage[slot];
                 ht2gpu_read_batch_t rb; memset(&rb, 0, sizeof(rb));
                 rb.n_reads = hb.n_reads; rb.paired = paired ? 1 : 0; rb.seq = hb.seq; rb.qual = hb.haveQual ? hb.qual : NULL; rb.offs = hb.offs; rb.seeds = hb.seeds;
+                const double ts = nowS();
                 rc = ht2gpu_submit_sam(h, slot, &rb, hb.names, hb.nameOffs, hb.namesBytes);
+                submitS += nowS() - ts;
                 if (rc != HT2GPU_OK) e = ht2gpu_last_error(h);
             }
             std::lock_guard<std::mutex> lk(mu);
@@ -106,12 +133,16 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
             if (submitted <= i) { rc = prodRc != HT2GPU_OK ? prodRc : HT2GPU_ERR_ARG; break; }
         }
         ht2gpu_sam_result_t r;
+        const double tw = nowS();
         rc = ht2gpu_wait_sam(h, slot, &r);
+        waitS += nowS() - tw;
         if (rc != HT2GPU_OK) { prodErr = ht2gpu_last_error(h); break; }
         S.n_batches++; S.n_units += r.n_units; S.n_reads += stage[slot].n_reads; S.sam_bytes += r.sam_len; S.n_err_reads += r.n_err_reads;
         S.ms_align += r.ms_align; S.ms_sam += r.ms_sam; S.ms_h2d += r.ms_h2d; S.ms_d2h += r.ms_d2h;
         S.h2d_bytes += r.h2d_bytes; S.d2h_bytes += r.d2h_bytes; S.n_launches += r.n_launches;
+        const double tk = nowS();
         if (sink && r.sam_len) { if (sink(ctx, r.sam, r.sam_len) != 0) { rc = HT2GPU_ERR_ARG; prodErr = "the SAM sink reported an error"; } }
+        sinkS += nowS() - tk;
         { std::lock_guard<std::mutex> lk(mu); state[slot] = 0; if (rc != HT2GPU_OK) prodRc = rc; cv.notify_all(); }
         if (rc != HT2GPU_OK) break;
     }
@@ -119,9 +150,8 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
     producer.join();
     // drain anything still in flight after an error
     if (rc != HT2GPU_OK) for (int s = 0; s < nSlots; s++) if (state[s] == 1) { ht2gpu_sam_result_t r; ht2gpu_wait_sam(h, s, &r); }
-    for (auto& hb : stage) hb.freeAll();
     ht2_source_close(a); ht2_source_close(b);
-    S.s_parse = parseS; S.s_total = nowS() - t0;
+    S.s_parse = parseS; S.s_submit = submitS; S.s_wait = waitS; S.s_sink = sinkS; S.s_total = nowS() - t0;
     if (st) *st = S;
     if (rc != HT2GPU_OK) ht2gpu_set_error(h, prodErr.empty() ? "ht2gpu_run_reads failed" : prodErr.c_str());
     return rc;
@@ -155,7 +185,8 @@ extern "C" int ht2gpu_parse_reads(const ht2gpu_reads_input_t* in, ht2gpu_parsed_
         if (r0 > r1) r0 = r1;
         if (in->upto && r0 + in->upto < r1) r1 = r0 + in->upto;
         Ht2ReadsOpts ro; ro.fastq = fastq; ro.trim5 = in->trim5; ro.trim3 = in->trim3; ro.phred64 = in->phred64 != 0; ro.seed = in->seed;
-        ok = ht2_parse_batch(a, paired ? &b : NULL, r0, r1, ro, *hb, pool, err);
+        Ht2ParseScratch scratch;
+        ok = ht2_parse_batch(a, paired ? &b : NULL, r0, r1, ro, *hb, pool, scratch, err);
     }
     ht2_source_close(a); ht2_source_close(b);
     if (!ok) { hb->freeAll(); delete hb; return fail(err); }

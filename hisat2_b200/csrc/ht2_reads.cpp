@@ -305,14 +305,15 @@ template <typename T> bool ensure(Ht2HostBatch& b, T*& p, size_t count)
 
 } // namespace
 
+Ht2ParseScratch::Ht2ParseScratch() : impl(new std::vector<Local>()) {}
+Ht2ParseScratch::~Ht2ParseScratch() { delete (std::vector<Local>*)impl; }
+
 bool ht2_parse_batch(const Ht2ReadSource& a, const Ht2ReadSource* b, uint64_t r0, uint64_t r1, const Ht2ReadsOpts& o,
-                     Ht2HostBatch& out, Ht2ThreadPool& pool, std::string& err)
+                     Ht2HostBatch& out, Ht2ThreadPool& pool, Ht2ParseScratch& scratch, std::string& err)
 {
     const uint64_t nrec = r1 - r0;
     const unsigned T = nrec < 2048 ? 1 : pool.size();
-    static thread_local std::vector<Local>* tlsLocals = NULL;   // reused across batches by the (single) producer thread
-    if (!tlsLocals) tlsLocals = new std::vector<Local>();
-    std::vector<Local>& loc = *tlsLocals;
+    std::vector<Local>& loc = *(std::vector<Local>*)scratch.impl;
     if (loc.size() < T) loc.resize(T);
     auto parse = [&](unsigned t) {
         if (t >= T) return;

@@ -80,8 +80,15 @@ struct Ht2HostBatch {
     void freeAll();
 };
 
+// Per-thread parse buffers, kept across batches (and across runs) so that steady-state parsing touches no fresh memory.
+struct Ht2ParseScratch {
+    void* impl;
+    Ht2ParseScratch();
+    ~Ht2ParseScratch();
+};
+
 // Parse records [r0, r1) of 'a' (and, for pairs, the same records of 'b': reads are interleaved mate 1, mate 2).
 bool ht2_parse_batch(const Ht2ReadSource& a, const Ht2ReadSource* b, uint64_t r0, uint64_t r1, const Ht2ReadsOpts& o,
-                     Ht2HostBatch& out, Ht2ThreadPool& pool, std::string& err);
+                     Ht2HostBatch& out, Ht2ThreadPool& pool, Ht2ParseScratch& scratch, std::string& err);
 
 #endif

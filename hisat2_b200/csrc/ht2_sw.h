@@ -71,6 +71,11 @@ HT2_HD static bool swFrameRect(int64_t off, uint32_t rdlen, int64_t reflen, SwRe
 
 HT2_HD static uint8_t swMask2dna(int code) { return (uint8_t)("ACGTN"[code]); }
 
+// plane pool accessors (Ht2SwScratch, ht2_core.h): score planes 0 = H, 1 = E, 2 = F; small per-problem arrays
+// 0..4 = negated query profile per reference character, 5 = gap barrier, 6 = barrier + read-gap-open
+#define HT2_SWP(pl, idx) swPl[((size_t)(pl) * HT2_SW_PLANE_WORDS + (size_t)(idx)) * swStride]
+#define HT2_SWQ(k, s) swPl[((size_t)3 * HT2_SW_PLANE_WORDS + (size_t)(k) * HT2_SW_SEG + (size_t)(s)) * swStride]
+
 #define HT2_SW_TOP 16383      /* raw value of a perfect score; 0 = floor */
 #define HT2_SW_BAR 16384      /* gap-barrier penalty: larger than any raw value */
 
@@ -101,52 +106,50 @@ HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const
             g  |= (uint32_t)(uint16_t)(-bar) << (16 * k);
             go |= (uint32_t)(uint16_t)(-(bar + rdgapo)) << (16 * k);
         }
-        S.gbar[s] = g; S.rdoBar[s] = go;
-        for (int refc = 0; refc < 5; refc++) S.prof[refc][s] = w[refc];
+        HT2_SWQ(5, s) = g; HT2_SWQ(6, s) = go;
+        for (int refc = 0; refc < 5; refc++) HT2_SWQ(refc, s) = w[refc];
     }
     const uint32_t nRDE = ht2_v2_splat(-P->rdGapLinear);
     const uint32_t nRFO = ht2_v2_splat(-(P->rfGapConst + P->rfGapLinear)), nRFE = ht2_v2_splat(-P->rfGapLinear);
-    uint32_t* const Hz = S.H + (size_t)ncol * seg;   // an all-floor column standing in for column -1
-    for (uint32_t s = 0; s < seg; s++) { Hz[s] = 0; S.E[s] = 0; }
+    const size_t Hz = (size_t)ncol * seg;   // an all-floor column of H standing in for column -1
+    for (uint32_t s = 0; s < seg; s++) { HT2_SWP(0, Hz + s) = 0; HT2_SWP(1, s) = 0; }
     const uint32_t lastW = (nrow - 1) % seg, lastB = 16 * ((nrow - 1) / seg);
     int best = 0;
     for (uint32_t j = 0; j < ncol; j++) {
-        const uint32_t* prof = S.prof[rf[j] > 4 ? 4 : rf[j]];
-        uint32_t* Hc = S.H + (size_t)j * seg; uint32_t* Fc = S.F + (size_t)j * seg;
-        const uint32_t* Ec = S.E + (size_t)j * seg; uint32_t* En = S.E + (size_t)(j + 1) * seg;
-        const uint32_t* Hp = j ? S.H + (size_t)(j - 1) * seg : Hz;
+        const uint32_t pr = rf[j] > 4 ? 4u : (uint32_t)rf[j];
+        const size_t c0 = (size_t)j * seg, cn = (size_t)(j + 1) * seg, cp = j ? (size_t)(j - 1) * seg : Hz;   // this / next / previous column
         uint32_t vF = 0;
-        uint32_t vH = (Hp[seg - 1] << 16) | (uint32_t)HT2_SW_TOP;   // diagonal of row 0 = perfect; of row seg = last row of half 0
+        uint32_t vH = (HT2_SWP(0, cp + seg - 1) << 16) | (uint32_t)HT2_SW_TOP;   // diagonal of row 0 = perfect; of row seg = last row of half 0
         for (uint32_t s = 0; s < seg; s++) {
-            uint32_t vE = Ec[s];
-            vF = ht2_v2_addmax(vF, S.gbar[s], 0);                       // veto ref-gap extensions in barrier rows
-            Fc[s] = vF;
-            vH = ht2_v2_addmax(vH, prof[s], 0);                         // match / mismatch
+            uint32_t vE = HT2_SWP(1, c0 + s);
+            vF = ht2_v2_addmax(vF, HT2_SWQ(5, s), 0);                       // veto ref-gap extensions in barrier rows
+            HT2_SWP(2, c0 + s) = vF;
+            vH = ht2_v2_addmax(vH, HT2_SWQ(pr, s), 0);                         // match / mismatch
             vH = ht2_v2_max3(vH, vE, vF);
-            Hc[s] = vH;
-            vE = ht2_v2_addmax(vE, nRDE, ht2_v2_addmax(vH, S.rdoBar[s], 0));   // E of the next column
-            En[s] = vE;
+            HT2_SWP(0, c0 + s) = vH;
+            vE = ht2_v2_addmax(vE, nRDE, ht2_v2_addmax(vH, HT2_SWQ(6, s), 0));   // E of the next column
+            HT2_SWP(1, cn + s) = vE;
             vF = ht2_v2_addmax(vF, nRFE, ht2_v2_addmax(vH, nRFO, 0));   // F of the next row
-            vH = Hp[s];
+            vH = HT2_SWP(0, cp + s);
         }
         // lazy F: carry each half's last F into the other half's first rows while it still improves
         {
             uint32_t s = 0;
-            vF = ht2_v2_addmax(vF << 16, S.gbar[0], 0);
+            vF = ht2_v2_addmax(vF << 16, HT2_SWQ(5, 0), 0);
             for (;;) {
-                const uint32_t old = Fc[s];
+                const uint32_t old = HT2_SWP(2, c0 + s);
                 const uint32_t nf = ht2_v2_max(old, vF);
                 if (nf == old) break;
-                Fc[s] = nf;
-                const uint32_t vh = ht2_v2_max(Hc[s], nf);
-                Hc[s] = vh;
-                En[s] = ht2_v2_max(En[s], ht2_v2_addmax(vh, S.rdoBar[s], 0));
+                HT2_SWP(2, c0 + s) = nf;
+                const uint32_t vh = ht2_v2_max(HT2_SWP(0, c0 + s), nf);
+                HT2_SWP(0, c0 + s) = vh;
+                HT2_SWP(1, cn + s) = ht2_v2_max(HT2_SWP(1, cn + s), ht2_v2_addmax(vh, HT2_SWQ(6, s), 0));
                 vF = nf;
                 if (++s == seg) { s = 0; vF <<= 16; }
-                vF = ht2_v2_addmax(ht2_v2_addmax(vF, nRFE, 0), S.gbar[s], 0);
+                vF = ht2_v2_addmax(ht2_v2_addmax(vF, nRFE, 0), HT2_SWQ(5, s), 0);
             }
         }
-        const int lr = (int)((Hc[lastW] >> lastB) & 0xffffu);
+        const int lr = (int)((HT2_SWP(0, c0 + lastW) >> lastB) & 0xffffu);
         S.lastH[j] = lr - HT2_SW_TOP;
         if (lr > best) best = lr;
     }
@@ -154,8 +157,8 @@ HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const
     return best - HT2_SW_TOP;
 }
 
-HT2_HD static int swRaw(const uint32_t* plane, uint32_t seg, uint32_t row, uint32_t col) {
-    return (int)((plane[(size_t)col * seg + row % seg] >> (16 * (row / seg))) & 0xffffu);
+HT2_HD int swRaw(int plane, uint32_t seg, uint32_t row, uint32_t col) const {
+    return (int)((HT2_SWP(plane, (size_t)col * seg + row % seg) >> (16 * (row / seg))) & 0xffffu);
 }
 // Move bits of a cell from the score planes (what the reference recomputes at every visited cell,
 // aligner_swsse_ee_u8.cpp:1376-1545); row > 0.
@@ -166,13 +169,13 @@ HT2_NI uint32_t swCellFromPlanes(const uint8_t* rd, const uint8_t* rf, uint32_t 
     const int rfgapo = P->rfGapConst + P->rfGapLinear, rfgape = P->rfGapLinear;
     const uint32_t gapbar = (uint32_t)P->gapbar;
     const bool gb = (row < gapbar) || (nrow - 1 - row < gapbar);
-    const int h = swRaw(S.H, seg, row, col), e = swRaw(S.E, seg, row, col), f = swRaw(S.F, seg, row, col);
-    const int hup = swRaw(S.H, seg, row - 1, col), fup = swRaw(S.F, seg, row - 1, col);
+    const int h = swRaw(0, seg, row, col), e = swRaw(1, seg, row, col), f = swRaw(2, seg, row, col);
+    const int hup = swRaw(0, seg, row - 1, col), fup = swRaw(2, seg, row - 1, col);
     uint32_t hm = 0, em = 0, fm = 0;
     if (!gb) { if (h + rfgapo == hup) hm |= 1; if (h + rfgape == fup) hm |= 4; }
     if (col > 0) {
-        const int hleft = swRaw(S.H, seg, row, col - 1), eleft = swRaw(S.E, seg, row, col - 1);
-        const int hd = swRaw(S.H, seg, row - 1, col - 1);
+        const int hleft = swRaw(0, seg, row, col - 1), eleft = swRaw(1, seg, row, col - 1);
+        const int hd = swRaw(0, seg, row - 1, col - 1);
         const int rdc = rd[row], refc = rf[col];
         const int pen = (rdc > 3 || refc > 3) ? P->npen : (rdc == refc ? 0 : (int)S.rowPen[row]);
         if (!gb) { if (h + rdgapo == hleft) hm |= 2; if (h + rdgape == eleft) hm |= 8; }

@@ -236,6 +236,7 @@ typedef struct {
 typedef struct {
     uint64_t n_reads, n_units, sam_bytes, n_err_reads, n_batches;
     double   s_index, s_parse, s_total;          /* host wall clock: record indexing, batch parsing (overlapped), whole call */
+    double   s_submit, s_wait, s_sink;           /* host wall clock inside ht2gpu_submit_sam / ht2gpu_wait_sam / the sink */
     float    ms_h2d, ms_align, ms_sam, ms_d2h;   /* summed CUDA-event times of the batches */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t n_launches, pad;
@@ -259,6 +260,9 @@ void ht2gpu_free_parsed(ht2gpu_parsed_reads_t* p);
 void* ht2gpu_host_alloc(size_t bytes);
 void ht2gpu_host_free(void* p);
 void ht2gpu_set_error(ht2gpu_handle_t* h, const char* msg);
+/* An opaque per-handle context slot (the pipeline keeps its thread pool and pinned staging there); freed by ht2gpu_close. */
+void* ht2gpu_ctx_get(ht2gpu_handle_t* h);
+void ht2gpu_ctx_set(ht2gpu_handle_t* h, void* ctx, void (*release)(void*));
 
 /* ---- seed search on its own (linear AND graph/SNP indexes) -------------------
  * For every read and strand (fw first): the chain of partial searches

@@ -96,8 +96,9 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
             d.tidx = r.tidx; d.toff = r.toff; d.score = (int32_t)r.score; d.fw = (uint8_t)r.fw; d.mate = (uint8_t)m;
             d.n_edits = (uint16_t)r.nedits; d.trim5 = (uint16_t)r.trim5p; d.trim3 = (uint16_t)r.trim3p; d.ref_extent = r.rfextent;
             d.edit_off = (uint32_t)bEdits.size();
+            const Ht2Edit* red = Wk->resEdits + r.editOff;
             for (uint32_t k = 0; k < r.nedits; k++) {
-                ht2gpu_edit_t e; e.pos = r.edits[k].pos; e.chr = r.edits[k].chr; e.qchr = r.edits[k].qchr; e.type = r.edits[k].type; e.pad = r.edits[k].pad; e.snp_id = r.edits[k].snpID;
+                ht2gpu_edit_t e; e.pos = red[k].pos; e.chr = red[k].chr; e.qchr = red[k].qchr; e.type = red[k].type; e.pad = red[k].pad; e.snp_id = red[k].snpID;
                 bEdits.push_back(e);
             }
             bAlns.push_back(d);
@@ -107,6 +108,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
     };
     Ht2Work* W = new Ht2Work();
     Ht2SwScratch* swScratch = P.bowtie2Dp ? new Ht2SwScratch() : NULL;
+    uint32_t* swPool = P.bowtie2Dp ? new uint32_t[HT2_SW_POOL_WORDS] : NULL;
     Ht2AlignerT<GRAPH> A;
     size_t nerr = 0;
     uint64_t nLF = 0;
@@ -117,7 +119,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         r1.seed = ht2_gen_rand_seed(r1, 0); r2.seed = ht2_gen_rand_seed(r2, 0);
         int64_t ms1 = ht2_minsc(P, (uint32_t)r1.seq.size()), ms2 = ht2_minsc(P, (uint32_t)r2.seq.size());
         Ht2ReadFilters f1 = ht2_filters(r1, ms1), f2 = ht2_filters(r2, ms2);
-        A.bind(img->blob.data(), &P, W); A.sw = swScratch; HT2_SET_SPLT(A);
+        A.bind(img->blob.data(), &P, W); A.sw = swScratch; A.swPl = swPool; A.swStride = 1; HT2_SET_SPLT(A);
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         bool p1 = f1.pass(), p2 = f2.pass();
         W->rnd.init((p1 && p2) ? (r1.seed ^ r2.seed) : r1.seed);
@@ -151,7 +153,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         rd.seed = ht2_gen_rand_seed(rd, 0);
         int64_t minsc = ht2_minsc(P, (uint32_t)rd.seq.size());
         Ht2ReadFilters f = ht2_filters(rd, minsc);
-        A.bind(img->blob.data(), &P, W); A.sw = swScratch; HT2_SET_SPLT(A);
+        A.bind(img->blob.data(), &P, W); A.sw = swScratch; A.swPl = swPool; A.swStride = 1; HT2_SET_SPLT(A);
         W->err = 0; W->localindexatts = 0; W->maxLocalindexatts = 0; W->nLF = 0; W->nSides = 0; W->algBytes = 0; W->maxPool = W->maxDepth = W->maxEdits = 0;
         W->rnd.init(rd.seed);
         A.paired = false; A.rightendonly = false;
@@ -202,7 +204,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
 static int swSelfTest(int n, unsigned seed) {
     Ht2Params P; memset(&P, 0, sizeof(P));
     Ht2Work* W = new Ht2Work(); Ht2SwScratch* S = new Ht2SwScratch();
-    Ht2AlignerT<false> A; A.blob = NULL; A.H = NULL; A.P = &P; A.W = W; A.sw = S;
+    Ht2AlignerT<false> A; A.blob = NULL; A.H = NULL; A.P = &P; A.W = W; A.sw = S; A.swPl = new uint32_t[HT2_SW_POOL_WORDS]; A.swStride = 1;
     uint32_t rng = seed ? seed : 1;
     auto rnd = [&](uint32_t m) { rng = rng * 1664525u + 1013904223u; return (rng >> 8) % m; };
     int bad = 0; long cells = 0, traced = 0;

@@ -238,6 +238,53 @@ def test_read_front_end_matches_python_restatement(lib, tmp_path):
         RB.parse(g("tiny_pe_1.fa"), g("tiny_se.fa"))
 
 
+def test_ht2_h_clients_link_unchanged(lib, tmp_path):
+    """libht2gpu.so exports the hisat2lib API (hisat2lib/ht2.h:67-150) under the reference's names and struct
+    layouts: a C client compiled against the REFERENCE's own ht2.h links to this library and reads the reference
+    names of the tiny fixture.  Without /root/reference (the GPU box) the same client is built from declarations
+    written out here."""
+    ref_h = "/root/reference/hisat2lib"
+    src = str(tmp_path / "client.c")
+    decls = '#include "ht2.h"' if os.path.exists(os.path.join(ref_h, "ht2.h")) else """
+#include <stdint.h>
+typedef int ht2_error_t; typedef void* ht2_handle_t;
+struct ht2_options { int offRate, useMm, useShmem, mmSweep, noRefNames, noSplicedAlignment, gVerbose, startVerbose, sanityCheck, useHaplotype; };
+typedef struct ht2_options ht2_option_t;
+struct ht2_index_getrefnames_result { int count; char* names[0]; };
+ht2_handle_t ht2_init(const char*, ht2_option_t*); void ht2_close(ht2_handle_t); ht2_error_t ht2_init_options(ht2_option_t*);
+const char* ht2_index_getrefnamebyid(ht2_handle_t, uint32_t);
+ht2_error_t ht2_index_getrefnames(ht2_handle_t, struct ht2_index_getrefnames_result**);
+"""
+    open(src, "w").write(decls + """
+#include <stdio.h>
+#include <stdlib.h>
+int main(int argc, char** argv) {
+    ht2_option_t o;
+    if (ht2_init_options(&o) != 0 || o.offRate != -1 || o.noSplicedAlignment != 0) return 2;
+    ht2_handle_t h = ht2_init(argv[1], &o);
+    if (!h) return 3;
+    struct ht2_index_getrefnames_result* r = NULL;
+    if (ht2_index_getrefnames(h, &r) != 0) return 4;
+    printf("%d\\n", r->count);
+    for (int i = 0; i < r->count; i++) printf("%s|%s\\n", r->names[i], ht2_index_getrefnamebyid(h, (uint32_t)i));
+    printf("%s\\n", ht2_index_getrefnamebyid(h, (uint32_t)r->count) ? "extra" : "null");
+    free(r);
+    ht2_close(h);
+    return 0;
+}
+""")
+    exe = str(tmp_path / "client")
+    libdir = os.path.join(ROOT, "hisat2_b200")
+    subprocess.run(["gcc", "-std=gnu99", "-o", exe, src, "-I", ref_h, "-L", libdir, "-l:libht2gpu.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe, os.path.join(GOLDEN, "tiny")], check=True, stdout=subprocess.PIPE).stdout.decode().splitlines()
+    from hisat2_b200 import api
+    names = [l.split("\t")[1][3:] for l in open(os.path.join(GOLDEN, "tiny_se.sam")).read().splitlines() if l.startswith("@SQ")]
+    assert int(out[0]) == len(names) and out[-1] == "null"
+    for tok, nm in zip(out[1:-1], names):
+        a, b = tok.split("|")
+        assert a == b and a.split()[0] == nm
+
+
 def test_abi_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "ht2gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(ht2gpu_[a-z_]+)\s*\(", hdr)))
