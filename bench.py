@@ -7,7 +7,7 @@
 Workload (config.workload): BASELINE.json configs[2], the configuration the metric is quoted on -- the linear
 22_20-21M example index, a FIXED set of 10 M synthetic 2x101-bp pairs (seeded generator, tools/simreads_fast.c),
 --no-spliced-alignment -- sharded over the N ranks by contiguous pair ranges (strong scaling).  One "step" =
-one pass of the whole path over the rank's shard, in device batches of 1 M reads.
+one pass of the whole path over the rank's shard, in device batches of 4 M reads.
   e2e   : FASTA bytes in host memory -> SAM bytes in host memory through ht2gpu_run_reads (multi-threaded
           parser, H2D, alignment kernel, SAM kernels, D2H), host wall clock, max over ranks.  THE headline.
   value : the same job counted on the device only: reads / sum of the CUDA-event times of the alignment and
@@ -217,7 +217,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--pairs", type=int, default=10000000, help="pairs of the whole job (fixed as N grows)")
-    ap.add_argument("--batch-reads", type=int, default=1000000, help="reads per device batch")
+    ap.add_argument("--batch-reads", type=int, default=4000000, help="reads per device batch")
     ap.add_argument("--ref-sample-pairs", type=int, default=500000, help="pairs per step of the CPU reference (bounded sample)")
     ap.add_argument("--threads", type=int, default=0, help="host parser threads per rank (0 = cores / local ranks, at most 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -86,7 +86,7 @@ EXPORTS = [
     "ht2gpu_seed_search", "ht2gpu_free_seed_results", "ht2gpu_index_is_graph",
     "ht2gpu_sam_slots", "ht2gpu_submit_sam", "ht2gpu_wait_sam", "ht2gpu_align_sam", "ht2gpu_run_reads",
     "ht2gpu_host_alloc", "ht2gpu_host_free", "ht2gpu_set_error", "ht2gpu_parse_reads", "ht2gpu_free_parsed",
-    "ht2gpu_ctx_get", "ht2gpu_ctx_set",
+    "ht2gpu_ctx_get", "ht2gpu_ctx_set", "ht2gpu_run_reads_multi", "ht2gpu_open_peer",
 ]
 
 
@@ -144,6 +144,8 @@ def load_library(path=None):
     lib.ht2gpu_wait_sam.argtypes = [C.c_void_p, C.c_int, C.POINTER(CSamResult)]
     lib.ht2gpu_align_sam.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CSamResult)]
     lib.ht2gpu_run_reads.argtypes = [C.c_void_p, C.POINTER(CReadsInput), SINK_FN, C.c_void_p, C.POINTER(CRunStats)]
+    lib.ht2gpu_run_reads_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(CReadsInput), SINK_FN, C.c_void_p, C.POINTER(CRunStats)]
+    lib.ht2gpu_open_peer.argtypes = [C.c_void_p, C.POINTER(Options), C.POINTER(C.c_void_p)]
     lib.ht2gpu_host_alloc.argtypes = [C.c_size_t]; lib.ht2gpu_host_alloc.restype = C.c_void_p
     lib.ht2gpu_host_free.argtypes = [C.c_void_p]
     lib.ht2gpu_set_error.argtypes = [C.c_void_p, C.c_char_p]
@@ -419,6 +421,7 @@ class Index(object):
 
     def __init__(self, base=None, image=None, device_image=None, device=0, **opts):
         self._lib = load_library()
+        self._opts = dict(opts)
         o = Options()
         self._lib.ht2gpu_default_options(C.byref(o))
         o.device = device
@@ -484,9 +487,27 @@ class Index(object):
             return s, {k: getattr(cr, k) for k, _ in CSamResult._fields_ if k != "sam"}
         return s
 
-    def run_reads(self, path1=None, path2=None, data1=None, data2=None, fastq=False, collect=True, **kw):
-        """ht2gpu_run_reads: FASTA/FASTQ (files or bytes in host memory) -> SAM records through the overlapped
-        pipeline.  Returns (sam bytes or None, stats dict)."""
+    def peer(self, device):
+        """ht2gpu_open_peer: a replica of this index on another device of this process (device-to-device copy)."""
+        o = Options()
+        self._lib.ht2gpu_default_options(C.byref(o))
+        for k, v in self._opts.items():
+            setattr(o, k, v)
+        o.device = device
+        other = Index.__new__(Index)
+        other._lib = self._lib
+        other._opts = dict(self._opts)
+        other._h = C.c_void_p()
+        rc = self._lib.ht2gpu_open_peer(self._h, C.byref(o), C.byref(other._h))
+        if rc != 0:
+            msg = self._lib.ht2gpu_last_error(other._h).decode() if other._h else "open failed"
+            other.close()
+            raise Ht2GpuError("ht2gpu_open_peer rc=%d: %s" % (rc, msg))
+        return other
+
+    def run_reads(self, path1=None, path2=None, data1=None, data2=None, fastq=False, collect=True, peers=(), **kw):
+        """ht2gpu_run_reads(_multi): FASTA/FASTQ (files or bytes in host memory) -> SAM records through the overlapped
+        pipeline, on this index's device and on the devices of `peers`.  Returns (sam bytes or None, stats dict)."""
         ri = CReadsInput()
         keep = []
         if path1 is not None:
@@ -512,7 +533,8 @@ class Index(object):
             return 0
         cb = SINK_FN(_sink) if collect else SINK_FN()     # NULL sink: the text still lands in pinned host memory
         st = CRunStats()
-        self._check(self._lib.ht2gpu_run_reads(self._h, C.byref(ri), cb, None, C.byref(st)), "ht2gpu_run_reads")
+        hs = (C.c_void_p * (1 + len(peers)))(self._h, *[p._h for p in peers])
+        self._check(self._lib.ht2gpu_run_reads_multi(hs, len(hs), C.byref(ri), cb, None, C.byref(st)), "ht2gpu_run_reads")
         stats = {k: getattr(st, k) for k, _ in CRunStats._fields_ if k != "pad"}
         return (b"".join(chunks) if collect else None), stats
 

@@ -12,7 +12,7 @@
 static void usage() {
     fprintf(stderr, "hisat2-b200 -x <index> {-U <r> | -1 <m1> -2 <m2>} [-S out.sam] [-f|-q] --no-spliced-alignment [-k N]\n"
                     "            [--mp MX,MN] [--sp MX,MN] [--np N] [--rdg C,L] [--rfg C,L] [--ignore-quals] [--nofw] [--norc]\n"
-                    "            [-I N] [-X N] [--no-mixed] [--no-discordant] [--seed N] [--batch N] [--device N] [-p N]\n"
+                    "            [-I N] [-X N] [--no-mixed] [--no-discordant] [--seed N] [--batch N] [--device N] [--gpus N] [-p N]\n"
                     "            [-5 N] [-3 N] [-s N] [-u N] [--phred33|--phred64] [--no-temp-splicesite]\n"
                     "            [--bowtie2-dp 0|1|2] [--score-min F,C,L] [--gbar N] [--sensitive] [--very-sensitive] [--fast]\n");
 }
@@ -23,8 +23,8 @@ int main(int argc, char** argv)
     ht2gpu_options_t o; ht2gpu_default_options(&o);
     o.no_spliced_alignment = 0; // must be requested explicitly, like the reference's default is spliced
     const char *idx = NULL, *u = NULL, *m1 = NULL, *m2 = NULL, *out = NULL;
-    bool fastq = true; size_t batchSz = 1000000; uint32_t gseed = 0;
-    int trim5 = 0, trim3 = 0, threads = 0; bool phred64 = false; uint64_t skip = 0, upto = 0;
+    bool fastq = true; size_t batchSz = 0 /* library default */; uint32_t gseed = 0;
+    int trim5 = 0, trim3 = 0, threads = 0, gpus = 1; bool phred64 = false; uint64_t skip = 0, upto = 0;
     bool sensitive = false, verySensitive = false, fast = false, noTempSpliceSite = false;
     bool mpGiven = false;   // "--mp a,b" becomes MMP=Q,a,b, which switches the cost model back to quality-aware even
                             // under --ignore-quals (aligner_seed_policy.cpp:396-418)
@@ -45,6 +45,7 @@ int main(int argc, char** argv)
         else if (a == "--no-mixed") o.no_mixed = 1; else if (a == "--no-discordant") o.no_discordant = 1;
         else if (a == "--seed") gseed = (uint32_t)atoi(next()); else if (a == "--batch") batchSz = (size_t)atol(next());
         else if (a == "--device") o.device = atoi(next());
+        else if (a == "--gpus") gpus = atoi(next());   // devices device .. device + gpus - 1: batches round-robin, output in input order
         else if (a == "--bowtie2-dp") { o.bowtie2_dp = atoi(next()); if (o.bowtie2_dp < 0 || o.bowtie2_dp > 2) { fprintf(stderr, "Error: --bowtie2-dp arg must be 0, 1, or 2\n"); return 1; } }
         else if (a == "--gbar") o.gbar = atoi(next());
         else if (a == "--score-min" || a == "--min-score") {   // <type>,<const>,<coeff>; missing tokens keep the default (PARSE_FUNC, aligner_seed_policy.cpp:47-62)
@@ -93,7 +94,15 @@ int main(int argc, char** argv)
     in.skip = skip; in.upto = upto; in.batch_reads = (uint32_t)batchSz; in.threads = threads;
     ht2gpu_run_stats_t st;
     auto sink = [](void* ctx, const char* sam, size_t len) -> int { return fwrite(sam, 1, len, (FILE*)ctx) == len ? 0 : 1; };
-    if (ht2gpu_run_reads(h, &in, sink, fo, &st) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(h)); return 1; }
+    std::vector<ht2gpu_handle_t*> hs(1, h);
+    for (int g = 1; g < gpus; g++) {   // replicate the index device to device
+        ht2gpu_options_t og = o; og.device = o.device + g;
+        ht2gpu_handle_t* hg = NULL;
+        if (ht2gpu_open_peer(h, &og, &hg) != HT2GPU_OK) { fprintf(stderr, "Error: device %d: %s\n", og.device, ht2gpu_last_error(hg)); return 1; }
+        hs.push_back(hg);
+    }
+    if (ht2gpu_run_reads_multi(hs.data(), (int)hs.size(), &in, sink, fo, &st) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(h)); return 1; }
+    for (size_t g = 1; g < hs.size(); g++) ht2gpu_close(hs[g]);
     if (st.n_err_reads)
         fprintf(stderr, "Warning: %llu read(s) exceeded a device-side capacity; their records may differ from hisat2's\n", (unsigned long long)st.n_err_reads);
     if (fo != stdout) fclose(fo);

@@ -287,6 +287,11 @@ struct Ht2Work {
     uint8_t     curRdi, curFw, alignRet, pad8;
     uint8_t     found[2][2];
     uint32_t    hybIter, hybHj, mateI, mateJ, mateSize[2];
+    // partialSearch continuation (time slicing, HT2_PS_SLICE): a search that has not finished after a slice of LF
+    // steps parks its loop state here and the slot stays in TS_PS, so that a round never lasts longer than one slice
+    // while most lanes of the group have long finished (a partial search is ~12 steps on average, ~90 at most)
+    uint32_t    psCont, psTop, psBot, psNtop, psNbot, psDep, psSame, psSimilar;
+    uint8_t     psPseudo, psAnchor, psPad[2];
     Ht2Frame    frames[HT2_DEPTH_CAP];
     uint32_t    nSides;   // sides touched
     uint32_t    algBytes; // algorithmic bytes: sides*sideSz + ftab/eftab entries + SA samples + 2-bit ref bytes
@@ -811,9 +816,13 @@ struct Ht2AlignerT {
     }
 
     // HI_Aligner::partialSearch (hi_aligner.h:6361-6600).  Returns stop
-    // flags through pseudogeneStop/anchorStop like the reference.
-    HT2_NI void partialSearch(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
-        if (GRAPH) { partialSearchGraph(rdi, fw, pseudogeneStop, anchorStop); return; }
+    // flags through pseudogeneStop/anchorStop like the reference.  Returns false when the search was parked after a
+    // slice of LF steps (W->psCont): the caller calls again, with the same arguments, to continue it.
+#ifndef HT2_PS_SLICE
+#define HT2_PS_SLICE 16
+#endif
+    HT2_NI bool partialSearch(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
+        if (GRAPH) { partialSearchGraph(rdi, fw, pseudogeneStop, anchorStop); return true; }
         bool pseudogeneStop_ = pseudogeneStop, anchorStop_ = anchorStop;
         pseudogeneStop = anchorStop = false;
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
@@ -821,19 +830,28 @@ struct Ht2AlignerT {
         const uint32_t len = W->rd[rdi].len;
         const uint8_t* seq = W->rd[rdi].seq[fw ? 0 : 1];
         const uint32_t minK = P->minK;
-        hit.numPartialSearch++;
+        const bool resume = W->psCont != 0;
+        if (!resume) hit.numPartialSearch++;
         uint32_t offset = hit.cur;
         uint32_t dep = offset;
         uint32_t left = len - dep;
-        if (hit.nhits >= HT2_MAX_PHITS) { W->err |= HT2_ERR_PHITS; hit.cur = len; hit.done = 1; return; }
+        if (!resume && hit.nhits >= HT2_MAX_PHITS) { W->err |= HT2_ERR_PHITS; hit.cur = len; hit.done = 1; return true; }
         Ht2BwtHit& ph = hit.hits[hit.nhits];
+        uint32_t top = 0, bot = 0, ntop = 0, nbot = 0;
+        uint32_t same_range = 0, similar_range = 0;
+        if (resume) {
+            top = W->psTop; bot = W->psBot; ntop = W->psNtop; nbot = W->psNbot; dep = W->psDep;
+            same_range = W->psSame; similar_range = W->psSimilar;
+            pseudogeneStop_ = W->psPseudo != 0; anchorStop_ = W->psAnchor != 0;
+            W->psCont = 0;
+        } else {
         ph.top = ph.bot = ph.node_top = ph.node_bot = HT2_IDX_MAX32;
         ph.bwoff = offset; ph.hit_type = HT2_CANDIDATE_HIT; ph.hasCoords = 0;
         if (left < ftabLen + 1) {
             hit.cur = len;
             ph.len = hit.cur - offset; hit.nhits++;
             hit.done = 1;
-            return;
+            return true;
         }
         for (uint32_t i = 0; i < ftabLen; i++) {
             int c = seq[len - dep - 1 - i];
@@ -841,10 +859,9 @@ struct Ht2AlignerT {
                 hit.cur += (i + 1);
                 ph.len = hit.cur - offset; hit.nhits++;
                 if (hit.cur >= len) hit.done = 1;
-                return;
+                return true;
             }
         }
-        uint32_t top = 0, bot = 0, ntop = 0, nbot = 0;
         ht2_ftab_lohi(gfm, seq, len - dep - ftabLen, top, bot);
         W->algBytes += 8;
         dep += ftabLen;
@@ -852,13 +869,21 @@ struct Ht2AlignerT {
             hit.cur = dep;
             ph.len = hit.cur - offset; hit.nhits++;
             if (hit.cur >= len) hit.done = 1;
-            return;
+            return true;
         }
-        uint32_t same_range = 0, similar_range = 0;
+        }
         uint32_t khits5 = P->khits < 5 ? P->khits : 5;
         uint32_t nlf = 0, lfBytes = 0;
+        uint32_t budget = HT2_PS_SLICE;
         // node_range starts as (0,0) in the reference (hi_aligner.h:6396)
         while (dep < len) {
+            if (budget-- == 0) {   // park: the slot stays in TS_PS and is regrouped with other searches
+                W->psCont = 1; W->psTop = top; W->psBot = bot; W->psNtop = ntop; W->psNbot = nbot; W->psDep = dep;
+                W->psSame = same_range; W->psSimilar = similar_range;
+                W->psPseudo = pseudogeneStop_ ? 1 : 0; W->psAnchor = anchorStop_ ? 1 : 0;
+                W->nLF += nlf; W->algBytes += lfBytes;
+                return false;
+            }
             int c = seq[len - dep - 1];
             uint32_t ttop = 0, tbot = 0;
             if (c <= 3) lfStep(gfm, top, bot, c, ttop, tbot, nlf, lfBytes);
@@ -912,6 +937,7 @@ struct Ht2AlignerT {
                 hit.done = 1;
             }
         }
+        return true;
     }
 
     // HI_Aligner::globalGFMSearch / localGFMSearch (hi_aligner.h:6606-6744,
@@ -1795,7 +1821,7 @@ struct Ht2AlignerT {
                     }
                 }
             }
-            partialSearch(rdi, fw, pseudogeneStop, anchorStop);
+            while (!partialSearch(rdi, fw, pseudogeneStop, anchorStop)) {}
             if (hit.done) return true;
             if (!pseudogeneStop) { if (hit.cur + 1 < hit.len) hit.cur++; }
             if (anchorStop) { hit.done = 1; return true; }

@@ -224,110 +224,104 @@ __device__ __forceinline__ uint32_t rg_code(const Ht2Work* W)
 }
 
 // ---------------------------------------------------------------------------
-// ht2_align_pool_kernel: block-shared slot pool, warp-independent rounds.
+// ht2_align_pool_kernel: block-shared slot pool, warp-independent rounds, lock-free claims.
 //
-// The NW warps of a block share one pool of NW*32*K read slots whose state
-// codes live in shared memory.  Every warp runs its own rounds -- claim up to
-// 32 slots that are in the block's current target state (one
-// warp at a time, under a block lock held for the few hundred cycles of the
-// gather), run one segment of each, publish the new state codes -- and never
-// waits for another warp's segments.  The target state is a block-wide hint: warps stay
-// on it while it has plenty of claimable slots and otherwise re-elect the most
-// populous state from per-state counters, so the warps of an SM execute the
-// same code most of the time (instruction fetch is the scarce resource: the
-// 32 KB L1.5 I-cache and the GPC instruction cache saturate when every warp
-// walks different code) while groups are drawn from a pool large enough to
-// fill all 32 lanes.
+// The NW warps of a block share one pool of NW*32*K read slots.  What a slot has to do next (its state code)
+// is kept as one BIT PER SLOT in a per-state bitmap in shared memory (a slot that is being run is in no bitmap).
+// Every warp runs its own rounds: pick the block's target state, claim up to 32 of its slots straight out of the
+// bitmap (lane w reads word w, a warp prefix sum decides how many bits each lane may take, atomicAnd takes them,
+// the returned old word tells which ones were really won), run one segment of each claimed slot on its 32 lanes,
+// and publish the new states with atomicOr.  No lock, no scan over the slot array, no waiting for another warp's
+// segments (round 1 serialised the gather under a block lock: 20 % of all executed instructions were warps
+// spinning on it, profiles/r02_*).  The target state is a block-wide hint: warps stay on it while it has
+// plenty of claimable slots and otherwise re-elect the most populous state from per-state counters, so the warps
+// of an SM execute the same code most of the time (instruction fetch is the scarce resource: the L1.5 I-cache and
+// the GPC instruction cache saturate when every warp walks different code) while groups are drawn from a pool
+// large enough to fill all 32 lanes.
 // ---------------------------------------------------------------------------
-#define RG_BUSY 254u
-#define PL_MIN_GROUP 16
-
 template <int NW, int K, bool GRAPH>
 __global__ void __launch_bounds__(32 * NW)
 ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
 {
     constexpr int S = NW * 32 * K;      // slots of this block
-    constexpr int NJ = S / 32;          // slots a lane may claim: lane + 32*j
-    __shared__ unsigned int sCode[S];
-    __shared__ int sCount[RG_BINS];     // claimable slots per state code
+    constexpr int NWORD = S / 32;       // bitmap words per state; lane w owns word w during a gather
+    static_assert(NWORD <= 32, "one bitmap word per lane");
+    __shared__ unsigned int sBits[RG_BINS][NWORD];
+    __shared__ int sCount[RG_BINS];     // claimable slots per state code (a hint: updated after the bitmaps)
     __shared__ unsigned int sTarget;
-    __shared__ int sExit, sLock;
+    __shared__ int sExit;
     __shared__ uint16_t sSel[NW][32];
     const uint32_t t = threadIdx.x, lane = t & 31, wib = t >> 5;
     Ht2Work* base = work + (size_t)blockIdx.x * S;
-    for (int i = t; i < S; i += 32 * NW) sCode[i] = RG_NEED;
+    for (int i = t; i < RG_BINS * NWORD; i += 32 * NW) sBits[i / NWORD][i % NWORD] = (i / NWORD == (int)RG_NEED) ? 0xffffffffu : 0u;
     if (t < RG_BINS) sCount[t] = (t == RG_NEED) ? S : 0;
-    if (t == 0) { sTarget = RG_NEED; sExit = 0; sLock = 0; }
+    if (t == 0) { sTarget = RG_NEED; sExit = 0; }
     Ht2AlignerT<GRAPH> A;
     A.bind(blob, &P, base);
     A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
-    A.swPl = b.swPool ? b.swPool + ((size_t)blockIdx.x * NW + wib) * ((size_t)HT2_SW_POOL_WORDS * 32) + lane : NULL;
-    A.swStride = 32;
+    A.swPl = b.swPool ? b.swPool + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)HT2_SW_POOL_WORDS : NULL;
+    A.swStride = 1;
 #ifdef HT2_ENABLE_SPLICED
     A.splT = b.splT;
 #endif
     __syncthreads();
-    volatile unsigned int* vCode = sCode;
     volatile int* vCount = sCount;
     uint16_t* sel = sSel[wib];
-    uint32_t round = wib * 5;
+    uint32_t rot = wib * (NWORD / NW > 0 ? NWORD / NW : 1);   // warps start their scans at different words
     for (;;) {
-        // ---- nothing claimable at all (every remaining slot is being run by another warp, or the
-        // batch has drained): wait without touching the lock -- spinning warps cost instruction fetch
+        // ---- nothing claimable at all (every remaining slot is being run by another warp, or the batch has
+        // drained): wait -- spinning warps cost instruction fetch
+        uint32_t T;
         {
-            const int c0 = vCount[lane], c1 = vCount[lane + 32];
+            int c0 = vCount[lane], c1 = vCount[lane + 32];
             if (__ballot_sync(0xffffffffu, c0 > 0 || c1 > 0) == 0) {
                 const bool done = __shfl_sync(0xffffffffu, *(volatile int*)&sExit >= S ? 1 : 0, 0) != 0;
                 if (done) break;
-                __nanosleep(2000);
+                __nanosleep(1000);
                 continue;
             }
-        }
-        // ---- one warp at a time forms a group (whole groups, not fragments shared between warps)
-        if (lane == 0) { unsigned ns = 32; while (atomicCAS(&sLock, 0, 1) != 0) { __nanosleep(ns); if (ns < 1024) ns <<= 1; } }
-        __syncwarp();
-        // every decision below is made warp-uniform (the counters change under our feet)
-        uint32_t T = __shfl_sync(0xffffffffu, *(volatile unsigned int*)&sTarget, 0);
-        const int cT = __shfl_sync(0xffffffffu, vCount[T], 0);
-        if (cT < 32) {
-            // elect the most populous claimable state
-            int c0 = vCount[lane], c1 = vCount[lane + 32];
-            if (c0 < 0) c0 = 0;
-            if (c1 < 0) c1 = 0;
-            uint32_t best = c0 >= c1 ? (((uint32_t)c0 << 8) | lane) : (((uint32_t)c1 << 8) | (lane + 32));
-            for (int off = 16; off > 0; off >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best, off); best = v > best ? v : best; }
-            if ((best >> 8) == 0) {
-                const bool done = __shfl_sync(0xffffffffu, *(volatile int*)&sExit >= S ? 1 : 0, 0) != 0;   // every slot has drained
-                __syncwarp();
-                if (lane == 0) atomicExch(&sLock, 0);
-                if (done) break;
-                __nanosleep(400);                                 // the rest is being run by other warps
-                continue;
+            // every decision below is made warp-uniform (the counters change under our feet)
+            T = __shfl_sync(0xffffffffu, *(volatile unsigned int*)&sTarget, 0);
+            const int cT = __shfl_sync(0xffffffffu, vCount[T], 0);
+            if (cT < 32) {
+                // elect the most populous claimable state
+                if (c0 < 0) c0 = 0;
+                if (c1 < 0) c1 = 0;
+                uint32_t best = c0 >= c1 ? (((uint32_t)c0 << 8) | lane) : (((uint32_t)c1 << 8) | (lane + 32));
+                for (int off = 16; off > 0; off >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best, off); best = v > best ? v : best; }
+                if ((best >> 8) == 0) { __nanosleep(200); continue; }
+                T = best & 0xff;
+                if (lane == 0) *(volatile unsigned int*)&sTarget = T;
             }
-            T = best & 0xff;
-            if (lane == 0) *(volatile unsigned int*)&sTarget = T;
         }
-        // ---- gather up to 32 slots in state T
-        uint32_t taken = 0;
+        // ---- claim up to 32 slots in state T out of its bitmap
+        uint32_t nsel;
         {
-            uint32_t j = round % NJ;
-            for (int jj = 0; jj < NJ && taken < 32; jj++) {
-                const uint32_t idx = lane + 32 * j;
-                const bool m = vCode[idx] == T;
-                const uint32_t mask = __ballot_sync(0xffffffffu, m);
-                const uint32_t rank = taken + __popc(mask & ((1u << lane) - 1));
-                if (m && rank < 32) { sel[rank] = (uint16_t)idx; vCode[idx] = RG_BUSY; }
-                taken += __popc(mask);
-                j = (j + 1 == NJ) ? 0 : j + 1;
+            const uint32_t w = (lane + rot) & (NWORD - 1);
+            const bool mine = lane < (uint32_t)NWORD;
+            const uint32_t word = mine ? *(volatile unsigned int*)&sBits[T][w] : 0u;
+            const uint32_t c = (uint32_t)__popc(word);
+            uint32_t incl = c;
+            for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if ((int)lane >= off) incl += v; }
+            const uint32_t before = incl - c;
+            const uint32_t want = before >= 32u ? 0u : (c < 32u - before ? c : 32u - before);
+            uint32_t got = 0;
+            if (want) {
+                const uint32_t last = __fns(word, 0, (int)want);            // position of the want-th set bit
+                const uint32_t mask = word & (0xffffffffu >> (31u - last));
+                got = atomicAnd(&sBits[T][w], ~mask) & mask;                  // the bits this lane really won
             }
+            const uint32_t g = (uint32_t)__popc(got);
+            uint32_t gi = g;
+            for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, gi, off); if ((int)lane >= off) gi += v; }
+            nsel = __shfl_sync(0xffffffffu, gi, 31);
+            uint32_t r = gi - g;
+            while (got) { const uint32_t bpos = (uint32_t)__ffs((int)got) - 1u; sel[r++] = (uint16_t)(w * 32u + bpos); got &= got - 1u; }
+            if (lane == 0 && nsel) atomicSub(&sCount[T], (int)nsel);
+            rot += 5;
         }
-        round++;
-        const uint32_t nsel = taken < 32 ? taken : 32;
-        if (lane == 0 && nsel) atomicSub(&sCount[T], (int)nsel);
-        __threadfence_block();
         __syncwarp();
-        if (lane == 0) atomicExch(&sLock, 0);
-        if (nsel == 0) continue;
+        if (nsel == 0) continue;        // another warp took them first, or the counter was ahead of the bitmap
         const int my = lane < nsel ? (int)sel[lane] : -1;
         __threadfence_block();   // acquire: the previous owner's workspace writes
         const long long t0 = o.stats ? clock64() : 0;
@@ -353,8 +347,8 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
                 nc = rg_code(W);
             }
             __threadfence_block();   // release
-            if (nc == RG_EXIT) { vCode[my] = RG_EXIT; atomicAdd(&sExit, 1); }
-            else { atomicExch(&sCode[my], nc); atomicAdd(&sCount[nc], 1); }
+            if (nc == RG_EXIT) atomicAdd(&sExit, 1);
+            else { atomicOr(&sBits[nc][my >> 5], 1u << (my & 31)); atomicAdd(&sCount[nc], 1); }
         }
         __syncwarp();
         if (o.stats && lane == 0) {
@@ -601,7 +595,7 @@ static bool pinnedGet(size_t need, ResPriv& out)
     }
     size_t cap = need + need / 4 + 4096;
     void* p = NULL;
-    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return false;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) return false;
     out.buf = p; out.cap = cap;
     return true;
 }
@@ -674,8 +668,8 @@ static int finishOpen(ht2gpu_handle* h)
     h->tpb = 32 * h->poolWarps;
     h->bpsm = (h->opt.blocks_per_sm > 0 && !h->graph) ? h->opt.blocks_per_sm : 1;
     h->rgK = (h->opt.slots_per_lane > 0 && !h->graph) ? h->opt.slots_per_lane : 4;
-    if (h->rgK != 2 && h->rgK != 4 && h->rgK != 8) h->rgK = 4;
-    if (h->poolWarps == 16 && h->rgK == 8) h->rgK = 4;
+    if (h->rgK != 2 && h->rgK != 4) h->rgK = 4;
+    if (h->poolWarps == 16) h->rgK = 2;   // at most 1024 slots per block: one bitmap word per lane
     h->nWork = (size_t)h->nSM * h->bpsm * h->poolWarps * 32 * h->rgK;
     CK(cudaMalloc(&h->dMinsc, sizeof(h->P.minscTab)));
     CK(cudaMemcpy(h->dMinsc, h->P.minscTab, sizeof(h->P.minscTab), cudaMemcpyHostToDevice));
@@ -781,6 +775,28 @@ extern "C" int ht2gpu_open_device_image(const void* dev_image, size_t bytes, con
     return finishOpen(h);
 }
 
+extern "C" int ht2gpu_open_peer(const ht2gpu_handle_t* src, const ht2gpu_options_t* opt, ht2gpu_handle_t** out)
+{
+    if (!src || !out || !src->dBlob || !src->img) return HT2GPU_ERR_ARG;
+    ht2gpu_handle* h = newHandle(opt ? opt : &src->opt);
+    *out = h;
+    int rc = selectDevice(h);
+    if (rc) return rc;
+    h->img = new Ht2Image();
+    h->img->blob = src->img->blob;            // host copy: reference names / lengths for SAM
+    h->blobBytes = src->blobBytes;
+    CK(cudaMalloc(&h->dBlob, h->blobBytes));
+    h->ownBlob = true;
+    if (h->device == src->device) CK(cudaMemcpy(h->dBlob, src->dBlob, h->blobBytes, cudaMemcpyDeviceToDevice));
+    else {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, h->device, src->device);
+        if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError(); }
+        CK(cudaMemcpyPeer(h->dBlob, h->device, src->dBlob, src->device, h->blobBytes));
+    }
+    return finishOpen(h);
+}
+
 extern "C" int ht2gpu_open(const char* index_base, const ht2gpu_options_t* opt, ht2gpu_handle_t** out)
 {
     if (!index_base || !out) return HT2GPU_ERR_ARG;
@@ -862,7 +878,7 @@ static int slotInit(ht2gpu_handle* h, SamSlot& S)
     CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 6; i++) CK(cudaEventCreate(&S.ev[i]));
     CK(cudaMalloc(&S.dCounters, 8 * sizeof(unsigned int)));
-    CK(cudaHostAlloc(&S.hMeta, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&S.hMeta, 16 * sizeof(unsigned long long), cudaHostAllocPortable));
     S.init = true;
     return HT2GPU_OK;
 }
@@ -928,9 +944,7 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
     else {
         switch (h->poolWarps * 100 + h->rgK) {
             case 802:  ht2_align_pool_kernel<8, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 808:  ht2_align_pool_kernel<8, 8, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
             case 1602: ht2_align_pool_kernel<16, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 1604: ht2_align_pool_kernel<16, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
             default:   ht2_align_pool_kernel<8, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
         }
     }
@@ -1118,7 +1132,7 @@ static int enqueueKernels(ht2gpu_handle* h, SamSlot& S, bool withAlign)
 }
 
 extern "C" int ht2gpu_sam_slots(const ht2gpu_handle_t*) { return HT2GPU_N_SLOTS; }
-extern "C" void* ht2gpu_host_alloc(size_t bytes) { void* p = NULL; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : NULL; }
+extern "C" void* ht2gpu_host_alloc(size_t bytes) { void* p = NULL; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) == cudaSuccess ? p : NULL; }
 extern "C" void ht2gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" void ht2gpu_set_error(ht2gpu_handle_t* h, const char* msg) { if (h) h->err = msg ? msg : ""; }
 extern "C" void* ht2gpu_ctx_get(ht2gpu_handle_t* h) { return h ? h->pipeCtx : NULL; }
@@ -1178,7 +1192,7 @@ extern "C" int ht2gpu_wait_sam(ht2gpu_handle_t* h, int slot, ht2gpu_sam_result_t
         if (S.hSam) cudaFreeHost(S.hSam);
         S.hSam = NULL; S.capHSam = 0;
         const size_t cap = total + total / 8 + 4096;
-        CK(cudaHostAlloc(&S.hSam, cap, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&S.hSam, cap, cudaHostAllocPortable));
         S.capHSam = cap;
     }
     CK(cudaMemcpyAsync(S.hSam, S.dSam, total, cudaMemcpyDeviceToHost, S.stream));

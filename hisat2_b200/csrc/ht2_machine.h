@@ -611,7 +611,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
         bool pseudogeneStop = gfm.g->linearFM && !P->noSplicedAlignment;
         bool anchorStop = P->anchorStop != 0;
-        partialSearch(rdi, fw, pseudogeneStop, anchorStop);
+        if (!partialSearch(rdi, fw, pseudogeneStop, anchorStop)) break;   // parked after a slice of LF steps: stay in TS_PS
         if (hit.done) { W->st = TS_ALIGN; break; }
         if (!pseudogeneStop) { if (hit.cur + 1 < hit.len) hit.cur++; }
         if (anchorStop) { hit.done = 1; W->st = TS_ALIGN; break; }
@@ -752,7 +752,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
 }
 
 // Run one read (pair) to completion (host build and the one-lane-per-read kernel loop).
-template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStart() { W->st = TS_START; W->nFrames = 0; }
+template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStart() { W->st = TS_START; W->nFrames = 0; W->psCont = 0; }
 template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineDone() const { return W->st == TS_DONE && W->nFrames == 0; }
 template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStep()
 {

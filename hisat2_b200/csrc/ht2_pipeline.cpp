@@ -51,13 +51,25 @@ PipeCtx* ctxOf(ht2gpu_handle_t* h, unsigned nth, int nSlots)
 
 extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* in, ht2gpu_sink_fn sink, void* ctx, ht2gpu_run_stats_t* st)
 {
-    if (!h || !in) return HT2GPU_ERR_ARG;
+    return ht2gpu_run_reads_multi(&h, 1, in, sink, ctx, st);
+}
+
+// The same pipeline over several devices of one process (hisat2-b200 --gpus N): batch i goes to handle i % n,
+// the sink still receives the batches in input order.  The index is replicated (ht2gpu_open_peer), reads are the
+// only thing that is sharded, no data-path collective.  Context (thread pool, pinned staging) lives in hs[0].
+extern "C" int ht2gpu_run_reads_multi(ht2gpu_handle_t** hs, int nDev, const ht2gpu_reads_input_t* in, ht2gpu_sink_fn sink, void* ctx,
+                                      ht2gpu_run_stats_t* st)
+{
+    if (!hs || nDev < 1 || !in) return HT2GPU_ERR_ARG;
+    for (int i = 0; i < nDev; i++) if (!hs[i]) return HT2GPU_ERR_ARG;
+    ht2gpu_handle_t* h = hs[0];
     ht2gpu_run_stats_t S; memset(&S, 0, sizeof(S));
     const double t0 = nowS();
     unsigned nth = in->threads > 0 ? (unsigned)in->threads : std::thread::hardware_concurrency();
     if (nth < 1) nth = 1;
     if (nth > 64) nth = 64;
-    const int nSlots = ht2gpu_sam_slots(h);
+    const int perDev = ht2gpu_sam_slots(h);
+    const int nSlots = perDev * nDev;          // stage k: device k % nDev, device slot k / nDev
     PipeCtx* C = ctxOf(h, nth, nSlots);
     std::lock_guard<std::mutex> runLock(C->mu);
     Ht2ThreadPool& pool = *C->pool;
@@ -82,7 +94,7 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
     uint64_t r0 = in->skip, r1 = a.nRecords();
     if (r0 > r1) r0 = r1;
     if (in->upto && r0 + in->upto < r1) r1 = r0 + in->upto;
-    uint64_t perBatch = in->batch_reads ? in->batch_reads : 1000000;
+    uint64_t perBatch = in->batch_reads ? in->batch_reads : 4000000;   // large batches amortise the drain of the pool kernel's last reads
     if (paired) perBatch = (perBatch + 1) / 2;   // batch_reads counts reads, a record here is a pair
     if (perBatch < 1) perBatch = 1;
     const uint64_t nBatches = (r1 - r0 + perBatch - 1) / perBatch;
@@ -110,9 +122,9 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
                 ht2gpu_read_batch_t rb; memset(&rb, 0, sizeof(rb));
                 rb.n_reads = hb.n_reads; rb.paired = paired ? 1 : 0; rb.seq = hb.seq; rb.qual = hb.haveQual ? hb.qual : NULL; rb.offs = hb.offs; rb.seeds = hb.seeds;
                 const double ts = nowS();
-                rc = ht2gpu_submit_sam(h, slot, &rb, hb.names, hb.nameOffs, hb.namesBytes);
+                rc = ht2gpu_submit_sam(hs[slot % nDev], slot / nDev, &rb, hb.names, hb.nameOffs, hb.namesBytes);
                 submitS += nowS() - ts;
-                if (rc != HT2GPU_OK) e = ht2gpu_last_error(h);
+                if (rc != HT2GPU_OK) e = ht2gpu_last_error(hs[slot % nDev]);
             }
             std::lock_guard<std::mutex> lk(mu);
             if (rc != HT2GPU_OK) { prodRc = rc; prodErr = e; cv.notify_all(); break; }
@@ -134,9 +146,9 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
         }
         ht2gpu_sam_result_t r;
         const double tw = nowS();
-        rc = ht2gpu_wait_sam(h, slot, &r);
+        rc = ht2gpu_wait_sam(hs[slot % nDev], slot / nDev, &r);
         waitS += nowS() - tw;
-        if (rc != HT2GPU_OK) { prodErr = ht2gpu_last_error(h); break; }
+        if (rc != HT2GPU_OK) { prodErr = ht2gpu_last_error(hs[slot % nDev]); break; }
         S.n_batches++; S.n_units += r.n_units; S.n_reads += stage[slot].n_reads; S.sam_bytes += r.sam_len; S.n_err_reads += r.n_err_reads;
         S.ms_align += r.ms_align; S.ms_sam += r.ms_sam; S.ms_h2d += r.ms_h2d; S.ms_d2h += r.ms_d2h;
         S.h2d_bytes += r.h2d_bytes; S.d2h_bytes += r.d2h_bytes; S.n_launches += r.n_launches;
@@ -149,7 +161,7 @@ extern "C" int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* 
     { std::lock_guard<std::mutex> lk(mu); if (rc != HT2GPU_OK && prodRc == HT2GPU_OK) prodRc = rc; cv.notify_all(); }
     producer.join();
     // drain anything still in flight after an error
-    if (rc != HT2GPU_OK) for (int s = 0; s < nSlots; s++) if (state[s] == 1) { ht2gpu_sam_result_t r; ht2gpu_wait_sam(h, s, &r); }
+    if (rc != HT2GPU_OK) for (int s = 0; s < nSlots; s++) if (state[s] == 1) { ht2gpu_sam_result_t r; ht2gpu_wait_sam(hs[s % nDev], s / nDev, &r); }
     ht2_source_close(a); ht2_source_close(b);
     S.s_parse = parseS; S.s_submit = submitS; S.s_wait = waitS; S.s_sink = sinkS; S.s_total = nowS() - t0;
     if (st) *st = S;

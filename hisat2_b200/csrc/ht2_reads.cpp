@@ -192,24 +192,39 @@ void Ht2HostBatch::freeAll()
 namespace {
 
 struct Tables {
-    uint8_t cat[256], code[256];
+    uint8_t isBase[256];   // FASTA: asc2dnacat > 0 (alphabet.cpp)
+    uint8_t isAlpha[256];  // FASTQ: letters, and '.' which reads as N (pat.cpp:1030-1290)
+    uint8_t code[256];     // asc2dna; '.' -> 4
     Tables() {
-        memset(cat, 0, sizeof(cat)); memset(code, 0, sizeof(code));
-        for (const char* c = "ACGTacgt"; *c; c++) cat[(uint8_t)*c] = 1;
-        for (const char* c = "BDHKMNRSVWXYbdhkmnrsvwxy"; *c; c++) cat[(uint8_t)*c] = 2;
-        cat[(uint8_t)'-'] = 3;
+        memset(isBase, 0, sizeof(isBase)); memset(isAlpha, 0, sizeof(isAlpha)); memset(code, 0, sizeof(code));
+        for (const char* c = "ACGTacgtBDHKMNRSVWXYbdhkmnrsvwxy-"; *c; c++) isBase[(uint8_t)*c] = 1;
+        for (int c = 'a'; c <= 'z'; c++) { isAlpha[c] = 1; isAlpha[c - 32] = 1; }
+        isAlpha[(uint8_t)'.'] = 1;
         code[(uint8_t)'C'] = code[(uint8_t)'c'] = 1; code[(uint8_t)'G'] = code[(uint8_t)'g'] = 2;
-        code[(uint8_t)'T'] = code[(uint8_t)'t'] = 3; code[(uint8_t)'N'] = code[(uint8_t)'n'] = 4;
+        code[(uint8_t)'T'] = code[(uint8_t)'t'] = 3; code[(uint8_t)'N'] = code[(uint8_t)'n'] = 4; code[(uint8_t)'.'] = 4;
     }
 };
 const Tables TB;
 
+struct RawBuf {   // grow-only byte buffer written through raw pointers (no per-byte capacity checks, no zero fill)
+    uint8_t* p; size_t n, cap;
+    RawBuf() : p(NULL), n(0), cap(0) {}
+    ~RawBuf() { free(p); }
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    RawBuf(RawBuf&& o) : p(o.p), n(o.n), cap(o.cap) { o.p = NULL; o.n = o.cap = 0; }
+    void need(size_t extra) {
+        if (n + extra <= cap) return;
+        size_t c = (n + extra) * 3 / 2 + 4096;
+        p = (uint8_t*)realloc(p, c); cap = c;
+    }
+};
+
 struct Local {   // one thread's share of a batch
-    std::vector<uint8_t> seq, qual;
+    RawBuf seq, qual, names;
     std::vector<uint32_t> len, nameLen, seed;
-    std::string names;
     std::string err;
-    void clear() { seq.clear(); qual.clear(); len.clear(); nameLen.clear(); seed.clear(); names.clear(); err.clear(); }
+    void clear() { seq.n = qual.n = names.n = 0; len.clear(); nameLen.clear(); seed.clear(); err.clear(); }
 };
 
 // genRandSeed (pat.h:55-91)
@@ -218,7 +233,9 @@ inline uint32_t genSeed(const uint8_t* sq, const uint8_t* ql, uint32_t n, const 
     uint32_t rseed = (seed + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83;
     for (uint32_t i = 0; i < n; i++) rseed ^= ((uint32_t)sq[i] << ((i & 15) << 1));
     if (ql) for (uint32_t i = 0; i < n; i++) rseed ^= ((uint32_t)ql[i] << ((i & 3) << 3));
-    else for (uint32_t i = 0; i < n; i++) rseed ^= ((uint32_t)'I' << ((i & 3) << 3));
+    else {   // FASTA: every quality is 'I'; byte lane k of the word collects one 'I' per i with i % 4 == k
+        for (uint32_t k = 0; k < 4; k++) if (((n + 3 - k) >> 2) & 1u) rseed ^= ((uint32_t)'I' << (k << 3));
+    }
     for (size_t i = 0; i < nameLen; i++) {
         const int p = (int)name[i];
         if (p == '/') break;
@@ -232,64 +249,65 @@ bool parseRecord(const Ht2ReadSource& src, uint64_t r, int mate, const Ht2ReadsO
 {
     const char* d = src.data;
     size_t p = (size_t)src.rec[r]; const size_t e = (size_t)src.rec[r + 1];
-    const size_t seqAt = L.seq.size(), nameAt = L.names.size();
+    const size_t span = e - p;
+    L.seq.need(span + 8); L.names.need(span + 32);
+    if (o.fastq) L.qual.need(span + 8);
+    uint8_t* sq = L.seq.p + L.seq.n;
+    char* nm = (char*)L.names.p + L.names.n;
+    size_t nl = 0;
     p++;   // '>' or '@'
-    while (p < e && d[p] != '\n' && d[p] != '\r') L.names.push_back(d[p++]);
+    {   // the name: up to the end of the line
+        const char* q = (const char*)memchr(d + p, '\n', e - p);
+        size_t le = q ? (size_t)(q - d) : e;
+        size_t ne = le;
+        const char* cr = (const char*)memchr(d + p, '\r', le - p);
+        if (cr) ne = (size_t)(cr - d);
+        nl = ne - p;
+        memcpy(nm, d + p, nl);
+        p = le;
+    }
+    size_t n = 0;
     if (!o.fastq) {
-        while (p < e && (d[p] == '\n' || d[p] == '\r')) p++;
-        int begin = 0;
-        for (; p < e; p++) {
-            const uint8_t c = (uint8_t)d[p];
-            if (TB.cat[c] > 0 && begin++ >= o.trim5) L.seq.push_back(TB.code[c]);
-        }
-        size_t n = L.seq.size() - seqAt;
-        const size_t t3 = (size_t)o.trim3 < n ? (size_t)o.trim3 : n;
-        L.seq.resize(L.seq.size() - t3);
+        for (; p < e; p++) { const uint8_t c = (uint8_t)d[p]; sq[n] = TB.code[c]; n += TB.isBase[c]; }
+        if (o.trim5 > 0) { const size_t t5 = (size_t)o.trim5 < n ? (size_t)o.trim5 : n; memmove(sq, sq + t5, n - t5); n -= t5; }
+        n -= (size_t)o.trim3 < n ? (size_t)o.trim3 : n;
     } else {
-        if (p < e && d[p] == '\r') p++;
-        if (p < e && d[p] == '\n') p++;
-        int begin = 0;
-        for (; p < e && d[p] != '\n'; p++) {
-            int c = (uint8_t)d[p];
-            if (c == '.') c = 'N';
-            if (((c | 32) >= 'a' && (c | 32) <= 'z') && begin++ >= o.trim5) L.seq.push_back(TB.code[c]);
-        }
+        if (p < e) p++;   // the newline that ends the name line
+        for (; p < e && d[p] != '\n'; p++) { const uint8_t c = (uint8_t)d[p]; sq[n] = TB.code[c]; n += TB.isAlpha[c]; }
         if (p < e) p++;
         if (p >= e || d[p] != '+') { L.err = "reads file does not look like a FASTQ file"; return false; }
-        while (p < e && d[p] != '\n') p++;
-        if (p < e) p++;
-        size_t n = L.seq.size() - seqAt;
+        { const char* q = (const char*)memchr(d + p, '\n', e - p); p = q ? (size_t)(q - d) + 1 : e; }
+        const size_t t5 = (size_t)o.trim5 < n ? (size_t)o.trim5 : n;
+        if (t5) { memmove(sq, sq + t5, n - t5); n -= t5; }
         const size_t t3 = (size_t)o.trim3 < n ? (size_t)o.trim3 : n;
-        L.seq.resize(L.seq.size() - t3);
         n -= t3;
         // qualities: the line's characters (minus '\r'), trimmed like the bases, converted to Phred+33
-        size_t qn = 0, taken = 0; int qbegin = 0;
-        size_t q = p;
-        while (q < e && d[q] != '\n') { if (d[q] != '\r') qn++; q++; }
+        uint8_t* ql = L.qual.p + L.qual.n;
+        size_t qn = 0;
+        for (; p < e && d[p] != '\n'; p++) { const uint8_t c = (uint8_t)d[p]; ql[qn] = c; qn += (c != '\r'); }
         const size_t qkeep = qn > (size_t)o.trim5 + t3 ? qn - (size_t)o.trim5 - t3 : 0;
-        std::string nm(L.names.begin() + nameAt, L.names.end());
-        if (qkeep < n) { L.err = "fewer quality values than bases for read " + nm; return false; }
-        if (qkeep > n) { L.err = "more quality values than bases for read " + nm; return false; }
-        for (; p < e && d[p] != '\n' && taken < n; p++) {
-            int c = (uint8_t)d[p];
-            if (c == '\r') continue;
-            if (qbegin++ < o.trim5) continue;
-            if (o.phred64) { if (c < 64) { L.err = "quality value below Phred+64 range in read " + nm; return false; } c -= 31; }
-            if (c < 33) { L.err = "quality value below Phred+33 range in read " + nm; return false; }
-            L.qual.push_back((uint8_t)c); taken++;
+        if (qkeep != n) {
+            L.err = std::string(qkeep < n ? "fewer" : "more") + " quality values than bases for read " + std::string(nm, nl);
+            return false;
         }
+        if (o.trim5 > 0) memmove(ql, ql + o.trim5, n);
+        if (o.phred64) {
+            for (size_t i = 0; i < n; i++) { if (ql[i] < 64) { L.err = "quality value below Phred+64 range in read " + std::string(nm, nl); return false; } ql[i] = (uint8_t)(ql[i] - 31); }
+        }
+        uint8_t lo = 255;
+        for (size_t i = 0; i < n; i++) lo = ql[i] < lo ? ql[i] : lo;
+        if (n && lo < 33) { L.err = "quality value below Phred+33 range in read " + std::string(nm, nl); return false; }
+        L.qual.n += n;
     }
-    if (L.names.size() == nameAt) { char b[24]; snprintf(b, sizeof(b), "%llu", (unsigned long long)r); L.names += b; }   // the read ordinal
+    if (nl == 0) nl = (size_t)snprintf(nm, 24, "%llu", (unsigned long long)r);   // unnamed read: the read ordinal
     if (mate) {   // Read::fixMateName (read.h:171-196)
-        const size_t nl = L.names.size() - nameAt;
         const char want = mate == 1 ? '1' : '2';
-        if (nl < 2 || L.names[L.names.size() - 2] != '/' || L.names[L.names.size() - 1] != want) { L.names.push_back('/'); L.names.push_back(want); }
+        if (nl < 2 || nm[nl - 2] != '/' || nm[nl - 1] != want) { nm[nl++] = '/'; nm[nl++] = want; }
     }
-    const uint32_t n = (uint32_t)(L.seq.size() - seqAt);
-    const size_t nl = L.names.size() - nameAt;
-    L.seed.push_back(genSeed(L.seq.data() + seqAt, o.fastq ? L.qual.data() + (L.qual.size() - n) : NULL, n, L.names.data() + nameAt, nl, o.seed));
-    L.names.push_back('\0');
-    L.len.push_back(n);
+    L.seed.push_back(genSeed(sq, o.fastq ? L.qual.p + (L.qual.n - n) : NULL, (uint32_t)n, nm, nl, o.seed));
+    nm[nl] = '\0';
+    L.seq.n += n; L.names.n += nl + 1;
+    L.len.push_back((uint32_t)n);
     L.nameLen.push_back((uint32_t)nl + 1);
     return true;
 }
@@ -329,7 +347,7 @@ bool ht2_parse_batch(const Ht2ReadSource& a, const Ht2ReadSource* b, uint64_t r0
     std::vector<uint64_t> baseAt(T + 1, 0), readAt(T + 1, 0), nameAt(T + 1, 0);
     for (unsigned t = 0; t < T; t++) {
         if (!loc[t].err.empty()) { err = loc[t].err; return false; }
-        baseAt[t + 1] = baseAt[t] + loc[t].seq.size(); readAt[t + 1] = readAt[t] + loc[t].len.size(); nameAt[t + 1] = nameAt[t] + loc[t].names.size();
+        baseAt[t + 1] = baseAt[t] + loc[t].seq.n; readAt[t + 1] = readAt[t] + loc[t].len.size(); nameAt[t + 1] = nameAt[t] + loc[t].names.n;
     }
     const size_t nb = (size_t)baseAt[T], nr = (size_t)readAt[T], nn = (size_t)nameAt[T];
     if (nr > 0xfffffff0ull || nn > 0xfffffff0ull) { err = "batch too large"; return false; }
@@ -351,9 +369,9 @@ bool ht2_parse_batch(const Ht2ReadSource& a, const Ht2ReadSource* b, uint64_t r0
     auto place = [&](unsigned t) {
         if (t >= T) return;
         const Local& L = loc[t];
-        if (!L.seq.empty()) memcpy(out.seq + baseAt[t], L.seq.data(), L.seq.size());
-        if (o.fastq && !L.qual.empty()) memcpy(out.qual + baseAt[t], L.qual.data(), L.qual.size());
-        if (!L.names.empty()) memcpy(out.names + nameAt[t], L.names.data(), L.names.size());
+        if (L.seq.n) memcpy(out.seq + baseAt[t], L.seq.p, L.seq.n);
+        if (o.fastq && L.qual.n) memcpy(out.qual + baseAt[t], L.qual.p, L.qual.n);
+        if (L.names.n) memcpy(out.names + nameAt[t], L.names.p, L.names.n);
         uint64_t bo = baseAt[t], no = nameAt[t];
         const size_t k0 = (size_t)readAt[t];
         for (size_t k = 0; k < L.len.size(); k++) {

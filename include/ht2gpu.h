@@ -230,7 +230,7 @@ typedef struct {
     uint32_t    seed;       /* --seed (per-read seeds, pat.h:55-91) */
     uint64_t    skip;       /* -s */
     uint64_t    upto;       /* -u; 0 = no limit */
-    uint32_t    batch_reads;/* reads per device batch; 0 = 1,000,000 */
+    uint32_t    batch_reads;/* reads per device batch; 0 = 4,000,000 */
     int32_t     threads;    /* host parser threads (-p); 0 = all cores, at most 64 */
 } ht2gpu_reads_input_t;
 typedef struct {
@@ -242,6 +242,14 @@ typedef struct {
     uint32_t n_launches, pad;
 } ht2gpu_run_stats_t;
 int ht2gpu_run_reads(ht2gpu_handle_t* h, const ht2gpu_reads_input_t* in, ht2gpu_sink_fn sink, void* ctx, ht2gpu_run_stats_t* stats);
+/* The same over several devices of ONE process (hisat2 -p N + --reorder, hisat2.cpp:3657-3696, outq.cpp:51-99, with
+ * GPUs in place of threads): batch i runs on hs[i % n], the sink receives the batches in input order.  Every handle
+ * holds a replica of the same index (ht2gpu_open_peer); reads are the only thing that is sharded. */
+int ht2gpu_run_reads_multi(ht2gpu_handle_t** hs, int n, const ht2gpu_reads_input_t* in, ht2gpu_sink_fn sink, void* ctx,
+                           ht2gpu_run_stats_t* stats);
+/* Replicate an open index onto another device of this process: the packed image is copied device to device
+ * (cudaMemcpyPeer: NVLink / NVSwitch when peer access exists), options as given (opt->device = the target). */
+int ht2gpu_open_peer(const ht2gpu_handle_t* src, const ht2gpu_options_t* opt, ht2gpu_handle_t** out);
 
 /* The read front end on its own, host only (no device): the whole input as ONE batch in the layout
  * ht2gpu_align_batch / ht2gpu_submit_sam take (FastaPatternSource / FastqPatternSource + genRandSeed +

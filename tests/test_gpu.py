@@ -460,7 +460,7 @@ def test_long_pairs_capacity_errors_are_flagged_never_silent(h2, chr22, tmp_path
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
 def test_full_size_byte_parity_1M_reads_and_500k_pairs(h2, chr22, tmp_path):
     """BASELINE configs[1] size (1M x 101 bp SE) and the configs[2] shape (500k pairs 2x101): the bench workload's own
-    generator, FASTA bytes through ht2gpu_run_reads (1M-read device batches), byte-compared with the unmodified
+    generator, FASTA bytes through ht2gpu_run_reads, byte-compared with the unmodified
     reference run on this box; plus determinism of a second pass."""
     sys.path.insert(0, ROOT)
     import bench
@@ -489,3 +489,63 @@ def test_full_size_byte_parity_1M_reads_and_500k_pairs(h2, chr22, tmp_path):
     assert st["n_units"] == k and st["n_err_reads"] == 0
     want = open(out, "rb").read()
     assert sam == want[want.index(b"\nr00000000\t") + 1:]
+
+
+def test_two_devices_one_process_equal_one_device(h2, tmp_path):
+    """hisat2-b200 --gpus 2 / ht2gpu_run_reads_multi: batches round-robin over two devices of one process (index
+    replicated device to device), output in input order -- byte-identical to the single-device run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    base = os.path.join(DATA, "22_20-21M")
+    f1, f2 = os.path.join(DATA, "sim200k_1.fa"), os.path.join(DATA, "sim200k_2.fa")
+    if not os.path.exists(f1):
+        pytest.skip(f1 + " not staged")
+    a = h2.Index(base, device=0)
+    one, _ = a.run_reads(path1=f1, path2=f2, batch_reads=40000)
+    b = a.peer(1)
+    two, st = a.run_reads(path1=f1, path2=f2, batch_reads=40000, peers=[b])
+    assert st["n_batches"] == 10 and two == one
+    b.close(); a.close()
+    cli = os.path.join(ROOT, "hisat2_b200", "hisat2-b200")
+    out = str(tmp_path / "cli2.sam")
+    subprocess.run([cli, "--no-spliced-alignment", "-f", "-x", base, "-1", f1, "-2", f2, "-S", out, "--batch", "40000", "--gpus", "2"], check=True,
+                   stderr=subprocess.DEVNULL)
+    body = open(out, "rb").read()
+    assert body[body.index(b"\n@PG") + 1:].split(b"\n", 1)[1] == one
+
+
+def test_torchrun_two_ranks_concatenate_to_the_single_rank_output(h2, tmp_path):
+    """The bench's N-rank layout on hardware: two torchrun ranks (NCCL broadcast of the index image, contiguous pair
+    ranges) each write their shard's SAM; the rank-order concatenation equals the one-GPU output byte for byte."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    f1, f2 = os.path.join(DATA, "sim200k_1.fa"), os.path.join(DATA, "sim200k_2.fa")
+    if not os.path.exists(f1):
+        pytest.skip(f1 + " not staged")
+    script = str(tmp_path / "rank.py")
+    open(script, "w").write("""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import hisat2_b200 as h2
+from hisat2_b200.parallel import broadcast_image, shard_range
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+img = h2.Index.build_image(%r) if rank == 0 else None
+dev = broadcast_image(img, rank, device=torch.device("cuda", local))
+torch.cuda.synchronize()
+idx = h2.Index(device_image=(dev.data_ptr(), dev.numel(), dev[:4096].cpu().numpy()), device=local)
+lo, hi = shard_range(200000, rank, world)
+sam, st = idx.run_reads(path1=%r, path2=%r, skip=lo, upto=hi - lo, batch_reads=60000)
+open(os.path.join(%r, "part%%d.sam" %% rank), "wb").write(sam)
+dist.barrier(); dist.destroy_process_group()
+""" % (ROOT, os.path.join(DATA, "22_20-21M"), f1, f2, str(tmp_path)))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                    "--master-port", "29517", script], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    a = h2.Index(os.path.join(DATA, "22_20-21M"), device=0)
+    one, _ = a.run_reads(path1=f1, path2=f2)
+    a.close()
+    assert open(str(tmp_path / "part0.sam"), "rb").read() + open(str(tmp_path / "part1.sam"), "rb").read() == one
