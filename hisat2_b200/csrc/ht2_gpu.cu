@@ -664,11 +664,11 @@ static int finishOpen(ht2gpu_handle* h)
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->nSM = prop.multiProcessorCount;
     // the pool kernel: one block of poolWarps warps per SM, rgK read slots per lane
-    h->poolWarps = (h->opt.threads_per_block >= 512 && !h->graph) ? 16 : 8;
+    h->poolWarps = (h->opt.threads_per_block >= 512 && !h->graph) ? 16 : ((h->opt.threads_per_block == 128 && !h->graph) ? 4 : 8);
     h->tpb = 32 * h->poolWarps;
     h->bpsm = (h->opt.blocks_per_sm > 0 && !h->graph) ? h->opt.blocks_per_sm : 1;
     h->rgK = (h->opt.slots_per_lane > 0 && !h->graph) ? h->opt.slots_per_lane : 4;
-    if (h->rgK != 2 && h->rgK != 4) h->rgK = 4;
+    if (h->rgK != 2 && h->rgK != 4 && !(h->poolWarps == 4 && h->rgK == 8)) h->rgK = 4;
     if (h->poolWarps == 16) h->rgK = 2;   // at most 1024 slots per block: one bitmap word per lane
     h->nWork = (size_t)h->nSM * h->bpsm * h->poolWarps * 32 * h->rgK;
     CK(cudaMalloc(&h->dMinsc, sizeof(h->P.minscTab)));
@@ -944,6 +944,8 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
     else {
         switch (h->poolWarps * 100 + h->rgK) {
             case 802:  ht2_align_pool_kernel<8, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 408:  ht2_align_pool_kernel<4, 8, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 404:  ht2_align_pool_kernel<4, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
             case 1602: ht2_align_pool_kernel<16, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
             default:   ht2_align_pool_kernel<8, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
         }

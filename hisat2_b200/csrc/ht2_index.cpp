@@ -10,6 +10,7 @@
 //   gfm.h:714-778, alt.h:197-204             (.7 ALTs)
 // Little-endian files only (the reference refuses byte-swapped mmap too).
 #include "ht2_index.h"
+#include "ht2_fm.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,6 +19,7 @@
 #include <algorithm>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -223,6 +225,58 @@ void readBody(FileBuf& f, Blob& b, Ht2Gfm& g)
     g.o_eftab = b.put(f.take((size_t)g.eftabLen * eb), (size_t)g.eftabLen * eb, 16);
 }
 
+
+// Densify the suffix-array sample of a LINEAR index.  The .ht2 files sample every 2^offRate-th row (offRate 4 by
+// default: gfm.h:5682 getOffset walks ~7.5 LF steps per resolved row, a third of all LF steps of a read); the
+// image spends HBM instead -- 180 GB per GPU -- and keeps every 2^HT2_DENSE_OFFRATE-th row, so that
+// tryOffset succeeds after ~1.5 steps.  The value of a row is a property of the index, not of the sampling:
+// new[r] = old[row'] + steps for the first sampled row' on r's LF walk, exactly what getOffset returns.
+#ifndef HT2_DENSE_OFFRATE
+#define HT2_DENSE_OFFRATE 2
+#endif
+template <typename IT>
+void densifySample(Blob& b, Ht2Gfm& g)
+{
+    if (!g.linearFM || g.len == 0 || g.offRate <= HT2_DENSE_OFFRATE) return;
+    const uint32_t newRate = HT2_DENSE_OFFRATE;
+    const uint32_t entryMax = (sizeof(IT) == 4) ? 0xffffffffu : 0xffffu;
+    const uint32_t nNew = (g.numNodes + (1u << newRate) - 1) >> newRate;
+    const uint64_t oNew = b.alloc((size_t)nNew * sizeof(IT), 128);   // may move the blob: take pointers afterwards
+    Ht2Fm<IT> fm;
+    fm.init(b.d.data(), &g);
+    IT* out = (IT*)(b.d.data() + oNew);
+    const uint32_t oldMask = g.offMask, oldRate = g.offRate, z0 = g.zOff0;
+    unsigned nth = std::thread::hardware_concurrency();
+    if (nth < 1) nth = 1;
+    if (nth > 32) nth = 32;
+    if (nNew < (1u << 16)) nth = 1;
+    auto work = [&](unsigned t) {
+        const uint32_t k0 = (uint32_t)((uint64_t)nNew * t / nth), k1 = (uint32_t)((uint64_t)nNew * (t + 1) / nth);
+        for (uint32_t k = k0; k < k1; k++) {
+            uint32_t row = k << newRate, steps = 0;
+            uint32_t v;
+            for (;;) {
+                if (row == z0) { v = steps; break; }
+                if ((row & oldMask) == row) { v = (uint32_t)fm.offs[row >> oldRate] + steps; break; }
+                int c;
+                row = ht2_lf_own(fm, row, c);
+                steps++;
+            }
+            out[k] = (IT)v;
+        }
+    };
+    if (nth == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    g.o_offs = oNew;
+    g.offRate = newRate;
+    g.offMask = (entryMax << newRate) & entryMax;
+    g.offsLen = nNew;
+}
+
 } // namespace
 
 Ht2Image* ht2_image_load(const char* base_c, std::string& err)
@@ -279,6 +333,7 @@ Ht2Image* ht2_image_load(const char* base_c, std::string& err)
             f2.u32(); // endian hint
             size_t n = (size_t)h.global.offsLen * 4;
             h.global.o_offs = b.put(f2.take(n), n, 128);
+            densifySample<uint32_t>(b, h.global);
         }
 
         // ---- .5/.6.ht2 : local indexes --------------------------------
@@ -309,6 +364,7 @@ Ht2Image* ht2_image_load(const char* base_c, std::string& err)
                     readBody(f5, b, g);
                     size_t n = (size_t)g.offsLen * 2;
                     g.o_offs = b.put(f6.take(n), n, 16);
+                    densifySample<uint16_t>(b, g);
                 }
                 // the reference appends local indexes to the list of their
                 // reference in file order (hgfm.h:2637-2641)
