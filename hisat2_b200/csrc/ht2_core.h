@@ -229,25 +229,20 @@ struct Ht2SwScratch {
 };
 
 // Per-read (pair) workspace.  One per in-flight GPU thread.
-struct Ht2Work {
-    Ht2Read     rd[2];
-    Ht2ReadHits hits[2][2];                 // [mate][fw=0/rc=1]
-    Ht2Hit      genomeHits[HT2_MAX_GHITS];  // _genomeHits
-    uint8_t     genomeHitsDone[HT2_MAX_GHITS];
-    uint32_t    nGenomeHits;
-    Ht2Hit      pool[HT2_POOL];             // GenomeHit temporaries (stack)
-    uint32_t    poolTop;
-    // _hits_searched (hi_aligner.h:6898-6922) as compact records in one arena shared by both
-    // mates: exactly the fields GenomeHit::operator== compares (Ht2SearchedRec + 8 B per edit)
-    alignas(8) uint8_t searched[HT2_SEARCHED_BYTES];
+struct alignas(128) Ht2Work {
+    // ---- scalars first: every segment of the state machine starts by reading a handful of them, and a slot's
+    // workspace is cold (evicted from L1, often from L2) when its next round begins -- three adjacent 128-byte
+    // lines instead of twenty scattered over 240 kB
+    // explicit-stack state machine (ht2_machine.h)
+    int64_t     childRet;
+    uint32_t    st, nFrames;
+    uint8_t     curRdi, curFw, alignRet, pad8;
+    uint8_t     found[2][2];
+    uint32_t    err;
+    uint32_t    nGenomeHits, poolTop;
     uint32_t    searchedTop;                // bytes used
     uint32_t    nSearched[2];
-    Ht2Res      res[2][HT2_MAX_RES];        // rs1u_/rs2u_ of AlnSinkWrap
-    uint32_t    nRes[2];
-    Ht2Edit     resEdits[HT2_RES_EDITS];    // their edits, appended in report order
-    uint32_t    nResEdits;
-    uint16_t    pairs[HT2_MAX_PAIRS][2];    // rs1_/rs2_ as indexes into res
-    uint32_t    nPairs;
+    uint32_t    nRes[2], nResEdits, nPairs, nCoords, nCurIe, nOffDiffs;
     // AlnSinkWrap best-score tracking (aln_sink.h:2600-2655)
     int64_t     bestPair, best2Pair, bestUnp[2], best2Unp[2];
 #ifdef HT2_ENABLE_SPLICED
@@ -258,8 +253,38 @@ struct Ht2Work {
     uint32_t    doneConcord, doneUnpair[2], stDone;
     int64_t     concordBest;
     uint32_t    concordInspected[2];        // _concordantIdxInspected
+    Ht2Rng      rnd;
+    // work counters (HIMetrics hi_aligner.h:3897 + roofline accounting)
+    uint32_t    localindexatts;
+    uint32_t    maxLocalindexatts;
+    uint32_t    nLF;      // LF steps (boundary ranks) executed
+    uint32_t    nSides;   // sides touched
+    uint32_t    algBytes; // algorithmic bytes: sides*sideSz + ftab/eftab entries + SA samples + 2-bit ref bytes
+    uint32_t    maxPool, maxDepth, maxEdits; // high-water marks (sizing evidence)
+    // per-read configuration (so a workspace can be resumed by any lane)
+    int64_t     cfgMinsc[2];
+    uint8_t     cfgPaired, cfgRightendonly, cfgNofw[2], cfgNorc[2], cfgPad[2];
+    uint32_t    unit, filtBits;
+    uint32_t    hybIter, hybHj, mateI, mateJ, mateSize[2];
+    // partialSearch continuation (time slicing, HT2_PS_SLICE): a search that has not finished after a slice of LF
+    // steps parks its loop state here and the slot stays in TS_PS, so that a round never lasts longer than one slice
+    // while most lanes of the group have long finished (a partial search is ~12 steps on average, ~90 at most)
+    uint32_t    psCont, psTop, psBot, psNtop, psNbot, psDep, psSame, psSimilar;
+    uint8_t     psPseudo, psAnchor, psPad[2];
+    // ---- arrays
+    Ht2Read     rd[2];
+    Ht2ReadHits hits[2][2];                 // [mate][fw=0/rc=1]
+    Ht2Frame    frames[HT2_DEPTH_CAP];
+    Ht2Hit      genomeHits[HT2_MAX_GHITS];  // _genomeHits
+    uint8_t     genomeHitsDone[HT2_MAX_GHITS];
+    Ht2Hit      pool[HT2_POOL];             // GenomeHit temporaries (stack)
+    // _hits_searched (hi_aligner.h:6898-6922) as compact records in one arena shared by both
+    // mates: exactly the fields GenomeHit::operator== compares (Ht2SearchedRec + 8 B per edit)
+    alignas(8) uint8_t searched[HT2_SEARCHED_BYTES];
+    Ht2Res      res[2][HT2_MAX_RES];        // rs1u_/rs2u_ of AlnSinkWrap
+    Ht2Edit     resEdits[HT2_RES_EDITS];    // their edits, appended in report order
+    uint16_t    pairs[HT2_MAX_PAIRS][2];    // rs1_/rs2_ as indexes into res
     Ht2Coord    coords[HT2_MAX_COORDS];     // BWTHit::_coords scratch
-    uint32_t    nCoords;
     alignas(8) uint8_t refbuf[HT2_REFBUF + 16];   // getStretch stores 32-bit words
     alignas(8) uint8_t refbuf2[HT2_REFBUF + 16];
     int64_t     tscores[HT2_MAX_RDLEN];
@@ -267,34 +292,7 @@ struct Ht2Work {
     Ht2AltScratch alt;                      // graph indexes only
     Ht2GWalk    gw;                         // group walk over graph indexes (ht2_gwalk.h)
     uint16_t    curIe[24][2];               // in-edge list of the most recent global/local GFM search (graph)
-    uint32_t    nCurIe;
     uint32_t    offDiffs[40][2];            // findOffDiffs scratch: (|diff|, sign as 0/1/2 = -1/0/+1)
-    uint32_t    nOffDiffs;
-    Ht2Rng      rnd;
-    uint32_t    err;
-    // work counters (HIMetrics hi_aligner.h:3897 + roofline accounting)
-    uint32_t    localindexatts;
-    uint32_t    maxLocalindexatts;
-    uint32_t    nLF;      // LF steps (boundary ranks) executed
-    uint32_t    maxPool, maxDepth, maxEdits; // high-water marks (sizing evidence)
-    // per-read configuration (so a workspace can be resumed by any lane)
-    int64_t     cfgMinsc[2];
-    uint8_t     cfgPaired, cfgRightendonly, cfgNofw[2], cfgNorc[2], cfgPad[2];
-    uint32_t    unit, filtBits;
-    // explicit-stack state machine (ht2_machine.h)
-    uint32_t    st, nFrames;
-    int64_t     childRet;
-    uint8_t     curRdi, curFw, alignRet, pad8;
-    uint8_t     found[2][2];
-    uint32_t    hybIter, hybHj, mateI, mateJ, mateSize[2];
-    // partialSearch continuation (time slicing, HT2_PS_SLICE): a search that has not finished after a slice of LF
-    // steps parks its loop state here and the slot stays in TS_PS, so that a round never lasts longer than one slice
-    // while most lanes of the group have long finished (a partial search is ~12 steps on average, ~90 at most)
-    uint32_t    psCont, psTop, psBot, psNtop, psNbot, psDep, psSame, psSimilar;
-    uint8_t     psPseudo, psAnchor, psPad[2];
-    Ht2Frame    frames[HT2_DEPTH_CAP];
-    uint32_t    nSides;   // sides touched
-    uint32_t    algBytes; // algorithmic bytes: sides*sideSz + ftab/eftab entries + SA samples + 2-bit ref bytes
 };
 
 // ------------------------------------------------------------------------

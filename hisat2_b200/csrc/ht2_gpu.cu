@@ -323,6 +323,12 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
         __syncwarp();
         if (nsel == 0) continue;        // another warp took them first, or the counter was ahead of the bitmap
         const int my = lane < nsel ? (int)sel[lane] : -1;
+        if (my >= 0) {   // the slot's scalars (first three lines of Ht2Work) are cold by now: fetch them side by side, not one after the other
+            const char* wp = (const char*)(base + my);
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(wp));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(wp + 128));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(wp + 256));
+        }
         __threadfence_block();   // acquire: the previous owner's workspace writes
         const long long t0 = o.stats ? clock64() : 0;
         if (my >= 0) {
