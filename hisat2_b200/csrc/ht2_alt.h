@@ -421,18 +421,24 @@
 
     // HI_Aligner::partialSearch on a graph index: the generic chain step of ht2_seed.h, stored as a BWTHit
     // with its in-edge list (hi_aligner.h:6361-6601).
-    HT2_NI void partialSearchGraph(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
+    // Returns false when the search was parked after a slice of steps (W->psG): call again to continue.
+#ifndef HT2_PSG_SLICE
+#define HT2_PSG_SLICE 8
+#endif
+    HT2_NI bool partialSearchGraph(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
-        if (hit.nhits >= HT2_MAX_PHITS) { W->err |= HT2_ERR_PHITS; hit.cur = W->rd[rdi].len; hit.done = 1; return; }
+        if (!W->psG.active && hit.nhits >= HT2_MAX_PHITS) { W->err |= HT2_ERR_PHITS; hit.cur = W->rd[rdi].len; hit.done = 1; return true; }
         Ht2SeedState st;
         st.len = W->rd[rdi].len; st.cur = hit.cur; st.done = hit.done;
         st.numPartialSearch = hit.numPartialSearch; st.numUniqueSearch = hit.numUniqueSearch;
         st.err = 0; st.nLF = 0; st.algBytes = 0;
         Ht2SeedHit sh;
-        ht2_seed_partial<true>(gfm, *P, W->rd[rdi].seq[fw ? 0 : 1], st, sh, pseudogeneStop, anchorStop);
-        hit.cur = st.cur; hit.done = st.done; hit.numPartialSearch = st.numPartialSearch; hit.numUniqueSearch = st.numUniqueSearch;
+        const bool finished = ht2_seed_partial<true>(gfm, *P, W->rd[rdi].seq[fw ? 0 : 1], st, sh, pseudogeneStop, anchorStop, &W->psG, HT2_PSG_SLICE);
+        hit.numPartialSearch = st.numPartialSearch;
         W->nLF += st.nLF; W->algBytes += st.algBytes;
         if (st.err) HT2_GERR(5);
+        if (!finished) return false;
+        hit.cur = st.cur; hit.done = st.done; hit.numUniqueSearch = st.numUniqueSearch;
         Ht2BwtHit& ph = hit.hits[hit.nhits++];
         ph.top = sh.top; ph.bot = sh.bot; ph.node_top = sh.node_top; ph.node_bot = sh.node_bot;
         ph.bwoff = sh.bwoff; ph.len = sh.len; ph.hit_type = sh.hit_type; ph.hasCoords = 0;
@@ -444,6 +450,7 @@
                 ph.ieN = sh.niedges; hit.nie += sh.niedges;
             }
         }
+        return true;
     }
 
     // globalGFMSearch / localGFMSearch on a graph index (hi_aligner.h:6606-6744, 6751-6892); the in-edge list

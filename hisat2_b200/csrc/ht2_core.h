@@ -272,6 +272,7 @@ struct alignas(128) Ht2Work {
     uint32_t    psCont, psTop, psBot, psNtop, psNbot, psDep, psSame, psSimilar;
     uint8_t     psPseudo, psAnchor, psPad[2];
     // ---- arrays
+    Ht2SeedResume psG;                      // the same for graph indexes (ht2_seed_partial)
     Ht2Read     rd[2];
     Ht2ReadHits hits[2][2];                 // [mate][fw=0/rc=1]
     Ht2Frame    frames[HT2_DEPTH_CAP];
@@ -820,7 +821,7 @@ struct Ht2AlignerT {
 #define HT2_PS_SLICE 16
 #endif
     HT2_NI bool partialSearch(uint32_t rdi, bool fw, bool& pseudogeneStop, bool& anchorStop) {
-        if (GRAPH) { partialSearchGraph(rdi, fw, pseudogeneStop, anchorStop); return true; }
+        if (GRAPH) return partialSearchGraph(rdi, fw, pseudogeneStop, anchorStop);
         bool pseudogeneStop_ = pseudogeneStop, anchorStop_ = anchorStop;
         pseudogeneStop = anchorStop = false;
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];

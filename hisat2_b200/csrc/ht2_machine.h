@@ -752,7 +752,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
 }
 
 // Run one read (pair) to completion (host build and the one-lane-per-read kernel loop).
-template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStart() { W->st = TS_START; W->nFrames = 0; W->psCont = 0; }
+template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStart() { W->st = TS_START; W->nFrames = 0; W->psCont = 0; W->psG.active = 0; }
 template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineDone() const { return W->st == TS_DONE && W->nFrames == 0; }
 template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStep()
 {

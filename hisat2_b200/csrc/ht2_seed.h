@@ -50,38 +50,62 @@ HT2_HD void ht2_seed_step(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c
     if (overflow) st.err |= 1;
 }
 
-// HI_Aligner::partialSearch.  pseudogeneStop / anchorStop are in/out like the reference's.
+// A partial search parked after a slice of LF steps (time slicing inside the alignment kernel: the slot stays in
+// TS_PS and is regrouped, so that a round is never as long as its slowest lane's search).
+struct Ht2SeedResume {
+    uint32_t active, top, bot, ntop, nbot, dep, same, similar, nie;
+    uint8_t  pseudo, anchor, pad[2];
+    uint16_t ie[HT2G_MAX_IEDGES][2];
+};
+
+// HI_Aligner::partialSearch.  pseudogeneStop / anchorStop are in/out like the reference's.  With rs != NULL the
+// search runs at most `budget` steps per call: it returns false after parking its state in *rs (call again with
+// the same arguments to continue) and true when it has finished.
 template <bool GRAPH>
-HT2_HD void ht2_seed_partial(const Ht2Fm<uint32_t>& fm, const Ht2ParamsCore& P, const uint8_t* seq, Ht2SeedState& st,
-                             Ht2SeedHit& ph, bool& pseudogeneStop, bool& anchorStop) {
+HT2_HD bool ht2_seed_partial(const Ht2Fm<uint32_t>& fm, const Ht2ParamsCore& P, const uint8_t* seq, Ht2SeedState& st,
+                             Ht2SeedHit& ph, bool& pseudogeneStop, bool& anchorStop, Ht2SeedResume* rs = NULL, uint32_t budget = 0xffffffffu) {
     bool pseudogeneStop_ = pseudogeneStop, anchorStop_ = anchorStop;
     pseudogeneStop = anchorStop = false;
     const uint32_t ftabLen = fm.g->ftabChars, len = st.len, minK = P.minK;
-    st.numPartialSearch++;
+    const bool resume = rs != NULL && rs->active != 0;
+    if (!resume) st.numPartialSearch++;
     const uint32_t offset = st.cur;
     uint32_t dep = offset;
     ph.top = ph.bot = ph.node_top = ph.node_bot = HT2_IDX_MAX32;
     ph.bwoff = offset; ph.hit_type = 1 /*CANDIDATE_HIT*/; ph.niedges = 0; ph.pseudogeneStop = ph.anchorStop = 0;
+    uint32_t top = 0, bot = 0, ntop = 0, nbot = 0;
+    uint32_t same_range = 0, similar_range = 0;
+    uint16_t ie[HT2G_MAX_IEDGES][2], tie[HT2G_MAX_IEDGES][2];
+    uint32_t nie = 0, ntie = 0;
+    if (resume) {
+        top = rs->top; bot = rs->bot; ntop = rs->ntop; nbot = rs->nbot; dep = rs->dep; same_range = rs->same; similar_range = rs->similar;
+        pseudogeneStop_ = rs->pseudo != 0; anchorStop_ = rs->anchor != 0; nie = rs->nie;
+        for (uint32_t e = 0; e < nie; e++) { ie[e][0] = rs->ie[e][0]; ie[e][1] = rs->ie[e][1]; }
+        rs->active = 0;
+    } else {
     const uint32_t left = len - dep;
-    if (left < ftabLen + 1) { st.cur = len; ph.len = st.cur - offset; st.done = 1; return; }
+    if (left < ftabLen + 1) { st.cur = len; ph.len = st.cur - offset; st.done = 1; return true; }
     for (uint32_t i = 0; i < ftabLen; i++) {
         if (seq[len - dep - 1 - i] > 3) {
             st.cur += (i + 1);
             ph.len = st.cur - offset;
             if (st.cur >= len) st.done = 1;
-            return;
+            return true;
         }
     }
-    uint32_t top = 0, bot = 0, ntop = 0, nbot = 0;
     ht2_ftab_lohi(fm, seq, len - dep - ftabLen, top, bot);
     st.algBytes += 8;
     dep += ftabLen;
-    if (top >= bot) { st.cur = dep; ph.len = st.cur - offset; if (st.cur >= len) st.done = 1; return; }
-    uint32_t same_range = 0, similar_range = 0;
+    if (top >= bot) { st.cur = dep; ph.len = st.cur - offset; if (st.cur >= len) st.done = 1; return true; }
+    }
     const uint32_t khits5 = P.khits < 5 ? P.khits : 5;
-    uint16_t ie[HT2G_MAX_IEDGES][2], tie[HT2G_MAX_IEDGES][2];
-    uint32_t nie = 0, ntie = 0;
     while (dep < len) {
+        if (rs != NULL && budget-- == 0) {
+            rs->active = 1; rs->top = top; rs->bot = bot; rs->ntop = ntop; rs->nbot = nbot; rs->dep = dep; rs->same = same_range; rs->similar = similar_range;
+            rs->pseudo = pseudogeneStop_ ? 1 : 0; rs->anchor = anchorStop_ ? 1 : 0; rs->nie = nie;
+            for (uint32_t e = 0; e < nie; e++) { rs->ie[e][0] = ie[e][0]; rs->ie[e][1] = ie[e][1]; }
+            return false;
+        }
         const int c = seq[len - dep - 1];
         uint32_t ttop = 0, tbot = 0, tntop = 0, tnbot = 0;
         ntie = 0;
@@ -130,6 +154,7 @@ HT2_HD void ht2_seed_partial(const Ht2Fm<uint32_t>& fm, const Ht2ParamsCore& P, 
     }
     ph.pseudogeneStop = pseudogeneStop ? 1 : 0;
     ph.anchorStop = anchorStop ? 1 : 0;
+    return true;
 }
 
 // Joined offset of element i of a hit's node range (group_walk.h:545-560: first BW row of the node).

@@ -120,17 +120,23 @@ HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const
         const size_t c0 = (size_t)j * seg, cn = (size_t)(j + 1) * seg, cp = j ? (size_t)(j - 1) * seg : Hz;   // this / next / previous column
         uint32_t vF = 0;
         uint32_t vH = (HT2_SWP(0, cp + seg - 1) << 16) | (uint32_t)HT2_SW_TOP;   // diagonal of row 0 = perfect; of row seg = last row of half 0
+        // The loads of iteration s + 1 are issued before the stores of iteration s: all planes live in one pool, so
+        // the compiler must assume the stores alias them and would otherwise start each iteration's loads only
+        // after the previous iteration's stores (the fill was 87 % long_scoreboard in the round-2 profile).
+        uint32_t nE = HT2_SWP(1, c0), nHp = HT2_SWP(0, cp), nG = HT2_SWQ(5, 0), nP = HT2_SWQ(pr, 0), nR = HT2_SWQ(6, 0);
         for (uint32_t s = 0; s < seg; s++) {
-            uint32_t vE = HT2_SWP(1, c0 + s);
-            vF = ht2_v2_addmax(vF, HT2_SWQ(5, s), 0);                       // veto ref-gap extensions in barrier rows
+            uint32_t vE = nE;
+            const uint32_t hp = nHp, wG = nG, wP = nP, wR = nR;
+            if (s + 1 < seg) { nE = HT2_SWP(1, c0 + s + 1); nHp = HT2_SWP(0, cp + s + 1); nG = HT2_SWQ(5, s + 1); nP = HT2_SWQ(pr, s + 1); nR = HT2_SWQ(6, s + 1); }
+            vF = ht2_v2_addmax(vF, wG, 0);                                  // veto ref-gap extensions in barrier rows
             HT2_SWP(2, c0 + s) = vF;
-            vH = ht2_v2_addmax(vH, HT2_SWQ(pr, s), 0);                         // match / mismatch
+            vH = ht2_v2_addmax(vH, wP, 0);                                  // match / mismatch
             vH = ht2_v2_max3(vH, vE, vF);
             HT2_SWP(0, c0 + s) = vH;
-            vE = ht2_v2_addmax(vE, nRDE, ht2_v2_addmax(vH, HT2_SWQ(6, s), 0));   // E of the next column
+            vE = ht2_v2_addmax(vE, nRDE, ht2_v2_addmax(vH, wR, 0));         // E of the next column
             HT2_SWP(1, cn + s) = vE;
-            vF = ht2_v2_addmax(vF, nRFE, ht2_v2_addmax(vH, nRFO, 0));   // F of the next row
-            vH = HT2_SWP(0, cp + s);
+            vF = ht2_v2_addmax(vF, nRFE, ht2_v2_addmax(vH, nRFO, 0));       // F of the next row
+            vH = hp;
         }
         // lazy F: carry each half's last F into the other half's first rows while it still improves
         {
