@@ -461,8 +461,12 @@ HT2_HD int64_t ht2_intron_pen(int intronlen) {
 // ------------------------------------------------------------------------
 // The aligner
 // ------------------------------------------------------------------------
-template <bool GRAPH>
+// NOSPL = true compiles the aligner for --no-spliced-alignment only: every spliced branch (the spliced join of
+// combineWith, splice scoring, intron windows) becomes dead code.  The pool kernel is bound by instruction fetch
+// (DESIGN.md 4.1), so the DNA configuration gets its own, smaller instantiation; NOSPL = false reads the option.
+template <bool GRAPH, bool NOSPL = false>
 struct Ht2AlignerT {
+    HT2_HD bool noSpl() const { return NOSPL ? true : (P->noSplicedAlignment != 0); }
     const uint8_t*        blob;
     const Ht2ImageHeader* H;
     Ht2Fm<uint32_t>       gfm;
@@ -1288,7 +1292,7 @@ struct Ht2AlignerT {
         if (this_toff > other_toff) return false;
         uint32_t refdif = other_toff - this_toff;
         uint32_t rddif = other_rdoff - this_rdoff;
-        if (!P->noSplicedAlignment) {
+        if (!noSpl()) {
             if (refdif > rddif + P->maxIntronLen) return false;
         }
         return true;
@@ -1348,7 +1352,7 @@ struct Ht2AlignerT {
         bool spliced = false, ins = false, del = false;
         if (refdif != rddif) {
             if (refdif > rddif) {
-                if (!P->noSplicedAlignment && refdif - rddif >= P->minIntronLen) spliced = true;
+                if (!noSpl() && refdif - rddif >= P->minIntronLen) spliced = true;
                 else del = true;
             } else ins = true;
         }
@@ -1797,7 +1801,7 @@ struct Ht2AlignerT {
         while (pickNextReadToSearch(rdi, fw)) {
             uint32_t fwi = fw ? 0 : 1;
             Ht2ReadHits& hit = W->hits[rdi][fwi];
-            bool pseudogeneStop = gfm.g->linearFM && !P->noSplicedAlignment;
+            bool pseudogeneStop = gfm.g->linearFM && !noSpl();
             bool anchorStop = P->anchorStop != 0;
             if (!P->secondary) {
                 uint32_t numSearched = hit.numPartialSearch - hit.numUniqueSearch;
@@ -1909,7 +1913,7 @@ struct Ht2AlignerT {
                     if (gh.tidx != coord.ref || gh.fw != coord.fw) continue;
                     uint32_t hitoff = gh.toff + hit.len - gh.rdoff;
                     uint32_t hitoff2 = coord.off + hit.len - rdoff;
-                    int64_t hitoff_diff = (P->noSplicedAlignment ? 0 : (int64_t)P->maxIntronLen);
+                    int64_t hitoff_diff = (noSpl() ? 0 : (int64_t)P->maxIntronLen);
                     int64_t d = (int64_t)hitoff - (int64_t)hitoff2;
                     if (d < 0) d = -d;
                     if (d <= hitoff_diff) { overlapped = true; gh.hitcount++; break; }

@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t rg_code(const Ht2Work* W)
 // the GPC instruction cache saturate when every warp walks different code) while groups are drawn from a pool
 // large enough to fill all 32 lanes.
 // ---------------------------------------------------------------------------
-template <int NW, int K, bool GRAPH>
+template <int NW, int K, bool GRAPH, bool NOSPL>
 __global__ void __launch_bounds__(32 * NW)
 ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatch b, DevOut o, Ht2Work* work)
 {
@@ -256,7 +256,7 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
     for (int i = t; i < RG_BINS * NWORD; i += 32 * NW) sBits[i / NWORD][i % NWORD] = (i / NWORD == (int)RG_NEED) ? 0xffffffffu : 0u;
     if (t < RG_BINS) sCount[t] = (t == RG_NEED) ? S : 0;
     if (t == 0) { sTarget = RG_NEED; sExit = 0; }
-    Ht2AlignerT<GRAPH> A;
+    Ht2AlignerT<GRAPH, NOSPL> A;
     A.bind(blob, &P, base);
     A.sw = b.sw ? b.sw + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) : NULL;
     A.swPl = b.swPool ? b.swPool + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)HT2_SW_POOL_WORDS : NULL;
@@ -670,12 +670,12 @@ static int finishOpen(ht2gpu_handle* h)
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->nSM = prop.multiProcessorCount;
     // the pool kernel: one block of poolWarps warps per SM, rgK read slots per lane
-    h->poolWarps = (h->opt.threads_per_block >= 512 && !h->graph) ? 16 : ((h->opt.threads_per_block == 128 && !h->graph) ? 4 : 8);
+    h->poolWarps = (h->opt.threads_per_block == 128 && !h->graph) ? 4 : 8;
     h->tpb = 32 * h->poolWarps;
     h->bpsm = (h->opt.blocks_per_sm > 0 && !h->graph) ? h->opt.blocks_per_sm : 1;
     h->rgK = (h->opt.slots_per_lane > 0 && !h->graph) ? h->opt.slots_per_lane : 4;
     if (h->rgK != 2 && h->rgK != 4 && !(h->poolWarps == 4 && h->rgK == 8)) h->rgK = 4;
-    if (h->poolWarps == 16) h->rgK = 2;   // at most 1024 slots per block: one bitmap word per lane
+    if (h->poolWarps == 16) { h->poolWarps = 8; h->tpb = 256; }   // the 16-warp variant was slower and is no longer built
     h->nWork = (size_t)h->nSM * h->bpsm * h->poolWarps * 32 * h->rgK;
     CK(cudaMalloc(&h->dMinsc, sizeof(h->P.minscTab)));
     CK(cudaMemcpy(h->dMinsc, h->P.minscTab, sizeof(h->P.minscTab), cudaMemcpyHostToDevice));
@@ -691,8 +691,8 @@ static int finishOpen(ht2gpu_handle* h)
         // known call tree; graph indexes recurse through alignWithALTs (ht2_alt.h, depth <= HT2_ALT_MAXDEP).
         size_t need = 0;
         cudaFuncAttributes fa;
-        if (h->graph) { CK(cudaFuncGetAttributes(&fa, ht2_align_pool_kernel<8, 4, true>)); need = fa.localSizeBytes + 36 * 1024; }
-        else { CK(cudaFuncGetAttributes(&fa, ht2_align_pool_kernel<8, 4, false>)); need = fa.localSizeBytes + 4 * 1024; }
+        if (h->graph) { CK(cudaFuncGetAttributes(&fa, ht2_align_pool_kernel<8, 4, true, false>)); need = fa.localSizeBytes + 36 * 1024; }
+        else { CK(cudaFuncGetAttributes(&fa, ht2_align_pool_kernel<8, 4, false, false>)); need = fa.localSizeBytes + 4 * 1024; }
         CK(cudaFuncGetAttributes(&fa, ht2_sam_kernel<true>));
         if (fa.localSizeBytes + 2048 > need) need = fa.localSizeBytes + 2048;
         size_t cur = 0;
@@ -946,14 +946,18 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
     o.stats = h->dStats;
     CK(cudaMemsetAsync(S.dCounters, 0, 8 * sizeof(unsigned int), S.stream));
     const uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
-    if (h->graph) ht2_align_pool_kernel<8, 4, true><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
-    else {
+    const bool nospl = h->P.noSplicedAlignment != 0;   // the DNA-only instantiation has less code
+    if (h->graph) {
+        if (nospl) ht2_align_pool_kernel<8, 4, true, true><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
+        else ht2_align_pool_kernel<8, 4, true, false><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
+    } else {
         switch (h->poolWarps * 100 + h->rgK) {
-            case 802:  ht2_align_pool_kernel<8, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 408:  ht2_align_pool_kernel<4, 8, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 404:  ht2_align_pool_kernel<4, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 1602: ht2_align_pool_kernel<16, 2, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            default:   ht2_align_pool_kernel<8, 4, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 802:  ht2_align_pool_kernel<8, 2, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 408:  ht2_align_pool_kernel<4, 8, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            default:
+                if (nospl) ht2_align_pool_kernel<8, 4, false, true><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
+                else ht2_align_pool_kernel<8, 4, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
+                break;
         }
     }
     CK(cudaGetLastError());

@@ -31,7 +31,7 @@ enum {
 };
 
 // push a child frame (== a recursive call of hybridSearch_recur)
-template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::pushFrame(uint32_t rdi, const Ht2Hit* hit, uint32_t hitoff, uint32_t hitlen, bool alignMate, uint32_t dep)
+template <bool GRAPH, bool NOSPL> HT2_HD void Ht2AlignerT<GRAPH, NOSPL>::pushFrame(uint32_t rdi, const Ht2Hit* hit, uint32_t hitoff, uint32_t hitlen, bool alignMate, uint32_t dep)
 {
     if (W->nFrames >= HT2_DEPTH_CAP) { W->err |= HT2_ERR_DEPTH; W->childRet = HT2_MIN_I64; return; }
     Ht2Frame& f = W->frames[W->nFrames++];
@@ -39,7 +39,7 @@ template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::pushFrame(uint32_t rdi, co
 }
 
 // One segment of one hybridSearch_recur activation.
-template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
+template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFrame()
 {
     Ht2Frame& f = W->frames[W->nFrames - 1];
     const uint32_t rdi = f.rdi;
@@ -54,7 +54,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
     case F_ENTER: {
         f.maxsc = HT2_MIN_I64;
         f.cushion = 0;
-        if (P->noSplicedAlignment)
+        if (noSpl())
             f.cushion = alignMate ? (int64_t)((double)rdlen * 0.03 * (double)ht2_mmpen(*P, 255)) : 0;
         f.poolMark = W->poolTop;
         if (hit.score + f.cushion < minsc[rdi]) { f.pc = F_RETURN; break; }
@@ -555,7 +555,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runFrame()
 }
 
 // One segment of the top-level control (go / nextBWT / align / hybridSearch / alignMate).
-template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
+template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runTop()
 {
     switch (W->st) {
     case TS_START: {
@@ -609,7 +609,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
     case TS_PS: {
         const uint32_t rdi = W->curRdi; const bool fw = W->curFw != 0;
         Ht2ReadHits& hit = W->hits[rdi][fw ? 0 : 1];
-        bool pseudogeneStop = gfm.g->linearFM && !P->noSplicedAlignment;
+        bool pseudogeneStop = gfm.g->linearFM && !noSpl();
         bool anchorStop = P->anchorStop != 0;
         if (!partialSearch(rdi, fw, pseudogeneStop, anchorStop)) break;   // parked after a slice of LF steps: stay in TS_PS
         if (hit.done) { W->st = TS_ALIGN; break; }
@@ -752,9 +752,9 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::runTop()
 }
 
 // Run one read (pair) to completion (host build and the one-lane-per-read kernel loop).
-template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStart() { W->st = TS_START; W->nFrames = 0; W->psCont = 0; W->psG.active = 0; }
-template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineDone() const { return W->st == TS_DONE && W->nFrames == 0; }
-template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStep()
+template <bool GRAPH, bool NOSPL> HT2_HD void Ht2AlignerT<GRAPH, NOSPL>::machineStart() { W->st = TS_START; W->nFrames = 0; W->psCont = 0; W->psG.active = 0; }
+template <bool GRAPH, bool NOSPL> HT2_HD bool Ht2AlignerT<GRAPH, NOSPL>::machineDone() const { return W->st == TS_DONE && W->nFrames == 0; }
+template <bool GRAPH, bool NOSPL> HT2_HD void Ht2AlignerT<GRAPH, NOSPL>::machineStep()
 {
     if (W->nFrames > 0) runFrame();
     else runTop();
@@ -762,7 +762,7 @@ template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineStep()
 // "Heavy" states are the ones worth regrouping lanes for (index searches,
 // reference extension, combine); everything else is short glue that is chained
 // onto the end of the previous segment.
-template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineAtHeavyState() const
+template <bool GRAPH, bool NOSPL> HT2_HD bool Ht2AlignerT<GRAPH, NOSPL>::machineAtHeavyState() const
 {
     if (W->nFrames > 0) {
         switch (W->frames[W->nFrames - 1].pc) {
@@ -779,7 +779,7 @@ template <bool GRAPH> HT2_HD bool Ht2AlignerT<GRAPH>::machineAtHeavyState() cons
     }
 }
 // run one heavy segment plus the glue that follows it
-template <bool GRAPH> HT2_HD void Ht2AlignerT<GRAPH>::machineRun()
+template <bool GRAPH, bool NOSPL> HT2_HD void Ht2AlignerT<GRAPH, NOSPL>::machineRun()
 {
     do { machineStep(); } while (!machineAtHeavyState());
 }

@@ -6,7 +6,7 @@
 // PairedEndPolicy::peClassifyPair (pe.cpp:38-132) with the hisat2 defaults
 // olapOk = containOk = expandToFit = true, dovetailOk = false (hisat2.cpp:348-352).
 // Returns true iff the pair is NOT discordant.
-template <bool GRAPH> HT2_NI bool Ht2AlignerT<GRAPH>::peConcordant(int64_t off1, uint32_t len1, bool fw1, int64_t off2, uint32_t len2, bool fw2) const
+template <bool GRAPH, bool NOSPL> HT2_NI bool Ht2AlignerT<GRAPH, NOSPL>::peConcordant(int64_t off1, uint32_t len1, bool fw1, int64_t off2, uint32_t len2, bool fw2) const
 {
     uint32_t maxfrag = P->maxFrag;
     if (len1 > maxfrag) maxfrag = len1;
@@ -37,7 +37,7 @@ template <bool GRAPH> HT2_NI bool Ht2AlignerT<GRAPH>::peConcordant(int64_t off1,
 
 // HI_Aligner::pairReads (hi_aligner.h:5948-6057) + AlnSinkWrap::report for a
 // pair (aln_sink.h:2565-2611) + ReportingState::foundConcordant (aln_sink.cpp:72-92).
-template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::pairReads()
+template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::pairReads()
 {
     const uint32_t n1 = W->nRes[0], n2 = W->nRes[1];
     uint32_t start_i = W->concordInspected[0], start_j = W->concordInspected[1];
@@ -66,11 +66,11 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::pairReads()
             if (right > right2) continue;
             if (right + (int64_t)(int)P->maxIntronLen < left2) continue;
             bool dna_frag_pass = true;
-            if (P->noSplicedAlignment) {
+            if (noSpl()) {
                 if (r1.toff < r2.toff) dna_frag_pass = peConcordant(r1.toff, r1.rfextent, r1.fw != 0, r2.toff, r2.rfextent, r2.fw != 0);
                 else dna_frag_pass = peConcordant(r2.toff, r2.rfextent, r2.fw != 0, r1.toff, r1.rfextent, r1.fw != 0);
             }
-            if (!P->noSplicedAlignment || dna_frag_pass) {
+            if (!noSpl() || dna_frag_pass) {
                 int64_t threshold = W->bestPair;
                 if (W->bestUnp[0] >= minsc[0] && W->bestUnp[1] >= minsc[1]) {
                     double t = (double)(W->bestUnp[0] + W->bestUnp[1]) -
@@ -96,7 +96,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::pairReads()
 }
 
 // anchor search part of alignMate (hi_aligner.h:5600-5717): fills W->genomeHits
-template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
+template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::alignMateAnchors(uint32_t rdi, bool fw, uint32_t tidx, uint32_t toff)
 {
     const uint32_t ordi = 1 - rdi;
     const bool ofw = (fw == (P->gMate2fw != 0)) ? (P->gMate1fw != 0) : (P->gMate2fw != 0);
@@ -130,7 +130,7 @@ template <bool GRAPH> HT2_NI void Ht2AlignerT<GRAPH>::alignMateAnchors(uint32_t 
                 W->nGenomeHits = 0;
                 for (uint32_t ri = 0; ri < ncoords; ri++) {
                     const Ht2Coord& coord = coords[ri];
-                    if (P->noSplicedAlignment) {
+                    if (noSpl()) {
                         if (coord.off + P->maxFrag * 2 < toff || toff + P->maxFrag * 2 < coord.off) continue;
                     }
                     if (W->nGenomeHits >= HT2_MAX_GHITS) { W->err |= HT2_ERR_GHITS; break; }
