@@ -84,20 +84,12 @@ extern "C" int ht2gpu_run_reads_multi(ht2gpu_handle_t** hs, int nDev, const ht2g
     if (in->path2) { if (!ht2_source_open(b, in->path2, err)) return fail(HT2GPU_ERR_ARG, err); }
     else if (in->data2) ht2_source_memory(b, in->data2, in->len2);
     const bool fastq = in->format == 1;
-    if (!ht2_source_index(a, fastq, pool, err)) return fail(HT2GPU_ERR_ARG, err);
-    if (paired && !ht2_source_index(b, fastq, pool, err)) return fail(HT2GPU_ERR_ARG, err);
-    if (paired && a.nRecords() != b.nRecords())
-        return fail(HT2GPU_ERR_ARG, a.nRecords() < b.nRecords() ? "fewer reads in file specified with -1 than in file specified with -2"
-                                                                : "fewer reads in file specified with -2 than in file specified with -1");
-    S.s_index = nowS() - t0;
-    // -s / -u (hisat2.cpp:1959-1964, 3319): records [skip, min(n, skip + upto))
-    uint64_t r0 = in->skip, r1 = a.nRecords();
-    if (r0 > r1) r0 = r1;
-    if (in->upto && r0 + in->upto < r1) r1 = r0 + in->upto;
+    // -s / -u (hisat2.cpp:1959-1964, 3319): records [skip, skip + upto)
+    const uint64_t r0 = in->skip;
+    const uint64_t rEnd = in->upto ? r0 + in->upto : ~(uint64_t)0;
     uint64_t perBatch = in->batch_reads ? in->batch_reads : 4000000;   // large batches amortise the drain of the pool kernel's last reads
     if (paired) perBatch = (perBatch + 1) / 2;   // batch_reads counts reads, a record here is a pair
     if (perBatch < 1) perBatch = 1;
-    const uint64_t nBatches = (r1 - r0 + perBatch - 1) / perBatch;
     Ht2ReadsOpts ro; ro.fastq = fastq; ro.trim5 = in->trim5; ro.trim3 = in->trim3; ro.phred64 = in->phred64 != 0; ro.seed = in->seed;
 
     // slot states: 0 free, 1 submitted
@@ -105,18 +97,42 @@ extern "C" int ht2gpu_run_reads_multi(ht2gpu_handle_t** hs, int nDev, const ht2g
     std::vector<int> state((size_t)nSlots, 0);
     uint64_t submitted = 0;
     int prodRc = HT2GPU_OK; std::string prodErr; bool prodDone = false;
-    double parseS = 0, submitS = 0, waitS = 0, sinkS = 0;
+    double parseS = 0, submitS = 0, waitS = 0, sinkS = 0, indexS = 0;
 
+    // The producer indexes the input only as far ahead as the next batch needs (so that indexing overlaps the device
+    // work), parses the batch on all threads and submits it.  The first batch is a quarter of the others: the device
+    // starts early, the later batches are large.
     std::thread producer([&]() {
-        for (uint64_t i = 0; i < nBatches; i++) {
+        uint64_t r = r0;
+        for (uint64_t i = 0; ; i++) {
             const int slot = (int)(i % (uint64_t)nSlots);
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[slot] == 0 || prodRc != HT2GPU_OK; }); if (prodRc != HT2GPU_OK) break; }
-            const uint64_t q0 = r0 + i * perBatch, q1 = q0 + perBatch < r1 ? q0 + perBatch : r1;
-            const double tp = nowS();
             std::string e;
             int rc = HT2GPU_OK;
-            if (!ht2_parse_batch(a, paired ? &b : NULL, q0, q1, ro, stage[slot], pool, C->scratch, e)) rc = HT2GPU_ERR_ARG;
-            parseS += nowS() - tp;
+            uint64_t want = (i == 0 && perBatch >= 8) ? perBatch / 4 : perBatch;
+            if (r + want > rEnd) want = rEnd > r ? rEnd - r : 0;
+            // make sure the records [r, r + want) -- and the start of the one after -- are indexed in every source
+            const double ti = nowS();
+            for (int k = 0; k < (paired ? 2 : 1) && rc == HT2GPU_OK; k++) {
+                Ht2ReadSource& src = k ? b : a;
+                while (!src.scanDone && src.nRecords() < r + want)
+                    if (!ht2_source_scan(src, fastq, pool, (size_t)256 << 20, e)) { rc = HT2GPU_ERR_ARG; break; }
+            }
+            indexS += nowS() - ti;
+            uint64_t avail = a.nRecords();
+            if (paired && b.nRecords() < avail) avail = b.nRecords();
+            uint64_t q1 = r + want < avail ? r + want : avail;
+            if (rc == HT2GPU_OK && paired && a.scanDone && b.scanDone && a.nRecords() != b.nRecords() && q1 >= avail && q1 < rEnd) {
+                rc = HT2GPU_ERR_ARG;
+                e = a.nRecords() < b.nRecords() ? "fewer reads in file specified with -1 than in file specified with -2"
+                                                : "fewer reads in file specified with -2 than in file specified with -1";
+            }
+            if (rc == HT2GPU_OK && q1 <= r) break;   // nothing left
+            if (rc == HT2GPU_OK) {
+                const double tp = nowS();
+                if (!ht2_parse_batch(a, paired ? &b : NULL, r, q1, ro, stage[slot], pool, C->scratch, e)) rc = HT2GPU_ERR_ARG;
+                parseS += nowS() - tp;
+            }
             if (rc == HT2GPU_OK) {
                 Ht2HostBatch& hb = stage[slot];
                 ht2gpu_read_batch_t rb; memset(&rb, 0, sizeof(rb));
@@ -129,6 +145,7 @@ extern "C" int ht2gpu_run_reads_multi(ht2gpu_handle_t** hs, int nDev, const ht2g
             std::lock_guard<std::mutex> lk(mu);
             if (rc != HT2GPU_OK) { prodRc = rc; prodErr = e; cv.notify_all(); break; }
             state[slot] = 1; submitted = i + 1;
+            r = q1;
             cv.notify_all();
         }
         std::lock_guard<std::mutex> lk(mu);
@@ -137,12 +154,12 @@ extern "C" int ht2gpu_run_reads_multi(ht2gpu_handle_t** hs, int nDev, const ht2g
     });
 
     int rc = HT2GPU_OK;
-    for (uint64_t i = 0; i < nBatches; i++) {
+    for (uint64_t i = 0; ; i++) {
         const int slot = (int)(i % (uint64_t)nSlots);
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return submitted > i || prodRc != HT2GPU_OK || prodDone; });
-            if (submitted <= i) { rc = prodRc != HT2GPU_OK ? prodRc : HT2GPU_ERR_ARG; break; }
+            if (submitted <= i) { rc = prodRc; break; }   // the producer has finished (or failed)
         }
         ht2gpu_sam_result_t r;
         const double tw = nowS();
@@ -163,7 +180,7 @@ extern "C" int ht2gpu_run_reads_multi(ht2gpu_handle_t** hs, int nDev, const ht2g
     // drain anything still in flight after an error
     if (rc != HT2GPU_OK) for (int s = 0; s < nSlots; s++) if (state[s] == 1) { ht2gpu_sam_result_t r; ht2gpu_wait_sam(hs[s % nDev], s / nDev, &r); }
     ht2_source_close(a); ht2_source_close(b);
-    S.s_parse = parseS; S.s_submit = submitS; S.s_wait = waitS; S.s_sink = sinkS; S.s_total = nowS() - t0;
+    S.s_index = indexS; S.s_parse = parseS; S.s_submit = submitS; S.s_wait = waitS; S.s_sink = sinkS; S.s_total = nowS() - t0;
     if (st) *st = S;
     if (rc != HT2GPU_OK) ht2gpu_set_error(h, prodErr.empty() ? "ht2gpu_run_reads failed" : prodErr.c_str());
     return rc;

@@ -80,22 +80,27 @@ void ht2_source_memory(Ht2ReadSource& s, const char* data, size_t n) { s.data = 
 void ht2_source_close(Ht2ReadSource& s)
 {
     if (s.map) munmap(s.map, s.mapLen);
-    s.map = NULL; s.data = NULL; s.size = 0; s.own.clear(); s.rec.clear();
+    s.map = NULL; s.data = NULL; s.size = 0; s.own.clear(); s.rec.clear(); s.scanPos = 0; s.scanDone = false; s.lineCarry = 0; s.strictFastq = true;
 }
 
-static void chunkOf(size_t size, unsigned t, unsigned T, size_t& c0, size_t& c1) { c0 = size / T * t; c1 = (t + 1 == T) ? size : size / T * (t + 1); }
-
-bool ht2_source_index(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, std::string& err)
+// Scan the next block of the input for record starts (appended to s.rec).  Blocks are scanned by all threads; the
+// pipeline calls this only as far ahead as the next batch needs, so that indexing overlaps the device work instead
+// of preceding it.  When the end of the input is reached the sentinel (== size) is appended and scanDone is set.
+bool ht2_source_scan(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, size_t blockBytes, std::string& err)
 {
-    s.rec.clear();
+    if (s.scanDone) return true;
     const char* d = s.data; const size_t n = s.size;
-    const unsigned T = (n < (1u << 20)) ? 1 : pool.size();
+    const size_t b0 = s.scanPos, b1 = (blockBytes == 0 || n - b0 <= blockBytes) ? n : b0 + blockBytes;
+    const size_t len = b1 - b0;
+    const unsigned T = (len < (1u << 20)) ? 1 : pool.size();
     std::vector<std::vector<uint64_t> > part(T);
+    auto chunk = [&](unsigned t, size_t& c0, size_t& c1) { c0 = b0 + len / T * t; c1 = (t + 1 == T) ? b1 : b0 + len / T * (t + 1); };
+    auto finish = [&]() { s.scanPos = b1; if (b1 == n) { s.rec.push_back(n); s.scanDone = true; } return true; };
     if (!fastq) {
         // a record starts at a '>' that begins a line
         auto scan = [&](unsigned t) {
             if (t >= T) return;
-            size_t c0, c1; chunkOf(n, t, T, c0, c1);
+            size_t c0, c1; chunk(t, c0, c1);
             std::vector<uint64_t>& v = part[t];
             const char* p = d + c0; const char* e = d + c1;
             while (p < e) {
@@ -106,45 +111,45 @@ bool ht2_source_index(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, std::st
             }
         };
         if (T == 1) scan(0); else pool.run(scan);
-        size_t tot = 0; for (auto& v : part) tot += v.size();
-        s.rec.reserve(tot + 1);
+        const bool hadNone = s.rec.empty();
         for (auto& v : part) s.rec.insert(s.rec.end(), v.begin(), v.end());
-        // what precedes the first record may only be blank or comment lines (pat.cpp:741-756)
-        size_t p = 0; const size_t first = s.rec.empty() ? n : (size_t)s.rec[0];
-        while (p < first) {
-            if (d[p] == '#' || d[p] == ';') { while (p < first && d[p] != '\n') p++; }
-            else if (d[p] == '\n' || d[p] == '\r') p++;
-            else { err = "reads file does not look like a FASTA file"; return false; }
+        if (hadNone && (!s.rec.empty() || b1 == n)) {
+            // what precedes the first record may only be blank or comment lines (pat.cpp:741-756)
+            size_t p = 0; const size_t first = s.rec.empty() ? n : (size_t)s.rec[0];
+            while (p < first) {
+                if (d[p] == '#' || d[p] == ';') { while (p < first && d[p] != '\n') p++; }
+                else if (d[p] == '\n' || d[p] == '\r') p++;
+                else { err = "reads file does not look like a FASTA file"; return false; }
+            }
         }
-        s.rec.push_back(n);
-        return true;
+        return finish();
     }
-    // FASTQ: strict 4-line records start at lines 0, 4, 8, ... -- count newlines per chunk, then emit and verify
-    bool strict = true;
-    {
+    if (s.strictFastq) {
+        // strict 4-line records start at lines 0, 4, 8, ...: count newlines per chunk, then emit and verify
         std::vector<uint64_t> nl(T + 1, 0);
         auto count = [&](unsigned t) {
             if (t >= T) return;
-            size_t c0, c1; chunkOf(n, t, T, c0, c1);
+            size_t c0, c1; chunk(t, c0, c1);
             uint64_t k = 0;
             const char* p = d + c0; const char* e = d + c1;
             while (p < e) { const char* q = (const char*)memchr(p, '\n', (size_t)(e - p)); if (!q) break; k++; p = q + 1; }
             nl[t + 1] = k;
         };
         if (T == 1) count(0); else pool.run(count);
+        nl[0] = s.lineCarry;
         for (unsigned t = 0; t < T; t++) nl[t + 1] += nl[t];
         std::vector<uint8_t> bad(T, 0);
         auto emit = [&](unsigned t) {
             if (t >= T) return;
-            size_t c0, c1; chunkOf(n, t, T, c0, c1);
+            size_t c0, c1; chunk(t, c0, c1);
             std::vector<uint64_t>& v = part[t];
-            uint64_t line = nl[t];          // index of the line that starts after the first newline at or after c0 ...
+            uint64_t line = nl[t];          // the line that starts after the next newline at or after c0 has index line + 1
             const char* p = d + c0; const char* e = d + c1;
             if (c0 == 0) { if (n > 0) { if (d[0] == '@') v.push_back(0); else bad[t] = 1; } }
             while (p < e) {
                 const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
                 if (!q) break;
-                line++;                     // ... line 'line' starts at q + 1
+                line++;
                 const size_t st = (size_t)(q - d) + 1;
                 if ((line & 3) == 0 && st < n) {
                     if (d[st] == '@') v.push_back(st);
@@ -157,16 +162,21 @@ bool ht2_source_index(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, std::st
             }
         };
         if (T == 1) emit(0); else pool.run(emit);
-        for (unsigned t = 0; t < T; t++) if (bad[t]) strict = false;
+        bool ok = true;
+        for (unsigned t = 0; t < T; t++) if (bad[t]) ok = false;
+        if (ok) {
+            for (auto& v : part) s.rec.insert(s.rec.end(), v.begin(), v.end());
+            s.lineCarry = nl[T];
+            return finish();
+        }
+        s.strictFastq = false;   // blank lines between records: fall through to the sequential scan of the rest
     }
-    if (strict) {
-        size_t tot = 0; for (auto& v : part) tot += v.size();
-        s.rec.reserve(tot + 1);
-        for (auto& v : part) s.rec.insert(s.rec.end(), v.begin(), v.end());
-    } else {
-        // blank lines between records (FastqPatternSource skips them): one sequential pass
-        size_t p = 0;
+    {
+        // blank lines between records (FastqPatternSource skips them): one sequential pass over the rest, from the
+        // end of the last complete record
+        size_t p = s.rec.empty() ? 0 : (size_t)s.rec.back();
         auto skipLine = [&]() { while (p < n && d[p] != '\n') p++; if (p < n) p++; };
+        if (!s.rec.empty()) { skipLine(); skipLine(); skipLine(); skipLine(); }
         while (p < n) {
             while (p < n && (d[p] == '\n' || d[p] == '\r')) p++;
             if (p >= n) break;
@@ -174,8 +184,15 @@ bool ht2_source_index(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, std::st
             s.rec.push_back(p);
             skipLine(); skipLine(); skipLine(); skipLine();
         }
+        s.scanPos = n; s.rec.push_back(n); s.scanDone = true;
+        return true;
     }
-    s.rec.push_back(n);
+}
+
+bool ht2_source_index(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, std::string& err)
+{
+    s.rec.clear(); s.scanPos = 0; s.scanDone = false; s.lineCarry = 0; s.strictFastq = true;
+    while (!s.scanDone) if (!ht2_source_scan(s, fastq, pool, 0, err)) return false;
     return true;
 }
 

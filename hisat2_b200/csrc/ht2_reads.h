@@ -48,14 +48,21 @@ struct Ht2ReadSource {          // one input file (or memory range) and its reco
     void*       map;            // mmap base (NULL when not mapped)
     size_t      mapLen;
     std::vector<char> own;      // slurped input (stdin)
-    std::vector<uint64_t> rec;  // offsets of the record starts, plus a final sentinel == size
-    Ht2ReadSource() : data(NULL), size(0), map(NULL), mapLen(0) {}
+    std::vector<uint64_t> rec;  // offsets of the record starts found so far; a final sentinel == size once scanDone
+    size_t      scanPos;        // incremental index: bytes scanned so far
+    bool        scanDone;
+    uint64_t    lineCarry;      // FASTQ: newlines before scanPos
+    bool        strictFastq;    // FASTQ: still in the 4-lines-per-record fast path
+    Ht2ReadSource() : data(NULL), size(0), map(NULL), mapLen(0), scanPos(0), scanDone(false), lineCarry(0), strictFastq(true) {}
+    // records whose END is known: record k spans [rec[k], rec[k+1])
     uint64_t nRecords() const { return rec.empty() ? 0 : rec.size() - 1; }
 };
 
 bool ht2_source_open(Ht2ReadSource& s, const char* path, std::string& err);        // "-" = stdin
 void ht2_source_memory(Ht2ReadSource& s, const char* data, size_t n);
-bool ht2_source_index(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, std::string& err);
+bool ht2_source_index(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, std::string& err);   // the whole input
+// the next blockBytes (0 = the rest) of the input; appends to s.rec, sets s.scanDone at the end
+bool ht2_source_scan(Ht2ReadSource& s, bool fastq, Ht2ThreadPool& pool, size_t blockBytes, std::string& err);
 void ht2_source_close(Ht2ReadSource& s);
 
 struct Ht2ReadsOpts {

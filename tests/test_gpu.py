@@ -42,6 +42,15 @@ def chr22(h2):
     idx.close()
 
 
+def n_batches(units, batch_reads, paired=False):
+    """Batches ht2gpu_run_reads cuts `units` reads (pairs) into: the first batch is a quarter of the others."""
+    per = batch_reads if batch_reads else 4000000
+    if paired:
+        per = (per + 1) // 2
+    first = per // 4 if per >= 8 else per
+    return 1 if units <= first else 1 + -(-(units - first) // per)
+
+
 def gpu_sam(idx, batch):
     """Header + SAM records of a batch.  The records are formatted ON THE DEVICE (ht2gpu_align_sam: the alignment
     kernel followed by the SAM kernels, csrc/ht2_sam.h) and must equal, byte for byte, what the host formatter
@@ -165,7 +174,7 @@ def test_pipeline_reads_in_sam_out_matches_golden(h2, tiny):
         sam, st = tiny.run_reads(path1=g("tiny_se.fa"), batch_reads=batch_reads)
         assert sam_lines(hdr + sam) == want, batch_reads
         assert st["n_reads"] == 700 and st["n_err_reads"] == 0 and st["sam_bytes"] == len(sam)
-        assert st["n_batches"] == (1 if batch_reads == 0 else -(-700 // batch_reads))
+        assert st["n_batches"] == n_batches(700, batch_reads)
     sam, st = tiny.run_reads(data1=open(g("tiny_se.fq"), "rb").read(), fastq=True, batch_reads=100, threads=3)
     assert sam_lines(hdr + sam) == sam_lines(open(g("tiny_se_fq.sam"), "rb").read())
     sam, st = tiny.run_reads(path1=g("tiny_pe_1.fq"), path2=g("tiny_pe_2.fq"), fastq=True, batch_reads=90)
@@ -189,7 +198,7 @@ def test_pipeline_reads_in_sam_out_matches_golden(h2, tiny):
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
 def test_pipeline_and_cli_match_reference_binary_at_scale(h2, chr22, tmp_path):
-    """200k pairs of the chr22 set through ht2gpu_run_reads (50k-read batches: eight batches over three slots)
+    """200k pairs of the chr22 set through ht2gpu_run_reads (50k-read batches: nine batches over three slots)
     and through the hisat2-b200 command line: both byte-identical to the reference binary run here."""
     f1, f2 = os.path.join(DATA, "sim200k_1.fa"), os.path.join(DATA, "sim200k_2.fa")
     if not os.path.exists(f1):
@@ -200,7 +209,7 @@ def test_pipeline_and_cli_match_reference_binary_at_scale(h2, chr22, tmp_path):
                     "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
     want = sam_lines(open(out, "rb").read())
     sam, st = chr22.run_reads(path1=f1, path2=f2, batch_reads=50000)
-    assert st["n_batches"] == 8 and st["n_err_reads"] == 0
+    assert st["n_batches"] == n_batches(200000, 50000, paired=True) and st["n_err_reads"] == 0
     assert sam_lines(chr22.sam_header() + sam) == want
     cli = os.path.join(ROOT, "hisat2_b200", "hisat2-b200")
     out2 = str(tmp_path / "cli.sam")
@@ -505,7 +514,7 @@ def test_two_devices_one_process_equal_one_device(h2, tmp_path):
     one, _ = a.run_reads(path1=f1, path2=f2, batch_reads=40000)
     b = a.peer(1)
     two, st = a.run_reads(path1=f1, path2=f2, batch_reads=40000, peers=[b])
-    assert st["n_batches"] == 10 and two == one
+    assert st["n_batches"] == n_batches(200000, 40000, paired=True) and two == one
     b.close(); a.close()
     cli = os.path.join(ROOT, "hisat2_b200", "hisat2-b200")
     out = str(tmp_path / "cli2.sam")
