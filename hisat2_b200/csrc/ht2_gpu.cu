@@ -52,6 +52,25 @@ struct DevOut {
     unsigned long long*   stats;    // optional (HT2GPU_STATS=1): per state code [rounds, lanes, cycles, max cycles]
 };
 
+// Four bytes starting at any byte address, from two aligned 32-bit loads (the batch buffers have 8 bytes of slack).
+__device__ __forceinline__ uint32_t ht2_ld4(const uint8_t* p)
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t lo = w[0];
+    return sh ? __funnelshift_r(lo, w[1], sh) : lo;
+}
+// complement of four base codes 0..4 (N stays N)
+__device__ __forceinline__ uint32_t ht2_comp4(uint32_t x)
+{
+    const uint32_t n4 = x & 0x04040404u;
+    return ((x ^ 0x03030303u) & ~(n4 | (n4 >> 1) | (n4 >> 2))) | n4;
+}
+
+// Read i of the batch into the workspace: forward and reverse-complement bases, forward and reversed qualities
+// (Read::finalize, read.h:84-92).  Word-wise: one lane loads a whole read, so byte accesses (404 byte stores and
+// 202 byte loads per 101-bp read) made this the most expensive glue state of the kernel.
 __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, uint32_t ri, uint32_t& err)
 {
     uint64_t o0 = b.offs[ri], o1 = b.offs[ri + 1];
@@ -60,13 +79,22 @@ __device__ __forceinline__ void ht2_load_read(Ht2Read& dst, const DevBatch& b, u
     dst.len = n;
     const uint8_t* s = b.seq + o0;
     const uint8_t* q = b.qual ? b.qual + o0 : NULL;
-    for (uint32_t i = 0; i < n; i++) {
-        uint8_t c = s[i];
-        dst.seq[0][i] = c;
-        dst.seq[1][n - i - 1] = c < 4 ? (uint8_t)(c ^ 3) : (uint8_t)4;
-        uint8_t qq = q ? q[i] : (uint8_t)'I';
-        dst.qual[0][i] = qq;
-        dst.qual[1][n - i - 1] = qq;
+    uint32_t* f0 = (uint32_t*)dst.seq[0]; uint32_t* f1 = (uint32_t*)dst.seq[1];
+    uint32_t* q0 = (uint32_t*)dst.qual[0]; uint32_t* q1 = (uint32_t*)dst.qual[1];
+    for (uint32_t k = 0; k < n; k += 4) {                     // forward strand: words straight through
+        f0[k >> 2] = ht2_ld4(s + k);
+        q0[k >> 2] = q ? ht2_ld4(q + k) : 0x49494949u;
+    }
+    uint32_t m = 0;
+    for (; m + 4 <= n; m += 4) {                              // reverse strand: bytes [n-4-m, n-m) reversed
+        const uint32_t x = __byte_perm(ht2_ld4(s + (n - 4 - m)), 0, 0x0123);
+        f1[m >> 2] = ht2_comp4(x);
+        q1[m >> 2] = q ? __byte_perm(ht2_ld4(q + (n - 4 - m)), 0, 0x0123) : 0x49494949u;
+    }
+    for (; m < n; m++) {                                      // the last 1-3 positions = the read's first bases
+        const uint8_t c = s[n - 1 - m];
+        dst.seq[1][m] = c < 4 ? (uint8_t)(c ^ 3) : (uint8_t)4;
+        dst.qual[1][m] = q ? q[n - 1 - m] : (uint8_t)'I';
     }
 }
 
@@ -85,7 +113,11 @@ __device__ __forceinline__ bool ht2_dev_filter(const DevBatch& b, uint32_t ri, i
     const uint32_t maxns = (uint32_t)((double)0.0f + (double)0.15f * (double)len);   // nCeil = L,0,0.15 (aligner_seed_policy.cpp:293-296)
     const uint8_t* s = b.seq + o0;
     uint32_t ns = 0;
-    for (uint32_t k = 0; k < len; k++) ns += (s[k] == 4);
+    for (uint32_t k = 0; k < len; k += 4) {
+        uint32_t x = ht2_ld4(s + k);
+        if (k + 4 > len) x &= (1u << (8 * (len - k))) - 1u;
+        ns += (uint32_t)__popc(x & 0x04040404u);
+    }
     return ns <= maxns && len >= 2 && 0 >= m;
 }
 
