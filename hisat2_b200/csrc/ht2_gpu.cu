@@ -8,6 +8,7 @@
 //   ht2_sam_*_kernel      : the SAM back end on the device (ht2_sam.h): finishRead for every read of the batch.
 // Host code here only moves bytes and launches; it never aligns anything.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,6 +44,8 @@ struct DevBatch {
 };
 
 struct DevOut {
+    unsigned int*         tailFlag; // written (atomicMax, tailTag) once half of all slots have run dry: the next batch's kernel may start
+    unsigned int          tailTag, tailAt;
     ht2gpu_read_result_t* reads;
     ht2gpu_aln_t*         alns;
     ht2gpu_edit_t*        edits;
@@ -385,7 +388,11 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
                 nc = rg_code(W);
             }
             __threadfence_block();   // release
-            if (nc == RG_EXIT) atomicAdd(&sExit, 1);
+            if (nc == RG_EXIT) {
+                atomicAdd(&sExit, 1);
+                // this kernel is draining: when half of all slots of the grid have run dry, let the next batch's kernel in
+                if (atomicAdd(&o.counters[5], 1u) + 1u == o.tailAt) { __threadfence(); atomicMax(o.tailFlag, o.tailTag); }
+            }
             else { atomicOr(&sBits[nc][my >> 5], 1u << (my & 31)); atomicAdd(&sCount[nc], 1); }
         }
         __syncwarp();
@@ -562,7 +569,7 @@ ht2_sam_scan_kernel(unsigned long long* blk, uint32_t nBlk)
 // One in-flight batch of the SAM path (ht2gpu_submit_sam / ht2gpu_wait_sam): its own stream, device input
 // buffers, device result pools, device SAM text and pinned host output, so that the H2D copy of batch i+1 and
 // the D2H copy of batch i-1 overlap the kernels of batch i.  The alignment workspaces (dWork) are shared by all
-// slots: kernels of different slots are chained through ht2gpu_handle::evCompute.
+// slots: kernels of different slots are chained through the device's WorkPool.
 #define HT2GPU_N_SLOTS 3
 struct SamSlot {
     bool         init;
@@ -582,7 +589,49 @@ struct SamSlot {
     bool pending;
 };
 
+// Alignment workspaces are a property of the DEVICE, not of an index handle: every handle of the process that runs
+// the same launch geometry on a device shares one WorkPool (a test process opens a dozen handles; 38 GB each would
+// not fit).  A pool holds TWO workspaces: consecutive kernels alternate between them, and kernel j+1 is released
+// when kernel j has started to drain (stream wait on kernel j's tail flag, cuStreamWaitValue32), so that the slow
+// end of a batch -- few slots left, most lanes idle -- overlaps the full-speed start of the next batch.
+struct WorkPool {
+    int            device;
+    size_t         nWork;
+    Ht2Work*       dWork[2];
+    cudaEvent_t    evDone[2];     // recorded after the latest alignment kernel that used workspace w
+    unsigned int*  dFlags;        // [0] / [1]: tag of the latest kernel on workspace w that reached its tail
+    Ht2SwScratch*  dSw[2];        // --bowtie2-dp scratch per launched thread (allocated on first use)
+    uint32_t*      dSwPool[2];
+    size_t         swThreads;
+    unsigned int   seq;           // kernels enqueued so far
+    std::mutex     mu;            // [waits, launches, records] of one kernel are one critical section
+    int            refs;
+};
+static std::mutex gPoolMu;
+static std::vector<WorkPool*> gPools;
+
+// cuStreamWaitValue32 from the driver, if it can be had without linking libcuda (the library must load on machines
+// without a driver: image building, read parsing and the ht2.h calls are host-only)
+typedef int (*WaitValue32Fn)(void* stream, unsigned long long addr, unsigned int value, unsigned int flags);
+static WaitValue32Fn waitValue32()
+{
+    static WaitValue32Fn fn = NULL;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        if (!getenv("HT2GPU_NO_TAIL_OVERLAP")) {
+            void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+            if (lib) {
+                fn = (WaitValue32Fn)dlsym(lib, "cuStreamWaitValue32_v2");
+                if (!fn) fn = (WaitValue32Fn)dlsym(lib, "cuStreamWaitValue32");
+            }
+        }
+    }
+    return fn;
+}
+
 struct ht2gpu_handle {
+    WorkPool*      pool;
     Ht2Image*      img;        // host copy (may hold only the header prefix when adopting a device image)
     uint8_t*       dBlob;
     bool           ownBlob;
@@ -595,16 +644,11 @@ struct ht2gpu_handle {
     bool           graph;
     int            poolWarps;
     int            rgK;
-    Ht2Work*       dWork;
     int32_t*       dMinsc;   // --score-min table on the device (Ht2Params::minscTab)
     void*          dSplT;    // spliced builds: Ht2SplTables on the device
-    Ht2SwScratch*  dSw;      // --bowtie2-dp: one scratch per launched thread
-    uint32_t*      dSwPool;  //               and the interleaved score-plane pool
     size_t         nWork;
     cudaStream_t   stream;
     cudaEvent_t    ev[4];
-    cudaEvent_t    evCompute;      // recorded after the last kernel that uses dWork / dSw
-    std::mutex     launchMu;       // [wait evCompute, launches, record evCompute] is one critical section
     std::string    err;
     unsigned long long* dStats;   // HT2GPU_STATS=1: per-state round statistics of the pool kernel
     SamSlot        slots[HT2GPU_N_SLOTS];
@@ -711,12 +755,35 @@ static int finishOpen(ht2gpu_handle* h)
     h->nWork = (size_t)h->nSM * h->bpsm * h->poolWarps * 32 * h->rgK;
     CK(cudaMalloc(&h->dMinsc, sizeof(h->P.minscTab)));
     CK(cudaMemcpy(h->dMinsc, h->P.minscTab, sizeof(h->P.minscTab), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&h->dWork, h->nWork * sizeof(Ht2Work)));
-    CK(cudaMemset(h->dWork, 0, h->nWork * sizeof(Ht2Work)));
-    if (h->P.bowtie2Dp) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
-        size_t nThreads = (size_t)h->nSM * h->bpsm * (size_t)h->tpb;
-        CK(cudaMalloc(&h->dSw, nThreads * sizeof(Ht2SwScratch)));
-        CK(cudaMalloc(&h->dSwPool, nThreads * (size_t)HT2_SW_POOL_WORDS * sizeof(uint32_t)));
+    {   // the device's workspace pool for this launch geometry
+        std::lock_guard<std::mutex> lk(gPoolMu);
+        WorkPool* wp = NULL;
+        for (WorkPool* q : gPools) if (q->device == h->device && q->nWork == h->nWork) wp = q;
+        if (!wp) {
+            wp = new WorkPool();
+            wp->device = h->device; wp->nWork = h->nWork; wp->seq = 0; wp->refs = 0; wp->swThreads = 0;
+            wp->dWork[0] = wp->dWork[1] = NULL; wp->dSw[0] = wp->dSw[1] = NULL; wp->dSwPool[0] = wp->dSwPool[1] = NULL; wp->dFlags = NULL;
+            for (int w = 0; w < 2; w++) {
+                CK(cudaMalloc(&wp->dWork[w], wp->nWork * sizeof(Ht2Work)));
+                CK(cudaMemset(wp->dWork[w], 0, wp->nWork * sizeof(Ht2Work)));
+                CK(cudaEventCreateWithFlags(&wp->evDone[w], cudaEventDisableTiming));
+                CK(cudaEventRecord(wp->evDone[w], 0));
+            }
+            CK(cudaMalloc(&wp->dFlags, 2 * sizeof(unsigned int)));
+            CK(cudaMemset(wp->dFlags, 0, 2 * sizeof(unsigned int)));
+            CK(cudaDeviceSynchronize());
+            gPools.push_back(wp);
+        }
+        if (h->P.bowtie2Dp && !wp->dSw[0]) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
+            const size_t nThreads = (size_t)h->nSM * h->bpsm * (size_t)h->tpb;
+            for (int w = 0; w < 2; w++) {
+                CK(cudaMalloc(&wp->dSw[w], nThreads * sizeof(Ht2SwScratch)));
+                CK(cudaMalloc(&wp->dSwPool[w], nThreads * (size_t)HT2_SW_POOL_WORDS * sizeof(uint32_t)));
+            }
+            wp->swThreads = nThreads;
+        }
+        wp->refs++;
+        h->pool = wp;
     }
     {   // per-thread stack: what the kernels of this index type need, not a blanket value (the limit is
         // context-wide and the driver backs it for every resident thread).  Linear indexes have a statically
@@ -733,16 +800,14 @@ static int finishOpen(ht2gpu_handle* h)
     }
     CK(cudaStreamCreate(&h->stream));
     for (int i = 0; i < 4; i++) CK(cudaEventCreate(&h->ev[i]));
-    CK(cudaEventCreateWithFlags(&h->evCompute, cudaEventDisableTiming));
-    CK(cudaEventRecord(h->evCompute, h->stream));
     return HT2GPU_OK;
 }
 
 static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
-    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->dWork = NULL; h->nWork = 0; h->dSw = NULL; h->dSwPool = NULL; h->dMinsc = NULL; h->dSplT = NULL;
-    h->stream = 0; h->evCompute = 0;
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->pool = NULL; h->nWork = 0; h->dMinsc = NULL; h->dSplT = NULL;
+    h->stream = 0;
     h->dStats = NULL;
     memset((void*)h->slots, 0, sizeof(h->slots));
     h->pipeCtx = NULL; h->pipeCtxFree = NULL;
@@ -864,9 +929,19 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     if (!h) return HT2GPU_OK;
     if (h->pipeCtx && h->pipeCtxFree) h->pipeCtxFree(h->pipeCtx);
     if (h->dBlob && h->ownBlob) cudaFree(h->dBlob);
-    if (h->dWork) cudaFree(h->dWork);
-    if (h->dSw) cudaFree(h->dSw);
-    if (h->dSwPool) cudaFree(h->dSwPool);
+    if (h->pool) {   // the last handle of a pool frees the workspaces
+        std::lock_guard<std::mutex> lk(gPoolMu);
+        WorkPool* wp = h->pool;
+        if (--wp->refs == 0) {
+            cudaSetDevice(wp->device);
+            cudaDeviceSynchronize();
+            for (int w = 0; w < 2; w++) { cudaFree(wp->dWork[w]); cudaFree(wp->dSw[w]); cudaFree(wp->dSwPool[w]); cudaEventDestroy(wp->evDone[w]); }
+            cudaFree(wp->dFlags);
+            for (size_t i = 0; i < gPools.size(); i++) if (gPools[i] == wp) { gPools.erase(gPools.begin() + i); break; }
+            delete wp;
+        }
+        h->pool = NULL;
+    }
     if (h->dMinsc) cudaFree(h->dMinsc);
     if (h->dSplT) cudaFree(h->dSplT);
     cudaFree(h->dStats);
@@ -882,7 +957,6 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
         cudaStreamDestroy(S.stream);
         for (int i = 0; i < 6; i++) cudaEventDestroy(S.ev[i]);
     }
-    if (h->evCompute) cudaEventDestroy(h->evCompute);
     if (h->stream) { cudaStreamDestroy(h->stream); for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]); }
     delete h->img;
     delete h;
@@ -961,38 +1035,53 @@ static int ensureOut(ht2gpu_handle* h, SamSlot& S, uint32_t units, size_t alns, 
     return HT2GPU_OK;
 }
 
-// Enqueue the alignment kernel of the slot's batch on the slot's stream.  The caller holds h->launchMu and has
-// made the stream wait for h->evCompute (the workspaces are shared by all slots).
-static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* b, uint32_t units)
+// Enqueue the alignment kernel of the slot's batch on the slot's stream, on the pool's next workspace: wait until
+// that workspace is free (the kernel before the previous one has finished), wait until the previous kernel -- on the
+// other workspace -- has started to drain (tail flag; exclusive = true waits for its end instead: launches that
+// share output buffers), launch, record.  One critical section per kernel.
+static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* b, uint32_t units, bool exclusive, cudaEvent_t evStart = NULL)
 {
+    WorkPool* wp = h->pool;
+    std::lock_guard<std::mutex> lk(wp->mu);
+    const unsigned int seq = wp->seq++;
+    const int w = (int)(seq & 1u);
+    CK(cudaStreamWaitEvent(S.stream, wp->evDone[w], 0));
+    WaitValue32Fn wait32 = exclusive ? NULL : waitValue32();
+    bool gated = false;
+    if (wait32 && seq > 0) gated = wait32((void*)S.stream, (unsigned long long)(uintptr_t)(wp->dFlags + (1 - w)), seq, 0 /* GEQ */) == 0;   // kernel seq-1 wrote tag seq
+    if (!gated) CK(cudaStreamWaitEvent(S.stream, wp->evDone[1 - w], 0));
     DevBatch db;
     db.seq = S.dSeq; db.qual = b->qual ? S.dQual : NULL; db.offs = S.dOffs; db.seeds = S.dSeeds;
-    db.n_units = units; db.paired = b->paired; db.sw = h->dSw; db.swPool = h->dSwPool; db.minscTab = h->dMinsc;
+    db.n_units = units; db.paired = b->paired; db.sw = h->P.bowtie2Dp ? wp->dSw[w] : NULL; db.swPool = h->P.bowtie2Dp ? wp->dSwPool[w] : NULL; db.minscTab = h->dMinsc;
 #ifdef HT2_ENABLE_SPLICED
     db.splT = (const Ht2SplTables*)h->dSplT;
 #endif
     DevOut o;
+    o.tailFlag = wp->dFlags + w; o.tailTag = seq + 1; o.tailAt = (unsigned int)(wp->nWork / 2 > 0 ? wp->nWork / 2 : 1);
     o.reads = S.dReads; o.alns = S.dAlns; o.edits = S.dEdits; o.pairs = S.dPairs;
     o.capAlns = (uint32_t)S.capAlns; o.capEdits = (uint32_t)S.capEdits; o.capPairs = (uint32_t)S.capPairs;
     o.counters = S.dCounters;
     o.stats = h->dStats;
     CK(cudaMemsetAsync(S.dCounters, 0, 8 * sizeof(unsigned int), S.stream));
+    if (evStart) CK(cudaEventRecord(evStart, S.stream));   // kernel time is counted from here: after the waits for the previous kernels
+    Ht2Work* work = wp->dWork[w];
     const uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
     const bool nospl = h->P.noSplicedAlignment != 0;   // the DNA-only instantiation has less code
     if (h->graph) {
-        if (nospl) ht2_align_pool_kernel<8, 4, true, true><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
-        else ht2_align_pool_kernel<8, 4, true, false><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
+        if (nospl) ht2_align_pool_kernel<8, 4, true, true><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, work);
+        else ht2_align_pool_kernel<8, 4, true, false><<<grid, 256, 0, S.stream>>>(h->dBlob, h->P, db, o, work);
     } else {
         switch (h->poolWarps * 100 + h->rgK) {
-            case 802:  ht2_align_pool_kernel<8, 2, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
-            case 408:  ht2_align_pool_kernel<4, 8, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork); break;
+            case 802:  ht2_align_pool_kernel<8, 2, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, work); break;
+            case 408:  ht2_align_pool_kernel<4, 8, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, work); break;
             default:
-                if (nospl) ht2_align_pool_kernel<8, 4, false, true><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
-                else ht2_align_pool_kernel<8, 4, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, h->dWork);
+                if (nospl) ht2_align_pool_kernel<8, 4, false, true><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, work);
+                else ht2_align_pool_kernel<8, 4, false, false><<<grid, h->tpb, 0, S.stream>>>(h->dBlob, h->P, db, o, work);
                 break;
         }
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(wp->evDone[w], S.stream));
     return HT2GPU_OK;
 }
 
@@ -1064,14 +1153,8 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
     for (int attempt = 0; attempt < 4; attempt++) {
         rc = ensureOut(h, S, units, capA, capE, capP);
         if (rc) return rc;
-        {
-            std::lock_guard<std::mutex> lk(h->launchMu);
-            CK(cudaStreamWaitEvent(S.stream, h->evCompute, 0));
-            CK(cudaEventRecord(S.ev[1], S.stream));
-            for (int it = 0; it < iters; it++) { rc = launchAlign(h, S, b, units); if (rc) return rc; nLaunch++; }
-            CK(cudaEventRecord(S.ev[2], S.stream));
-            CK(cudaEventRecord(h->evCompute, S.stream));
-        }
+        for (int it = 0; it < iters; it++) { rc = launchAlign(h, S, b, units, true, it == 0 ? S.ev[1] : NULL); if (rc) return rc; nLaunch++; }   // the launches share this slot's result pools
+        CK(cudaEventRecord(S.ev[2], S.stream));
         CK(cudaMemcpyAsync(counters, S.dCounters, sizeof(counters), cudaMemcpyDeviceToHost, S.stream));
         CK(cudaStreamSynchronize(S.stream));
         CK(cudaEventElapsedTime(&msKernel, S.ev[1], S.ev[2]));
@@ -1156,10 +1239,8 @@ static int enqueueKernels(ht2gpu_handle* h, SamSlot& S, bool withAlign)
     const uint32_t nBlk = (units + HT2_SAM_TPB - 1) / HT2_SAM_TPB;
     CK(growBuf(S.dSamLen, S.capSamLen, units));
     CK(growBuf(S.dBlk, S.capBlk, (size_t)nBlk + 2));
-    std::lock_guard<std::mutex> lk(h->launchMu);
-    CK(cudaStreamWaitEvent(S.stream, h->evCompute, 0));
-    CK(cudaEventRecord(S.ev[2], S.stream));
-    if (withAlign) { int rc = launchAlign(h, S, &S.batch, units); if (rc) return rc; S.nLaunch++; }
+    if (withAlign) { int rc = launchAlign(h, S, &S.batch, units, false, S.ev[2]); if (rc) return rc; S.nLaunch++; }
+    else CK(cudaEventRecord(S.ev[2], S.stream));
     CK(cudaEventRecord(S.ev[3], S.stream));
     const Ht2SamIn in = samIn(h, S);
     ht2_sam_kernel<false><<<nBlk, HT2_SAM_TPB, 0, S.stream>>>(in, units, S.dSamLen, S.dBlk, NULL, 0, S.dCounters);
@@ -1168,7 +1249,6 @@ static int enqueueKernels(ht2gpu_handle* h, SamSlot& S, bool withAlign)
     CK(cudaGetLastError());
     S.nLaunch += 3;
     CK(cudaEventRecord(S.ev[4], S.stream));
-    CK(cudaEventRecord(h->evCompute, S.stream));
     // meta: total SAM bytes, result counters, reads with errors
     CK(cudaMemcpyAsync(&S.hMeta[0], S.dBlk + nBlk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, S.stream));
     CK(cudaMemcpyAsync(&S.hMeta[1], S.dCounters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
