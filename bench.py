@@ -40,6 +40,13 @@ DIGITS = 8
 RECSZ = 2 + DIGITS + 1 + RDLEN + 1
 WORKLOAD = ("BASELINE configs[2]: 22_20-21M linear index, fixed set of %d synthetic 2x101bp pairs (seed 1, --fr, -I 0 -X 1000), "
             "--no-spliced-alignment -k 5, sharded over the ranks by contiguous pair ranges")
+L2_NOTE = ("inputs larger than L2: every step streams the whole read set (110 B of FASTA per read in, ~360 B of SAM per read out) through "
+           "the device; the 7 MB index image is L2-resident by construction (SURVEY 0.4); no flush between steps")
+
+
+def workload_config(pairs):
+    """The `config` object, identical for both arms."""
+    return {"workload": WORKLOAD % pairs, "read_len": RDLEN, "pairs_total": pairs, "l2": L2_NOTE}
 
 
 def huge_buffer(nbytes):
@@ -174,7 +181,7 @@ def reference_arm(args, rank):
     line = {"impl": "reference", "metric": "reads_per_sec_aligned", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % args.pairs, "read_len": RDLEN},
+            "config": workload_config(args.pairs),
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "reference",
                              "sample": "first %d pairs (%d reads) of the workload per step, hisat2-align-s -p %d --reorder (fastest of the -p table, "
                                        "measured on this full sample), wall clock incl. index load, FASTA parsing and SAM to /dev/null" % (npairs, nreads, threads),
@@ -338,13 +345,12 @@ def main():
         "metric": "reads_per_sec_aligned", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % args.pairs, "read_len": RDLEN, "pairs_total": args.pairs, "reads_per_step_all_ranks": int(total_reads),
-                   "device_batch_reads": args.batch_reads, "host_parser_threads_per_rank": threads,
-                   "parallelism": "contiguous pair ranges x%d, index replicated (NCCL broadcast at load), no data-path collective; "
-                                  "SAM stays in rank order in host memory" % world,
-                   "l2": "inputs larger than L2: every step streams %.0f MB of read batches and %.0f MB of SAM text per rank; the 6.9 MB index image "
-                         "is L2-resident by construction (SURVEY 0.4); no flush between steps" % (n_reads * 110 / 1e6, float(tot[5]) / world / args.steps / 1e6),
-                   "aligned_fraction": aligned, "lf_steps_per_read": lf_per_read, "capacity_error_reads": int(tot[2])},
+        "config": workload_config(args.pairs),
+        "run": {"reads_per_step_all_ranks": int(total_reads), "device_batch_reads": args.batch_reads, "host_parser_threads_per_rank": threads,
+                "parallelism": "contiguous pair ranges x%d, index replicated (NCCL broadcast at load), no data-path collective; "
+                               "SAM stays in rank order in host memory" % world,
+                "sam_MB_per_step_per_rank": float(tot[5]) / world / args.steps / 1e6,
+                "aligned_fraction": aligned, "lf_steps_per_read": lf_per_read, "capacity_error_reads": int(tot[2])},
         "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": int(tot[3] / args.steps), "d2h_bytes_per_step": int(tot[4] / args.steps),
                 "ms_per_step": e2e_ms / args.steps, "sam_bytes_per_step": int(tot[5] / args.steps),
                 "what": "ht2gpu_run_reads: FASTA text in host memory -> SAM text in (pinned) host memory; record indexing, multi-threaded parsing, "

@@ -8,7 +8,6 @@
 //   ht2_sam_*_kernel      : the SAM back end on the device (ht2_sam.h): finishRead for every read of the batch.
 // Host code here only moves bytes and launches; it never aligns anything.
 #include <cuda_runtime.h>
-#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -44,8 +43,6 @@ struct DevBatch {
 };
 
 struct DevOut {
-    unsigned int*         tailFlag; // written (atomicMax, tailTag) once half of all slots have run dry: the next batch's kernel may start
-    unsigned int          tailTag, tailAt;
     ht2gpu_read_result_t* reads;
     ht2gpu_aln_t*         alns;
     ht2gpu_edit_t*        edits;
@@ -388,11 +385,7 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
                 nc = rg_code(W);
             }
             __threadfence_block();   // release
-            if (nc == RG_EXIT) {
-                atomicAdd(&sExit, 1);
-                // this kernel is draining: when half of all slots of the grid have run dry, let the next batch's kernel in
-                if (atomicAdd(&o.counters[5], 1u) + 1u == o.tailAt) { __threadfence(); atomicMax(o.tailFlag, o.tailTag); }
-            }
+            if (nc == RG_EXIT) atomicAdd(&sExit, 1);
             else { atomicOr(&sBits[nc][my >> 5], 1u << (my & 31)); atomicAdd(&sCount[nc], 1); }
         }
         __syncwarp();
@@ -591,44 +584,21 @@ struct SamSlot {
 
 // Alignment workspaces are a property of the DEVICE, not of an index handle: every handle of the process that runs
 // the same launch geometry on a device shares one WorkPool (a test process opens a dozen handles; 38 GB each would
-// not fit).  A pool holds TWO workspaces: consecutive kernels alternate between them, and kernel j+1 is released
-// when kernel j has started to drain (stream wait on kernel j's tail flag, cuStreamWaitValue32), so that the slow
-// end of a batch -- few slots left, most lanes idle -- overlaps the full-speed start of the next batch.
+// not fit).  Kernels that use the workspace are chained through evDone.  (Round 2 also tried two workspaces with
+// the next batch's kernel released by the previous kernel's tail flag -- cuStreamWaitValue32 -- so that the drain
+// of one batch overlaps the start of the next: no gain; removed.)
 struct WorkPool {
     int            device;
     size_t         nWork;
-    Ht2Work*       dWork[2];
-    cudaEvent_t    evDone[2];     // recorded after the latest alignment kernel that used workspace w
-    unsigned int*  dFlags;        // [0] / [1]: tag of the latest kernel on workspace w that reached its tail
-    Ht2SwScratch*  dSw[2];        // --bowtie2-dp scratch per launched thread (allocated on first use)
-    uint32_t*      dSwPool[2];
-    size_t         swThreads;
-    unsigned int   seq;           // kernels enqueued so far
-    std::mutex     mu;            // [waits, launches, records] of one kernel are one critical section
+    Ht2Work*       dWork;
+    cudaEvent_t    evDone;        // recorded after the latest kernels of a batch (alignment + SAM)
+    Ht2SwScratch*  dSw;           // --bowtie2-dp scratch per launched thread (allocated on first use)
+    uint32_t*      dSwPool;
+    std::mutex     mu;            // [wait, launches, record] of one batch are one critical section
     int            refs;
 };
 static std::mutex gPoolMu;
 static std::vector<WorkPool*> gPools;
-
-// cuStreamWaitValue32 from the driver, if it can be had without linking libcuda (the library must load on machines
-// without a driver: image building, read parsing and the ht2.h calls are host-only)
-typedef int (*WaitValue32Fn)(void* stream, unsigned long long addr, unsigned int value, unsigned int flags);
-static WaitValue32Fn waitValue32()
-{
-    static WaitValue32Fn fn = NULL;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        if (!getenv("HT2GPU_NO_TAIL_OVERLAP")) {
-            void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-            if (lib) {
-                fn = (WaitValue32Fn)dlsym(lib, "cuStreamWaitValue32_v2");
-                if (!fn) fn = (WaitValue32Fn)dlsym(lib, "cuStreamWaitValue32");
-            }
-        }
-    }
-    return fn;
-}
 
 struct ht2gpu_handle {
     WorkPool*      pool;
@@ -761,26 +731,19 @@ static int finishOpen(ht2gpu_handle* h)
         for (WorkPool* q : gPools) if (q->device == h->device && q->nWork == h->nWork) wp = q;
         if (!wp) {
             wp = new WorkPool();
-            wp->device = h->device; wp->nWork = h->nWork; wp->seq = 0; wp->refs = 0; wp->swThreads = 0;
-            wp->dWork[0] = wp->dWork[1] = NULL; wp->dSw[0] = wp->dSw[1] = NULL; wp->dSwPool[0] = wp->dSwPool[1] = NULL; wp->dFlags = NULL;
-            for (int w = 0; w < 2; w++) {
-                CK(cudaMalloc(&wp->dWork[w], wp->nWork * sizeof(Ht2Work)));
-                CK(cudaMemset(wp->dWork[w], 0, wp->nWork * sizeof(Ht2Work)));
-                CK(cudaEventCreateWithFlags(&wp->evDone[w], cudaEventDisableTiming));
-                CK(cudaEventRecord(wp->evDone[w], 0));
-            }
-            CK(cudaMalloc(&wp->dFlags, 2 * sizeof(unsigned int)));
-            CK(cudaMemset(wp->dFlags, 0, 2 * sizeof(unsigned int)));
+            wp->device = h->device; wp->nWork = h->nWork; wp->refs = 0;
+            wp->dWork = NULL; wp->dSw = NULL; wp->dSwPool = NULL;
+            CK(cudaMalloc(&wp->dWork, wp->nWork * sizeof(Ht2Work)));
+            CK(cudaMemset(wp->dWork, 0, wp->nWork * sizeof(Ht2Work)));
+            CK(cudaEventCreateWithFlags(&wp->evDone, cudaEventDisableTiming));
+            CK(cudaEventRecord(wp->evDone, 0));
             CK(cudaDeviceSynchronize());
             gPools.push_back(wp);
         }
-        if (h->P.bowtie2Dp && !wp->dSw[0]) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
+        if (h->P.bowtie2Dp && !wp->dSw) {   // dynamic-programming scratch (ht2_sw.h): per executing thread, not per read slot
             const size_t nThreads = (size_t)h->nSM * h->bpsm * (size_t)h->tpb;
-            for (int w = 0; w < 2; w++) {
-                CK(cudaMalloc(&wp->dSw[w], nThreads * sizeof(Ht2SwScratch)));
-                CK(cudaMalloc(&wp->dSwPool[w], nThreads * (size_t)HT2_SW_POOL_WORDS * sizeof(uint32_t)));
-            }
-            wp->swThreads = nThreads;
+            CK(cudaMalloc(&wp->dSw, nThreads * sizeof(Ht2SwScratch)));
+            CK(cudaMalloc(&wp->dSwPool, nThreads * (size_t)HT2_SW_POOL_WORDS * sizeof(uint32_t)));
         }
         wp->refs++;
         h->pool = wp;
@@ -935,8 +898,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
         if (--wp->refs == 0) {
             cudaSetDevice(wp->device);
             cudaDeviceSynchronize();
-            for (int w = 0; w < 2; w++) { cudaFree(wp->dWork[w]); cudaFree(wp->dSw[w]); cudaFree(wp->dSwPool[w]); cudaEventDestroy(wp->evDone[w]); }
-            cudaFree(wp->dFlags);
+            cudaFree(wp->dWork); cudaFree(wp->dSw); cudaFree(wp->dSwPool); cudaEventDestroy(wp->evDone);
             for (size_t i = 0; i < gPools.size(); i++) if (gPools[i] == wp) { gPools.erase(gPools.begin() + i); break; }
             delete wp;
         }
@@ -1035,36 +997,25 @@ static int ensureOut(ht2gpu_handle* h, SamSlot& S, uint32_t units, size_t alns, 
     return HT2GPU_OK;
 }
 
-// Enqueue the alignment kernel of the slot's batch on the slot's stream, on the pool's next workspace: wait until
-// that workspace is free (the kernel before the previous one has finished), wait until the previous kernel -- on the
-// other workspace -- has started to drain (tail flag; exclusive = true waits for its end instead: launches that
-// share output buffers), launch, record.  One critical section per kernel.
-static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* b, uint32_t units, bool exclusive, cudaEvent_t evStart = NULL)
+// Enqueue the alignment kernel of the slot's batch on the slot's stream.  The caller holds the pool's mutex and has
+// made the stream wait for the pool's evDone (the workspaces are shared by every slot of every handle).
+static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* b, uint32_t units, cudaEvent_t evStart = NULL)
 {
     WorkPool* wp = h->pool;
-    std::lock_guard<std::mutex> lk(wp->mu);
-    const unsigned int seq = wp->seq++;
-    const int w = (int)(seq & 1u);
-    CK(cudaStreamWaitEvent(S.stream, wp->evDone[w], 0));
-    WaitValue32Fn wait32 = exclusive ? NULL : waitValue32();
-    bool gated = false;
-    if (wait32 && seq > 0) gated = wait32((void*)S.stream, (unsigned long long)(uintptr_t)(wp->dFlags + (1 - w)), seq, 0 /* GEQ */) == 0;   // kernel seq-1 wrote tag seq
-    if (!gated) CK(cudaStreamWaitEvent(S.stream, wp->evDone[1 - w], 0));
     DevBatch db;
     db.seq = S.dSeq; db.qual = b->qual ? S.dQual : NULL; db.offs = S.dOffs; db.seeds = S.dSeeds;
-    db.n_units = units; db.paired = b->paired; db.sw = h->P.bowtie2Dp ? wp->dSw[w] : NULL; db.swPool = h->P.bowtie2Dp ? wp->dSwPool[w] : NULL; db.minscTab = h->dMinsc;
+    db.n_units = units; db.paired = b->paired; db.sw = h->P.bowtie2Dp ? wp->dSw : NULL; db.swPool = h->P.bowtie2Dp ? wp->dSwPool : NULL; db.minscTab = h->dMinsc;
 #ifdef HT2_ENABLE_SPLICED
     db.splT = (const Ht2SplTables*)h->dSplT;
 #endif
     DevOut o;
-    o.tailFlag = wp->dFlags + w; o.tailTag = seq + 1; o.tailAt = (unsigned int)(wp->nWork / 2 > 0 ? wp->nWork / 2 : 1);
     o.reads = S.dReads; o.alns = S.dAlns; o.edits = S.dEdits; o.pairs = S.dPairs;
     o.capAlns = (uint32_t)S.capAlns; o.capEdits = (uint32_t)S.capEdits; o.capPairs = (uint32_t)S.capPairs;
     o.counters = S.dCounters;
     o.stats = h->dStats;
     CK(cudaMemsetAsync(S.dCounters, 0, 8 * sizeof(unsigned int), S.stream));
     if (evStart) CK(cudaEventRecord(evStart, S.stream));   // kernel time is counted from here: after the waits for the previous kernels
-    Ht2Work* work = wp->dWork[w];
+    Ht2Work* work = wp->dWork;
     const uint32_t grid = (uint32_t)(h->nSM * h->bpsm);
     const bool nospl = h->P.noSplicedAlignment != 0;   // the DNA-only instantiation has less code
     if (h->graph) {
@@ -1081,7 +1032,6 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
         }
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(wp->evDone[w], S.stream));
     return HT2GPU_OK;
 }
 
@@ -1153,8 +1103,13 @@ static int runBatch(ht2gpu_handle* h, const ht2gpu_read_batch_t* b, int iters, h
     for (int attempt = 0; attempt < 4; attempt++) {
         rc = ensureOut(h, S, units, capA, capE, capP);
         if (rc) return rc;
-        for (int it = 0; it < iters; it++) { rc = launchAlign(h, S, b, units, true, it == 0 ? S.ev[1] : NULL); if (rc) return rc; nLaunch++; }   // the launches share this slot's result pools
-        CK(cudaEventRecord(S.ev[2], S.stream));
+        {
+            std::lock_guard<std::mutex> lk(h->pool->mu);
+            CK(cudaStreamWaitEvent(S.stream, h->pool->evDone, 0));
+            for (int it = 0; it < iters; it++) { rc = launchAlign(h, S, b, units, it == 0 ? S.ev[1] : NULL); if (rc) return rc; nLaunch++; }
+            CK(cudaEventRecord(S.ev[2], S.stream));
+            CK(cudaEventRecord(h->pool->evDone, S.stream));
+        }
         CK(cudaMemcpyAsync(counters, S.dCounters, sizeof(counters), cudaMemcpyDeviceToHost, S.stream));
         CK(cudaStreamSynchronize(S.stream));
         CK(cudaEventElapsedTime(&msKernel, S.ev[1], S.ev[2]));
@@ -1239,7 +1194,9 @@ static int enqueueKernels(ht2gpu_handle* h, SamSlot& S, bool withAlign)
     const uint32_t nBlk = (units + HT2_SAM_TPB - 1) / HT2_SAM_TPB;
     CK(growBuf(S.dSamLen, S.capSamLen, units));
     CK(growBuf(S.dBlk, S.capBlk, (size_t)nBlk + 2));
-    if (withAlign) { int rc = launchAlign(h, S, &S.batch, units, false, S.ev[2]); if (rc) return rc; S.nLaunch++; }
+    std::lock_guard<std::mutex> lk(h->pool->mu);
+    CK(cudaStreamWaitEvent(S.stream, h->pool->evDone, 0));
+    if (withAlign) { int rc = launchAlign(h, S, &S.batch, units, S.ev[2]); if (rc) return rc; S.nLaunch++; }
     else CK(cudaEventRecord(S.ev[2], S.stream));
     CK(cudaEventRecord(S.ev[3], S.stream));
     const Ht2SamIn in = samIn(h, S);
@@ -1249,6 +1206,7 @@ static int enqueueKernels(ht2gpu_handle* h, SamSlot& S, bool withAlign)
     CK(cudaGetLastError());
     S.nLaunch += 3;
     CK(cudaEventRecord(S.ev[4], S.stream));
+    CK(cudaEventRecord(h->pool->evDone, S.stream));
     // meta: total SAM bytes, result counters, reads with errors
     CK(cudaMemcpyAsync(&S.hMeta[0], S.dBlk + nBlk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, S.stream));
     CK(cudaMemcpyAsync(&S.hMeta[1], S.dCounters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
