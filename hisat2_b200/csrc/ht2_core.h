@@ -21,14 +21,15 @@
 #include "ht2_params.h"
 
 #ifndef HT2_MAX_RDLEN
-#define HT2_MAX_RDLEN 256
+#define HT2_MAX_RDLEN 1024
 #endif
-#define HT2_MAX_EDITS 96   /* edits of one (trial) hit: a 250-bp read at --very-sensitive scores admits ~80 deleted bases */
-#define HT2_MAX_PHITS 64
+#define HT2_SW_MAX_RDLEN 256   /* --bowtie2-dp: the score planes are quadratic in the read length; longer reads skip the DP and are flagged */
+#define HT2_MAX_EDITS 128  /* edits of one (trial) hit: a 250-bp read at --very-sensitive scores admits ~80 deleted bases, a 1 000-base read ~100 mismatches */
+#define HT2_MAX_PHITS 160   /* partial searches per strand: a 1 000-base read makes ~70 */
 #ifndef HT2_MAX_GHITS
 #define HT2_MAX_GHITS 64   /* max(khits, kseeds) anchors: --very-sensitive runs -k 30, i.e. 60 seeds */
 #endif
-#define HT2_POOL 40
+#define HT2_POOL 64
 #define HT2_IE_POOL 96           /* in-edge entries per strand (graph indexes) */
 #define HT2_SEARCHED_BYTES 24576   /* ~600 searched hits (40 B typical) for both mates */
 
@@ -40,7 +41,7 @@
 #endif
 #define HT2_MAX_DEPTH 128
 #ifndef HT2_DEPTH_CAP
-#define HT2_DEPTH_CAP 32   /* recursion depth the workspace/stack is sized for */
+#define HT2_DEPTH_CAP 48   /* recursion depth the workspace/stack is sized for */
 #endif
 #ifndef HT2_REFBUF
 #define HT2_REFBUF (HT2_MAX_RDLEN + 128)   /* read + the read gaps minsc allows (combineWith window): 83 at minsc -256 with the default --rdg */
@@ -209,9 +210,9 @@ struct Ht2AltScratch {
 // problem starts and ends inside one state-machine segment), not per read slot,
 // and only allocated when --bowtie2-dp is on.
 #define HT2_SW_MAXGAP 10
-#define HT2_SW_MAXCOLS (HT2_MAX_RDLEN + 4 * HT2_SW_MAXGAP)
+#define HT2_SW_MAXCOLS (HT2_SW_MAX_RDLEN + 4 * HT2_SW_MAXGAP)
 #define HT2_SW_MAX_EDITS 160
-#define HT2_SW_SEG ((HT2_MAX_RDLEN + 1) / 2)     /* words per column: 2 rows (s16 halves) per 32-bit word */
+#define HT2_SW_SEG ((HT2_SW_MAX_RDLEN + 1) / 2)     /* words per column: 2 rows (s16 halves) per 32-bit word */
 // The three score matrices H, E, F (striped: row i = half i / seg of word i % seg; column-major; one spare column)
 // live OUTSIDE the scratch struct, in a plane pool addressed with a stride: word idx of plane p of a lane is
 // pool[(p * HT2_SW_PLANE_WORDS + idx) * stride + lane].  On the device stride = 32 and the 32 lanes of a warp
@@ -220,10 +221,10 @@ struct Ht2AltScratch {
 #define HT2_SW_PLANE_WORDS ((HT2_SW_MAXCOLS + 1) * HT2_SW_SEG)
 #define HT2_SW_POOL_WORDS (3 * HT2_SW_PLANE_WORDS + 7 * HT2_SW_SEG)   /* per lane: H, E, F + query profile (5) + gap barrier + barrier/read-gap-open words */
 struct Ht2SwScratch {
-    uint32_t rep[((size_t)HT2_SW_MAXCOLS * HT2_MAX_RDLEN + 31) / 32];   // reported-through bit per cell (col * nrow + row)
+    uint32_t rep[((size_t)HT2_SW_MAXCOLS * HT2_SW_MAX_RDLEN + 31) / 32];   // reported-through bit per cell (col * nrow + row)
     uint32_t nrow, seg;
     int32_t  lastH[HT2_SW_MAXCOLS];                          // last-row H per column (the candidates)
-    uint8_t  rowPen[HT2_MAX_RDLEN];                          // mismatch penalty of each read row
+    uint8_t  rowPen[HT2_SW_MAX_RDLEN];                          // mismatch penalty of each read row
     alignas(8) uint8_t rf[HT2_SW_MAXCOLS + 16];              // reference window, codes 0..4
     Ht2Edit  ned[HT2_SW_MAX_EDITS];
 };

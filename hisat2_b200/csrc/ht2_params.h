@@ -9,7 +9,7 @@
 
 #include <stdint.h>
 
-#define HT2_PARAMS_MAX_RDLEN 256
+#define HT2_PARAMS_MAX_RDLEN 1024
 
 // The part the kernels receive BY VALUE (kernel parameter space, read through the constant cache).
 struct Ht2ParamsCore {

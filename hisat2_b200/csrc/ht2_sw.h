@@ -355,7 +355,7 @@ HT2_NI bool swExtendAnchor(uint32_t rdi, Ht2Hit& gh) {
     SwRect rect;
     if (!swFrameRect((int64_t)refoff, rdlen, tlen, rect)) return false;
     const uint32_t ncol = (uint32_t)(rect.refr - rect.refl + 1);
-    if (ncol > HT2_SW_MAXCOLS) { W->err |= HT2_ERR_SW; return false; }
+    if (ncol > HT2_SW_MAXCOLS || rdlen > HT2_SW_MAX_RDLEN) { W->err |= HT2_ERR_SW; return false; }   // the score planes are sized for reads of up to 256 bases
     // reference window; positions past the end of the sequence read as N (aligner_sw.cpp:160-212)
     const uint8_t* rf = getStretch(S.rf, gh.tidx, (uint32_t)rect.refl, ncol);
     const int64_t msc = minsc[rdi];

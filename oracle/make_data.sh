@@ -28,6 +28,12 @@ for L in 36 150 250; do
     python ../tools/simreads.py $D/22_20-21M.fa 20000 $D/len${L} --seed $((70 + L)) --paired --indel 0.004 --nrate 0.002 --sub 0.01 --ragged --rdlen $L
   fi
 done
+# long reads (the capacity is 1 024 bases): 500 and 1000 bp, 3 000 pairs each
+for L in 500 1000; do
+  if [ ! -f $D/len${L}_1.fa ]; then
+    python ../tools/simreads.py $D/22_20-21M.fa 3000 $D/len${L} --seed $((70 + L)) --paired --indel 0.003 --nrate 0.002 --sub 0.01 --ragged --rdlen $L
+  fi
+done
 # reads carrying ALT alleles of the bundled SNP list (graph index 22_20-21M_snp)
 if [ ! -f $D/alt20k_1.fa ]; then
   python ../tools/altreads.py $D/22_20-21M.fa $D/22_20-21M.snp 20000 $D/alt20k --seed 9 --paired

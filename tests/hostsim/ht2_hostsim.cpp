@@ -212,7 +212,7 @@ static int swSelfTest(int n, unsigned seed) {
         P.mmpMax = 2 + rnd(6); P.mmpMin = 1 + rnd(P.mmpMax); P.npen = 1 + rnd(2); P.mmcostConstant = rnd(4) == 0;
         P.rdGapConst = 1 + rnd(8); P.rdGapLinear = 1 + rnd(4); P.rfGapConst = 1 + rnd(8); P.rfGapLinear = 1 + rnd(4);
         P.gapbar = 1 + rnd(12);
-        const uint32_t nrow = 20 + rnd(HT2_MAX_RDLEN - 20), ncol = nrow + 40;
+        const uint32_t nrow = 20 + rnd(HT2_SW_MAX_RDLEN - 20), ncol = nrow + 40;
         std::vector<uint8_t> ref(ncol + 8), rd, qu;
         for (auto& c : ref) c = rnd(50) == 0 ? 4 : rnd(4);
         for (uint32_t j = 20; rd.size() < nrow && j < ncol;) {   // the read: the window with substitutions and small indels

@@ -86,7 +86,7 @@ def test_tiny_pe_matches_golden_reference_sam(h2, tiny):
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
-@pytest.mark.parametrize("name", ["sim10k", "hard20k", "len36", "len150"])
+@pytest.mark.parametrize("name", ["sim10k", "hard20k", "len36", "len150", "len500"])
 def test_chr22_paired_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
     """BASELINE configs[2]-shaped input (2x101 bp pairs): SAM identical to the reference."""
     f1, f2 = os.path.join(DATA, name + "_1.fa"), os.path.join(DATA, name + "_2.fa")
@@ -402,15 +402,15 @@ def test_batch_composition_invariance_and_determinism(h2, tiny):
 
 
 def test_edge_cases(h2, tiny):
-    """empty batch, reads shorter than the ftab, all-N read, 1-base read, max-length read."""
+    """empty batch, reads shorter than the ftab, all-N read, 1-base read, max-length (1 024-base) read."""
     lib = h2.load_library()
     empty = h2.ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(0, np.uint32), [])
     r = tiny.align(empty)
     assert len(r.reads) == 0 and len(r.alns) == 0
     rng = np.random.default_rng(5)
     seqs = [np.array([0, 1, 2], np.uint8), np.full(60, 4, np.uint8), np.array([2], np.uint8),
-            rng.integers(0, 4, 256).astype(np.uint8), rng.integers(0, 4, 7).astype(np.uint8)]
-    names = [b"short3", b"allN", b"one", b"len256", b"short7"]
+            rng.integers(0, 4, 1024).astype(np.uint8), rng.integers(0, 4, 7).astype(np.uint8)]
+    names = [b"short3", b"allN", b"one", b"len1024", b"short7"]
     offs = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint64)
     seeds = np.array([lib.ht2gpu_read_seed(np.ascontiguousarray(s).ctypes.data, None, len(s), n, 0)
                       for s, n in zip(seqs, names)], dtype=np.uint32)
@@ -422,7 +422,7 @@ def test_edge_cases(h2, tiny):
     assert all(l.split("\t")[1] == "4" for l in sam)           # nothing aligns
     assert "YF:Z:NS" in sam[1] and "YF:Z:LN" in sam[2]           # N filter / length filter (hisat2.cpp:3417-3440)
     # over-long read: reported as a capacity error, never silently truncated
-    long_ = h2.ReadBatch(rng.integers(0, 4, 300).astype(np.uint8), np.array([0, 300], np.uint64), np.array([1], np.uint32), [b"len300"])
+    long_ = h2.ReadBatch(rng.integers(0, 4, 1100).astype(np.uint8), np.array([0, 1100], np.uint64), np.array([1], np.uint32), [b"len1100"])
     res = tiny.align(long_)                      # the call succeeds; the read is flagged and counted
     assert res.reads["err"][0] != 0 and res.n_err_reads == 1
     sam, st = tiny.align_sam(long_, with_stats=True)
@@ -430,7 +430,7 @@ def test_edge_cases(h2, tiny):
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
-@pytest.mark.parametrize("name", ["reads", "hard20k", "sim200k", "len36", "len150", "len250"])
+@pytest.mark.parametrize("name", ["reads", "hard20k", "sim200k", "len36", "len150", "len250", "len500", "len1000"])
 def test_chr22_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
     """BASELINE configs[0]/[1]-shaped inputs: SAM byte-identical to the unmodified
     reference run on this box (-p N --reorder)."""
@@ -446,16 +446,18 @@ def test_chr22_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
-def test_long_pairs_capacity_errors_are_flagged_never_silent(h2, chr22, tmp_path):
-    """2x250 bp pairs with indels and Ns: a handful of pairs need more than HT2_MAX_EDITS (40) edits in one
-    alignment; those are flagged (err != 0, HT2GPU_ERR_CAPACITY) and every OTHER pair is byte-identical."""
-    f1, f2 = os.path.join(DATA, "len250_1.fa"), os.path.join(DATA, "len250_2.fa")
+@pytest.mark.parametrize("name", ["len250", "len1000"])
+def test_long_pairs_capacity_errors_are_flagged_never_silent(h2, chr22, name, tmp_path):
+    """2x250 bp and 2x1000 bp pairs with indels and Ns.  Capacities are compile-time (1 024 bases, 128 edits per
+    trial alignment, 48 nested extensions): a pair that needs more is flagged (err != 0, counted in n_err_reads), the
+    call succeeds, and every OTHER pair is byte-identical to the reference.  2x250 no longer flags anything."""
+    f1, f2 = os.path.join(DATA, name + "_1.fa"), os.path.join(DATA, name + "_2.fa")
     if not os.path.exists(f1):
         pytest.skip(f1 + " not staged")
     batch = h2.ReadBatch.from_fasta(f1, path2=f2)
     res = chr22.align(batch)
     bad = set(np.flatnonzero(res.reads["err"] != 0).tolist())
-    assert len(bad) <= 10
+    assert len(bad) == res.n_err_reads and len(bad) <= (0 if name == "len250" else 150)
     sam = chr22.sam_header() + chr22.format_sam(batch, res)
     out = str(tmp_path / "ref.sam")
     subprocess.run([REFBIN, "--no-spliced-alignment", "-f", "-x", os.path.join(DATA, "22_20-21M"), "-1", f1, "-2", f2, "-S", out,
