@@ -1038,12 +1038,12 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
 // HT2GPU_STATS=1: per-state statistics of the pool kernel's rounds (investigation aid).
 static void dumpStats(ht2gpu_handle* h)
 {
-    static const char* topN[] = {"START", "NEXTBWT", "PS", "ALIGN", "HYB_EXTEND", "HYB_PICK", "HYB_RET", "POST_ALIGN", "AFTER_LOOP",
+    static const char* topN[] = {"START", "NEXTBWT", "PS", "ALIGN", "HYB_EXTEND", "HYB_PICK", "HYB_RET", "HYB_DP", "HYB_DP_RET", "POST_ALIGN", "AFTER_LOOP",
                                  "MATE_NEXT", "MATE_SEARCH", "MATE_ANCHOR", "MATE_RET", "MATE_DONE", "DONE"};
     static const char* frN[] = {"ENTER", "L_START", "L_WHILE", "L_COORD", "L_COORD_RET", "L_WHILE_TAIL", "L_STASH", "L_STASH_RET",
                                 "L_AFTER_WHILE", "L_GCOORD", "L_GCOORD_RET", "L_TRIM", "L_TRIM_RET", "L_EXT", "R_START", "R_WHILE",
                                 "R_COORD", "R_COORD_RET", "R_WHILE_TAIL", "R_STASH", "R_STASH_RET", "R_AFTER_WHILE", "R_GCOORD",
-                                "R_GCOORD_RET", "R_TRIM", "R_TRIM_RET", "R_EXT", "FINAL_RET", "RETURN"};
+                                "R_GCOORD_RET", "R_TRIM", "R_TRIM_RET", "R_EXT", "FINAL_RET", "RETURN", "L_COMBINE", "L_GCOMBINE", "R_COMBINE", "R_GCOMBINE"};
     std::vector<unsigned long long> st(1024 + 256 * 12);
     if (cudaMemcpy(st.data(), h->dStats, st.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
     cudaMemset(h->dStats, 0, st.size() * 8);
@@ -1055,8 +1055,8 @@ static void dumpStats(ht2gpu_handle* h)
         char nm[32];
         if (c == 0) snprintf(nm, sizeof nm, "NEED");
         else if (c == 1) snprintf(nm, sizeof nm, "FINISH");
-        else if (c < 20) snprintf(nm, sizeof nm, "T_%s", c - 2 < 15 ? topN[c - 2] : "?");
-        else snprintf(nm, sizeof nm, "F_%s", c - 20 < 29 ? frN[c - 20] : "?");
+        else if (c < 20) snprintf(nm, sizeof nm, "T_%s", c - 2 < 17 ? topN[c - 2] : "?");
+        else snprintf(nm, sizeof nm, "F_%s", c - 20 < 33 ? frN[c - 20] : "?");
         fprintf(stderr, "%-16s %10llu %7.2f %10.0f %9llu %6.2f |", nm, st[c * 4], (double)st[c * 4 + 1] / st[c * 4],
                 (double)st[c * 4 + 2] / st[c * 4], st[c * 4 + 3], 100.0 * st[c * 4 + 2] / (totC ? totC : 1));
         // cycles per round by group size: 1, 2-3, 4-7, 8-15, 16-31, 32 lanes

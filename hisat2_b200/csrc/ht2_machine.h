@@ -17,7 +17,7 @@
 
 enum {
     // top-level states (HI_Aligner::go, hi_aligner.h:4048-4149)
-    TS_START = 0, TS_NEXTBWT, TS_PS, TS_ALIGN, TS_HYB_EXTEND, TS_HYB_PICK, TS_HYB_RET, TS_HYB_DP_RET, TS_POST_ALIGN,
+    TS_START = 0, TS_NEXTBWT, TS_PS, TS_ALIGN, TS_HYB_EXTEND, TS_HYB_PICK, TS_HYB_RET, TS_HYB_DP, TS_HYB_DP_RET, TS_POST_ALIGN,
     TS_AFTER_LOOP, TS_MATE_NEXT, TS_MATE_SEARCH, TS_MATE_ANCHOR, TS_MATE_RET, TS_MATE_DONE, TS_DONE
 };
 enum {
@@ -27,7 +27,10 @@ enum {
     F_L_GCOORD, F_L_GCOORD_RET, F_L_TRIM, F_L_TRIM_RET, F_L_EXT,
     F_R_START, F_R_WHILE, F_R_COORD, F_R_COORD_RET, F_R_WHILE_TAIL, F_R_STASH, F_R_STASH_RET, F_R_AFTER_WHILE,
     F_R_GCOORD, F_R_GCOORD_RET, F_R_TRIM, F_R_TRIM_RET, F_R_EXT,
-    F_FINAL_RET, F_RETURN
+    F_FINAL_RET, F_RETURN,
+    // the expensive half of the four *COORD states (extend + combineWith): its own states, so that a round gathers only
+    // slots that really have a pair of hits to join (the cheap half -- build the hit, compatibleWith -- is glue)
+    F_L_COMBINE, F_L_GCOMBINE, F_R_COMBINE, F_R_GCOMBINE
 };
 
 // push a child frame (== a recursive call of hybridSearch_recur)
@@ -145,12 +148,19 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFram
             if (f.count == 1) { f.ri--; break; }
             f.pc = F_L_WHILE_TAIL; break;
         }
+        f.tempHit = tp; f.pc = F_L_COMBINE;
+        break;
+    }
+    case F_L_COMBINE: {
+        Ht2Hit* tp = f.tempHit;
+        Ht2Hit& tempHit = *tp;
         if (f.uniqueStop) {
             uint32_t leftext = HT2_IDX_MAX32, rightext = 0;
             extend(tempHit, rdi, leftext, rightext, 0);
         }
         bool combined = combineWith(tempHit, hit, rdi, minsc[rdi]);
         int64_t msc = sinkFloor(rdi, f.cushion);
+        f.pc = F_L_COORD;
         if (combined && tempHit.score >= msc) {
             if (tempHit.score >= f.prev_score - mmpMax) {
                 f.pc = F_L_COORD_RET;
@@ -227,12 +237,19 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFram
         initHit(tempHit, coord.fw != 0, f.extoff + 1 - f.extlen, f.extlen, 0, 0, coord.ref, coord.off, coord.joinedOff);
         if (GRAPH && !adjustWithALT(tempHit, rdi)) { W->poolTop--; f.ri--; break; }   // spliced_aligner.h:946, 1139, 1635, 1826
         if (!compatibleWith(tempHit, hit, rdi)) { W->poolTop--; f.ri--; break; }
+        f.tempHit = tp; f.pc = F_L_GCOMBINE;
+        break;
+    }
+    case F_L_GCOMBINE: {
+        Ht2Hit* tp = f.tempHit;
+        Ht2Hit& tempHit = *tp;
         if (f.uniqueStop) {
             uint32_t leftext = HT2_IDX_MAX32, rightext = 0;
             extend(tempHit, rdi, leftext, rightext, 0);
         }
         bool combined = combineWith(tempHit, hit, rdi, minsc[rdi]);
         int64_t msc = sinkFloor(rdi, f.cushion);
+        f.pc = F_L_GCOORD;
         if (combined && tempHit.score >= msc) {
             f.pc = F_L_GCOORD_RET;
             pushFrame(rdi, tp, tempHit.rdoff, tempHit.len + tempHit.trim3, alignMate, f.dep + 1);
@@ -375,6 +392,12 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFram
             if (f.count == 1) { f.ri++; break; }
             f.pc = F_R_WHILE_TAIL; break;
         }
+        f.tempHit = tp; f.pc = F_R_COMBINE;
+        break;
+    }
+    case F_R_COMBINE: {
+        Ht2Hit* tp = f.tempHit;
+        Ht2Hit& tempHit = *tp;
         uint32_t leftext = 0, rightext = HT2_IDX_MAX32;
         extend(tempHit, rdi, leftext, rightext, 0);
         Ht2Hit* cp = poolAlloc();
@@ -385,6 +408,7 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFram
         // keep the combined hit in tempHit's slot so the pool stays a stack
         copyHit(tempHit, combinedHit);
         W->poolTop--; // combinedHit slot
+        f.pc = F_R_COORD;
         if (combined && tempHit.score >= msc) {
             if (tempHit.score >= f.prev_score - mmpMax) {
                 f.pc = F_R_COORD_RET;
@@ -461,6 +485,12 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFram
         initHit(tempHit, coord.fw != 0, f.extoff + 1 - f.extlen, f.extlen, 0, 0, coord.ref, coord.off, coord.joinedOff);
         if (GRAPH && !adjustWithALT(tempHit, rdi)) { W->poolTop--; f.ri++; break; }   // spliced_aligner.h:946, 1139, 1635, 1826
         if (!compatibleWith(hit, tempHit, rdi)) { W->poolTop--; f.ri++; break; }
+        f.tempHit = tp; f.pc = F_R_GCOMBINE;
+        break;
+    }
+    case F_R_GCOMBINE: {
+        Ht2Hit* tp = f.tempHit;
+        Ht2Hit& tempHit = *tp;
         uint32_t leftext = 0, rightext = HT2_IDX_MAX32;
         extend(tempHit, rdi, leftext, rightext, 0);
         Ht2Hit* cp = poolAlloc();
@@ -470,6 +500,7 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFram
         int64_t msc = sinkFloor(rdi, f.cushion);
         copyHit(tempHit, combinedHit);
         W->poolTop--;
+        f.pc = F_R_GCOORD;
         if (combined && tempHit.score >= msc) {
             f.pc = F_R_GCOORD_RET;
             pushFrame(rdi, tp, tempHit.rdoff - tempHit.trim5, tempHit.len + tempHit.trim5, alignMate, f.dep + 1);
@@ -676,13 +707,27 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runTop(
 #ifndef HT2_NO_DP
         if (P->bowtie2Dp == 2 || (P->bowtie2Dp == 1 && W->childRet < minsc[W->curRdi])) {
             Ht2Hit& gh = W->genomeHits[W->hybHj];
-            if (!W->err && swExtendAnchor(W->curRdi, gh)) {
-                W->st = TS_HYB_DP_RET;
+            if (!W->err) {
+                if (gh.len < W->rd[W->curRdi].len) { W->st = TS_HYB_DP; break; }   // a DP problem: its own heavy state, so that
+                                                                                   // the lanes of a round all run the fill
+                W->st = TS_HYB_DP_RET;                                             // already full length (swExtendAnchor's first line)
                 pushFrame(W->curRdi, &gh, gh.rdoff, gh.len, false, 0);
                 break;
             }
         }
 #endif
+        W->genomeHitsDone[W->hybHj] = 1;
+        W->hybIter++;
+        W->st = TS_HYB_PICK;
+        break;
+    }
+    case TS_HYB_DP: {
+        Ht2Hit& gh = W->genomeHits[W->hybHj];
+        if (swExtendAnchor(W->curRdi, gh)) {
+            W->st = TS_HYB_DP_RET;
+            pushFrame(W->curRdi, &gh, gh.rdoff, gh.len, false, 0);
+            break;
+        }
         W->genomeHitsDone[W->hybHj] = 1;
         W->hybIter++;
         W->st = TS_HYB_PICK;
@@ -766,15 +811,15 @@ template <bool GRAPH, bool NOSPL> HT2_HD bool Ht2AlignerT<GRAPH, NOSPL>::machine
 {
     if (W->nFrames > 0) {
         switch (W->frames[W->nFrames - 1].pc) {
-            case F_ENTER: case F_L_START: case F_L_WHILE: case F_L_COORD: case F_L_AFTER_WHILE: case F_L_GCOORD: case F_L_TRIM: case F_L_EXT:
-            case F_R_START: case F_R_WHILE: case F_R_COORD: case F_R_AFTER_WHILE: case F_R_GCOORD: case F_R_TRIM: case F_R_EXT:
+            case F_ENTER: case F_L_START: case F_L_WHILE: case F_L_COMBINE: case F_L_AFTER_WHILE: case F_L_GCOMBINE: case F_L_TRIM: case F_L_EXT:
+            case F_R_START: case F_R_WHILE: case F_R_COMBINE: case F_R_AFTER_WHILE: case F_R_GCOMBINE: case F_R_TRIM: case F_R_EXT:
                 return true;
             default: return false;
         }
     }
     switch (W->st) {
         case TS_PS: case TS_ALIGN: case TS_HYB_EXTEND: case TS_MATE_SEARCH: case TS_MATE_ANCHOR: case TS_DONE: return true;
-        case TS_HYB_RET: return P->bowtie2Dp != 0;   // the dynamic-programming extension runs here
+        case TS_HYB_DP: return true;                 // the dynamic-programming extension runs here
         default: return false;
     }
 }
