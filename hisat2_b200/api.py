@@ -86,7 +86,7 @@ EXPORTS = [
     "ht2gpu_seed_search", "ht2gpu_free_seed_results", "ht2gpu_index_is_graph",
     "ht2gpu_sam_slots", "ht2gpu_submit_sam", "ht2gpu_wait_sam", "ht2gpu_align_sam", "ht2gpu_run_reads",
     "ht2gpu_host_alloc", "ht2gpu_host_free", "ht2gpu_set_error", "ht2gpu_parse_reads", "ht2gpu_free_parsed",
-    "ht2gpu_ctx_get", "ht2gpu_ctx_set", "ht2gpu_run_reads_multi", "ht2gpu_open_peer",
+    "ht2gpu_ctx_get", "ht2gpu_ctx_set", "ht2gpu_run_reads_multi", "ht2gpu_open_peer", "ht2gpu_sw_selftest",
 ]
 
 
@@ -151,9 +151,19 @@ def load_library(path=None):
     lib.ht2gpu_set_error.argtypes = [C.c_void_p, C.c_char_p]
     lib.ht2gpu_parse_reads.argtypes = [C.POINTER(CReadsInput), C.POINTER(CParsedReads), C.c_char_p, C.c_size_t]
     lib.ht2gpu_free_parsed.argtypes = [C.POINTER(CParsedReads)]
+    lib.ht2gpu_sw_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     if path is None:
         _lib = lib
     return lib
+
+
+def sw_selftest(n=2000, seed=1, device=0):
+    """ht2gpu_sw_selftest: warp-wide DP fill vs lane fill on n random problems -> dict(mismatches, problems, cells, valid)."""
+    out = (C.c_uint64 * 4)()
+    rc = load_library().ht2gpu_sw_selftest(device, n, seed, out)
+    if rc != 0:
+        raise Ht2GpuError("ht2gpu_sw_selftest failed (%d)" % rc)
+    return {"mismatches": int(out[0]), "problems": int(out[1]), "cells": int(out[2]), "valid": int(out[3])}
 
 
 _ASC2DNA = np.zeros(256, dtype=np.uint8)

@@ -213,21 +213,30 @@ struct Ht2AltScratch {
 #define HT2_SW_MAXCOLS (HT2_SW_MAX_RDLEN + 4 * HT2_SW_MAXGAP)
 #define HT2_SW_MAX_EDITS 160
 #define HT2_SW_SEG ((HT2_SW_MAX_RDLEN + 1) / 2)     /* words per column: 2 rows (s16 halves) per 32-bit word */
-// The three score matrices H, E, F (striped: row i = half i / seg of word i % seg; column-major; one spare column)
-// live OUTSIDE the scratch struct, in a plane pool addressed with a stride: word idx of plane p of a lane is
-// pool[(p * HT2_SW_PLANE_WORDS + idx) * stride + lane].  On the device stride = 32 and the 32 lanes of a warp
-// interleave their words, so that a converged warp -- the lanes of a round run their DP problems together -- writes
-// and reads whole 128-byte lines per instruction instead of 32 separate sectors; the host build uses stride 1.
-#define HT2_SW_PLANE_WORDS ((HT2_SW_MAXCOLS + 1) * HT2_SW_SEG)
+// The three score matrices H, E, F (column-major, one spare column) live OUTSIDE the scratch struct, in a plane pool of
+// HT2_SW_POOL_WORDS words per executing lane.  Two stripings of a column share that space (ht2_sw.h):
+//   lane fill (swFill, host and single-lane device path): 2 rows per word -- row i = half i / seg of word i % seg,
+//     seg = ceil(nrow / 2);
+//   warp fill (swFillCoop, the pool kernel's DP rounds): an anti-diagonal wavefront, lane L owning the R = ceil(nrow / 32)
+//     rows L*R .., stored step-major: ncol + 31 steps of 32 * ceil(R / 2) words.
+#define HT2_SW_PLANE_WORDS ((HT2_SW_MAXCOLS + 32) * HT2_SW_SEG)
 #define HT2_SW_POOL_WORDS (3 * HT2_SW_PLANE_WORDS + 7 * HT2_SW_SEG)   /* per lane: H, E, F + query profile (5) + gap barrier + barrier/read-gap-open words */
+struct Ht2SwRect { int64_t refl, refr; uint32_t triml, trimr, corel, corer; };
 struct Ht2SwScratch {
     uint32_t rep[((size_t)HT2_SW_MAXCOLS * HT2_SW_MAX_RDLEN + 31) / 32];   // reported-through bit per cell (col * nrow + row)
     uint32_t nrow, seg;
+    uint32_t coop, rcp;                                      // layout of the planes: 0 = lane fill (striped), 1 = warp fill (seg = rows per lane, rcp = ceil(65536 / seg))
+    // the framed problem (swPrepare -> swFill / swFillCoop -> swFinish)
+    const uint8_t* jrd; const uint8_t* jqu; const uint8_t* jrf;
+    uint32_t jncol, jfw;
+    int64_t  jmsc, jbest;
+    Ht2SwRect jrect;
     int32_t  lastH[HT2_SW_MAXCOLS];                          // last-row H per column (the candidates)
     uint8_t  rowPen[HT2_SW_MAX_RDLEN];                          // mismatch penalty of each read row
     alignas(8) uint8_t rf[HT2_SW_MAXCOLS + 16];              // reference window, codes 0..4
     Ht2Edit  ned[HT2_SW_MAX_EDITS];
 };
+static_assert(HT2_SW_SEG >= 32 * ((((HT2_SW_MAX_RDLEN + 31) / 32) + 1) / 2), "warp fill: 32 lanes x ceil(R / 2) words per step fit a column of the pool");
 
 // Per-read (pair) workspace.  One per in-flight GPU thread.
 struct alignas(128) Ht2Work {
@@ -476,6 +485,8 @@ struct Ht2AlignerT {
     Ht2SwScratch*         sw;      // --bowtie2-dp scratch of this lane (NULL when dp is off)
     uint32_t*             swPl;    // the lane's first word in the H / E / F plane pool
     uint32_t              swStride;
+    uint32_t              swStage; // 0, or set by the pool kernel's DP round: 1 = problem framed and filled by the warp, 2 = nothing to fill (answer in swRetv)
+    bool                  swRetv;
 #ifdef HT2_ENABLE_SPLICED
     const Ht2SplTables*   splT;    // donor / acceptor probability tables (spliced mode)
 #endif
@@ -502,7 +513,7 @@ struct Ht2AlignerT {
         gfm.init(blob_, &H->global);
         P = P_;
         W = W_;
-        sw = NULL;
+        sw = NULL; swPl = NULL; swStride = 1; swStage = 0; swRetv = false;
 #ifdef HT2_ENABLE_SPLICED
         splT = NULL;
 #endif

@@ -363,6 +363,31 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
         }
         __threadfence_block();   // acquire: the previous owner's workspace writes
         const long long t0 = o.stats ? clock64() : 0;
+#ifndef HT2_NO_DP
+        if (T == RG_TOP + TS_HYB_DP) {
+            // A round of DP problems (--bowtie2-dp): every lane frames its own rectangle, then the WARP fills the
+            // score planes of one problem after the other (ht2_sw.h swFillCoop: a 64-row vector per column instead
+            // of a lone lane's 2), and the lanes go back to their own candidates / backtraces below.
+            bool fill = false;
+            if (my >= 0) {
+                Ht2Work* W = base + my;
+                A.attach(W);
+                bool ret;
+                fill = A.swPrepare(W->curRdi, W->genomeHits[W->hybHj], ret);
+                A.swStage = fill ? 1u : 2u; A.swRetv = ret;
+            }
+            __syncwarp();
+            uint32_t m = __ballot_sync(0xffffffffu, fill);
+            while (m) {
+                const int k = __ffs((int)m) - 1;
+                m &= m - 1;
+                Ht2SwScratch* Sk = (Ht2SwScratch*)__shfl_sync(0xffffffffu, (unsigned long long)A.sw, k);
+                uint32_t* pk = (uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)A.swPl, k);
+                A.swFillCoop(Sk, pk, lane);
+            }
+            __syncwarp();
+        }
+#endif
         if (my >= 0) {
             Ht2Work* W = base + my;
             uint32_t nc;
@@ -1317,6 +1342,100 @@ struct SeedPriv {
 };
 
 extern "C" int ht2gpu_index_is_graph(const ht2gpu_handle_t* h) { return h && h->graph ? 1 : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ht2gpu_sw_selftest: the warp-wide DP fill (swFillCoop) against the lane fill (swFill, itself pinned to a plain
+// scalar statement of the recurrences by the host self-test, tests/hostsim --sw-selftest) on random problems:
+// every H, E and F cell, every last-row score and the best score must be equal.  One warp per problem.
+// ---------------------------------------------------------------------------------------------------------------
+struct SwTestProblem {
+    int32_t mmpMax, mmpMin, npen, mmcostConstant, rdGapConst, rdGapLinear, rfGapConst, rfGapLinear, gapbar;
+    uint32_t nrow, ncol;
+    int64_t minsc;
+    uint8_t rd[HT2_SW_MAX_RDLEN], qu[HT2_SW_MAX_RDLEN], rf[HT2_SW_MAXCOLS + 8];
+};
+__global__ void __launch_bounds__(32)
+ht2_sw_selftest_kernel(const SwTestProblem* probs, uint32_t n, Ht2SwScratch* scr, uint32_t* pools, unsigned long long* out)
+{
+    const uint32_t lane = threadIdx.x;
+    Ht2SwScratch* S0 = scr + (size_t)blockIdx.x * 2; Ht2SwScratch* S1 = S0 + 1;
+    uint32_t* p0 = pools + (size_t)blockIdx.x * 2 * HT2_SW_POOL_WORDS; uint32_t* p1 = p0 + HT2_SW_POOL_WORDS;
+    __shared__ Ht2ParamsCore P;
+    for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
+        const SwTestProblem& q = probs[it];
+        __syncwarp();
+        if (lane == 0) {
+            memset(&P, 0, sizeof(P));
+            P.mmpMax = q.mmpMax; P.mmpMin = q.mmpMin; P.npen = q.npen; P.mmcostConstant = q.mmcostConstant != 0;
+            P.rdGapConst = q.rdGapConst; P.rdGapLinear = q.rdGapLinear; P.rfGapConst = q.rfGapConst; P.rfGapLinear = q.rfGapLinear;
+            P.gapbar = q.gapbar;
+        }
+        __syncwarp();
+        Ht2AlignerT<false> A0, A1;
+        A0.blob = NULL; A0.H = NULL; A0.P = &P; A0.W = NULL; A0.sw = S0; A0.swPl = p0; A0.swStride = 1; A0.swStage = 0;
+        A1 = A0; A1.sw = S1; A1.swPl = p1;
+        long long best0 = 0;
+        if (lane == 0) {
+            best0 = A0.swFill(q.rd, q.qu, q.nrow, q.rf, q.ncol, q.minsc);
+            S1->jrd = q.rd; S1->jqu = q.qu; S1->jrf = q.rf; S1->nrow = q.nrow; S1->jncol = q.ncol; S1->jmsc = q.minsc; S1->jbest = 0;
+        }
+        __syncwarp();
+        A1.swFillCoop(S1, p1, lane);
+        unsigned long long bad = 0;
+        for (uint32_t c = lane; c < q.nrow * q.ncol; c += 32) {
+            const uint32_t row = c % q.nrow, col = c / q.nrow;
+            for (int pl = 0; pl < 3; pl++) if (A0.swRaw(pl, S0->seg, row, col) != A1.swRaw(pl, S1->seg, row, col)) bad++;
+        }
+        for (uint32_t j = lane; j < q.ncol; j += 32) if (S0->lastH[j] != S1->lastH[j]) bad++;
+        if (lane == 0 && best0 != S1->jbest) bad++;
+        if (bad) atomicAdd(&out[0], bad);
+        if (lane == 0) { atomicAdd(&out[1], 1ull); atomicAdd(&out[2], (unsigned long long)q.nrow * q.ncol); if (best0 != HT2_MIN_I64) atomicAdd(&out[3], 1ull); }
+    }
+}
+extern "C" int ht2gpu_sw_selftest(int device, uint32_t n, uint32_t seed, uint64_t out[4])
+{
+    if (cudaSetDevice(device) != cudaSuccess) return HT2GPU_ERR_CUDA;
+    std::vector<SwTestProblem> probs(n);
+    uint32_t rng = seed ? seed : 1;
+    auto rnd = [&](uint32_t m) { rng = rng * 1664525u + 1013904223u; return (rng >> 8) % m; };
+    for (uint32_t it = 0; it < n; it++) {
+        SwTestProblem& q = probs[it];
+        memset(&q, 0, sizeof(q));
+        q.mmpMax = 2 + rnd(6); q.mmpMin = 1 + rnd(q.mmpMax); q.npen = 1 + rnd(2); q.mmcostConstant = rnd(4) == 0;
+        q.rdGapConst = 1 + rnd(8); q.rdGapLinear = 1 + rnd(4); q.rfGapConst = 1 + rnd(8); q.rfGapLinear = 1 + rnd(4);
+        q.gapbar = 1 + rnd(12);
+        q.nrow = 20 + rnd(HT2_SW_MAX_RDLEN - 20); q.ncol = q.nrow + 40;
+        for (uint32_t j = 0; j < q.ncol + 8; j++) q.rf[j] = rnd(50) == 0 ? 4 : rnd(4);
+        uint32_t k = 0;
+        for (uint32_t j = 20; k < q.nrow && j < q.ncol;) {       // the read: the window with substitutions and small indels
+            const uint32_t r = rnd(100);
+            if (r < 3) q.rd[k++] = (uint8_t)rnd(4);
+            else if (r < 6) j++;
+            else { q.rd[k++] = r < 12 ? (uint8_t)rnd(5) : q.rf[j]; j++; }
+        }
+        while (k < q.nrow) q.rd[k++] = (uint8_t)rnd(4);
+        for (uint32_t i = 0; i < q.nrow; i++) q.qu[i] = (uint8_t)(33 + rnd(42));
+        q.minsc = -(int64_t)(10 + rnd(3 * q.nrow));
+    }
+    const int grid = 64;
+    SwTestProblem* dP = NULL; Ht2SwScratch* dS = NULL; uint32_t* dPool = NULL; unsigned long long* dOut = NULL;
+    int rc = HT2GPU_OK;
+    if (cudaMalloc(&dP, sizeof(SwTestProblem) * (size_t)(n ? n : 1)) != cudaSuccess || cudaMalloc(&dS, sizeof(Ht2SwScratch) * 2 * grid) != cudaSuccess ||
+        cudaMalloc(&dPool, sizeof(uint32_t) * (size_t)HT2_SW_POOL_WORDS * 2 * grid) != cudaSuccess || cudaMalloc(&dOut, 4 * sizeof(unsigned long long)) != cudaSuccess) rc = HT2GPU_ERR_CUDA;
+    if (rc == HT2GPU_OK) {
+        cudaMemcpy(dP, probs.data(), sizeof(SwTestProblem) * (size_t)n, cudaMemcpyHostToDevice);
+        cudaMemset(dOut, 0, 4 * sizeof(unsigned long long));
+        cudaMemset(dS, 0, sizeof(Ht2SwScratch) * 2 * grid);
+        size_t lim = 0; cudaDeviceGetLimit(&lim, cudaLimitStackSize);
+        if (lim < 8192) cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+        ht2_sw_selftest_kernel<<<grid, 32>>>(dP, n, dS, dPool, dOut);
+        unsigned long long o4[4] = {0, 0, 0, 0};
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(o4, dOut, sizeof(o4), cudaMemcpyDeviceToHost) != cudaSuccess) rc = HT2GPU_ERR_CUDA;
+        for (int i = 0; i < 4; i++) out[i] = o4[i];
+    }
+    cudaFree(dP); cudaFree(dS); cudaFree(dPool); cudaFree(dOut);
+    return rc;
+}
 
 namespace {
 struct DevTmp {   // temporaries of one ht2gpu_seed_search call: freed on every return path

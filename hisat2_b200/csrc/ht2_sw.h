@@ -52,7 +52,7 @@
 #define HT2_SWM_OE        (1u << 11)
 #define HT2_SWM_OF        (1u << 12)
 
-struct SwRect { int64_t refl, refr; uint32_t triml, trimr, corel, corer; };
+typedef Ht2SwRect SwRect;
 
 // DynProgFramer::frameSeedExtensionRect with readGaps = refGaps = maxhalf = 10, nceil = 0,
 // trimToRef = false (the arguments of spliced_aligner.h:226-239)
@@ -87,7 +87,7 @@ HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const
     const uint32_t seg = (nrow + 1) >> 1;
     const uint32_t gapbar = (uint32_t)P->gapbar;
     const int rdgapo = P->rdGapConst + P->rdGapLinear;
-    S.nrow = nrow; S.seg = seg;
+    S.nrow = nrow; S.seg = seg; S.coop = 0; S.rcp = 0;
     for (uint32_t k = 0, n = (ncol * nrow + 31) >> 5; k < n; k++) S.rep[k] = 0;   // reported-through bits
     for (uint32_t i = 0; i < nrow; i++) S.rowPen[i] = (uint8_t)ht2_mmpen(*P, (int)qu[i] - 33);
     for (uint32_t s = 0; s < seg; s++) {   // negated query profile / gap-barrier words (buildQueryProfileEnd2EndSseU8, :76-140)
@@ -111,51 +111,59 @@ HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const
     }
     const uint32_t nRDE = ht2_v2_splat(-P->rdGapLinear);
     const uint32_t nRFO = ht2_v2_splat(-(P->rfGapConst + P->rfGapLinear)), nRFE = ht2_v2_splat(-P->rfGapLinear);
-    const size_t Hz = (size_t)ncol * seg;   // an all-floor column of H standing in for column -1
-    for (uint32_t s = 0; s < seg; s++) { HT2_SWP(0, Hz + s) = 0; HT2_SWP(1, s) = 0; }
+    // plain pointers into the lane's pool (stride 1): the inner loop is latency-bound on a lone lane -- one DP problem
+    // rarely has company in its warp -- so every address computation it does not do counts (the strided accessor
+    // macros cost ~40 of the ~70 instructions per word in the round-2 profile)
+    uint32_t* const plH = &HT2_SWP(0, 0); uint32_t* const plE = &HT2_SWP(1, 0); uint32_t* const plF = &HT2_SWP(2, 0);
+    const uint32_t* const qG = &HT2_SWQ(5, 0); const uint32_t* const qR = &HT2_SWQ(6, 0);
+    uint32_t* const Hzc = plH + (size_t)ncol * seg;   // an all-floor column of H standing in for column -1
+    for (uint32_t s = 0; s < seg; s++) { Hzc[s] = 0; plE[s] = 0; }
     const uint32_t lastW = (nrow - 1) % seg, lastB = 16 * ((nrow - 1) / seg);
     int best = 0;
     for (uint32_t j = 0; j < ncol; j++) {
         const uint32_t pr = rf[j] > 4 ? 4u : (uint32_t)rf[j];
-        const size_t c0 = (size_t)j * seg, cn = (size_t)(j + 1) * seg, cp = j ? (size_t)(j - 1) * seg : Hz;   // this / next / previous column
+        const uint32_t* const qP = &HT2_SWQ(pr, 0);
+        uint32_t* const Hc = plH + (size_t)j * seg; uint32_t* const Fc = plF + (size_t)j * seg;
+        uint32_t* const Ec = plE + (size_t)j * seg; uint32_t* const En = Ec + seg;
+        const uint32_t* const Hp = j ? Hc - seg : Hzc;
         uint32_t vF = 0;
-        uint32_t vH = (HT2_SWP(0, cp + seg - 1) << 16) | (uint32_t)HT2_SW_TOP;   // diagonal of row 0 = perfect; of row seg = last row of half 0
+        uint32_t vH = (Hp[seg - 1] << 16) | (uint32_t)HT2_SW_TOP;   // diagonal of row 0 = perfect; of row seg = last row of half 0
         // The loads of iteration s + 1 are issued before the stores of iteration s: all planes live in one pool, so
         // the compiler must assume the stores alias them and would otherwise start each iteration's loads only
-        // after the previous iteration's stores (the fill was 87 % long_scoreboard in the round-2 profile).
-        uint32_t nE = HT2_SWP(1, c0), nHp = HT2_SWP(0, cp), nG = HT2_SWQ(5, 0), nP = HT2_SWQ(pr, 0), nR = HT2_SWQ(6, 0);
+        // after the previous iteration's stores.
+        uint32_t nE = Ec[0], nHp = Hp[0], nG = qG[0], nP = qP[0], nR = qR[0];
         for (uint32_t s = 0; s < seg; s++) {
             uint32_t vE = nE;
             const uint32_t hp = nHp, wG = nG, wP = nP, wR = nR;
-            if (s + 1 < seg) { nE = HT2_SWP(1, c0 + s + 1); nHp = HT2_SWP(0, cp + s + 1); nG = HT2_SWQ(5, s + 1); nP = HT2_SWQ(pr, s + 1); nR = HT2_SWQ(6, s + 1); }
+            if (s + 1 < seg) { nE = Ec[s + 1]; nHp = Hp[s + 1]; nG = qG[s + 1]; nP = qP[s + 1]; nR = qR[s + 1]; }
             vF = ht2_v2_addmax(vF, wG, 0);                                  // veto ref-gap extensions in barrier rows
-            HT2_SWP(2, c0 + s) = vF;
+            Fc[s] = vF;
             vH = ht2_v2_addmax(vH, wP, 0);                                  // match / mismatch
             vH = ht2_v2_max3(vH, vE, vF);
-            HT2_SWP(0, c0 + s) = vH;
+            Hc[s] = vH;
             vE = ht2_v2_addmax(vE, nRDE, ht2_v2_addmax(vH, wR, 0));         // E of the next column
-            HT2_SWP(1, cn + s) = vE;
+            En[s] = vE;
             vF = ht2_v2_addmax(vF, nRFE, ht2_v2_addmax(vH, nRFO, 0));       // F of the next row
             vH = hp;
         }
         // lazy F: carry each half's last F into the other half's first rows while it still improves
         {
             uint32_t s = 0;
-            vF = ht2_v2_addmax(vF << 16, HT2_SWQ(5, 0), 0);
+            vF = ht2_v2_addmax(vF << 16, qG[0], 0);
             for (;;) {
-                const uint32_t old = HT2_SWP(2, c0 + s);
+                const uint32_t old = Fc[s];
                 const uint32_t nf = ht2_v2_max(old, vF);
                 if (nf == old) break;
-                HT2_SWP(2, c0 + s) = nf;
-                const uint32_t vh = ht2_v2_max(HT2_SWP(0, c0 + s), nf);
-                HT2_SWP(0, c0 + s) = vh;
-                HT2_SWP(1, cn + s) = ht2_v2_max(HT2_SWP(1, cn + s), ht2_v2_addmax(vh, HT2_SWQ(6, s), 0));
+                Fc[s] = nf;
+                const uint32_t vh = ht2_v2_max(Hc[s], nf);
+                Hc[s] = vh;
+                En[s] = ht2_v2_max(En[s], ht2_v2_addmax(vh, qR[s], 0));
                 vF = nf;
                 if (++s == seg) { s = 0; vF <<= 16; }
-                vF = ht2_v2_addmax(ht2_v2_addmax(vF, nRFE, 0), HT2_SWQ(5, s), 0);
+                vF = ht2_v2_addmax(ht2_v2_addmax(vF, nRFE, 0), qG[s], 0);
             }
         }
-        const int lr = (int)((HT2_SWP(0, c0 + lastW) >> lastB) & 0xffffu);
+        const int lr = (int)((Hc[lastW] >> lastB) & 0xffffu);
         S.lastH[j] = lr - HT2_SW_TOP;
         if (lr > best) best = lr;
     }
@@ -163,7 +171,103 @@ HT2_NI int64_t swFill(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const
     return best - HT2_SW_TOP;
 }
 
+#if defined(__CUDACC__)
+// One vector position down: element p of the warp-wide vector (lane p % 32, half p / 32) receives element p - 1;
+// element 0 receives 'first'.  The s16x2 counterpart of the striped kernel's byte shift (_mm_slli_si128).
+__device__ __forceinline__ static uint32_t swShift1(uint32_t w, uint32_t lane, uint32_t first) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, w, 1);
+    const uint32_t l31 = __shfl_sync(0xffffffffu, w, 31);
+    return lane ? up : ((l31 << 16) | first);
+}
+// The fill run by a whole warp on ONE problem (the problem framed in *Sp by swPrepare on its owner lane; planes
+// into the owner's pool), as an anti-diagonal wavefront: lane L owns the R = ceil(nrow / 32) consecutive rows
+// L*R .. L*R + R - 1 and works on column t - L at step t, so that everything a cell needs is either in the lane's
+// own registers (left neighbours, the rows above inside its block) or was produced by lane L - 1 one step earlier
+// (H and F of its last row: two shuffles per step).  ncol + 31 steps of R cells; a cell is ~12 scalar DPX /
+// integer instructions.  This evaluates the saturating recurrences at the top of this file DIRECTLY -- no lazy-F
+// loop: the striped kernel's lazy-F pass, cheap with 2 (swFill) or 16 (SSE) rows per vector, degenerates when
+// the vector is a warp wide, because a reference-gap chain below the read's diagonal crosses a vector position
+// every R rows and each crossing costs a pass (measured: ~20 passes per column, profiles/r02_*dp2*).  Cell values
+// are those of swFill; they are stored skewed, step-major (word q of lane L at step t), so that every store is a
+// coalesced line: cell (row, col) = half k & 1 of word ((col + L) * 32 + L) * RW + k / 2, L = row / R, k = row % R,
+// RW = ceil(R / 2) (swRaw).  All 32 lanes must call this with the same arguments.
+__device__ __noinline__ void swFillCoop(Ht2SwScratch* Sp, uint32_t* pool, uint32_t lane) const {
+    constexpr int MR = (HT2_SW_MAX_RDLEN + 31) / 32;
+    Ht2SwScratch& S = *Sp;
+    const uint32_t nrow = S.nrow, ncol = S.jncol;
+    const uint8_t* const rd = S.jrd; const uint8_t* const qu = S.jqu; const uint8_t* const rf = S.jrf;
+    const uint32_t R = (nrow + 31) >> 5, RW = (R + 1) >> 1;
+    const uint32_t gapbar = (uint32_t)P->gapbar;
+    const int rdo = P->rdGapConst + P->rdGapLinear, rde = P->rdGapLinear, rfo = P->rfGapConst + P->rfGapLinear, rfe = P->rfGapLinear;
+    const int npen = P->npen;
+    for (uint32_t k = lane, n = (ncol * nrow + 31) >> 5; k < n; k += 32) S.rep[k] = 0;
+    int rdc[MR], mm[MR], nbar[MR], nbo[MR], Hl[MR], El[MR], Fk[MR];
+#pragma unroll
+    for (int k = 0; k < MR; k++) {
+        const uint32_t i = lane * R + (uint32_t)k;
+        rdc[k] = 0; mm[k] = 0; nbar[k] = 0; nbo[k] = -rdo; Hl[k] = 0; El[k] = 0; Fk[k] = 0;
+        if ((uint32_t)k < R && i < nrow) {
+            const int bar = (i < gapbar || nrow - 1 - i < gapbar) ? HT2_SW_BAR : 0;
+            rdc[k] = rd[i];
+            mm[k] = ht2_mmpen(*P, (int)qu[i] - 33);
+            S.rowPen[i] = (uint8_t)mm[k];
+            nbar[k] = -bar; nbo[k] = -(bar + rdo);
+        }
+    }
+    uint32_t* const plH = pool + lane * RW; uint32_t* const plE = plH + (size_t)HT2_SW_PLANE_WORDS; uint32_t* const plF = plE + (size_t)HT2_SW_PLANE_WORDS;
+    const uint32_t lastLane = ((nrow - 1) * ((65536 + R - 1) / R)) >> 16, lastK = (nrow - 1) - lastLane * R;
+    int diagIn = 0, outH = 0, outF = 0, best = 0;
+    const uint32_t nstep = ncol + 31;
+    for (uint32_t t = 0; t < nstep; t++) {
+        const int inH = __shfl_up_sync(0xffffffffu, outH, 1), inF = __shfl_up_sync(0xffffffffu, outF, 1);
+        const uint32_t j = t - lane;
+        if (j < ncol) {                                   // (t < lane wraps to a huge j)
+            int refc = rf[j]; if (refc > 4) refc = 4;
+            int hd = lane ? diagIn : HT2_SW_TOP;          // H[i-1][j-1]: row 0's diagonal is the perfect score
+            int hu = inH, fu = inF;
+#pragma unroll
+            for (int k = 0; k < MR; k++) if ((uint32_t)k < R) {
+                const int e = __viaddmax_s32(El[k], -rde, __viaddmax_s32(Hl[k], nbo[k], 0));
+                int f = __viaddmax_s32(__viaddmax_s32(fu, -rfe, __viaddmax_s32(hu, -rfo, 0)), nbar[k], 0);
+                if (k == 0 && lane == 0) f = 0;           // row 0 has no row above
+                const int pen = (rdc[k] > 3 || refc > 3) ? npen : (rdc[k] == refc ? 0 : mm[k]);
+                const int h = __vimax3_s32(__viaddmax_s32(hd, -pen, 0), e, f);
+                hd = Hl[k];
+                Hl[k] = h; El[k] = e; Fk[k] = f;
+                hu = h; fu = f;
+            }
+            diagIn = inH; outH = hu; outF = fu;
+            const size_t o = (size_t)t * 32 * RW;
+#pragma unroll
+            for (int q = 0; q < MR / 2; q++) if ((uint32_t)q < RW) {
+                plH[o + q] = (uint32_t)Hl[2 * q] | ((uint32_t)Hl[2 * q + 1] << 16);
+                plE[o + q] = (uint32_t)El[2 * q] | ((uint32_t)El[2 * q + 1] << 16);
+                plF[o + q] = (uint32_t)Fk[2 * q] | ((uint32_t)Fk[2 * q + 1] << 16);
+            }
+            if (lane == lastLane) {
+                int lr = 0;
+#pragma unroll
+                for (int k = 0; k < MR; k++) if ((uint32_t)k == lastK) lr = Hl[k];
+                S.lastH[j] = lr - HT2_SW_TOP;
+                if (lr > best) best = lr;
+            }
+        }
+    }
+    best = __shfl_sync(0xffffffffu, best, lastLane);
+    if (lane == 0) {
+        S.seg = R; S.coop = 1; S.rcp = (65536 + R - 1) / R;
+        S.jbest = ((int64_t)(best - HT2_SW_TOP) < S.jmsc) ? HT2_MIN_I64 : (int64_t)(best - HT2_SW_TOP);
+    }
+    __syncwarp();
+}
+#endif
+
 HT2_HD int swRaw(int plane, uint32_t seg, uint32_t row, uint32_t col) const {
+    const Ht2SwScratch& S = *sw;
+    if (S.coop) {   // warp fill (seg = R rows per lane; the 16-bit reciprocal is exact for row < 8192)
+        const uint32_t L = (row * S.rcp) >> 16, k = row - L * seg, rw = (seg + 1) >> 1;
+        return (int)((HT2_SWP(plane, ((size_t)(col + L) * 32 + L) * rw + (k >> 1)) >> (16 * (k & 1))) & 0xffffu);
+    }
     return (int)((HT2_SWP(plane, (size_t)col * seg + row % seg) >> (16 * (row / seg))) & 0xffffu);
 }
 // Move bits of a cell from the score planes (what the reference recomputes at every visited cell,
@@ -339,32 +443,43 @@ HT2_NI void replaceEditsWithAlts(Ht2Hit& h, uint32_t rdi) {
     calculateScore(h, rdi);
 }
 
-// The dp block of SplicedAligner::hybridSearch (spliced_aligner.h:209-297).  Returns
-// 'found': true when the caller has to run hybridSearch_recur on gh once more.
-HT2_NI bool swExtendAnchor(uint32_t rdi, Ht2Hit& gh) {
+// The dp block of SplicedAligner::hybridSearch (spliced_aligner.h:209-297) in three steps, so that the pool kernel
+// can run the middle one with a whole warp per problem: swPrepare frames the rectangle and fetches the reference
+// window (returns false when there is nothing to fill: the answer is 'ret'), swFill / swFillCoop fill the planes,
+// swFinish walks the candidates.
+HT2_NI bool swPrepare(uint32_t rdi, Ht2Hit& gh, bool& ret) {
+    ret = false;
     const Ht2Read& R = W->rd[rdi];
     const uint32_t rdlen = R.len;
-    if (gh.len >= rdlen) return true;
+    if (gh.len >= rdlen) { ret = true; return false; }
     if (sw == NULL) { W->err |= HT2_ERR_SW; return false; }
     Ht2SwScratch& S = *sw;
     const bool fw = gh.fw != 0;
-    const uint8_t* rd = R.seq[fw ? 0 : 1];
-    const uint8_t* qu = R.qual[fw ? 0 : 1];
     const int64_t tlen = (int64_t)refLen(gh.tidx);
     const uint32_t refoff = gh.toff > gh.rdoff ? gh.toff - gh.rdoff : 0;
     SwRect rect;
     if (!swFrameRect((int64_t)refoff, rdlen, tlen, rect)) return false;
     const uint32_t ncol = (uint32_t)(rect.refr - rect.refl + 1);
     if (ncol > HT2_SW_MAXCOLS || rdlen > HT2_SW_MAX_RDLEN) { W->err |= HT2_ERR_SW; return false; }   // the score planes are sized for reads of up to 256 bases
-    // reference window; positions past the end of the sequence read as N (aligner_sw.cpp:160-212)
-    const uint8_t* rf = getStretch(S.rf, gh.tidx, (uint32_t)rect.refl, ncol);
     const int64_t msc = minsc[rdi];
-    const bool use16 = !(msc >= -254);                    // the reference's 16-bit path (aligner_sw.cpp:496): only the RNG reseeding differs
     if (msc < -15000) { W->err |= HT2_ERR_SW; return false; }
+    // reference window; positions past the end of the sequence read as N (aligner_sw.cpp:160-212)
+    S.jrf = getStretch(S.rf, gh.tidx, (uint32_t)rect.refl, ncol);
+    S.jrd = R.seq[fw ? 0 : 1]; S.jqu = R.qual[fw ? 0 : 1];
+    S.nrow = rdlen; S.jncol = ncol; S.jfw = fw ? 1u : 0u; S.jmsc = msc; S.jrect = rect; S.jbest = HT2_MIN_I64;
+    return true;
+}
+HT2_NI bool swFinish(uint32_t rdi, Ht2Hit& gh) {
+    Ht2SwScratch& S = *sw;
+    const uint8_t* rd = S.jrd; const uint8_t* qu = S.jqu; const uint8_t* rf = S.jrf;
+    const uint32_t rdlen = S.nrow, ncol = S.jncol;
+    const bool fw = S.jfw != 0;
+    const int64_t msc = S.jmsc;
+    const SwRect rect = S.jrect;
+    const bool use16 = !(msc >= -254);                    // the reference's 16-bit path (aligner_sw.cpp:496): only the RNG reseeding differs
     // nCeil = L,0,0.15 (SwAligner::initRead, aligner_sw.cpp:45)
     const int nceil = (int)((double)0.0f + (double)0.15f * (double)rdlen);
-    const int64_t best = swFill(rd, qu, rdlen, rf, ncol, msc);
-    if (best == HT2_MIN_I64) return false;
+    if (S.jbest == HT2_MIN_I64) return false;
     // SwAligner::nextAlignment: candidates in (score desc, col desc) order
     int64_t prevScore = 0; uint32_t prevCol = 0; bool havePrev = false;
     for (;;) {
@@ -396,4 +511,17 @@ HT2_NI bool swExtendAnchor(uint32_t rdi, Ht2Hit& gh) {
         replaceEditsWithAlts(gh, rdi);
         return true;
     }
+}
+// Returns 'found': true when the caller has to run hybridSearch_recur on gh once more.
+HT2_NI bool swExtendAnchor(uint32_t rdi, Ht2Hit& gh) {
+    if (swStage) {                                       // framed (and filled) by the pool kernel's warp-wide DP round
+        const bool filled = swStage == 1;
+        swStage = 0;
+        return filled ? swFinish(rdi, gh) : swRetv;
+    }
+    bool ret;
+    if (!swPrepare(rdi, gh, ret)) return ret;
+    Ht2SwScratch& S = *sw;
+    S.jbest = swFill(S.jrd, S.jqu, S.nrow, S.jrf, S.jncol, S.jmsc);
+    return swFinish(rdi, gh);
 }

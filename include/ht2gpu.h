@@ -337,6 +337,11 @@ uint32_t ht2gpu_ref_len(const ht2gpu_handle_t* h, uint32_t i);
 uint32_t ht2gpu_read_seed(const uint8_t* seq, const uint8_t* qual, uint32_t len,
                           const char* name, uint32_t global_seed);
 
+/* Diagnostics: the warp-wide fill of the --bowtie2-dp score planes against the single-lane fill on n random
+ * problems (aligner_swsse_ee_u8.cpp:791-1163 restated twice, ht2_sw.h).  out[0] = mismatching cells / scores
+ * (must be 0), out[1] = problems run, out[2] = cells compared per plane, out[3] = problems with a valid best. */
+int ht2gpu_sw_selftest(int device, uint32_t n, uint32_t seed, uint64_t out[4]);
+
 const char* ht2gpu_last_error(const ht2gpu_handle_t* h);
 int ht2gpu_close(ht2gpu_handle_t* h);
 

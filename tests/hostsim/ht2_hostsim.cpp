@@ -204,7 +204,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
 static int swSelfTest(int n, unsigned seed) {
     Ht2Params P; memset(&P, 0, sizeof(P));
     Ht2Work* W = new Ht2Work(); Ht2SwScratch* S = new Ht2SwScratch();
-    Ht2AlignerT<false> A; A.blob = NULL; A.H = NULL; A.P = &P; A.W = W; A.sw = S; A.swPl = new uint32_t[HT2_SW_POOL_WORDS]; A.swStride = 1;
+    Ht2AlignerT<false> A; A.blob = NULL; A.H = NULL; A.P = &P; A.W = W; A.sw = S; A.swPl = new uint32_t[HT2_SW_POOL_WORDS]; A.swStride = 1; A.swStage = 0;
     uint32_t rng = seed ? seed : 1;
     auto rnd = [&](uint32_t m) { rng = rng * 1664525u + 1013904223u; return (rng >> 8) % m; };
     int bad = 0; long cells = 0, traced = 0;

@@ -305,6 +305,17 @@ def test_bundled_graph_index_matches_reference_binary_run_here(h2, name, paired,
     index.close()
 
 
+def test_warp_wide_dp_fill_equals_lane_fill_cell_by_cell(h2):
+    """ht2_sw.h: the DP rounds of the pool kernel fill the score planes with a whole warp per problem (64 rows per
+    vector, lazy-F across lanes by shuffle).  On 3000 random problems (20..256 rows, random penalties, gap
+    barriers, N's, indels) every H, E and F cell, every last-row score and the best score must equal the lane
+    fill's, which the host self-test pins to a plain scalar statement of the recurrences (test_cpu.py)."""
+    from hisat2_b200 import api
+    r = api.sw_selftest(3000, seed=5)
+    assert r["problems"] == 3000 and r["cells"] > 3000 * 20 * 60 and r["valid"] > 300
+    assert r["mismatches"] == 0
+
+
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
 @pytest.mark.parametrize("index,name,paired,flags,opts", [
     ("22_20-21M", "hard20k", False, ["--bowtie2-dp", "2"], dict(bowtie2_dp=2)),

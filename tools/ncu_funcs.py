@@ -21,9 +21,12 @@ def main():
     labels = []
     insec = False
     cur = None
+    first = None
     for line in open(dis):
         if line.lstrip().startswith(".section"):
-            insec = (".text." in line) and (kname in line)
+            insec = (".text." in line) and (kname in line) and (first is None or first == line)
+            if insec:
+                first = line                              # one instantiation only: a looser substring would mix the offsets of several
             continue
         if not insec:
             continue
@@ -55,6 +58,22 @@ def main():
             if v:
                 d["stalls"][n] = d["stalls"].get(n, 0) + v
         tot_i += int(r[ii]); tot_s += int(r[isamp])
+    detail = __import__("os").environ.get("NCU_FUNC_DETAIL")
+    if detail:                                           # hottest SASS rows of the functions whose name contains $NCU_FUNC_DETAIL
+        isrc = h.index("Source")
+        hot = []
+        for r in data:
+            off = int(r[ia], 16) - a0
+            k = bisect.bisect_right(offs, off) - 1
+            name = labels[k][1] if k >= 0 else "?"
+            if detail in name:
+                st = sorted(((int(r[i]) if r[i].isdigit() else 0, n[6:]) for i, n in stall_cols), reverse=True)[:2]
+                hot.append((int(r[isamp]), off, int(r[ii]), r[isrc][:70], st))
+        tot = sum(x[0] for x in hot)
+        print("== %s: %d samples (%.1f%% of kernel), rows by offset with >= 0.5%% of the function's samples" % (detail, tot, 100.0 * tot / max(tot_s, 1)))
+        for smp, off, ninst, text, st in hot:
+            if smp >= 0.005 * tot:
+                print("  %06x  inst %10d  samples %7d (%4.1f%%)  %-70s %s" % (off, ninst, smp, 100.0 * smp / max(tot, 1), text, st))
     out = []
     for name, d in agg.items():
         st = sorted(d["stalls"].items(), key=lambda kv: -kv[1])[:4]
