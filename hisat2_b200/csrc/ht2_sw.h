@@ -279,13 +279,31 @@ HT2_NI uint32_t swCellFromPlanes(const uint8_t* rd, const uint8_t* rf, uint32_t 
     const int rfgapo = P->rfGapConst + P->rfGapLinear, rfgape = P->rfGapLinear;
     const uint32_t gapbar = (uint32_t)P->gapbar;
     const bool gb = (row < gapbar) || (nrow - 1 - row < gapbar);
-    const int h = swRaw(0, seg, row, col), e = swRaw(1, seg, row, col), f = swRaw(2, seg, row, col);
-    const int hup = swRaw(0, seg, row - 1, col), fup = swRaw(2, seg, row - 1, col);
+    int h, e, f, hup, fup, hleft = 0, eleft = 0, hd = 0;
+    if (S.coop) {
+        // warp-fill layout: all eight words are addressed first and loaded side by side -- the planes were written by
+        // other lanes, so every load is an L2 round trip, and a backtrace is a chain of ~nrow such cells
+        const uint32_t rw = (seg + 1) >> 1;
+        const uint32_t L = (row * S.rcp) >> 16, k = row - L * seg;
+        const uint32_t Lu = k ? L : L - 1, ku = k ? k - 1 : seg - 1;              // row - 1
+        const size_t a = ((size_t)(col + L) * 32 + L) * rw + (k >> 1), au = ((size_t)(col + Lu) * 32 + Lu) * rw + (ku >> 1);
+        const size_t back = (size_t)32 * rw;                                      // one column to the left = one step earlier
+        const uint32_t* const pH = swPl; const uint32_t* const pE = swPl + (size_t)HT2_SW_PLANE_WORDS; const uint32_t* const pF = pE + (size_t)HT2_SW_PLANE_WORDS;
+        const bool left = col > 0;
+        const uint32_t wh = pH[a], we = pE[a], wf = pF[a], whu = pH[au], wfu = pF[au];
+        const uint32_t whl = left ? pH[a - back] : 0u, wel = left ? pE[a - back] : 0u, whd = left ? pH[au - back] : 0u;
+        const uint32_t sh = 16 * (k & 1), su = 16 * (ku & 1);
+        h = (int)((wh >> sh) & 0xffffu); e = (int)((we >> sh) & 0xffffu); f = (int)((wf >> sh) & 0xffffu);
+        hup = (int)((whu >> su) & 0xffffu); fup = (int)((wfu >> su) & 0xffffu);
+        hleft = (int)((whl >> sh) & 0xffffu); eleft = (int)((wel >> sh) & 0xffffu); hd = (int)((whd >> su) & 0xffffu);
+    } else {
+        h = swRaw(0, seg, row, col); e = swRaw(1, seg, row, col); f = swRaw(2, seg, row, col);
+        hup = swRaw(0, seg, row - 1, col); fup = swRaw(2, seg, row - 1, col);
+        if (col > 0) { hleft = swRaw(0, seg, row, col - 1); eleft = swRaw(1, seg, row, col - 1); hd = swRaw(0, seg, row - 1, col - 1); }
+    }
     uint32_t hm = 0, em = 0, fm = 0;
     if (!gb) { if (h + rfgapo == hup) hm |= 1; if (h + rfgape == fup) hm |= 4; }
     if (col > 0) {
-        const int hleft = swRaw(0, seg, row, col - 1), eleft = swRaw(1, seg, row, col - 1);
-        const int hd = swRaw(0, seg, row - 1, col - 1);
         const int rdc = rd[row], refc = rf[col];
         const int pen = (rdc > 3 || refc > 3) ? P->npen : (rdc == refc ? 0 : (int)S.rowPen[row]);
         if (!gb) { if (h + rdgapo == hleft) hm |= 2; if (h + rdgape == eleft) hm |= 8; }
@@ -297,18 +315,6 @@ HT2_NI uint32_t swCellFromPlanes(const uint8_t* rd, const uint8_t* rf, uint32_t 
     if (fup - rfgape == f) fm |= 2;
     return hm | (em << 5) | (fm << 7) | (hm ? HT2_SWM_OH : 0) | (em ? HT2_SWM_OE : 0) | (fm ? HT2_SWM_OF : 0);
 }
-HT2_NI uint32_t swGetCell(const uint8_t* rd, const uint8_t* rf, uint32_t row, uint32_t col) const {
-    const Ht2SwScratch& S = *sw;
-    const uint32_t bit = col * S.nrow + row;
-    if ((S.rep[bit >> 5] >> (bit & 31)) & 1u) return HT2_SWM_REP;
-    return row > 0 ? swCellFromPlanes(rd, rf, row, col) : 0;
-}
-HT2_HD void swMarkCell(uint32_t row, uint32_t col) {
-    Ht2SwScratch& S = *sw;
-    const uint32_t bit = col * S.nrow + row;
-    S.rep[bit >> 5] |= 1u << (bit & 31);
-}
-
 // One backtrace (aligner_swsse_ee_u8.cpp:1309-1902).  Edits land in S.ned (left to right).
 HT2_NI bool swBacktrace(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, const uint8_t* rf, const SwRect& rect, int nceil,
                         uint32_t row, uint32_t col, uint32_t& nedOut, uint32_t& offOut, int64_t& scoreOut) {
@@ -322,7 +328,10 @@ HT2_NI bool swBacktrace(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, con
     int64_t score = 0; int ns = 0;
     bool ovl = false;
     for (;;) {
-        const uint32_t cell = swGetCell(rd, rf, row, col);
+        const uint32_t bit = col * S.nrow + row;
+        const uint32_t repw = S.rep[bit >> 5];                                   // read once: reported-through test here, mark below
+        const uint32_t planes = row > 0 ? swCellFromPlanes(rd, rf, row, col) : 0u;
+        const uint32_t cell = ((repw >> (bit & 31)) & 1u) ? (uint32_t)HT2_SWM_REP : planes;
         bool empty = false, canMoveThru = true;
         int cur = -1;
         if (cell & HT2_SWM_REP) canMoveThru = false;
@@ -350,7 +359,7 @@ HT2_NI bool swBacktrace(const uint8_t* rd, const uint8_t* qu, uint32_t nrow, con
                 } else { empty = true; canMoveThru = (cell & HT2_SWM_OH) == 0; }
             }
         }
-        swMarkCell(row, col);
+        S.rep[bit >> 5] = repw | (1u << (bit & 31));
         if (!canMoveThru) return false;
         {   // the cell joins the path: does it sit on a core diagonal?
             int64_t diagi = (int64_t)col - (int64_t)row + (int64_t)rect.triml;
@@ -492,7 +501,7 @@ HT2_NI bool swFinish(uint32_t rdi, Ht2Hit& gh) {
         }
         if (!got) return false;
         prevScore = cs; prevCol = cc; havePrev = true;
-        if (swGetCell(rd, rf, rdlen - 1, cc) & HT2_SWM_REP) continue;   // starting cell already covered
+        { const uint32_t bit = cc * S.nrow + (rdlen - 1); if ((S.rep[bit >> 5] >> (bit & 31)) & 1u) continue; }   // starting cell already covered
         uint32_t reseed = W->rnd.nextU32() + 1;
         if (!use16) W->rnd.init(reseed);
         uint32_t ned = 0, off = 0; int64_t score = 0;

@@ -9,8 +9,8 @@ prof() {  # name kernel-substring env-index reads extra-opts...
   python tools/ncu_funcs.py /tmp/${name}_source.csv.gz /tmp/cubx/all.sass $ksub $O/${name}_functions.json > $O/${name}_functions.txt 2>&1
   python tools/ncu_summary.py /tmp/$name.ncu-rep $O/${name}_summary.json "$name" > /dev/null 2>&1
 }
-prof pool_linear_1M ht2_align_pool_kernelILi8ELi4ELb0E 22_20-21M synth:1000000
-prof pool_graph_500k ht2_align_pool_kernelILi8ELi4ELb1E 22_20-21M_snp synth:500000
-prof pool_dp2_200k ht2_align_pool_kernelILi8ELi4ELb0E 22_20-21M synth:200000 bowtie2_dp=2
+prof pool_linear_1M ht2_align_pool_kernelILi8ELi4ELb0ELb1E 22_20-21M synth:1000000
+prof pool_graph_500k ht2_align_pool_kernelILi8ELi4ELb1ELb1E 22_20-21M_snp synth:500000
+prof pool_dp2_200k ht2_align_pool_kernelILi8ELi4ELb0ELb1E 22_20-21M synth:200000 bowtie2_dp=2
 ncu --set full --clock-control none -k regex:ht2_sam_kernel -c 2 -o /tmp/sam_1M python tools/prof_run.py synth:1000000 1 > $O/ncu_sam.log 2>&1
 ncu -i /tmp/sam_1M.ncu-rep --page raw --csv > $O/sam_1M_raw.csv 2>/dev/null
