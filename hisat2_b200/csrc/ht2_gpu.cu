@@ -37,6 +37,7 @@ struct DevBatch {
     Ht2SwScratch*   sw;     // --bowtie2-dp scratch, one per launched thread (NULL when dp is off)
     uint32_t*       swPool; // ... and the H / E / F plane pool: HT2_SW_POOL_WORDS words per thread, interleaved per warp
     const int32_t*  minscTab; // --score-min per read length (Ht2Params::minscTab)
+    uint32_t        elect;    // a warp stays on the block's current target state while it has at least this many claimable slots
 #ifdef HT2_ENABLE_SPLICED
     const Ht2SplTables* splT; // donor / acceptor probability tables (spliced mode)
 #endif
@@ -315,7 +316,7 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
             // every decision below is made warp-uniform (the counters change under our feet)
             T = __shfl_sync(0xffffffffu, *(volatile unsigned int*)&sTarget, 0);
             const int cT = __shfl_sync(0xffffffffu, vCount[T], 0);
-            if (cT < 32) {
+            if (cT < (int)b.elect) {
                 // elect the most populous claimable state
                 if (c0 < 0) c0 = 0;
                 if (c1 < 0) c1 = 0;
@@ -1030,6 +1031,7 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
     DevBatch db;
     db.seq = S.dSeq; db.qual = b->qual ? S.dQual : NULL; db.offs = S.dOffs; db.seeds = S.dSeeds;
     db.n_units = units; db.paired = b->paired; db.sw = h->P.bowtie2Dp ? wp->dSw : NULL; db.swPool = h->P.bowtie2Dp ? wp->dSwPool : NULL; db.minscTab = h->dMinsc;
+    { static const int e = getenv("HT2GPU_ELECT") ? atoi(getenv("HT2GPU_ELECT")) : 8; db.elect = (uint32_t)(e < 1 ? 1 : (e > 32 ? 32 : e)); }
 #ifdef HT2_ENABLE_SPLICED
     db.splT = (const Ht2SplTables*)h->dSplT;
 #endif
@@ -1464,7 +1466,7 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     rc = uploadBatch(h, S, b, NULL, NULL, 0, h2d);
     if (rc) return rc;
     DevBatch db;
-    db.seq = S.dSeq; db.qual = NULL; db.offs = S.dOffs; db.seeds = S.dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.swPool = NULL; db.minscTab = h->dMinsc;
+    db.seq = S.dSeq; db.qual = NULL; db.offs = S.dOffs; db.seeds = S.dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.swPool = NULL; db.minscTab = h->dMinsc; db.elect = 32;
 #ifdef HT2_ENABLE_SPLICED
     db.splT = NULL;
 #endif
