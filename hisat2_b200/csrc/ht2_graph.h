@@ -88,7 +88,7 @@ HT2_HD uint32_t ht2g_select64(uint64_t x, uint32_t n) {
 
 // Row of the count-th (>= 1) set F bit at or after 'row' (select_F walks forward across sides).
 template <typename IT>
-HT2_HD uint32_t ht2g_select_F(const Ht2Fm<IT>& fm, uint32_t row, uint32_t count) {
+HT2_NI uint32_t ht2g_select_F(const Ht2Fm<IT>& fm, uint32_t row, uint32_t count) {
     uint32_t s = row >> HT2_SIDE_SHIFT;
     const uint32_t lastSide = fm.g->numSides;    // one zeroed slack side follows the last side
     uint64_t bits = ((const Ht2GSide*)(fm.gfm + ((uint64_t)s << 6)))->F >> (row & (HT2_SIDE_CHARS - 1));
@@ -148,7 +148,7 @@ HT2_HD uint32_t ht2g_in_edge_count(const Ht2Fm<IT>& fm, uint32_t top, uint32_t b
 
 // GFM::mapGLF.  k = kseeds: the in-edge list is only built for node ranges <= k.
 template <typename IT>
-HT2_HD void ht2g_mapGLF(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c, uint32_t k,
+HT2_NI void ht2g_mapGLF(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c, uint32_t k,
                         uint32_t& ntop, uint32_t& nbot, uint32_t& node_top, uint32_t& node_bot,
                         uint16_t (*iedges)[2], uint32_t& niedges, bool& overflow) {
     niedges = 0;
@@ -171,7 +171,7 @@ HT2_HD void ht2g_mapGLF(const Ht2Fm<IT>& fm, uint32_t top, uint32_t bot, int c, 
 
 // GFM::mapGLF1(row, l, c): one-row range extended with base c.
 template <typename IT>
-HT2_HD void ht2g_mapGLF1c(const Ht2Fm<IT>& fm, uint32_t row, int c,
+HT2_NI void ht2g_mapGLF1c(const Ht2Fm<IT>& fm, uint32_t row, int c,
                           uint32_t& ntop, uint32_t& nbot, uint32_t& node_top, uint32_t& node_bot) {
     if (ht2g_rowL(fm, row) != c || ht2g_is_zoff(fm, row)) { ntop = nbot = node_top = node_bot = 0; return; }
     const uint32_t t = ht2g_lf(fm, row, c);
@@ -183,7 +183,7 @@ HT2_HD void ht2g_mapGLF1c(const Ht2Fm<IT>& fm, uint32_t row, int c,
 
 // GFM::mapGLF1(row, l): follow the row's own character.  Returns false on a '$' row.
 template <typename IT>
-HT2_HD bool ht2g_mapGLF1(const Ht2Fm<IT>& fm, uint32_t row, uint32_t& ntop, uint32_t& node_top) {
+HT2_NI bool ht2g_mapGLF1(const Ht2Fm<IT>& fm, uint32_t row, uint32_t& ntop, uint32_t& node_top) {
     if (ht2g_is_zoff(fm, row)) return false;
     const int c = ht2g_rowL(fm, row);
     const uint32_t t = ht2g_lf(fm, row, c);
@@ -194,7 +194,7 @@ HT2_HD bool ht2g_mapGLF1(const Ht2Fm<IT>& fm, uint32_t row, uint32_t& ntop, uint
 
 // GFM::getOffset(row, node): joined-text offset of a node reached through BW row 'row'.
 template <typename IT>
-HT2_HD uint32_t ht2g_get_offset(const Ht2Fm<IT>& fm, uint32_t row, uint32_t node, uint32_t& nsteps) {
+HT2_NI uint32_t ht2g_get_offset(const Ht2Fm<IT>& fm, uint32_t row, uint32_t node, uint32_t& nsteps) {
     nsteps = 0;
     if (ht2g_is_zoff(fm, row)) return 0;
     if ((node & fm.offMask) == node) {
