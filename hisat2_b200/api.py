@@ -86,7 +86,7 @@ EXPORTS = [
     "ht2gpu_seed_search", "ht2gpu_free_seed_results", "ht2gpu_index_is_graph",
     "ht2gpu_sam_slots", "ht2gpu_submit_sam", "ht2gpu_wait_sam", "ht2gpu_align_sam", "ht2gpu_run_reads",
     "ht2gpu_host_alloc", "ht2gpu_host_free", "ht2gpu_set_error", "ht2gpu_parse_reads", "ht2gpu_free_parsed",
-    "ht2gpu_ctx_get", "ht2gpu_ctx_set", "ht2gpu_run_reads_multi", "ht2gpu_open_peer", "ht2gpu_sw_selftest",
+    "ht2gpu_ctx_get", "ht2gpu_ctx_set", "ht2gpu_run_reads_multi", "ht2gpu_open_peer", "ht2gpu_sw_selftest", "ht2gpu_load_splicesites",
 ]
 
 
@@ -152,6 +152,7 @@ def load_library(path=None):
     lib.ht2gpu_parse_reads.argtypes = [C.POINTER(CReadsInput), C.POINTER(CParsedReads), C.c_char_p, C.c_size_t]
     lib.ht2gpu_free_parsed.argtypes = [C.POINTER(CParsedReads)]
     lib.ht2gpu_sw_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.ht2gpu_load_splicesites.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint32)]
     if path is None:
         _lib = lib
     return lib
@@ -496,6 +497,13 @@ class Index(object):
         if with_stats:
             return s, {k: getattr(cr, k) for k, _ in CSamResult._fields_ if k != "sam"}
         return s
+
+    def load_splicesites(self, known=None, novel=None):
+        """ht2gpu_load_splicesites: --known-splicesite-infile / --novel-splicesite-infile; returns the number of sites kept."""
+        n = C.c_uint32(0)
+        self._check(self._lib.ht2gpu_load_splicesites(self._h, known.encode() if known else None, novel.encode() if novel else None, C.byref(n)),
+                    "ht2gpu_load_splicesites")
+        return int(n.value)
 
     def peer(self, device):
         """ht2gpu_open_peer: a replica of this index on another device of this process (device-to-device copy)."""

@@ -19,6 +19,7 @@
 #include "ht2_seed.h"
 #include "ht2_gwalk.h"
 #include "ht2_params.h"
+#include "ht2_ssdb.h"
 
 #ifndef HT2_MAX_RDLEN
 #define HT2_MAX_RDLEN 1024
@@ -77,7 +78,7 @@ struct Ht2Edit {          // edit.h:41-330
     uint8_t  pad;
     uint32_t snpID;
 };
-enum { HT2_SPL_UNKNOWN = 1, HT2_SPL_FW, HT2_SPL_RC, HT2_SPL_SEMI_FW, HT2_SPL_SEMI_RC };   // splice_site.h:37-43
+// HT2_SPL_* direction codes: ht2_ssdb.h (splice_site.h:37-43)
 // A splice edit (type HT2_EDIT_SPL; spliced alignment, host test build only for now) keeps the
 // same 12 bytes: intron length (20 bits) in chr | qchr << 8 | (pad & 15) << 16, direction in pad bits 4-6,
 // "known site" in pad bit 7, and -- instead of the reference's donor / acceptor context words, whose only
@@ -184,6 +185,7 @@ struct Ht2Frame {
     const Ht2Hit* hit;
     Ht2Hit*  tempHit;
     uint32_t hitoff, hitlen, dep, count, extoff, extlen, ncoords, nLocalHits, ti, poolMark;
+    uint32_t ssi, ssHi;       // cursor over the splice-site DB's sites of this activation (ssi == 0xffffffff: range not computed yet)
     int32_t  lid, ri;
     int64_t  maxsc, prev_score, cushion;
     Ht2Coord coords[8];
@@ -489,6 +491,7 @@ struct Ht2AlignerT {
     bool                  swRetv;
 #ifdef HT2_ENABLE_SPLICED
     const Ht2SplTables*   splT;    // donor / acceptor probability tables (spliced mode)
+    const uint8_t*        ssT;     // read-only splice-site DB of the run (ht2_ssdb.h), NULL = empty (SpliceSiteDB::empty())
 #endif
     bool     paired;
     bool     rightendonly;
@@ -515,7 +518,7 @@ struct Ht2AlignerT {
         W = W_;
         sw = NULL; swPl = NULL; swStride = 1; swStage = 0; swRetv = false;
 #ifdef HT2_ENABLE_SPLICED
-        splT = NULL;
+        splT = NULL; ssT = NULL;
 #endif
     }
 
@@ -588,6 +591,62 @@ struct Ht2AlignerT {
         if (W->poolTop + 1 > W->maxPool) W->maxPool = W->poolTop + 1;
         return &W->pool[W->poolTop++];
     }
+
+
+#ifdef HT2_ENABLE_SPLICED
+    // ---- the run's splice-site DB (ht2_ssdb.h) ---------------------------------
+    HT2_HD bool ssdbEmpty() const { return ssT == NULL; }   // SpliceSiteDB::empty(): false once a file was read, even one without sites
+    // GenomeHit::getLeftAnchor / getRightAnchor (hi_aligner.h:1040-1079)
+    HT2_HD static void getLeftAnchor(const Ht2Hit& h, uint32_t& anchor, uint32_t& nedits) {
+        anchor = h.len; nedits = 0;
+        for (uint32_t i = 0; i < h.nedits; i++) {
+            const Ht2Edit& e = h.edits[i];
+            if (e.type == HT2_EDIT_SPL) { anchor = e.pos; break; }
+            else if (e.type == HT2_EDIT_MM || e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_REF_GAP) nedits++;
+        }
+    }
+    HT2_HD static void getRightAnchor(const Ht2Hit& h, uint32_t& anchor, uint32_t& nedits) {
+        anchor = h.len; nedits = 0;
+        for (int i = (int)h.nedits - 1; i >= 0; i--) {
+            const Ht2Edit& e = h.edits[i];
+            if (e.type == HT2_EDIT_SPL) { anchor = h.len - e.pos - 1; break; }
+            else if (e.type == HT2_EDIT_MM || e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_REF_GAP) nedits++;
+        }
+    }
+    // GFM::textOffToJoined (gfm.h:5603-5650): (reference, offset) -> offset in the joined text; false inside an N gap
+    HT2_NI bool textOffToJoined(uint32_t tid, uint32_t textoff, uint32_t& off) const {
+        const uint32_t nFrag = gfm.g->nFrag;
+        const uint32_t* rs = gfm.rstarts;
+        uint32_t top = 0, bot = nFrag, elt = HT2_IDX_MAX32;
+        while (true) {
+            const uint32_t oldelt = elt;
+            elt = top + ((bot - top) >> 1);
+            if (oldelt == elt) return false;
+            const uint32_t elt_tid = rs[elt * 3 + 1];
+            if (elt_tid == tid) {
+                while (true) {
+                    if (tid != rs[elt * 3 + 1]) return false;
+                    if (rs[elt * 3 + 2] <= textoff) break;
+                    if (elt == 0) return false;
+                    elt--;
+                }
+                while (true) {
+                    if (elt + 1 == nFrag || tid + 1 == rs[(elt + 1) * 3 + 1] || textoff < rs[(elt + 1) * 3 + 2]) {
+                        off = rs[elt * 3] + (textoff - rs[elt * 3 + 2]);
+                        if (elt + 1 < nFrag && tid == rs[(elt + 1) * 3 + 1] && off >= rs[(elt + 1) * 3]) return false;
+                        break;
+                    }
+                    elt++;
+                }
+                break;
+            } else if (elt_tid < tid) top = elt;
+            else bot = elt;
+        }
+        return true;
+    }
+#else
+    HT2_HD bool ssdbEmpty() const { return true; }
+#endif
 
     // GenomeHit::getLeft (hi_aligner.h:919-957)
     HT2_NI void getLeft(const Ht2Hit& h, uint32_t& rdoff, uint32_t& len, uint32_t& toff, int64_t* score, uint32_t rdi) const {
@@ -1349,7 +1408,7 @@ struct Ht2AlignerT {
 
     // GenomeHit::combineWith (hi_aligner.h:1420-2025), non-spliced paths
     // (splicing is rejected under --no-spliced-alignment, :1500-1502).
-    HT2_NI bool combineWith(Ht2Hit& a, const Ht2Hit& o, uint32_t rdi, int64_t minsc_) {
+    HT2_NI bool combineWith(Ht2Hit& a, const Ht2Hit& o, uint32_t rdi, int64_t minsc_, const Ht2SsSite* spliceSite = NULL) {
         if (&a == &o) return false;
         uint32_t this_rdoff, this_len, this_toff, other_rdoff, other_len, other_toff;
         int64_t this_score, other_score;
@@ -1433,6 +1492,10 @@ struct Ht2AlignerT {
                 if (ts2[i2] < remainsc) break;
             }
             int i2_limit = i2 > 0 ? i2 : 0;
+            if (spliceSite != NULL) {   // a site of the splice-site DB: only its own split point is tried (hi_aligner.h:1626-1634)
+                if (i2_limit <= (int)(spliceSite->left - this_toff)) { i2_limit = (int)(spliceSite->left - this_toff); i_limit = i2_limit + 1; }
+                else i_limit = i2_limit;
+            }
             for (i = i2_limit, i2 = i2_limit + 1; i < i_limit && i2 < (int)len; i++, i2++) {
                 int64_t tempscore = ts[i] + ts2[i2];
                 int donor = 0xff, acceptor = 0xff;   // (char)0xff in the reference: compares unequal to every motif
@@ -1476,7 +1539,7 @@ struct Ht2AlignerT {
                 }
             }
             if (maxscore == HT2_MIN_I64) return false;
-            {
+            if (spliceSite == NULL) {   // hi_aligner.h:1797
                 uint32_t shorter_anchor_len = maxscorei + 1 < len - maxscorei - 1 ? maxscorei + 1 : len - maxscorei - 1;
                 if (maxspldir == HT2_SPL_SEMI_FW || maxspldir == HT2_SPL_SEMI_RC || maxspldir == HT2_SPL_UNKNOWN) {
                     if (shorter_anchor_len < P->minAnchorLenNoncan) {
@@ -1546,7 +1609,7 @@ struct Ht2AlignerT {
                     uint32_t right = other_toff + other_len - (len - i - 1);
                     Ht2Edit e = mkEdit(i + 1 + addoff, 'A', 'A', HT2_EDIT_SPL);
                     if (right - left > HT2_MAX_SPL_LEN) { W->err |= HT2_ERR_SPLICE; return false; }
-                    ht2_spl_set(e, right - left, maxspldir, false, ht2_spl_probscore(*splT, donor_seq, acceptor_seq));
+                    ht2_spl_set(e, right - left, maxspldir, spliceSite != NULL, ht2_spl_probscore(*splT, donor_seq, acceptor_seq));
                     if (!pushEdit(a, e)) return false;
                 }
             }

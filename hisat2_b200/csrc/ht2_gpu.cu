@@ -40,6 +40,7 @@ struct DevBatch {
     uint32_t        elect;    // a warp stays on the block's current target state while it has at least this many claimable slots
 #ifdef HT2_ENABLE_SPLICED
     const Ht2SplTables* splT; // donor / acceptor probability tables (spliced mode)
+    const uint8_t*  ssT;      // the run's splice-site DB (ht2_ssdb.h) or NULL
 #endif
 };
 
@@ -295,7 +296,7 @@ ht2_align_pool_kernel(const uint8_t* __restrict__ blob, Ht2ParamsCore P, DevBatc
     A.swPl = b.swPool ? b.swPool + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)HT2_SW_POOL_WORDS : NULL;
     A.swStride = 1;
 #ifdef HT2_ENABLE_SPLICED
-    A.splT = b.splT;
+    A.splT = b.splT; A.ssT = b.ssT;
 #endif
     __syncthreads();
     volatile int* vCount = sCount;
@@ -642,6 +643,8 @@ struct ht2gpu_handle {
     int            rgK;
     int32_t*       dMinsc;   // --score-min table on the device (Ht2Params::minscTab)
     void*          dSplT;    // spliced builds: Ht2SplTables on the device
+    uint8_t*       dSsT;     // the run's splice-site DB on the device (ht2gpu_load_splicesites) or NULL
+    std::vector<uint8_t> ssBlob;   // ... and its host copy (host formatter)
     size_t         nWork;
     cudaStream_t   stream;
     cudaEvent_t    ev[4];
@@ -795,7 +798,7 @@ static int finishOpen(ht2gpu_handle* h)
 static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
-    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->pool = NULL; h->nWork = 0; h->dMinsc = NULL; h->dSplT = NULL;
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->pool = NULL; h->nWork = 0; h->dMinsc = NULL; h->dSplT = NULL; h->dSsT = NULL;
     h->stream = 0;
     h->dStats = NULL;
     memset((void*)h->slots, 0, sizeof(h->slots));
@@ -932,6 +935,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
     }
     if (h->dMinsc) cudaFree(h->dMinsc);
     if (h->dSplT) cudaFree(h->dSplT);
+    if (h->dSsT) cudaFree(h->dSsT);
     cudaFree(h->dStats);
     for (int k = 0; k < HT2GPU_N_SLOTS; k++) {
         SamSlot& S = h->slots[k];
@@ -1033,7 +1037,7 @@ static int launchAlign(ht2gpu_handle* h, SamSlot& S, const ht2gpu_read_batch_t* 
     db.n_units = units; db.paired = b->paired; db.sw = h->P.bowtie2Dp ? wp->dSw : NULL; db.swPool = h->P.bowtie2Dp ? wp->dSwPool : NULL; db.minscTab = h->dMinsc;
     { static const int e = getenv("HT2GPU_ELECT") ? atoi(getenv("HT2GPU_ELECT")) : 8; db.elect = (uint32_t)(e < 1 ? 1 : (e > 32 ? 32 : e)); }
 #ifdef HT2_ENABLE_SPLICED
-    db.splT = (const Ht2SplTables*)h->dSplT;
+    db.splT = (const Ht2SplTables*)h->dSplT; db.ssT = h->dSsT;
 #endif
     DevOut o;
     o.reads = S.dReads; o.alns = S.dAlns; o.edits = S.dEdits; o.pairs = S.dPairs;
@@ -1070,7 +1074,8 @@ static void dumpStats(ht2gpu_handle* h)
     static const char* frN[] = {"ENTER", "L_START", "L_WHILE", "L_COORD", "L_COORD_RET", "L_WHILE_TAIL", "L_STASH", "L_STASH_RET",
                                 "L_AFTER_WHILE", "L_GCOORD", "L_GCOORD_RET", "L_TRIM", "L_TRIM_RET", "L_EXT", "R_START", "R_WHILE",
                                 "R_COORD", "R_COORD_RET", "R_WHILE_TAIL", "R_STASH", "R_STASH_RET", "R_AFTER_WHILE", "R_GCOORD",
-                                "R_GCOORD_RET", "R_TRIM", "R_TRIM_RET", "R_EXT", "FINAL_RET", "RETURN", "L_COMBINE", "L_GCOMBINE", "R_COMBINE", "R_GCOMBINE"};
+                                "R_GCOORD_RET", "R_TRIM", "R_TRIM_RET", "R_EXT", "FINAL_RET", "RETURN", "L_COMBINE", "L_GCOMBINE", "R_COMBINE", "R_GCOMBINE",
+                                "SS_FULL", "L_SS", "L_SS_RET", "R_SS", "R_SS_RET"};
     std::vector<unsigned long long> st(1024 + 256 * 12);
     if (cudaMemcpy(st.data(), h->dStats, st.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
     cudaMemset(h->dStats, 0, st.size() * 8);
@@ -1083,7 +1088,7 @@ static void dumpStats(ht2gpu_handle* h)
         if (c == 0) snprintf(nm, sizeof nm, "NEED");
         else if (c == 1) snprintf(nm, sizeof nm, "FINISH");
         else if (c < 20) snprintf(nm, sizeof nm, "T_%s", c - 2 < 17 ? topN[c - 2] : "?");
-        else snprintf(nm, sizeof nm, "F_%s", c - 20 < 33 ? frN[c - 20] : "?");
+        else snprintf(nm, sizeof nm, "F_%s", c - 20 < 38 ? frN[c - 20] : "?");
         fprintf(stderr, "%-16s %10llu %7.2f %10.0f %9llu %6.2f |", nm, st[c * 4], (double)st[c * 4 + 1] / st[c * 4],
                 (double)st[c * 4 + 2] / st[c * 4], st[c * 4 + 3], 100.0 * st[c * 4 + 2] / (totC ? totC : 1));
         // cycles per round by group size: 1, 2-3, 4-7, 8-15, 16-31, 32 lanes
@@ -1209,7 +1214,7 @@ static Ht2SamIn samIn(const ht2gpu_handle* h, const SamSlot& S)
     in.seq = S.dSeq; in.qual = S.batch.qual ? S.dQual : NULL; in.offs = S.dOffs; in.names = S.dNames; in.nameOffs = S.dNameOffs;
     in.n_reads = S.batch.n_reads; in.paired = S.batch.paired;
     in.reads = S.dReads; in.alns = S.dAlns; in.edits = S.dEdits; in.pairs = S.dPairs;
-    in.khits = h->P.khits; in.secondary = h->P.secondary; in.mixed = h->P.mixed; in.discord = h->P.discord;
+    in.khits = h->P.khits; in.secondary = h->P.secondary; in.mixed = h->P.mixed; in.discord = h->P.discord; in.ssT = h->dSsT;
     return in;
 }
 
@@ -1468,7 +1473,7 @@ extern "C" int ht2gpu_seed_search(ht2gpu_handle_t* h, const ht2gpu_read_batch_t*
     DevBatch db;
     db.seq = S.dSeq; db.qual = NULL; db.offs = S.dOffs; db.seeds = S.dSeeds; db.n_units = n; db.paired = 0; db.sw = NULL; db.swPool = NULL; db.minscTab = h->dMinsc; db.elect = 32;
 #ifdef HT2_ENABLE_SPLICED
-    db.splT = NULL;
+    db.splT = NULL; db.ssT = NULL;
 #endif
     DevTmp tmp;
     uint32_t *dCounts = NULL, *dOffs3 = NULL;
@@ -1548,11 +1553,38 @@ extern "C" int ht2gpu_sam_header(ht2gpu_handle_t* h, char** out, size_t* out_len
 }
 extern "C" void ht2gpu_free_text(char* p) { free(p); }
 
+// The run's read-only splice-site DB: --known-splicesite-infile / --novel-splicesite-infile (hisat2.cpp:4101-4116,
+// SpliceSiteDB::read splice_site.cpp:727).  Replaces a DB loaded earlier.  Call between batches, not during one.
+extern "C" int ht2gpu_load_splicesites(ht2gpu_handle_t* h, const char* known_path, const char* novel_path, uint32_t* n_sites)
+{
+    if (!h) return HT2GPU_ERR_ARG;
+#ifdef HT2_ENABLE_SPLICED
+    std::vector<Ht2SsFile> files;
+    if (known_path && *known_path) files.push_back({known_path, true});
+    if (novel_path && *novel_path) files.push_back({novel_path, false});
+    if (h->dSsT) { cudaFree(h->dSsT); h->dSsT = NULL; }
+    h->ssBlob.clear();
+    if (n_sites) *n_sites = 0;
+    if (files.empty()) return HT2GPU_OK;
+    for (const Ht2SsFile& f : files) { FILE* t = fopen(f.path.c_str(), "rb"); if (!t) { h->err = "ht2gpu: cannot open " + f.path; return HT2GPU_ERR_INDEX; } fclose(t); }
+    std::string err; uint32_t ns = 0;
+    if (!ht2_ssdb_build(*h->img, files, h->ssBlob, ns, err)) { h->err = err; h->ssBlob.clear(); return HT2GPU_ERR_INDEX; }
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(&h->dSsT, h->ssBlob.size()));
+    CK(cudaMemcpy(h->dSsT, h->ssBlob.data(), h->ssBlob.size(), cudaMemcpyHostToDevice));
+    if (n_sites) *n_sites = ns;
+    return HT2GPU_OK;
+#else
+    (void)known_path; (void)novel_path; (void)n_sites;
+    h->err = "ht2gpu: built without spliced alignment"; return HT2GPU_ERR_UNSUPPORTED;
+#endif
+}
+
 extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, const char* names,
                                  const ht2gpu_result_batch_t* res, char** out, size_t* out_len)
 {
     if (!h || !b || !res || !names || !out) return HT2GPU_ERR_ARG;
     unsigned nth = std::thread::hardware_concurrency();
     if (const char* e = getenv("HT2GPU_THREADS")) nth = (unsigned)atoi(e);
-    return ht2_format_batch(*h->img, h->P, b, names, res, out, out_len, nth) ? HT2GPU_OK : HT2GPU_ERR_ARG;
+    return ht2_format_batch(*h->img, h->P, b, names, res, out, out_len, nth, h->ssBlob.empty() ? NULL : h->ssBlob.data()) ? HT2GPU_OK : HT2GPU_ERR_ARG;
 }

@@ -510,3 +510,63 @@ Ht2Image* ht2_image_load(const char* base_c, std::string& err)
         return nullptr;
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Splice-site DB blob (ht2_ssdb.h)
+// ---------------------------------------------------------------------------------------------------------------
+#include "ht2_ssdb.h"
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include <set>
+#include <tuple>
+bool ht2_ssdb_build(const Ht2Image& img, const std::vector<Ht2SsFile>& files, std::vector<uint8_t>& blob, uint32_t& nSites, std::string& err)
+{
+    const uint32_t nRefs = img.header()->nRefs;
+    std::vector<std::string> names(nRefs);
+    for (uint32_t r = 0; r < nRefs; r++) {
+        const char* n = img.refName(r);
+        size_t i = 0;
+        while (n[i] && !isspace((unsigned char)n[i])) i++;
+        names[r].assign(n, i);
+    }
+    std::vector<std::vector<Ht2SsSite>> per(nRefs);
+    std::vector<std::set<std::tuple<uint32_t, uint32_t, uint32_t>>> seen(nRefs);
+    for (const Ht2SsFile& f : files) {
+        std::ifstream in(f.path.c_str(), std::ios::in);
+        if (!in.is_open()) continue;
+        std::string refname, sl, sr, sd;
+        while (in >> refname) {
+            if (!(in >> sl >> sr >> sd)) { err = "ht2: truncated splice-site record in " + f.path; return false; }
+            char* e1 = NULL; char* e2 = NULL;
+            const unsigned long long l = strtoull(sl.c_str(), &e1, 10), r = strtoull(sr.c_str(), &e2, 10);
+            if (*e1 || *e2 || l > 0xfffffffeull || r > 0xfffffffeull) { err = "ht2: malformed splice-site record in " + f.path + ": " + refname + " " + sl + " " + sr; return false; }
+            uint32_t ref = 0;
+            for (; ref < nRefs; ref++) if (names[ref] == refname) break;
+            if (ref >= nRefs) continue;
+            Ht2SsSite s; s.left = (uint32_t)l; s.right = (uint32_t)r; s.dir = sd[0] == '+' ? HT2_SPL_FW : HT2_SPL_RC; s.known = f.known ? 1u : 0u;
+            if (seen[ref].insert(std::make_tuple(s.left, s.right, s.dir)).second) per[ref].push_back(s);   // a site already present is dropped (_fwIndex->add fails)
+        }
+    }
+    nSites = 0;
+    for (auto& v : per) nSites += (uint32_t)v.size();
+    const size_t offWords = ((size_t)nRefs + 1 + 3) & ~(size_t)3;
+    blob.assign(sizeof(Ht2SsHeader) + offWords * 4 + (size_t)nSites * 2 * sizeof(Ht2SsSite), 0);
+    Ht2SsHeader* h = (Ht2SsHeader*)blob.data();
+    h->magic = HT2_SS_MAGIC; h->nRefs = nRefs; h->nSites = nSites; h->pad = 0;
+    uint32_t* refOff = (uint32_t*)(blob.data() + sizeof(Ht2SsHeader));
+    Ht2SsSite* fw = (Ht2SsSite*)(blob.data() + sizeof(Ht2SsHeader) + offWords * 4);
+    Ht2SsSite* bw = fw + nSites;
+    uint32_t at = 0;
+    for (uint32_t r = 0; r < nRefs; r++) {
+        refOff[r] = at;
+        std::vector<Ht2SsSite> a = per[r], b = per[r];
+        std::sort(a.begin(), a.end(), [](const Ht2SsSite& x, const Ht2SsSite& y) { return x.left != y.left ? x.left < y.left : (x.right != y.right ? x.right < y.right : x.dir < y.dir); });
+        std::sort(b.begin(), b.end(), [](const Ht2SsSite& x, const Ht2SsSite& y) { return x.right != y.right ? x.right < y.right : (x.left != y.left ? x.left < y.left : x.dir < y.dir); });
+        for (size_t i = 0; i < a.size(); i++) { fw[at + i] = a[i]; bw[at + i] = b[i]; }
+        at += (uint32_t)a.size();
+    }
+    refOff[nRefs] = at;
+    return true;
+}

@@ -21,4 +21,12 @@ struct Ht2Image {
 // Parse <base>.[1-8].ht2 into an image.  Returns NULL and sets 'err' on failure.
 Ht2Image* ht2_image_load(const char* base, std::string& err);
 
+// The read-only splice-site DB of a run (ht2_ssdb.h) from the text files of --known-splicesite-infile ('known' = true)
+// and --novel-splicesite-infile (false): "<chr> <left> <right> <+|->" per site, 0-based, as hisat2_extract_splice_sites.py
+// writes them (SpliceSiteDB::read, splice_site.cpp:727-775: names compared up to the first white space, unknown
+// names skipped, a site already present is dropped).  Files are read in the order given.  An unreadable file is
+// skipped like the reference does (hisat2.cpp:4101-4116); a malformed one is an error.
+struct Ht2SsFile { std::string path; bool known; };
+bool ht2_ssdb_build(const Ht2Image& img, const std::vector<Ht2SsFile>& files, std::vector<uint8_t>& blob, uint32_t& nSites, std::string& err);
+
 #endif

@@ -30,7 +30,9 @@ enum {
     F_FINAL_RET, F_RETURN,
     // the expensive half of the four *COORD states (extend + combineWith): its own states, so that a round gathers only
     // slots that really have a pair of hits to join (the cheap half -- build the hit, compatibleWith -- is glue)
-    F_L_COMBINE, F_L_GCOMBINE, F_R_COMBINE, F_R_GCOMBINE
+    F_L_COMBINE, F_L_GCOMBINE, F_R_COMBINE, F_R_GCOMBINE,
+    // the three uses of a populated splice-site DB (spliced_aligner.h:409-668, 685-811, 1365-1494)
+    F_SS_FULL, F_L_SS, F_L_SS_RET, F_R_SS, F_R_SS_RET
 };
 
 // push a child frame (== a recursive call of hybridSearch_recur)
@@ -69,16 +71,217 @@ template <bool GRAPH, bool NOSPL> HT2_NI void Ht2AlignerT<GRAPH, NOSPL>::runFram
         }
         if (W->err) { f.pc = F_RETURN; break; }
         f.nLocalHits = 0;
+        const bool ss = !ssdbEmpty() && !noSpl();   // with --no-spliced-alignment the DB branches reduce to the plain ones
+        f.ssi = HT2_IDX_MAX32; f.ssHi = 0;
         if (hitoff == 0 && hitlen == rdlen) {
             if (!redundant(rdi, hit)) {
+                if (ss) { f.pc = F_SS_FULL; break; }
                 reportHit(rdi, hit);
                 if (hit.score > f.maxsc) f.maxsc = hit.score;
             }
             f.pc = F_RETURN;
-        } else if (hitoff > 0 && (hitoff + hitlen == rdlen || hitoff + hitoff < rdlen - hitlen)) f.pc = F_L_START;
-        else f.pc = F_R_START;
+        } else if (hitoff > 0 && (hitoff + hitlen == rdlen || hitoff + hitoff < rdlen - hitlen)) f.pc = ss ? F_L_SS : F_L_START;
+        else f.pc = ss ? F_R_SS : F_R_START;
         break;
     }
+#ifdef HT2_ENABLE_SPLICED
+    // ------------------------------------------------ splice-site DB: a full-length hit (spliced_aligner.h:409-664) --
+    // Known / novel sites next to the hit's first and last exon-like fragment are tried as alternative ends of the
+    // alignment: a read that runs a few bases into the next exon aligns those bases as mismatches or soft clips
+    // otherwise.  No recursion in here: one heavy segment.
+    case F_SS_FULL: {
+        Ht2SsView ssv; ssv.init(ssT);
+        enum { MAXL = 24 };
+        Ht2Hit* list[MAXL]; uint32_t n = 0;
+        int64_t best_score = hit.score;
+        list[n] = poolAlloc(); copyHit(*list[n], hit); list[n]->hitcount = hit.hitcount; n++;
+        uint32_t fragoff = 0, fraglen = 0, left = 0, right = 0;
+        getLeft(hit, fragoff, fraglen, left, NULL, rdi);
+        const uint32_t minMatchLen = minK;
+        if (fraglen >= minMatchLen && left >= minMatchLen && hit.trim5 == 0) {
+            uint32_t lo, hi;
+            ssv.leftSites(hit.tidx, left + minMatchLen, minMatchLen, lo, hi);
+            for (uint32_t si = lo; si < hi && !W->err; si++) {
+                const Ht2SsSite ss1 = ssv.bw[si];
+                if (left + fraglen - 1 < ss1.right) continue;
+                const uint32_t frag2off = ss1.left - (ss1.right - left);
+                if (frag2off + 1 < hitoff) continue;
+                if (fragoff + ss1.right < left + 1) continue;
+                const uint32_t readoff = fragoff + ss1.right - left - 1;
+                uint32_t joinedOff = 0;
+                if (!textOffToJoined(hit.tidx, ss1.left, joinedOff)) continue;
+                Ht2Hit* tp = poolAlloc();
+                Ht2Hit& tempHit = *tp;
+                initHit(tempHit, hit.fw != 0, readoff + 1, 0, 0, 0, hit.tidx, ss1.left + 1, joinedOff + 1);
+                uint32_t leftext = readoff + 1, rightext = 0;
+                extend(tempHit, rdi, leftext, rightext, 0);
+                bool keep = false;
+                if (tempHit.len > 0 && compatibleWith(tempHit, hit, rdi)) {
+                    int64_t msc = minsc[rdi] > best_score ? minsc[rdi] : best_score;
+                    const bool combined = combineWith(tempHit, hit, rdi, msc, &ss1);
+                    if (W->bestUnp[rdi] > msc) msc = W->bestUnp[rdi];
+                    uint32_t anchor = 0, ned = 0;
+                    getLeftAnchor(tempHit, anchor, ned);
+                    if (combined && tempHit.score >= msc && ned <= anchor / 4) {   // no short anchors with many mismatches
+                        if (!isSearched(tempHit, rdi) && !redundant(rdi, tempHit)) {
+                            if (tempHit.score > best_score) best_score = tempHit.score;
+                            if (n < MAXL) { list[n++] = tp; keep = true; } else W->err |= HT2_ERR_POOL;
+                        }
+                    }
+                }
+                if (!keep) W->poolTop--;
+            }
+        }
+        const uint32_t num = n;
+        for (uint32_t i = 0; i < num && !W->err; i++) {
+            const Ht2Hit& canHit = *list[i];
+            getRight(canHit, fragoff, fraglen, right, NULL, rdi);
+            if (canHit.score < best_score) continue;
+            if (!(fraglen >= minMatchLen && canHit.trim3 == 0)) continue;
+            uint32_t lo, hi;
+            ssv.rightSites(canHit.tidx, right + fraglen - minMatchLen, minMatchLen, lo, hi);
+            for (uint32_t si = lo; si < hi && !W->err; si++) {
+                const Ht2SsSite ss1 = ssv.fw[si];
+                if (right > ss1.left) continue;
+                const uint32_t readoff = fragoff + ss1.left - right + 1;
+                if (readoff >= rdlen) continue;
+                uint32_t joinedOff = 0;
+                if (!textOffToJoined(canHit.tidx, ss1.right, joinedOff)) continue;
+                Ht2Hit* cp = poolAlloc();        // the combined hit, kept when it survives ...
+                Ht2Hit* tp = poolAlloc();        // ... the fragment beyond the site, always released
+                Ht2Hit& tempHit = *tp;
+                initHit(tempHit, canHit.fw != 0, readoff, 0, 0, 0, canHit.tidx, ss1.right, joinedOff);
+                uint32_t leftext = 0, rightext = rdlen - readoff;
+                extend(tempHit, rdi, leftext, rightext, 0);
+                bool keep = false;
+                if (tempHit.len > 0 && compatibleWith(canHit, tempHit, rdi)) {
+                    Ht2Hit& combinedHit = *cp;
+                    copyHit(combinedHit, canHit); combinedHit.hitcount = canHit.hitcount;
+                    int64_t msc = minsc[rdi] > best_score ? minsc[rdi] : best_score;
+                    const bool combined = combineWith(combinedHit, tempHit, rdi, msc, &ss1);
+                    if (W->bestUnp[rdi] > msc) msc = W->bestUnp[rdi];
+                    uint32_t anchor = 0, ned = 0;
+                    getRightAnchor(combinedHit, anchor, ned);
+                    if (combined && combinedHit.score >= msc && ned <= anchor / 4) {
+                        if (!isSearched(combinedHit, rdi) && !redundant(rdi, combinedHit)) {
+                            if (combinedHit.score > best_score) best_score = tempHit.score;   // sic: the fragment's score (spliced_aligner.h:632)
+                            if (n < MAXL) { list[n++] = cp; keep = true; } else W->err |= HT2_ERR_POOL;
+                        }
+                    }
+                }
+                W->poolTop--;                    // tempHit
+                if (!keep) W->poolTop--;         // combinedHit
+            }
+        }
+        for (uint32_t i = 0; i < n && !W->err; i++) {
+            const Ht2Hit& canHit = *list[i];
+            if (!P->secondary && canHit.score < best_score) continue;
+            if (i > 0 && !isSearched(canHit, rdi)) addSearched(canHit, rdi);
+            if (!redundant(rdi, canHit)) {
+                reportHit(rdi, canHit);
+                if (canHit.score > f.maxsc) f.maxsc = canHit.score;
+            }
+        }
+        f.pc = F_RETURN;
+        break;
+    }
+    // ------------------------- splice-site DB: a partial hit to be extended to the left (spliced_aligner.h:685-811) --
+    case F_L_SS: {
+        Ht2SsView ssv; ssv.init(ssT);
+        uint32_t fragoff = 0, fraglen = 0, left = 0;
+        getLeft(hit, fragoff, fraglen, left, NULL, rdi);
+        const uint32_t minMatchLen = minKL;
+        if (f.ssi == HT2_IDX_MAX32) {
+            f.ssi = 0; f.ssHi = 0;
+            if (fraglen >= minMatchLen && left >= minMatchLen)
+                ssv.leftSites(hit.tidx, left + minMatchLen, minMatchLen + (minMatchLen < fragoff ? minMatchLen : fragoff), f.ssi, f.ssHi);
+        }
+        f.pc = F_L_START;
+        while (f.ssi < f.ssHi && !W->err) {
+            const Ht2SsSite ss1 = ssv.bw[f.ssi++];
+            if (left + fraglen - 1 < ss1.right) continue;
+            if (fragoff + ss1.right < left + 1) continue;
+            const uint32_t readoff = fragoff + ss1.right - left - 1;
+            uint32_t joinedOff = 0;
+            if (!textOffToJoined(hit.tidx, ss1.left, joinedOff)) continue;
+            Ht2Hit* tp = poolAlloc();
+            Ht2Hit& tempHit = *tp;
+            initHit(tempHit, hit.fw != 0, readoff + 1, 0, 0, 0, hit.tidx, ss1.left + 1, joinedOff + 1);
+            uint32_t leftext = readoff + 1, rightext = 0;
+            extend(tempHit, rdi, leftext, rightext, 0);
+            if (tempHit.len > 0 && compatibleWith(tempHit, hit, rdi)) {
+                const bool combined = combineWith(tempHit, hit, rdi, minsc[rdi], &ss1);
+                const int64_t msc = sinkFloor(rdi, f.cushion);
+                if (combined && tempHit.score >= msc &&
+                    tempHit.score + (int64_t)((uint32_t)ht2_scpen(*P, 0) * hit.rdoff) >= hit.score) {   // soft-clipping might be better
+                    f.pc = F_L_SS_RET;
+                    pushFrame(rdi, tp, tempHit.rdoff, tempHit.len + tempHit.trim3, alignMate, f.dep + 1);
+                    break;
+                }
+            }
+            W->poolTop--;
+        }
+        break;
+    }
+    case F_L_SS_RET: {
+        if (W->childRet > f.maxsc) f.maxsc = W->childRet;
+        W->poolTop--;   // tempHit
+        f.pc = F_L_SS;
+        break;
+    }
+    // ----------------------- splice-site DB: a partial hit to be extended to the right (spliced_aligner.h:1365-1494) --
+    case F_R_SS: {
+        Ht2SsView ssv; ssv.init(ssT);
+        uint32_t fragoff = 0, fraglen = 0, right = 0;
+        getRight(hit, fragoff, fraglen, right, NULL, rdi);
+        const uint32_t minMatchLen = minKL;
+        if (f.ssi == HT2_IDX_MAX32) {
+            f.ssi = 0; f.ssHi = 0;
+            if (fraglen >= minMatchLen) {
+                const uint32_t right_unmapped_len = rdlen - fragoff - fraglen;
+                ssv.rightSites(hit.tidx, right + fraglen - minMatchLen, minMatchLen + (minMatchLen < right_unmapped_len ? minMatchLen : right_unmapped_len), f.ssi, f.ssHi);
+            }
+        }
+        f.pc = F_R_START;
+        while (f.ssi < f.ssHi && !W->err) {
+            const Ht2SsSite ss1 = ssv.fw[f.ssi++];
+            if (right > ss1.left) continue;
+            const uint32_t readoff = fragoff + ss1.left - right + 1;
+            if (readoff >= rdlen) continue;
+            uint32_t joinedOff = 0;
+            if (!textOffToJoined(hit.tidx, ss1.right, joinedOff)) continue;
+            Ht2Hit* cp = poolAlloc();
+            Ht2Hit* tp = poolAlloc();
+            Ht2Hit& tempHit = *tp;
+            initHit(tempHit, hit.fw != 0, readoff, 0, 0, 0, hit.tidx, ss1.right, joinedOff);
+            uint32_t leftext = 0, rightext = rdlen - readoff;
+            extend(tempHit, rdi, leftext, rightext, 0);
+            bool go = false;
+            if (tempHit.len > 0 && compatibleWith(hit, tempHit, rdi)) {
+                Ht2Hit& combinedHit = *cp;
+                copyHit(combinedHit, hit); combinedHit.hitcount = hit.hitcount;
+                const bool combined = combineWith(combinedHit, tempHit, rdi, minsc[rdi], &ss1);
+                const int64_t msc = sinkFloor(rdi, f.cushion);
+                if (combined && combinedHit.score >= msc &&
+                    combinedHit.score + (int64_t)((uint32_t)ht2_scpen(*P, 0) * (rdlen - hit.rdoff - hit.len - hit.trim5)) >= hit.score) go = true;
+            }
+            W->poolTop--;       // tempHit
+            if (go) {
+                f.pc = F_R_SS_RET;
+                pushFrame(rdi, cp, cp->rdoff - cp->trim5, cp->len + cp->trim5, alignMate, f.dep + 1);
+                break;
+            }
+            W->poolTop--;       // combinedHit
+        }
+        break;
+    }
+    case F_R_SS_RET: {
+        if (W->childRet > f.maxsc) f.maxsc = W->childRet;
+        W->poolTop--;   // combinedHit
+        f.pc = F_R_SS;
+        break;
+    }
+#endif
     // ------------------------------------------------------------ left --
     case F_L_START: {
         f.use_localindex = 1;
@@ -813,6 +1016,7 @@ template <bool GRAPH, bool NOSPL> HT2_HD bool Ht2AlignerT<GRAPH, NOSPL>::machine
         switch (W->frames[W->nFrames - 1].pc) {
             case F_ENTER: case F_L_START: case F_L_WHILE: case F_L_COMBINE: case F_L_AFTER_WHILE: case F_L_GCOMBINE: case F_L_TRIM: case F_L_EXT:
             case F_R_START: case F_R_WHILE: case F_R_COMBINE: case F_R_AFTER_WHILE: case F_R_GCOMBINE: case F_R_TRIM: case F_R_EXT:
+            case F_SS_FULL: case F_L_SS: case F_R_SS:
                 return true;
             default: return false;
         }

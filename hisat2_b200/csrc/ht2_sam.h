@@ -39,6 +39,7 @@ struct Ht2SamIn {
     const ht2gpu_edit_t*        edits;
     const uint16_t*             pairs;
     uint32_t khits, secondary, mixed, discord;
+    const uint8_t*  ssT;         // the run's splice-site DB (ht2_ssdb.h) or NULL: template-length adjustment of concordant pairs
 };
 
 template <bool WRITE>
@@ -291,7 +292,7 @@ struct Ht2SamFmt {
         en = (int64_t)r.toff + r.ref_extent - 1 + trim_en;
         st2 = st + introns; en2 = en + introns;
     }
-    HT2_HD int64_t fragmentLength(const ht2gpu_aln_t& me, const ht2gpu_aln_t& o, bool meMate1) const {
+    HT2_HD int64_t fragmentLength(const ht2gpu_aln_t& me, const ht2gpu_aln_t& o, bool meMate1, bool useSs = false) const {
         int64_t st, en, st2, en2, ost, oen, ost2, oen2;
         extents(me, st, en, st2, en2); extents(o, ost, oen, ost2, oen2);
         bool imUpstream;
@@ -301,10 +302,24 @@ struct Ht2SamFmt {
             else if (me.fw && !o.fw) imUpstream = true;
             else imUpstream = false;
         } else imUpstream = false;
-        int64_t up, dn;
-        if (imUpstream) { up = st2 < ost ? st2 : ost; dn = en2 > oen ? en2 : oen; }
-        else { up = st < ost2 ? st : ost2; dn = en > oen2 ? en : oen2; }
-        int64_t fraglen = 1 + dn - up;
+        int64_t up, dn, up_right, dn_left;
+        if (imUpstream) { up = st2 < ost ? st2 : ost; up_right = en2 < oen ? en2 : oen; dn_left = st2 > ost ? st2 : ost; dn = en2 > oen ? en2 : oen; }
+        else { up = st < ost2 ? st : ost2; up_right = en < oen2 ? en : oen2; dn_left = st > ost2 ? st : ost2; dn = en > oen2 ? en : oen2; }
+        // concordant pairs, templateLenAdjustment (the default): the longest known intron that lies strictly between the
+        // mates does not count (AlnRes::setFragmentLength, aligner_result.h:1666-1683)
+        int64_t intron_len = 0;
+        if (useSs && in->ssT != NULL && up_right + 100 < dn_left) {
+            Ht2SsView ssv; ssv.init(in->ssT);
+            uint32_t lo, hi;
+            ssv.rightSites(me.tidx, (uint32_t)up_right, (uint32_t)(dn_left - up_right), lo, hi);
+            for (uint32_t si = lo; si < hi; si++) {
+                const Ht2SsSite& ss = ssv.fw[si];
+                if ((int64_t)ss.left <= up || (int64_t)ss.right >= dn) continue;
+                const int64_t l = (int64_t)(ss.right - ss.left - 1);
+                if (intron_len < l) intron_len = l;
+            }
+        }
+        int64_t fraglen = 1 + dn - up - intron_len;
         if (!imUpstream) fraglen = -fraglen;
         return fraglen;
     }
@@ -656,8 +671,8 @@ struct Ht2SamFmt {
             for (uint32_t i = 0; i < nsel; i++) {
                 const ht2gpu_aln_t& a = rs1u[pairs[2 * sel[i]]]; const ht2gpu_aln_t& b = rs2u[pairs[2 * sel[i] + 1]];
                 fl1.primary = fl2.primary = (i == 0);
-                appendMate(o, rd1, rd2.len, &a, &b, summ, fl1, true, fragmentLength(a, b, true), true);
-                appendMate(o, rd2, rd1.len, &b, &a, summ, fl2, true, fragmentLength(b, a, false), true);
+                appendMate(o, rd1, rd2.len, &a, &b, summ, fl1, true, fragmentLength(a, b, true, true), true);
+                appendMate(o, rd2, rd1.len, &b, &a, summ, fl2, true, fragmentLength(b, a, false, true), true);
             }
             return;
         } else if (discordant) {

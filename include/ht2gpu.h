@@ -337,6 +337,16 @@ uint32_t ht2gpu_ref_len(const ht2gpu_handle_t* h, uint32_t i);
 uint32_t ht2gpu_read_seed(const uint8_t* seq, const uint8_t* qual, uint32_t len,
                           const char* name, uint32_t global_seed);
 
+/* The run's read-only splice-site DB (spliced mode): the sites of --known-splicesite-infile and
+ * --novel-splicesite-infile ("<chr> <left> <right> <+|->" per line, 0-based; hisat2.cpp:4101-4116,
+ * SpliceSiteDB::read splice_site.cpp:727-775; either path may be NULL).  With a DB loaded, alignment runs the
+ * three `if(!ssdb.empty())` branches of hybridSearch_recur (spliced_aligner.h:409-668, 685-811, 1365-1494):
+ * short exon ends next to a listed site are aligned across it, and the template length of a concordant pair
+ * excludes the longest listed intron between the mates (aligner_result.h:1631-1690).  Replaces a DB loaded
+ * earlier; not to be called while a batch is in flight.  Temporary sites (learned while aligning) are not
+ * modelled: the reference's own output depends on thread timing there. */
+int ht2gpu_load_splicesites(ht2gpu_handle_t* h, const char* known_path, const char* novel_path, uint32_t* n_sites);
+
 /* Diagnostics: the warp-wide fill of the --bowtie2-dp score planes against the single-lane fill on n random
  * problems (aligner_swsse_ee_u8.cpp:791-1163 restated twice, ht2_sw.h).  out[0] = mismatching cells / scores
  * (must be 0), out[1] = problems run, out[2] = cells compared per plane, out[3] = problems with a valid best. */

@@ -265,6 +265,33 @@ def spliced():
     os.remove(os.path.join(G, "spl.tmp"))
 
 
+def known_splice():
+    """Spliced mode with a POPULATED, read-only splice-site DB: --no-temp-splicesite --known-splicesite-infile (and
+    --novel-splicesite-infile).  Reads and sites from tools/sim_rna.py (seed 23): 600 single-end reads, many with only
+    1-11 bases beyond a junction, 300 pairs with mates in different exons, 1104 site lines (85 % of the introns used,
+    decoys, duplicates, an unknown sequence name)."""
+    import sim_rna
+    al = os.path.join(REF, "hisat2-align-s")
+    refs = sim_rna.load_fasta(os.path.join(G, "tiny.fa"))
+    se, pairs, lines = sim_rna.sim(refs, 600, 300, 23)
+    sim_rna.write(os.path.join(G, "tiny_ss_rna"), se, pairs, lines)
+    ss = open(os.path.join(G, "tiny_ss_rna_ss.txt")).read().splitlines()
+    open(os.path.join(G, "tiny_ss_known.txt"), "w").write("\n".join(ss[:300]) + "\n")
+    open(os.path.join(G, "tiny_ss_novel.txt"), "w").write("\n".join(ss[250:]) + "\n")
+    K = ["--no-temp-splicesite", "--known-splicesite-infile", "tiny_ss_rna_ss.txt"]
+    for idx, flags, args, out in (("tiny", K, ["-U", "tiny_ss_rna.fa"], "tiny_ss_rna_se.sam"),
+                                  ("tiny", K, ["-1", "tiny_ss_rna_1.fa", "-2", "tiny_ss_rna_2.fa"], "tiny_ss_rna_pe.sam"),
+                                  ("tiny_snp", K, ["-1", "tiny_ss_rna_1.fa", "-2", "tiny_ss_rna_2.fa"], "tiny_snp_ss_rna_pe.sam"),
+                                  ("tiny", K + ["-k", "20", "--secondary"], ["-U", "tiny_ss_rna.fa"], "tiny_ss_rna_se_k20_secondary.sam"),
+                                  ("tiny", ["--no-temp-splicesite", "--known-splicesite-infile", "tiny_ss_known.txt", "--novel-splicesite-infile", "tiny_ss_novel.txt"],
+                                   ["-1", "tiny_ss_rna_1.fa", "-2", "tiny_ss_rna_2.fa"], "tiny_ss_rna_pe_known_novel.sam")):
+        subprocess.run([al, "-f", "-x", idx] + flags + args + ["-S", "ss.tmp"], check=True, cwd=G, stderr=subprocess.DEVNULL)
+        data = b"".join(l for l in open(os.path.join(G, "ss.tmp"), "rb") if not l.startswith(b"@PG"))
+        open(os.path.join(G, out), "wb").write(data)
+        print(out, data.count(b"\n"), "records,", sum(1 for l in data.splitlines() if not l.startswith(b"@") and b"N" in l.split(b"\t")[5]), "spliced")
+    os.remove(os.path.join(G, "ss.tmp"))
+
+
 def options():
     """md5 of the reference's SAM (minus @PG) for every option case -> option_matrix.json."""
     import hashlib, json
@@ -287,6 +314,9 @@ def options():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "spliced":
         spliced()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "known_splice":
+        known_splice()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "options":
         options()

@@ -70,8 +70,11 @@ static void seedDump(const Ht2Image& img, const Ht2Params& P, const std::vector<
 }
 
 #ifdef HT2_ENABLE_SPLICED
-#define HT2_SET_SPLT(A) (A).splT = &ht2_spl_tables()
+static std::vector<uint8_t> g_ssBlob;      // HT2_SS=<known-splicesite file>[,<novel-splicesite file>]: the run's splice-site DB (ht2_ssdb.h)
+#define HT2_SS_BLOB (g_ssBlob.empty() ? (const uint8_t*)NULL : g_ssBlob.data())
+#define HT2_SET_SPLT(A) do { (A).splT = &ht2_spl_tables(); (A).ssT = HT2_SS_BLOB; } while (0)
 #else
+#define HT2_SS_BLOB ((const uint8_t*)NULL)
 #define HT2_SET_SPLT(A) (void)0
 #endif
 
@@ -185,7 +188,7 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         char* txt = NULL; size_t len = 0;
         const unsigned nth = getenv("HT2_THREADS") ? (unsigned)atoi(getenv("HT2_THREADS")) : 1;
         auto t0 = std::chrono::steady_clock::now();
-        if (!ht2_format_batch(*img, P, &rb, names.c_str(), &res, &txt, &len, nth)) { fprintf(stderr, "ht2_format_batch failed\n"); return 1; }
+        if (!ht2_format_batch(*img, P, &rb, names.c_str(), &res, &txt, &len, nth, HT2_SS_BLOB)) { fprintf(stderr, "ht2_format_batch failed\n"); return 1; }
         finishNs += (std::chrono::steady_clock::now() - t0).count();
         sam.append(txt, len); free(txt);
     }
@@ -304,6 +307,17 @@ int main(int argc, char** argv) {
     if (pairedMode && !ht2_read_reads(argv[4], reads2, 2, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     Ht2Params P;
     ht2_default_params(P, *img, true);
+#ifdef HT2_ENABLE_SPLICED
+    if (const char* ssf = getenv("HT2_SS")) {
+        std::vector<Ht2SsFile> files;
+        std::string a(ssf); size_t c = a.find(',');
+        files.push_back({a.substr(0, c), true});
+        if (c != std::string::npos) files.push_back({a.substr(c + 1), false});
+        uint32_t ns = 0;
+        if (!ht2_ssdb_build(*img, files, g_ssBlob, ns, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        fprintf(stderr, "splice-site DB: %u sites\n", ns);
+    }
+#endif
     // HT2_OPTS="khits=1,mp_max=4,...": the ht2gpu_options_t fields, mapped like applyOptions (ht2_gpu.cu)
     if (const char* os = getenv("HT2_OPTS")) {
         std::string o(os); size_t p0 = 0;

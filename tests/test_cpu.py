@@ -158,6 +158,34 @@ def test_spliced_alignment_host_build_matches_golden_reference_sam(hostsim_splic
     assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, "tiny_pe.sam"), "rb").read())
 
 
+def test_populated_splice_site_db_host_build_matches_golden_reference_sam(hostsim_spliced_bin, tmp_path):
+    """--known-splicesite-infile / --novel-splicesite-infile with --no-temp-splicesite: the three
+    `if(!ssdb.empty())` branches of hybridSearch_recur (spliced_aligner.h:409-668, 685-811, 1365-1494), combineWith
+    pinned to a listed site, known-site scoring, and the template-length adjustment of concordant pairs
+    (aligner_result.h:1631-1690) -- host build of the same sources against golden SAM of the unmodified reference:
+    600 RNA-like reads (many with 1-11 bases beyond a junction), 300 pairs with mates in different exons, on the
+    linear and the graph index, with -k 20 --secondary, and with the sites split over the two files."""
+    env = dict(os.environ, HT2_OPTS="spliced=1")
+    for idx, ss, opts, args, gold in (
+            ("tiny", "tiny_ss_rna_ss.txt", "", ["tiny_ss_rna.fa"], "tiny_ss_rna_se.sam"),
+            ("tiny", "tiny_ss_rna_ss.txt", "", ["tiny_ss_rna_1.fa", "tiny_ss_rna_2.fa"], "tiny_ss_rna_pe.sam"),
+            ("tiny_snp", "tiny_ss_rna_ss.txt", "", ["tiny_ss_rna_1.fa", "tiny_ss_rna_2.fa"], "tiny_snp_ss_rna_pe.sam"),
+            ("tiny", "tiny_ss_rna_ss.txt", ",khits=20,secondary=1", ["tiny_ss_rna.fa"], "tiny_ss_rna_se_k20_secondary.sam"),
+            ("tiny", "tiny_ss_known.txt,tiny_ss_novel.txt", "", ["tiny_ss_rna_1.fa", "tiny_ss_rna_2.fa"], "tiny_ss_rna_pe_known_novel.sam")):
+        out = str(tmp_path / "o.sam")
+        e = dict(env, HT2_SS=ss, HT2_OPTS=env["HT2_OPTS"] + opts)
+        r = subprocess.run([hostsim_spliced_bin, idx, args[0], out] + args[1:], cwd=GOLDEN, check=True, stderr=subprocess.PIPE, env=e)
+        assert b"errors=0" in r.stderr, gold
+        assert sam_lines(open(out, "rb").read()) == sam_lines(open(os.path.join(GOLDEN, gold), "rb").read()), gold
+    # the DB matters: without it the same reads align differently (so the test above is not vacuous)
+    out = str(tmp_path / "o2.sam")
+    subprocess.run([hostsim_spliced_bin, "tiny", "tiny_ss_rna.fa", out], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL, env=env)
+    a, b = sam_lines(open(out, "rb").read()), sam_lines(open(os.path.join(GOLDEN, "tiny_ss_rna_se.sam"), "rb").read())
+    assert sum(1 for x, y in zip(a, b) if x != y) > 200
+    gold = open(os.path.join(GOLDEN, "tiny_ss_rna_se.sam")).read().splitlines()
+    assert sum(1 for l in gold if not l.startswith("@") and "N" in l.split("\t")[5]) >= 350
+
+
 def test_striped_dp_fill_and_backtrace_against_plain_scalar_dp(hostsim_bin):
     """The --bowtie2-dp kernel on its own (ht2_sw.h: striped s16x2 fill with the DPX-style max(a+b,c) steps +
     plane-derived backtrace) against an independent scalar statement of the recurrences: 400 random problems

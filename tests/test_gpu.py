@@ -380,6 +380,62 @@ def test_spliced_alignment_when_compiled_in(h2, tmp_path):
         idx.close()
 
 
+def test_populated_splice_site_db_matches_reference(h2, tmp_path):
+    """SURVEY 8f.3, the read-only part: --known-splicesite-infile / --novel-splicesite-infile with --no-temp-splicesite.
+    The DB lives in HBM (ht2gpu_load_splicesites); the pool kernel runs the three `if(!ssdb.empty())` branches of
+    hybridSearch_recur and the SAM kernel adjusts the template length of concordant pairs.  Golden SAM of the
+    unmodified reference on the tiny fixtures (linear + graph index, -k 20 --secondary, two site files), the command
+    line front end, and -- when oracle/_ref is on the box -- 20 k reads + 10 k pairs simulated over the chr22 example
+    region with 34 k site lines, against the reference run in place."""
+    g = lambda n: os.path.join(GOLDEN, n)
+    for index, known, novel, opts, args, gold in (
+            ("tiny", "tiny_ss_rna_ss.txt", None, {}, ("tiny_ss_rna.fa",), "tiny_ss_rna_se.sam"),
+            ("tiny", "tiny_ss_rna_ss.txt", None, {}, ("tiny_ss_rna_1.fa", "tiny_ss_rna_2.fa"), "tiny_ss_rna_pe.sam"),
+            ("tiny_snp", "tiny_ss_rna_ss.txt", None, {}, ("tiny_ss_rna_1.fa", "tiny_ss_rna_2.fa"), "tiny_snp_ss_rna_pe.sam"),
+            ("tiny", "tiny_ss_rna_ss.txt", None, dict(khits=20, secondary=1), ("tiny_ss_rna.fa",), "tiny_ss_rna_se_k20_secondary.sam"),
+            ("tiny", "tiny_ss_known.txt", "tiny_ss_novel.txt", {}, ("tiny_ss_rna_1.fa", "tiny_ss_rna_2.fa"), "tiny_ss_rna_pe_known_novel.sam")):
+        idx = h2.Index(g(index), no_spliced_alignment=0, **opts)
+        n = idx.load_splicesites(g(known), g(novel) if novel else None)
+        assert n > 250
+        batch = h2.ReadBatch.from_fasta(g(args[0]), path2=g(args[1]) if len(args) > 1 else None)
+        sam, _ = gpu_sam(idx, batch)           # device SAM == host formatter is asserted inside
+        assert sam_lines(sam) == sam_lines(open(g(gold), "rb").read()), gold
+        if index == "tiny" and not opts and len(args) == 1:
+            assert idx.load_splicesites(None, None) == 0          # unloading restores the empty-DB behaviour
+            sam0, _ = gpu_sam(idx, batch)
+            assert sam_lines(sam0) != sam_lines(sam)
+        idx.close()
+    cli = os.path.join(ROOT, "hisat2_b200", "hisat2-b200")
+    if os.path.exists(cli):
+        out = str(tmp_path / "cli.sam")
+        subprocess.run([cli, "--no-temp-splicesite", "--known-splicesite-infile", "tiny_ss_rna_ss.txt", "-x", "tiny", "-f", "-1", "tiny_ss_rna_1.fa",
+                        "-2", "tiny_ss_rna_2.fa", "-S", out], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL)
+        assert sam_lines(open(out, "rb").read()) == sam_lines(open(g("tiny_ss_rna_pe.sam"), "rb").read())
+        r = subprocess.run([cli, "--known-splicesite-infile", "/nonexistent/ss.txt", "-x", "tiny", "-f", "-U", "tiny_ss_rna.fa", "-S", out], cwd=GOLDEN,
+                           stderr=subprocess.PIPE)
+        assert r.returncode != 0 and b"cannot open" in r.stderr
+    base = os.path.join(DATA, "22_20-21M")
+    if os.path.exists(REFBIN) and os.path.exists(base + ".1.ht2") and os.path.exists(base + ".fa"):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sim_rna
+        se, pairs, lines = sim_rna.sim(sim_rna.load_fasta(base + ".fa"), 20000, 10000, 5)
+        pre = str(tmp_path / "c")
+        sim_rna.write(pre, se, pairs, lines)
+        idx = h2.Index(base, no_spliced_alignment=0)
+        assert idx.load_splicesites(pre + "_ss.txt") > 20000
+        for paired in (False, True):
+            batch = h2.ReadBatch.from_fasta(pre + ("_1.fa" if paired else ".fa"), path2=pre + "_2.fa" if paired else None)
+            sam, _ = gpu_sam(idx, batch)
+            out = str(tmp_path / "ref.sam")
+            subprocess.run([REFBIN, "--no-temp-splicesite", "--known-splicesite-infile", pre + "_ss.txt", "-f", "-x", base] +
+                           (["-1", pre + "_1.fa", "-2", pre + "_2.fa"] if paired else ["-U", pre + ".fa"]) +
+                           ["-S", out, "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+            want = sam_lines(open(out, "rb").read())
+            assert sam_lines(sam) == want
+            assert sum(1 for l in want if not l.startswith(b"@") and b"N" in l.split(b"\t")[5]) > (3000 if paired else 8000)
+        idx.close()
+
+
 def test_seed_search_bundled_graph_index_matches_oracle(h2, oracle_bin):
     """The reference's bundled example index (22_20-21M_snp: 3,689 SNPs/indels, 958,359 rows over
     954,773 nodes): every H/G/C record of 20k hard reads equals the pinned oracle's."""
