@@ -1,0 +1,4 @@
+set -x
+O=gpurun_out/r2w; mkdir -p $O
+timeout 1200 python -m pytest tests/test_gpu.py -m gpu -x -q -k "populated_splice or spliced_alignment or command_line" > $O/pytest_ss.log 2>&1; tail -15 $O/pytest_ss.log
+timeout 2400 python -m pytest tests/test_gpu.py -m gpu -x -q > $O/pytest.log 2>&1; tail -5 $O/pytest.log
