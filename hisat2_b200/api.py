@@ -86,7 +86,8 @@ EXPORTS = [
     "ht2gpu_seed_search", "ht2gpu_free_seed_results", "ht2gpu_index_is_graph",
     "ht2gpu_sam_slots", "ht2gpu_submit_sam", "ht2gpu_wait_sam", "ht2gpu_align_sam", "ht2gpu_run_reads",
     "ht2gpu_host_alloc", "ht2gpu_host_free", "ht2gpu_set_error", "ht2gpu_parse_reads", "ht2gpu_free_parsed",
-    "ht2gpu_ctx_get", "ht2gpu_ctx_set", "ht2gpu_run_reads_multi", "ht2gpu_open_peer", "ht2gpu_sw_selftest", "ht2gpu_load_splicesites",
+    "ht2gpu_ctx_get", "ht2gpu_ctx_set", "ht2gpu_run_reads_multi", "ht2gpu_open_peer", "ht2gpu_sw_selftest", "ht2gpu_load_splicesites", "ht2gpu_collect_splicesites",
+    "ht2gpu_write_novel_splicesites",
 ]
 
 
@@ -153,6 +154,8 @@ def load_library(path=None):
     lib.ht2gpu_free_parsed.argtypes = [C.POINTER(CParsedReads)]
     lib.ht2gpu_sw_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.ht2gpu_load_splicesites.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint32)]
+    lib.ht2gpu_collect_splicesites.argtypes = [C.c_void_p, C.c_int]
+    lib.ht2gpu_write_novel_splicesites.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.POINTER(C.c_uint64)]
     if path is None:
         _lib = lib
     return lib
@@ -503,6 +506,17 @@ class Index(object):
         n = C.c_uint32(0)
         self._check(self._lib.ht2gpu_load_splicesites(self._h, known.encode() if known else None, novel.encode() if novel else None, C.byref(n)),
                     "ht2gpu_load_splicesites")
+        return int(n.value)
+
+    def collect_splicesites(self, enable=True):
+        """ht2gpu_collect_splicesites: record the junctions of printed alignments (--novel-splicesite-outfile)."""
+        self._check(self._lib.ht2gpu_collect_splicesites(self._h, 1 if enable else 0), "ht2gpu_collect_splicesites")
+
+    def write_novel_splicesites(self, path, peers=()):
+        """ht2gpu_write_novel_splicesites over this handle (+ peers); returns the number of sites written."""
+        hs = (C.c_void_p * (1 + len(peers)))(self._h, *[p._h for p in peers])
+        n = C.c_uint64(0)
+        self._check(self._lib.ht2gpu_write_novel_splicesites(hs, 1 + len(peers), path.encode(), C.byref(n)), "ht2gpu_write_novel_splicesites")
         return int(n.value)
 
     def peer(self, device):

@@ -14,7 +14,7 @@ static void usage() {
                     "            [--mp MX,MN] [--sp MX,MN] [--np N] [--rdg C,L] [--rfg C,L] [--ignore-quals] [--nofw] [--norc]\n"
                     "            [-I N] [-X N] [--no-mixed] [--no-discordant] [--seed N] [--batch N] [--device N] [--gpus N] [-p N]\n"
                     "            [-5 N] [-3 N] [-s N] [-u N] [--phred33|--phred64] [--no-temp-splicesite]\n"
-                    "            [--known-splicesite-infile F] [--novel-splicesite-infile F]\n"
+                    "            [--known-splicesite-infile F] [--novel-splicesite-infile F] [--novel-splicesite-outfile F]\n"
                     "            [--bowtie2-dp 0|1|2] [--score-min F,C,L] [--gbar N] [--sensitive] [--very-sensitive] [--fast]\n");
 }
 static void two(const char* a, int32_t& x, int32_t& y) { sscanf(a, "%d,%d", &x, &y); }
@@ -27,7 +27,7 @@ int main(int argc, char** argv)
     bool fastq = true; size_t batchSz = 0 /* library default */; uint32_t gseed = 0;
     int trim5 = 0, trim3 = 0, threads = 0, gpus = 1; bool phred64 = false; uint64_t skip = 0, upto = 0;
     bool sensitive = false, verySensitive = false, fast = false, noTempSpliceSite = false;
-    const char *knownSs = NULL, *novelSs = NULL;   // --known-splicesite-infile / --novel-splicesite-infile (hisat2.cpp:1689-1691)
+    const char *knownSs = NULL, *novelSs = NULL, *novelOut = NULL;   // --known-splicesite-infile / --novel-splicesite-infile (hisat2.cpp:1689-1691)
     bool mpGiven = false;   // "--mp a,b" becomes MMP=Q,a,b, which switches the cost model back to quality-aware even
                             // under --ignore-quals (aligner_seed_policy.cpp:396-418)
     for (int i = 1; i < argc; i++) {
@@ -38,6 +38,7 @@ int main(int argc, char** argv)
         else if (a == "--no-spliced-alignment") o.no_spliced_alignment = 1;
         else if (a == "--no-temp-splicesite") noTempSpliceSite = true;   // spliced mode with an empty splice-site DB: the only spliced form a (HT2_SPLICED=1) library build honours
         else if (a == "--known-splicesite-infile") knownSs = next(); else if (a == "--novel-splicesite-infile") novelSs = next();
+        else if (a == "--novel-splicesite-outfile") novelOut = next();
         else if (a == "-k") o.khits = atoi(next()); else if (a == "--max-seeds") o.max_seeds = atoi(next());
         else if (a == "--secondary") o.secondary = 1;
         else if (a == "--mp") { two(next(), o.mp_max, o.mp_min); mpGiven = true; } else if (a == "--sp") { two(next(), o.sp_max, o.sp_min); o.sp_min = o.sp_max; /* the reference reads BOTH values from the first number, aligner_seed_policy.cpp:438-441 */ }
@@ -109,7 +110,14 @@ int main(int argc, char** argv)
         for (ht2gpu_handle_t* hh : hs)
             if (ht2gpu_load_splicesites(hh, knownSs, novelSs, &ns) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(hh)); return 1; }
     }
+    if (novelOut)
+        for (ht2gpu_handle_t* hh : hs)
+            if (ht2gpu_collect_splicesites(hh, 1) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(hh)); return 1; }
     if (ht2gpu_run_reads_multi(hs.data(), (int)hs.size(), &in, sink, fo, &st) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(h)); return 1; }
+    if (novelOut) {
+        uint64_t nw = 0;
+        if (ht2gpu_write_novel_splicesites(hs.data(), (int)hs.size(), novelOut, &nw) != HT2GPU_OK) { fprintf(stderr, "Error: %s\n", ht2gpu_last_error(h)); return 1; }
+    }
     for (size_t g = 1; g < hs.size(); g++) ht2gpu_close(hs[g]);
     if (st.n_err_reads)
         fprintf(stderr, "Warning: %llu read(s) exceeded a device-side capacity; their records may differ from hisat2's\n", (unsigned long long)st.n_err_reads);

@@ -602,6 +602,7 @@ struct SamSlot {
     uint32_t* dSamLen; size_t capSamLen;          // bytes of SAM text per unit
     unsigned long long* dBlk; size_t capBlk;      // per-block sums, then exclusive block offsets; [nBlk] = total
     char* dSam; size_t capSam;
+    Ht2SsRec* dColRecs; size_t capCol;            // --novel-splicesite-outfile: junction records of the batch (count in dCounters[6])
     char* hSam; size_t capHSam;                   // pinned
     unsigned long long* hMeta;                    // pinned: [0] total SAM bytes, [1..4] result counters, [5] reads with errors
     // the submitted batch (for a re-run after a pool overflow)
@@ -644,6 +645,9 @@ struct ht2gpu_handle {
     int32_t*       dMinsc;   // --score-min table on the device (Ht2Params::minscTab)
     void*          dSplT;    // spliced builds: Ht2SplTables on the device
     uint8_t*       dSsT;     // the run's splice-site DB on the device (ht2gpu_load_splicesites) or NULL
+    bool           collectSs; // --novel-splicesite-outfile: collect the junctions of printed alignments
+    Ht2NovelSites  novel;     // ... aggregated here (ht2gpu_wait_sam), written by ht2gpu_write_novel_splicesites
+    std::mutex     novelMu;
     std::vector<uint8_t> ssBlob;   // ... and its host copy (host formatter)
     size_t         nWork;
     cudaStream_t   stream;
@@ -798,7 +802,7 @@ static int finishOpen(ht2gpu_handle* h)
 static ht2gpu_handle* newHandle(const ht2gpu_options_t* opt)
 {
     ht2gpu_handle* h = new ht2gpu_handle();
-    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->pool = NULL; h->nWork = 0; h->dMinsc = NULL; h->dSplT = NULL; h->dSsT = NULL;
+    h->img = NULL; h->dBlob = NULL; h->ownBlob = false; h->blobBytes = 0; h->pool = NULL; h->nWork = 0; h->dMinsc = NULL; h->dSplT = NULL; h->dSsT = NULL; h->collectSs = false;
     h->stream = 0;
     h->dStats = NULL;
     memset((void*)h->slots, 0, sizeof(h->slots));
@@ -943,7 +947,7 @@ extern "C" int ht2gpu_close(ht2gpu_handle_t* h)
         cudaStreamSynchronize(S.stream);
         cudaFree(S.dSeq); cudaFree(S.dQual); cudaFree(S.dOffs); cudaFree(S.dSeeds); cudaFree(S.dNames); cudaFree(S.dNameOffs);
         cudaFree(S.dReads); cudaFree(S.dAlns); cudaFree(S.dEdits); cudaFree(S.dPairs); cudaFree(S.dCounters);
-        cudaFree(S.dSamLen); cudaFree(S.dBlk); cudaFree(S.dSam);
+        cudaFree(S.dSamLen); cudaFree(S.dBlk); cudaFree(S.dSam); cudaFree(S.dColRecs);
         if (S.hSam) cudaFreeHost(S.hSam);
         if (S.hMeta) cudaFreeHost(S.hMeta);
         cudaStreamDestroy(S.stream);
@@ -1215,6 +1219,7 @@ static Ht2SamIn samIn(const ht2gpu_handle* h, const SamSlot& S)
     in.n_reads = S.batch.n_reads; in.paired = S.batch.paired;
     in.reads = S.dReads; in.alns = S.dAlns; in.edits = S.dEdits; in.pairs = S.dPairs;
     in.khits = h->P.khits; in.secondary = h->P.secondary; in.mixed = h->P.mixed; in.discord = h->P.discord; in.ssT = h->dSsT;
+    in.colCount = h->collectSs ? S.dCounters + 6 : NULL; in.colRecs = S.dColRecs; in.colCap = (uint32_t)S.capCol;
     return in;
 }
 
@@ -1226,11 +1231,13 @@ static int enqueueKernels(ht2gpu_handle* h, SamSlot& S, bool withAlign)
     const uint32_t nBlk = (units + HT2_SAM_TPB - 1) / HT2_SAM_TPB;
     CK(growBuf(S.dSamLen, S.capSamLen, units));
     CK(growBuf(S.dBlk, S.capBlk, (size_t)nBlk + 2));
+    if (h->collectSs) CK(growBuf(S.dColRecs, S.capCol, (size_t)S.batch.n_reads * 4 + 1024, 1, 1));
     std::lock_guard<std::mutex> lk(h->pool->mu);
     CK(cudaStreamWaitEvent(S.stream, h->pool->evDone, 0));
     if (withAlign) { int rc = launchAlign(h, S, &S.batch, units, S.ev[2]); if (rc) return rc; S.nLaunch++; }
     else CK(cudaEventRecord(S.ev[2], S.stream));
     CK(cudaEventRecord(S.ev[3], S.stream));
+    if (h->collectSs) CK(cudaMemsetAsync(S.dCounters + 6, 0, sizeof(unsigned int), S.stream));
     const Ht2SamIn in = samIn(h, S);
     ht2_sam_kernel<false><<<nBlk, HT2_SAM_TPB, 0, S.stream>>>(in, units, S.dSamLen, S.dBlk, NULL, 0, S.dCounters);
     ht2_sam_scan_kernel<<<1, 1024, 0, S.stream>>>(S.dBlk, nBlk);
@@ -1313,6 +1320,14 @@ extern "C" int ht2gpu_wait_sam(ht2gpu_handle_t* h, int slot, ht2gpu_sam_result_t
     CK(cudaEventRecord(S.ev[5], S.stream));
     CK(cudaStreamSynchronize(S.stream));
     S.hSam[total] = 0;
+    if (h->collectSs) {
+        const unsigned int nrec = ((const unsigned int*)&S.hMeta[1])[6];
+        if (nrec > S.capCol) { h->err = "ht2gpu_wait_sam: more junction records than the batch's buffer holds"; return HT2GPU_ERR_CAPACITY; }
+        std::vector<Ht2SsRec> recs(nrec);
+        if (nrec) CK(cudaMemcpy(recs.data(), S.dColRecs, (size_t)nrec * sizeof(Ht2SsRec), cudaMemcpyDeviceToHost));
+        std::lock_guard<std::mutex> lk(h->novelMu);
+        h->novel.add(recs.data(), recs.size());
+    }
     if (h->dStats) dumpStats(h);
     const unsigned int* c = (const unsigned int*)&S.hMeta[1];
     out->sam = S.hSam; out->sam_len = total;
@@ -1562,6 +1577,7 @@ extern "C" int ht2gpu_load_splicesites(ht2gpu_handle_t* h, const char* known_pat
     std::vector<Ht2SsFile> files;
     if (known_path && *known_path) files.push_back({known_path, true});
     if (novel_path && *novel_path) files.push_back({novel_path, false});
+    if (h->collectSs && files.size()) { h->err = "ht2gpu: a splice-site DB cannot be loaded while novel splice sites are collected"; return HT2GPU_ERR_UNSUPPORTED; }
     if (h->dSsT) { cudaFree(h->dSsT); h->dSsT = NULL; }
     h->ssBlob.clear();
     if (n_sites) *n_sites = 0;
@@ -1578,6 +1594,30 @@ extern "C" int ht2gpu_load_splicesites(ht2gpu_handle_t* h, const char* known_pat
     (void)known_path; (void)novel_path; (void)n_sites;
     h->err = "ht2gpu: built without spliced alignment"; return HT2GPU_ERR_UNSUPPORTED;
 #endif
+}
+
+// --novel-splicesite-outfile (hisat2.cpp:4092, aln_sink.h:1571-1580, splice_site.cpp:190-350, 565-651): collect the
+// junctions of every printed alignment while batches run through ht2gpu_*_sam / ht2gpu_run_reads, then write the
+// filtered site list.  Deterministic only with an empty DB (a site learned from one read would otherwise steer later
+// reads in the reference), so collecting is refused while a DB is loaded.
+extern "C" int ht2gpu_collect_splicesites(ht2gpu_handle_t* h, int enable)
+{
+    if (!h) return HT2GPU_ERR_ARG;
+    if (enable && h->dSsT) { h->err = "ht2gpu: --novel-splicesite-outfile together with a loaded splice-site DB is order dependent in the reference; not supported"; return HT2GPU_ERR_UNSUPPORTED; }
+    if (enable && h->P.noSplicedAlignment) { h->err = "ht2gpu: novel splice sites need spliced alignment"; return HT2GPU_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lk(h->novelMu);
+    if (enable && !h->collectSs) h->novel.sites.clear();
+    h->collectSs = enable != 0;
+    return HT2GPU_OK;
+}
+extern "C" int ht2gpu_write_novel_splicesites(ht2gpu_handle_t** hs, int n, const char* path, uint64_t* n_written)
+{
+    if (!hs || n < 1 || !hs[0] || !path) return HT2GPU_ERR_ARG;
+    Ht2NovelSites all;
+    for (int i = 0; i < n; i++) { if (!hs[i]) return HT2GPU_ERR_ARG; std::lock_guard<std::mutex> lk(hs[i]->novelMu); all.merge(hs[i]->novel); }
+    std::string err;
+    if (!all.write(*hs[0]->img, path, n_written, err)) { hs[0]->err = err; return HT2GPU_ERR_INDEX; }
+    return HT2GPU_OK;
 }
 
 extern "C" int ht2gpu_format_sam(ht2gpu_handle_t* h, const ht2gpu_read_batch_t* b, const char* names,

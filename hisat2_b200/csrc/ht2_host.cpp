@@ -279,7 +279,7 @@ void ht2_sam_header(std::string& o, const Ht2Image& img)
 // source the device kernel runs -- on host threads over contiguous unit ranges: a counting pass, a prefix
 // over the ranges, a writing pass straight into the output (records in read order = --reorder).
 bool ht2_format_batch(const Ht2Image& img, const Ht2Params& P, const ht2gpu_read_batch_t* b, const char* names,
-                      const ht2gpu_result_batch_t* res, char** out, size_t* out_len, unsigned nth, const uint8_t* ssT)
+                      const ht2gpu_result_batch_t* res, char** out, size_t* out_len, unsigned nth, const uint8_t* ssT, uint32_t* colCount, Ht2SsRec* colRecs, uint32_t colCap)
 {
     const uint32_t units = b->paired ? b->n_reads / 2 : b->n_reads;
     std::vector<uint32_t> nameOffs((size_t)b->n_reads + 1);
@@ -293,7 +293,7 @@ bool ht2_format_batch(const Ht2Image& img, const Ht2Params& P, const ht2gpu_read
     in.seq = b->seq; in.qual = b->qual; in.offs = b->offs; in.names = names; in.nameOffs = nameOffs.data();
     in.n_reads = b->n_reads; in.paired = b->paired;
     in.reads = res->reads; in.alns = res->alns; in.edits = res->edits; in.pairs = res->pairs;
-    in.khits = P.khits; in.secondary = P.secondary; in.mixed = P.mixed; in.discord = P.discord; in.ssT = ssT;
+    in.khits = P.khits; in.secondary = P.secondary; in.mixed = P.mixed; in.discord = P.discord; in.ssT = ssT; in.colCount = colCount; in.colRecs = colRecs; in.colCap = colCap;
     Ht2SamFmt F; F.bind(&in);
     if (nth > 64) nth = 64;
     if (nth < 1 || units < 4096) nth = 1;

@@ -48,6 +48,7 @@ bool ht2_read_reads(const char* path, std::vector<Ht2HostRead>& out, int mate, s
 void ht2_sam_header(std::string& o, const Ht2Image& img);
 // ht2gpu_format_sam's body: host-only, shared with the test build
 bool ht2_format_batch(const Ht2Image& img, const Ht2Params& P, const ht2gpu_read_batch_t* b, const char* names,
-                      const ht2gpu_result_batch_t* res, char** out, size_t* out_len, unsigned nthreads, const uint8_t* ssT = NULL);
+                      const ht2gpu_result_batch_t* res, char** out, size_t* out_len, unsigned nthreads, const uint8_t* ssT = NULL,
+                      uint32_t* colCount = NULL, struct Ht2SsRec* colRecs = NULL, uint32_t colCap = 0);
 
 #endif

@@ -570,3 +570,68 @@ bool ht2_ssdb_build(const Ht2Image& img, const std::vector<Ht2SsFile>& files, st
     refOff[nRefs] = at;
     return true;
 }
+
+
+void Ht2NovelSites::add(const Ht2SsRec* recs, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        const Ht2SsRec& r = recs[i];
+        const uint32_t dir = r.dirEd & 0xffu, ed = r.dirEd >> 8;
+        auto it = sites.find(std::make_tuple(r.ref, r.left, r.right, dir));
+        if (it == sites.end()) sites[std::make_tuple(r.ref, r.left, r.right, dir)] = std::make_pair(1u, ed);
+        else { it->second.first += 1; if (ed < it->second.second) it->second.second = ed; }
+    }
+}
+void Ht2NovelSites::merge(const Ht2NovelSites& o)
+{
+    for (const auto& kv : o.sites) {
+        auto it = sites.find(kv.first);
+        if (it == sites.end()) sites[kv.first] = kv.second;
+        else { it->second.first += kv.second.first; if (kv.second.second < it->second.second) it->second.second = kv.second.second; }
+    }
+}
+bool Ht2NovelSites::write(const Ht2Image& img, const char* path, uint64_t* nWritten, std::string& err) const
+{
+    FILE* f = fopen(path, "wb");
+    if (!f) { err = std::string("ht2: cannot write ") + path; return false; }
+    // calculate_splicesite_read_dist (splice_site.cpp:528-563): smallest read count whose cumulative share of the sites exceeds 0.7
+    int64_t dist[100]; for (int i = 0; i < 100; i++) dist[i] = 0;
+    for (const auto& kv : sites) { const uint32_t n = kv.second.first; if (n < 100) dist[n] += 1; else dist[99] += 1; }
+    for (int i = 1; i < 100; i++) dist[i] += dist[i - 1];
+    uint32_t cutoff = 0;
+    for (int i = 0; i < 100; i++) { const float cmf = float(dist[i]) / dist[99]; if (cmf > 0.7) { cutoff = (uint32_t)i; break; } }
+    const uint32_t cutoff2 = (uint32_t)(sites.size() / 100000);
+    struct S { uint32_t ref, left, right, dir, numreads; };
+    std::vector<S> list;
+    uint64_t nw = 0;
+    auto name = [&](uint32_t ref) { const char* n = img.refName(ref); size_t i = 0; while (n[i] && !isspace((unsigned char)n[i])) i++; return std::string(n, i); };
+    auto impl = [&](const S* ss) {   // print_impl (splice_site.cpp:605-651)
+        size_t i = 0;
+        while (i < list.size()) {
+            const S tmp = list[i];
+            bool do_print = true;
+            if (ss != NULL && tmp.ref == ss->ref && ss->left < tmp.left + 10) {
+                do_print = false;
+                const int d = ((int)ss->left - (int)tmp.left) - ((int)ss->right - (int)tmp.right);
+                if ((d < 0 ? -d : d) <= 10) {
+                    if (tmp.numreads < ss->numreads) { list.erase(list.begin() + i); list.push_back(*ss); }
+                    return;
+                }
+            }
+            if (!do_print) { i++; continue; }
+            const char c = (tmp.dir == HT2_SPL_FW || tmp.dir == HT2_SPL_SEMI_FW) ? '+' : ((tmp.dir == HT2_SPL_RC || tmp.dir == HT2_SPL_SEMI_RC) ? '-' : '.');
+            fprintf(f, "%s\t%u\t%u\t%c\n", name(tmp.ref).c_str(), tmp.left, tmp.right, c);
+            nw++;
+            list.erase(list.begin() + i);
+        }
+        if (ss != NULL) list.push_back(*ss);
+    };
+    for (const auto& kv : sites) {   // std::map order = (ref, left, right, dir): the in-order walk of every _fwIndex in turn
+        const S ss = {std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first), std::get<3>(kv.first), kv.second.first};
+        if (ss.numreads >= cutoff || (kv.second.second == 0 && ss.numreads >= cutoff2)) impl(&ss);
+    }
+    impl(NULL);
+    fclose(f);
+    if (nWritten) *nWritten = nw;
+    return true;
+}

@@ -40,6 +40,9 @@ struct Ht2SamIn {
     const uint16_t*             pairs;
     uint32_t khits, secondary, mixed, discord;
     const uint8_t*  ssT;         // the run's splice-site DB (ht2_ssdb.h) or NULL: template-length adjustment of concordant pairs
+    uint32_t*       colCount;    // --novel-splicesite-outfile: junctions of the printed alignments (write pass only), or NULL
+    Ht2SsRec*       colRecs;
+    uint32_t        colCap;
 };
 
 template <bool WRITE>
@@ -356,6 +359,73 @@ struct Ht2SamFmt {
         else if (!rd.scfilt) o.s("\tYF:Z:SC");
     }
 
+    // SpliceSiteDB::addSpliceSite (splice_site.cpp:190-350) for one printed alignment: every junction whose anchors
+    // are long enough (15 bases + 2 per mismatch / gap on its side, + 6 without a canonical motif) is recorded with the
+    // alignment's edit distance.  Alignments with soft-trimmed ends are skipped.  (The threshold of a junction that is
+    // followed by another one uses the NEXT junction's direction and the mismatches seen so far -- as the reference.)
+    HT2_HD void collectSites(const ht2gpu_aln_t* rs, uint32_t rdlen) const {
+        if (rs->trim5 + rs->trim3 > 0) return;
+        const ht2gpu_edit_t* ed = in->edits + rs->edit_off;
+        const uint32_t ned = rs->n_edits;
+        uint32_t editdist = 0; bool spliced = false;
+        for (uint32_t k = 0; k < ned; k++) {
+            if (ed[k].type == HT2_EDIT_SPL) spliced = true;
+            else if (ed[k].type == HT2_EDIT_MM || ed[k].type == HT2_EDIT_READ_GAP || ed[k].type == HT2_EDIT_REF_GAP) editdist++;
+        }
+        if (!spliced) return;
+        const bool fw = rs->fw != 0;
+        // edit k in left-to-right order and its position there (Edit::invertPoss for the reverse strand)
+        auto at = [&](uint32_t k) -> const ht2gpu_edit_t& { return fw ? ed[k] : ed[ned - 1 - k]; };
+        auto posOf = [&](uint32_t k) -> uint32_t {
+            const ht2gpu_edit_t& e = at(k);
+            if (fw) return e.pos;
+            return (e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_SPL) ? rdlen - e.pos : rdlen - e.pos - 1;
+        };
+        auto isEd = [&](const ht2gpu_edit_t& e) { return e.type == HT2_EDIT_MM || e.type == HT2_EDIT_READ_GAP || e.type == HT2_EDIT_REF_GAP; };
+        auto splLen = [&](const ht2gpu_edit_t& e) { return (uint32_t)e.chr | ((uint32_t)e.qchr << 8) | ((uint32_t)(e.pad & 15) << 16); };
+        auto splDir = [&](const ht2gpu_edit_t& e) { return (uint32_t)(e.pad >> 4) & 7u; };
+        auto push = [&](uint32_t l, uint32_t r, uint32_t d) {
+#ifdef __CUDA_ARCH__
+            const uint32_t idx = atomicAdd(in->colCount, 1u);
+#else
+            const uint32_t idx = __sync_fetch_and_add(in->colCount, 1u);
+#endif
+            if (idx < in->colCap) { Ht2SsRec rec; rec.ref = rs->tidx; rec.left = l; rec.right = r; rec.dirEd = d | (editdist << 8); in->colRecs[idx] = rec; }
+        };
+        const uint32_t minAnchorLen = 15;
+        uint32_t refoff = rs->toff, leftAnchor = 0, rightAnchor = 0, eidx = 0, last = 0, mm = 0;
+        uint32_t sl = 0, sr = 0, sd = 0; bool inited = false;
+        for (uint32_t i = 0; i < rdlen; i++, refoff++) {
+            while (eidx < ned && posOf(eidx) == i) {
+                const ht2gpu_edit_t& e = at(eidx);
+                if (e.type == HT2_EDIT_READ_GAP) refoff++;
+                else if (e.type == HT2_EDIT_REF_GAP) refoff--;
+                if (isEd(e)) mm++;
+                if (e.type == HT2_EDIT_SPL) {
+                    if (inited) {
+                        rightAnchor = posOf(eidx) - posOf(last);
+                        const uint32_t unk = splDir(e) == HT2_SPL_UNKNOWN ? 6u : 0u;
+                        uint32_t mm2 = 0;
+                        for (uint32_t j = eidx + 1; j < ned; j++) if (isEd(at(j))) mm2++;
+                        if (leftAnchor >= minAnchorLen + mm * 2 + unk && rightAnchor >= minAnchorLen + mm2 * 2 + unk) push(sl, sr, sd);
+                        leftAnchor = rightAnchor; rightAnchor = 0;
+                    } else leftAnchor = posOf(eidx);
+                    sl = refoff - 1; sr = refoff + splLen(e); sd = splDir(e); inited = true;
+                    refoff += splLen(e);
+                    last = eidx;
+                }
+                eidx++;
+            }
+        }
+        if (inited) {
+            rightAnchor = rdlen - posOf(last);
+            const uint32_t unk = splDir(at(last)) == HT2_SPL_UNKNOWN ? 6u : 0u;
+            uint32_t mm2 = 0;
+            for (uint32_t j = last + 1; j < ned; j++) if (isEd(at(j))) mm2++;
+            if (leftAnchor >= minAnchorLen + mm * 2 + unk && rightAnchor >= minAnchorLen + mm2 * 2 + unk) push(sl, sr, sd);
+        }
+    }
+
     // AlnSinkSam::appendMate (aln_sink.h:3024-3250)
     template <bool W>
     HT2_NI void appendMate(Ht2SamOut<W>& o, const Ht2SamRead& rd, uint32_t ordlen, const ht2gpu_aln_t* rs, const ht2gpu_aln_t* rso,
@@ -385,6 +455,7 @@ struct Ht2SamFmt {
             o.c('\n');
             return;
         }
+        if (W && in->colCount != NULL) collectSites(rs, rd.len);   // AlnSinkSam::append (aln_sink.h:1571, 1579)
         const ht2gpu_edit_t* ed = in->edits + rs->edit_off;
         const uint32_t ned = rs->n_edits;
         // Gapless alignments (mismatches only; the vast majority): CIGAR and MD:Z follow from the edit positions

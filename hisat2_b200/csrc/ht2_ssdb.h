@@ -20,6 +20,9 @@ enum { HT2_SPL_UNKNOWN = 1, HT2_SPL_FW, HT2_SPL_RC, HT2_SPL_SEMI_FW, HT2_SPL_SEM
 
 struct Ht2SsSite { uint32_t left, right; uint32_t dir; uint32_t known; };   // left = last base of the upstream exon, right = first base of the downstream exon (0-based)
 struct Ht2SsHeader { uint32_t magic, nRefs, nSites, pad; };
+// One junction of one printed alignment, as SpliceSiteDB::addSpliceSite would record it (--novel-splicesite-outfile):
+// appended by the SAM write pass, aggregated on the host (ht2_index.h Ht2NovelSites)
+struct Ht2SsRec { uint32_t ref, left, right; uint32_t dirEd; };   // dirEd = direction | edit distance of the alignment << 8
 
 struct Ht2SsView {
     const Ht2SsHeader* h;

@@ -347,6 +347,16 @@ uint32_t ht2gpu_read_seed(const uint8_t* seq, const uint8_t* qual, uint32_t len,
  * modelled: the reference's own output depends on thread timing there. */
 int ht2gpu_load_splicesites(ht2gpu_handle_t* h, const char* known_path, const char* novel_path, uint32_t* n_sites);
 
+/* --novel-splicesite-outfile (hisat2.cpp:4092; aln_sink.h:1571-1580; SpliceSiteDB::addSpliceSite / print,
+ * splice_site.cpp:190-350, 565-651): while enabled, the SAM kernel records the junctions of every printed alignment
+ * (anchors >= 15 bases + 2 per mismatch, + 6 without a canonical motif; soft-trimmed alignments skipped) and
+ * ht2gpu_wait_sam aggregates them per handle; ht2gpu_write_novel_splicesites merges the handles of a run and writes
+ * "<chr> <left> <right> <+|-|.>" with the reference's read-count cutoffs and near-duplicate suppression -- the
+ * first pass of the two-pass use (second pass: ht2gpu_load_splicesites(h, NULL, file)).  Refused while a DB is
+ * loaded: the reference would let such sites steer later reads, i.e. depend on read order. */
+int ht2gpu_collect_splicesites(ht2gpu_handle_t* h, int enable);
+int ht2gpu_write_novel_splicesites(ht2gpu_handle_t** hs, int n, const char* path, uint64_t* n_written);
+
 /* Diagnostics: the warp-wide fill of the --bowtie2-dp score planes against the single-lane fill on n random
  * problems (aligner_swsse_ee_u8.cpp:791-1163 restated twice, ht2_sw.h).  out[0] = mismatching cells / scores
  * (must be 0), out[1] = problems run, out[2] = cells compared per plane, out[3] = problems with a valid best. */

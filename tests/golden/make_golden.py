@@ -290,6 +290,11 @@ def known_splice():
         open(os.path.join(G, out), "wb").write(data)
         print(out, data.count(b"\n"), "records,", sum(1 for l in data.splitlines() if not l.startswith(b"@") and b"N" in l.split(b"\t")[5]), "spliced")
     os.remove(os.path.join(G, "ss.tmp"))
+    # --novel-splicesite-outfile (first pass of the two-pass use; no DB loaded, so the SAM is that of --no-temp-splicesite)
+    for args, out in ((["-1", "tiny_ss_rna_1.fa", "-2", "tiny_ss_rna_2.fa"], "tiny_ss_rna_pe_novel_out.txt"), (["-U", "tiny_rna.fa"], "tiny_rna_novel_out.txt")):
+        subprocess.run([al, "-f", "-x", "tiny", "--no-temp-splicesite", "--novel-splicesite-outfile", out] + args + ["-S", "/dev/null"], check=True, cwd=G,
+                       stderr=subprocess.DEVNULL)
+        print(out, sum(1 for _ in open(os.path.join(G, out))), "sites")
 
 
 def options():

@@ -188,7 +188,16 @@ static int alignAll(Ht2Image* img, Ht2Params& P, std::vector<Ht2HostRead>& reads
         char* txt = NULL; size_t len = 0;
         const unsigned nth = getenv("HT2_THREADS") ? (unsigned)atoi(getenv("HT2_THREADS")) : 1;
         auto t0 = std::chrono::steady_clock::now();
-        if (!ht2_format_batch(*img, P, &rb, names.c_str(), &res, &txt, &len, nth, HT2_SS_BLOB)) { fprintf(stderr, "ht2_format_batch failed\n"); return 1; }
+        // HT2_SS_OUT=<file>: --novel-splicesite-outfile through the formatter's junction collection
+        const char* ssOut = getenv("HT2_SS_OUT");
+        uint32_t colCount = 0; std::vector<Ht2SsRec> colRecs(ssOut ? rb.n_reads * 4 + 16 : 0);
+        if (!ht2_format_batch(*img, P, &rb, names.c_str(), &res, &txt, &len, nth, HT2_SS_BLOB, ssOut ? &colCount : NULL, colRecs.data(), (uint32_t)colRecs.size())) { fprintf(stderr, "ht2_format_batch failed\n"); return 1; }
+        if (ssOut) {
+            Ht2NovelSites ns; ns.add(colRecs.data(), colCount < colRecs.size() ? colCount : colRecs.size());
+            uint64_t nw = 0; std::string e2;
+            if (!ns.write(*img, ssOut, &nw, e2)) { fprintf(stderr, "%s\n", e2.c_str()); return 1; }
+            fprintf(stderr, "novel splice sites: %u junction records, %zu sites, %llu written\n", colCount, ns.sites.size(), (unsigned long long)nw);
+        }
         finishNs += (std::chrono::steady_clock::now() - t0).count();
         sam.append(txt, len); free(txt);
     }

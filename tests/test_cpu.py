@@ -184,6 +184,12 @@ def test_populated_splice_site_db_host_build_matches_golden_reference_sam(hostsi
     assert sum(1 for x, y in zip(a, b) if x != y) > 200
     gold = open(os.path.join(GOLDEN, "tiny_ss_rna_se.sam")).read().splitlines()
     assert sum(1 for l in gold if not l.startswith("@") and "N" in l.split("\t")[5]) >= 350
+    # --novel-splicesite-outfile: the junctions of the printed alignments, collected by the formatter and filtered like
+    # SpliceSiteDB::print (read-count cutoffs, near-duplicate suppression) == the reference's file
+    for args, gold in ((["tiny_ss_rna_1.fa", "tiny_ss_rna_2.fa"], "tiny_ss_rna_pe_novel_out.txt"), (["tiny_rna.fa"], "tiny_rna_novel_out.txt")):
+        out, ss = str(tmp_path / "o3.sam"), str(tmp_path / "novel.txt")
+        subprocess.run([hostsim_spliced_bin, "tiny", args[0], out] + args[1:], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL, env=dict(env, HT2_SS_OUT=ss))
+        assert open(ss).read() == open(os.path.join(GOLDEN, gold)).read(), gold
 
 
 def test_striped_dp_fill_and_backtrace_against_plain_scalar_dp(hostsim_bin):

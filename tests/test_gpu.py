@@ -414,6 +414,22 @@ def test_populated_splice_site_db_matches_reference(h2, tmp_path):
         r = subprocess.run([cli, "--known-splicesite-infile", "/nonexistent/ss.txt", "-x", "tiny", "-f", "-U", "tiny_ss_rna.fa", "-S", out], cwd=GOLDEN,
                            stderr=subprocess.PIPE)
         assert r.returncode != 0 and b"cannot open" in r.stderr
+    # --novel-splicesite-outfile (first pass of the two-pass use): junctions collected by the SAM kernel == the reference's file
+    idx = h2.Index(g("tiny"), no_spliced_alignment=0)
+    idx.collect_splicesites(True)
+    sam, st = idx.run_reads(path1=g("tiny_ss_rna_1.fa"), path2=g("tiny_ss_rna_2.fa"), fastq=False, batch_reads=128)   # several batches
+    novel = str(tmp_path / "novel.txt")
+    assert idx.write_novel_splicesites(novel) == 89
+    assert open(novel).read() == open(g("tiny_ss_rna_pe_novel_out.txt")).read()
+    with pytest.raises(h2.Ht2GpuError):
+        idx.load_splicesites(g("tiny_ss_rna_ss.txt"))            # a DB while collecting: order dependent in the reference, refused
+    idx.close()
+    if os.path.exists(cli):
+        out = str(tmp_path / "cli2.sam")
+        subprocess.run([cli, "--no-temp-splicesite", "--novel-splicesite-outfile", novel, "-x", "tiny", "-f", "-U", "tiny_rna.fa", "-S", out], cwd=GOLDEN,
+                       check=True, stderr=subprocess.DEVNULL)
+        assert open(novel).read() == open(g("tiny_rna_novel_out.txt")).read()
+        assert sam_lines(open(out, "rb").read()) == sam_lines(open(g("tiny_spliced_rna.sam"), "rb").read())
     base = os.path.join(DATA, "22_20-21M")
     if os.path.exists(REFBIN) and os.path.exists(base + ".1.ht2") and os.path.exists(base + ".fa"):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -433,6 +449,24 @@ def test_populated_splice_site_db_matches_reference(h2, tmp_path):
             want = sam_lines(open(out, "rb").read())
             assert sam_lines(sam) == want
             assert sum(1 for l in want if not l.startswith(b"@") and b"N" in l.split(b"\t")[5]) > (3000 if paired else 8000)
+        idx.close()
+        # two-pass: pass one writes the novel sites (== the reference's outfile), pass two uses them (== the reference again)
+        idx = h2.Index(base, no_spliced_alignment=0)
+        idx.collect_splicesites(True)
+        idx.run_reads(path1=pre + "_1.fa", path2=pre + "_2.fa", fastq=False, collect=False)
+        novel, refnovel = str(tmp_path / "n.txt"), str(tmp_path / "rn.txt")
+        assert idx.write_novel_splicesites(novel) > 2000
+        subprocess.run([REFBIN, "--no-temp-splicesite", "--novel-splicesite-outfile", refnovel, "-f", "-x", base, "-1", pre + "_1.fa", "-2", pre + "_2.fa",
+                        "-S", "/dev/null", "-p", "4"], check=True, stderr=subprocess.DEVNULL)
+        assert open(novel).read() == open(refnovel).read()
+        idx.collect_splicesites(False)
+        assert idx.load_splicesites(None, novel) > 2000
+        batch = h2.ReadBatch.from_fasta(pre + "_1.fa", path2=pre + "_2.fa")
+        sam, _ = gpu_sam(idx, batch)
+        out = str(tmp_path / "ref2.sam")
+        subprocess.run([REFBIN, "--no-temp-splicesite", "--novel-splicesite-infile", refnovel, "-f", "-x", base, "-1", pre + "_1.fa", "-2", pre + "_2.fa",
+                        "-S", out, "-p", str(min(16, os.cpu_count() or 1)), "--reorder"], check=True, stderr=subprocess.DEVNULL)
+        assert sam_lines(sam) == sam_lines(open(out, "rb").read())
         idx.close()
 
 
