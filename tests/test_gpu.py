@@ -530,6 +530,35 @@ def test_edge_cases(h2, tiny):
     assert st["n_err_reads"] == 1
 
 
+def test_slot_buffers_have_their_own_capacities(h2, tmp_path):
+    """a handle that first sees a big FASTA batch (no qualities), then a small FASTQ batch, then a
+    medium FASTQ batch must not write the third batch's qualities past the buffer sized for the second: every slot
+    buffer tracks its own capacity.  The SAM of each batch must equal the golden output whatever came before (a
+    quality overflow corrupts neighbouring buffers, i.e. the records of the batch)."""
+    g = lambda n: os.path.join(GOLDEN, n)
+    idx = h2.Index(g("tiny"))
+    big = h2.ReadBatch.from_fasta(g("tiny_se.fa"))                      # 700 reads, qual == NULL
+    fq = h2.ReadBatch.from_fastq(g("tiny_se.fq"))
+    gold_fq = sam_lines(open(g("tiny_se_fq.sam"), "rb").read())
+    nsq = sum(1 for l in gold_fq if l.startswith(b"@"))
+    def sub(b, lo, hi):
+        o = b.offs
+        return h2.ReadBatch(b.seq[int(o[lo]):int(o[hi])], (o[lo:hi + 1] - o[lo]).astype(np.uint64), b.seeds[lo:hi], b.names[lo:hi],
+                            qual=None if b.qual is None else b.qual[int(o[lo]):int(o[hi])])
+    body = lambda sam: [l for l in sam_lines(sam) if not l.startswith(b"@")]
+    want = [l for l in gold_fq[nsq:]]
+    per_read = {}
+    for l in want:
+        per_read.setdefault(l.split(b"\t")[0], []).append(l)
+    expect = lambda b: [l for n in b.names for l in per_read[n.split(b" ")[0]]]
+    assert body(idx.align_sam(big)) == body(open(g("tiny_se.sam"), "rb").read())
+    small, medium = sub(fq, 0, 40), sub(fq, 40, 520)
+    assert body(idx.align_sam(small)) == expect(small)
+    assert body(idx.align_sam(medium)) == expect(medium)
+    assert body(idx.align_sam(fq)) == want
+    idx.close()
+
+
 @pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built on this box")
 @pytest.mark.parametrize("name", ["reads", "hard20k", "sim200k", "len36", "len150", "len250", "len500", "len1000"])
 def test_chr22_matches_reference_binary_run_here(h2, chr22, name, tmp_path):
