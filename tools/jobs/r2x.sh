@@ -1,5 +1,6 @@
 set -x
-O=gpurun_out/r2x; mkdir -p $O
+O=gpurun_out/r2z; mkdir -p $O
+timeout 2400 python -m pytest tests/test_gpu.py -m gpu -x -q > $O/pytest.log 2>&1; tail -4 $O/pytest.log
 # profile of the final kernel on a bench-shaped launch (2 M pairs = 4 M reads)
 cd /tmp && rm -rf cubx && mkdir cubx && cd cubx && cuobjdump -xelf all $GRAFT_REPO_ROOT/hisat2_b200/libht2gpu.so > /dev/null 2>&1 && nvdisasm -c ht2_gpu.sm_100a.cubin > all.sass 2>/dev/null; cd $GRAFT_REPO_ROOT
 ncu --set full --clock-control none --import-source on -k regex:ht2_align_pool_kernel -c 1 -o /tmp/pool_pe python tools/prof_run.py synthpe:2000000 1 no_spliced_alignment=1 > $O/ncu_pool_pe.log 2>&1
