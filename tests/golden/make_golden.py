@@ -295,6 +295,12 @@ def known_splice():
         subprocess.run([al, "-f", "-x", "tiny", "--no-temp-splicesite", "--novel-splicesite-outfile", out] + args + ["-S", "/dev/null"], check=True, cwd=G,
                        stderr=subprocess.DEVNULL)
         print(out, sum(1 for _ in open(os.path.join(G, out))), "sites")
+    # read-count cutoffs of SpliceSiteDB::print: tiny_rna.fa plus a renamed copy of its first 200 reads
+    lines = open(os.path.join(G, "tiny_rna.fa")).read().splitlines(True)
+    open(os.path.join(G, "dup.tmp.fa"), "w").write("".join(lines) + "".join(l.replace(">t", ">dup", 1) if l.startswith(">") else l for l in lines[:400]))
+    subprocess.run([al, "-f", "-x", "tiny", "--no-temp-splicesite", "--novel-splicesite-outfile", "tiny_rna_dup_novel_out.txt", "-U", "dup.tmp.fa", "-S", "/dev/null"],
+                   check=True, cwd=G, stderr=subprocess.DEVNULL)
+    os.remove(os.path.join(G, "dup.tmp.fa"))
 
 
 def options():

@@ -190,6 +190,20 @@ def test_populated_splice_site_db_host_build_matches_golden_reference_sam(hostsi
         out, ss = str(tmp_path / "o3.sam"), str(tmp_path / "novel.txt")
         subprocess.run([hostsim_spliced_bin, "tiny", args[0], out] + args[1:], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL, env=dict(env, HT2_SS_OUT=ss))
         assert open(ss).read() == open(os.path.join(GOLDEN, gold)).read(), gold
+    # read-count cutoffs: tiny_rna.fa plus a renamed copy of its first 200 reads -> 70 % of the sites have one read, the
+    # cutoff becomes 2 and single-read sites survive only with edit distance 0 (275 sites, 223 written by the reference)
+    dup = str(tmp_path / "dup.fa")
+    lines = open(os.path.join(GOLDEN, "tiny_rna.fa")).read().splitlines(True)
+    open(dup, "w").write("".join(lines) + "".join(l.replace(">t", ">dup", 1) if l.startswith(">") else l for l in lines[:400]))
+    ss = str(tmp_path / "novel_dup.txt")
+    subprocess.run([hostsim_spliced_bin, "tiny", dup, str(tmp_path / "o4.sam")], cwd=GOLDEN, check=True, stderr=subprocess.DEVNULL, env=dict(env, HT2_SS_OUT=ss))
+    got = open(ss).read()
+    assert got == open(os.path.join(GOLDEN, "tiny_rna_dup_novel_out.txt")).read() and got.count("\n") == 223
+    # a malformed site file is an error, not a silent skip
+    bad = str(tmp_path / "bad_ss.txt")
+    open(bad, "w").write("chrA\t100\n")
+    r = subprocess.run([hostsim_spliced_bin, "tiny", "tiny_rna.fa", str(tmp_path / "o5.sam")], cwd=GOLDEN, stderr=subprocess.PIPE, env=dict(env, HT2_SS=bad))
+    assert r.returncode != 0 and b"truncated splice-site record" in r.stderr
 
 
 def test_striped_dp_fill_and_backtrace_against_plain_scalar_dp(hostsim_bin):
