@@ -506,6 +506,7 @@ class Index(object):
         n = C.c_uint32(0)
         self._check(self._lib.ht2gpu_load_splicesites(self._h, known.encode() if known else None, novel.encode() if novel else None, C.byref(n)),
                     "ht2gpu_load_splicesites")
+        self._ss = (known, novel) if (known or novel) else None      # replicas made by peer() afterwards load the same files
         return int(n.value)
 
     def collect_splicesites(self, enable=True):
@@ -535,6 +536,8 @@ class Index(object):
             msg = self._lib.ht2gpu_last_error(other._h).decode() if other._h else "open failed"
             other.close()
             raise Ht2GpuError("ht2gpu_open_peer rc=%d: %s" % (rc, msg))
+        if getattr(self, "_ss", None):
+            other.load_splicesites(*self._ss)
         return other
 
     def run_reads(self, path1=None, path2=None, data1=None, data2=None, fastq=False, collect=True, peers=(), **kw):
